@@ -1,0 +1,311 @@
+"""Synthetic scenes and the NVM reader for the Line3D++ matching path.
+
+The reference never ships runnable inputs for this path (no images, testdata4/vsfm_result.nvm is
+empty), so scenes are synthesised: world 3-D segments are projected into pinhole cameras, noised,
+clipped, padded with clutter up to exactly N segments per view and sorted by length (the order
+`Line3D::detectLineSegments` produces, reference src/line3D.cc:342-384).  Everything is numpy on
+the host; nothing here touches the GPU or the oracle.
+"""
+from __future__ import annotations
+
+import dataclasses
+import math
+from typing import Dict, List, Optional
+
+import numpy as np
+
+BASE_SEED = 20261018
+
+
+@dataclasses.dataclass
+class SceneView:
+    cam_id: int
+    K: np.ndarray          # (3,3) float64
+    R: np.ndarray          # (3,3) float64   x_cam = R X + t
+    t: np.ndarray          # (3,)  float64
+    width: int
+    height: int
+    median_depth: float
+    segs: np.ndarray       # (N,4) float32  x1 y1 x2 y2, sorted by length descending
+    neighbors: List[int]   # explicit visual neighbours (camera ids)
+    worldpoints: Optional[List[int]] = None  # world-point ids (NVM input)
+
+
+@dataclasses.dataclass
+class Scene:
+    name: str
+    views: List[SceneView]
+    max_image_width: int
+    params: Dict[str, float]
+    neighbors_by_worldpoints: bool = False
+
+    @property
+    def num_views(self) -> int:
+        return len(self.views)
+
+    def total_segments(self) -> int:
+        return int(sum(v.segs.shape[0] for v in self.views))
+
+
+DEFAULT_PARAMS = dict(sigma_p=5.0, sigma_a=10.0, num_neighbors=10, epipolar_overlap=0.25, knn=10,
+                      const_reg_depth=-1.0)  # reference include/L3DPPing.h:77-91
+
+
+def look_at(center: np.ndarray, target: np.ndarray, up=(0.0, 0.0, 1.0)) -> np.ndarray:
+    """World->camera rotation with +z forward, +x right, +y down."""
+    f = target - center
+    f = f / np.linalg.norm(f)
+    upv = np.asarray(up, dtype=np.float64)
+    r = np.cross(f, upv)
+    if np.linalg.norm(r) < 1e-9:
+        r = np.cross(f, np.array([0.0, 1.0, 0.0]))
+    r = r / np.linalg.norm(r)
+    d = np.cross(f, r)
+    return np.stack([r, d, f], axis=0)
+
+
+def rotation_from_q(qw, qx, qy, qz) -> np.ndarray:
+    """Quaternion -> rotation, same convention as reference src/line3D.cc:3221-3245."""
+    n = qw * qw + qx * qx + qy * qy + qz * qz
+    s = 0.0 if abs(n) < 1e-12 else 2.0 / n
+    wx, wy, wz = s * qw * qx, s * qw * qy, s * qw * qz
+    xx, xy, xz = s * qx * qx, s * qx * qy, s * qx * qz
+    yy, yz, zz = s * qy * qy, s * qy * qz, s * qz * qz
+    return np.array([[1.0 - (yy + zz), xy - wz, xz + wy],
+                     [xy + wz, 1.0 - (xx + zz), yz - wx],
+                     [xz - wy, yz + wx, 1.0 - (xx + yy)]], dtype=np.float64)
+
+
+def _clip_segment_to_image(p, q, w, h):
+    """Liang-Barsky clip of a 2-D segment to [0,w]x[0,h]; returns None if outside."""
+    d = q - p
+    t0, t1 = 0.0, 1.0
+    for pk, qk in ((-d[0], p[0]), (d[0], w - p[0]), (-d[1], p[1]), (d[1], h - p[1])):
+        if abs(pk) < 1e-12:
+            if qk < 0:
+                return None
+        else:
+            r = qk / pk
+            if pk < 0:
+                if r > t1:
+                    return None
+                t0 = max(t0, r)
+            else:
+                if r < t0:
+                    return None
+                t1 = min(t1, r)
+    if t1 - t0 <= 0:
+        return None
+    return p + t0 * d, p + t1 * d
+
+
+def _project_world_segments(P1, P2, K, R, t, w, h, near=0.2):
+    """Project world segments, clip against the near plane and the image rectangle."""
+    X1 = P1 @ R.T + t
+    X2 = P2 @ R.T + t
+    out = []
+    depths = []
+    for a, b in zip(X1, X2):
+        if a[2] < near and b[2] < near:
+            continue
+        if a[2] < near:
+            s = (near - a[2]) / (b[2] - a[2])
+            a = a + s * (b - a)
+        elif b[2] < near:
+            s = (near - b[2]) / (a[2] - b[2])
+            b = b + s * (a - b)
+        pa = K @ a
+        pb = K @ b
+        pa = pa[:2] / pa[2]
+        pb = pb[:2] / pb[2]
+        c = _clip_segment_to_image(pa, pb, float(w), float(h))
+        if c is None:
+            continue
+        out.append((c[0][0], c[0][1], c[1][0], c[1][1]))
+        depths.append(0.5 * (np.linalg.norm(a) + np.linalg.norm(b)))
+    return np.asarray(out, dtype=np.float64).reshape(-1, 4), np.asarray(depths)
+
+
+def _make_view_segments(rng, P1, P2, K, R, t, w, h, n_seg, noise_px, min_len, clutter_med):
+    real, depths = _project_world_segments(P1, P2, K, R, t, w, h)
+    if real.shape[0]:
+        real = real + rng.normal(0.0, noise_px, size=real.shape)
+        real[:, 0::2] = np.clip(real[:, 0::2], 0.0, float(w))
+        real[:, 1::2] = np.clip(real[:, 1::2], 0.0, float(h))
+        ln = np.hypot(real[:, 0] - real[:, 2], real[:, 1] - real[:, 3])
+        keep = ln >= min_len
+        real, depths = real[keep], depths[keep]
+    n_real = min(real.shape[0], n_seg)
+    if real.shape[0] > n_seg:
+        ln = np.hypot(real[:, 0] - real[:, 2], real[:, 1] - real[:, 3])
+        order = np.argsort(-ln, kind="stable")[:n_seg]
+        real = real[order]
+    n_cl = n_seg - n_real
+    segs = [real]
+    if n_cl > 0:
+        cx = rng.uniform(0, w, size=n_cl)
+        cy = rng.uniform(0, h, size=n_cl)
+        ln = np.maximum(min_len, rng.lognormal(math.log(clutter_med), 0.6, size=n_cl))
+        ang = rng.uniform(0, math.pi, size=n_cl)
+        dx, dy = 0.5 * ln * np.cos(ang), 0.5 * ln * np.sin(ang)
+        cl = np.stack([cx - dx, cy - dy, cx + dx, cy + dy], axis=1)
+        cl[:, 0::2] = np.clip(cl[:, 0::2], 0.0, float(w))
+        cl[:, 1::2] = np.clip(cl[:, 1::2], 0.0, float(h))
+        segs.append(cl)
+    segs = np.concatenate(segs, axis=0).astype(np.float32)
+    ln = np.hypot(segs[:, 0] - segs[:, 2], segs[:, 1] - segs[:, 3])
+    segs = segs[np.argsort(-ln, kind="stable")]
+    med = float(np.median(depths)) if depths.size else 1.0
+    return np.ascontiguousarray(segs), med
+
+
+def _nearest_neighbors(centers: np.ndarray, axes: np.ndarray, nbrs: int) -> List[List[int]]:
+    out = []
+    n = centers.shape[0]
+    for i in range(n):
+        d = np.linalg.norm(centers - centers[i], axis=1)
+        ang_ok = (axes @ axes[i]) > 0.0  # optical-axis angle < pi/2
+        cand = [j for j in np.argsort(d, kind="stable") if j != i and ang_ok[j]]
+        out.append(sorted(int(j) for j in cand[:nbrs]))
+    return out
+
+
+def _world_segments(rng, n, box_lo, box_hi, med_len):
+    c = rng.uniform(box_lo, box_hi, size=(n, 3))
+    ln = rng.lognormal(math.log(med_len), 0.6, size=n)
+    d = rng.normal(size=(n, 3))
+    # man-made bias: most segments axis-aligned
+    axis = rng.integers(0, 3, size=n)
+    aligned = rng.uniform(size=n) < 0.7
+    d[aligned] = np.eye(3)[axis[aligned]]
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    return c - 0.5 * ln[:, None] * d, c + 0.5 * ln[:, None] * d
+
+
+def make_scene(kind: str = "c2", n_views: Optional[int] = None, n_seg: Optional[int] = None,
+               nbrs: Optional[int] = None, seed: Optional[int] = None,
+               n_world: Optional[int] = None) -> Scene:
+    """Synthetic scenes of the BASELINE.json shapes.
+
+    kind: "tiny" (CPU tests), "c2" (50x1000x10, 640x480), "c4" (500x3000x20, 1920x1080),
+          "c5" (5000x5000x20 city grid).  Sizes can be overridden for scaled-down variants.
+    """
+    presets = {
+        #        views seg  nbrs world  w     h     f       box                       layout
+        "tiny": (8, 160, 4, 120, 640, 480, 517.0, ((-5, -5, 0), (5, 5, 4)), "circle"),
+        "c2": (50, 1000, 10, 600, 640, 480, 517.0, ((-5, -5, 0), (5, 5, 4)), "circle"),
+        "c4": (500, 3000, 20, 4000, 1920, 1080, 1500.0, ((-30, -30, 0), (30, 30, 10)), "lawn"),
+        "c5": (5000, 5000, 20, 200000, 1920, 1080, 1500.0, ((-500, -500, 0), (500, 500, 30)), "grid"),
+    }
+    idx = {"tiny": 9, "c2": 1, "c4": 3, "c5": 4}[kind]
+    V, N, NB, L, w, h, f, box, layout = presets[kind]
+    V = n_views or V
+    N = n_seg or N
+    NB = nbrs or NB
+    L = n_world or L
+    rng = np.random.Generator(np.random.PCG64((seed if seed is not None else BASE_SEED + idx)))
+    lo, hi = np.asarray(box[0], float), np.asarray(box[1], float)
+    P1, P2 = _world_segments(rng, L, lo, hi, 1.0 if kind != "c5" else 3.0)
+
+    K = np.array([[f, 0, w / 2.0], [0, f, h / 2.0], [0, 0, 1.0]], dtype=np.float64)
+    centers, Rs = [], []
+    if layout == "circle":
+        for i in range(V):
+            a = 2 * math.pi * i / V
+            c = np.array([3.0 * math.cos(a), 3.0 * math.sin(a), 1.6 + 0.2 * math.sin(3 * a)])
+            tgt = np.array([-1.0 * math.cos(a), -1.0 * math.sin(a), 1.8])
+            centers.append(c)
+            Rs.append(look_at(c, tgt))
+    elif layout == "lawn":
+        per_row = max(2, int(round(math.sqrt(V * (hi[0] - lo[0]) / (hi[1] - lo[1])))))
+        for i in range(V):
+            row, col = divmod(i, per_row)
+            x = lo[0] + 5 + (col if row % 2 == 0 else per_row - 1 - col) * 1.0
+            y = lo[1] + 5 + row * 1.0
+            c = np.array([x, y, 1.6])
+            yaw = 0.35 * math.sin(0.37 * i)
+            tgt = c + np.array([math.sin(yaw), math.cos(yaw), 0.05])
+            centers.append(c)
+            Rs.append(look_at(c, tgt))
+    else:  # street grid, 2 m spacing
+        per_row = max(2, int(round(math.sqrt(V))))
+        for i in range(V):
+            row, col = divmod(i, per_row)
+            c = np.array([lo[0] + 20 + 2.0 * col, lo[1] + 20 + 14.0 * row, 1.7])
+            yaw = 0.5 * math.sin(0.11 * i)
+            tgt = c + np.array([math.cos(yaw), math.sin(yaw), 0.1])
+            centers.append(c)
+            Rs.append(look_at(c, tgt))
+    centers = np.asarray(centers)
+    axes = np.asarray([R[2] for R in Rs])
+    nbr_lists = _nearest_neighbors(centers, axes, NB)
+
+    views = []
+    for i in range(V):
+        R = Rs[i]
+        t = -R @ centers[i]
+        segs, med = _make_view_segments(rng, P1, P2, K, R, t, w, h, N, 0.5, 15.0, 40.0)
+        views.append(SceneView(i, K.copy(), R, t, w, h, med, segs, nbr_lists[i]))
+    params = dict(DEFAULT_PARAMS)
+    params["num_neighbors"] = NB
+    return Scene(kind, views, max(w, h), params, False)
+
+
+# ----------------------------------------------------------------------------------------------
+# NVM (the reference's own dump format: src/System.cc:459-535, header "NVM_BTREE_Test_v1")
+# ----------------------------------------------------------------------------------------------
+def read_nvm(path: str):
+    """Returns (cams, points): cams = list of dict(name,f,q,C,dist); points = list of
+    dict(X, obs=[(cam_idx, feat_idx, x, y), ...])."""
+    with open(path, "r") as fh:
+        toks = fh.read().split()
+    pos = 0
+    header = toks[pos]; pos += 1
+    if not header.startswith("NVM_"):
+        raise ValueError("not an NVM file: %r" % header)
+    ncam = int(toks[pos]); pos += 1
+    cams = []
+    for _ in range(ncam):
+        name = toks[pos]
+        vals = [float(x) for x in toks[pos + 1:pos + 10]]
+        pos += 11  # name f qw qx qy qz Cx Cy Cz dist 0
+        cams.append(dict(name=name, f=vals[0], q=vals[1:5], C=np.array(vals[5:8]), dist=vals[8]))
+    npts = int(toks[pos]); pos += 1
+    pts = []
+    for _ in range(npts):
+        X = np.array([float(toks[pos]), float(toks[pos + 1]), float(toks[pos + 2])])
+        nobs = int(toks[pos + 6])
+        pos += 7
+        obs = []
+        for _o in range(nobs):
+            obs.append((int(toks[pos]), int(toks[pos + 1]), float(toks[pos + 2]), float(toks[pos + 3])))
+            pos += 4
+        pts.append(dict(X=X, obs=obs))
+    return cams, pts
+
+
+def scene_from_nvm(path: str, n_seg: int = 400, width: int = 640, height: int = 480,
+                   seed: Optional[int] = None, n_world: int = 300) -> Scene:
+    """BASELINE config 1: cameras + world-point visibility from the reference's NVM dump, 2-D
+    segments synthesised (the images the file names refer to are not shipped)."""
+    cams, pts = read_nvm(path)
+    rng = np.random.Generator(np.random.PCG64(seed if seed is not None else BASE_SEED + 0))
+    X = np.asarray([p["X"] for p in pts])
+    lo, hi = np.percentile(X, 5, axis=0), np.percentile(X, 95, axis=0)
+    P1, P2 = _world_segments(rng, n_world, lo, hi, 0.25 * float(np.median(hi - lo)))
+    wps: Dict[int, List[int]] = {i: [] for i in range(len(cams))}
+    for pid, p in enumerate(pts):
+        for (ci, _fi, _x, _y) in p["obs"]:
+            if 0 <= ci < len(cams):
+                wps[ci].append(pid)
+    views = []
+    for i, c in enumerate(cams):
+        R = rotation_from_q(*c["q"])
+        t = -R @ c["C"]
+        K = np.array([[c["f"], 0, width / 2.0], [0, c["f"], height / 2.0], [0, 0, 1.0]])
+        segs, _ = _make_view_segments(rng, P1, P2, K, R, t, width, height, n_seg, 0.5, 15.0, 40.0)
+        d = [np.linalg.norm(X[pid] - c["C"]) for pid in wps[i]]
+        med = float(sorted(d)[len(d) // 2]) if d else 1.0
+        views.append(SceneView(i, K, R, t, width, height, med, segs, [], list(wps[i])))
+    params = dict(DEFAULT_PARAMS)
+    return Scene("c1_nvm", views, max(width, height), params, True)
