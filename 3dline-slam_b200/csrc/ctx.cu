@@ -1,0 +1,1043 @@
+// ctx.cu -- context, host orchestration and the C ABI of libl3dpp_b200.so (include/l3dpp_b200.h).
+//
+// Host side of Line3D::matchImages / computeMatches / reconstruct3Dlines (src/line3D.cc:496-640,
+// 846-930, 2018-2118): camera set-up, translation, pair list, per-batch K1/K2, the per-view
+// scoring wavefront, K4, and the (unchanged) clustering on the host.  No CPU fallback: every
+// compute entry point needs a CUDA device.
+#include "ctx.h"
+
+static thread_local std::string g_err;
+int fail(int code, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+const char* l3d_last_error(void) { return g_err.c_str(); }
+const char* l3d_version(void) { return "l3dpp-b200 0.1 (sm_100a)"; }
+
+int l3d_ctx_create(l3d_ctx** out, int device)
+{
+    if (!out) return fail(L3D_ERR_ARG, "out is NULL");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(L3D_ERR_CUDA, "no CUDA device available (%s); libl3dpp_b200 has no CPU fallback",
+                    cudaGetErrorString(e));
+    if (device < 0) CK(cudaGetDevice(&device));
+    if (device >= ndev) return fail(L3D_ERR_ARG, "device %d out of range (%d devices)", device, ndev);
+    CK(cudaSetDevice(device));
+    l3d_ctx* c = new l3d_ctx();
+    c->device = device;
+    *out = c;
+    return L3D_OK;
+}
+
+void l3d_ctx_destroy(l3d_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    ctx->tm.reset();
+    delete ctx;
+}
+
+int l3d_ctx_set_stream(l3d_ctx* ctx, void* cuda_stream)
+{
+    if (!ctx) return fail(L3D_ERR_ARG, "ctx is NULL");
+    ctx->stream = (cudaStream_t)cuda_stream;
+    return L3D_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// scene
+// ------------------------------------------------------------------------------------------
+int l3d_scene_begin(l3d_ctx* ctx)
+{
+    if (!ctx) return fail(L3D_ERR_ARG, "ctx is NULL");
+    ctx->views.clear();
+    ctx->cam2view.clear();
+    ctx->committed = false;
+    ctx->stage = 0;
+    ctx->pairs.clear();
+    return L3D_OK;
+}
+
+int l3d_scene_add_view(l3d_ctx* ctx, const l3d_view* view, const float* segs, const uint32_t* nbrs, uint32_t nn)
+{
+    if (!ctx || !view) return fail(L3D_ERR_ARG, "NULL argument");
+    if (ctx->committed) return fail(L3D_ERR_STATE, "scene already committed; call l3d_scene_begin");
+    // same argument checks as Line3D::addImage (src/line3D.cc:123-205)
+    if (std::max(view->width, view->height) < 400)
+        return fail(L3D_ERR_ARG, "image is too small for reliable results: %u px (larger side should be >= 400px)",
+                    std::max(view->width, view->height));
+    for (auto& hv : ctx->views)
+        if (hv.v.cam_id == view->cam_id) return fail(L3D_ERR_ARG, "camera ID [%u] already in use!", view->cam_id);
+    if (nn == 0) return fail(L3D_ERR_ARG, "view [%u] has no visual neighbors!", view->cam_id);
+    if (view->num_segs == 0 || !segs) return fail(L3D_ERR_ARG, "no line segments found in image [%u]!", view->cam_id);
+    HostView hv;
+    hv.v = *view;
+    hv.segs.assign(segs, segs + 4 * (size_t)view->num_segs);
+    hv.nbrs.assign(nbrs, nbrs + nn);
+    hv.cam.init(view->K, view->R, view->t);
+    ctx->views.push_back(std::move(hv));
+    return L3D_OK;
+}
+
+int l3d_scene_commit(l3d_ctx* ctx)
+{
+    if (!ctx) return fail(L3D_ERR_ARG, "ctx is NULL");
+    if (ctx->views.empty()) return fail(L3D_ERR_STATE, "no images to match! forgot to add them?");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    std::sort(ctx->views.begin(), ctx->views.end(),
+              [](const HostView& a, const HostView& b) { return a.v.cam_id < b.v.cam_id; });
+    ctx->cam2view.clear();
+    uint64_t S = 0;
+    for (size_t i = 0; i < ctx->views.size(); ++i) {
+        ctx->cam2view[ctx->views[i].v.cam_id] = (uint32_t)i;
+        ctx->views[i].seg_off = (uint32_t)S;
+        S += ctx->views[i].v.num_segs;
+    }
+    if (S > 0xfffffff0ull) return fail(L3D_ERR_CAPACITY, "too many segments (%llu)", (unsigned long long)S);
+    ctx->S = (uint32_t)S;
+    const uint32_t V = (uint32_t)ctx->views.size();
+    // pinned staging: one H2D copy of all segments
+    std::vector<uint32_t> seg_view(S);
+    float4* hseg = nullptr;
+    CK(cudaMallocHost((void**)&hseg, std::max<size_t>(S, 1) * sizeof(float4)));
+    for (uint32_t v = 0; v < V; ++v) {
+        const HostView& hv = ctx->views[v];
+        memcpy(hseg + hv.seg_off, hv.segs.data(), hv.segs.size() * sizeof(float));
+        std::fill(seg_view.begin() + hv.seg_off, seg_view.begin() + hv.seg_off + hv.v.num_segs, v);
+    }
+    CK(ctx->d_segs.ensure(S));
+    CK(ctx->d_seg_view.ensure(S));
+    CK(ctx->d_desc.ensure(S));
+    CK(ctx->d_rays.ensure(S));
+    CK(ctx->d_midray.ensure(3 * S));
+    CK(ctx->d_view_xb.ensure(V));
+    CK(ctx->d_views.ensure(V));
+    CK(cudaMemcpyAsync(ctx->d_segs.p, hseg, S * sizeof(float4), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_seg_view.p, seg_view.data(), S * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaFreeHost(hseg));
+    ctx->committed = true;
+    ctx->stage = 0;
+    return L3D_OK;
+}
+
+// ViewDev table from the host cameras (C is the current, possibly translated, centre)
+int upload_views(l3d_ctx* ctx)
+{
+    const uint32_t V = (uint32_t)ctx->views.size();
+    std::vector<ViewDev> vd(V);
+    for (uint32_t v = 0; v < V; ++v) {
+        const HostView& hv = ctx->views[v];
+        ViewDev& d = vd[v];
+        d.C[0] = hv.cam.C.x; d.C[1] = hv.cam.C.y; d.C[2] = hv.cam.C.z;
+        memcpy(d.RtKinv, hv.cam.RtKinv.m, sizeof(d.RtKinv));
+        d.k = hv.k;
+        d.median_depth = hv.median_depth;
+        d.seg_off = hv.seg_off;
+        d.n_seg = hv.v.num_segs;
+        d.cam_id = hv.v.cam_id;
+        d.xb = 0.0f;
+        d.order = v;
+        d.pad = 0;
+    }
+    CK(cudaMemcpyAsync(ctx->d_views.p, vd.data(), V * sizeof(ViewDev), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return L3D_OK;
+}
+
+// Line3D::translate (src/line3D.cc:643-680): per-axis median of the camera centres
+static void compute_translation(l3d_ctx* ctx)
+{
+    double* tr[3] = {&ctx->translation.x, &ctx->translation.y, &ctx->translation.z};
+    for (int a = 0; a < 3; ++a) {
+        *tr[a] = 0.0;
+        std::vector<double> c;
+        for (auto& hv : ctx->views) {
+            const double val = a == 0 ? hv.cam.C.x : (a == 1 ? hv.cam.C.y : hv.cam.C.z);
+            if (std::fabs(val) > 1e-12) c.push_back(val);
+        }
+        if (!c.empty()) {
+            std::sort(c.begin(), c.end());
+            *tr[a] = c[c.size() / 2];
+        }
+    }
+}
+static void apply_translation(l3d_ctx* ctx, double sign)
+{
+    const hg::V3 tv{sign * ctx->translation.x, sign * ctx->translation.y, sign * ctx->translation.z};
+    for (auto& hv : ctx->views) hv.cam.translate(tv);
+}
+
+__global__ void pair_totals_kernel(const PairDev* __restrict__ pairs, uint32_t P, const uint32_t* __restrict__ fwd_off,
+                                   const uint32_t* __restrict__ fwd_cnt, uint32_t* __restrict__ out)
+{
+    // forward records of a pair are contiguous (rows ascending): total = end(last row) - start(first row)
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    const PairDev& D = pairs[p];
+    if (D.n_src == 0) {
+        out[p] = 0;
+        return;
+    }
+    const uint32_t r0 = D.row_base, r1 = D.row_base + D.n_src - 1;
+    out[p] = fwd_off[r1] + fwd_cnt[r1] - fwd_off[r0];
+}
+
+
+// per-pair forward-record totals -> host (list capacities, record ranges of the canonical layout)
+int refresh_pair_totals(l3d_ctx* ctx)
+{
+    const uint32_t P = (uint32_t)ctx->pairs.size();
+    cudaStream_t st = ctx->stream;
+    if (!P) return L3D_OK;
+    CK(ctx->d_scan_tmp.ensure((size_t)std::max(P, ctx->total_tgt_rows) + 2));
+    pair_totals_kernel<<<(P + 255) / 256, 256, 0, st>>>(ctx->d_pairs.p, P, ctx->d_fwd_off.p, ctx->d_fwd_cnt.p,
+                                                        ctx->d_scan_tmp.p);
+    ctx->cnt.gpu_launches++;
+    std::vector<uint32_t> tot(P);
+    CK(cudaMemcpyAsync(tot.data(), ctx->d_scan_tmp.p, P * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    uint64_t run = 0;
+    for (uint32_t p = 0; p < P; ++p) {
+        ctx->pairs[p].fwd_total = tot[p];
+        ctx->pairs[p].rec_start = (uint32_t)run;
+        run += tot[p];
+    }
+    return L3D_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// planning: pair list, batches, incident lists
+// ------------------------------------------------------------------------------------------
+int plan_pairs(l3d_ctx* ctx)
+{
+    const l3d_params& prm = ctx->prm;
+    const uint32_t V = (uint32_t)ctx->views.size();
+    // visual neighbours = fixed neighbours that exist (src/line3D.cc:604-616)
+    std::vector<std::set<uint32_t>> nb(V);
+    for (uint32_t v = 0; v < V; ++v)
+        for (uint32_t cam : ctx->views[v].nbrs) {
+            auto f = ctx->cam2view.find(cam);
+            if (f != ctx->cam2view.end()) nb[v].insert(f->second);  // view index order == cam id order
+        }
+    // computeMatches pair order (src/line3D.cc:848-887)
+    std::vector<std::set<uint32_t>> matched(V);
+    ctx->pairs.clear();
+    for (uint32_t s = 0; s < V; ++s)
+        for (uint32_t t : nb[s])
+            if (!matched[s].count(t)) {
+                HostPair hp;
+                hp.src = s;
+                hp.tgt = t;
+                hp.batch = 0;
+                ctx->pairs.push_back(hp);
+                matched[s].insert(t);
+                matched[t].insert(s);
+            }
+    const uint32_t P = (uint32_t)ctx->pairs.size();
+    const int world = prm.shard_world > 1 ? prm.shard_world : 1;
+    const int rank = world > 1 ? prm.shard_rank : 0;
+    ctx->pairs_h.assign(P, PairDev{});
+    uint64_t row = 0, trow = 0;
+    ctx->cnt.pair_tests = 0;
+    ctx->cnt.num_pairs_local = 0;
+    for (uint32_t p = 0; p < P; ++p) {
+        HostPair& hp = ctx->pairs[p];
+        hp.local = ((int)(p % world) == rank);
+        const HostView& vs = ctx->views[hp.src];
+        const HostView& vt = ctx->views[hp.tgt];
+        PairDev& d = ctx->pairs_h[p];
+        if (ctx->raw_mode) {
+            memcpy(d.F, ctx->F_override, sizeof(d.F));
+        } else {
+            const hg::M3 F = hg::fundamental(vs.cam, vt.cam);
+            memcpy(d.F, F.m, sizeof(d.F));
+        }
+        d.src_view = hp.src;
+        d.tgt_view = hp.tgt;
+        d.src_off = vs.seg_off;
+        d.n_src = vs.v.num_segs;
+        d.tgt_off = vt.seg_off;
+        d.n_tgt = vt.v.num_segs;
+        d.row_base = (uint32_t)row;
+        d.tgt_base = (uint32_t)trow;
+        d.words = (d.n_tgt + 31) / 32;
+        d.emit_inverse = hp.tgt > hp.src ? 1u : 0u;  // !processed_[tgt] (src/line3D.cc:1994)
+        row += d.n_src;
+        trow += d.n_tgt;
+        if (hp.local) {
+            ctx->cnt.pair_tests += (uint64_t)d.n_src * d.n_tgt;
+            ctx->cnt.num_pairs_local++;
+        }
+    }
+    if (row > 0xfffffff0ull || trow > 0xfffffff0ull)
+        return fail(L3D_ERR_CAPACITY, "row index space exhausted (%llu rows)", (unsigned long long)row);
+    ctx->total_rows = (uint32_t)row;
+    ctx->total_tgt_rows = (uint32_t)trow;
+
+    // batches over local pairs: bounded bit-mask size
+    const uint64_t max_words = 1ull << 27;  // 512 MB of mask
+    const uint32_t rows_per_cta = (uint32_t)k1_rows_per_cta();
+    ctx->batches.clear();
+    ctx->ctas_h.clear();
+    Batch cur{};
+    bool open = false;
+    auto close = [&]() {
+        if (open) {
+            cur.n_ctas = (uint32_t)ctx->ctas_h.size() - cur.cta0;
+            ctx->batches.push_back(cur);
+            open = false;
+        }
+    };
+    for (uint32_t p = 0; p < P; ++p) {
+        if (!ctx->pairs[p].local) {
+            close();  // keep batch rows contiguous
+            continue;
+        }
+        PairDev& d = ctx->pairs_h[p];
+        const uint64_t w = (uint64_t)d.words * d.n_src;
+        if (open && cur.mask_words + w > max_words) close();
+        if (!open) {
+            cur = Batch{};
+            cur.pair0 = p;
+            cur.row0 = d.row_base;
+            cur.cta0 = (uint32_t)ctx->ctas_h.size();
+            open = true;
+        }
+        d.mask_base = cur.mask_words;
+        d.batch_row0 = cur.row0;
+        cur.mask_words += w;
+        cur.n_rows += d.n_src;
+        cur.pair1 = p + 1;
+        ctx->pairs[p].batch = (uint32_t)ctx->batches.size();
+        for (uint32_t t = 0; t * rows_per_cta < d.n_src; ++t) ctx->ctas_h.push_back(K1Cta{p, t});
+    }
+    close();
+
+    // incident pairs per view in list order: inverse blocks (source views ascending = the order
+    // their storeInverseMatches ran), then forward blocks (targets ascending)
+    ctx->inc_off_h.assign(V + 1, 0);
+    ctx->inc_h.clear();
+    std::vector<std::vector<uint32_t>> inv_of(V), fwd_of(V);
+    for (uint32_t p = 0; p < P; ++p) {
+        fwd_of[ctx->pairs[p].src].push_back(p);
+        if (ctx->pairs_h[p].emit_inverse) inv_of[ctx->pairs[p].tgt].push_back(p);
+    }
+    for (uint32_t v = 0; v < V; ++v) {
+        ctx->inc_off_h[v] = (uint32_t)ctx->inc_h.size();
+        for (uint32_t p : inv_of[v]) ctx->inc_h.push_back(IncDev{p, 1u});  // pairs are sorted by src
+        for (uint32_t p : fwd_of[v]) ctx->inc_h.push_back(IncDev{p, 0u});  // and by tgt within a src
+    }
+    ctx->inc_off_h[V] = (uint32_t)ctx->inc_h.size();
+    ctx->cnt.num_pairs = P;
+    ctx->cnt.num_views = V;
+    return L3D_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// stage 1 + 2
+// ------------------------------------------------------------------------------------------
+int set_params(l3d_ctx* ctx, const l3d_params* params)
+{
+    if (!params) return fail(L3D_ERR_ARG, "params is NULL");
+    ctx->prm = *params;
+    l3d_params& p = ctx->prm;
+    // parameter clamps of Line3D::matchImages (src/line3D.cc:517-536)
+    p.num_neighbors = (uint32_t)std::max((int)p.num_neighbors, 2);
+    p.sigma_a = (float)std::fmin(std::fabs((double)p.sigma_a), 90.0);
+    ctx->two_sigA_sqr = 2.0f * p.sigma_a * p.sigma_a;
+    ctx->epi_overlap = (float)std::fmin(std::fabs((double)p.epipolar_overlap), (double)0.99f);
+    if (p.sigma_p < 0.0f)
+        return fail(L3D_ERR_ARG, "sigma_p < 0 (metric regulariser) is not supported by this build");
+    p.sigma_p = (float)std::fmax((double)0.1f, (double)p.sigma_p);
+    if (p.max_image_width <= 0)
+        return fail(L3D_ERR_ARG, "max_image_width must be > 0 (the reference's bounds test rejects every pair otherwise)");
+    ctx->have_params = true;
+    return L3D_OK;
+}
+
+int l3d_match_stage12(l3d_ctx* ctx, const l3d_params* params)
+{
+    if (!ctx) return fail(L3D_ERR_ARG, "ctx is NULL");
+    if (!ctx->committed) return fail(L3D_ERR_STATE, "scene not committed");
+    int rc = set_params(ctx, params);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    ctx->tm.reset();
+    cudaEvent_t ev_total = ctx->tm.begin(L3D_T_TOTAL, st);
+
+    // translate(), spatial regularisers (src/line3D.cc:568-590)
+    if (!ctx->raw_mode) {
+        compute_translation(ctx);
+        apply_translation(ctx, -1.0);
+        for (auto& hv : ctx->views) {
+            hv.k = hv.cam.spatial_regularizer(ctx->prm.sigma_p);
+            hv.median_depth = 0.0f;
+        }
+    }
+    rc = plan_pairs(ctx);
+    if (rc) return rc;
+    rc = upload_views(ctx);
+    if (rc) return rc;
+    const uint32_t V = (uint32_t)ctx->views.size(), P = (uint32_t)ctx->pairs.size(), S = ctx->S;
+
+    // per-segment tables
+    cudaEvent_t ev = ctx->tm.begin(L3D_T_PREP, st);
+    CK(cudaMemsetAsync(ctx->d_view_xb.p, 0, V * sizeof(float), st));
+    ctx->cnt.gpu_launches += launch_k0_prep(ctx->d_segs.p, ctx->d_seg_view.p, ctx->d_views.p, S,
+                                            ctx->prm.max_image_width, ctx->d_desc.p, ctx->d_rays.p, ctx->d_midray.p,
+                                            ctx->d_view_xb.p, st);
+    ctx->tm.end(ev, st);
+
+    CK(ctx->d_fwd_off.ensure((size_t)ctx->total_rows + 1));
+    CK(ctx->d_fwd_cnt.ensure((size_t)ctx->total_rows + 1));
+    CK(cudaMemsetAsync(ctx->d_fwd_cnt.p, 0, ((size_t)ctx->total_rows + 1) * sizeof(uint32_t), st));
+    CK(cudaMemsetAsync(ctx->d_fwd_off.p, 0, ((size_t)ctx->total_rows + 1) * sizeof(uint32_t), st));
+    ctx->total_fwd = 0;
+    ctx->cnt.candidates = 0;
+
+    if (P) {
+        uint32_t max_rows = 0;
+        uint64_t max_words = 0;
+        for (auto& b : ctx->batches) {
+            max_rows = std::max(max_rows, b.n_rows);
+            max_words = std::max(max_words, b.mask_words);
+        }
+        CK(ctx->d_mask.ensure(max_words));
+        CK(ctx->d_cand_cnt.ensure((size_t)max_rows + 1));
+        CK(ctx->d_cand_off.ensure((size_t)max_rows + 1));
+        CK(ctx->d_fin_cnt.ensure((size_t)max_rows + 1));
+        CK(ctx->d_fin_off.ensure((size_t)max_rows + 1));
+        CK(ctx->d_scan.ensure(scan_scratch_words(std::max(max_rows, ctx->total_tgt_rows) + 1) + 64));
+        CK(ctx->d_ctas.ensure(ctx->ctas_h.size()));
+        CK(cudaMemcpyAsync(ctx->d_ctas.p, ctx->ctas_h.data(), ctx->ctas_h.size() * sizeof(K1Cta),
+                           cudaMemcpyHostToDevice, st));
+        CK(ctx->d_pairs.ensure(P));
+        CK(cudaMemcpyAsync(ctx->d_pairs.p, ctx->pairs_h.data(), P * sizeof(PairDev), cudaMemcpyHostToDevice, st));
+    }
+
+    uint32_t rec_base = 0;  // running start of this shard's forward records (local layout)
+    for (const Batch& b : ctx->batches) {
+        // K1
+        cudaEvent_t e1 = ctx->tm.begin(L3D_T_PAIRTEST, st);
+        cudaEvent_t ek = ctx->tm.begin(L3D_T_K1_KERNEL, st);
+        ctx->cnt.gpu_launches +=
+            launch_k1_pairtest(ctx->d_pairs.p, ctx->d_ctas.p + b.cta0, b.n_ctas, ctx->d_segs.p, ctx->d_desc.p,
+                               ctx->d_view_xb.p, ctx->d_mask.p, ctx->d_cand_cnt.p, ctx->epi_overlap,
+                               ctx->prm.filter_mode, st);
+        ctx->tm.end(ek, st);
+        ctx->tm.ms[L3D_T_K1_LAUNCHES] += 1.0f;
+        ctx->cnt.gpu_launches += launch_scan_u32(ctx->d_cand_cnt.p, ctx->d_cand_off.p, b.n_rows, ctx->d_scan.p,
+                                                 ctx->d_scan.cap, st);
+        ctx->tm.end(e1, st);
+        uint32_t n_cand = 0;
+        CK(cudaMemcpyAsync(&n_cand, ctx->d_cand_off.p + b.n_rows, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        ctx->cnt.candidates += n_cand;
+        // K2
+        CK(ctx->d_heap.ensure(n_cand));
+        CK(ctx->d_cand_rec.ensure(n_cand));
+        CK(ctx->d_fin_rec.ensure(n_cand));
+        cudaEvent_t e2 = ctx->tm.begin(L3D_T_EXACT, st);
+        ctx->cnt.gpu_launches +=
+            launch_k2_exact(ctx->d_pairs.p, ctx->d_ctas.p + b.cta0, b.n_ctas, ctx->d_segs.p, ctx->d_rays.p,
+                            ctx->d_midray.p, ctx->d_views.p, ctx->d_mask.p, ctx->d_cand_off.p, ctx->d_heap.p,
+                            ctx->d_cand_rec.p, ctx->d_fin_rec.p, ctx->d_fin_cnt.p, ctx->epi_overlap, ctx->prm.knn,
+                            ctx->prm.max_image_width, st);
+        ctx->cnt.gpu_launches +=
+            launch_scan_u32(ctx->d_fin_cnt.p, ctx->d_fin_off.p, b.n_rows, ctx->d_scan.p, ctx->d_scan.cap, st);
+        uint32_t n_fin = 0;
+        CK(cudaMemcpyAsync(&n_fin, ctx->d_fin_off.p + b.n_rows, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if ((uint64_t)rec_base + n_fin > 0xfffffff0ull) return fail(L3D_ERR_CAPACITY, "too many forward matches");
+        CK(ctx->d_fwd_rec.ensure((size_t)rec_base + n_fin, rec_base, st));
+        ctx->cnt.gpu_launches +=
+            launch_k2_compact(ctx->d_cand_off.p, ctx->d_fin_cnt.p, ctx->d_fin_off.p, rec_base, ctx->d_fin_rec.p,
+                              ctx->d_fwd_rec.p, ctx->d_fwd_off.p + b.row0, b.n_rows, st);
+        CK(cudaMemcpyAsync(ctx->d_fwd_cnt.p + b.row0, ctx->d_fin_cnt.p, b.n_rows * sizeof(uint32_t),
+                           cudaMemcpyDeviceToDevice, st));
+        ctx->tm.end(e2, st);
+        rec_base += n_fin;
+    }
+    ctx->total_fwd = rec_base;
+
+    rc = refresh_pair_totals(ctx);
+    if (rc) return rc;
+    ctx->tm.end(ev_total, st);
+    CK(cudaStreamSynchronize(st));
+    ctx->tm.collect();
+    ctx->cnt.forward_matches = ctx->total_fwd;
+    ctx->stage = 1;
+    return L3D_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// stage 3: scoring wavefront
+// ------------------------------------------------------------------------------------------
+int l3d_match_stage3(l3d_ctx* ctx)
+{
+    if (!ctx) return fail(L3D_ERR_ARG, "ctx is NULL");
+    if (ctx->stage < 1) return fail(L3D_ERR_STATE, "l3d_match_stage12 has not run");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const uint32_t V = (uint32_t)ctx->views.size(), P = (uint32_t)ctx->pairs.size(), S = ctx->S;
+
+    cudaEvent_t ev_total = ctx->tm.begin(L3D_T_TOTAL, st);
+    cudaEvent_t ev = ctx->tm.begin(L3D_T_SCORE, st);
+    const size_t F = (size_t)ctx->total_fwd;
+    CK(ctx->d_inc.ensure(ctx->inc_h.size()));
+    if (!ctx->inc_h.empty())
+        CK(cudaMemcpyAsync(ctx->d_inc.p, ctx->inc_h.data(), ctx->inc_h.size() * sizeof(IncDev), cudaMemcpyHostToDevice,
+                           st));
+    CK(ctx->d_inv_cnt.ensure((size_t)ctx->total_tgt_rows + 1));
+    CK(ctx->d_inv_fill.ensure((size_t)ctx->total_tgt_rows + 1));
+    CK(ctx->d_inv_off.ensure((size_t)ctx->total_tgt_rows + 1));
+    CK(ctx->d_inv_ent.ensure(F + 1));
+    CK(cudaMemsetAsync(ctx->d_inv_cnt.p, 0, ((size_t)ctx->total_tgt_rows + 1) * 4, st));
+    CK(cudaMemsetAsync(ctx->d_inv_fill.p, 0, ((size_t)ctx->total_tgt_rows + 1) * 4, st));
+    CK(cudaMemsetAsync(ctx->d_inv_off.p, 0, ((size_t)ctx->total_tgt_rows + 1) * 4, st));
+    CK(ctx->d_scan_tmp.ensure((size_t)std::max(P, ctx->total_tgt_rows) + 2));
+    CK(ctx->d_scan.ensure(scan_scratch_words(std::max(ctx->total_tgt_rows, S) * 2 + 2) + 64));
+
+    uint32_t maxN = 0;
+    for (auto& hv : ctx->views) maxN = std::max(maxN, hv.v.num_segs);
+    CK(ctx->d_L_cnt.ensure((size_t)maxN + 1));
+    CK(ctx->d_L_off.ensure((size_t)maxN + 1));
+    CK(ctx->d_F_cnt.ensure((size_t)maxN + 1));
+    CK(ctx->d_F_off.ensure((size_t)maxN + 1));
+
+    // list capacities: forward records of the view's own pairs + of the pairs pointing at it
+    std::vector<uint64_t> cap(V, 0);
+    for (uint32_t p = 0; p < P; ++p) {
+        cap[ctx->pairs[p].src] += ctx->pairs[p].fwd_total;
+        if (ctx->pairs_h[p].emit_inverse) cap[ctx->pairs[p].tgt] += ctx->pairs[p].fwd_total;
+    }
+    const bool keep = ctx->prm.keep_scored != 0;
+    ctx->L_base_h.assign(V + 1, 0);
+    uint64_t Lcap = 0;
+    if (keep) {
+        for (uint32_t v = 0; v < V; ++v) {
+            ctx->L_base_h[v] = Lcap;
+            Lcap += cap[v];
+        }
+        ctx->L_base_h[V] = Lcap;
+        CK(ctx->d_L_off_all.ensure((size_t)S + V + 1));
+    } else {
+        for (uint32_t v = 0; v < V; ++v) Lcap = std::max(Lcap, cap[v]);
+    }
+    if (Lcap > 0xfffffff0ull || 2 * F > 0xfffffff0ull) return fail(L3D_ERR_CAPACITY, "match lists too large");
+    CK(ctx->d_L_rec.ensure(Lcap + 1));
+    CK(ctx->d_L_geo.ensure(Lcap + 1));
+    CK(ctx->d_filt_rec.ensure(2 * F + 1));
+    CK(ctx->d_filt_off.ensure((size_t)S + 1));
+    CK(ctx->d_filt_cnt.ensure((size_t)S + 1));
+    CK(ctx->d_small.ensure(16));
+    CK(cudaMemsetAsync(ctx->d_small.p, 0, 16 * 4, st));
+    CK(ctx->d_stats.ensure(2 * k3_stats_bytes()));
+    CK(cudaMemsetAsync(ctx->d_stats.p, 0, 2 * k3_stats_bytes(), st));
+    CK(ctx->d_entries.ensure((size_t)S + 1));
+    void* stats = ctx->d_stats.p;
+    void* accum = ctx->d_stats.p + k3_stats_bytes();
+    uint32_t* filt_total = ctx->d_small.p;
+    uint32_t* err_flag = ctx->d_small.p + 1;
+
+    for (uint32_t v = 0; v < V; ++v) {
+        const HostView& hv = ctx->views[v];
+        const uint32_t N = hv.v.num_segs;
+        const uint32_t i0 = ctx->inc_off_h[v], n_inc = ctx->inc_off_h[v + 1] - i0;
+        ListRec* Lr = ctx->d_L_rec.p + (keep ? ctx->L_base_h[v] : 0);
+        ListGeo* Lg = ctx->d_L_geo.p + (keep ? ctx->L_base_h[v] : 0);
+        ctx->cnt.gpu_launches += launch_k3_count(ctx->d_inc.p + i0, n_inc, ctx->d_pairs.p, ctx->d_fwd_cnt.p,
+                                                 ctx->d_inv_cnt.p, N, ctx->d_L_cnt.p, st);
+        ctx->cnt.gpu_launches += launch_scan_u32(ctx->d_L_cnt.p, ctx->d_L_off.p, N, ctx->d_scan.p, ctx->d_scan.cap, st);
+        ctx->cnt.gpu_launches +=
+            launch_k3_gather(v, N, ctx->d_inc.p + i0, n_inc, ctx->d_pairs.p, ctx->d_views.p, ctx->d_rays.p,
+                             ctx->d_fwd_off.p, ctx->d_fwd_cnt.p, ctx->d_fwd_rec.p, ctx->d_inv_off.p, ctx->d_inv_cnt.p,
+                             ctx->d_inv_ent.p, ctx->d_L_off.p, Lr, Lg, err_flag, st);
+        ctx->cnt.gpu_launches +=
+            launch_k3_score(N, ctx->d_L_off.p, Lr, Lg, ctx->d_fwd_rec.p, ctx->two_sigA_sqr, 0.5f, stats, st);
+        // inverse matches towards later views
+        uint32_t first_p = 0xffffffffu, last_p = 0;
+        bool any_emit = false;
+        for (uint32_t q = i0; q < i0 + n_inc; ++q)
+            if (!ctx->inc_h[q].inverse) {
+                first_p = std::min(first_p, ctx->inc_h[q].pair);
+                last_p = std::max(last_p, ctx->inc_h[q].pair);
+                any_emit |= ctx->pairs_h[ctx->inc_h[q].pair].emit_inverse != 0;
+            }
+        if (any_emit) {
+            const uint32_t first_row = ctx->pairs_h[first_p].tgt_base;
+            const uint32_t n_rows_t = ctx->pairs_h[last_p].tgt_base + ctx->pairs_h[last_p].n_tgt - first_row;
+            const uint32_t grid = (uint32_t)std::min<uint64_t>(std::max<uint64_t>((cap[v] + 255) / 256, 1), 148 * 8);
+            ctx->cnt.gpu_launches += launch_k3_inverse(
+                N, ctx->d_L_off.p, Lr, Lg, ctx->d_pairs.p, first_row, n_rows_t, ctx->pairs[first_p].rec_start,
+                ctx->d_inv_cnt.p, ctx->d_inv_fill.p, ctx->d_inv_off.p, ctx->d_inv_ent.p, ctx->d_scan_tmp.p,
+                ctx->d_scan.p, ctx->d_scan.cap, grid, st);
+        }
+        ctx->cnt.gpu_launches += launch_k3_filter(v, N, ctx->d_views.p, ctx->d_rays.p, ctx->d_L_off.p, Lr, stats, accum,
+                                                  ctx->d_F_cnt.p, ctx->d_F_off.p, ctx->d_entries.p, filt_total,
+                                                  ctx->d_filt_rec.p, ctx->d_filt_off.p, ctx->d_filt_cnt.p, ctx->d_scan.p,
+                                                  ctx->d_scan.cap, st);
+        if (keep)
+            CK(cudaMemcpyAsync(ctx->d_L_off_all.p + hv.seg_off + v, ctx->d_L_off.p, ((size_t)N + 1) * 4,
+                               cudaMemcpyDeviceToDevice, st));
+    }
+    // estimated_position3D_ index (canonical order = global segment order) and median depths
+    CK(ctx->d_has.ensure((size_t)S + 1));
+    CK(ctx->d_entry_idx.ensure((size_t)S + 2));
+    ctx->cnt.gpu_launches += launch_k4_has(ctx->d_entries.p, S, ctx->d_has.p, st);
+    ctx->cnt.gpu_launches += launch_scan_u32(ctx->d_has.p, ctx->d_entry_idx.p, S, ctx->d_scan.p, ctx->d_scan.cap, st);
+    ctx->cnt.gpu_launches += launch_k4_median(ctx->d_views.p, V, ctx->d_entries.p, ctx->d_small.p + 2, st);
+    ctx->tm.end(ev, st);
+    ctx->tm.end(ev_total, st);
+
+    uint32_t small[4] = {0, 0, 0, 0};
+    uint32_t n_entries = 0;
+    std::vector<unsigned char> acc(k3_stats_bytes());
+    std::vector<ViewDev> vd(V);
+    CK(cudaMemcpyAsync(small, ctx->d_small.p, sizeof(small), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&n_entries, ctx->d_entry_idx.p + S, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(acc.data(), accum, acc.size(), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(vd.data(), ctx->d_views.p, V * sizeof(ViewDev), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    ctx->tm.collect();
+    if (small[1]) return fail(L3D_ERR_STATE, "a match list holds a camera in two separate runs");
+    if (small[2]) return fail(L3D_ERR_CAPACITY, "more than 8192 hypotheses in one view (median-depth kernel)");
+    ctx->cnt.filtered_entries = small[0];
+    ctx->cnt.num_entries = n_entries;
+    {
+        const unsigned long long* a = (const unsigned long long*)acc.data();
+        ctx->cnt.sim_evals = a[0];
+        ctx->cnt.scored_entries = a[1];
+    }
+    for (uint32_t v = 0; v < V; ++v) {
+        ctx->views[v].median_depth = vd[v].median_depth;
+        ctx->views[v].median_sigma = ctx->views[v].k * vd[v].median_depth;  // view.h:122-135
+    }
+    // update_Matches_and_Estimated_position3D (src/line3D.cc:1857-1908) re-triangulates the best
+    // matches with unchanged poses: the identical call, hence identical depths -- nothing to do.
+    apply_translation(ctx, +1.0);  // untranslate()
+    ctx->stage = 2;
+    return L3D_OK;
+}
+
+int l3d_match_images(l3d_ctx* ctx, const l3d_params* params)
+{
+    int rc = l3d_match_stage12(ctx, params);
+    if (rc) return rc;
+    float keep_ms[L3D_T_COUNT];
+    memcpy(keep_ms, ctx->tm.ms, sizeof(keep_ms));
+    rc = l3d_match_stage3(ctx);
+    for (int i = 0; i < L3D_T_COUNT; ++i) ctx->tm.ms[i] += keep_ms[i];
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------
+// stage 4: affinity + clustering
+// ------------------------------------------------------------------------------------------
+int l3d_affinity(l3d_ctx* ctx)
+{
+    if (!ctx) return fail(L3D_ERR_ARG, "ctx is NULL");
+    if (ctx->stage < 2) return fail(L3D_ERR_STATE, "l3d_match_images has not run");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const uint32_t V = (uint32_t)ctx->views.size(), S = ctx->S;
+    ctx->cnt.num_edges = 0;
+    ctx->cnt.num_local_ids = 0;
+    ctx->cluster_ids.clear();
+    if (ctx->cnt.num_entries == 0) {  // "no clusterable segments" (src/line3D.cc:2028-2034)
+        ctx->stage = 3;
+        return L3D_OK;
+    }
+    // translate() again (src/line3D.cc:2065); only the camera centres move
+    compute_translation(ctx);
+    apply_translation(ctx, -1.0);
+    // median scene depth of the lines (src/line3D.cc:2074-2091)
+    std::vector<float> sd;
+    for (auto& hv : ctx->views)
+        if (hv.median_depth > 1e-12) sd.push_back(hv.median_depth);
+    if (!sd.empty()) {
+        std::sort(sd.begin(), sd.end());
+        ctx->med_scene_depth_lines = sd[sd.size() / 2];
+    } else
+        ctx->med_scene_depth_lines = 0.0f;
+
+    cudaEvent_t ev_total = ctx->tm.begin(L3D_T_TOTAL, st);
+    cudaEvent_t ev = ctx->tm.begin(L3D_T_AFFINITY, st);
+    const size_t nf = (size_t)ctx->cnt.filtered_entries;
+    CK(ctx->d_filt_sim.ensure(nf + 1));
+    CK(ctx->d_E_cnt.ensure((size_t)S + 1));
+    CK(ctx->d_E_off.ensure((size_t)S + 2));
+    CK(ctx->d_tests.ensure(2));
+    CK(cudaMemsetAsync(ctx->d_tests.p, 0, 16, st));
+    CK(ctx->d_first_touch.ensure((size_t)S + 1));
+    CK(cudaMemsetAsync(ctx->d_first_touch.p, 0xff, ((size_t)S + 1) * 4, st));
+    ctx->cnt.gpu_launches +=
+        launch_k4_edges_count(ctx->d_views.p, ctx->d_seg_view.p, ctx->d_entries.p, S, ctx->d_filt_off.p,
+                              ctx->d_filt_cnt.p, ctx->d_filt_rec.p, ctx->two_sigA_sqr, ctx->med_scene_depth_lines,
+                              ctx->d_filt_sim.p, ctx->d_E_cnt.p, ctx->d_tests.p, st);
+    ctx->cnt.gpu_launches += launch_scan_u32(ctx->d_E_cnt.p, ctx->d_E_off.p, S, ctx->d_scan.p, ctx->d_scan.cap, st);
+    uint32_t n_edges = 0;
+    CK(cudaMemcpyAsync(&n_edges, ctx->d_E_off.p + S, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    uint32_t n_local = 0;
+    if (n_edges) {
+        CK(ctx->d_edges.ensure((size_t)n_edges * k4_edge_bytes()));
+        CK(ctx->d_flags.ensure(2 * (size_t)n_edges + 1));
+        CK(ctx->d_flag_scan.ensure(2 * (size_t)n_edges + 2));
+        CK(ctx->d_A_ij.ensure(2 * (size_t)n_edges));
+        CK(ctx->d_A_w.ensure(2 * (size_t)n_edges));
+        CK(ctx->d_l2g.ensure(2 * (size_t)n_edges));
+        CK(ctx->d_scan.ensure(scan_scratch_words(2 * n_edges + 2) + 64));
+        ctx->cnt.gpu_launches +=
+            launch_k4_edges_write(ctx->d_views.p, S, ctx->d_filt_off.p, ctx->d_filt_cnt.p, ctx->d_filt_rec.p,
+                                  ctx->d_filt_sim.p, ctx->d_E_off.p, ctx->d_edges.p, ctx->d_first_touch.p, st);
+        ctx->cnt.gpu_launches +=
+            launch_k4_ids(ctx->d_edges.p, n_edges, ctx->d_first_touch.p, ctx->d_flags.p, ctx->d_flag_scan.p,
+                          ctx->d_scan.p, ctx->d_scan.cap, ctx->d_A_ij.p, ctx->d_A_w.p, ctx->d_l2g.p, st);
+        CK(cudaMemcpyAsync(&n_local, ctx->d_flag_scan.p + 2 * (size_t)n_edges, 4, cudaMemcpyDeviceToHost, st));
+    }
+    ctx->tm.end(ev, st);
+    ctx->tm.end(ev_total, st);
+    CK(cudaStreamSynchronize(st));
+    ctx->tm.collect();
+    ctx->cnt.num_edges = 2 * n_edges;  // A_ holds both directions
+    ctx->cnt.num_local_ids = n_local;
+    apply_translation(ctx, +1.0);  // untranslate() (src/line3D.cc:2140)
+    ctx->stage = 3;
+    (void)V;
+    return L3D_OK;
+}
+
+// Felzenszwalb-Huttenlocher clustering, src/clustering.cc:7-48 + include/universe.h:59-117
+int l3d_cluster_edges(const int32_t* ij, const float* w, uint32_t ne, uint32_t n, int32_t* out)
+{
+    if ((ne && (!ij || !w)) || (n && !out)) return fail(L3D_ERR_ARG, "NULL argument");
+    struct El {
+        int rank, id, size;
+    };
+    std::vector<El> el(n);
+    for (uint32_t i = 0; i < n; ++i) el[i] = El{0, (int)i, 1};
+    auto find = [&](int x) {
+        int y = x;
+        while (y != el[y].id) y = el[y].id;
+        el[x].id = y;
+        return y;
+    };
+    if (ne) {
+        std::vector<uint32_t> order(ne);
+        for (uint32_t i = 0; i < ne; ++i) order[i] = i;
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return w[a] < w[b]; });
+        const float c = 3.0f;
+        std::vector<float> thr(n, c);
+        for (uint32_t o : order) {
+            const int i = ij[2 * o], j = ij[2 * o + 1];
+            if (i < 0 || j < 0 || (uint32_t)i >= n || (uint32_t)j >= n) return fail(L3D_ERR_ARG, "edge out of range");
+            int a = find(i), b = find(j);
+            if (a != b && w[o] <= thr[a] && w[o] <= thr[b]) {
+                if (el[a].rank > el[b].rank) {
+                    el[b].id = a;
+                    el[a].size += el[b].size;
+                } else {
+                    el[a].id = b;
+                    el[b].size += el[a].size;
+                    if (el[a].rank == el[b].rank) el[b].rank++;
+                }
+                a = find(a);
+                thr[a] = w[o] + c / (float)el[a].size;
+            }
+        }
+    }
+    for (uint32_t i = 0; i < n; ++i) out[i] = find((int)i);
+    return L3D_OK;
+}
+
+int l3d_cluster(l3d_ctx* ctx)
+{
+    if (!ctx) return fail(L3D_ERR_ARG, "ctx is NULL");
+    if (ctx->stage < 3) return fail(L3D_ERR_STATE, "l3d_affinity has not run");
+    const uint32_t ne = ctx->cnt.num_edges, n = ctx->cnt.num_local_ids;
+    ctx->cluster_ids.assign(n, 0);
+    ctx->cnt.num_clusters = 0;
+    if (ne == 0) {
+        ctx->stage = 4;
+        return L3D_OK;
+    }
+    std::vector<int32_t> ij(2 * (size_t)ne);
+    std::vector<float> w(ne);
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(ij.data(), ctx->d_A_ij.p, (size_t)ne * sizeof(int2), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(w.data(), ctx->d_A_w.p, (size_t)ne * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    int rc = l3d_cluster_edges(ij.data(), w.data(), ne, n, ctx->cluster_ids.data());
+    if (rc) return rc;
+    std::set<int32_t> uniq(ctx->cluster_ids.begin(), ctx->cluster_ids.end());
+    ctx->cnt.num_clusters = (uint32_t)uniq.size();
+    ctx->stage = 4;
+    return L3D_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// results
+// ------------------------------------------------------------------------------------------
+int l3d_get_counts(l3d_ctx* ctx, l3d_counts* out)
+{
+    if (!ctx || !out) return fail(L3D_ERR_ARG, "NULL argument");
+    *out = ctx->cnt;
+    return L3D_OK;
+}
+int l3d_reset_counters(l3d_ctx* ctx)
+{
+    if (!ctx) return fail(L3D_ERR_ARG, "ctx is NULL");
+    ctx->cnt.gpu_launches = 0;
+    return L3D_OK;
+}
+int l3d_get_timings(l3d_ctx* ctx, float* ms, uint32_t n)
+{
+    if (!ctx || !ms) return fail(L3D_ERR_ARG, "NULL argument");
+    for (uint32_t i = 0; i < n && i < L3D_T_COUNT; ++i) ms[i] = ctx->tm.ms[i];
+    return L3D_OK;
+}
+int l3d_get_pairs(l3d_ctx* ctx, uint32_t* out, uint32_t cap)
+{
+    if (!ctx) return fail(L3D_ERR_ARG, "ctx is NULL");
+    if (cap < ctx->pairs.size()) return fail(L3D_ERR_CAPACITY, "need %zu pairs", ctx->pairs.size());
+    for (size_t p = 0; p < ctx->pairs.size(); ++p) {
+        out[2 * p] = ctx->views[ctx->pairs[p].src].v.cam_id;
+        out[2 * p + 1] = ctx->views[ctx->pairs[p].tgt].v.cam_id;
+    }
+    return L3D_OK;
+}
+
+int l3d_get_view_lists(l3d_ctx* ctx, uint32_t cam_id, int which, uint32_t* row_off, l3d_list_rec* recs, uint64_t cap,
+                       uint64_t* out_count)
+{
+    if (!ctx || !row_off) return fail(L3D_ERR_ARG, "NULL argument");
+    if (ctx->stage < 2) return fail(L3D_ERR_STATE, "l3d_match_images has not run");
+    auto f = ctx->cam2view.find(cam_id);
+    if (f == ctx->cam2view.end()) return fail(L3D_ERR_ARG, "unknown camera %u", cam_id);
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const uint32_t v = f->second;
+    const HostView& hv = ctx->views[v];
+    const uint32_t N = hv.v.num_segs;
+    std::vector<uint32_t> off(N + 1), cnt(N);
+    const ListRec* src = nullptr;
+    uint64_t total = 0;
+    if (which == 0) {
+        if (!ctx->prm.keep_scored) return fail(L3D_ERR_STATE, "keep_scored was not set");
+        CK(cudaMemcpyAsync(off.data(), ctx->d_L_off_all.p + hv.seg_off + v, ((size_t)N + 1) * 4,
+                           cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        src = ctx->d_L_rec.p + ctx->L_base_h[v];
+        total = off[N];
+        for (uint32_t i = 0; i <= N; ++i) row_off[i] = off[i];
+    } else {
+        CK(cudaMemcpyAsync(off.data(), ctx->d_filt_off.p + hv.seg_off, (size_t)N * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(cnt.data(), ctx->d_filt_cnt.p + hv.seg_off, (size_t)N * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        const uint32_t base = N ? off[0] : 0;
+        src = ctx->d_filt_rec.p + base;
+        uint32_t run = 0;
+        for (uint32_t i = 0; i < N; ++i) {
+            row_off[i] = run;
+            run += cnt[i];
+        }
+        row_off[N] = run;
+        total = run;
+    }
+    if (out_count) *out_count = total;
+    if (total > cap) return fail(L3D_ERR_CAPACITY, "need %llu records", (unsigned long long)total);
+    if (total == 0) return L3D_OK;
+    if (!recs) return fail(L3D_ERR_ARG, "recs is NULL");
+    std::vector<ListRec> tmp(total);
+    CK(cudaMemcpyAsync(tmp.data(), src, total * sizeof(ListRec), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    for (uint64_t i = 0; i < total; ++i) {
+        const ListRec& L = tmp[i];
+        l3d_list_rec& o = recs[i];
+        o.tgt_cam = ctx->views[L.tgt_view].v.cam_id;
+        o.tgt_seg = L.tgt_seg;
+        o.overlap_score = L.overlap;
+        o.score3D = L.score;
+        o.depth_p1 = L.d_p1;
+        o.depth_p2 = L.d_p2;
+        o.depth_q1 = L.d_q1;
+        o.depth_q2 = L.d_q2;
+        o.flags = L.flags & 1u;
+    }
+    return L3D_OK;
+}
+
+int l3d_get_entries(l3d_ctx* ctx, l3d_entry* out, uint32_t cap)
+{
+    if (!ctx) return fail(L3D_ERR_ARG, "ctx is NULL");
+    if (ctx->stage < 2) return fail(L3D_ERR_STATE, "l3d_match_images has not run");
+    if (cap < ctx->cnt.num_entries) return fail(L3D_ERR_CAPACITY, "need %u entries", ctx->cnt.num_entries);
+    if (ctx->cnt.num_entries == 0) return L3D_OK;
+    CK(cudaSetDevice(ctx->device));
+    std::vector<EntryDev> e(ctx->S);
+    CK(cudaMemcpyAsync(e.data(), ctx->d_entries.p, (size_t)ctx->S * sizeof(EntryDev), cudaMemcpyDeviceToHost,
+                       ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    uint32_t n = 0;
+    for (uint32_t v = 0; v < ctx->views.size(); ++v) {
+        const HostView& hv = ctx->views[v];
+        for (uint32_t i = 0; i < hv.v.num_segs; ++i) {
+            const EntryDev& E = e[hv.seg_off + i];
+            if (!E.has) continue;
+            l3d_entry& o = out[n++];
+            o.src_cam = hv.v.cam_id;
+            o.src_seg = i;
+            o.tgt_cam = ctx->views[E.tgt_view].v.cam_id;
+            o.tgt_seg = E.tgt_seg;
+            o.overlap_score = E.overlap;
+            o.score3D = E.score;
+            o.depth_p1 = E.d_p1; o.depth_p2 = E.d_p2; o.depth_q1 = E.d_q1; o.depth_q2 = E.d_q2;
+            o.length = E.length;
+            o.pad = 0;
+            memcpy(o.P1, E.P1, 24);
+            memcpy(o.P2, E.P2, 24);
+            memcpy(o.dir, E.dir, 24);
+        }
+    }
+    return L3D_OK;
+}
+
+int l3d_get_edges(l3d_ctx* ctx, int32_t* ij, float* w, uint32_t cap)
+{
+    if (!ctx) return fail(L3D_ERR_ARG, "ctx is NULL");
+    if (ctx->stage < 3) return fail(L3D_ERR_STATE, "l3d_affinity has not run");
+    const uint32_t ne = ctx->cnt.num_edges;
+    if (cap < ne) return fail(L3D_ERR_CAPACITY, "need %u edges", ne);
+    if (!ne) return L3D_OK;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(ij, ctx->d_A_ij.p, (size_t)ne * sizeof(int2), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(w, ctx->d_A_w.p, (size_t)ne * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return L3D_OK;
+}
+
+int l3d_get_local2global(l3d_ctx* ctx, uint32_t* cam_seg, uint32_t cap)
+{
+    if (!ctx) return fail(L3D_ERR_ARG, "ctx is NULL");
+    if (ctx->stage < 3) return fail(L3D_ERR_STATE, "l3d_affinity has not run");
+    const uint32_t n = ctx->cnt.num_local_ids;
+    if (cap < n) return fail(L3D_ERR_CAPACITY, "need %u ids", n);
+    if (!n) return L3D_OK;
+    CK(cudaSetDevice(ctx->device));
+    std::vector<uint32_t> g(n);
+    CK(cudaMemcpyAsync(g.data(), ctx->d_l2g.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (uint32_t i = 0; i < n; ++i) {
+        // global segment -> (cam, seg): views are sorted by seg_off
+        uint32_t lo = 0, hi = (uint32_t)ctx->views.size();
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) / 2;
+            if (ctx->views[mid].seg_off <= g[i]) lo = mid; else hi = mid;
+        }
+        cam_seg[2 * i] = ctx->views[lo].v.cam_id;
+        cam_seg[2 * i + 1] = g[i] - ctx->views[lo].seg_off;
+    }
+    return L3D_OK;
+}
+
+int l3d_get_cluster_ids(l3d_ctx* ctx, int32_t* out, uint32_t cap)
+{
+    if (!ctx) return fail(L3D_ERR_ARG, "ctx is NULL");
+    if (ctx->stage < 4) return fail(L3D_ERR_STATE, "l3d_cluster has not run");
+    if (cap < ctx->cluster_ids.size()) return fail(L3D_ERR_CAPACITY, "need %zu ids", ctx->cluster_ids.size());
+    if (!ctx->cluster_ids.empty()) memcpy(out, ctx->cluster_ids.data(), ctx->cluster_ids.size() * 4);
+    return L3D_OK;
+}
+
+int l3d_get_view_info(l3d_ctx* ctx, uint32_t cam_id, double* C, float* kmm)
+{
+    if (!ctx || !C || !kmm) return fail(L3D_ERR_ARG, "NULL argument");
+    auto f = ctx->cam2view.find(cam_id);
+    if (f == ctx->cam2view.end()) return fail(L3D_ERR_ARG, "unknown camera %u", cam_id);
+    const HostView& hv = ctx->views[f->second];
+    C[0] = hv.cam.C.x; C[1] = hv.cam.C.y; C[2] = hv.cam.C.z;
+    kmm[0] = hv.k;
+    kmm[1] = hv.median_depth;
+    kmm[2] = hv.median_sigma;
+    return L3D_OK;
+}
+
+int l3d_get_med_scene_depth_lines(l3d_ctx* ctx, float* out)
+{
+    if (!ctx || !out) return fail(L3D_ERR_ARG, "NULL argument");
+    *out = ctx->med_scene_depth_lines;
+    return L3D_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// device-math test hooks and the FP32 peak probe
+// ------------------------------------------------------------------------------------------
+int l3d_test_expf(l3d_ctx* ctx, const float* x, float* y, uint32_t n)
+{
+    if (!ctx || !x || !y) return fail(L3D_ERR_ARG, "NULL argument");
+    CK(cudaSetDevice(ctx->device));
+    DevBuf<float> dx, dy;
+    CK(dx.ensure(n));
+    CK(dy.ensure(n));
+    CK(cudaMemcpyAsync(dx.p, x, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->cnt.gpu_launches += launch_test_expf(dx.p, dy.p, n, ctx->stream);
+    CK(cudaMemcpyAsync(y, dy.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return L3D_OK;
+}
+int l3d_test_acos(l3d_ctx* ctx, const double* x, double* y, uint32_t n)
+{
+    if (!ctx || !x || !y) return fail(L3D_ERR_ARG, "NULL argument");
+    CK(cudaSetDevice(ctx->device));
+    DevBuf<double> dx, dy;
+    CK(dx.ensure(n));
+    CK(dy.ensure(n));
+    CK(cudaMemcpyAsync(dx.p, x, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->cnt.gpu_launches += launch_test_acos(dx.p, dy.p, n, ctx->stream);
+    CK(cudaMemcpyAsync(y, dy.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return L3D_OK;
+}
+int l3d_bench_fp32_peak(l3d_ctx* ctx, float* tflops)
+{
+    if (!ctx || !tflops) return fail(L3D_ERR_ARG, "NULL argument");
+    CK(cudaSetDevice(ctx->device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, ctx->device));
+    DevBuf<float> sink;
+    CK(sink.ensure(1 << 20));
+    const int blocks = prop.multiProcessorCount * 8, iters = 4096;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    float best = 0.0f;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(a, ctx->stream);
+        ctx->cnt.gpu_launches += launch_fp32_peak(sink.p, blocks, iters, ctx->stream);
+        cudaEventRecord(b, ctx->stream);
+        CK(cudaStreamSynchronize(ctx->stream));
+        float ms = 0.0f;
+        cudaEventElapsedTime(&ms, a, b);
+        // 16 independent FMA chains per thread, 2 flop per FMA
+        const double flop = (double)blocks * 256.0 * (double)iters * 16.0 * 2.0;
+        if (rep > 0 && ms > 0) best = std::max(best, (float)(flop / (ms * 1e-3) / 1e12));
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    *tflops = best;
+    return L3D_OK;
+}

@@ -1,0 +1,242 @@
+// ctx.h -- the context object behind the C ABI (private to libl3dpp_b200.so)
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <list>
+#include <map>
+#include <set>
+#include <string>
+#include <vector>
+
+#include "../../include/l3dpp_b200.h"
+#include "host_geom.h"
+#include "internal.h"
+
+namespace l3d {
+// launchers defined in the other translation units
+int launch_k1_pairtest(const PairDev*, const K1Cta*, uint32_t, const float4*, const SegDesc*, const float*, uint32_t*,
+                       uint32_t*, float, int, cudaStream_t);
+int k1_rows_per_cta();
+int launch_k2_exact(const PairDev*, const K1Cta*, uint32_t, const float4*, const SegRays*, const double*,
+                    const ViewDev*, const uint32_t*, const uint32_t*, unsigned long long*, FwdRec*, FwdRec*, uint32_t*,
+                    float, int, int, cudaStream_t);
+int launch_k2_compact(const uint32_t*, const uint32_t*, const uint32_t*, uint32_t, const FwdRec*, FwdRec*, uint32_t*,
+                      uint32_t, cudaStream_t);
+int launch_k3_count(const IncDev*, uint32_t, const PairDev*, const uint32_t*, const uint32_t*, uint32_t, uint32_t*,
+                    cudaStream_t);
+int launch_k3_gather(uint32_t, uint32_t, const IncDev*, uint32_t, const PairDev*, const ViewDev*, const SegRays*,
+                     const uint32_t*, const uint32_t*, const FwdRec*, const uint32_t*, const uint32_t*, const uint2*,
+                     const uint32_t*, ListRec*, ListGeo*, uint32_t*, cudaStream_t);
+int launch_k3_score(uint32_t, const uint32_t*, ListRec*, const ListGeo*, FwdRec*, float, float, void*, cudaStream_t);
+int launch_k3_inverse(uint32_t, const uint32_t*, const ListRec*, const ListGeo*, const PairDev*, uint32_t, uint32_t,
+                      uint32_t, uint32_t*, uint32_t*, uint32_t*, uint2*, uint32_t*, uint32_t*, size_t, uint32_t,
+                      cudaStream_t);
+int launch_k3_filter(uint32_t, uint32_t, const ViewDev*, const SegRays*, const uint32_t*, const ListRec*, void*, void*,
+                     uint32_t*, uint32_t*, EntryDev*, uint32_t*, ListRec*, uint32_t*, uint32_t*, uint32_t*, size_t,
+                     cudaStream_t);
+size_t k3_stats_bytes();
+int launch_k4_has(const EntryDev*, uint32_t, uint32_t*, cudaStream_t);
+int launch_k4_median(ViewDev*, uint32_t, const EntryDev*, uint32_t*, cudaStream_t);
+int launch_k4_edges_count(const ViewDev*, const uint32_t*, const EntryDev*, uint32_t, const uint32_t*, const uint32_t*,
+                          const ListRec*, float, float, float*, uint32_t*, unsigned long long*, cudaStream_t);
+int launch_k4_edges_write(const ViewDev*, uint32_t, const uint32_t*, const uint32_t*, const ListRec*, const float*,
+                          const uint32_t*, void*, uint32_t*, cudaStream_t);
+int launch_k4_ids(const void*, uint32_t, const uint32_t*, uint32_t*, uint32_t*, uint32_t*, size_t, int2*, float*,
+                  uint32_t*, cudaStream_t);
+size_t k4_edge_bytes();
+int launch_test_expf(const float*, float*, uint32_t, cudaStream_t);
+int launch_test_acos(const double*, double*, uint32_t, cudaStream_t);
+int launch_fp32_peak(float*, int, int, cudaStream_t);
+int launch_score_prep(const float4*, uint32_t, const float4*, const float2*, const double*, const double*, float,
+                      const uint32_t*, ListRec*, ListGeo*, cudaStream_t);
+int launch_fwd_merge_cnt(const uint32_t*, uint64_t, int, uint32_t, uint32_t*, cudaStream_t);
+int launch_fwd_merge_copy(const uint32_t*, uint64_t, int, uint32_t, const uint32_t*, const uint32_t*, FwdRec*,
+                          cudaStream_t);
+}  // namespace l3d
+
+using namespace l3d;
+
+// ------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------
+int fail(int code, const char* fmt, ...);
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e__ = (call);                                                                        \
+        if (e__ != cudaSuccess)                                                                          \
+            return fail(L3D_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, \
+                        __LINE__);                                                                       \
+    } while (0)
+
+// growable device buffer
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    ~DevBuf() { release(); }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    // capacity >= n; contents are NOT preserved unless keep (number of elements to keep) is given
+    cudaError_t ensure(size_t n, size_t keep = 0, cudaStream_t st = 0)
+    {
+        if (n <= cap) return cudaSuccess;
+        size_t ncap = std::max(n, cap + cap / 2);
+        T* np = nullptr;
+        cudaError_t e = cudaMalloc((void**)&np, std::max<size_t>(ncap, 1) * sizeof(T));
+        if (e != cudaSuccess) return e;
+        if (keep && p) {
+            e = cudaMemcpyAsync(np, p, keep * sizeof(T), cudaMemcpyDeviceToDevice, st);
+            if (e != cudaSuccess) return e;
+            e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) return e;
+        }
+        if (p) cudaFree(p);
+        p = np;
+        cap = ncap;
+        return cudaSuccess;
+    }
+};
+
+struct HostView {
+    l3d_view v;
+    std::vector<float> segs;
+    std::vector<uint32_t> nbrs;
+    hg::Camera cam;
+    float k = 0.0f, median_depth = 0.0f, median_sigma = 0.0f;
+    uint32_t seg_off = 0;
+};
+
+struct HostPair {
+    uint32_t src, tgt;  // view indices
+    uint32_t batch;
+    uint64_t fwd_total = 0;  // forward records of this pair
+    uint32_t rec_start = 0;  // first forward record (canonical layout)
+    bool local = true;       // matched by this shard
+};
+
+struct Batch {
+    uint32_t pair0, pair1;  // [pair0, pair1)
+    uint32_t row0, n_rows;
+    uint32_t cta0, n_ctas;
+    uint64_t mask_words;
+};
+
+struct StageTimer {
+    std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> ev;
+    float ms[L3D_T_COUNT] = {0};
+    void reset()
+    {
+        for (auto& e : ev) {
+            cudaEventDestroy(e.second.first);
+            cudaEventDestroy(e.second.second);
+        }
+        ev.clear();
+        memset(ms, 0, sizeof(ms));
+    }
+    cudaEvent_t begin(int id, cudaStream_t st)
+    {
+        cudaEvent_t a, b;
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+        cudaEventRecord(a, st);
+        ev.push_back({id, {a, b}});
+        return b;
+    }
+    void end(cudaEvent_t b, cudaStream_t st) { cudaEventRecord(b, st); }
+    void collect()
+    {
+        for (auto& e : ev) {
+            float t = 0.0f;
+            if (cudaEventElapsedTime(&t, e.second.first, e.second.second) == cudaSuccess) ms[e.first] += t;
+            cudaEventDestroy(e.second.first);
+            cudaEventDestroy(e.second.second);
+        }
+        ev.clear();
+    }
+};
+
+struct l3d_ctx {
+    int device = 0;
+    cudaStream_t stream = 0;
+    l3d_params prm{};
+    bool have_params = false;
+
+    // host scene
+    std::vector<HostView> views;  // sorted by cam id at commit
+    std::map<uint32_t, uint32_t> cam2view;
+    bool committed = false;
+    uint32_t S = 0;  // total segments
+    hg::V3 translation{0, 0, 0};
+    float two_sigA_sqr = 200.0f, epi_overlap = 0.25f;
+    float med_scene_depth_lines = 0.0f;
+
+    std::vector<HostPair> pairs;
+    std::vector<PairDev> pairs_h;
+    std::vector<Batch> batches;
+    std::vector<K1Cta> ctas_h;
+    std::vector<uint32_t> inc_off_h;  // per view
+    std::vector<IncDev> inc_h;
+    uint32_t total_rows = 0, total_tgt_rows = 0;
+    uint64_t total_fwd = 0;
+    int stage = 0;  // 0: scene, 1: stage12 done, 2: stage3 done, 3: affinity done, 4: clustered
+    bool raw_mode = false;        // l3d_match_lines: cameras given as (RtKinv, C), F given, no translation
+    double F_override[9] = {0};
+
+    // device tables
+    DevBuf<float4> d_segs;
+    DevBuf<uint32_t> d_seg_view;
+    DevBuf<SegDesc> d_desc;
+    DevBuf<SegRays> d_rays;
+    DevBuf<double> d_midray;
+    DevBuf<float> d_view_xb;
+    DevBuf<ViewDev> d_views;
+    DevBuf<PairDev> d_pairs;
+    DevBuf<K1Cta> d_ctas;
+    DevBuf<IncDev> d_inc;
+    // stage 1/2 scratch
+    DevBuf<uint32_t> d_mask, d_cand_cnt, d_cand_off, d_fin_cnt, d_fin_off, d_scan;
+    DevBuf<unsigned long long> d_heap;
+    DevBuf<FwdRec> d_cand_rec, d_fin_rec;
+    // forward store
+    DevBuf<FwdRec> d_fwd_rec;
+    DevBuf<uint32_t> d_fwd_off, d_fwd_cnt;
+    // stage 3
+    DevBuf<uint32_t> d_inv_cnt, d_inv_fill, d_inv_off, d_scan_tmp;
+    DevBuf<uint2> d_inv_ent;
+    DevBuf<uint32_t> d_L_cnt, d_L_off, d_F_cnt, d_F_off;
+    DevBuf<ListRec> d_L_rec;
+    DevBuf<ListGeo> d_L_geo;
+    DevBuf<ListRec> d_filt_rec;
+    DevBuf<uint32_t> d_filt_off, d_filt_cnt, d_small;  // d_small: [0]=filt_total [1]=err [2]=median overflow
+    DevBuf<unsigned char> d_stats;                     // 2 x ScoreStats
+    DevBuf<EntryDev> d_entries;
+    DevBuf<uint32_t> d_has, d_entry_idx;
+    std::vector<uint64_t> L_base_h;  // keep_scored: per-view base into d_L_rec
+    DevBuf<uint32_t> d_L_off_all;    // keep_scored: per-view list offsets, [seg_off + view .. ]
+    // stage 4
+    DevBuf<float> d_filt_sim;
+    DevBuf<uint32_t> d_E_cnt, d_E_off, d_first_touch, d_flags, d_flag_scan, d_l2g;
+    DevBuf<unsigned char> d_edges;
+    DevBuf<int2> d_A_ij;
+    DevBuf<float> d_A_w;
+    DevBuf<unsigned long long> d_tests;
+    // host results
+    std::vector<int32_t> cluster_ids;
+
+    l3d_counts cnt{};
+    StageTimer tm;
+};
+
+
+// shared between ctx.cu and abi.cu
+int refresh_pair_totals(l3d_ctx* ctx);
+int plan_pairs(l3d_ctx* ctx);
+int upload_views(l3d_ctx* ctx);
+int set_params(l3d_ctx* ctx, const l3d_params* params);

@@ -1,0 +1,97 @@
+// host_geom.cpp -- see host_geom.h.  Compile with -ffp-contract=off.
+#include "host_geom.h"
+
+#include <cstring>
+
+namespace l3d {
+namespace hg {
+
+namespace {
+// asin(x)/x = sum c_n x^(2n), c_n = (2n)!/(4^n (n!)^2 (2n+1)), n = 0..29
+const double kAsin[30] = {
+    0x1.0000000000000p+0,  0x1.5555555555555p-3,  0x1.3333333333333p-4,  0x1.6db6db6db6db7p-5,
+    0x1.f1c71c71c71c7p-6,  0x1.6e8ba2e8ba2e9p-6,  0x1.1c4ec4ec4ec4fp-6,  0x1.c99999999999ap-7,
+    0x1.7a87878787878p-7,  0x1.3fde50d79435ep-7,  0x1.12ef3cf3cf3cfp-7,  0x1.df3bd37a6f4dfp-8,
+    0x1.a6863d70a3d71p-8,  0x1.782dda12f684cp-8,  0x1.51ba308d3dcb1p-8,  0x1.31683bdef7bdfp-8,
+    0x1.15ee9d45d1746p-8,  0x1.fcaf8fb6db6dbp-9,  0x1.d3d2a8e0dd67dp-9,  0x1.b026f57b13b14p-9,
+    0x1.90cb77f60c7cep-9,  0x1.750de64d7d05fp-9,  0x1.5c5f56efaaaabp-9,  0x1.464c0950f7d47p-9,
+    0x1.3275586c5f2f0p-9,  0x1.208d3570ae5a6p-9,  0x1.1052bc5fa960ap-9,  0x1.018f963c229bfp-9,
+    0x1.e82be60d9127ep-10, 0x1.cf7dea5b6e830p-10};
+// (-1)^n/(2n+1)! and (-1)^n/(2n)!
+const double kSin[12] = {0x1.0000000000000p+0,   -0x1.5555555555555p-3,  0x1.1111111111111p-7,
+                         -0x1.a01a01a01a01ap-13, 0x1.71de3a556c734p-19,  -0x1.ae64567f544e4p-26,
+                         0x1.6124613a86d09p-33,  -0x1.ae7f3e733b81fp-41, 0x1.952c77030ad4ap-49,
+                         -0x1.2f49b46814157p-57, 0x1.71b8ef6dcf572p-66,  -0x1.761b41316381ap-75};
+const double kCos[12] = {0x1.0000000000000p+0,   -0x1.0000000000000p-1,  0x1.5555555555555p-5,
+                         -0x1.6c16c16c16c17p-10, 0x1.a01a01a01a01ap-16,  -0x1.27e4fb7789f5cp-22,
+                         0x1.1eed8eff8d898p-29,  -0x1.93974a8c07c9dp-37, 0x1.ae7f3e733b81fp-45,
+                         -0x1.6827863b97d97p-53, 0x1.e542ba4020225p-62,  -0x1.0ce396db7f853p-70};
+const double kPi = 0x1.921fb54442d18p+1, kPi2 = 0x1.921fb54442d18p+0, kPi4 = 0x1.921fb54442d18p-1;
+
+double horner(const double* c, int n, double z)
+{
+    double s = c[n - 1];
+    for (int i = n - 2; i >= 0; --i) s = s * z + c[i];
+    return s;
+}
+}  // namespace
+
+double det_acos(double x)
+{
+    const double ax = std::fabs(x);
+    if (!(ax <= 1.0)) return NAN;
+    if (ax <= 0.5) return kPi2 - x * horner(kAsin, 30, x * x);
+    const double z = (1.0 - ax) * 0.5;
+    const double a = 2.0 * (std::sqrt(z) * horner(kAsin, 30, z));
+    return x > 0.0 ? a : kPi - a;
+}
+
+double det_sin(double x)
+{
+    const double xr = x > kPi2 ? kPi - x : x;
+    if (xr <= kPi4) return xr * horner(kSin, 12, xr * xr);
+    const double y = kPi2 - xr;
+    return horner(kCos, 12, y * y);
+}
+
+void Camera::init(const double* K9, const double* R9, const double* t3)
+{
+    std::memcpy(K.m, K9, sizeof(K.m));
+    std::memcpy(R.m, R9, sizeof(R.m));
+    t = V3{t3[0], t3[1], t3[2]};
+    pp = V3{K.m[2], K.m[5], 1.0};
+    Kinv = inverse(K);
+    Rt = transpose(R);
+    RtKinv = matmul(Rt, Kinv);
+    C = mul(Rt, V3{t.x * -1.0, t.y * -1.0, t.z * -1.0});
+}
+
+void Camera::translate(const V3& tv)
+{
+    C = C + tv;
+    const V3 rc = mul(R, C);
+    t = V3{-rc.x, -rc.y, -rc.z};
+}
+
+float Camera::spatial_regularizer(float r) const
+{
+    const V3 pps = V3{pp.x + (double)r, pp.y + 0.0, pp.z + 0.0};
+    const V3 a = normalized(mul(RtKinv, pp)), b = normalized(mul(RtKinv, pps));
+    const double alpha = det_acos(std::fmin(std::fmax(dot(a, b), -1.0), 1.0));
+    return (float)det_sin(alpha);
+}
+
+M3 fundamental(const Camera& s, const Camera& tg)
+{
+    const M3 R = matmul(tg.R, transpose(s.R));
+    const V3 tt = tg.t - mul(R, s.t);
+    M3 T;
+    T.m[0] = 0.0;   T.m[1] = -tt.z; T.m[2] = tt.y;
+    T.m[3] = tt.z;  T.m[4] = 0.0;   T.m[5] = -tt.x;
+    T.m[6] = -tt.y; T.m[7] = tt.x;  T.m[8] = 0.0;
+    const M3 E = matmul(T, R);
+    return matmul(matmul(inverse(transpose(tg.K)), E), inverse(s.K));
+}
+
+}  // namespace hg
+}  // namespace l3d

@@ -1,0 +1,120 @@
+// internal.h -- device-side table layouts and kernel launchers shared by the translation units of
+// libl3dpp_b200.so.  Data layout in HBM:
+//   segs      float4[S]        x1,y1,x2,y2 of every 2-D segment, views concatenated       16 B/seg
+//   desc      SegDesc[S]       K1 target-side descriptor (1-D parametrisation)           32 B/seg
+//   rays      SegRays[S]       normalised viewing rays of both endpoints (double)        48 B/seg
+//   midray    double[3][S]     normalised ray through the 2-D midpoint (AoS double3)      24 B/seg
+//   views     ViewDev[V]
+//   pairs     PairDev[P]       matched view pairs in reference order (src asc, tgt asc)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace l3d {
+
+struct __align__(16) SegDesc {
+    float q1x, q1y, ux, uy;  // first endpoint and unit direction of the segment
+    float L, slo, shi, g;    // length, admissible parameter interval (image bounds), guard term
+};
+static_assert(sizeof(SegDesc) == 32, "SegDesc must be 32 bytes");
+
+struct SegRays {
+    double r1[3], r2[3];
+};
+
+struct ViewDev {
+    double C[3];
+    double RtKinv[9];
+    float k;
+    float median_depth;
+    uint32_t seg_off, n_seg;
+    uint32_t cam_id;
+    float xb;  // max |x1|+|y1| over the view's segments (K1 guard)
+    uint32_t order, pad;
+};
+
+struct PairDev {
+    double F[9];
+    uint32_t src_view, tgt_view;
+    uint32_t src_off, n_src;
+    uint32_t tgt_off, n_tgt;
+    uint32_t row_base;   // global row index of (pair,0): prefix sum of n_src over pairs
+    uint32_t tgt_base;   // prefix sum of n_tgt over pairs (inverse-match CSR rows)
+    uint32_t words;      // ceil(n_tgt/32)
+    uint32_t emit_inverse;  // tgt view is processed after src view (line3D.cc:1994)
+    uint64_t mask_base;  // word offset of this pair's bit mask inside the batch buffer
+    uint32_t batch_row0; // first row of the batch this pair belongs to
+    uint32_t pad;
+};
+
+// forward match record, 32 B (matches_ entries produced by matching, line3D.cc:1169-1181)
+struct __align__(16) FwdRec {
+    uint32_t c;       // tgt segment
+    float overlap;
+    float d_p1, d_p2, d_q1, d_q2;
+    float score;
+    uint32_t flags;
+};
+static_assert(sizeof(FwdRec) == 32, "FwdRec must be 32 bytes");
+
+// list entry at scoring / after filtering, 40 B
+struct ListRec {
+    uint32_t tgt_view, tgt_seg;
+    float overlap, score;
+    float d_p1, d_p2, d_q1, d_q2;
+    uint32_t flags;    // bit0 orientation flag (inverse matches), bit1: inverse
+    uint32_t src_idx;  // forward-record index this entry came from (score write-back), or ~0u
+};
+static_assert(sizeof(ListRec) == 40, "ListRec must be 40 bytes");
+
+// per-entry geometry staged for scoring, 48 B
+struct ListGeo {
+    double dir[3];
+    float reg1, reg2;
+    float length;
+    uint32_t run;  // 1 if this entry starts a new target-camera run
+    uint32_t pad0, pad1;
+};
+
+// best hypothesis of a segment (estimated_position3D_ row), indexed by global segment id
+struct EntryDev {
+    double P1[3], P2[3], dir[3];
+    float length;
+    uint32_t tgt_view, tgt_seg;
+    float overlap, score;
+    float d_p1, d_p2, d_q1, d_q2;
+    uint32_t has;  // 1 if the segment has a best match with score > 0.75
+};
+
+struct K1Cta {
+    uint32_t pair, tile;
+};
+
+struct IncDev {  // one incident pair of a view, in list order
+    uint32_t pair;
+    uint32_t inverse;  // 1: this view is the pair's target (entries come from the inverse CSR)
+};
+
+// ---------------- launchers (each returns the number of kernels launched) ----------------
+int launch_scan_u32(const uint32_t* in, uint32_t* out, uint32_t n, uint32_t* scratch,
+                    size_t scratch_words, cudaStream_t st);
+size_t scan_scratch_words(uint32_t n);
+
+int launch_k0_prep(const float4* segs, const uint32_t* seg_view, const ViewDev* views, uint32_t S,
+                   int max_image_width, SegDesc* desc, SegRays* rays, double* midray, float* view_xb,
+                   cudaStream_t st);
+
+int launch_k1_pairtest(const PairDev* pairs, const K1Cta* ctas, uint32_t n_ctas, const float4* segs,
+                       const SegDesc* desc, const float* view_xb, uint32_t* mask, uint32_t* cand_cnt,
+                       float thr, int filter_mode, cudaStream_t st);
+
+int launch_k2_exact(const PairDev* pairs, const uint32_t* row_pair_lut, uint32_t pair0, uint32_t n_pairs,
+                    uint32_t n_rows, const float4* segs, const SegRays* rays, const double* midray,
+                    const ViewDev* views, const uint32_t* mask, const uint32_t* cand_off,
+                    unsigned long long* heap, FwdRec* cand_rec, FwdRec* fin_rec, uint32_t* fin_cnt,
+                    float thr, int knn, int max_image_width, cudaStream_t st);
+
+int launch_k2_compact(const uint32_t* cand_off, const uint32_t* fin_cnt, const uint32_t* fwd_off,
+                      const FwdRec* fin_rec, FwdRec* fwd_rec, uint32_t n_rows, cudaStream_t st);
+
+}  // namespace l3d

@@ -1,0 +1,166 @@
+// misc.cu -- device-math test hooks, the FP32 peak probe and the list preparation of
+// l3d_score_matches (exact TU).
+#include "detmath.cuh"
+#include "exact.cuh"
+#include "internal.h"
+
+namespace l3d {
+
+__global__ void test_expf_kernel(const float* __restrict__ x, float* __restrict__ y, uint32_t n)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = det_expf(x[i]);
+}
+__global__ void test_acos_kernel(const double* __restrict__ x, double* __restrict__ y, uint32_t n)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = det_acos(x[i]);
+}
+
+int launch_test_expf(const float* x, float* y, uint32_t n, cudaStream_t st)
+{
+    if (!n) return 0;
+    test_expf_kernel<<<(n + 255) / 256, 256, 0, st>>>(x, y, n);
+    return 1;
+}
+int launch_test_acos(const double* x, double* y, uint32_t n, cudaStream_t st)
+{
+    if (!n) return 0;
+    test_acos_kernel<<<(n + 255) / 256, 256, 0, st>>>(x, y, n);
+    return 1;
+}
+
+// 16 independent FFMA chains per thread: measures the FP32 pipe peak the K1 roofline divides by
+__global__ void __launch_bounds__(256) fp32_peak_kernel(float* __restrict__ sink, int iters)
+{
+    float a[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = 1.0f + 1e-3f * (float)(threadIdx.x + i);
+    const float b = 0.999f, c = 1e-4f;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) a[i] = __fmaf_rn(a[i], b, c);
+    }
+    float s = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += a[i];
+    if (s == 12345.678f) sink[(blockIdx.x * blockDim.x + threadIdx.x) & ((1 << 20) - 1)] = s;
+}
+int launch_fp32_peak(float* sink, int blocks, int iters, cudaStream_t st)
+{
+    fp32_peak_kernel<<<blocks, 256, 0, st>>>(sink, iters);
+    return 1;
+}
+
+// list preparation for l3d_score_matches: one thread per source segment walks its range
+// (src/line3D.cc:1582-1623 packs the same data on the host)
+__global__ void __launch_bounds__(128) score_prep_kernel(const float4* __restrict__ lines, uint32_t n_lines,
+                                                         const float4* __restrict__ matches,
+                                                         const float2* __restrict__ regs_tgt,
+                                                         const double* __restrict__ RtKinv,
+                                                         const double* __restrict__ C, float k,
+                                                         const uint32_t* __restrict__ off,
+                                                         ListRec* __restrict__ L_rec, ListGeo* __restrict__ L_geo)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_lines) return;
+    const uint32_t b = off[i], e = off[i + 1];
+    if (b == e) return;
+    const D3 Cc = d3(C[0], C[1], C[2]);
+    uint32_t prev = 0xffffffffu;
+    for (uint32_t z = b; z < e; ++z) {
+        const float4 m = matches[z];
+        const uint32_t seg = (uint32_t)m.x;
+        const uint32_t cam = (uint32_t)m.y;
+        ListRec L;
+        L.tgt_view = cam;
+        L.tgt_seg = 0;
+        L.overlap = 0.0f;
+        L.score = 0.0f;
+        L.d_p1 = m.z;
+        L.d_p2 = m.w;
+        L.d_q1 = L.d_q2 = 0.0f;
+        L.flags = 0;
+        L.src_idx = 0xffffffffu;
+        ListGeo G;
+        D3 dir = d3(0, 0, 0);
+        float len = 0.0f;
+        if (seg < n_lines) {
+            const float4 sg = lines[seg];
+            const D3 r1 = normalized3(mul33(RtKinv, d3((double)sg.x, (double)sg.y, 1.0)));
+            const D3 r2 = normalized3(mul33(RtKinv, d3((double)sg.z, (double)sg.w, 1.0)));
+            const D3 P1 = add3(Cc, scale3(r1, (double)m.z));
+            const D3 P2 = add3(Cc, scale3(r2, (double)m.w));
+            len = (float)norm3(sub3(P1, P2));
+            if (len > 1e-12) dir = normalized3(sub3(P2, P1));
+            else len = 0.0f;
+        }
+        const float sig1 = fm(m.z, k), sig2 = fm(m.w, k);
+        const float2 rt = regs_tgt[z];
+        G.reg1 = fm(0.5f, fa(fm(fm(2.0f, sig1), sig1), fm(fm(2.0f, rt.x), rt.x)));
+        G.reg2 = fm(0.5f, fa(fm(fm(2.0f, sig2), sig2), fm(fm(2.0f, rt.y), rt.y)));
+        G.dir[0] = dir.x; G.dir[1] = dir.y; G.dir[2] = dir.z;
+        G.length = len;
+        G.run = (cam != prev) ? 1u : 0u;
+        G.pad0 = G.pad1 = 0;
+        prev = cam;
+        L_rec[z] = L;
+        L_geo[z] = G;
+    }
+}
+
+int launch_score_prep(const float4* lines, uint32_t n_lines, const float4* matches, const float2* regs_tgt,
+                      const double* RtKinv, const double* C, float k, const uint32_t* off, ListRec* L_rec,
+                      ListGeo* L_geo, cudaStream_t st)
+{
+    if (!n_lines) return 0;
+    score_prep_kernel<<<(n_lines + 127) / 128, 128, 0, st>>>(lines, n_lines, matches, regs_tgt, RtKinv, C, k, off,
+                                                              L_rec, L_geo);
+    return 1;
+}
+
+// merge of per-shard forward lists into the canonical layout (multi-GPU import)
+__global__ void __launch_bounds__(256) fwd_merge_cnt_kernel(const uint32_t* __restrict__ blobs, uint64_t stride_words,
+                                                            int world, uint32_t n_rows, uint32_t* __restrict__ cnt)
+{
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rows) return;
+    uint32_t s = 0;
+    for (int w = 0; w < world; ++w) s += blobs[(size_t)w * stride_words + r];
+    cnt[r] = s;
+}
+__global__ void __launch_bounds__(256) fwd_merge_copy_kernel(const uint32_t* __restrict__ blobs, uint64_t stride_words,
+                                                             int world, uint32_t n_rows,
+                                                             const uint32_t* __restrict__ shard_off,
+                                                             const uint32_t* __restrict__ fwd_off,
+                                                             FwdRec* __restrict__ fwd_rec)
+{
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rows) return;
+    const uint32_t rows_pad = (n_rows + 7u) & ~7u;  // records start 32-byte aligned after the counts
+    for (int w = 0; w < world; ++w) {
+        const uint32_t* base = blobs + (size_t)w * stride_words;
+        const uint32_t n = base[r];
+        if (!n) continue;
+        const FwdRec* src = (const FwdRec*)(base + rows_pad) + shard_off[(size_t)w * (n_rows + 1) + r];
+        FwdRec* dst = fwd_rec + fwd_off[r];
+        for (uint32_t i = 0; i < n; ++i) dst[i] = src[i];
+    }
+}
+int launch_fwd_merge_cnt(const uint32_t* blobs, uint64_t stride_words, int world, uint32_t n_rows, uint32_t* cnt,
+                         cudaStream_t st)
+{
+    if (!n_rows) return 0;
+    fwd_merge_cnt_kernel<<<(n_rows + 255) / 256, 256, 0, st>>>(blobs, stride_words, world, n_rows, cnt);
+    return 1;
+}
+int launch_fwd_merge_copy(const uint32_t* blobs, uint64_t stride_words, int world, uint32_t n_rows,
+                          const uint32_t* shard_off, const uint32_t* fwd_off, FwdRec* fwd_rec, cudaStream_t st)
+{
+    if (!n_rows) return 0;
+    fwd_merge_copy_kernel<<<(n_rows + 255) / 256, 256, 0, st>>>(blobs, stride_words, world, n_rows, shard_off, fwd_off,
+                                                                 fwd_rec);
+    return 1;
+}
+
+}  // namespace l3d

@@ -1,0 +1,220 @@
+/* l3dpp_b200.h -- C ABI of libl3dpp_b200.so
+ *
+ * B200-native (sm_100a) implementation of the Line3D++ multi-view 2-D segment
+ * matching -> two-view triangulation -> multi-view scoring -> affinity-matrix stage that
+ * BTREE-C802/3DLine-SLAM runs inside Line3D::matchImages / Line3D::reconstruct3Dlines.
+ *
+ * This header is the drop-in boundary.  Every entry point names the reference interface it
+ * replaces (file:line relative to the reference tree).  Plain pointers and sizes only; all
+ * functions return 0 on success or a negative code (l3d_last_error() has the text).  There is no
+ * CPU fallback: without a CUDA device every compute call fails with L3D_ERR_CUDA.
+ *
+ * Two levels:
+ *   (1) cudawrapper level -- l3d_match_lines / l3d_score_matches take HOST buffers exactly like
+ *       the DataArray arguments of L3DPP::match_lines_GPU / score_matches_GPU
+ *       (include/cudawrapper.h:63-81) and are blocking, like DataArray::upload()
+ *       (include/dataArray.h:199-218).
+ *   (2) Line3D level -- l3d_scene_* / l3d_match_images / l3d_affinity keep every table resident in
+ *       HBM and run the whole of Line3D::computeMatches (src/line3D.cc:846-930) and
+ *       Line3D::computingAffinityMatrix (src/line3D.cc:2275-2402) on the device.
+ */
+#ifndef L3DPP_B200_H_
+#define L3DPP_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define L3D_OK 0
+#define L3D_ERR_ARG (-1)
+#define L3D_ERR_CUDA (-2)
+#define L3D_ERR_STATE (-3)
+#define L3D_ERR_CAPACITY (-4)
+
+typedef struct l3d_ctx l3d_ctx;
+
+/* One potential match: the POD image of L3DPP::Match (include/commons.h:197-219). */
+typedef struct {
+    uint32_t src_cam, src_seg, tgt_cam, tgt_seg;
+    float overlap_score, score3D;
+    float depth_p1, depth_p2, depth_q1, depth_q2;
+    uint32_t flags; /* bit0 = match_orientation_ */
+} l3d_match;
+
+/* One list entry of matches_[cam][seg] as returned by l3d_get_view_lists (36 bytes). */
+typedef struct {
+    uint32_t tgt_cam, tgt_seg;
+    float overlap_score, score3D;
+    float depth_p1, depth_p2, depth_q1, depth_q2;
+    uint32_t flags;
+} l3d_list_rec;
+
+/* One row of estimated_position3D_ (src/line3D.cc:1957-1967): best match + its 3-D segment. */
+typedef struct {
+    uint32_t src_cam, src_seg, tgt_cam, tgt_seg;
+    float overlap_score, score3D;
+    float depth_p1, depth_p2, depth_q1, depth_q2;
+    float length;
+    uint32_t pad;
+    double P1[3], P2[3], dir[3];
+} l3d_entry;
+
+/* Arguments of Line3D::addImage (src/line3D.cc:117-121) with the image reduced to its size. */
+typedef struct {
+    uint32_t cam_id;
+    uint32_t width, height;
+    uint32_t num_segs;
+    double K[9], R[9], t[3]; /* row-major; camera model x = K [R|t] X */
+    float median_depth;
+} l3d_view;
+
+/* Arguments of Line3D::matchImages (src/line3D.cc:496-498) + the constructor's max_img_width. */
+typedef struct {
+    float sigma_p;
+    float sigma_a;
+    uint32_t num_neighbors;
+    float epipolar_overlap;
+    int32_t knn;
+    float const_reg_depth;
+    int32_t max_image_width; /* Line3D::max_image_width_, used by the bounds test line3D.cc:1142-1148 */
+    int32_t filter_mode;     /* 0: FP32 guard-banded pre-filter (default); 1: none (every pair exact) */
+    int32_t keep_scored;     /* 1: keep the pre-filter lists of every view (parity tests) */
+    int32_t shard_rank;      /* multi-GPU: this process matches pairs p with p % shard_world == rank */
+    int32_t shard_world;     /* 0 or 1: no sharding */
+} l3d_params;
+
+typedef struct {
+    uint64_t pair_tests;      /* sum over matched pairs of N_src * N_tgt (this shard) */
+    uint64_t candidates;      /* survivors of the FP32 pre-filter (this shard) */
+    uint64_t forward_matches; /* matches kept after kNN + orientation filter (all shards once gathered) */
+    uint64_t scored_entries;  /* sum of list lengths at scoring time */
+    uint64_t sim_evals;       /* sibling pairs visited by the scoring kernel */
+    uint64_t filtered_entries;
+    uint32_t num_views, num_pairs, num_pairs_local;
+    uint32_t num_entries, num_edges, num_local_ids, num_clusters;
+    uint32_t gpu_launches;    /* kernels launched since the last l3d_reset_counters */
+} l3d_counts;
+
+/* indices into the array filled by l3d_get_timings (milliseconds, CUDA events on the ctx stream) */
+enum {
+    L3D_T_PREP = 0,    /* per-segment descriptors + rays */
+    L3D_T_PAIRTEST,    /* K1: FP32 pair test + compaction */
+    L3D_T_EXACT,       /* K2: exact re-test, triangulation, kNN, orientation filter */
+    L3D_T_SCORE,       /* K3: list assembly + scoring wavefront + inverse matches + filtering */
+    L3D_T_AFFINITY,    /* K4 */
+    L3D_T_TOTAL,
+    L3D_T_K1_KERNEL,   /* sum of K1 kernel launches alone */
+    L3D_T_K1_LAUNCHES,
+    L3D_T_COUNT
+};
+
+const char* l3d_last_error(void);
+const char* l3d_version(void);
+
+/* replaces: implicit CUDA context of the reference GPU path. device < 0: current device. */
+int l3d_ctx_create(l3d_ctx** out, int device);
+void l3d_ctx_destroy(l3d_ctx* ctx);
+/* All kernels of ctx are launched on `cuda_stream` (a cudaStream_t; NULL = legacy default). */
+int l3d_ctx_set_stream(l3d_ctx* ctx, void* cuda_stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (1) cudawrapper level, host buffers in / host buffers out, blocking
+ * ------------------------------------------------------------------------------------------ */
+
+/* replaces L3DPP::match_lines_GPU (include/cudawrapper.h:63-71, call site src/line3D.cc:1257-1261)
+ * with the results of Line3D::matchingCPU (src/line3D.cc:1097-1212): for every source segment
+ * the <= kNN matches with the highest epipolar overlap (all of them if kNN <= 0) that pass the
+ * bounds test and have four positive triangulated depths, in the order the reference appends them
+ * to matches_[src][r] (rows ascending, priority-queue pop order inside a row).
+ * lines_*: n x (x1,y1,x2,y2) float, F/RtKinv_*: row-major 3x3 double, C_*: double[3].
+ * out_row_off: n_src+1 offsets into out (may be NULL). Returns L3D_ERR_CAPACITY if cap is too small
+ * (*out_count then holds the required size). */
+int l3d_match_lines(l3d_ctx* ctx, const float* lines_src, uint32_t n_src, const float* lines_tgt,
+                    uint32_t n_tgt, const double* F, const double* RtKinv_src,
+                    const double* RtKinv_tgt, const double* C_src, const double* C_tgt,
+                    uint32_t src_cam, uint32_t tgt_cam, float epi_overlap, int32_t knn,
+                    int32_t max_image_width, int32_t filter_mode, l3d_match* out, uint64_t cap,
+                    uint64_t* out_count, uint32_t* out_row_off);
+
+/* replaces L3DPP::score_matches_GPU (include/cudawrapper.h:74-81, call site src/line3D.cc:1633-1635)
+ * with the arithmetic of Line3D::scoringCPU's new-match branch (src/line3D.cc:1513-1547):
+ * matches[i] = {srcSeg, tgtCam, depth_p1, depth_p2} (float4, src/line3D.cc:1616-1617),
+ * ranges[s] = {first,last} inclusive or {-1,-1} (int2, src/line3D.cc:1582-1596),
+ * regularizers_tgt[i] = {sigma_tgt(P1), sigma_tgt(P2)} (float2, src/line3D.cc:1619-1620),
+ * scores[i] receives score3D_. */
+int l3d_score_matches(l3d_ctx* ctx, const float* lines, uint32_t n_lines, const float* matches,
+                      uint32_t n_matches, const int32_t* ranges, float* scores,
+                      const float* regularizers_tgt, const double* RtKinv, const double* C,
+                      float two_sigA_sqr, float k, float min_similarity);
+
+/* ------------------------------------------------------------------------------------------
+ * (2) Line3D level, tables resident in HBM
+ * ------------------------------------------------------------------------------------------ */
+
+/* replaces Line3D::addImage + UpdataImage bookkeeping (src/line3D.cc:117-227, 433-487) for a batch
+ * of views: begin, add every active view (explicit neighbour lists = the
+ * neighbors_by_worldpoints=false path, src/line3D.cc:604-616), commit (uploads the tables). */
+int l3d_scene_begin(l3d_ctx* ctx);
+int l3d_scene_add_view(l3d_ctx* ctx, const l3d_view* view, const float* segs_xyxy,
+                       const uint32_t* neighbor_cam_ids, uint32_t num_neighbors);
+int l3d_scene_commit(l3d_ctx* ctx);
+
+/* replaces Line3D::matchImages (src/line3D.cc:496-640): translate(), spatial regularisers,
+ * computeMatches() (matching, orientation filter, scoring, inverse matches, filtering) and the
+ * estimated_position3D_ table, all on the device.  Stage-wise variants for multi-GPU runs:
+ * l3d_match_stage12 runs matching only (this shard's pairs), l3d_export/import_forward move the
+ * forward-match lists between processes, l3d_match_stage3 runs the scoring wavefront. */
+int l3d_match_images(l3d_ctx* ctx, const l3d_params* params);
+int l3d_match_stage12(l3d_ctx* ctx, const l3d_params* params);
+int l3d_match_stage3(l3d_ctx* ctx);
+
+/* replaces Line3D::computingAffinityMatrix (src/line3D.cc:2275-2402) incl. the median scene depth
+ * (src/line3D.cc:2074-2091): builds A_ (edge list with first-touch local IDs) on the device. */
+int l3d_affinity(l3d_ctx* ctx);
+
+/* Unchanged consumer, provided for convenience: Felzenszwalb-Huttenlocher clustering of A_
+ * exactly as L3DPP::performClustering (src/clustering.cc:7-48, include/universe.h:59-117), on
+ * the host. */
+int l3d_cluster(l3d_ctx* ctx);
+/* stand-alone form of the same routine (edges: ne x (i,j), weights: ne, out: n root ids) */
+int l3d_cluster_edges(const int32_t* edges_ij, const float* weights, uint32_t ne, uint32_t n,
+                      int32_t* out_root);
+
+/* results (host pointers) */
+int l3d_get_counts(l3d_ctx* ctx, l3d_counts* out);
+int l3d_reset_counters(l3d_ctx* ctx);
+int l3d_get_timings(l3d_ctx* ctx, float* ms, uint32_t n);
+int l3d_get_pairs(l3d_ctx* ctx, uint32_t* src_tgt_cam_ids, uint32_t cap_pairs);
+/* which: 0 = lists as they were right after scoring (needs keep_scored), 1 = filtered lists
+ * (= matches_[cam] after filterMatches). row_off: num_segs+1. Returns L3D_ERR_CAPACITY with the
+ * needed record count in *out_count if cap is too small. */
+int l3d_get_view_lists(l3d_ctx* ctx, uint32_t cam_id, int which, uint32_t* row_off,
+                       l3d_list_rec* recs, uint64_t cap, uint64_t* out_count);
+int l3d_get_entries(l3d_ctx* ctx, l3d_entry* out, uint32_t cap);
+int l3d_get_edges(l3d_ctx* ctx, int32_t* edges_ij, float* weights, uint32_t cap);
+int l3d_get_local2global(l3d_ctx* ctx, uint32_t* cam_seg, uint32_t cap);
+int l3d_get_cluster_ids(l3d_ctx* ctx, int32_t* out, uint32_t cap);
+/* info[0..2] = camera centre C (current, untranslated), kmm = {k, median_depth, median_sigma} */
+int l3d_get_view_info(l3d_ctx* ctx, uint32_t cam_id, double* C, float* kmm);
+int l3d_get_med_scene_depth_lines(l3d_ctx* ctx, float* out);
+
+/* Multi-GPU plumbing (one process per GPU; the collective itself is torch.distributed / NCCL):
+ * forward-match lists of this shard as one flat device/host blob of 32-byte records preceded by
+ * per-row counts; `device_ptr` != 0 means the pointers are device pointers. */
+int l3d_forward_blob_size(l3d_ctx* ctx, uint64_t* bytes);
+int l3d_export_forward(l3d_ctx* ctx, void* dst, uint64_t cap_bytes, int device_ptr);
+int l3d_import_forward(l3d_ctx* ctx, const void* src, uint64_t bytes, int shard_rank, int device_ptr);
+
+/* deterministic device math exposed for parity tests (n values, host pointers) */
+int l3d_test_expf(l3d_ctx* ctx, const float* x, float* y, uint32_t n);
+int l3d_test_acos(l3d_ctx* ctx, const double* x, double* y, uint32_t n);
+/* peak-FP32 micro-benchmark used by bench.py for the roofline denominator (TFLOP/s) */
+int l3d_bench_fp32_peak(l3d_ctx* ctx, float* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* L3DPP_B200_H_ */

@@ -1,0 +1,48 @@
+"""CPU: the C-ABI library builds, loads and exports every symbol include/l3dpp_b200.h declares;
+without a CUDA device the product refuses to run (no CPU fallback)."""
+import ctypes as C
+import os
+
+import pytest
+
+from conftest import has_gpu
+
+
+def test_library_exports_every_declared_symbol(api):
+    api.build()
+    assert os.path.exists(api.LIB_PATH)
+    names = api.declared_symbols()
+    assert len(names) >= 25, names
+    L = C.CDLL(api.LIB_PATH)
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+
+
+def test_version_and_error_strings(api):
+    L = api.lib()
+    assert b"sm_100a" in L.l3d_version()
+    assert isinstance(L.l3d_last_error(), bytes)
+
+
+@pytest.mark.skipif(has_gpu(), reason="only meaningful on a box without a GPU")
+def test_no_cpu_fallback(api):
+    with pytest.raises(api.L3DError) as e:
+        api.Context()
+    assert "no CPU fallback" in str(e.value) or "CUDA" in str(e.value)
+
+
+def test_host_clustering_matches_oracle_kat(api, oracle):
+    import numpy as np
+    rng = np.random.default_rng(5)
+    n = 60
+    ij = rng.integers(0, n, size=(400, 2)).astype(np.int32)
+    ij = ij[ij[:, 0] != ij[:, 1]]
+    w = (0.5 + 0.5 * rng.random(len(ij))).astype(np.float32)
+    w[::7] = w[3]  # ties exercise the stable sort
+    both = np.concatenate([ij, ij[:, ::-1]], axis=1).reshape(-1, 2)  # (i,j),(j,i) like A_
+    wb = np.repeat(w, 2)
+    got = api.cluster_edges(both, wb, n)
+    exp = np.zeros(n, dtype=np.int32)
+    m = oracle.lib().orc_kat_cluster(both.ctypes.data, wb.ctypes.data, len(wb), n, exp.ctypes.data)
+    assert m == n
+    assert (got == exp).all()
