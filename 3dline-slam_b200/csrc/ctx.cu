@@ -637,11 +637,7 @@ int l3d_match_images(l3d_ctx* ctx, const l3d_params* params)
 {
     int rc = l3d_match_stage12(ctx, params);
     if (rc) return rc;
-    float keep_ms[L3D_T_COUNT];
-    memcpy(keep_ms, ctx->tm.ms, sizeof(keep_ms));
-    rc = l3d_match_stage3(ctx);
-    for (int i = 0; i < L3D_T_COUNT; ++i) ctx->tm.ms[i] += keep_ms[i];
-    return rc;
+    return l3d_match_stage3(ctx);  // stage timers keep accumulating until the next stage12
 }
 
 // ------------------------------------------------------------------------------------------

@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""bench.py -- segment-pair tests/s and views/s of the Line3D++ matching -> scoring -> affinity
+path on B200 (BASELINE.json metric), with the K1 roofline, the CPU baseline and the end-to-end
+number.  One "step" = one full pass of stages 1-4 (l3d_match_images + l3d_affinity) over one
+synthetic scene.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2]
+
+N=1: BASELINE config[1] (50 views x 1000 segments x 10 neighbours, 640x480).  N>1 (torchrun, one
+process per GPU): the scene grows with N (50*N views, weak scaling); pairs are sharded over the
+ranks for stages 1-2, the forward-match lists are all-gathered with NCCL, stages 3-4 run replicated
+on every rank.
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np
+
+FLOP_PER_TEST = 114.0  # algorithmic FP32 flop of one segment-pair test
+
+
+def make_workload(scene_mod, name, n_gpus):
+    if name == "c2":
+        return scene_mod.make_scene("c2", n_views=50 * n_gpus), "c2" if n_gpus == 1 else "c2x%d" % n_gpus
+    if name == "c4":
+        return scene_mod.make_scene("c4"), "c4"
+    if name == "tiny":
+        return scene_mod.make_scene("tiny"), "tiny"
+    raise SystemExit("unknown workload %r" % name)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def run_cpu_oracle(scene, threads=0, snapshot=False):
+    import oracle_py
+    t0 = time.perf_counter()
+    o = oracle_py.run_scene(scene, threads=threads, snapshot=snapshot)
+    dt = time.perf_counter() - t0
+    tests = o.pair_tests()
+    tm = o.timers()
+    cores = oracle_py.lib().orc_max_threads()
+    o.close()
+    return dict(seconds=dt, tests=tests, timers=tm, cores=cores)
+
+
+def bench_reference(args, scene_mod):
+    """--impl reference: the reference's own CPU implementation of the path = the oracle port
+    (the reference cannot be compiled here: no Eigen/Boost/OpenCV), all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    scene, wname = make_workload(scene_mod, args.workload, 1)
+    times, tests, cores = [], 0, 1
+    for i in range(args.warmup + args.steps):
+        r = run_cpu_oracle(scene)
+        tests, cores = r["tests"], r["cores"]
+        if i >= args.warmup:
+            times.append(r["timers"]["match_images"] + r["timers"]["reconstruct"])
+    T = float(np.sum(times))
+    value = tests * len(times) / T
+    line = {
+        "impl": "reference", "metric": "segment_pair_tests_per_s", "value": value, "unit": "tests/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * T / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wname, "views": scene.num_views, "segments_per_view": scene.views[0].segs.shape[0],
+                   "neighbours": scene.params["num_neighbors"]},
+        "views_per_s": scene.num_views * len(times) / T,
+        "cpu_baseline": {"value": value, "unit": "tests/s", "cores": cores, "kind": "port",
+                         "sample": "full %s scene, stages 1-4, %d passes" % (wname, len(times))},
+        "e2e": {"value": value, "unit": "tests/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--check", action="store_true", help="also verify the result against the CPU oracle")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+
+    scene_mod = importlib.import_module("3dline-slam_b200.scene")
+    if args.impl == "reference":
+        bench_reference(args, scene_mod)
+        return
+
+    import torch
+    api = importlib.import_module("3dline-slam_b200.api")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank if world > 1 else 0)
+    torch.cuda.set_device(dev)
+    n_gpus = world if world > 1 else 1
+    if args.gpus != n_gpus and rank == 0:
+        print("note: --gpus %d but WORLD_SIZE=%d; using %d" % (args.gpus, world, n_gpus), file=sys.stderr)
+
+    scene, wname = make_workload(scene_mod, args.workload, n_gpus)
+    prm = scene.params
+    stream = torch.cuda.current_stream(dev)
+    l3 = api.Line3D("", False, scene.max_image_width, 3000, False, True, dev.index, stream.cuda_stream)
+    l3.shard = (rank, n_gpus)
+    l3.load_scene(scene)
+    l3.upload()  # tables resident in HBM before the timed region
+
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
+
+    def exchange():
+        """all-gather of the per-shard forward-match lists (NCCL over NVLink)."""
+        nbytes = l3.forward_blob_size()
+        sz = torch.tensor([nbytes], dtype=torch.int64, device=dev)
+        szs = [torch.zeros_like(sz) for _ in range(n_gpus)]
+        dist.all_gather(szs, sz)
+        stride = int(max(int(s.item()) for s in szs))
+        stride = (stride + 31) // 32 * 32
+        mine = torch.zeros(stride, dtype=torch.uint8, device=dev)
+        l3.export_forward(mine.data_ptr(), stride, True)
+        allb = torch.empty(stride * n_gpus, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(allb, mine)
+        torch.cuda.current_stream(dev).synchronize()
+        l3.import_forward(allb.data_ptr(), stride, n_gpus, True)
+        return stride * n_gpus
+
+    def step():
+        if n_gpus == 1:
+            l3.matchImages(prm["sigma_p"], prm["sigma_a"], prm["num_neighbors"], prm["epipolar_overlap"], prm["knn"],
+                           prm["const_reg_depth"])
+        else:
+            l3.match_stage12(prm["sigma_p"], prm["sigma_a"], prm["num_neighbors"], prm["epipolar_overlap"],
+                             prm["knn"], prm["const_reg_depth"])
+            exchange()
+            l3.match_stage3()
+        l3.affinity()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        flush.zero_()
+        step()
+    barrier()
+
+    sampler = ClockSampler(dev.index)
+    sampler.start()
+    l3.reset_counters()
+    total_ms = 0.0
+    stage_ms = {}
+    k1_ms, k1_launches = 0.0, 0
+    barrier()
+    for _ in range(args.steps):
+        flush.zero_()  # flush L2 between timed iterations (inputs are smaller than L2)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(stream)
+        step()
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+        total_ms += e0.elapsed_time(e1)
+        # stage timers of the library (CUDA events on the same stream); affinity() resets them,
+        # so read both halves
+        for k, v in l3.timings().items():
+            stage_ms[k] = stage_ms.get(k, 0.0) + v
+    barrier()
+    clocks = sampler.stop()
+    cnt = l3.counts()
+    launches = cnt["gpu_launches"]
+
+    # max over ranks
+    if dist is not None:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+        tt = torch.tensor([float(cnt["pair_tests"])], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.SUM)
+        tests_per_step = float(tt.item())
+    else:
+        tests_per_step = float(cnt["pair_tests"])
+
+    # ---- separate instrumented passes for the per-stage / K1 numbers (same workload) ----
+    l3.match_stage12(prm["sigma_p"], prm["sigma_a"], prm["num_neighbors"], prm["epipolar_overlap"], prm["knn"],
+                     prm["const_reg_depth"])
+    t12 = l3.timings()
+    c12 = l3.counts()
+    if n_gpus > 1:
+        exchange()
+    l3.match_stage3()
+    t3 = l3.timings()
+    l3.affinity()
+    t4 = l3.timings()
+    cfin = l3.counts()
+    k1_s = max(t12["k1_kernel"], 1e-9) * 1e-3
+    k1_tests = float(c12["pair_tests"])
+
+    value = tests_per_step * args.steps / (total_ms * 1e-3)
+    views_per_s = scene.num_views * args.steps / (total_ms * 1e-3)
+
+    # ---- end to end through the public API with host buffers (H2D of the scene, D2H of A_) ----
+    e2e = None
+    if n_gpus == 1:
+        h2d = scene.total_segments() * 16 + scene.num_views * (8 * 21 + 20) + sum(4 * len(v.neighbors) for v in scene.views)
+        d2h = 0
+        t_e2e = 0.0
+        for i in range(2 + args.steps):
+            flush.zero_()
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            l3.upload()                      # host -> device: segments, cameras, neighbour lists
+            step()
+            ij, w = l3.edges()               # device -> host: A_ (what the CPU clustering consumes)
+            l2g = l3.local2global()
+            torch.cuda.synchronize(dev)
+            dt = time.perf_counter() - t0
+            if i >= 2:
+                t_e2e += dt
+            d2h = ij.nbytes + w.nbytes + l2g.nbytes
+        e2e = {"value": tests_per_step * args.steps / t_e2e, "unit": "tests/s", "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * t_e2e / args.steps,
+               "views_per_s": scene.num_views * args.steps / t_e2e}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (K1) ----
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    sm_max = clocks.get("sm_max_mhz") or peaks.get("sm_max_mhz") or 1965.0
+    n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+    fp32_nominal = n_sm * 128 * 2 * sm_max * 1e6 / 1e12
+    fp32_measured = api.Context(dev.index, stream.cuda_stream).fp32_peak_tflops()
+    achieved = FLOP_PER_TEST * k1_tests / k1_s / 1e12
+    roofline = {
+        "kernel": "k1_pairtest_kernel", "bound": "fp32", "achieved": achieved, "peak": fp32_measured,
+        "unit": "TFLOP/s", "frac": achieved / fp32_measured if fp32_measured else None,
+        "peak_source": "measured here: dense FFMA micro-benchmark (l3d_bench_fp32_peak); nominal %d SMs x 128 x 2 x %.0f MHz = %.1f TFLOP/s"
+                       % (n_sm, sm_max, fp32_nominal),
+        "peak_nominal": fp32_nominal, "frac_of_nominal": achieved / fp32_nominal,
+        "algorithmic_flop_per_test": FLOP_PER_TEST, "tests_per_launch": k1_tests / max(t12["k1_launches"], 1),
+        "launch_ms": 1e3 * k1_s / max(t12["k1_launches"], 1), "k1_tests_per_s": k1_tests / k1_s,
+        "hbm_peak_gbs": peaks.get("hbm_gbs"), "traffic": None,
+    }
+
+    cpu_baseline = None
+    if not args.no_cpu_baseline:
+        base_scene, bname = make_workload(scene_mod, args.workload, 1)
+        r = run_cpu_oracle(base_scene)
+        tcpu = r["timers"]["match_images"] + r["timers"]["reconstruct"]
+        cpu_baseline = {"value": r["tests"] / tcpu, "unit": "tests/s", "cores": r["cores"], "kind": "port",
+                        "sample": "full %s scene (%d views), stages 1-4, one pass, %.1f s" % (bname, base_scene.num_views, tcpu),
+                        "views_per_s": base_scene.num_views / tcpu,
+                        "stage1_tests_per_s": r["tests"] / max(r["timers"]["match"], 1e-9)}
+
+    if args.check:
+        import oracle_py
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from parity_utils import compare_full
+        l3.reconstruct3Dlines()
+        orc = oracle_py.run_scene(scene)
+        print("check vs oracle:", compare_full(l3, orc, scene, check_scored=False), file=sys.stderr)
+
+    line = {
+        "metric": "segment_pair_tests_per_s", "value": value, "unit": "tests/s", "n_gpus": n_gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32 pre-filter + f64 exact", "data": "synthetic",
+        "config": {"workload": wname, "views": scene.num_views, "segments_per_view": scene.views[0].segs.shape[0],
+                   "neighbours": prm["num_neighbors"], "image": "%dx%d" % (scene.views[0].width, scene.views[0].height),
+                   "l2": "flushed between timed iterations (256 MB write)",
+                   "parallelism": "pairs sharded over %d rank(s), stages 3-4 replicated" % n_gpus},
+        "views_per_s": views_per_s,
+        "stage1_tests_per_s": k1_tests / max((t12["pairtest"] + t12["exact"]) * 1e-3, 1e-9),
+        "stage_ms": {"prep": t12["prep"], "k1_pairtest": t12["pairtest"], "k2_exact": t12["exact"],
+                     "k3_score": t3["score"], "k4_affinity": t4["affinity"]},
+        "counts": {k: cfin[k] for k in ("pair_tests", "candidates", "forward_matches", "scored_entries", "sim_evals",
+                                         "filtered_entries", "num_pairs", "num_entries", "num_edges", "num_local_ids")},
+        "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+    }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
