@@ -156,7 +156,7 @@ int l3d_score_matches(l3d_ctx* ctx, const float* lines, uint32_t n_lines, const 
     ctx->cnt.gpu_launches +=
         launch_score_prep(d_lines.p, n_lines, d_m.p, d_rt.p, d_cam.p, d_cam.p + 9, k, d_off.p, d_L.p, d_G.p, st);
     ctx->cnt.gpu_launches +=
-        launch_k3_score(n_lines, d_off.p, d_L.p, d_G.p, nullptr, two_sigA_sqr, min_similarity, d_stats.p, st);
+        launch_k3_score(n_lines, d_off.p, d_L.p, d_G.p, two_sigA_sqr, min_similarity, d_stats.p, st);
     std::vector<ListRec> L(n_matches);
     CK(cudaMemcpyAsync(L.data(), d_L.p, (size_t)n_matches * sizeof(ListRec), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));

@@ -493,107 +493,100 @@ int l3d_match_stage3(l3d_ctx* ctx)
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     const uint32_t V = (uint32_t)ctx->views.size(), P = (uint32_t)ctx->pairs.size(), S = ctx->S;
+    for (uint32_t v = 0; v < V; ++v)
+        if (ctx->inc_off_h[v + 1] - ctx->inc_off_h[v] > (uint32_t)k3_wf_max_inc())
+            return fail(L3D_ERR_CAPACITY, "view %u takes part in more than %d matched pairs", ctx->views[v].v.cam_id,
+                        k3_wf_max_inc());
 
     cudaEvent_t ev_total = ctx->tm.begin(L3D_T_TOTAL, st);
     cudaEvent_t ev = ctx->tm.begin(L3D_T_SCORE, st);
     const size_t F = (size_t)ctx->total_fwd;
-    CK(ctx->d_inc.ensure(ctx->inc_h.size()));
+    const size_t TR = (size_t)ctx->total_tgt_rows;
+    CK(ctx->d_inc.ensure(ctx->inc_h.size() + 1));
+    CK(ctx->d_inc_off.ensure((size_t)V + 1));
     if (!ctx->inc_h.empty())
         CK(cudaMemcpyAsync(ctx->d_inc.p, ctx->inc_h.data(), ctx->inc_h.size() * sizeof(IncDev), cudaMemcpyHostToDevice,
                            st));
-    CK(ctx->d_inv_cnt.ensure((size_t)ctx->total_tgt_rows + 1));
-    CK(ctx->d_inv_fill.ensure((size_t)ctx->total_tgt_rows + 1));
-    CK(ctx->d_inv_off.ensure((size_t)ctx->total_tgt_rows + 1));
+    CK(cudaMemcpyAsync(ctx->d_inc_off.p, ctx->inc_off_h.data(), ((size_t)V + 1) * 4, cudaMemcpyHostToDevice, st));
+    CK(ctx->d_inv_cap.ensure(TR + 1));
+    CK(ctx->d_inv_fill.ensure(TR + 1));
+    CK(ctx->d_inv_off.ensure(TR + 2));
     CK(ctx->d_inv_ent.ensure(F + 1));
-    CK(cudaMemsetAsync(ctx->d_inv_cnt.p, 0, ((size_t)ctx->total_tgt_rows + 1) * 4, st));
-    CK(cudaMemsetAsync(ctx->d_inv_fill.p, 0, ((size_t)ctx->total_tgt_rows + 1) * 4, st));
-    CK(cudaMemsetAsync(ctx->d_inv_off.p, 0, ((size_t)ctx->total_tgt_rows + 1) * 4, st));
-    CK(ctx->d_scan_tmp.ensure((size_t)std::max(P, ctx->total_tgt_rows) + 2));
-    CK(ctx->d_scan.ensure(scan_scratch_words(std::max(ctx->total_tgt_rows, S) * 2 + 2) + 64));
+    CK(cudaMemsetAsync(ctx->d_inv_cap.p, 0, (TR + 1) * 4, st));
+    CK(cudaMemsetAsync(ctx->d_inv_fill.p, 0, (TR + 1) * 4, st));
+    CK(ctx->d_scan.ensure(scan_scratch_words((uint32_t)std::max<size_t>(TR, S) + 2) + 64));
+    CK(ctx->d_L_ub.ensure((size_t)S + 1));
+    CK(ctx->d_L_off.ensure((size_t)S + 2));
+    CK(ctx->d_L_cnt.ensure((size_t)S + 1));
+    CK(cudaMemsetAsync(ctx->d_L_cnt.p, 0, ((size_t)S + 1) * 4, st));
 
-    uint32_t maxN = 0;
-    for (auto& hv : ctx->views) maxN = std::max(maxN, hv.v.num_segs);
-    CK(ctx->d_L_cnt.ensure((size_t)maxN + 1));
-    CK(ctx->d_L_off.ensure((size_t)maxN + 1));
-    CK(ctx->d_F_cnt.ensure((size_t)maxN + 1));
-    CK(ctx->d_F_off.ensure((size_t)maxN + 1));
+    // pre-pass: CSR slots of the inverse matches and of the lists, from upper bounds
+    ctx->cnt.gpu_launches += launch_k3_inv_capacity(ctx->d_pairs.p, P, ctx->total_rows, ctx->d_fwd_off.p,
+                                                    ctx->d_fwd_cnt.p, ctx->d_fwd_rec.p, ctx->d_inv_cap.p, st);
+    ctx->cnt.gpu_launches +=
+        launch_scan_u32(ctx->d_inv_cap.p, ctx->d_inv_off.p, (uint32_t)TR, ctx->d_scan.p, ctx->d_scan.cap, st);
+    ctx->cnt.gpu_launches +=
+        launch_k3_list_capacity(ctx->d_views.p, ctx->d_seg_view.p, S, ctx->d_inc.p, ctx->d_inc_off.p, ctx->d_pairs.p,
+                                ctx->d_fwd_cnt.p, ctx->d_inv_cap.p, ctx->d_L_ub.p, st);
+    ctx->cnt.gpu_launches += launch_scan_u32(ctx->d_L_ub.p, ctx->d_L_off.p, S, ctx->d_scan.p, ctx->d_scan.cap, st);
 
-    // list capacities: forward records of the view's own pairs + of the pairs pointing at it
-    std::vector<uint64_t> cap(V, 0);
+    // list regions: forward records of the view's own pairs + of the pairs pointing at it
+    std::vector<uint64_t>& cap = ctx->L_cap_h;
+    cap.assign(V, 0);
     for (uint32_t p = 0; p < P; ++p) {
         cap[ctx->pairs[p].src] += ctx->pairs[p].fwd_total;
         if (ctx->pairs_h[p].emit_inverse) cap[ctx->pairs[p].tgt] += ctx->pairs[p].fwd_total;
     }
     const bool keep = ctx->prm.keep_scored != 0;
     ctx->L_base_h.assign(V + 1, 0);
-    uint64_t Lcap = 0;
+    uint64_t Lcap = 0, maxcap = 0;
+    uint32_t maxN = 0;
+    for (uint32_t v = 0; v < V; ++v) {
+        maxcap = std::max(maxcap, cap[v]);
+        maxN = std::max(maxN, ctx->views[v].v.num_segs);
+    }
     if (keep) {
         for (uint32_t v = 0; v < V; ++v) {
             ctx->L_base_h[v] = Lcap;
             Lcap += cap[v];
         }
-        ctx->L_base_h[V] = Lcap;
-        CK(ctx->d_L_off_all.ensure((size_t)S + V + 1));
     } else {
-        for (uint32_t v = 0; v < V; ++v) Lcap = std::max(Lcap, cap[v]);
+        for (uint32_t v = 0; v < V; ++v) ctx->L_base_h[v] = (v & 1) ? maxcap : 0;  // double buffer
+        Lcap = 2 * maxcap;
     }
     if (Lcap > 0xfffffff0ull || 2 * F > 0xfffffff0ull) return fail(L3D_ERR_CAPACITY, "match lists too large");
+    CK(ctx->d_L_base.ensure((size_t)V + 1));
+    CK(cudaMemcpyAsync(ctx->d_L_base.p, ctx->L_base_h.data(), ((size_t)V + 1) * 8, cudaMemcpyHostToDevice, st));
     CK(ctx->d_L_rec.ensure(Lcap + 1));
-    CK(ctx->d_L_geo.ensure(Lcap + 1));
-    CK(ctx->d_filt_rec.ensure(2 * F + 1));
+    CK(ctx->d_L_sib.ensure((Lcap + 1) * k3_sib_bytes()));
+    CK(ctx->d_L_dir.ensure(3 * (Lcap + 1)));
+    CK(ctx->d_L_reg.ensure(Lcap + 1));
+    const size_t filt_cap = 2 * F + 1;
+    CK(ctx->d_filt_rec.ensure(filt_cap));
     CK(ctx->d_filt_off.ensure((size_t)S + 1));
     CK(ctx->d_filt_cnt.ensure((size_t)S + 1));
+    CK(cudaMemsetAsync(ctx->d_filt_cnt.p, 0, ((size_t)S + 1) * 4, st));
+    CK(cudaMemsetAsync(ctx->d_filt_off.p, 0, ((size_t)S + 1) * 4, st));
+    CK(ctx->d_view_max.ensure((size_t)V + 1));
+    CK(cudaMemsetAsync(ctx->d_view_max.p, 0, ((size_t)V + 1) * 4, st));
     CK(ctx->d_small.ensure(16));
     CK(cudaMemsetAsync(ctx->d_small.p, 0, 16 * 4, st));
-    CK(ctx->d_stats.ensure(2 * k3_stats_bytes()));
-    CK(cudaMemsetAsync(ctx->d_stats.p, 0, 2 * k3_stats_bytes(), st));
+    CK(ctx->d_stats.ensure(k3_wf_stats_bytes()));
+    CK(cudaMemsetAsync(ctx->d_stats.p, 0, k3_wf_stats_bytes(), st));
     CK(ctx->d_entries.ensure((size_t)S + 1));
-    void* stats = ctx->d_stats.p;
-    void* accum = ctx->d_stats.p + k3_stats_bytes();
-    uint32_t* filt_total = ctx->d_small.p;
-    uint32_t* err_flag = ctx->d_small.p + 1;
 
-    for (uint32_t v = 0; v < V; ++v) {
-        const HostView& hv = ctx->views[v];
-        const uint32_t N = hv.v.num_segs;
-        const uint32_t i0 = ctx->inc_off_h[v], n_inc = ctx->inc_off_h[v + 1] - i0;
-        ListRec* Lr = ctx->d_L_rec.p + (keep ? ctx->L_base_h[v] : 0);
-        ListGeo* Lg = ctx->d_L_geo.p + (keep ? ctx->L_base_h[v] : 0);
-        ctx->cnt.gpu_launches += launch_k3_count(ctx->d_inc.p + i0, n_inc, ctx->d_pairs.p, ctx->d_fwd_cnt.p,
-                                                 ctx->d_inv_cnt.p, N, ctx->d_L_cnt.p, st);
-        ctx->cnt.gpu_launches += launch_scan_u32(ctx->d_L_cnt.p, ctx->d_L_off.p, N, ctx->d_scan.p, ctx->d_scan.cap, st);
-        ctx->cnt.gpu_launches +=
-            launch_k3_gather(v, N, ctx->d_inc.p + i0, n_inc, ctx->d_pairs.p, ctx->d_views.p, ctx->d_rays.p,
-                             ctx->d_fwd_off.p, ctx->d_fwd_cnt.p, ctx->d_fwd_rec.p, ctx->d_inv_off.p, ctx->d_inv_cnt.p,
-                             ctx->d_inv_ent.p, ctx->d_L_off.p, Lr, Lg, err_flag, st);
-        ctx->cnt.gpu_launches +=
-            launch_k3_score(N, ctx->d_L_off.p, Lr, Lg, ctx->d_fwd_rec.p, ctx->two_sigA_sqr, 0.5f, stats, st);
-        // inverse matches towards later views
-        uint32_t first_p = 0xffffffffu, last_p = 0;
-        bool any_emit = false;
-        for (uint32_t q = i0; q < i0 + n_inc; ++q)
-            if (!ctx->inc_h[q].inverse) {
-                first_p = std::min(first_p, ctx->inc_h[q].pair);
-                last_p = std::max(last_p, ctx->inc_h[q].pair);
-                any_emit |= ctx->pairs_h[ctx->inc_h[q].pair].emit_inverse != 0;
-            }
-        if (any_emit) {
-            const uint32_t first_row = ctx->pairs_h[first_p].tgt_base;
-            const uint32_t n_rows_t = ctx->pairs_h[last_p].tgt_base + ctx->pairs_h[last_p].n_tgt - first_row;
-            const uint32_t grid = (uint32_t)std::min<uint64_t>(std::max<uint64_t>((cap[v] + 255) / 256, 1), 148 * 8);
-            ctx->cnt.gpu_launches += launch_k3_inverse(
-                N, ctx->d_L_off.p, Lr, Lg, ctx->d_pairs.p, first_row, n_rows_t, ctx->pairs[first_p].rec_start,
-                ctx->d_inv_cnt.p, ctx->d_inv_fill.p, ctx->d_inv_off.p, ctx->d_inv_ent.p, ctx->d_scan_tmp.p,
-                ctx->d_scan.p, ctx->d_scan.cap, grid, st);
-        }
-        ctx->cnt.gpu_launches += launch_k3_filter(v, N, ctx->d_views.p, ctx->d_rays.p, ctx->d_L_off.p, Lr, stats, accum,
-                                                  ctx->d_F_cnt.p, ctx->d_F_off.p, ctx->d_entries.p, filt_total,
-                                                  ctx->d_filt_rec.p, ctx->d_filt_off.p, ctx->d_filt_cnt.p, ctx->d_scan.p,
-                                                  ctx->d_scan.cap, st);
-        if (keep)
-            CK(cudaMemcpyAsync(ctx->d_L_off_all.p + hv.seg_off + v, ctx->d_L_off.p, ((size_t)N + 1) * 4,
-                               cudaMemcpyDeviceToDevice, st));
-    }
+    int cuerr = 0;
+    const int nl = launch_k3_wavefront(
+        ctx->d_views.p, ctx->d_pairs.p, ctx->d_inc.p, ctx->d_inc_off.p, ctx->d_rays.p, ctx->d_fwd_off.p,
+        ctx->d_fwd_cnt.p, ctx->d_fwd_rec.p, ctx->d_inv_off.p, ctx->d_inv_fill.p, ctx->d_inv_ent.p, ctx->d_L_off.p,
+        ctx->d_L_base.p, ctx->d_L_cnt.p, ctx->d_L_rec.p, ctx->d_L_sib.p, ctx->d_L_dir.p, ctx->d_L_reg.p,
+        ctx->d_view_max.p, ctx->d_filt_rec.p, (uint32_t)filt_cap, ctx->d_filt_off.p, ctx->d_filt_cnt.p,
+        ctx->d_entries.p, ctx->d_stats.p, V, maxN, ctx->two_sigA_sqr, st, &cuerr);
+    if (nl < 0)
+        return fail(L3D_ERR_CUDA, "cooperative launch of the scoring wavefront failed: %s",
+                    cudaGetErrorString((cudaError_t)cuerr));
+    ctx->cnt.gpu_launches += nl;
+
     // estimated_position3D_ index (canonical order = global segment order) and median depths
     CK(ctx->d_has.ensure((size_t)S + 1));
     CK(ctx->d_entry_idx.ensure((size_t)S + 2));
@@ -605,30 +598,34 @@ int l3d_match_stage3(l3d_ctx* ctx)
 
     uint32_t small[4] = {0, 0, 0, 0};
     uint32_t n_entries = 0;
-    std::vector<unsigned char> acc(k3_stats_bytes());
+    std::vector<unsigned char> acc(k3_wf_stats_bytes());
     std::vector<ViewDev> vd(V);
     CK(cudaMemcpyAsync(small, ctx->d_small.p, sizeof(small), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(&n_entries, ctx->d_entry_idx.p + S, 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(acc.data(), accum, acc.size(), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(acc.data(), ctx->d_stats.p, acc.size(), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(vd.data(), ctx->d_views.p, V * sizeof(ViewDev), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     ctx->tm.collect();
-    if (small[1]) return fail(L3D_ERR_STATE, "a match list holds a camera in two separate runs");
-    if (small[2]) return fail(L3D_ERR_CAPACITY, "more than 8192 hypotheses in one view (median-depth kernel)");
-    ctx->cnt.filtered_entries = small[0];
-    ctx->cnt.num_entries = n_entries;
     {
-        const unsigned long long* a = (const unsigned long long*)acc.data();
-        ctx->cnt.sim_evals = a[0];
-        ctx->cnt.scored_entries = a[1];
+        const unsigned long long* a64 = (const unsigned long long*)acc.data();
+        const uint32_t* a32 = (const uint32_t*)(acc.data() + 16);
+        ctx->cnt.sim_evals = a64[0];
+        ctx->cnt.scored_entries = a64[1];
+        ctx->cnt.filtered_entries = a32[1];  // filt_cursor
+        if (a32[2] & 2u) return fail(L3D_ERR_CAPACITY, "filtered-match store overflow");
     }
+    if (small[2]) return fail(L3D_ERR_CAPACITY, "more than 8192 hypotheses in one view (median-depth kernel)");
+    ctx->cnt.num_entries = n_entries;
     for (uint32_t v = 0; v < V; ++v) {
         ctx->views[v].median_depth = vd[v].median_depth;
         ctx->views[v].median_sigma = ctx->views[v].k * vd[v].median_depth;  // view.h:122-135
     }
     // update_Matches_and_Estimated_position3D (src/line3D.cc:1857-1908) re-triangulates the best
     // matches with unchanged poses: the identical call, hence identical depths -- nothing to do.
-    apply_translation(ctx, +1.0);  // untranslate()
+    if (!ctx->raw_mode) {
+        const hg::V3 tv{ctx->translation.x, ctx->translation.y, ctx->translation.z};
+        for (auto& hv : ctx->views) hv.cam.translate(tv);  // untranslate()
+    }
     ctx->stage = 2;
     return L3D_OK;
 }
@@ -829,51 +826,61 @@ int l3d_get_view_lists(l3d_ctx* ctx, uint32_t cam_id, int which, uint32_t* row_o
     const uint32_t v = f->second;
     const HostView& hv = ctx->views[v];
     const uint32_t N = hv.v.num_segs;
-    std::vector<uint32_t> off(N + 1), cnt(N);
+    std::vector<uint32_t> off(N + 1, 0), cnt(N, 0);
     const ListRec* src = nullptr;
-    uint64_t total = 0;
+    uint64_t region = 0;
     if (which == 0) {
         if (!ctx->prm.keep_scored) return fail(L3D_ERR_STATE, "keep_scored was not set");
-        CK(cudaMemcpyAsync(off.data(), ctx->d_L_off_all.p + hv.seg_off + v, ((size_t)N + 1) * 4,
-                           cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(off.data(), ctx->d_L_off.p + hv.seg_off, ((size_t)N + 1) * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(cnt.data(), ctx->d_L_cnt.p + hv.seg_off, (size_t)N * 4, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
+        const uint32_t o0 = off[0];
+        for (uint32_t i = 0; i <= N; ++i) off[i] -= o0;
         src = ctx->d_L_rec.p + ctx->L_base_h[v];
-        total = off[N];
-        for (uint32_t i = 0; i <= N; ++i) row_off[i] = off[i];
+        region = off[N];
     } else {
         CK(cudaMemcpyAsync(off.data(), ctx->d_filt_off.p + hv.seg_off, (size_t)N * 4, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(cnt.data(), ctx->d_filt_cnt.p + hv.seg_off, (size_t)N * 4, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
-        const uint32_t base = N ? off[0] : 0;
-        src = ctx->d_filt_rec.p + base;
-        uint32_t run = 0;
-        for (uint32_t i = 0; i < N; ++i) {
-            row_off[i] = run;
-            run += cnt[i];
-        }
-        row_off[N] = run;
-        total = run;
+        uint32_t lo = 0xffffffffu, hi = 0;
+        for (uint32_t i = 0; i < N; ++i)
+            if (cnt[i]) {
+                lo = std::min(lo, off[i]);
+                hi = std::max(hi, off[i] + cnt[i]);
+            }
+        if (lo == 0xffffffffu) lo = hi = 0;
+        for (uint32_t i = 0; i < N; ++i) off[i] = cnt[i] ? off[i] - lo : 0;
+        src = ctx->d_filt_rec.p + lo;
+        region = hi - lo;
     }
+    uint64_t total = 0;
+    for (uint32_t i = 0; i < N; ++i) {
+        row_off[i] = (uint32_t)total;
+        total += cnt[i];
+    }
+    row_off[N] = (uint32_t)total;
     if (out_count) *out_count = total;
     if (total > cap) return fail(L3D_ERR_CAPACITY, "need %llu records", (unsigned long long)total);
     if (total == 0) return L3D_OK;
     if (!recs) return fail(L3D_ERR_ARG, "recs is NULL");
-    std::vector<ListRec> tmp(total);
-    CK(cudaMemcpyAsync(tmp.data(), src, total * sizeof(ListRec), cudaMemcpyDeviceToHost, st));
+    std::vector<ListRec> tmp(region);
+    CK(cudaMemcpyAsync(tmp.data(), src, region * sizeof(ListRec), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    for (uint64_t i = 0; i < total; ++i) {
-        const ListRec& L = tmp[i];
-        l3d_list_rec& o = recs[i];
-        o.tgt_cam = ctx->views[L.tgt_view].v.cam_id;
-        o.tgt_seg = L.tgt_seg;
-        o.overlap_score = L.overlap;
-        o.score3D = L.score;
-        o.depth_p1 = L.d_p1;
-        o.depth_p2 = L.d_p2;
-        o.depth_q1 = L.d_q1;
-        o.depth_q2 = L.d_q2;
-        o.flags = L.flags & 1u;
-    }
+    uint64_t n = 0;
+    for (uint32_t i = 0; i < N; ++i)
+        for (uint32_t e = 0; e < cnt[i]; ++e) {
+            const ListRec& L = tmp[(size_t)off[i] + e];
+            l3d_list_rec& o = recs[n++];
+            o.tgt_cam = ctx->views[L.tgt_view].v.cam_id;
+            o.tgt_seg = L.tgt_seg;
+            o.overlap_score = L.overlap;
+            o.score3D = L.score;
+            o.depth_p1 = L.d_p1;
+            o.depth_p2 = L.d_p2;
+            o.depth_q1 = L.d_q1;
+            o.depth_q2 = L.d_q2;
+            o.flags = L.flags & 1u;
+        }
     return L3D_OK;
 }
 

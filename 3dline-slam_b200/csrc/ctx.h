@@ -25,18 +25,19 @@ int launch_k2_exact(const PairDev*, const K1Cta*, uint32_t, const float4*, const
                     float, int, int, cudaStream_t);
 int launch_k2_compact(const uint32_t*, const uint32_t*, const uint32_t*, uint32_t, const FwdRec*, FwdRec*, uint32_t*,
                       uint32_t, cudaStream_t);
-int launch_k3_count(const IncDev*, uint32_t, const PairDev*, const uint32_t*, const uint32_t*, uint32_t, uint32_t*,
-                    cudaStream_t);
-int launch_k3_gather(uint32_t, uint32_t, const IncDev*, uint32_t, const PairDev*, const ViewDev*, const SegRays*,
-                     const uint32_t*, const uint32_t*, const FwdRec*, const uint32_t*, const uint32_t*, const uint2*,
-                     const uint32_t*, ListRec*, ListGeo*, uint32_t*, cudaStream_t);
-int launch_k3_score(uint32_t, const uint32_t*, ListRec*, const ListGeo*, FwdRec*, float, float, void*, cudaStream_t);
-int launch_k3_inverse(uint32_t, const uint32_t*, const ListRec*, const ListGeo*, const PairDev*, uint32_t, uint32_t,
-                      uint32_t, uint32_t*, uint32_t*, uint32_t*, uint2*, uint32_t*, uint32_t*, size_t, uint32_t,
-                      cudaStream_t);
-int launch_k3_filter(uint32_t, uint32_t, const ViewDev*, const SegRays*, const uint32_t*, const ListRec*, void*, void*,
-                     uint32_t*, uint32_t*, EntryDev*, uint32_t*, ListRec*, uint32_t*, uint32_t*, uint32_t*, size_t,
-                     cudaStream_t);
+int launch_k3_score(uint32_t, const uint32_t*, ListRec*, const ListGeo*, float, float, void*, cudaStream_t);
+int launch_k3_inv_capacity(const PairDev*, uint32_t, uint32_t, const uint32_t*, const uint32_t*, const FwdRec*,
+                           uint32_t*, cudaStream_t);
+int launch_k3_list_capacity(const ViewDev*, const uint32_t*, uint32_t, const IncDev*, const uint32_t*, const PairDev*,
+                            const uint32_t*, const uint32_t*, uint32_t*, cudaStream_t);
+int launch_k3_wavefront(const ViewDev*, const PairDev*, const IncDev*, const uint32_t*, const SegRays*,
+                        const uint32_t*, const uint32_t*, FwdRec*, const uint32_t*, uint32_t*, uint2*,
+                        const uint32_t*, const uint64_t*, uint32_t*, ListRec*, void*, double*, float2*, uint32_t*,
+                        ListRec*, uint32_t, uint32_t*, uint32_t*, EntryDev*, void*, uint32_t, uint32_t, float,
+                        cudaStream_t, int*);
+size_t k3_wf_stats_bytes();
+size_t k3_sib_bytes();
+int k3_wf_max_inc();
 size_t k3_stats_bytes();
 int launch_k4_has(const EntryDev*, uint32_t, uint32_t*, cudaStream_t);
 int launch_k4_median(ViewDev*, uint32_t, const EntryDev*, uint32_t*, cudaStream_t);
@@ -208,18 +209,21 @@ struct l3d_ctx {
     DevBuf<FwdRec> d_fwd_rec;
     DevBuf<uint32_t> d_fwd_off, d_fwd_cnt;
     // stage 3
-    DevBuf<uint32_t> d_inv_cnt, d_inv_fill, d_inv_off, d_scan_tmp;
+    DevBuf<uint32_t> d_inv_cap, d_inv_fill, d_inv_off, d_scan_tmp, d_inc_off, d_view_max;
     DevBuf<uint2> d_inv_ent;
-    DevBuf<uint32_t> d_L_cnt, d_L_off, d_F_cnt, d_F_off;
+    DevBuf<uint32_t> d_L_ub, d_L_off, d_L_cnt;
     DevBuf<ListRec> d_L_rec;
-    DevBuf<ListGeo> d_L_geo;
+    DevBuf<unsigned char> d_L_sib;
+    DevBuf<double> d_L_dir;
+    DevBuf<float2> d_L_reg;
+    DevBuf<uint64_t> d_L_base;
+    std::vector<uint64_t> L_cap_h;   // per-view list capacity
     DevBuf<ListRec> d_filt_rec;
     DevBuf<uint32_t> d_filt_off, d_filt_cnt, d_small;  // d_small: [0]=filt_total [1]=err [2]=median overflow
     DevBuf<unsigned char> d_stats;                     // 2 x ScoreStats
     DevBuf<EntryDev> d_entries;
     DevBuf<uint32_t> d_has, d_entry_idx;
-    std::vector<uint64_t> L_base_h;  // keep_scored: per-view base into d_L_rec
-    DevBuf<uint32_t> d_L_off_all;    // keep_scored: per-view list offsets, [seg_off + view .. ]
+    std::vector<uint64_t> L_base_h;  // per-view base into the list buffers
     // stage 4
     DevBuf<float> d_filt_sim;
     DevBuf<uint32_t> d_E_cnt, d_E_off, d_first_touch, d_flags, d_flag_scan, d_l2g;
