@@ -447,14 +447,18 @@ int l3d_match_stage12(l3d_ctx* ctx, const l3d_params* params)
         CK(cudaStreamSynchronize(st));
         ctx->cnt.candidates += n_cand;
         // K2
-        CK(ctx->d_heap.ensure(n_cand));
-        CK(ctx->d_cand_rec.ensure(n_cand));
-        CK(ctx->d_fin_rec.ensure(n_cand));
+        CK(ctx->d_heap.ensure((size_t)n_cand + 1));
+        CK(ctx->d_cand_rec.ensure((size_t)n_cand + 1));
+        CK(ctx->d_fin_rec.ensure((size_t)n_cand + 1));
+        CK(ctx->d_cand_c.ensure((size_t)n_cand + 1));
+        CK(ctx->d_cand_row.ensure((size_t)n_cand + 1));
+        CK(ctx->d_row_pair.ensure((size_t)b.n_rows + 1));
         cudaEvent_t e2 = ctx->tm.begin(L3D_T_EXACT, st);
         ctx->cnt.gpu_launches +=
-            launch_k2_exact(ctx->d_pairs.p, ctx->d_ctas.p + b.cta0, b.n_ctas, ctx->d_segs.p, ctx->d_rays.p,
-                            ctx->d_midray.p, ctx->d_views.p, ctx->d_mask.p, ctx->d_cand_off.p, ctx->d_heap.p,
-                            ctx->d_cand_rec.p, ctx->d_fin_rec.p, ctx->d_fin_cnt.p, ctx->epi_overlap, ctx->prm.knn,
+            launch_k2_exact(ctx->d_pairs.p, ctx->d_ctas.p + b.cta0, b.n_ctas, b.n_rows, n_cand, ctx->d_segs.p,
+                            ctx->d_rays.p, ctx->d_midray.p, ctx->d_views.p, ctx->d_mask.p, ctx->d_cand_off.p,
+                            ctx->d_cand_c.p, ctx->d_cand_row.p, ctx->d_row_pair.p, ctx->d_heap.p, ctx->d_cand_rec.p,
+                            ctx->d_fin_rec.p, ctx->d_fin_cnt.p, ctx->epi_overlap, ctx->prm.knn,
                             ctx->prm.max_image_width, st);
         ctx->cnt.gpu_launches +=
             launch_scan_u32(ctx->d_fin_cnt.p, ctx->d_fin_off.p, b.n_rows, ctx->d_scan.p, ctx->d_scan.cap, st);
@@ -575,16 +579,37 @@ int l3d_match_stage3(l3d_ctx* ctx)
     CK(cudaMemsetAsync(ctx->d_stats.p, 0, k3_wf_stats_bytes(), st));
     CK(ctx->d_entries.ensure((size_t)S + 1));
 
+    CK(ctx->d_G_fwd.ensure((F + 1) * k3_geo_bytes()));
+    CK(ctx->d_G_inv.ensure((F + 1) * k3_geo_bytes()));
+    ctx->cnt.gpu_launches +=
+        launch_k3_geom(ctx->d_pairs.p, P, ctx->total_rows, ctx->d_views.p, ctx->d_rays.p, ctx->d_fwd_off.p,
+                       ctx->d_fwd_cnt.p, ctx->d_fwd_rec.p, ctx->d_G_fwd.p, ctx->d_G_inv.p, st);
+    DevBuf<uint32_t> dbg;  // developer aid: L3D_WF_DEBUG=<file> dumps per-row cycle counters
+    const char* dbg_path = getenv("L3D_WF_DEBUG");
+    if (dbg_path) {
+        CK(dbg.ensure(4 * (size_t)S + 4));
+        CK(cudaMemsetAsync(dbg.p, 0, (4 * (size_t)S + 4) * 4, st));
+    }
     int cuerr = 0;
     const int nl = launch_k3_wavefront(
         ctx->d_views.p, ctx->d_pairs.p, ctx->d_inc.p, ctx->d_inc_off.p, ctx->d_rays.p, ctx->d_fwd_off.p,
-        ctx->d_fwd_cnt.p, ctx->d_fwd_rec.p, ctx->d_inv_off.p, ctx->d_inv_fill.p, ctx->d_inv_ent.p, ctx->d_L_off.p,
+        ctx->d_fwd_cnt.p, ctx->d_fwd_rec.p, ctx->d_G_fwd.p, ctx->d_G_inv.p, ctx->d_inv_off.p, ctx->d_inv_fill.p,
+        ctx->d_inv_ent.p, ctx->d_L_off.p,
         ctx->d_L_base.p, ctx->d_L_cnt.p, ctx->d_L_rec.p, ctx->d_L_sib.p, ctx->d_L_dir.p, ctx->d_L_reg.p,
         ctx->d_view_max.p, ctx->d_filt_rec.p, (uint32_t)filt_cap, ctx->d_filt_off.p, ctx->d_filt_cnt.p,
-        ctx->d_entries.p, ctx->d_stats.p, V, maxN, ctx->two_sigA_sqr, st, &cuerr);
+        ctx->d_entries.p, ctx->d_stats.p, V, maxN, ctx->two_sigA_sqr, dbg.p, st, &cuerr);
     if (nl < 0)
         return fail(L3D_ERR_CUDA, "cooperative launch of the scoring wavefront failed: %s",
                     cudaGetErrorString((cudaError_t)cuerr));
+    if (dbg_path) {
+        std::vector<uint32_t> hd(4 * (size_t)S);
+        CK(cudaMemcpyAsync(hd.data(), dbg.p, hd.size() * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (FILE* fp = fopen(dbg_path, "wb")) {
+            fwrite(hd.data(), 4, hd.size(), fp);
+            fclose(fp);
+        }
+    }
     ctx->cnt.gpu_launches += nl;
 
     // estimated_position3D_ index (canonical order = global segment order) and median depths

@@ -82,6 +82,28 @@ __device__ __forceinline__ double det_acos(double x)
     return (x > 0.0) ? a : __dsub_rn(L3D_PI, a);
 }
 
-__device__ __forceinline__ float det_acosf(float x) { return (float)det_acos((double)x); }
+// acosf: float in / float out; 16-term asin series, Estrin evaluation (short dependency chain)
+__device__ __forceinline__ double det_asin_series16(double z)
+{
+    const double z2 = __dmul_rn(z, z), z4 = __dmul_rn(z2, z2), z8 = __dmul_rn(z4, z4);
+#define L3D_PAIR(a, b) __dadd_rn(c_ASIN[a], __dmul_rn(c_ASIN[b], z))
+    const double p0 = L3D_PAIR(0, 1), p1 = L3D_PAIR(2, 3), p2 = L3D_PAIR(4, 5), p3 = L3D_PAIR(6, 7);
+    const double p4 = L3D_PAIR(8, 9), p5 = L3D_PAIR(10, 11), p6 = L3D_PAIR(12, 13), p7 = L3D_PAIR(14, 15);
+#undef L3D_PAIR
+    const double q0 = __dadd_rn(p0, __dmul_rn(p1, z2)), q1 = __dadd_rn(p2, __dmul_rn(p3, z2));
+    const double q2 = __dadd_rn(p4, __dmul_rn(p5, z2)), q3 = __dadd_rn(p6, __dmul_rn(p7, z2));
+    const double r0 = __dadd_rn(q0, __dmul_rn(q1, z4)), r1 = __dadd_rn(q2, __dmul_rn(q3, z4));
+    return __dadd_rn(r0, __dmul_rn(r1, z8));
+}
+__device__ __forceinline__ float det_acosf(float xf)
+{
+    const double x = (double)xf;
+    const double ax = fabs(x);
+    if (!(ax <= 1.0)) return __int_as_float(0x7fc00000);
+    if (ax <= 0.5) return (float)__dsub_rn(L3D_PI_2, __dmul_rn(x, det_asin_series16(__dmul_rn(x, x))));
+    const double z = __dmul_rn(__dsub_rn(1.0, ax), 0.5);
+    const double a = __dmul_rn(2.0, __dmul_rn(__dsqrt_rn(z), det_asin_series16(z)));
+    return (float)((x > 0.0) ? a : __dsub_rn(L3D_PI, a));
+}
 
 }  // namespace l3d

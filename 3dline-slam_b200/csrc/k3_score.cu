@@ -18,7 +18,8 @@ struct ScoreStats {
 __global__ void __launch_bounds__(256) k3_score_kernel(uint32_t n_rows, const uint32_t* __restrict__ L_off,
                                                        ListRec* __restrict__ L_rec,
                                                        const ListGeo* __restrict__ L_geo, float two_sigA_sqr,
-                                                       float min_sim, ScoreStats* __restrict__ stats)
+                                                       float min_sim, float dotcut,
+                                                       ScoreStats* __restrict__ stats)
 {
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t lane = threadIdx.x & 31;
@@ -59,7 +60,7 @@ __global__ void __launch_bounds__(256) k3_score_kernel(uint32_t n_rows, const ui
             s2.cam = M2.tgt_view;
             s2.flags = (G2.length < 1e-12) ? 0u : 2u;
             const float sim = sim_for_scoring(M.d_p1, M.d_p2, G.reg1, G.reg2, Mvalid, dirM, s2, G2.dir, two_sigA_sqr,
-                                              min_sim, xcut, pcut);
+                                              min_sim, xcut, pcut, dotcut);
             if (in_run) {
                 if (sim > stored) {
                     score = fs(score, stored);
@@ -88,7 +89,7 @@ int launch_k3_score(uint32_t n_rows, const uint32_t* L_off, ListRec* L_rec, cons
     if (!n_rows) return 0;
     const uint32_t warps_per_block = 8;
     k3_score_kernel<<<(n_rows + warps_per_block - 1) / warps_per_block, 256, 0, st>>>(
-        n_rows, L_off, L_rec, L_geo, two_sigA_sqr, min_sim, (ScoreStats*)stats);
+        n_rows, L_off, L_rec, L_geo, two_sigA_sqr, min_sim, score_dotcut(two_sigA_sqr, min_sim), (ScoreStats*)stats);
     return 1;
 }
 

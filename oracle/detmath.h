@@ -99,7 +99,29 @@ static inline double orc_acos(double x)
     return (x > 0.0) ? a : (ORC_PI - a);
 }
 
-static inline float orc_acosf(float x) { return (float)orc_acos((double)x); }
+/* acosf: float in / float out.  Same range reduction as orc_acos, but the asin series is cut at
+ * 16 terms (relative error < 5e-12, far below a float ulp) and evaluated with Estrin's scheme:
+ * pairs (c0+c1 z), ..., then z^2, z^4, z^8 combinations -- a short dependency chain for the GPU. */
+static inline double orc_asin_series16(double z)
+{
+    const double* c = ORC_ASIN_C;
+    const double z2 = z * z, z4 = z2 * z2, z8 = z4 * z4;
+    const double p0 = c[0] + c[1] * z, p1 = c[2] + c[3] * z, p2 = c[4] + c[5] * z, p3 = c[6] + c[7] * z;
+    const double p4 = c[8] + c[9] * z, p5 = c[10] + c[11] * z, p6 = c[12] + c[13] * z, p7 = c[14] + c[15] * z;
+    const double q0 = p0 + p1 * z2, q1 = p2 + p3 * z2, q2 = p4 + p5 * z2, q3 = p6 + p7 * z2;
+    const double r0 = q0 + q1 * z4, r1 = q2 + q3 * z4;
+    return r0 + r1 * z8;
+}
+static inline float orc_acosf(float xf)
+{
+    const double x = (double)xf;
+    const double ax = fabs(x);
+    if (!(ax <= 1.0)) return NAN;
+    if (ax <= 0.5) return (float)(ORC_PI_2 - x * orc_asin_series16(x * x));
+    const double z = (1.0 - ax) * 0.5;
+    const double a = 2.0 * (sqrt(z) * orc_asin_series16(z));
+    return (float)((x > 0.0) ? a : (ORC_PI - a));
+}
 
 /* sin(x) for x in [0, pi] (only use: View::getSpecificSpatialReg, view.cc:341-342) */
 static inline double orc_sin(double x)
