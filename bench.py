@@ -178,21 +178,11 @@ def main():
 
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
 
+    sharding = importlib.import_module("3dline-slam_b200.sharding")
+
     def exchange():
         """all-gather of the per-shard forward-match lists (NCCL over NVLink)."""
-        nbytes = l3.forward_blob_size()
-        sz = torch.tensor([nbytes], dtype=torch.int64, device=dev)
-        szs = [torch.zeros_like(sz) for _ in range(n_gpus)]
-        dist.all_gather(szs, sz)
-        stride = int(max(int(s.item()) for s in szs))
-        stride = (stride + 31) // 32 * 32
-        mine = torch.zeros(stride, dtype=torch.uint8, device=dev)
-        l3.export_forward(mine.data_ptr(), stride, True)
-        allb = torch.empty(stride * n_gpus, dtype=torch.uint8, device=dev)
-        dist.all_gather_into_tensor(allb, mine)
-        torch.cuda.current_stream(dev).synchronize()
-        l3.import_forward(allb.data_ptr(), stride, n_gpus, True)
-        return stride * n_gpus
+        return sharding.exchange_forward(l3, dist, torch, dev)
 
     def step():
         if n_gpus == 1:

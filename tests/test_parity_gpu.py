@@ -67,3 +67,33 @@ def test_device_math_bit_exact(api, oracle):
     gotd = ctx.test_acos(xd)
     expd = np.array([L.orc_kat_acos(float(v)) for v in xd])
     assert (gotd.view(np.uint64) == expd.view(np.uint64)).all()
+
+
+def test_sharded_stage12_merges_to_the_same_result(api, oracle, scene_mod):
+    """Two shard contexts on one GPU (pairs p mod 2): export, merge, import -> stage 3/4 results
+    identical to the unsharded run and to the oracle."""
+    import ctypes as C
+    sc = scene_mod.make_scene("tiny", seed=31, n_views=7, n_seg=140, nbrs=4)
+    p = sc.params
+    shards = []
+    for r in range(2):
+        l3 = api.Line3D("", False, sc.max_image_width)
+        l3.keep_scored = True
+        l3.shard = (r, 2)
+        l3.load_scene(sc)
+        l3.match_stage12(p["sigma_p"], p["sigma_a"], p["num_neighbors"], p["epipolar_overlap"], p["knn"],
+                         p["const_reg_depth"])
+        shards.append(l3)
+    sizes = [s.forward_blob_size() for s in shards]
+    stride = (max(sizes) + 31) // 32 * 32
+    buf = np.zeros(2 * stride, dtype=np.uint8)
+    for r, s in enumerate(shards):
+        s.export_forward(buf[r * stride:].ctypes.data, stride, False)
+    total_tests = sum(s.counts()["pair_tests"] for s in shards)
+    orc = oracle.run_scene(sc)
+    assert total_tests == orc.pair_tests()
+    for s in shards:
+        s.import_forward(buf.ctypes.data, stride, 2, False)
+        s.match_stage3()
+        s.reconstruct3Dlines()
+        compare_full(s, orc, sc)
