@@ -249,12 +249,21 @@ int plan_pairs(l3d_ctx* ctx)
     const int world = prm.shard_world > 1 ? prm.shard_world : 1;
     const int rank = world > 1 ? prm.shard_rank : 0;
     ctx->pairs_h.assign(P, PairDev{});
+    // shard = a contiguous block of pairs (pairs are ordered by source view, so a block is a slice of
+    // reference views), balanced by the number of segment-pair tests
+    std::vector<uint64_t> cum(P + 1, 0);
+    for (uint32_t p = 0; p < P; ++p)
+        cum[p + 1] = cum[p] + (uint64_t)ctx->views[ctx->pairs[p].src].v.num_segs *
+                                  ctx->views[ctx->pairs[p].tgt].v.num_segs;
+    const uint64_t total_tests = cum[P];
     uint64_t row = 0, trow = 0;
     ctx->cnt.pair_tests = 0;
     ctx->cnt.num_pairs_local = 0;
     for (uint32_t p = 0; p < P; ++p) {
         HostPair& hp = ctx->pairs[p];
-        hp.local = ((int)(p % world) == rank);
+        const uint64_t mid = cum[p] + (cum[p + 1] - cum[p]) / 2;
+        const int owner = total_tests ? (int)std::min<uint64_t>((uint64_t)world - 1, mid * (uint64_t)world / total_tests) : 0;
+        hp.local = (owner == rank);
         const HostView& vs = ctx->views[hp.src];
         const HostView& vt = ctx->views[hp.tgt];
         PairDev& d = ctx->pairs_h[p];

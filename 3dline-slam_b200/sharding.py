@@ -1,4 +1,4 @@
-"""Multi-GPU plumbing: one process per GPU, pairs sharded `p -> rank p mod N` for stages 1-2, the
+"""Multi-GPU plumbing: one process per GPU, pairs sharded in contiguous blocks (slices of reference views, balanced by test count) for stages 1-2, the
 forward-match lists of all shards all-gathered (NCCL over NVLink on the GPU box, gloo in the CPU
 tests) and merged into the canonical layout before the scoring wavefront.
 

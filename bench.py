@@ -35,6 +35,8 @@ def make_workload(scene_mod, name, n_gpus):
         return scene_mod.make_scene("c2", n_views=50 * n_gpus), "c2" if n_gpus == 1 else "c2x%d" % n_gpus
     if name == "c4":
         return scene_mod.make_scene("c4"), "c4"
+    if name == "c4s":  # BASELINE config[3] shape, 100 of the 500 views (oracle-checkable in ~1 min)
+        return scene_mod.make_scene("c4", n_views=100), "c4s"
     if name == "tiny":
         return scene_mod.make_scene("tiny"), "tiny"
     raise SystemExit("unknown workload %r" % name)

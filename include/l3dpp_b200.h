@@ -82,7 +82,7 @@ typedef struct {
     int32_t max_image_width; /* Line3D::max_image_width_, used by the bounds test line3D.cc:1142-1148 */
     int32_t filter_mode;     /* 0: FP32 guard-banded pre-filter (default); 1: none (every pair exact) */
     int32_t keep_scored;     /* 1: keep the pre-filter lists of every view (parity tests) */
-    int32_t shard_rank;      /* multi-GPU: this process matches pairs p with p % shard_world == rank */
+    int32_t shard_rank;      /* multi-GPU: this process matches the shard_rank-th of shard_world contiguous pair blocks */
     int32_t shard_world;     /* 0 or 1: no sharding */
 } l3d_params;
 

@@ -70,7 +70,7 @@ def test_device_math_bit_exact(api, oracle):
 
 
 def test_sharded_stage12_merges_to_the_same_result(api, oracle, scene_mod):
-    """Two shard contexts on one GPU (pairs p mod 2): export, merge, import -> stage 3/4 results
+    """Two shard contexts on one GPU (two contiguous pair blocks): export, merge, import -> stage 3/4 results
     identical to the unsharded run and to the oracle."""
     import ctypes as C
     sc = scene_mod.make_scene("tiny", seed=31, n_views=7, n_seg=140, nbrs=4)
