@@ -22,7 +22,7 @@ int launch_k1_pairtest(const PairDev*, const K1Cta*, uint32_t, const float4*, co
 int k1_rows_per_cta();
 int launch_k2_exact(const PairDev*, const K1Cta*, uint32_t, uint32_t, uint32_t, const float4*, const SegRays*,
                     const double*, const ViewDev*, const uint32_t*, const uint32_t*, uint32_t*, uint32_t*, uint32_t*,
-                    unsigned long long*, FwdRec*, FwdRec*, uint32_t*, float, int, int, cudaStream_t);
+                    unsigned long long*, FwdRec*, FwdRec*, uint32_t*, float, int, int, int, cudaStream_t);
 int launch_k2_compact(const uint32_t*, const uint32_t*, const uint32_t*, uint32_t, const FwdRec*, FwdRec*, uint32_t*,
                       uint32_t, cudaStream_t);
 int launch_k3_score(uint32_t, const uint32_t*, ListRec*, const ListGeo*, float, float, void*, cudaStream_t);

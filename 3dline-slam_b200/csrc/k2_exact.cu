@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(K2_ROWS) k2b_select_kernel(const uint32_t* __r
                                                              unsigned long long* __restrict__ heap,
                                                              const FwdRec* __restrict__ cand_rec,
                                                              FwdRec* __restrict__ fin_rec,
-                                                             uint32_t* __restrict__ fin_cnt, int knn)
+                                                             uint32_t* __restrict__ fin_cnt, int knn, int apply_orient)
 {
     const uint32_t lrow = blockIdx.x * blockDim.x + threadIdx.x;
     if (lrow >= n_rows) return;
@@ -269,12 +269,18 @@ __global__ void __launch_bounds__(K2_ROWS) k2b_select_kernel(const uint32_t* __r
             heap_pop(hp, hn);
             --hn;
             FwdRec rc = crec[idx];
-            if (rc.flags == 0u) frec[nout++] = rc;
+            if (rc.flags == 0u || !apply_orient) {
+                rc.flags = 0u;
+                frec[nout++] = rc;
+            }
         }
     } else {
         for (uint32_t i = 0; i < cap; ++i) {
             FwdRec rc = crec[i];
-            if (rc.flags == 0u) frec[nout++] = rc;
+            if (rc.flags == 0u || (!apply_orient && rc.flags != K2_INVALID)) {
+                rc.flags = 0u;
+                frec[nout++] = rc;
+            }
         }
     }
     fin_cnt[lrow] = nout;
@@ -300,7 +306,7 @@ int launch_k2_exact(const PairDev* pairs, const K1Cta* ctas, uint32_t n_ctas, ui
                     const float4* segs, const SegRays* rays, const double* midray, const ViewDev* views,
                     const uint32_t* mask, const uint32_t* cand_off, uint32_t* cand_c, uint32_t* cand_row,
                     uint32_t* row_pair, unsigned long long* heap, FwdRec* cand_rec, FwdRec* fin_rec, uint32_t* fin_cnt,
-                    float thr, int knn, int max_image_width, cudaStream_t st)
+                    float thr, int knn, int max_image_width, int apply_orient, cudaStream_t st)
 {
     if (n_ctas == 0) return 0;
     int launches = 0;
@@ -312,7 +318,7 @@ int launch_k2_exact(const PairDev* pairs, const K1Cta* ctas, uint32_t n_ctas, ui
         ++launches;
     }
     k2b_select_kernel<<<(n_rows + K2_ROWS - 1) / K2_ROWS, K2_ROWS, 0, st>>>(cand_off, n_rows, heap, cand_rec, fin_rec,
-                                                                            fin_cnt, knn);
+                                                                            fin_cnt, knn, apply_orient);
     ++launches;
     return launches;
 }

@@ -256,30 +256,28 @@ def make_scene(kind: str = "c2", n_views: Optional[int] = None, n_seg: Optional[
 # ----------------------------------------------------------------------------------------------
 def read_nvm(path: str):
     """Returns (cams, points): cams = list of dict(name,f,q,C,dist); points = list of
-    dict(X, obs=[(cam_idx, feat_idx, x, y), ...])."""
+    dict(X, obs=[(cam_idx, feat_idx, x, y), ...]).  Parsed line by line: the observation count the
+    writer stores (`pMP->Observations()`) can exceed the observations it actually writes (bad key
+    frames are skipped, src/System.cc:519-522), so the line length is authoritative."""
     with open(path, "r") as fh:
-        toks = fh.read().split()
-    pos = 0
-    header = toks[pos]; pos += 1
-    if not header.startswith("NVM_"):
-        raise ValueError("not an NVM file: %r" % header)
-    ncam = int(toks[pos]); pos += 1
+        lines = [ln.strip() for ln in fh.read().splitlines()]
+    lines = [ln for ln in lines if ln]
+    if not lines or not lines[0].startswith("NVM_"):
+        raise ValueError("not an NVM file: %r" % (lines[0] if lines else ""))
+    ncam = int(lines[1])
     cams = []
-    for _ in range(ncam):
-        name = toks[pos]
-        vals = [float(x) for x in toks[pos + 1:pos + 10]]
-        pos += 11  # name f qw qx qy qz Cx Cy Cz dist 0
-        cams.append(dict(name=name, f=vals[0], q=vals[1:5], C=np.array(vals[5:8]), dist=vals[8]))
-    npts = int(toks[pos]); pos += 1
+    for ln in lines[2:2 + ncam]:
+        tk = ln.split()
+        vals = [float(x) for x in tk[1:10]]   # f qw qx qy qz Cx Cy Cz dist
+        cams.append(dict(name=tk[0], f=vals[0], q=vals[1:5], C=np.array(vals[5:8]), dist=vals[8]))
+    npts = int(lines[2 + ncam])
     pts = []
-    for _ in range(npts):
-        X = np.array([float(toks[pos]), float(toks[pos + 1]), float(toks[pos + 2])])
-        nobs = int(toks[pos + 6])
-        pos += 7
+    for ln in lines[3 + ncam:3 + ncam + npts]:
+        tk = ln.split()
+        X = np.array([float(tk[0]), float(tk[1]), float(tk[2])])
         obs = []
-        for _o in range(nobs):
-            obs.append((int(toks[pos]), int(toks[pos + 1]), float(toks[pos + 2]), float(toks[pos + 3])))
-            pos += 4
+        for o in range(7, len(tk) - 3, 4):
+            obs.append((int(tk[o]), int(tk[o + 1]), float(tk[o + 2]), float(tk[o + 3])))
         pts.append(dict(X=X, obs=obs))
     return cams, pts
 

@@ -1383,4 +1383,92 @@ int orc_kat_cluster(const int* ij, const float* w, int ne, int n, int* out)
     return (int)L.cluster_ids.size();
 }
 
+
+// ---- cudawrapper-level restatements (tests of l3d_match_lines / l3d_score_matches) ----
+// Runs translate() + getFundamentalMatrix + matchingCPU(src,tgt) only (no orientation filter, no
+// scoring): what L3DPP::match_lines_GPU has to deliver (src/line3D.cc:1237-1271).  Returns the
+// matrices the GPU entry point receives (row-major F, RtKinv of both views, translated centres).
+int orc_match_only(void* h, uint32_t src, uint32_t tgt, float epi_overlap, int knn, double* F9, double* Ms9,
+                   double* Mt9, double* Cs3, double* Ct3)
+{
+    Line3D* L = (Line3D*)h;
+    if (!L->views.count(src) || !L->views.count(tgt)) return -1;
+    L->epipolar_overlap = (float)std::fmin(std::fabs((double)epi_overlap), (double)0.99f);
+    L->kNN = knn;
+    L->translate();
+    View* vs = L->views[src];
+    View* vt = L->views[tgt];
+    const M3 F = L->fundamental(vs, vt);
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            F9[3 * i + j] = F.m[i][j];
+            Ms9[3 * i + j] = vs->RtKinv.m[i][j];
+            Mt9[3 * i + j] = vt->RtKinv.m[i][j];
+        }
+    Cs3[0] = vs->C.x; Cs3[1] = vs->C.y; Cs3[2] = vs->C.z;
+    Ct3[0] = vt->C.x; Ct3[1] = vt->C.y; Ct3[2] = vt->C.z;
+    L->matchingCPU(src, tgt, F);
+    return 0;
+}
+
+// Line3D::scoringCPU new-match branch (src/line3D.cc:1513-1547) over the packed buffers of
+// Line3D::scoringGPU (src/line3D.cc:1582-1623): matches = {srcSeg, tgtCam, d_p1, d_p2} per entry,
+// ranges = {first,last} per segment, regs_tgt = {sigma_tgt(P1), sigma_tgt(P2)}.
+void orc_score_packed(const float* lines, uint32_t n_lines, const float* matches, uint32_t n_matches,
+                      const int32_t* ranges, const float* regs_tgt, const double* RtKinv9, const double* C3,
+                      float two_sigA_sqr, float k, float min_sim, float* scores)
+{
+    Line3D L(640, false);
+    L.two_sigA_sqr = two_sigA_sqr;
+    View v;
+    v.RtKinv = toM3(RtKinv9);
+    v.C = {C3[0], C3[1], C3[2]};
+    v.lines.resize(n_lines);
+    for (uint32_t i = 0; i < n_lines; ++i) v.lines[i] = {lines[4 * i], lines[4 * i + 1], lines[4 * i + 2], lines[4 * i + 3]};
+    for (uint32_t i = 0; i < n_matches; ++i) scores[i] = 0.0f;
+    for (uint32_t s = 0; s < n_lines; ++s) {
+        const int a = ranges[2 * s], b = ranges[2 * s + 1];
+        if (a < 0) continue;
+        for (int e = a; e <= b; ++e) {
+            const uint32_t seg = (uint32_t)matches[4 * e];
+            const uint32_t cam = (uint32_t)matches[4 * e + 1];
+            const float d1 = matches[4 * e + 2], d2 = matches[4 * e + 3];
+            const Seg3D M3D = v.unproject(seg, d1, d2);
+            const float sig1 = d1 * k, sig2 = d2 * k;
+            float reg1 = 2.0f * sig1 * sig1, reg2 = 2.0f * sig2 * sig2;
+            const float s1t = regs_tgt[2 * e], s2t = regs_tgt[2 * e + 1];
+            reg1 = 0.5f * (reg1 + 2.0f * s1t * s1t);
+            reg2 = 0.5f * (reg2 + 2.0f * s2t * s2t);
+            std::map<uint32_t, float> per_cam;
+            float score = 0.0f;
+            for (int e2 = a; e2 <= b; ++e2) {
+                const uint32_t cam2 = (uint32_t)matches[4 * e2 + 1];
+                if (cam2 == cam) continue;
+                const Seg3D S2 = v.unproject((uint32_t)matches[4 * e2], matches[4 * e2 + 2], matches[4 * e2 + 3]);
+                float sim = 0.0f;
+                if (!(M3D.length < EPS || S2.length < EPS)) {
+                    const float dd1 = d1 - matches[4 * e2 + 2], dd2 = d2 - matches[4 * e2 + 3];
+                    const float sim_p = std::fmin(orc_expf(-dd1 * dd1 / reg1), orc_expf(-dd2 * dd2 / reg2));
+                    const float angle = Line3D::angleBetweenSeg3D(M3D, S2, true);
+                    const float sim_a = orc_expf(-angle * angle / two_sigA_sqr);
+                    const float sm = std::fmin(sim_a, sim_p);
+                    sim = (sm > min_sim) ? sm : 0.0f;
+                }
+                auto f = per_cam.find(cam2);
+                if (f != per_cam.end()) {
+                    if (sim > f->second) {
+                        score -= f->second;
+                        score += sim;
+                        f->second = sim;
+                    }
+                } else {
+                    score += sim;
+                    per_cam[cam2] = sim;
+                }
+            }
+            scores[e] = score;
+        }
+    }
+}
+
 }  // extern "C"

@@ -96,6 +96,10 @@ def lib():
         L.orc_kat_dist_point_line.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_kat_cluster.restype = C.c_int
         L.orc_kat_cluster.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.orc_match_only.restype = C.c_int
+        L.orc_match_only.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_float, C.c_int] + [C.c_void_p] * 5
+        L.orc_score_packed.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_void_p]
         _LIB = L
     return _LIB
 
@@ -235,6 +239,15 @@ class OracleLine3D:
     def med_scene_depth_lines(self):
         return float(self.L.orc_med_scene_depth_lines(self.h))
 
+    def match_only(self, src, tgt, epi_overlap=0.25, knn=10):
+        """translate + F + matchingCPU(src,tgt) only; returns (F, RtKinv_src, RtKinv_tgt, C_src, C_tgt)."""
+        F, Ms, Mt = np.zeros(9), np.zeros(9), np.zeros(9)
+        Cs, Ct = np.zeros(3), np.zeros(3)
+        rc = self.L.orc_match_only(self.h, int(src), int(tgt), float(epi_overlap), int(knn), _p(F), _p(Ms), _p(Mt),
+                                   _p(Cs), _p(Ct))
+        assert rc == 0
+        return F, Ms, Mt, Cs, Ct
+
     def timers(self):
         t = np.zeros(10)
         self.L.orc_get_timers(self.h, _p(t))
@@ -250,3 +263,17 @@ def run_scene(scene, threads=0, snapshot=True, reconstruct=True):
     if reconstruct:
         o.reconstruct()
     return o
+
+
+def score_packed(lines, matches, ranges, regs_tgt, RtKinv, Cc, two_sigA_sqr, k, min_sim=0.5):
+    """Oracle restatement of scoringCPU's new-match branch over scoringGPU's packed buffers."""
+    L = lib()
+    lines = np.ascontiguousarray(lines, dtype=np.float32)
+    matches = np.ascontiguousarray(matches, dtype=np.float32)
+    ranges = np.ascontiguousarray(ranges, dtype=np.int32)
+    regs = np.ascontiguousarray(regs_tgt, dtype=np.float32)
+    M, Cc = _f64(RtKinv), _f64(Cc)
+    out = np.zeros(matches.shape[0], dtype=np.float32)
+    L.orc_score_packed(_p(lines), lines.shape[0], _p(matches), matches.shape[0], _p(ranges), _p(regs), _p(M), _p(Cc),
+                       float(two_sigA_sqr), float(k), float(min_sim), _p(out))
+    return out

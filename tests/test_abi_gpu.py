@@ -1,0 +1,141 @@
+"""GPU: the cudawrapper-level C ABI entry points (host buffers in/out) against the oracle, and the
+error behaviour / edge cases of the Line3D-level entry points."""
+import numpy as np
+import pytest
+
+from parity_utils import assert_struct_equal, compare_full
+
+pytestmark = pytest.mark.gpu
+
+
+def _two_view_scene(scene_mod, seed=3, n_seg=220):
+    sc = scene_mod.make_scene("tiny", seed=seed, n_views=4, n_seg=n_seg, nbrs=3)
+    return sc, sc.views[1], sc.views[2]
+
+
+@pytest.mark.parametrize("knn", [10, 2, -1])
+def test_match_lines_equals_matchingCPU(api, oracle, scene_mod, knn):
+    """l3d_match_lines = the drop-in for L3DPP::match_lines_GPU: Line3D::matchingCPU's list."""
+    sc, va, vb = _two_view_scene(scene_mod)
+    o = oracle.OracleLine3D(sc.max_image_width, False)
+    o.load_scene(sc)
+    F, Ms, Mt, Cs, Ct = o.match_only(va.cam_id, vb.cam_id, 0.25, knn)
+    off_o, rec_o = o.lists(va.cam_id, 1)          # matches_[src] right after matchingCPU
+    ctx = api.Context()
+    got, off_g = ctx.match_lines(va.segs, vb.segs, F, Ms, Mt, Cs, Ct, va.cam_id, vb.cam_id, 0.25, knn,
+                                 sc.max_image_width)
+    assert (off_g == off_o).all()
+    assert len(got) == len(rec_o) > 0
+    assert (got["tgt_seg"] == rec_o["tgt_seg"]).all() and (got["tgt_cam"] == vb.cam_id).all()
+    rows = np.repeat(np.arange(len(off_o) - 1), np.diff(off_o.astype(np.int64)))
+    assert (got["src_seg"] == rows).all()
+    for a, b in (("overlap", "overlap"), ("d_p1", "d_p1"), ("d_p2", "d_p2"), ("d_q1", "d_q1"), ("d_q2", "d_q2")):
+        assert (got[a].view(np.uint32) == rec_o[b].view(np.uint32)).all(), a
+    # the FP32 pre-filter must not change anything
+    got2, _ = ctx.match_lines(va.segs, vb.segs, F, Ms, Mt, Cs, Ct, va.cam_id, vb.cam_id, 0.25, knn,
+                              sc.max_image_width, filter_mode=1)
+    assert got2.tobytes() == got.tobytes()
+
+
+def test_match_lines_empty_and_capacity(api, scene_mod):
+    sc, va, vb = _two_view_scene(scene_mod)
+    ctx = api.Context()
+    I = np.eye(3)
+    out, off = ctx.match_lines(np.zeros((0, 4), np.float32), vb.segs, I, I, I, np.zeros(3), np.ones(3), 1, 2, 0.25, 10, 640)
+    assert len(out) == 0 and len(off) == 1
+    with pytest.raises(api.L3DError):
+        ctx.match_lines(va.segs, vb.segs, I, I, I, np.zeros(3), np.ones(3), 7, 7, 0.25, 10, 640)  # same camera id
+
+
+def test_score_matches_equals_scoringCPU(api, oracle, scene_mod):
+    """l3d_score_matches = the drop-in for L3DPP::score_matches_GPU, on buffers packed the way
+    Line3D::scoringGPU packs them (sorted by target camera/segment, src/line3D.cc:1579-1623)."""
+    sc = scene_mod.make_scene("tiny", seed=11)
+    orc = oracle.run_scene(sc)
+    v = sc.views[3]
+    off, rec = orc.lists(v.cam_id, 0)
+    info = orc.view_info(v.cam_id)
+    n = len(v.segs)
+    matches, ranges, regs = [], np.full((n, 2), -1, np.int32), []
+    rng = np.random.default_rng(0)
+    for i in range(n):
+        r = rec[off[i]:off[i + 1]]
+        if len(r) == 0:
+            continue
+        order = np.lexsort((r["tgt_seg"], r["tgt_cam"]))       # sortMatchesByIDs
+        ranges[i] = (len(matches), len(matches) + len(r) - 1)
+        for e in r[order]:
+            matches.append((float(i), float(e["tgt_cam"]), e["d_p1"], e["d_p2"]))
+            regs.append((abs(rng.normal(0.03, 0.01)), abs(rng.normal(0.03, 0.01))))
+    matches = np.asarray(matches, np.float32)
+    regs = np.asarray(regs, np.float32)
+    # any consistent camera works for the entry point: use K^-1 with R = I, C = 0
+    RtKinv = np.linalg.inv(v.K)
+    Cc = np.array([0.1, -0.2, 0.3])
+    exp = oracle.score_packed(v.segs, matches, ranges, regs, RtKinv, Cc, 200.0, float(info["k"]), 0.5)
+    got = api.Context().score_matches(v.segs, matches, ranges, regs, RtKinv, Cc, 200.0, float(info["k"]), 0.5)
+    assert (got.view(np.uint32) == exp.view(np.uint32)).all()
+    assert (got > 0.75).sum() > 0
+    # a lower truncation threshold disables the early exits: still identical
+    exp2 = oracle.score_packed(v.segs, matches, ranges, regs, RtKinv, Cc, 200.0, float(info["k"]), 0.25)
+    got2 = api.Context().score_matches(v.segs, matches, ranges, regs, RtKinv, Cc, 200.0, float(info["k"]), 0.25)
+    assert (got2.view(np.uint32) == exp2.view(np.uint32)).all()
+
+
+def test_ragged_views_and_degenerate_segments(api, oracle, scene_mod):
+    """Different segment counts per view, zero-length and out-of-image segments, a neighbour id that
+    does not exist."""
+    sc = scene_mod.make_scene("tiny", seed=21, n_views=6, n_seg=150, nbrs=3)
+    for i, v in enumerate(sc.views):
+        s = v.segs[:150 - 17 * i].copy()
+        s[5] = (100.0, 100.0, 100.0, 100.0)            # zero length
+        s[6] = (-50.0, 20.0, 700.0, 500.0)              # leaves the image
+        s[7, 2:] = s[7, :2] + 0.25                      # shorter than one pixel
+        v.segs = s
+    sc.views[2].neighbors = sc.views[2].neighbors + [999]   # unknown camera: ignored (src/line3D.cc:612)
+    orc = oracle.run_scene(sc)
+    l3 = api.run_scene(sc, keep_scored=True)
+    compare_full(l3, orc, sc)
+
+
+def test_no_matches_at_all(api, oracle, scene_mod):
+    """A bounds window of 1 px rejects every pair: empty lists, no hypotheses, no edges."""
+    sc = scene_mod.make_scene("tiny", seed=5, n_views=4, n_seg=60, nbrs=2)
+    sc.max_image_width = 1
+    orc = oracle.run_scene(sc)
+    l3 = api.run_scene(sc, keep_scored=True)
+    sizes = compare_full(l3, orc, sc)
+    assert sizes["entries"] == 0 and sizes["edges"] == 0
+    assert l3.counts()["forward_matches"] == 0
+
+
+def test_error_behaviour_mirrors_addImage(api, scene_mod):
+    """Argument checks of Line3D::addImage (src/line3D.cc:123-205) surface as errors, not crashes."""
+    import ctypes as C
+    sc = scene_mod.make_scene("tiny", seed=1, n_views=3, n_seg=40, nbrs=2)
+    v = sc.views[0]
+    l3 = api.Line3D("", False, 640)
+    L, h = l3.L, l3.h
+    assert L.l3d_scene_begin(h) == 0
+
+    def add(cam, w, hh, segs, nb):
+        vv = api.View()
+        vv.cam_id, vv.width, vv.height, vv.num_segs = cam, w, hh, len(segs)
+        vv.K[:] = v.K.ravel().tolist(); vv.R[:] = v.R.ravel().tolist(); vv.t[:] = v.t.tolist()
+        nb = np.asarray(nb, np.uint32)
+        segs = np.ascontiguousarray(segs, np.float32)
+        return L.l3d_scene_add_view(h, C.byref(vv), segs.ctypes.data, nb.ctypes.data, nb.size)
+
+    assert add(0, 320, 240, v.segs, [1]) == -1 and b"too small" in L.l3d_last_error()
+    assert add(0, 640, 480, v.segs, [1]) == 0
+    assert add(0, 640, 480, v.segs, [1]) == -1 and b"already in use" in L.l3d_last_error()
+    assert add(1, 640, 480, v.segs, []) == -1 and b"no visual neighbors" in L.l3d_last_error()
+    assert add(2, 640, 480, v.segs[:0], [0]) == -1 and b"no line segments" in L.l3d_last_error()
+    # state errors
+    assert L.l3d_affinity(h) == -3 and b"has not run" in L.l3d_last_error()
+    p = api.Params()
+    p.sigma_p, p.sigma_a, p.num_neighbors, p.epipolar_overlap, p.knn, p.max_image_width = 5, 10, 10, 0.25, 10, -1
+    assert L.l3d_scene_commit(h) == 0
+    assert L.l3d_match_images(h, C.byref(p)) == -1 and b"max_image_width" in L.l3d_last_error()
+    with pytest.raises(api.L3DError):
+        api.Line3D("", False, 640, 3000, True)      # neighbors_by_worldpoints is not supported
