@@ -121,6 +121,7 @@ int l3d_scene_commit(l3d_ctx* ctx)
     CK(ctx->d_desc.ensure(S));
     CK(ctx->d_rays.ensure(S));
     CK(ctx->d_midray.ensure(3 * S));
+    CK(ctx->d_planes.ensure(S));
     CK(ctx->d_view_xb.ensure(V));
     CK(ctx->d_views.ensure(V));
     CK(cudaMemcpyAsync(ctx->d_segs.p, hseg, S * sizeof(float4), cudaMemcpyHostToDevice, st));
@@ -406,7 +407,7 @@ int l3d_match_stage12(l3d_ctx* ctx, const l3d_params* params)
     cudaEvent_t ev = ctx->tm.begin(L3D_T_PREP, st);
     CK(cudaMemsetAsync(ctx->d_view_xb.p, 0, V * sizeof(float), st));
     ctx->cnt.gpu_launches += launch_k0_prep(ctx->d_segs.p, ctx->d_seg_view.p, ctx->d_views.p, S,
-                                            ctx->prm.max_image_width, ctx->d_desc.p, ctx->d_rays.p, ctx->d_midray.p,
+                                            ctx->prm.max_image_width, ctx->d_desc.p, ctx->d_rays.p, ctx->d_midray.p, ctx->d_planes.p,
                                             ctx->d_view_xb.p, st);
     ctx->tm.end(ev, st);
 
@@ -459,14 +460,11 @@ int l3d_match_stage12(l3d_ctx* ctx, const l3d_params* params)
         CK(ctx->d_heap.ensure((size_t)n_cand + 1));
         CK(ctx->d_cand_rec.ensure((size_t)n_cand + 1));
         CK(ctx->d_fin_rec.ensure((size_t)n_cand + 1));
-        CK(ctx->d_cand_c.ensure((size_t)n_cand + 1));
-        CK(ctx->d_cand_row.ensure((size_t)n_cand + 1));
-        CK(ctx->d_row_pair.ensure((size_t)b.n_rows + 1));
         cudaEvent_t e2 = ctx->tm.begin(L3D_T_EXACT, st);
         ctx->cnt.gpu_launches +=
             launch_k2_exact(ctx->d_pairs.p, ctx->d_ctas.p + b.cta0, b.n_ctas, b.n_rows, n_cand, ctx->d_segs.p,
-                            ctx->d_rays.p, ctx->d_midray.p, ctx->d_views.p, ctx->d_mask.p, ctx->d_cand_off.p,
-                            ctx->d_cand_c.p, ctx->d_cand_row.p, ctx->d_row_pair.p, ctx->d_heap.p, ctx->d_cand_rec.p,
+                            ctx->d_rays.p, ctx->d_midray.p, ctx->d_planes.p, ctx->d_views.p, ctx->d_mask.p, ctx->d_cand_off.p,
+                            ctx->d_heap.p, ctx->d_cand_rec.p,
                             ctx->d_fin_rec.p, ctx->d_fin_cnt.p, ctx->epi_overlap, ctx->prm.knn,
                             ctx->prm.max_image_width, ctx->raw_mode ? 0 : 1, st);
         ctx->cnt.gpu_launches +=
@@ -506,10 +504,14 @@ int l3d_match_stage3(l3d_ctx* ctx)
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     const uint32_t V = (uint32_t)ctx->views.size(), P = (uint32_t)ctx->pairs.size(), S = ctx->S;
-    for (uint32_t v = 0; v < V; ++v)
-        if (ctx->inc_off_h[v + 1] - ctx->inc_off_h[v] > (uint32_t)k3_wf_max_inc())
+    uint32_t max_inc = 0;
+    for (uint32_t v = 0; v < V; ++v) {
+        const uint32_t n = ctx->inc_off_h[v + 1] - ctx->inc_off_h[v];
+        if (n > (uint32_t)k3_wf_max_inc())
             return fail(L3D_ERR_CAPACITY, "view %u takes part in more than %d matched pairs", ctx->views[v].v.cam_id,
                         k3_wf_max_inc());
+        max_inc = std::max(max_inc, n);
+    }
 
     cudaEvent_t ev_total = ctx->tm.begin(L3D_T_TOTAL, st);
     cudaEvent_t ev = ctx->tm.begin(L3D_T_SCORE, st);
@@ -525,25 +527,34 @@ int l3d_match_stage3(l3d_ctx* ctx)
     CK(ctx->d_inv_fill.ensure(TR + 1));
     CK(ctx->d_inv_off.ensure(TR + 2));
     CK(ctx->d_inv_ent.ensure(F + 1));
+    CK(ctx->d_fwd_row.ensure(F + 1));
     CK(cudaMemsetAsync(ctx->d_inv_cap.p, 0, (TR + 1) * 4, st));
     CK(cudaMemsetAsync(ctx->d_inv_fill.p, 0, (TR + 1) * 4, st));
     CK(ctx->d_scan.ensure(scan_scratch_words((uint32_t)std::max<size_t>(TR, S) + 2) + 64));
     CK(ctx->d_L_ub.ensure((size_t)S + 1));
     CK(ctx->d_L_off.ensure((size_t)S + 2));
     CK(ctx->d_L_cnt.ensure((size_t)S + 1));
-    CK(cudaMemsetAsync(ctx->d_L_cnt.p, 0, ((size_t)S + 1) * 4, st));
+    CK(ctx->d_stats.ensure(k3_wf_stats_bytes()));
+    CK(cudaMemsetAsync(ctx->d_stats.p, 0, k3_wf_stats_bytes(), st));
+    CK(ctx->d_G_fwd.ensure((F + 1) * k3_geo_bytes()));
+    CK(ctx->d_G_inv.ensure((F + 1) * k3_geo_bytes()));
 
-    // pre-pass: CSR slots of the inverse matches and of the lists, from upper bounds
+    // pre-pass: row of every forward record, the (static) inverse-match slots, the potential lists
     ctx->cnt.gpu_launches += launch_k3_inv_capacity(ctx->d_pairs.p, P, ctx->total_rows, ctx->d_fwd_off.p,
-                                                    ctx->d_fwd_cnt.p, ctx->d_fwd_rec.p, ctx->d_inv_cap.p, st);
+                                                    ctx->d_fwd_cnt.p, ctx->d_fwd_rec.p, ctx->d_fwd_row.p,
+                                                    ctx->d_inv_cap.p, st);
     ctx->cnt.gpu_launches +=
         launch_scan_u32(ctx->d_inv_cap.p, ctx->d_inv_off.p, (uint32_t)TR, ctx->d_scan.p, ctx->d_scan.cap, st);
     ctx->cnt.gpu_launches +=
+        launch_k3_records(ctx->d_pairs.p, P, (uint32_t)F, ctx->d_views.p, ctx->d_rays.p, ctx->d_fwd_row.p,
+                          ctx->d_fwd_rec.p, ctx->d_G_fwd.p, ctx->d_G_inv.p, ctx->d_inv_off.p, ctx->d_inv_fill.p,
+                          ctx->d_inv_ent.p, st);
+    ctx->cnt.gpu_launches +=
         launch_k3_list_capacity(ctx->d_views.p, ctx->d_seg_view.p, S, ctx->d_inc.p, ctx->d_inc_off.p, ctx->d_pairs.p,
-                                ctx->d_fwd_cnt.p, ctx->d_inv_cap.p, ctx->d_L_ub.p, st);
+                                ctx->d_fwd_cnt.p, ctx->d_inv_cap.p, ctx->d_L_ub.p, ctx->d_stats.p, st);
     ctx->cnt.gpu_launches += launch_scan_u32(ctx->d_L_ub.p, ctx->d_L_off.p, S, ctx->d_scan.p, ctx->d_scan.cap, st);
 
-    // list regions: forward records of the view's own pairs + of the pairs pointing at it
+    // potential lists: forward records of the view's own pairs + of the pairs pointing at it
     std::vector<uint64_t>& cap = ctx->L_cap_h;
     cap.assign(V, 0);
     for (uint32_t p = 0; p < P; ++p) {
@@ -552,93 +563,106 @@ int l3d_match_stage3(l3d_ctx* ctx)
     }
     const bool keep = ctx->prm.keep_scored != 0;
     ctx->L_base_h.assign(V + 1, 0);
-    uint64_t Lcap = 0, maxcap = 0;
-    uint32_t maxN = 0;
+    uint64_t Lcap = 0;
     for (uint32_t v = 0; v < V; ++v) {
-        maxcap = std::max(maxcap, cap[v]);
-        maxN = std::max(maxN, ctx->views[v].v.num_segs);
-    }
-    if (keep) {
-        for (uint32_t v = 0; v < V; ++v) {
-            ctx->L_base_h[v] = Lcap;
-            Lcap += cap[v];
-        }
-    } else {
-        for (uint32_t v = 0; v < V; ++v) ctx->L_base_h[v] = (v & 1) ? maxcap : 0;  // double buffer
-        Lcap = 2 * maxcap;
+        ctx->L_base_h[v] = Lcap;  // == L_off[first segment of v]
+        Lcap += cap[v];
     }
     if (Lcap > 0xfffffff0ull || 2 * F > 0xfffffff0ull) return fail(L3D_ERR_CAPACITY, "match lists too large");
-    CK(ctx->d_L_base.ensure((size_t)V + 1));
-    CK(cudaMemcpyAsync(ctx->d_L_base.p, ctx->L_base_h.data(), ((size_t)V + 1) * 8, cudaMemcpyHostToDevice, st));
-    CK(ctx->d_L_rec.ensure(Lcap + 1));
-    CK(ctx->d_L_sib.ensure((Lcap + 1) * k3_sib_bytes()));
-    CK(ctx->d_L_dir.ensure(3 * (Lcap + 1)));
-    CK(ctx->d_L_reg.ensure(Lcap + 1));
+    CK(ctx->d_L_f.ensure(Lcap + 1));
+    CK(ctx->d_L_meta.ensure(Lcap + 1));
+    CK(ctx->d_L_score.ensure(Lcap + 1));
+    CK(cudaMemsetAsync(ctx->d_L_score.p, 0, (Lcap + 1) * 4, st));
+    if (keep) CK(ctx->d_L_rec.ensure(Lcap + 1));
+    // rows are staged in shared memory up to maxm entries (an inverse block is not bounded by kNN:
+    // any number of source segments may match the same target segment): read the longest list back
+    uint32_t maxm = (uint32_t)k3_max_staged();
+    bool big_rows = true;
+    {
+        uint32_t dev_max = 0;  // WfStats::max_list
+        CK(cudaMemcpyAsync(&dev_max, ctx->d_stats.p + 36, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        big_rows = dev_max > maxm;
+        maxm = std::max<uint32_t>(std::min(dev_max, maxm), 1u);
+    }
+    if (const char* ov = getenv("L3D_K3_MAXM")) {  // test hook: force the long-row path
+        maxm = (uint32_t)std::max(1, atoi(ov));
+        big_rows = true;
+    }
+    if (big_rows) {
+        CK(ctx->d_L_sib.ensure((Lcap + 1) * k3_sib_bytes()));
+        CK(ctx->d_L_dir.ensure(3 * (Lcap + 1)));
+        CK(ctx->d_L_reg.ensure(Lcap + 1));
+        CK(ctx->d_L_c.ensure(Lcap + S + 2));
+        CK(ctx->d_L_h.ensure(Lcap + S + 2));
+    }
     const size_t filt_cap = 2 * F + 1;
     CK(ctx->d_filt_rec.ensure(filt_cap));
     CK(ctx->d_filt_off.ensure((size_t)S + 1));
     CK(ctx->d_filt_cnt.ensure((size_t)S + 1));
-    CK(cudaMemsetAsync(ctx->d_filt_cnt.p, 0, ((size_t)S + 1) * 4, st));
-    CK(cudaMemsetAsync(ctx->d_filt_off.p, 0, ((size_t)S + 1) * 4, st));
     CK(ctx->d_view_max.ensure((size_t)V + 1));
     CK(cudaMemsetAsync(ctx->d_view_max.p, 0, ((size_t)V + 1) * 4, st));
     CK(ctx->d_small.ensure(16));
     CK(cudaMemsetAsync(ctx->d_small.p, 0, 16 * 4, st));
-    CK(ctx->d_stats.ensure(k3_wf_stats_bytes()));
-    CK(cudaMemsetAsync(ctx->d_stats.p, 0, k3_wf_stats_bytes(), st));
     CK(ctx->d_entries.ensure((size_t)S + 1));
-
-    CK(ctx->d_G_fwd.ensure((F + 1) * k3_geo_bytes()));
-    CK(ctx->d_G_inv.ensure((F + 1) * k3_geo_bytes()));
-    ctx->cnt.gpu_launches +=
-        launch_k3_geom(ctx->d_pairs.p, P, ctx->total_rows, ctx->d_views.p, ctx->d_rays.p, ctx->d_fwd_off.p,
-                       ctx->d_fwd_cnt.p, ctx->d_fwd_rec.p, ctx->d_G_fwd.p, ctx->d_G_inv.p, st);
-    DevBuf<uint32_t> dbg;  // developer aid: L3D_WF_DEBUG=<file> dumps per-row cycle counters
-    const char* dbg_path = getenv("L3D_WF_DEBUG");
-    if (dbg_path) {
-        CK(dbg.ensure(4 * (size_t)S + 4));
-        CK(cudaMemsetAsync(dbg.p, 0, (4 * (size_t)S + 4) * 4, st));
-    }
-    int cuerr = 0;
-    const int nl = launch_k3_wavefront(
-        ctx->d_views.p, ctx->d_pairs.p, ctx->d_inc.p, ctx->d_inc_off.p, ctx->d_rays.p, ctx->d_fwd_off.p,
-        ctx->d_fwd_cnt.p, ctx->d_fwd_rec.p, ctx->d_G_fwd.p, ctx->d_G_inv.p, ctx->d_inv_off.p, ctx->d_inv_fill.p,
-        ctx->d_inv_ent.p, ctx->d_L_off.p,
-        ctx->d_L_base.p, ctx->d_L_cnt.p, ctx->d_L_rec.p, ctx->d_L_sib.p, ctx->d_L_dir.p, ctx->d_L_reg.p,
-        ctx->d_view_max.p, ctx->d_filt_rec.p, (uint32_t)filt_cap, ctx->d_filt_off.p, ctx->d_filt_cnt.p,
-        ctx->d_entries.p, ctx->d_stats.p, V, maxN, ctx->two_sigA_sqr, dbg.p, st, &cuerr);
-    if (nl < 0)
-        return fail(L3D_ERR_CUDA, "cooperative launch of the scoring wavefront failed: %s",
-                    cudaGetErrorString((cudaError_t)cuerr));
-    if (dbg_path) {
-        std::vector<uint32_t> hd(4 * (size_t)S);
-        CK(cudaMemcpyAsync(hd.data(), dbg.p, hd.size() * 4, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        if (FILE* fp = fopen(dbg_path, "wb")) {
-            fwrite(hd.data(), 4, hd.size(), fp);
-            fclose(fp);
-        }
-    }
-    ctx->cnt.gpu_launches += nl;
-
-    // estimated_position3D_ index (canonical order = global segment order) and median depths
-    CK(ctx->d_has.ensure((size_t)S + 1));
-    CK(ctx->d_entry_idx.ensure((size_t)S + 2));
-    ctx->cnt.gpu_launches += launch_k4_has(ctx->d_entries.p, S, ctx->d_has.p, st);
-    ctx->cnt.gpu_launches += launch_scan_u32(ctx->d_has.p, ctx->d_entry_idx.p, S, ctx->d_scan.p, ctx->d_scan.cap, st);
-    ctx->cnt.gpu_launches += launch_k4_median(ctx->d_views.p, V, ctx->d_entries.p, ctx->d_small.p + 2, st);
-    ctx->tm.end(ev, st);
-    ctx->tm.end(ev_total, st);
+    CK(ctx->d_prog_off.ensure((size_t)S + 1));
+    CK(ctx->d_prog_nh.ensure((size_t)S + 1));
+    if (ctx->prog_cap == 0) ctx->prog_cap = std::max<uint64_t>(24ull * S + 1024, 4096);
 
     uint32_t small[4] = {0, 0, 0, 0};
     uint32_t n_entries = 0;
     std::vector<unsigned char> acc(k3_wf_stats_bytes());
     std::vector<ViewDev> vd(V);
-    CK(cudaMemcpyAsync(small, ctx->d_small.p, sizeof(small), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(&n_entries, ctx->d_entry_idx.p + S, 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(acc.data(), ctx->d_stats.p, acc.size(), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(vd.data(), ctx->d_views.p, V * sizeof(ViewDev), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    for (int attempt = 0;; ++attempt) {
+        if (ctx->prog_cap > 0xfffffff0ull) return fail(L3D_ERR_CAPACITY, "fold programs too large");
+        CK(ctx->d_prog.ensure(ctx->prog_cap * 16));
+        int cuerr = 0;
+        const int nl = launch_k3_dataflow(
+            ctx->d_views.p, ctx->d_seg_view.p, ctx->d_pairs.p, ctx->d_inc.p, ctx->d_inc_off.p, ctx->d_rays.p,
+            ctx->d_fwd_off.p, ctx->d_fwd_cnt.p, ctx->d_fwd_rec.p, ctx->d_fwd_row.p, ctx->d_G_fwd.p, ctx->d_G_inv.p,
+            ctx->d_inv_off.p, ctx->d_inv_fill.p, ctx->d_inv_ent.p, ctx->d_L_off.p, ctx->d_L_f.p, ctx->d_L_meta.p,
+            ctx->d_L_score.p, big_rows ? ctx->d_L_sib.p : nullptr, big_rows ? ctx->d_L_dir.p : nullptr,
+            big_rows ? ctx->d_L_reg.p : nullptr, big_rows ? ctx->d_L_c.p : nullptr, big_rows ? ctx->d_L_h.p : nullptr,
+            ctx->d_prog_off.p, ctx->d_prog_nh.p, ctx->d_prog.p, (uint32_t)ctx->prog_cap, ctx->d_L_cnt.p,
+            keep ? ctx->d_L_rec.p : nullptr, ctx->d_view_max.p, ctx->d_filt_rec.p, (uint32_t)filt_cap,
+            ctx->d_filt_off.p, ctx->d_filt_cnt.p, ctx->d_entries.p, ctx->d_stats.p, S, maxm, ctx->two_sigA_sqr, st,
+            &cuerr);
+        if (nl < 0)
+            return fail(L3D_ERR_CUDA, "launch of the scoring kernels failed: %s", cudaGetErrorString((cudaError_t)cuerr));
+        ctx->cnt.gpu_launches += nl;
+
+        // estimated_position3D_ index (canonical order = global segment order) and median depths
+        CK(ctx->d_has.ensure((size_t)S + 1));
+        CK(ctx->d_entry_idx.ensure((size_t)S + 2));
+        ctx->cnt.gpu_launches += launch_k4_has(ctx->d_entries.p, S, ctx->d_has.p, st);
+        ctx->cnt.gpu_launches +=
+            launch_scan_u32(ctx->d_has.p, ctx->d_entry_idx.p, S, ctx->d_scan.p, ctx->d_scan.cap, st);
+        ctx->cnt.gpu_launches += launch_k4_median(ctx->d_views.p, V, ctx->d_entries.p, ctx->d_small.p + 2, st);
+        CK(cudaMemcpyAsync(small, ctx->d_small.p, sizeof(small), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&n_entries, ctx->d_entry_idx.p + S, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(acc.data(), ctx->d_stats.p, acc.size(), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(vd.data(), ctx->d_views.p, V * sizeof(ViewDev), cudaMemcpyDeviceToHost, st));
+        if (attempt == 0) {
+            ctx->tm.end(ev, st);
+            ctx->tm.end(ev_total, st);
+        }
+        CK(cudaStreamSynchronize(st));
+        const uint32_t* a32 = (const uint32_t*)(acc.data() + 16);
+        if (!(a32[2] & 4u)) break;
+        // the fold programs did not fit: grow the store and run the scoring kernels again
+        // (the record kernel resets the scores the aborted pass may have left behind)
+        if (attempt >= 8) return fail(L3D_ERR_CAPACITY, "fold program store overflow");
+        ctx->prog_cap = std::max<uint64_t>(2 * ctx->prog_cap, (uint64_t)a32[3] + 1024);
+        CK(cudaMemsetAsync(ctx->d_stats.p, 0, k3_wf_stats_bytes(), st));
+        CK(cudaMemsetAsync(ctx->d_inv_fill.p, 0, (TR + 1) * 4, st));
+        CK(cudaMemsetAsync(ctx->d_L_score.p, 0, (Lcap + 1) * 4, st));
+        CK(cudaMemsetAsync(ctx->d_view_max.p, 0, ((size_t)V + 1) * 4, st));
+        CK(cudaMemsetAsync(ctx->d_small.p, 0, 16 * 4, st));
+        ctx->cnt.gpu_launches +=
+            launch_k3_records(ctx->d_pairs.p, P, (uint32_t)F, ctx->d_views.p, ctx->d_rays.p, ctx->d_fwd_row.p,
+                              ctx->d_fwd_rec.p, ctx->d_G_fwd.p, ctx->d_G_inv.p, ctx->d_inv_off.p, ctx->d_inv_fill.p,
+                              ctx->d_inv_ent.p, st);
+    }
     ctx->tm.collect();
     {
         const unsigned long long* a64 = (const unsigned long long*)acc.data();
@@ -647,6 +671,7 @@ int l3d_match_stage3(l3d_ctx* ctx)
         ctx->cnt.scored_entries = a64[1];
         ctx->cnt.filtered_entries = a32[1];  // filt_cursor
         if (a32[2] & 2u) return fail(L3D_ERR_CAPACITY, "filtered-match store overflow");
+        if (a32[2] & 8u) return fail(L3D_ERR_STATE, "internal: scoring dependency wait timed out");
     }
     if (small[2]) return fail(L3D_ERR_CAPACITY, "more than 8192 hypotheses in one view (median-depth kernel)");
     ctx->cnt.num_entries = n_entries;

@@ -21,27 +21,28 @@ int launch_k1_pairtest(const PairDev*, const K1Cta*, uint32_t, const float4*, co
                        uint32_t*, float, int, cudaStream_t);
 int k1_rows_per_cta();
 int launch_k2_exact(const PairDev*, const K1Cta*, uint32_t, uint32_t, uint32_t, const float4*, const SegRays*,
-                    const double*, const ViewDev*, const uint32_t*, const uint32_t*, uint32_t*, uint32_t*, uint32_t*,
-                    unsigned long long*, FwdRec*, FwdRec*, uint32_t*, float, int, int, int, cudaStream_t);
+                    const double*, const SegPlane*, const ViewDev*, const uint32_t*, const uint32_t*, unsigned long long*, FwdRec*,
+                    FwdRec*, uint32_t*, float, int, int, int, cudaStream_t);
 int launch_k2_compact(const uint32_t*, const uint32_t*, const uint32_t*, uint32_t, const FwdRec*, FwdRec*, uint32_t*,
                       uint32_t, cudaStream_t);
 int launch_k3_score(uint32_t, const uint32_t*, ListRec*, const ListGeo*, float, float, void*, cudaStream_t);
 int launch_k3_inv_capacity(const PairDev*, uint32_t, uint32_t, const uint32_t*, const uint32_t*, const FwdRec*,
-                           uint32_t*, cudaStream_t);
+                           uint32_t*, uint32_t*, cudaStream_t);
 int launch_k3_list_capacity(const ViewDev*, const uint32_t*, uint32_t, const IncDev*, const uint32_t*, const PairDev*,
-                            const uint32_t*, const uint32_t*, uint32_t*, cudaStream_t);
-int launch_k3_geom(const PairDev*, uint32_t, uint32_t, const ViewDev*, const SegRays*, const uint32_t*, const uint32_t*,
-                   const FwdRec*, void*, void*, cudaStream_t);
+                            const uint32_t*, const uint32_t*, uint32_t*, void*, cudaStream_t);
+int launch_k3_records(const PairDev*, uint32_t, uint32_t, const ViewDev*, const SegRays*, const uint32_t*, FwdRec*,
+                      void*, void*, const uint32_t*, uint32_t*, uint2*, cudaStream_t);
 size_t k3_geo_bytes();
-int launch_k3_wavefront(const ViewDev*, const PairDev*, const IncDev*, const uint32_t*, const SegRays*,
-                        const uint32_t*, const uint32_t*, FwdRec*, const void*, const void*, const uint32_t*, uint32_t*,
-                        uint2*,
-                        const uint32_t*, const uint64_t*, uint32_t*, ListRec*, void*, double*, float2*, uint32_t*,
-                        ListRec*, uint32_t, uint32_t*, uint32_t*, EntryDev*, void*, uint32_t, uint32_t, float,
-                        uint32_t*, cudaStream_t, int*);
+int launch_k3_dataflow(const ViewDev*, const uint32_t*, const PairDev*, const IncDev*, const uint32_t*, const SegRays*,
+                       const uint32_t*, const uint32_t*, FwdRec*, const uint32_t*, const void*, const void*,
+                       const uint32_t*, const uint32_t*, const uint2*, const uint32_t*, uint32_t*, unsigned char*,
+                       float*, void*, double*, float2*, uint32_t*, uint32_t*, uint32_t*, uint32_t*, void*, uint32_t,
+                       uint32_t*, ListRec*, uint32_t*, ListRec*, uint32_t, uint32_t*, uint32_t*, EntryDev*, void*,
+                       uint32_t, uint32_t, float, cudaStream_t, int*);
 size_t k3_wf_stats_bytes();
 size_t k3_sib_bytes();
 int k3_wf_max_inc();
+int k3_max_staged();
 size_t k3_stats_bytes();
 int launch_k4_has(const EntryDev*, uint32_t, uint32_t*, cudaStream_t);
 int launch_k4_median(ViewDev*, uint32_t, const EntryDev*, uint32_t*, cudaStream_t);
@@ -200,13 +201,14 @@ struct l3d_ctx {
     DevBuf<SegDesc> d_desc;
     DevBuf<SegRays> d_rays;
     DevBuf<double> d_midray;
+    DevBuf<SegPlane> d_planes;
     DevBuf<float> d_view_xb;
     DevBuf<ViewDev> d_views;
     DevBuf<PairDev> d_pairs;
     DevBuf<K1Cta> d_ctas;
     DevBuf<IncDev> d_inc;
     // stage 1/2 scratch
-    DevBuf<uint32_t> d_mask, d_cand_cnt, d_cand_off, d_fin_cnt, d_fin_off, d_scan, d_cand_c, d_cand_row, d_row_pair;
+    DevBuf<uint32_t> d_mask, d_cand_cnt, d_cand_off, d_fin_cnt, d_fin_off, d_scan;
     DevBuf<unsigned long long> d_heap;
     DevBuf<FwdRec> d_cand_rec, d_fin_rec;
     // forward store
@@ -220,7 +222,10 @@ struct l3d_ctx {
     DevBuf<unsigned char> d_L_sib;
     DevBuf<double> d_L_dir;
     DevBuf<float2> d_L_reg;
-    DevBuf<uint64_t> d_L_base;
+    DevBuf<uint32_t> d_L_f, d_L_c, d_L_h, d_fwd_row, d_prog_off, d_prog_nh;
+    DevBuf<unsigned char> d_L_meta, d_prog;
+    DevBuf<float> d_L_score;
+    uint64_t prog_cap = 0;  // fold-program store, 16-byte units (grown on overflow)
     DevBuf<unsigned char> d_G_fwd, d_G_inv;
     std::vector<uint64_t> L_cap_h;   // per-view list capacity
     DevBuf<ListRec> d_filt_rec;

@@ -4,6 +4,7 @@
 //   desc      SegDesc[S]       K1 target-side descriptor (1-D parametrisation)           32 B/seg
 //   rays      SegRays[S]       normalised viewing rays of both endpoints (double)        48 B/seg
 //   midray    double[3][S]     normalised ray through the 2-D midpoint (AoS double3)      24 B/seg
+//   planes    SegPlane[S]      normal of the plane (centre, r1, r2) and n.C                  32 B/seg
 //   views     ViewDev[V]
 //   pairs     PairDev[P]       matched view pairs in reference order (src asc, tgt asc)
 #pragma once
@@ -20,6 +21,13 @@ static_assert(sizeof(SegDesc) == 32, "SegDesc must be 32 bytes");
 
 struct SegRays {
     double r1[3], r2[3];
+};
+
+// plane through the camera centre spanned by the two endpoint rays (Line3D::triangulationDepths,
+// src/line3D.cc:1373-1378): unit normal and its dot product with the (translated) camera centre
+struct SegPlane {
+    double n[3];
+    double cn;
 };
 
 struct ViewDev {
@@ -101,20 +109,12 @@ int launch_scan_u32(const uint32_t* in, uint32_t* out, uint32_t n, uint32_t* scr
 size_t scan_scratch_words(uint32_t n);
 
 int launch_k0_prep(const float4* segs, const uint32_t* seg_view, const ViewDev* views, uint32_t S,
-                   int max_image_width, SegDesc* desc, SegRays* rays, double* midray, float* view_xb,
+                   int max_image_width, SegDesc* desc, SegRays* rays, double* midray, SegPlane* planes,
+                   float* view_xb,
                    cudaStream_t st);
 
 int launch_k1_pairtest(const PairDev* pairs, const K1Cta* ctas, uint32_t n_ctas, const float4* segs,
                        const SegDesc* desc, const float* view_xb, uint32_t* mask, uint32_t* cand_cnt,
                        float thr, int filter_mode, cudaStream_t st);
-
-int launch_k2_exact(const PairDev* pairs, const uint32_t* row_pair_lut, uint32_t pair0, uint32_t n_pairs,
-                    uint32_t n_rows, const float4* segs, const SegRays* rays, const double* midray,
-                    const ViewDev* views, const uint32_t* mask, const uint32_t* cand_off,
-                    unsigned long long* heap, FwdRec* cand_rec, FwdRec* fin_rec, uint32_t* fin_cnt,
-                    float thr, int knn, int max_image_width, cudaStream_t st);
-
-int launch_k2_compact(const uint32_t* cand_off, const uint32_t* fin_cnt, const uint32_t* fwd_off,
-                      const FwdRec* fin_rec, FwdRec* fwd_rec, uint32_t n_rows, cudaStream_t st);
 
 }  // namespace l3d

@@ -16,7 +16,8 @@ __global__ void __launch_bounds__(256) k0_prep_kernel(const float4* __restrict__
                                                       const uint32_t* __restrict__ seg_view,
                                                       const ViewDev* __restrict__ views, uint32_t S, double W,
                                                       SegDesc* __restrict__ desc, SegRays* __restrict__ rays,
-                                                      double* __restrict__ midray, float* __restrict__ view_xb)
+                                                      double* __restrict__ midray, SegPlane* __restrict__ planes,
+                                                      float* __restrict__ view_xb)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= S) return;
@@ -37,6 +38,13 @@ __global__ void __launch_bounds__(256) k0_prep_kernel(const float4* __restrict__
     midray[3 * (size_t)i + 0] = rm.x;
     midray[3 * (size_t)i + 1] = rm.y;
     midray[3 * (size_t)i + 2] = rm.z;
+    // n = (r1 x r2).normalized() and n.C, the per-segment part of Line3D::triangulationDepths
+    const D3 n = normalized3(cross3(r1, r2));
+    const double* Cv = views[v].C;
+    SegPlane pl;
+    pl.n[0] = n.x; pl.n[1] = n.y; pl.n[2] = n.z;
+    pl.cn = dot3(d3(Cv[0], Cv[1], Cv[2]), n);
+    planes[i] = pl;
 
     // ---- K1 descriptor (conservative, not on the decision path) ----
     const double dx = x2 - x1, dy = y2 - y1;
@@ -71,12 +79,12 @@ __global__ void __launch_bounds__(256) k0_prep_kernel(const float4* __restrict__
 }
 
 int launch_k0_prep(const float4* segs, const uint32_t* seg_view, const ViewDev* views, uint32_t S,
-                   int max_image_width, SegDesc* desc, SegRays* rays, double* midray, float* view_xb,
-                   cudaStream_t st)
+                   int max_image_width, SegDesc* desc, SegRays* rays, double* midray, SegPlane* planes,
+                   float* view_xb, cudaStream_t st)
 {
     if (S == 0) return 0;
     k0_prep_kernel<<<(S + 255) / 256, 256, 0, st>>>(segs, seg_view, views, S, (double)max_image_width, desc,
-                                                     rays, midray, view_xb);
+                                                     rays, midray, planes, view_xb);
     return 1;
 }
 

@@ -122,168 +122,312 @@ __device__ __forceinline__ void heap_pop(unsigned long long* h, uint32_t n)
 
 __device__ __forceinline__ D3 ld3(const double* p) { return D3{p[0], p[1], p[2]}; }
 
-static constexpr uint32_t K2_INVALID = 0xffffffffu;
 
-// ---- K2 expand: bit mask -> per-row candidate lists (ascending target index) ----
-__global__ void __launch_bounds__(K2_ROWS) k2_expand_kernel(const PairDev* __restrict__ pairs,
-                                                            const K1Cta* __restrict__ ctas,
-                                                            const uint32_t* __restrict__ mask,
-                                                            const uint32_t* __restrict__ cand_off,
-                                                            uint32_t* __restrict__ cand_c,
-                                                            uint32_t* __restrict__ cand_row,
-                                                            uint32_t* __restrict__ row_pair)
+// Line3D::mutualOverlap (src/line3D.cc:1283-1362) for the four collinear points a, b, q1, q2 (all with
+// z == 1 exactly: x/x = 1 in IEEE arithmetic, so every z difference is exactly 0 and drops out of
+// the 3-D norms).  The reference takes the maximum of the six float-rounded distances with a strict
+// '>', i.e. the FIRST pair whose float distance equals the maximum.  float(sqrt(.)) is monotone in
+// the squared distance, so when the runner-up squared distance is below the maximum by more than
+// a relative 2^-21 it cannot round to the same float and the first double maximum is that pair:
+// one sqrt instead of six.  Otherwise (and for NaN) the reference sequence is evaluated literally.
+__device__ __forceinline__ float mutual_overlap_xy(double ax, double ay, double bx, double by, double q1x, double q1y,
+                                                   double q2x, double q2y)
 {
-    const K1Cta cta = ctas[blockIdx.x];
+    const D3 pt[4] = {d3(ax, ay, 1.0), d3(bx, by, 1.0), d3(q1x, q1y, 1.0), d3(q2x, q2y, 1.0)};
+    if (!(point_on_segment(pt[0], pt[2], pt[3]) || point_on_segment(pt[1], pt[2], pt[3]) ||
+          point_on_segment(pt[2], pt[0], pt[1]) || point_on_segment(pt[3], pt[0], pt[1])))
+        return 0.0f;
+    double d2[6];
+    {
+        int k = 0;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = i + 1; j < 4; ++j) {
+                const double dx = ds(pt[i].x, pt[j].x), dy = ds(pt[i].y, pt[j].y);
+                d2[k++] = da(dm(dx, dx), dm(dy, dy));  // + dz*dz with dz == 0 exactly
+            }
+    }
+    double m2 = d2[0];
+    int im = 0;
+#pragma unroll
+    for (int k = 1; k < 6; ++k)
+        if (d2[k] > m2) {
+            m2 = d2[k];
+            im = k;
+        }
+    // runner-up: the largest squared distance strictly below the maximum
+    const double lim = dm(m2, 1.0 - 0x1p-21);
+    bool clear = true;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) clear &= (d2[k] == m2) | (d2[k] <= lim);
+    if (clear) {
+        const float max_dist = (float)__dsqrt_rn(m2);
+        if (!(max_dist > 0.0f) || max_dist < 1.0f) return 0.0f;
+        double in2 = d2[5];  // inner pair = complement of the outer pair: index 5 - im
+        if (im == 1) in2 = d2[4];
+        if (im == 2) in2 = d2[3];
+        if (im == 3) in2 = d2[2];
+        if (im == 4) in2 = d2[1];
+        if (im == 5) in2 = d2[0];
+        return (float)dd(__dsqrt_rn(in2), (double)max_dist);
+    }
+    return mutual_overlap(pt);
+}
+
+static constexpr int K2_WARPS = 4;     // warps per CTA, one row per warp at a time
+static constexpr int K2_SUB = 64;      // rows per CTA (a quarter of a K1 tile)
+static constexpr int K2_CHUNK = 1024;  // target segments per enumeration chunk (32 mask words)
+
+struct K2WarpSmem {
+    float ps[K2_CHUNK];        // exact overlap of the candidates that pass the overlap test
+    unsigned short cl[K2_CHUNK];  // chunk-local target index: candidates, then (in place) the passing ones
+};
+
+// ---- K2: one warp per source row: enumerate the K1 candidates (ascending target index = the order
+// Line3D::matchingCPU pushes matches, src/line3D.cc:1124-1196), phase A: exact pair test of every
+// candidate, phase B: triangulation + orientation test of the ones that pass (dense lanes again),
+// then the kNN selection in priority-queue pop order and the orientation filter.  Only matches with
+// four positive depths are ever written to memory. ----
+__global__ void __launch_bounds__(K2_WARPS * 32) k2_row_kernel(
+    const PairDev* __restrict__ pairs, const K1Cta* __restrict__ ctas, const uint32_t* __restrict__ mask,
+    const uint32_t* __restrict__ cand_off, const float4* __restrict__ segs, const SegRays* __restrict__ rays,
+    const double* __restrict__ midray, const SegPlane* __restrict__ planes, const ViewDev* __restrict__ views,
+    unsigned long long* __restrict__ heap, FwdRec* __restrict__ cand_rec, FwdRec* __restrict__ fin_rec, uint32_t* __restrict__ fin_cnt, float thr, double W,
+    int knn, int apply_orient)
+{
+    __shared__ K2WarpSmem wsm[K2_WARPS];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    K2WarpSmem& sm = wsm[warp];
+    const K1Cta cta = ctas[blockIdx.x / (K2_ROWS / K2_SUB)];
     const PairDev& P = pairs[cta.pair];
-    const uint32_t r = cta.tile * K2_ROWS + threadIdx.x;
-    if (r >= P.n_src) return;
-    const uint32_t lrow = P.row_base - P.batch_row0 + r;
-    row_pair[lrow] = cta.pair;
-    uint32_t pos = cand_off[lrow];
-    const uint32_t* __restrict__ mrow = mask + P.mask_base + r;
-    for (uint32_t w = 0; w < P.words; ++w) {
-        uint32_t m = mrow[(size_t)w * P.n_src];
-        while (m) {
-            const uint32_t j = __ffs(m) - 1;
-            m &= m - 1;
-            cand_c[pos] = w * 32 + j;
-            cand_row[pos] = lrow;
-            ++pos;
-        }
-    }
-}
+    const uint32_t n_src = P.n_src, n_tgt = P.n_tgt, words = P.words;
+    const uint32_t row0 = cta.tile * K2_ROWS + (blockIdx.x % (K2_ROWS / K2_SUB)) * K2_SUB;
+    const ViewDev& vs = views[P.src_view];
+    const ViewDev& vt = views[P.tgt_view];
+    const D3 Cs = ld3(vs.C), Ct = ld3(vt.C);
 
-// ---- K2a: one thread per candidate: exact pair test, both triangulations, orientation test ----
-__global__ void __launch_bounds__(128) k2a_exact_kernel(
-    const PairDev* __restrict__ pairs, const uint32_t* __restrict__ row_pair, const uint32_t* __restrict__ cand_c,
-    const uint32_t* __restrict__ cand_row, uint32_t n_cand, const float4* __restrict__ segs,
-    const SegRays* __restrict__ rays, const double* __restrict__ midray, const ViewDev* __restrict__ views,
-    FwdRec* __restrict__ cand_rec, float thr, double W)
-{
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_cand) return;
-    const uint32_t lrow = cand_row[t];
-    const uint32_t c = cand_c[t];
-    const PairDev& P = pairs[row_pair[lrow]];
-    const uint32_t r = lrow - (P.row_base - P.batch_row0);
-    FwdRec rec;
-    rec.c = c;
-    rec.flags = K2_INVALID;
-    rec.overlap = 0.0f;
-    rec.d_p1 = rec.d_p2 = rec.d_q1 = rec.d_q2 = rec.score = 0.0f;
+    for (uint32_t rr = warp; rr < K2_SUB; rr += K2_WARPS) {
+        const uint32_t r = row0 + rr;
+        if (r >= n_src) break;  // warp-uniform
+        const uint32_t lrow = P.row_base - P.batch_row0 + r;
+        const uint32_t base = cand_off[lrow];
+        FwdRec* __restrict__ stage = cand_rec + base;
+        FwdRec* __restrict__ frec = fin_rec + base;
+        const uint32_t* __restrict__ mrow = mask + P.mask_base + r;
 
-    const float4 sg = segs[P.src_off + r];
-    const D3 p1 = d3((double)sg.x, (double)sg.y, 1.0), p2 = d3((double)sg.z, (double)sg.w, 1.0);
-    const D3 e1 = mul33(P.F, p1), e2 = mul33(P.F, p2);
-    const float4 tg = segs[P.tgt_off + c];
-    const D3 q1 = d3((double)tg.x, (double)tg.y, 1.0), q2 = d3((double)tg.z, (double)tg.w, 1.0);
-    const D3 l2 = cross3(q1, q2);
-    D3 a = cross3(l2, e1), b = cross3(l2, e2);
-    bool ok = fabs(a.z) > L3D_EPS && fabs(b.z) > L3D_EPS;
-    float score = 0.0f;
-    if (ok) {
-        a = d3(dd(a.x, a.z), dd(a.y, a.z), dd(a.z, a.z));
-        b = d3(dd(b.x, b.z), dd(b.y, b.z), dd(b.z, b.z));
-        ok = !(a.x < 0 || a.x > W || a.y < 0 || a.y > W || b.x < 0 || b.x > W || b.y < 0 || b.y > W);
-    }
-    if (ok) {
-        const D3 pts[4] = {a, b, q1, q2};
-        score = mutual_overlap(pts);
-        ok = score > thr;
-    }
-    if (ok) {
-        const ViewDev& vs = views[P.src_view];
-        const ViewDev& vt = views[P.tgt_view];
-        const SegRays sr = rays[P.src_off + r];
-        const D3 rp1 = ld3(sr.r1), rp2 = ld3(sr.r2);
-        const D3 Cs = ld3(vs.C), Ct = ld3(vt.C);
-        const SegRays tr = rays[P.tgt_off + c];
-        const D3 rq1 = ld3(tr.r1), rq2 = ld3(tr.r2);
-        double ds1 = -1.0, ds2 = -1.0, dt1 = -1.0, dt2 = -1.0;
-        {  // triangulationDepths(src,p | tgt,q)
-            const D3 nA = normalized3(cross3(rq1, rq2));
-            const double a1 = dot3(rp1, nA), a2 = dot3(rp2, nA);
-            if (!(fabs(a1) < L3D_EPS || fabs(a2) < L3D_EPS)) {
-                const double num = ds(dot3(Ct, nA), dot3(nA, Cs));
-                ds1 = dd(num, dot3(nA, rp1));
-                ds2 = dd(num, dot3(nA, rp2));
+        // row constants (src/line3D.cc:1113-1121)
+        const float4 sg = segs[P.src_off + r];
+        const D3 p1 = d3((double)sg.x, (double)sg.y, 1.0), p2 = d3((double)sg.z, (double)sg.w, 1.0);
+        const D3 e1 = mul33(P.F, p1), e2 = mul33(P.F, p2);
+        uint32_t n_valid = 0;
+
+        for (uint32_t cb = 0; cb < n_tgt; cb += K2_CHUNK) {
+            // ---- enumerate the candidates of this chunk in ascending target order ----
+            const uint32_t w = (cb >> 5) + lane;
+            uint32_t bits = (w < words) ? mrow[(size_t)w * n_src] : 0u;
+            const uint32_t cnt = __popc(bits);
+            uint32_t incl = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+                if ((int)lane >= d) incl += t;
             }
-        }
-        {  // triangulationDepths(tgt,q | src,p)
-            const D3 nB = normalized3(cross3(rp1, rp2));
-            const double b1 = dot3(rq1, nB), b2 = dot3(rq2, nB);
-            if (!(fabs(b1) < L3D_EPS || fabs(b2) < L3D_EPS)) {
-                const double numB = ds(dot3(Cs, nB), dot3(nB, Ct));
-                dt1 = dd(numB, dot3(nB, rq1));
-                dt2 = dd(numB, dot3(nB, rq2));
+            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+            if (total == 0) continue;  // warp-uniform
+            uint32_t off = incl - cnt;
+            while (bits) {
+                const uint32_t j = __ffs(bits) - 1;
+                bits &= bits - 1;
+                sm.cl[off++] = (unsigned short)(lane * 32 + j);
             }
-        }
-        if (ds1 > L3D_EPS && ds2 > L3D_EPS && dt1 > L3D_EPS && dt2 > L3D_EPS) {
-            rec.overlap = score;
-            rec.d_p1 = (float)ds1;
-            rec.d_p2 = (float)ds2;
-            rec.d_q1 = (float)dt1;
-            rec.d_q2 = (float)dt2;
-            // orientation test of the would-be match (checkMatchOrientation, src/line3D.cc:962-1014):
-            // flags = 0 keep, 1 = dropped by the orientation filter if it survives the kNN selection
-            const D3 P1 = add3(Cs, scale3(rp1, (double)rec.d_p1));
-            const D3 P2 = add3(Cs, scale3(rp2, (double)rec.d_p2));
-            const float len = (float)norm3(sub3(P1, P2));
-            D3 dir = d3(0.0, 0.0, 0.0);
-            if (len > L3D_EPS) dir = normalized3(sub3(P2, P1));
+            __syncwarp();
+
+            // ---- phase A: the pair test in the reference's double sequence (src/line3D.cc:1131-1158) ----
+            uint32_t npass = 0;
+            for (uint32_t k0 = 0; k0 < total; k0 += 32) {
+                const uint32_t k = k0 + lane;
+                const bool active = k < total;
+                const uint32_t cidx = active ? (uint32_t)sm.cl[k] : 0u;
+                float score = 0.0f;
+                bool pass = false;
+                if (active) {
+                    const float4 tg = segs[P.tgt_off + cb + cidx];
+                    const D3 q1 = d3((double)tg.x, (double)tg.y, 1.0), q2 = d3((double)tg.z, (double)tg.w, 1.0);
+                    const D3 l2 = cross3(q1, q2);
+                    const D3 a = cross3(l2, e1), b = cross3(l2, e2);
+                    if (fabs(a.z) > L3D_EPS && fabs(b.z) > L3D_EPS) {
+                        const double ax = dd(a.x, a.z), ay = dd(a.y, a.z), bx = dd(b.x, b.z), by = dd(b.y, b.z);
+                        if (!(ax < 0 || ax > W || ay < 0 || ay > W || bx < 0 || bx > W || by < 0 || by > W)) {
+                            score = mutual_overlap_xy(ax, ay, bx, by, q1.x, q1.y, q2.x, q2.y);
+                            pass = score > thr;
+                        }
+                    }
+                }
+                __syncwarp();  // every lane has read its cl[k] before the in-place compaction
+                const uint32_t bal = __ballot_sync(0xffffffffu, pass);
+                if (pass) {
+                    const uint32_t pos = npass + __popc(bal & lt_mask);
+                    sm.cl[pos] = (unsigned short)cidx;
+                    sm.ps[pos] = score;
+                }
+                npass += __popc(bal);
+                __syncwarp();
+            }
+            if (npass == 0) continue;
+
+            // ---- phase B: both triangulations (src/line3D.cc:1365-1390; the plane normals n = (r1 x r2)
+            // .normalized() and n.C are per-segment constants from k0_prep) + the orientation test of the
+            // would-be match (checkMatchOrientation, src/line3D.cc:962-1014) ----
+            const SegRays sr = rays[P.src_off + r];
+            const D3 rp1 = ld3(sr.r1), rp2 = ld3(sr.r2);
+            const SegPlane plB = planes[P.src_off + r];
+            const D3 nB = ld3(plB.n);
+            const double numB = ds(plB.cn, dot3(nB, Ct));
             const D3 rmid = ld3(midray + 3 * (size_t)(P.src_off + r));
-            const double ang = det_acos(fmin(fmax(dot3(rmid, dir), -1.0), 1.0));
-            rec.flags = (ang > (double)0.098174771f && ang < (double)3.043417886f) ? 0u : 1u;
+            for (uint32_t k0 = 0; k0 < npass; k0 += 32) {
+                const uint32_t k = k0 + lane;
+                bool valid = false;
+                FwdRec rec;
+                rec.flags = 0u;
+                rec.score = 0.0f;
+                if (k < npass) {
+                    const uint32_t c = cb + (uint32_t)sm.cl[k];
+                    const SegRays tr = rays[P.tgt_off + c];
+                    const SegPlane plA = planes[P.tgt_off + c];
+                    const D3 rq1 = ld3(tr.r1), rq2 = ld3(tr.r2);
+                    const D3 nA = ld3(plA.n);
+                    double ds1 = -1.0, ds2 = -1.0, dt1 = -1.0, dt2 = -1.0;
+                    {  // triangulationDepths(src,p | tgt,q)
+                        const double a1 = dot3(rp1, nA), a2 = dot3(rp2, nA);
+                        if (!(fabs(a1) < L3D_EPS || fabs(a2) < L3D_EPS)) {
+                            const double num = ds(plA.cn, dot3(nA, Cs));
+                            ds1 = dd(num, a1);  // n.ray(p1): the same products in the same order as ray(p1).n
+                            ds2 = dd(num, a2);
+                        }
+                    }
+                    {  // triangulationDepths(tgt,q | src,p)
+                        const double b1 = dot3(rq1, nB), b2 = dot3(rq2, nB);
+                        if (!(fabs(b1) < L3D_EPS || fabs(b2) < L3D_EPS)) {
+                            dt1 = dd(numB, b1);
+                            dt2 = dd(numB, b2);
+                        }
+                    }
+                    if (ds1 > L3D_EPS && ds2 > L3D_EPS && dt1 > L3D_EPS && dt2 > L3D_EPS) {
+                        valid = true;
+                        rec.c = c;
+                        rec.overlap = sm.ps[k];
+                        rec.d_p1 = (float)ds1;
+                        rec.d_p2 = (float)ds2;
+                        rec.d_q1 = (float)dt1;
+                        rec.d_q2 = (float)dt2;
+                        // flags = 1: dropped by the orientation filter if it survives the kNN selection.
+                        // The test is acos(x) in (0.0982, 3.0434) with x = ray(mid) . dir, dir = (P2-P1)/|P2-P1|,
+                        // i.e. |x| < 0.99518...: when (ray(mid).(P2-P1))^2 < 0.9951^2 |P2-P1|^2 the exact x
+                        // (relative error ~1e-15) is inside by a margin of 8e-5 and no sqrt/div/acos is needed.
+                        const D3 P1 = add3(Cs, scale3(rp1, (double)rec.d_p1));
+                        const D3 P2 = add3(Cs, scale3(rp2, (double)rec.d_p2));
+                        const D3 vv = sub3(P2, P1);
+                        const double v2 = dot3(vv, vv), sv = dot3(rmid, vv);
+                        if (!(v2 > 1e-20 && sv * sv < 0.99022401 * v2)) {
+                            const float len = (float)norm3(sub3(P1, P2));
+                            D3 dir = d3(0.0, 0.0, 0.0);
+                            if (len > L3D_EPS) dir = normalized3(vv);
+                            const double ang = det_acos(fmin(fmax(dot3(rmid, dir), -1.0), 1.0));
+                            rec.flags = (ang > (double)0.098174771f && ang < (double)3.043417886f) ? 0u : 1u;
+                        }
+                    }
+                }
+                const uint32_t bal = __ballot_sync(0xffffffffu, valid);
+                if (valid) stage[n_valid + __popc(bal & lt_mask)] = rec;
+                n_valid += __popc(bal);
+            }
+            __syncwarp();
         }
-    }
-    cand_rec[t] = rec;
-}
 
-// ---- K2b: one thread per row: priority-queue order, kNN pops, orientation filter ----
-__global__ void __launch_bounds__(K2_ROWS) k2b_select_kernel(const uint32_t* __restrict__ cand_off, uint32_t n_rows,
-                                                             unsigned long long* __restrict__ heap,
-                                                             const FwdRec* __restrict__ cand_rec,
-                                                             FwdRec* __restrict__ fin_rec,
-                                                             uint32_t* __restrict__ fin_cnt, int knn, int apply_orient)
-{
-    const uint32_t lrow = blockIdx.x * blockDim.x + threadIdx.x;
-    if (lrow >= n_rows) return;
-    const uint32_t base = cand_off[lrow];
-    const uint32_t cap = cand_off[lrow + 1] - base;
-    unsigned long long* __restrict__ hp = heap + base;
-    const FwdRec* __restrict__ crec = cand_rec + base;
-    FwdRec* __restrict__ frec = fin_rec + base;
-    uint32_t nout = 0;
-    if (knn > 0) {
-        uint32_t n = 0;
-        for (uint32_t i = 0; i < cap; ++i) {  // push order = ascending target index
-            const FwdRec rc = crec[i];
-            if (rc.flags == K2_INVALID) continue;
-            heap_push(hp, n, ((unsigned long long)__float_as_uint(rc.overlap) << 32) | i);
-            ++n;
-        }
-        const uint32_t npop = min((uint32_t)knn, n);
-        uint32_t hn = n;
-        for (uint32_t t = 0; t < npop; ++t) {
-            const uint32_t idx = (uint32_t)(hp[0] & 0xffffffffu);
-            heap_pop(hp, hn);
-            --hn;
-            FwdRec rc = crec[idx];
-            if (rc.flags == 0u || !apply_orient) {
-                rc.flags = 0u;
-                frec[nout++] = rc;
+        // ---- selection: std::priority_queue pop order (include/commons.h:233-244, src/line3D.cc:1198-1206),
+        // then the orientation filter ----
+        uint32_t nout = 0;
+        __syncwarp();
+        if (knn <= 0) {
+            for (uint32_t k0 = 0; k0 < n_valid; k0 += 32) {
+                const uint32_t k = k0 + lane;
+                FwdRec rc;
+                bool keep = false;
+                if (k < n_valid) {
+                    rc = stage[k];
+                    keep = (rc.flags == 0u) || !apply_orient;
+                }
+                const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+                if (keep) {
+                    rc.flags = 0u;
+                    frec[nout + __popc(bal & lt_mask)] = rc;
+                }
+                nout += __popc(bal);
+            }
+        } else if (n_valid) {
+            const uint32_t npop = min((uint32_t)knn, n_valid);
+            // distinct overlaps pop in descending order: rank = number of larger overlaps
+            bool fast = (n_valid <= K2_CHUNK) && (knn <= 32);
+            if (fast) {
+                for (uint32_t k = lane; k < n_valid; k += 32) sm.ps[k] = stage[k].overlap;
+                __syncwarp();
+                // rank = number of strictly larger overlaps; equal overlaps among the popped ones show up
+                // as a rank collision, i.e. fewer than npop distinct ranks below npop
+                uint32_t keepbits = 0, rankbits = 0;
+                for (uint32_t k = lane; k < n_valid; k += 32) {
+                    const float ov = sm.ps[k];
+                    uint32_t rank = 0;
+                    for (uint32_t j = 0; j < n_valid; ++j) rank += (sm.ps[j] > ov) ? 1u : 0u;
+                    bool keep = false;
+                    if (rank < npop) {
+                        rankbits |= 1u << rank;
+                        keep = !apply_orient || stage[k].flags == 0u;
+                        if (keep) keepbits |= 1u << rank;
+                    }
+                    sm.cl[k] = (unsigned short)(keep ? rank : 0xffffu);
+                }
+                rankbits = __reduce_or_sync(0xffffffffu, rankbits);
+                fast = (uint32_t)__popc(rankbits) == npop;
+                if (fast) {
+                    keepbits = __reduce_or_sync(0xffffffffu, keepbits);
+                    for (uint32_t k = lane; k < n_valid; k += 32) {
+                        const uint32_t rank = sm.cl[k];
+                        if (rank != 0xffffu) {
+                            FwdRec rc = stage[k];
+                            rc.flags = 0u;
+                            frec[__popc(keepbits & ((1u << rank) - 1u))] = rc;
+                        }
+                    }
+                    nout = __popc(keepbits);
+                }
+                __syncwarp();
+            }
+            if (!fast) {
+                // equal overlaps: replay the binary heap (push in ascending target order, pop kNN)
+                if (lane == 0) {
+                    unsigned long long* __restrict__ hp = heap + base;
+                    for (uint32_t i = 0; i < n_valid; ++i)
+                        heap_push(hp, i, ((unsigned long long)__float_as_uint(stage[i].overlap) << 32) | i);
+                    uint32_t hn = n_valid;
+                    for (uint32_t t = 0; t < npop; ++t) {
+                        const uint32_t idx = (uint32_t)(hp[0] & 0xffffffffu);
+                        heap_pop(hp, hn);
+                        --hn;
+                        FwdRec rc = stage[idx];
+                        if (rc.flags == 0u || !apply_orient) {
+                            rc.flags = 0u;
+                            frec[nout++] = rc;
+                        }
+                    }
+                }
+                nout = __shfl_sync(0xffffffffu, nout, 0);
             }
         }
-    } else {
-        for (uint32_t i = 0; i < cap; ++i) {
-            FwdRec rc = crec[i];
-            if (rc.flags == 0u || (!apply_orient && rc.flags != K2_INVALID)) {
-                rc.flags = 0u;
-                frec[nout++] = rc;
-            }
-        }
+        if (lane == 0) fin_cnt[lrow] = nout;
+        __syncwarp();
     }
-    fin_cnt[lrow] = nout;
 }
 
 __global__ void __launch_bounds__(256) k2_compact_kernel(const uint32_t* __restrict__ cand_off,
@@ -303,24 +447,18 @@ __global__ void __launch_bounds__(256) k2_compact_kernel(const uint32_t* __restr
 }
 
 int launch_k2_exact(const PairDev* pairs, const K1Cta* ctas, uint32_t n_ctas, uint32_t n_rows, uint32_t n_cand,
-                    const float4* segs, const SegRays* rays, const double* midray, const ViewDev* views,
-                    const uint32_t* mask, const uint32_t* cand_off, uint32_t* cand_c, uint32_t* cand_row,
-                    uint32_t* row_pair, unsigned long long* heap, FwdRec* cand_rec, FwdRec* fin_rec, uint32_t* fin_cnt,
-                    float thr, int knn, int max_image_width, int apply_orient, cudaStream_t st)
+                    const float4* segs, const SegRays* rays, const double* midray, const SegPlane* planes,
+                    const ViewDev* views, const uint32_t* mask, const uint32_t* cand_off, unsigned long long* heap, FwdRec* cand_rec,
+                    FwdRec* fin_rec, uint32_t* fin_cnt, float thr, int knn, int max_image_width, int apply_orient,
+                    cudaStream_t st)
 {
     if (n_ctas == 0) return 0;
-    int launches = 0;
-    k2_expand_kernel<<<n_ctas, K2_ROWS, 0, st>>>(pairs, ctas, mask, cand_off, cand_c, cand_row, row_pair);
-    ++launches;
-    if (n_cand) {
-        k2a_exact_kernel<<<(n_cand + 127) / 128, 128, 0, st>>>(pairs, row_pair, cand_c, cand_row, n_cand, segs, rays,
-                                                                midray, views, cand_rec, thr, (double)max_image_width);
-        ++launches;
-    }
-    k2b_select_kernel<<<(n_rows + K2_ROWS - 1) / K2_ROWS, K2_ROWS, 0, st>>>(cand_off, n_rows, heap, cand_rec, fin_rec,
-                                                                            fin_cnt, knn, apply_orient);
-    ++launches;
-    return launches;
+    (void)n_rows;
+    (void)n_cand;
+    k2_row_kernel<<<n_ctas * (K2_ROWS / K2_SUB), K2_WARPS * 32, 0, st>>>(pairs, ctas, mask, cand_off, segs, rays, midray,
+                                                                        planes, views, heap, cand_rec, fin_rec, fin_cnt, thr,
+                                                                        (double)max_image_width, knn, apply_orient);
+    return 1;
 }
 
 int launch_k2_compact(const uint32_t* cand_off, const uint32_t* fin_cnt, const uint32_t* fin_off,

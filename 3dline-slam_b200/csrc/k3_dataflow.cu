@@ -1,0 +1,877 @@
+// k3_dataflow.cu -- K3: scoring of Line3D::computeMatches (src/line3D.cc:846-930) as a data-flow
+// computation instead of a per-view wavefront (exact TU).
+//
+// The reference processes the views in ascending camera-ID order because
+// Line3D::storeInverseMatches (src/line3D.cc:1986-2015) appends every forward match of view A whose
+// score3D_ is > 0 to the list of its target segment in a not yet processed view B.  What flows from
+// A to B is only the PRESENCE of those entries: the similarity of two list entries
+// (Line3D::similarityForScoring, src/line3D.cc:1685-1716) depends on their depths and 3-D
+// directions, which are known as soon as matching is done.  So:
+//
+//   build  (all rows of all views at once, one CTA per segment): assemble the POTENTIAL list of the
+//          row = [every forward match pointing at this segment from an earlier view, in append
+//          order] ++ [its own forward matches per target camera]; evaluate the similarity of every
+//          (M, sibling) pair that can be non-zero; emit the row's "fold program": per match M
+//          with at least one such sibling a head record and the sibling records (record index whose
+//          score decides presence, similarity, camera block).
+//   fold   (one persistent kernel, rows handed out in (view, segment) order by a ticket counter):
+//          Line3D::scoringCPU's accumulation (src/line3D.cc:1515-1543) over the siblings that are
+//          present; a sibling that is an inverse match waits (spins) on the score of its forward
+//          record, which an earlier ticket produces.  Tickets are taken in order by resident warps
+//          and a row only ever waits on rows of earlier views, so the smallest unfinished ticket
+//          never waits: no deadlock, no grid-wide barrier, and the critical path is the longest
+//          dependency chain instead of the number of views.
+//   finish (all rows at once, one warp per segment): which potential entries exist, the scored
+//          lists (optional), Line3D::filterMatches (src/line3D.cc:1911-1983) and the
+//          estimated_position3D_ row.
+//
+// A sibling with similarity 0 never changes score3D_ (x + 0 = x; 0 > stored is false; a later
+// s > 0 of the same camera gives (score - 0) + s, the same value as a first add), so only pairs
+// that pass the cheap certain-reject test are evaluated and folded.
+#include "internal.h"
+#include "score_core.cuh"
+
+namespace l3d {
+
+#define L3D_EPS 1e-12
+static constexpr uint32_t NOIDX = 0xffffffffu;
+static constexpr int DF_THREADS = 64;
+static constexpr int DF_MAXINC = 64;      // incident pairs of one view
+static constexpr int DF_MAXM_CAP = 2048;  // potential entries staged in shared memory at most
+static constexpr uint32_t DF_SPIN_LIMIT = 1u << 22;
+
+struct WfStats {
+    unsigned long long sim_evals;
+    unsigned long long scored;
+    uint32_t num_valid;
+    uint32_t filt_cursor;  // bump allocator of the filtered-record store
+    uint32_t err;          // bit1: filtered store overflow, bit2: program store overflow, bit3: dependency timeout
+    uint32_t prog_cursor;  // bump allocator of the fold programs (16-byte units)
+    uint32_t ticket;
+    uint32_t max_list;     // longest potential list
+    uint32_t pad[2];
+};
+
+// per forward record: 3-D direction and regularisers of the match seen from its source view
+// (G_fwd) and, for inverse-emitting pairs, seen from its target view (G_inv)
+struct GeoRec {
+    double dir[3];
+    float reg1, reg2;
+    uint32_t valid;
+    uint32_t pad;
+};
+
+__device__ __forceinline__ D3 ld3w(const double* p) { return D3{p[0], p[1], p[2]}; }
+
+// ------------------------------------------------------------------------------------------
+// pre-pass
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pair_of_row(const PairDev* __restrict__ pairs, uint32_t P, uint32_t row)
+{
+    uint32_t lo = 0, hi = P;  // largest p with row_base <= row
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (pairs[mid].row_base <= row) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// per (pair, source row): the row of every forward record, and how many records point at each
+// (pair, target segment) = the capacity of its inverse-match slot
+__global__ void __launch_bounds__(256) k3_inv_capacity_kernel(const PairDev* __restrict__ pairs, uint32_t P,
+                                                              uint32_t n_rows, const uint32_t* __restrict__ fwd_off,
+                                                              const uint32_t* __restrict__ fwd_cnt,
+                                                              const FwdRec* __restrict__ fwd_rec,
+                                                              uint32_t* __restrict__ fwd_row,
+                                                              uint32_t* __restrict__ inv_cap)
+{
+    const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n_rows) return;
+    const uint32_t n = fwd_cnt[row];
+    if (!n) return;
+    const PairDev& D = pairs[pair_of_row(pairs, P, row)];
+    const uint32_t b = fwd_off[row];
+    for (uint32_t e = 0; e < n; ++e) {
+        fwd_row[b + e] = row;
+        if (D.emit_inverse) atomicAdd(&inv_cap[D.tgt_base + fwd_rec[b + e].c], 1u);
+    }
+}
+
+__global__ void __launch_bounds__(256) k3_list_capacity_kernel(const ViewDev* __restrict__ views,
+                                                               const uint32_t* __restrict__ seg_view, uint32_t S,
+                                                               const IncDev* __restrict__ inc,
+                                                               const uint32_t* __restrict__ inc_off,
+                                                               const PairDev* __restrict__ pairs,
+                                                               const uint32_t* __restrict__ fwd_cnt,
+                                                               const uint32_t* __restrict__ inv_cap,
+                                                               uint32_t* __restrict__ L_ub, WfStats* __restrict__ stats)
+{
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t m = 0;
+    if (g < S) {
+        const uint32_t v = seg_view[g];
+        const uint32_t i = g - views[v].seg_off;
+        for (uint32_t q = inc_off[v]; q < inc_off[v + 1]; ++q) {
+            const PairDev& P = pairs[inc[q].pair];
+            m += inc[q].inverse ? inv_cap[P.tgt_base + i] : fwd_cnt[P.row_base + i];
+        }
+        L_ub[g] = m;
+    }
+    m = __reduce_max_sync(0xffffffffu, m);
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(&stats->max_list, m);
+}
+
+__device__ __forceinline__ GeoRec make_geo(const D3& C, const D3& r1, const D3& r2, float d1, float d2, float k,
+                                           const D3& Co, float ko)
+{
+    // View::unprojectSegment (src/view.cc:385-400) + Segment3D ctor (include/segment3D.h:58-77)
+    D3 P1 = add3(C, scale3(r1, (double)d1));
+    D3 P2 = add3(C, scale3(r2, (double)d2));
+    float len = (float)norm3(sub3(P1, P2));
+    D3 dir = d3(0.0, 0.0, 0.0);
+    if (len > L3D_EPS) {
+        dir = normalized3(sub3(P2, P1));
+    } else {
+        P1 = d3(0.0, 0.0, 0.0);
+        P2 = d3(0.0, 0.0, 0.0);
+        len = 0.0f;
+    }
+    // regularisers (src/line3D.cc:1429-1438, src/view.cc:474-477)
+    const float sig1 = fm(d1, k), sig2 = fm(d2, k);
+    float reg1 = fm(fm(2.0f, sig1), sig1);
+    float reg2 = fm(fm(2.0f, sig2), sig2);
+    const float s1t = (float)dm(norm3(sub3(P1, Co)), (double)ko);
+    const float s2t = (float)dm(norm3(sub3(P2, Co)), (double)ko);
+    reg1 = fm(0.5f, fa(reg1, fm(fm(2.0f, s1t), s1t)));
+    reg2 = fm(0.5f, fa(reg2, fm(fm(2.0f, s2t), s2t)));
+    GeoRec G;
+    G.dir[0] = dir.x; G.dir[1] = dir.y; G.dir[2] = dir.z;
+    G.reg1 = reg1;
+    G.reg2 = reg2;
+    G.valid = (len < L3D_EPS) ? 0u : 1u;
+    G.pad = 0u;
+    return G;
+}
+
+// one thread per forward record: 3-D geometry seen from both views, the (static) inverse-match
+// slot of its target segment, score reset
+__global__ void __launch_bounds__(128) k3_record_kernel(const PairDev* __restrict__ pairs, uint32_t P, uint32_t F,
+                                                        const ViewDev* __restrict__ views,
+                                                        const SegRays* __restrict__ rays,
+                                                        const uint32_t* __restrict__ fwd_row,
+                                                        FwdRec* __restrict__ fwd_rec, GeoRec* __restrict__ G_fwd,
+                                                        GeoRec* __restrict__ G_inv,
+                                                        const uint32_t* __restrict__ inv_off,
+                                                        uint32_t* __restrict__ inv_fill, uint2* __restrict__ inv_ent)
+{
+    const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= F) return;
+    const uint32_t row = fwd_row[f];
+    const PairDev& D = pairs[pair_of_row(pairs, P, row)];
+    const uint32_t i = row - D.row_base;
+    const ViewDev& vs = views[D.src_view];
+    const ViewDev& vt = views[D.tgt_view];
+    const D3 Cs = ld3w(vs.C), Ct = ld3w(vt.C);
+    const SegRays sr = rays[D.src_off + i];
+    const FwdRec rec = fwd_rec[f];
+    fwd_rec[f].score = 0.0f;
+    G_fwd[f] = make_geo(Cs, ld3w(sr.r1), ld3w(sr.r2), rec.d_p1, rec.d_p2, vs.k, Ct, vt.k);
+    if (D.emit_inverse) {
+        const SegRays tr = rays[D.tgt_off + rec.c];
+        G_inv[f] = make_geo(Ct, ld3w(tr.r1), ld3w(tr.r2), rec.d_q1, rec.d_q2, vt.k, Cs, vs.k);
+        const uint32_t tr_row = D.tgt_base + rec.c;
+        const uint32_t slot = atomicAdd(&inv_fill[tr_row], 1u);
+        inv_ent[inv_off[tr_row] + slot] = make_uint2(f, i);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// build: potential list + fold program of one row
+// ------------------------------------------------------------------------------------------
+struct BuildArgs {
+    const ViewDev* views;
+    const uint32_t* seg_view;
+    const PairDev* pairs;
+    const IncDev* inc;
+    const uint32_t* inc_off;  // [V+1]
+    const uint32_t* fwd_off;
+    const uint32_t* fwd_cnt;
+    FwdRec* fwd_rec;
+    const GeoRec* G_fwd;
+    const GeoRec* G_inv;
+    const uint32_t* inv_off;   // start of the slot of every (pair, tgt segment)
+    const uint32_t* inv_fill;  // entries in the slot
+    const uint2* inv_ent;      // x: forward record index, y: source row
+    const uint32_t* L_off;     // [S+1] offsets of the potential lists (global segment order)
+    uint32_t* L_f;             // per potential entry: forward record index
+    unsigned char* L_meta;     // per potential entry: incident-pair slot | inverse << 7
+    // global staging for rows longer than maxm (may be NULL when the host knows every row fits)
+    Sib* L_sib;
+    double* L_dir;
+    float2* L_reg;
+    uint32_t* L_c;
+    uint32_t* L_h;
+    uint32_t* prog_off;  // [S] first 16-byte unit of the row's program
+    uint32_t* prog_nh;   // [S] number of head records (0: nothing to fold)
+    uint4* prog;
+    uint32_t prog_cap;
+    WfStats* stats;
+    uint32_t S;
+    uint32_t maxm;
+    float two_sigA_sqr;
+    float dotcut;  // see score_core.cuh
+};
+
+struct BlockTab {
+    uint32_t b[DF_MAXINC], n[DF_MAXINC], pos[DF_MAXINC + 1];
+    uint32_t other[DF_MAXINC];  // the other view of the pair
+    uint32_t inv[DF_MAXINC];    // 1: inverse block
+};
+
+// cheap certain reject of similarityForScoring: |d| > t >= sqrt(0.75 reg) (1 + 1e-5)  =>  -d^2/reg < -0.70
+// after every rounding of the exact sequence  =>  exp(.) < 0.4966 < 0.5  =>  the similarity is truncated
+// to 0.  The test only selects which pairs get the full evaluation; it never decides a result.
+__device__ __forceinline__ float reject_threshold(float reg)
+{
+    return (reg > 0.0f) ? __fsqrt_ru(0.75f * reg) * 1.00001f : __int_as_float(0x7f800000);
+}
+__device__ __forceinline__ bool pair_flagged(const Sib& M, bool Mok, float t1, float t2, const Sib& S2)
+{
+    const float d1 = fs(M.d_p1, S2.d_p1), d2 = fs(M.d_p2, S2.d_p2);
+    const bool rej = (fabsf(d1) > t1) | (fabsf(d2) > t2);
+    return Mok & ((S2.flags & 2u) != 0) & (S2.cam != M.cam) & !rej;
+}
+
+static constexpr int DF_MASKM = 256;            // rows up to this length keep their flag bits
+static constexpr int DF_MASKW = DF_MASKM / 32;  // in shared memory between the count and emit passes
+
+__global__ void __launch_bounds__(DF_THREADS) k3_build_kernel(const BuildArgs a)
+{
+    extern __shared__ __align__(16) unsigned char df_smem[];
+    __shared__ BlockTab bt;
+    __shared__ uint32_t s_tot[2], s_base;
+    const uint32_t g = blockIdx.x;
+    if (g >= a.S) return;
+    const uint32_t v = a.seg_view[g];
+    const ViewDev& va = a.views[v];
+    const uint32_t i = g - va.seg_off;
+    const uint32_t i0 = a.inc_off[v], n_inc = a.inc_off[v + 1] - i0;
+    const int tid = threadIdx.x;
+    const uint32_t lane = tid & 31;
+
+    // carve the dynamic shared memory
+    const uint32_t maxm = a.maxm;
+    double* sm_dir = reinterpret_cast<double*>(df_smem);
+    Sib* sm_sib = reinterpret_cast<Sib*>(sm_dir + 3 * (size_t)maxm);
+    float2* sm_reg = reinterpret_cast<float2*>(sm_sib + maxm);
+    uint32_t* sm_c = reinterpret_cast<uint32_t*>(sm_reg + maxm);
+    uint32_t* sm_h = sm_c + (maxm + 1);
+    uint32_t* sm_mask = sm_h + (maxm + 1);  // min(maxm, DF_MASKM) x DF_MASKW words
+
+    // block table (n_inc <= DF_MAXINC is checked on the host)
+    if (tid < (int)n_inc) {
+        const IncDev q = a.inc[i0 + tid];
+        const PairDev& P = a.pairs[q.pair];
+        if (q.inverse) {
+            bt.b[tid] = a.inv_off[P.tgt_base + i];
+            bt.n[tid] = a.inv_fill[P.tgt_base + i];
+            bt.other[tid] = P.src_view;
+            bt.inv[tid] = 1u;
+        } else {
+            bt.b[tid] = a.fwd_off[P.row_base + i];
+            bt.n[tid] = a.fwd_cnt[P.row_base + i];
+            bt.other[tid] = P.tgt_view;
+            bt.inv[tid] = 0u;
+        }
+    }
+    __syncthreads();
+    if (tid < 32) {  // exclusive prefix of the block sizes (n_inc <= 64: two values per lane)
+        const uint32_t n0 = (lane < n_inc) ? bt.n[lane] : 0u;
+        const uint32_t n1 = (lane + 32 < n_inc) ? bt.n[lane + 32] : 0u;
+        uint32_t x0 = n0, x1 = n1;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t0 = __shfl_up_sync(0xffffffffu, x0, d), t1 = __shfl_up_sync(0xffffffffu, x1, d);
+            if ((int)lane >= d) { x0 += t0; x1 += t1; }
+        }
+        const uint32_t tot0 = __shfl_sync(0xffffffffu, x0, 31);
+        if (lane < n_inc) bt.pos[lane] = x0 - n0;
+        if (lane + 32 < n_inc) bt.pos[lane + 32] = tot0 + x1 - n1;
+        const uint32_t tot = tot0 + __shfl_sync(0xffffffffu, x1, 31);
+        if (lane == 0) bt.pos[n_inc] = tot;
+    }
+    __syncthreads();
+    const uint32_t m = bt.pos[n_inc];
+    if (m == 0) {
+        if (tid == 0) a.prog_nh[g] = 0u;
+        return;  // uniform
+    }
+    const size_t lbase = a.L_off[g];
+    const bool in_smem = m <= maxm;
+    if (!in_smem && a.L_sib == nullptr) {  // the host sized maxm from an upper bound: cannot happen
+        if (tid == 0) {
+            a.prog_nh[g] = 0u;
+            atomicOr(&a.stats->err, 4u);
+        }
+        return;
+    }
+    Sib* __restrict__ sib = in_smem ? sm_sib : a.L_sib + lbase;
+    double* __restrict__ dirs = in_smem ? sm_dir : a.L_dir + 3 * lbase;
+    float2* __restrict__ regs = in_smem ? sm_reg : a.L_reg + lbase;
+    uint32_t* __restrict__ cnt = in_smem ? sm_c : a.L_c + lbase + g;   // m + 1 values per row
+    uint32_t* __restrict__ hof = in_smem ? sm_h : a.L_h + lbase + g;
+    uint32_t* __restrict__ Lf = a.L_f + lbase;
+    unsigned char* __restrict__ Lm = a.L_meta + lbase;
+
+    // ---- assemble: one thread per potential entry ----
+    for (uint32_t e = tid; e < m; e += DF_THREADS) {
+        uint32_t q = 0;
+        while (bt.pos[q + 1] <= e) ++q;  // n_inc is small
+        const uint32_t j = e - bt.pos[q];
+        const uint32_t b = bt.b[q], n = bt.n[q];
+        uint32_t dst = e, f;
+        Sib sb;
+        const GeoRec* gp;
+        if (bt.inv[q]) {
+            const uint2 ie = a.inv_ent[b + j];
+            // append order of the reference = ascending forward-record index: rank sort
+            uint32_t rank = 0;
+            for (uint32_t z = 0; z < n; ++z) rank += (a.inv_ent[b + z].x < ie.x) ? 1u : 0u;
+            dst = bt.pos[q] + rank;
+            f = ie.x;
+            const FwdRec r = a.fwd_rec[f];
+            gp = a.G_inv + f;
+            sb.d_p1 = r.d_q1;
+            sb.d_p2 = r.d_q2;
+        } else {
+            f = b + j;
+            const FwdRec r = a.fwd_rec[f];
+            gp = a.G_fwd + f;
+            sb.d_p1 = r.d_p1;
+            sb.d_p2 = r.d_p2;
+        }
+        const GeoRec G = *gp;
+        sb.cam = bt.other[q];
+        sb.flags = G.valid ? 2u : 0u;
+        Lf[dst] = f;
+        Lm[dst] = (unsigned char)(q | (bt.inv[q] << 7));
+        sib[dst] = sb;
+        dirs[3 * dst + 0] = G.dir[0];
+        dirs[3 * dst + 1] = G.dir[1];
+        dirs[3 * dst + 2] = G.dir[2];
+        regs[dst] = make_float2(G.reg1, G.reg2);
+    }
+    __threadfence_block();
+    __syncthreads();
+
+    // ---- count the (M, sibling) pairs that need the full similarity ----
+    const bool use_mask = m <= (uint32_t)DF_MASKM && m <= maxm;
+    for (uint32_t e = tid; e < m; e += DF_THREADS) {
+        const Sib M = sib[e];
+        const float2 rg = regs[e];
+        const float t1 = reject_threshold(rg.x), t2 = reject_threshold(rg.y);
+        const bool Mok = (M.flags & 2u) != 0;
+        uint32_t c = 0;
+        if (use_mask) {
+            const uint32_t words = (m + 31) >> 5;
+            for (uint32_t w = 0; w < words; ++w) {
+                uint32_t bits = 0;
+                const uint32_t jend = min(32u, m - (w << 5));
+                const Sib* __restrict__ sw = sib + (w << 5);
+#pragma unroll 4
+                for (uint32_t jj = 0; jj < jend; ++jj) bits |= (pair_flagged(M, Mok, t1, t2, sw[jj]) ? 1u : 0u) << jj;
+                sm_mask[e * DF_MASKW + w] = bits;
+                c += __popc(bits);
+            }
+        } else {
+#pragma unroll 4
+            for (uint32_t j = 0; j < m; ++j) c += pair_flagged(M, Mok, t1, t2, sib[j]) ? 1u : 0u;
+        }
+        cnt[e] = c;
+    }
+    __threadfence_block();
+    __syncthreads();
+    if (tid < 32) {  // exclusive prefixes: pair offsets and head indices
+        uint32_t run_c = 0, run_h = 0;
+        for (uint32_t base = 0; base < m; base += 32) {
+            const uint32_t e = base + lane;
+            const uint32_t c = (e < m) ? cnt[e] : 0u;
+            const uint32_t h = c ? 1u : 0u;
+            uint32_t xc = c, xh = h;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t tc = __shfl_up_sync(0xffffffffu, xc, d), th = __shfl_up_sync(0xffffffffu, xh, d);
+                if ((int)lane >= d) { xc += tc; xh += th; }
+            }
+            if (e < m) {
+                cnt[e] = run_c + xc - c;
+                hof[e] = h ? (run_h + xh - h) : NOIDX;
+            }
+            run_c += __shfl_sync(0xffffffffu, xc, 31);
+            run_h += __shfl_sync(0xffffffffu, xh, 31);
+        }
+        if (lane == 0) {
+            cnt[m] = run_c;
+            s_tot[0] = run_c;
+            s_tot[1] = run_h;
+            uint32_t base = NOIDX;
+            if (run_c) {
+                base = atomicAdd(&a.stats->prog_cursor, run_c + run_h);
+                if ((uint64_t)base + run_c + run_h > a.prog_cap) {
+                    atomicOr(&a.stats->err, 4u);
+                    base = NOIDX;
+                }
+            }
+            s_base = base;
+            a.prog_off[g] = base;
+            a.prog_nh[g] = (base == NOIDX) ? 0u : run_h;
+        }
+    }
+    __threadfence_block();
+    __syncthreads();
+    const uint32_t T = s_tot[0], NH = s_tot[1];
+    if (T == 0 || s_base == NOIDX) return;  // uniform
+    uint4* __restrict__ heads = a.prog + s_base;
+    uint4* __restrict__ prs = heads + NH;
+
+    // ---- emit: head + sibling records of every match with flagged siblings ----
+    for (uint32_t e = tid; e < m; e += DF_THREADS) {
+        const uint32_t start = cnt[e], c = cnt[e + 1] - start;
+        if (!c) continue;
+        const uint32_t f = Lf[e];
+        const uint32_t inv = Lm[e] >> 7;
+        heads[hof[e]] = make_uint4(e | (inv << 31), start, c, f);
+        if (!inv) a.fwd_rec[f].score = -1.0f;  // pending: the fold kernel publishes the score
+        uint32_t k = start;
+        if (use_mask) {
+            const uint32_t words = (m + 31) >> 5;
+            for (uint32_t w = 0; w < words; ++w) {
+                uint32_t bits = sm_mask[e * DF_MASKW + w];
+                while (bits) {
+                    const uint32_t j = (w << 5) + (__ffs(bits) - 1);
+                    bits &= bits - 1;
+                    const unsigned char mj = Lm[j];
+                    prs[k++] = make_uint4((mj >> 7) ? Lf[j] : NOIDX, 0u, e, j | ((uint32_t)(mj & 63u) << 24));
+                }
+            }
+        } else {
+            const Sib M = sib[e];
+            const float2 rg = regs[e];
+            const float t1 = reject_threshold(rg.x), t2 = reject_threshold(rg.y);
+            for (uint32_t j = 0; j < m; ++j)
+                if (pair_flagged(M, true, t1, t2, sib[j])) {
+                    const unsigned char mj = Lm[j];
+                    prs[k++] = make_uint4((mj >> 7) ? Lf[j] : NOIDX, 0u, e, j | ((uint32_t)(mj & 63u) << 24));
+                }
+        }
+    }
+    __threadfence_block();
+    __syncthreads();
+
+    // ---- the flagged pairs, one per thread: full similarity ----
+    for (uint32_t t = tid; t < T; t += DF_THREADS) {
+        const uint4 pr = prs[t];
+        const uint32_t e = pr.z, j = pr.w & 0xffffffu;
+        const Sib M = sib[e];
+        const float2 rg = regs[e];
+        const D3 dirM = d3(dirs[3 * e], dirs[3 * e + 1], dirs[3 * e + 2]);
+        const float sim = sim_for_scoring(M.d_p1, M.d_p2, rg.x, rg.y, true, dirM, sib[j], dirs + 3 * j, a.two_sigA_sqr,
+                                          0.5f, -0.70f, 0.5f, a.dotcut);
+        prs[t].y = __float_as_uint(sim);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// fold: scoringCPU's accumulation over the present siblings, in dependency order
+// ------------------------------------------------------------------------------------------
+struct FoldArgs {
+    const uint32_t* seg_view;
+    const uint32_t* L_off;
+    float* L_score;  // per potential entry: score3D_ of the entry as M (0 unless folded)
+    FwdRec* fwd_rec;
+    const uint32_t* prog_off;
+    const uint32_t* prog_nh;
+    const uint4* prog;
+    uint32_t* view_max;  // [V] ordered-uint maximum score of the view
+    WfStats* stats;
+    uint32_t S;
+    uint32_t chunk;  // rows per ticket (power of two <= 32)
+};
+
+__device__ __forceinline__ float wait_score(FwdRec* fwd_rec, uint32_t f, WfStats* stats)
+{
+    const volatile float* p = &fwd_rec[f].score;
+    float s = *p;
+    uint32_t spins = 0;
+    while (s < 0.0f) {
+        __nanosleep(40);
+        s = *p;
+        if (++spins > DF_SPIN_LIMIT) {  // cannot happen (see the header); never hang the device
+            atomicOr(&stats->err, 8u);
+            return 0.0f;
+        }
+    }
+    return s;
+}
+
+__global__ void __launch_bounds__(256) k3_fold_kernel(const FoldArgs a)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    for (;;) {
+        uint32_t chunk = 0;
+        if (lane == 0) chunk = atomicAdd(&a.stats->ticket, 1u);
+        chunk = __shfl_sync(0xffffffffu, chunk, 0);
+        const uint64_t g0 = (uint64_t)chunk * a.chunk;
+        if (g0 >= a.S) break;
+        const uint32_t gl = (uint32_t)g0 + lane;
+        const uint32_t nh_l = (lane < a.chunk && gl < a.S) ? a.prog_nh[gl] : 0u;
+        uint32_t todo = __ballot_sync(0xffffffffu, nh_l != 0u);
+        while (todo) {
+            const uint32_t l = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const uint32_t g = (uint32_t)g0 + l;
+            const uint32_t NH = __shfl_sync(0xffffffffu, nh_l, l);
+            const uint4* __restrict__ heads = a.prog + a.prog_off[g];
+            const uint4* __restrict__ prs = heads + NH;
+            const size_t lbase = a.L_off[g];
+            float wmax = 0.0f;
+            for (uint32_t h = lane; h < NH; h += 32) {
+                const uint4 H = heads[h];
+                const uint32_t e = H.x & 0x7fffffffu, inv = H.x >> 31;
+                // an inverse match exists iff its forward record scored > 0 (src/line3D.cc:1994-1996)
+                if (inv && !(wait_score(a.fwd_rec, H.w, a.stats) > 0.0f)) continue;
+                float score = 0.0f, stored = 0.0f;
+                uint32_t cur_run = NOIDX;
+                for (uint32_t t = H.y; t < H.y + H.z; ++t) {
+                    const uint4 pr = prs[t];
+                    const float sim = __uint_as_float(pr.y);
+                    if (!(sim > 0.0f)) continue;
+                    if (pr.x != NOIDX && !(wait_score(a.fwd_rec, pr.x, a.stats) > 0.0f)) continue;
+                    const uint32_t run = pr.w >> 24;
+                    if (run != cur_run) {  // first sibling of this camera (src/line3D.cc:1536-1540)
+                        score = fa(score, sim);
+                        stored = sim;
+                        cur_run = run;
+                    } else if (sim > stored) {  // src/line3D.cc:1527-1534
+                        score = fs(score, stored);
+                        score = fa(score, sim);
+                        stored = sim;
+                    }
+                }
+                a.L_score[lbase + e] = score;
+                if (!inv) *(volatile float*)&a.fwd_rec[H.w].score = score;
+                wmax = fmaxf(wmax, score);
+            }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, d));
+            if (lane == 0 && wmax > 0.0f) atomicMax(&a.view_max[a.seg_view[g]], float_ordered(wmax));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// finish: existing entries, scored lists, filterMatches, estimated_position3D_
+// ------------------------------------------------------------------------------------------
+struct FinishArgs {
+    const ViewDev* views;
+    const uint32_t* seg_view;
+    const PairDev* pairs;
+    const IncDev* inc;
+    const uint32_t* inc_off;
+    const SegRays* rays;
+    const FwdRec* fwd_rec;
+    const uint32_t* fwd_row;
+    const uint32_t* L_off;
+    const uint32_t* L_f;
+    const unsigned char* L_meta;
+    const float* L_score;
+    uint32_t* L_cnt;   // [S] actual list lengths
+    ListRec* L_rec;    // scored lists (NULL unless keep_scored), row g at L_off[g]
+    const uint32_t* view_max;
+    ListRec* filt_rec;
+    uint32_t filt_cap;
+    uint32_t* filt_off;  // [S]
+    uint32_t* filt_cnt;  // [S]
+    EntryDev* entries;   // [S]
+    WfStats* stats;
+    uint32_t S;
+};
+
+__device__ __forceinline__ ListRec make_list_rec(const FinishArgs& a, uint32_t i0, uint32_t f, uint32_t meta, float score)
+{
+    const FwdRec r = a.fwd_rec[f];
+    const PairDev& P = a.pairs[a.inc[i0 + (meta & 63u)].pair];
+    ListRec L;
+    L.overlap = r.overlap;
+    L.score = score;
+    if (meta >> 7) {  // storeInverseMatches: views and depths swapped, orientation flag set
+        L.tgt_view = P.src_view;
+        L.tgt_seg = a.fwd_row[f] - P.row_base;
+        L.d_p1 = r.d_q1;
+        L.d_p2 = r.d_q2;
+        L.d_q1 = r.d_p1;
+        L.d_q2 = r.d_p2;
+        L.flags = 3u;
+        L.src_idx = NOIDX;
+    } else {
+        L.tgt_view = P.tgt_view;
+        L.tgt_seg = r.c;
+        L.d_p1 = r.d_p1;
+        L.d_p2 = r.d_p2;
+        L.d_q1 = r.d_q1;
+        L.d_q2 = r.d_q2;
+        L.flags = 0u;
+        L.src_idx = f;
+    }
+    return L;
+}
+
+static constexpr int FIN_WARPS = 8;
+
+__global__ void __launch_bounds__(FIN_WARPS * 32) k3_finish_kernel(const FinishArgs a)
+{
+    __shared__ uint32_t blkcnt[FIN_WARPS][DF_MAXINC];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t g = blockIdx.x * FIN_WARPS + warp;
+    if (g >= a.S) return;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const size_t lbase = a.L_off[g];
+    const uint32_t m = a.L_off[g + 1] - a.L_off[g];
+    const uint32_t v = a.seg_view[g];
+    const ViewDev& va = a.views[v];
+    const uint32_t i0 = a.inc_off[v];
+    if (m == 0) {
+        if (lane == 0) {
+            a.L_cnt[g] = 0u;
+            a.filt_off[g] = 0u;
+            a.filt_cnt[g] = 0u;
+            a.entries[g].has = 0u;
+        }
+        return;
+    }
+    blkcnt[warp][lane] = 0u;
+    blkcnt[warp][lane + 32] = 0u;
+    __syncwarp();
+    const float max_score = fmaxf(0.0f, ordered_to_float(a.view_max[v]));
+    const float lim = fm(0.10f, max_score);
+    uint32_t n_present = 0, kept = 0;
+    float best = 0.0f;
+    uint32_t best_idx = NOIDX;
+    bool any_valid = false;
+    for (uint32_t base = 0; base < m; base += 32) {
+        const uint32_t x = base + lane;
+        bool present = false, keep = false;
+        float s = 0.0f;
+        uint32_t f = 0, meta = 0;
+        if (x < m) {
+            f = a.L_f[lbase + x];
+            meta = a.L_meta[lbase + x];
+            present = !(meta >> 7) || a.fwd_rec[f].score > 0.0f;
+            if (present) {
+                s = a.L_score[lbase + x];
+                keep = (s > 0.0f) && (s > lim);
+                any_valid |= (s > 0.75f);
+                atomicAdd(&blkcnt[warp][meta & 63u], 1u);
+            }
+        }
+        const uint32_t bal = __ballot_sync(0xffffffffu, present);
+        if (a.L_rec && present) a.L_rec[lbase + n_present + __popc(bal & lt_mask)] = make_list_rec(a, i0, f, meta, s);
+        n_present += __popc(bal);
+        kept += __popc(__ballot_sync(0xffffffffu, keep));
+        float cs = keep ? s : 0.0f;
+        uint32_t ci = keep ? x : NOIDX;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            const float os = __shfl_xor_sync(0xffffffffu, cs, d);
+            const uint32_t oi = __shfl_xor_sync(0xffffffffu, ci, d);
+            if (os > cs || (os == cs && oi < ci)) {
+                cs = os;
+                ci = oi;
+            }
+        }
+        if (ci != NOIDX && cs > best) {  // first strict maximum in list order
+            best = cs;
+            best_idx = ci;
+        }
+    }
+    __syncwarp();
+    // sibling pairs the reference visits: present entries of other cameras
+    unsigned long long sq = (unsigned long long)blkcnt[warp][lane] * blkcnt[warp][lane] +
+                            (unsigned long long)blkcnt[warp][lane + 32] * blkcnt[warp][lane + 32];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, d);
+    const bool row_valid = __any_sync(0xffffffffu, any_valid);
+
+    uint32_t dst0 = 0;
+    if (lane == 0 && kept) dst0 = atomicAdd(&a.stats->filt_cursor, kept);
+    dst0 = __shfl_sync(0xffffffffu, dst0, 0);
+    const bool fits = (kept == 0) || ((uint64_t)dst0 + kept <= a.filt_cap);
+    if (!fits && lane == 0) atomicOr(&a.stats->err, 2u);
+    uint32_t w = 0;
+    if (kept && fits)
+        for (uint32_t base = 0; base < m; base += 32) {
+            const uint32_t x = base + lane;
+            bool keep = false;
+            float s = 0.0f;
+            uint32_t f = 0, meta = 0;
+            if (x < m) {
+                f = a.L_f[lbase + x];
+                meta = a.L_meta[lbase + x];
+                if (!(meta >> 7) || a.fwd_rec[f].score > 0.0f) {
+                    s = a.L_score[lbase + x];
+                    keep = (s > 0.0f) && (s > lim);
+                }
+            }
+            const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+            if (keep) a.filt_rec[dst0 + w + __popc(bal & lt_mask)] = make_list_rec(a, i0, f, meta, s);
+            w += __popc(bal);
+        }
+    if (lane == 0) {
+        a.L_cnt[g] = n_present;
+        a.filt_off[g] = dst0;
+        a.filt_cnt[g] = fits ? kept : 0u;
+        atomicAdd(&a.stats->scored, (unsigned long long)n_present);
+        atomicAdd(&a.stats->sim_evals, (unsigned long long)n_present * n_present - sq);
+        if (row_valid) atomicAdd(&a.stats->num_valid, 1u);
+        EntryDev& E = a.entries[g];
+        if (best_idx != NOIDX && best > 0.75f) {
+            const ListRec B = make_list_rec(a, i0, a.L_f[lbase + best_idx], a.L_meta[lbase + best_idx], best);
+            const SegRays sr = a.rays[g];
+            const D3 Ca = ld3w(va.C);
+            D3 P1 = add3(Ca, scale3(ld3w(sr.r1), (double)B.d_p1));
+            D3 P2 = add3(Ca, scale3(ld3w(sr.r2), (double)B.d_p2));
+            float len = (float)norm3(sub3(P1, P2));
+            D3 dir = d3(0.0, 0.0, 0.0);
+            if (len > L3D_EPS) dir = normalized3(sub3(P2, P1));
+            else { P1 = d3(0, 0, 0); P2 = d3(0, 0, 0); len = 0.0f; }
+            E.P1[0] = P1.x; E.P1[1] = P1.y; E.P1[2] = P1.z;
+            E.P2[0] = P2.x; E.P2[1] = P2.y; E.P2[2] = P2.z;
+            E.dir[0] = dir.x; E.dir[1] = dir.y; E.dir[2] = dir.z;
+            E.length = len;
+            E.tgt_view = B.tgt_view;
+            E.tgt_seg = B.tgt_seg;
+            E.overlap = B.overlap;
+            E.score = B.score;
+            E.d_p1 = B.d_p1; E.d_p2 = B.d_p2; E.d_q1 = B.d_q1; E.d_q2 = B.d_q2;
+            E.has = 1u;
+        } else {
+            E.has = 0u;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------
+int launch_k3_inv_capacity(const PairDev* pairs, uint32_t P, uint32_t n_rows, const uint32_t* fwd_off,
+                           const uint32_t* fwd_cnt, const FwdRec* fwd_rec, uint32_t* fwd_row, uint32_t* inv_cap,
+                           cudaStream_t st)
+{
+    if (!n_rows || !P) return 0;
+    k3_inv_capacity_kernel<<<(n_rows + 255) / 256, 256, 0, st>>>(pairs, P, n_rows, fwd_off, fwd_cnt, fwd_rec, fwd_row,
+                                                                  inv_cap);
+    return 1;
+}
+
+int launch_k3_list_capacity(const ViewDev* views, const uint32_t* seg_view, uint32_t S, const IncDev* inc,
+                            const uint32_t* inc_off, const PairDev* pairs, const uint32_t* fwd_cnt,
+                            const uint32_t* inv_cap, uint32_t* L_ub, void* stats, cudaStream_t st)
+{
+    if (!S) return 0;
+    k3_list_capacity_kernel<<<(S + 255) / 256, 256, 0, st>>>(views, seg_view, S, inc, inc_off, pairs, fwd_cnt, inv_cap,
+                                                              L_ub, (WfStats*)stats);
+    return 1;
+}
+
+int launch_k3_records(const PairDev* pairs, uint32_t P, uint32_t F, const ViewDev* views, const SegRays* rays,
+                      const uint32_t* fwd_row, FwdRec* fwd_rec, void* G_fwd, void* G_inv, const uint32_t* inv_off,
+                      uint32_t* inv_fill, uint2* inv_ent, cudaStream_t st)
+{
+    if (!F || !P) return 0;
+    k3_record_kernel<<<(F + 127) / 128, 128, 0, st>>>(pairs, P, F, views, rays, fwd_row, fwd_rec, (GeoRec*)G_fwd,
+                                                       (GeoRec*)G_inv, inv_off, inv_fill, inv_ent);
+    return 1;
+}
+
+size_t k3_geo_bytes() { return sizeof(GeoRec); }
+size_t k3_wf_stats_bytes() { return sizeof(WfStats); }
+size_t k3_sib_bytes() { return sizeof(Sib); }
+int k3_wf_max_inc() { return DF_MAXINC; }
+int k3_max_staged() { return DF_MAXM_CAP; }
+
+static size_t build_smem_bytes(uint32_t maxm)
+{
+    return (size_t)maxm * (24 + sizeof(Sib) + sizeof(float2)) + 2 * ((size_t)maxm + 1) * 4 +
+           (size_t)(maxm < (uint32_t)DF_MASKM ? maxm : (uint32_t)DF_MASKM) * DF_MASKW * 4 + 16;
+}
+
+// build + fold + finish; returns the number of launches or a negative value (CUDA error in *err)
+int launch_k3_dataflow(const ViewDev* views, const uint32_t* seg_view, const PairDev* pairs, const IncDev* inc,
+                       const uint32_t* inc_off, const SegRays* rays, const uint32_t* fwd_off, const uint32_t* fwd_cnt,
+                       FwdRec* fwd_rec, const uint32_t* fwd_row, const void* G_fwd, const void* G_inv,
+                       const uint32_t* inv_off, const uint32_t* inv_fill, const uint2* inv_ent, const uint32_t* L_off,
+                       uint32_t* L_f, unsigned char* L_meta, float* L_score, void* L_sib, double* L_dir, float2* L_reg,
+                       uint32_t* L_c, uint32_t* L_h, uint32_t* prog_off, uint32_t* prog_nh, void* prog,
+                       uint32_t prog_cap, uint32_t* L_cnt, ListRec* L_rec, uint32_t* view_max, ListRec* filt_rec,
+                       uint32_t filt_cap, uint32_t* filt_off, uint32_t* filt_cnt, EntryDev* entries, void* stats,
+                       uint32_t S, uint32_t maxm, float two_sigA_sqr, cudaStream_t st, int* err)
+{
+    if (!S) return 0;
+    if (maxm > (uint32_t)DF_MAXM_CAP) maxm = DF_MAXM_CAP;
+    maxm = (maxm + 3u) & ~3u;  // keeps the shared-memory arrays 16-byte aligned
+    if (maxm < 4) maxm = 4;
+    BuildArgs b;
+    b.views = views; b.seg_view = seg_view; b.pairs = pairs; b.inc = inc; b.inc_off = inc_off;
+    b.fwd_off = fwd_off; b.fwd_cnt = fwd_cnt; b.fwd_rec = fwd_rec;
+    b.G_fwd = (const GeoRec*)G_fwd; b.G_inv = (const GeoRec*)G_inv;
+    b.inv_off = inv_off; b.inv_fill = inv_fill; b.inv_ent = inv_ent;
+    b.L_off = L_off; b.L_f = L_f; b.L_meta = L_meta;
+    b.L_sib = (Sib*)L_sib; b.L_dir = L_dir; b.L_reg = L_reg; b.L_c = L_c; b.L_h = L_h;
+    b.prog_off = prog_off; b.prog_nh = prog_nh; b.prog = (uint4*)prog; b.prog_cap = prog_cap;
+    b.stats = (WfStats*)stats; b.S = S; b.maxm = maxm; b.two_sigA_sqr = two_sigA_sqr;
+    b.dotcut = score_dotcut(two_sigA_sqr, 0.5f);
+    const size_t smem = build_smem_bytes(maxm);
+    cudaError_t e = cudaFuncSetAttribute(k3_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+        *err = (int)e;
+        return -1;
+    }
+    k3_build_kernel<<<S, DF_THREADS, smem, st>>>(b);
+
+    FoldArgs f;
+    f.seg_view = seg_view; f.L_off = L_off; f.L_score = L_score; f.fwd_rec = fwd_rec;
+    f.prog_off = prog_off; f.prog_nh = prog_nh; f.prog = (const uint4*)prog; f.view_max = view_max;
+    f.stats = (WfStats*)stats; f.S = S;
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k3_fold_kernel, 256, 0);
+    if (e != cudaSuccess || per_sm < 1) {
+        *err = (int)e;
+        return -1;
+    }
+    // every CTA must be resident (the ticket argument needs running warps): at most one wave;
+    // rows per ticket: about one ticket per resident warp, so that the rows run side by side
+    uint32_t grid = (uint32_t)(sms * per_sm);
+    uint32_t chunk = 1;
+    while (chunk < 32 && (uint64_t)chunk * grid * 8 < S) chunk <<= 1;
+    f.chunk = chunk;
+    const uint32_t want = (S + chunk * 8 - 1) / (chunk * 8);
+    if (want < grid) grid = want ? want : 1u;
+    k3_fold_kernel<<<grid, 256, 0, st>>>(f);
+
+    FinishArgs c;
+    c.views = views; c.seg_view = seg_view; c.pairs = pairs; c.inc = inc; c.inc_off = inc_off; c.rays = rays;
+    c.fwd_rec = fwd_rec; c.fwd_row = fwd_row; c.L_off = L_off; c.L_f = L_f; c.L_meta = L_meta; c.L_score = L_score;
+    c.L_cnt = L_cnt; c.L_rec = L_rec; c.view_max = view_max; c.filt_rec = filt_rec; c.filt_cap = filt_cap;
+    c.filt_off = filt_off; c.filt_cnt = filt_cnt; c.entries = entries; c.stats = (WfStats*)stats; c.S = S;
+    k3_finish_kernel<<<(S + FIN_WARPS - 1) / FIN_WARPS, FIN_WARPS * 32, 0, st>>>(c);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        *err = (int)e;
+        return -1;
+    }
+    return 3;
+}
+
+}  // namespace l3d

@@ -19,7 +19,6 @@
 namespace l3d {
 
 #define L3D_EPS 1e-12
-static constexpr uint32_t NOIDX = 0xffffffffu;
 
 __global__ void __launch_bounds__(256) k4_has_kernel(const EntryDev* __restrict__ entries, uint32_t S,
                                                      uint32_t* __restrict__ has)

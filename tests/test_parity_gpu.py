@@ -31,6 +31,15 @@ def test_prefilter_is_conservative(api, oracle, scene_mod):
     assert a.counts()["candidates"] == a.counts()["pair_tests"]
 
 
+def test_long_rows_use_the_global_staging_path(api, oracle, scene_mod, monkeypatch):
+    """Rows whose potential list does not fit the shared-memory staging (forced here) give the same result."""
+    monkeypatch.setenv("L3D_K3_MAXM", "6")
+    sc = scene_mod.make_scene("tiny", seed=5, n_views=6, n_seg=150, nbrs=4)
+    orc = oracle.run_scene(sc)
+    l3 = api.run_scene(sc, keep_scored=True)
+    compare_full(l3, orc, sc)
+
+
 def test_knn_variants(api, oracle, scene_mod):
     for knn in (1, 3, -1):
         sc = scene_mod.make_scene("tiny", seed=4242, n_views=5, n_seg=120, nbrs=3)
