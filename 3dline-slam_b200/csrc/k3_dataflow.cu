@@ -372,15 +372,27 @@ __global__ void __launch_bounds__(DF_THREADS) k3_build_kernel(const BuildArgs a)
         const float t1 = reject_threshold(rg.x), t2 = reject_threshold(rg.y);
         const bool Mok = (M.flags & 2u) != 0;
         uint32_t c = 0;
-        if (use_mask) {
-            const uint32_t words = (m + 31) >> 5;
-            for (uint32_t w = 0; w < words; ++w) {
+        if (!Mok) {  // an invalid 3-D segment has similarity 0 with everything
+            if (use_mask)
+                for (uint32_t w = 0; w < ((m + 31) >> 5); ++w) sm_mask[e * DF_MASKW + w] = 0u;
+            cnt[e] = 0;
+            continue;
+        }
+        if (use_mask) {  // shared-memory staging: typed pointers, constant bit positions
+            const uint32_t full = m >> 5;
+            for (uint32_t w = 0; w < full; ++w) {
                 uint32_t bits = 0;
-                const uint32_t jend = min(32u, m - (w << 5));
-                const Sib* __restrict__ sw = sib + (w << 5);
-#pragma unroll 4
-                for (uint32_t jj = 0; jj < jend; ++jj) bits |= (pair_flagged(M, Mok, t1, t2, sw[jj]) ? 1u : 0u) << jj;
+                const Sib* __restrict__ sw = sm_sib + (w << 5);
+#pragma unroll
+                for (uint32_t jj = 0; jj < 32; ++jj) bits |= (pair_flagged(M, Mok, t1, t2, sw[jj]) ? 1u : 0u) << jj;
                 sm_mask[e * DF_MASKW + w] = bits;
+                c += __popc(bits);
+            }
+            if (m & 31u) {
+                uint32_t bits = 0;
+                const Sib* __restrict__ sw = sm_sib + (full << 5);
+                for (uint32_t jj = 0; jj < (m & 31u); ++jj) bits |= (pair_flagged(M, Mok, t1, t2, sw[jj]) ? 1u : 0u) << jj;
+                sm_mask[e * DF_MASKW + full] = bits;
                 c += __popc(bits);
             }
         } else {
@@ -416,8 +428,8 @@ __global__ void __launch_bounds__(DF_THREADS) k3_build_kernel(const BuildArgs a)
             s_tot[1] = run_h;
             uint32_t base = NOIDX;
             if (run_c) {
-                base = atomicAdd(&a.stats->prog_cursor, run_c + run_h);
-                if ((uint64_t)base + run_c + run_h > a.prog_cap) {
+                base = atomicAdd(&a.stats->prog_cursor, 1u + run_c + run_h);
+                if ((uint64_t)base + 1u + run_c + run_h > a.prog_cap) {
                     atomicOr(&a.stats->err, 4u);
                     base = NOIDX;
                 }
@@ -431,7 +443,9 @@ __global__ void __launch_bounds__(DF_THREADS) k3_build_kernel(const BuildArgs a)
     __syncthreads();
     const uint32_t T = s_tot[0], NH = s_tot[1];
     if (T == 0 || s_base == NOIDX) return;  // uniform
-    uint4* __restrict__ heads = a.prog + s_base;
+    // program of the row: header {heads, siblings, segment}, head records, sibling records
+    if (tid == 0) a.prog[s_base] = make_uint4(NH, T, g, 0u);
+    uint4* __restrict__ heads = a.prog + s_base + 1;
     uint4* __restrict__ prs = heads + NH;
 
     // ---- emit: head + sibling records of every match with flagged siblings ----
@@ -514,9 +528,37 @@ __device__ __forceinline__ float wait_score(FwdRec* fwd_rec, uint32_t f, WfStats
     return s;
 }
 
-__global__ void __launch_bounds__(256) k3_fold_kernel(const FoldArgs a)
+static constexpr int FOLD_WARPS = 8;
+static constexpr int FOLD_CAP = 128;  // program records of one row staged in shared memory
+
+// the accumulation of src/line3D.cc:1515-1543 over the sibling records [first, first + n)
+__device__ __forceinline__ float fold_siblings(const uint4* prs, uint32_t first, uint32_t n)
 {
-    const uint32_t lane = threadIdx.x & 31;
+    float score = 0.0f, stored = 0.0f;
+    uint32_t cur_run = NOIDX;
+    for (uint32_t t = first; t < first + n; ++t) {
+        const uint4 pr = prs[t];
+        const float sim = __uint_as_float(pr.y);
+        if (!(sim > 0.0f)) continue;  // similarity 0 or sibling absent
+        const uint32_t run = pr.w >> 24;
+        if (run != cur_run) {  // first sibling of this camera (src/line3D.cc:1536-1540)
+            score = fa(score, sim);
+            stored = sim;
+            cur_run = run;
+        } else if (sim > stored) {  // src/line3D.cc:1527-1534
+            score = fs(score, stored);
+            score = fa(score, sim);
+            stored = sim;
+        }
+    }
+    return score;
+}
+
+__global__ void __launch_bounds__(FOLD_WARPS * 32) k3_fold_kernel(const FoldArgs a)
+{
+    __shared__ uint4 sprog[FOLD_WARPS][FOLD_CAP];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint4* sp = sprog[warp];
     for (;;) {
         uint32_t chunk = 0;
         if (lane == 0) chunk = atomicAdd(&a.stats->ticket, 1u);
@@ -524,47 +566,77 @@ __global__ void __launch_bounds__(256) k3_fold_kernel(const FoldArgs a)
         const uint64_t g0 = (uint64_t)chunk * a.chunk;
         if (g0 >= a.S) break;
         const uint32_t gl = (uint32_t)g0 + lane;
-        const uint32_t nh_l = (lane < a.chunk && gl < a.S) ? a.prog_nh[gl] : 0u;
+        const bool mine = lane < a.chunk && gl < a.S;
+        const uint32_t nh_l = mine ? a.prog_nh[gl] : 0u;
+        const uint32_t po_l = mine ? a.prog_off[gl] : 0u;
+        const uint32_t lo_l = mine ? a.L_off[gl] : 0u;
+        const uint32_t vw_l = mine ? a.seg_view[gl] : 0u;
         uint32_t todo = __ballot_sync(0xffffffffu, nh_l != 0u);
         while (todo) {
             const uint32_t l = __ffs(todo) - 1;
             todo &= todo - 1;
-            const uint32_t g = (uint32_t)g0 + l;
             const uint32_t NH = __shfl_sync(0xffffffffu, nh_l, l);
-            const uint4* __restrict__ heads = a.prog + a.prog_off[g];
+            const uint4* __restrict__ prog = a.prog + __shfl_sync(0xffffffffu, po_l, l);
+            const size_t lbase = __shfl_sync(0xffffffffu, lo_l, l);
+            const uint32_t view = __shfl_sync(0xffffffffu, vw_l, l);
+            const uint32_t T = prog[0].y;
+            const uint4* __restrict__ heads = prog + 1;
             const uint4* __restrict__ prs = heads + NH;
-            const size_t lbase = a.L_off[g];
             float wmax = 0.0f;
-            for (uint32_t h = lane; h < NH; h += 32) {
-                const uint4 H = heads[h];
-                const uint32_t e = H.x & 0x7fffffffu, inv = H.x >> 31;
-                // an inverse match exists iff its forward record scored > 0 (src/line3D.cc:1994-1996)
-                if (inv && !(wait_score(a.fwd_rec, H.w, a.stats) > 0.0f)) continue;
-                float score = 0.0f, stored = 0.0f;
-                uint32_t cur_run = NOIDX;
-                for (uint32_t t = H.y; t < H.y + H.z; ++t) {
-                    const uint4 pr = prs[t];
-                    const float sim = __uint_as_float(pr.y);
-                    if (!(sim > 0.0f)) continue;
-                    if (pr.x != NOIDX && !(wait_score(a.fwd_rec, pr.x, a.stats) > 0.0f)) continue;
-                    const uint32_t run = pr.w >> 24;
-                    if (run != cur_run) {  // first sibling of this camera (src/line3D.cc:1536-1540)
-                        score = fa(score, sim);
-                        stored = sim;
-                        cur_run = run;
-                    } else if (sim > stored) {  // src/line3D.cc:1527-1534
-                        score = fs(score, stored);
-                        score = fa(score, sim);
-                        stored = sim;
+            if (NH + T <= (uint32_t)FOLD_CAP) {
+                // stage the program, resolve every presence in parallel, then fold from shared memory:
+                // the time between the last dependency and the published score stays short
+                __syncwarp();
+                for (uint32_t x = lane; x < NH + T; x += 32) {
+                    uint4 r = heads[x];
+                    if (x < NH) {
+                        // an inverse match exists iff its forward record scored > 0 (src/line3D.cc:1994-1996)
+                        if ((r.x >> 31) && !(wait_score(a.fwd_rec, r.w, a.stats) > 0.0f)) r.z = 0xffffffffu;
+                    } else if (__uint_as_float(r.y) > 0.0f && r.x != NOIDX) {
+                        if (!(wait_score(a.fwd_rec, r.x, a.stats) > 0.0f)) r.y = 0u;
                     }
+                    sp[x] = r;
                 }
-                a.L_score[lbase + e] = score;
-                if (!inv) *(volatile float*)&a.fwd_rec[H.w].score = score;
-                wmax = fmaxf(wmax, score);
+                __syncwarp();
+                for (uint32_t h = lane; h < NH; h += 32) {
+                    const uint4 H = sp[h];
+                    if (H.z == 0xffffffffu) continue;  // absent inverse match
+                    const float score = fold_siblings(sp + NH, H.y, H.z);
+                    if (!(H.x >> 31)) *(volatile float*)&a.fwd_rec[H.w].score = score;
+                    a.L_score[lbase + (H.x & 0x7fffffffu)] = score;
+                    wmax = fmaxf(wmax, score);
+                }
+            } else {
+                for (uint32_t h = lane; h < NH; h += 32) {
+                    const uint4 H = heads[h];
+                    const uint32_t e = H.x & 0x7fffffffu, inv = H.x >> 31;
+                    if (inv && !(wait_score(a.fwd_rec, H.w, a.stats) > 0.0f)) continue;
+                    float score = 0.0f, stored = 0.0f;
+                    uint32_t cur_run = NOIDX;
+                    for (uint32_t t = H.y; t < H.y + H.z; ++t) {
+                        const uint4 pr = prs[t];
+                        const float sim = __uint_as_float(pr.y);
+                        if (!(sim > 0.0f)) continue;
+                        if (pr.x != NOIDX && !(wait_score(a.fwd_rec, pr.x, a.stats) > 0.0f)) continue;
+                        const uint32_t run = pr.w >> 24;
+                        if (run != cur_run) {
+                            score = fa(score, sim);
+                            stored = sim;
+                            cur_run = run;
+                        } else if (sim > stored) {
+                            score = fs(score, stored);
+                            score = fa(score, sim);
+                            stored = sim;
+                        }
+                    }
+                    if (!inv) *(volatile float*)&a.fwd_rec[H.w].score = score;
+                    a.L_score[lbase + e] = score;
+                    wmax = fmaxf(wmax, score);
+                }
             }
 #pragma unroll
             for (int d = 16; d > 0; d >>= 1) wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, d));
-            if (lane == 0 && wmax > 0.0f) atomicMax(&a.view_max[a.seg_view[g]], float_ordered(wmax));
+            if (lane == 0 && wmax > 0.0f) atomicMax(&a.view_max[view], float_ordered(wmax));
         }
     }
 }
@@ -845,20 +917,21 @@ int launch_k3_dataflow(const ViewDev* views, const uint32_t* seg_view, const Pai
     int dev = 0, sms = 0, per_sm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k3_fold_kernel, 256, 0);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k3_fold_kernel, FOLD_WARPS * 32, 0);
     if (e != cudaSuccess || per_sm < 1) {
         *err = (int)e;
         return -1;
     }
-    // every CTA must be resident (the ticket argument needs running warps): at most one wave;
-    // rows per ticket: about one ticket per resident warp, so that the rows run side by side
+    // every CTA must be resident (the ticket argument needs running warps): at most one wave.
+    // One row per ticket: rows of one view sit at the same dependency level, so a warp that held
+    // several of them would serialise the level; larger tickets only bound the atomic traffic.
     uint32_t grid = (uint32_t)(sms * per_sm);
     uint32_t chunk = 1;
-    while (chunk < 32 && (uint64_t)chunk * grid * 8 < S) chunk <<= 1;
+    while (chunk < 32 && (uint64_t)S > (4ull << 20) * chunk) chunk <<= 1;
     f.chunk = chunk;
     const uint32_t want = (S + chunk * 8 - 1) / (chunk * 8);
     if (want < grid) grid = want ? want : 1u;
-    k3_fold_kernel<<<grid, 256, 0, st>>>(f);
+    k3_fold_kernel<<<grid, FOLD_WARPS * 32, 0, st>>>(f);
 
     FinishArgs c;
     c.views = views; c.seg_view = seg_view; c.pairs = pairs; c.inc = inc; c.inc_off = inc_off; c.rays = rays;
