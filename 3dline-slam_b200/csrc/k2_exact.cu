@@ -15,6 +15,8 @@
 //            sift-down steps follow the textbook algorithm libstdc++ uses, so equal overlaps pop in
 //            the same order), pops min(kNN, n) (src/line3D.cc:1198-1206), drops the ones that fail
 //            the orientation test and leaves the survivors, in list order, in fin_rec.
+#include <cstdlib>
+
 #include "detmath.cuh"
 #include "exact.cuh"
 #include "internal.h"
@@ -175,6 +177,17 @@ __device__ __forceinline__ float mutual_overlap_xy(double ax, double ay, double 
     return mutual_overlap(pt);
 }
 
+// RN(num / den) > 1e-12, decided without the division whenever the quotient is not within 1e-10
+// (relative) of the threshold: rounding is monotone and doubles near 1e-12 are 2e-28 apart
+__device__ __forceinline__ bool depth_positive(double num, double den)
+{
+    if (num == 0.0 || ((num < 0.0) != (den < 0.0))) return false;
+    const double an = fabs(num), p = L3D_EPS * fabs(den);
+    if (an > p * 1.0000000001) return true;
+    if (an < p * 0.9999999999) return false;
+    return dd(num, den) > L3D_EPS;
+}
+
 static constexpr int K2_WARPS = 4;     // warps per CTA, one row per warp at a time
 static constexpr int K2_SUB = 64;      // rows per CTA (a quarter of a K1 tile)
 static constexpr int K2_CHUNK = 1024;  // target segments per enumeration chunk (32 mask words)
@@ -189,7 +202,8 @@ struct K2WarpSmem {
 // candidate, phase B: triangulation + orientation test of the ones that pass (dense lanes again),
 // then the kNN selection in priority-queue pop order and the orientation filter.  Only matches with
 // four positive depths are ever written to memory. ----
-__global__ void __launch_bounds__(K2_WARPS * 32) k2_row_kernel(
+template <int MINB>
+__global__ void __launch_bounds__(K2_WARPS * 32, MINB) k2_row_kernel(
     const PairDev* __restrict__ pairs, const K1Cta* __restrict__ ctas, const uint32_t* __restrict__ mask,
     const uint32_t* __restrict__ cand_off, const float4* __restrict__ segs, const SegRays* __restrict__ rays,
     const double* __restrict__ midray, const SegPlane* __restrict__ planes, const ViewDev* __restrict__ views,
@@ -213,7 +227,11 @@ __global__ void __launch_bounds__(K2_WARPS * 32) k2_row_kernel(
         if (r >= n_src) break;  // warp-uniform
         const uint32_t lrow = P.row_base - P.batch_row0 + r;
         const uint32_t base = cand_off[lrow];
-        FwdRec* __restrict__ stage = cand_rec + base;
+        // scratch of the row, sized by its K1 candidate count: staging keys (overlap << 32 | target),
+        // heap replay keys and the pop order
+        unsigned long long* __restrict__ stage = heap + base;
+        unsigned long long* __restrict__ hscr = reinterpret_cast<unsigned long long*>(cand_rec + base);
+        uint32_t* __restrict__ gsel = reinterpret_cast<uint32_t*>(hscr + (cand_off[lrow + 1] - base));
         FwdRec* __restrict__ frec = fin_rec + base;
         const uint32_t* __restrict__ mrow = mask + P.mask_base + r;
 
@@ -221,6 +239,13 @@ __global__ void __launch_bounds__(K2_WARPS * 32) k2_row_kernel(
         const float4 sg = segs[P.src_off + r];
         const D3 p1 = d3((double)sg.x, (double)sg.y, 1.0), p2 = d3((double)sg.z, (double)sg.w, 1.0);
         const D3 e1 = mul33(P.F, p1), e2 = mul33(P.F, p2);
+        // triangulation constants of the row: n = (r1 x r2).normalized() and n.C come from k0_prep
+        const SegRays sr = rays[P.src_off + r];
+        const D3 rp1 = ld3(sr.r1), rp2 = ld3(sr.r2);
+        const SegPlane plB = planes[P.src_off + r];
+        const D3 nB = ld3(plB.n);
+        const double numB = ds(plB.cn, dot3(nB, Ct));
+        const D3 rmid = ld3(midray + 3 * (size_t)(P.src_off + r));
         uint32_t n_valid = 0;
 
         for (uint32_t cb = 0; cb < n_tgt; cb += K2_CHUNK) {
@@ -277,153 +302,142 @@ __global__ void __launch_bounds__(K2_WARPS * 32) k2_row_kernel(
             }
             if (npass == 0) continue;
 
-            // ---- phase B: both triangulations (src/line3D.cc:1365-1390; the plane normals n = (r1 x r2)
-            // .normalized() and n.C are per-segment constants from k0_prep) + the orientation test of the
-            // would-be match (checkMatchOrientation, src/line3D.cc:962-1014) ----
-            const SegRays sr = rays[P.src_off + r];
-            const D3 rp1 = ld3(sr.r1), rp2 = ld3(sr.r2);
-            const SegPlane plB = planes[P.src_off + r];
-            const D3 nB = ld3(plB.n);
-            const double numB = ds(plB.cn, dot3(nB, Ct));
-            const D3 rmid = ld3(midray + 3 * (size_t)(P.src_off + r));
+            // ---- phase B: which candidates triangulate to four positive depths (src/line3D.cc:1160-1168,
+            // 1365-1390).  Only the sign of every depth is needed here; the divisions are done for the
+            // matches that survive the kNN selection. ----
             for (uint32_t k0 = 0; k0 < npass; k0 += 32) {
                 const uint32_t k = k0 + lane;
                 bool valid = false;
-                FwdRec rec;
-                rec.flags = 0u;
-                rec.score = 0.0f;
+                uint32_t c = 0;
                 if (k < npass) {
-                    const uint32_t c = cb + (uint32_t)sm.cl[k];
+                    c = cb + (uint32_t)sm.cl[k];
                     const SegRays tr = rays[P.tgt_off + c];
                     const SegPlane plA = planes[P.tgt_off + c];
-                    const D3 rq1 = ld3(tr.r1), rq2 = ld3(tr.r2);
                     const D3 nA = ld3(plA.n);
-                    double ds1 = -1.0, ds2 = -1.0, dt1 = -1.0, dt2 = -1.0;
-                    {  // triangulationDepths(src,p | tgt,q)
-                        const double a1 = dot3(rp1, nA), a2 = dot3(rp2, nA);
-                        if (!(fabs(a1) < L3D_EPS || fabs(a2) < L3D_EPS)) {
-                            const double num = ds(plA.cn, dot3(nA, Cs));
-                            ds1 = dd(num, a1);  // n.ray(p1): the same products in the same order as ray(p1).n
-                            ds2 = dd(num, a2);
-                        }
-                    }
-                    {  // triangulationDepths(tgt,q | src,p)
-                        const double b1 = dot3(rq1, nB), b2 = dot3(rq2, nB);
-                        if (!(fabs(b1) < L3D_EPS || fabs(b2) < L3D_EPS)) {
-                            dt1 = dd(numB, b1);
-                            dt2 = dd(numB, b2);
-                        }
-                    }
-                    if (ds1 > L3D_EPS && ds2 > L3D_EPS && dt1 > L3D_EPS && dt2 > L3D_EPS) {
-                        valid = true;
-                        rec.c = c;
-                        rec.overlap = sm.ps[k];
-                        rec.d_p1 = (float)ds1;
-                        rec.d_p2 = (float)ds2;
-                        rec.d_q1 = (float)dt1;
-                        rec.d_q2 = (float)dt2;
-                        // flags = 1: dropped by the orientation filter if it survives the kNN selection.
-                        // The test is acos(x) in (0.0982, 3.0434) with x = ray(mid) . dir, dir = (P2-P1)/|P2-P1|,
-                        // i.e. |x| < 0.99518...: when (ray(mid).(P2-P1))^2 < 0.9951^2 |P2-P1|^2 the exact x
-                        // (relative error ~1e-15) is inside by a margin of 8e-5 and no sqrt/div/acos is needed.
-                        const D3 P1 = add3(Cs, scale3(rp1, (double)rec.d_p1));
-                        const D3 P2 = add3(Cs, scale3(rp2, (double)rec.d_p2));
-                        const D3 vv = sub3(P2, P1);
-                        const double v2 = dot3(vv, vv), sv = dot3(rmid, vv);
-                        if (!(v2 > 1e-20 && sv * sv < 0.99022401 * v2)) {
-                            const float len = (float)norm3(sub3(P1, P2));
-                            D3 dir = d3(0.0, 0.0, 0.0);
-                            if (len > L3D_EPS) dir = normalized3(vv);
-                            const double ang = det_acos(fmin(fmax(dot3(rmid, dir), -1.0), 1.0));
-                            rec.flags = (ang > (double)0.098174771f && ang < (double)3.043417886f) ? 0u : 1u;
-                        }
+                    const double a1 = dot3(rp1, nA), a2 = dot3(rp2, nA);
+                    const double b1 = dot3(ld3(tr.r1), nB), b2 = dot3(ld3(tr.r2), nB);
+                    if (!(fabs(a1) < L3D_EPS || fabs(a2) < L3D_EPS || fabs(b1) < L3D_EPS || fabs(b2) < L3D_EPS)) {
+                        const double num = ds(plA.cn, dot3(nA, Cs));
+                        valid = depth_positive(num, a1) && depth_positive(num, a2) && depth_positive(numB, b1) &&
+                                depth_positive(numB, b2);
                     }
                 }
                 const uint32_t bal = __ballot_sync(0xffffffffu, valid);
-                if (valid) stage[n_valid + __popc(bal & lt_mask)] = rec;
+                if (valid)
+                    stage[n_valid + __popc(bal & lt_mask)] = ((unsigned long long)__float_as_uint(sm.ps[k]) << 32) | c;
                 n_valid += __popc(bal);
             }
             __syncwarp();
         }
 
-        // ---- selection: std::priority_queue pop order (include/commons.h:233-244, src/line3D.cc:1198-1206),
-        // then the orientation filter ----
-        uint32_t nout = 0;
+        // ---- selection: std::priority_queue pop order (include/commons.h:233-244, src/line3D.cc:1198-1206):
+        // sel[t] = staging index of the t-th popped match ----
         __syncwarp();
-        if (knn <= 0) {
-            for (uint32_t k0 = 0; k0 < n_valid; k0 += 32) {
-                const uint32_t k = k0 + lane;
-                FwdRec rc;
-                bool keep = false;
-                if (k < n_valid) {
-                    rc = stage[k];
-                    keep = (rc.flags == 0u) || !apply_orient;
-                }
-                const uint32_t bal = __ballot_sync(0xffffffffu, keep);
-                if (keep) {
-                    rc.flags = 0u;
-                    frec[nout + __popc(bal & lt_mask)] = rc;
-                }
-                nout += __popc(bal);
-            }
-        } else if (n_valid) {
-            const uint32_t npop = min((uint32_t)knn, n_valid);
-            // distinct overlaps pop in descending order: rank = number of larger overlaps
-            bool fast = (n_valid <= K2_CHUNK) && (knn <= 32);
+        uint32_t npop = n_valid;   // kNN <= 0: every match, ascending target order
+        int sel_mode = 0;          // 0: identity, 1: sm.cl (shared), 2: gsel (global)
+        if (knn > 0 && n_valid) {
+            npop = min((uint32_t)knn, n_valid);
+            bool fast = n_valid <= K2_CHUNK;
             if (fast) {
-                for (uint32_t k = lane; k < n_valid; k += 32) sm.ps[k] = stage[k].overlap;
+                // distinct overlaps pop in descending order: rank = number of strictly larger overlaps;
+                // equal overlaps among the popped ones show up as fewer than npop distinct ranks below npop
+                for (uint32_t k = lane; k < n_valid; k += 32) sm.ps[k] = key_overlap(stage[k]);
                 __syncwarp();
-                // rank = number of strictly larger overlaps; equal overlaps among the popped ones show up
-                // as a rank collision, i.e. fewer than npop distinct ranks below npop
-                uint32_t keepbits = 0, rankbits = 0;
+                uint32_t seen = 0, rankbits = 0;
                 for (uint32_t k = lane; k < n_valid; k += 32) {
                     const float ov = sm.ps[k];
                     uint32_t rank = 0;
                     for (uint32_t j = 0; j < n_valid; ++j) rank += (sm.ps[j] > ov) ? 1u : 0u;
-                    bool keep = false;
                     if (rank < npop) {
-                        rankbits |= 1u << rank;
-                        keep = !apply_orient || stage[k].flags == 0u;
-                        if (keep) keepbits |= 1u << rank;
+                        sm.cl[rank] = (unsigned short)k;  // colliding ranks are detected below
+                        rankbits |= 1u << (rank & 31u);
+                        ++seen;
                     }
-                    sm.cl[k] = (unsigned short)(keep ? rank : 0xffffu);
                 }
-                rankbits = __reduce_or_sync(0xffffffffu, rankbits);
-                fast = (uint32_t)__popc(rankbits) == npop;
-                if (fast) {
-                    keepbits = __reduce_or_sync(0xffffffffu, keepbits);
-                    for (uint32_t k = lane; k < n_valid; k += 32) {
-                        const uint32_t rank = sm.cl[k];
-                        if (rank != 0xffffu) {
-                            FwdRec rc = stage[k];
-                            rc.flags = 0u;
-                            frec[__popc(keepbits & ((1u << rank) - 1u))] = rc;
+                if (npop <= 32) {  // npop distinct ranks below npop <=> no two of them are equal
+                    fast = (uint32_t)__popc(__reduce_or_sync(0xffffffffu, rankbits)) == npop;
+                } else {
+#pragma unroll
+                    for (int d = 16; d > 0; d >>= 1) seen += __shfl_xor_sync(0xffffffffu, seen, d);
+                    fast = seen == npop;
+                    if (fast) {  // a collision leaves a slot stale: every slot must hold its own rank
+                        uint32_t ok = 1;
+                        for (uint32_t t = lane; t < npop; t += 32) {
+                            const float ov = sm.ps[sm.cl[t]];
+                            uint32_t rank = 0;
+                            for (uint32_t j = 0; j < n_valid; ++j) rank += (sm.ps[j] > ov) ? 1u : 0u;
+                            ok &= (rank == t) ? 1u : 0u;
                         }
+                        fast = __all_sync(0xffffffffu, ok != 0u);
                     }
-                    nout = __popc(keepbits);
                 }
                 __syncwarp();
+                sel_mode = 1;
             }
             if (!fast) {
                 // equal overlaps: replay the binary heap (push in ascending target order, pop kNN)
+                sel_mode = 2;
                 if (lane == 0) {
-                    unsigned long long* __restrict__ hp = heap + base;
                     for (uint32_t i = 0; i < n_valid; ++i)
-                        heap_push(hp, i, ((unsigned long long)__float_as_uint(stage[i].overlap) << 32) | i);
+                        heap_push(hscr, i, (stage[i] & 0xffffffff00000000ull) | i);
                     uint32_t hn = n_valid;
                     for (uint32_t t = 0; t < npop; ++t) {
-                        const uint32_t idx = (uint32_t)(hp[0] & 0xffffffffu);
-                        heap_pop(hp, hn);
+                        gsel[t] = (uint32_t)(hscr[0] & 0xffffffffu);
+                        heap_pop(hscr, hn);
                         --hn;
-                        FwdRec rc = stage[idx];
-                        if (rc.flags == 0u || !apply_orient) {
-                            rc.flags = 0u;
-                            frec[nout++] = rc;
-                        }
                     }
                 }
-                nout = __shfl_sync(0xffffffffu, nout, 0);
+                __syncwarp();
             }
+        }
+
+        // ---- the popped matches: depths (src/line3D.cc:1365-1390), the orientation test of the would-be
+        // match (checkMatchOrientation, src/line3D.cc:962-1014), output in pop order ----
+        uint32_t nout = 0;
+        for (uint32_t t0 = 0; t0 < npop; t0 += 32) {
+            const uint32_t t = t0 + lane;
+            bool keep = false;
+            FwdRec rec;
+            rec.flags = 0u;
+            rec.score = 0.0f;
+            if (t < npop) {
+                const uint32_t k = sel_mode == 0 ? t : (sel_mode == 1 ? (uint32_t)sm.cl[t] : gsel[t]);
+                const unsigned long long key = stage[k];
+                const uint32_t c = (uint32_t)(key & 0xffffffffu);
+                const SegRays tr = rays[P.tgt_off + c];
+                const SegPlane plA = planes[P.tgt_off + c];
+                const D3 nA = ld3(plA.n);
+                const double num = ds(plA.cn, dot3(nA, Cs));
+                // n.ray(p1): the same products in the same order as ray(p1).n
+                const double ds1 = dd(num, dot3(rp1, nA)), ds2 = dd(num, dot3(rp2, nA));
+                const double dt1 = dd(numB, dot3(ld3(tr.r1), nB)), dt2 = dd(numB, dot3(ld3(tr.r2), nB));
+                rec.c = c;
+                rec.overlap = key_overlap(key);
+                rec.d_p1 = (float)ds1;
+                rec.d_p2 = (float)ds2;
+                rec.d_q1 = (float)dt1;
+                rec.d_q2 = (float)dt2;
+                keep = true;
+                if (apply_orient) {
+                    // The test is acos(x) in (0.0982, 3.0434) with x = ray(mid) . dir, dir = (P2-P1)/|P2-P1|,
+                    // i.e. |x| < 0.99518...: when (ray(mid).(P2-P1))^2 < 0.9951^2 |P2-P1|^2 the exact x
+                    // (relative error ~1e-15) is inside by a margin of 8e-5 and no sqrt/div/acos is needed.
+                    const D3 P1 = add3(Cs, scale3(rp1, (double)rec.d_p1));
+                    const D3 P2 = add3(Cs, scale3(rp2, (double)rec.d_p2));
+                    const D3 vv = sub3(P2, P1);
+                    const double v2 = dot3(vv, vv), sv = dot3(rmid, vv);
+                    if (!(v2 > 1e-20 && sv * sv < 0.99022401 * v2)) {
+                        const float len = (float)norm3(sub3(P1, P2));
+                        D3 dir = d3(0.0, 0.0, 0.0);
+                        if (len > L3D_EPS) dir = normalized3(vv);
+                        const double ang = det_acos(fmin(fmax(dot3(rmid, dir), -1.0), 1.0));
+                        keep = ang > (double)0.098174771f && ang < (double)3.043417886f;
+                    }
+                }
+            }
+            const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+            if (keep) frec[nout + __popc(bal & lt_mask)] = rec;
+            nout += __popc(bal);
         }
         if (lane == 0) fin_cnt[lrow] = nout;
         __syncwarp();
@@ -455,9 +469,20 @@ int launch_k2_exact(const PairDev* pairs, const K1Cta* ctas, uint32_t n_ctas, ui
     if (n_ctas == 0) return 0;
     (void)n_rows;
     (void)n_cand;
-    k2_row_kernel<<<n_ctas * (K2_ROWS / K2_SUB), K2_WARPS * 32, 0, st>>>(pairs, ctas, mask, cand_off, segs, rays, midray,
-                                                                        planes, views, heap, cand_rec, fin_rec, fin_cnt, thr,
-                                                                        (double)max_image_width, knn, apply_orient);
+    static int minb = -1;
+    if (minb < 0) {
+        const char* e = getenv("L3D_K2_MINB");  // tuning hook: resident CTAs per SM the kernel is compiled for
+        minb = e ? atoi(e) : 4;
+    }
+    const dim3 grid(n_ctas * (K2_ROWS / K2_SUB)), block(K2_WARPS * 32);
+#define K2_LAUNCH(MB)                                                                                             \
+    k2_row_kernel<MB><<<grid, block, 0, st>>>(pairs, ctas, mask, cand_off, segs, rays, midray, planes, views, heap, \
+                                              cand_rec, fin_rec, fin_cnt, thr, (double)max_image_width, knn,       \
+                                              apply_orient)
+    if (minb >= 8) K2_LAUNCH(8);
+    else if (minb >= 6) K2_LAUNCH(6);
+    else K2_LAUNCH(4);
+#undef K2_LAUNCH
     return 1;
 }
 
