@@ -107,14 +107,21 @@ int l3d_scene_commit(l3d_ctx* ctx)
     if (S > 0xfffffff0ull) return fail(L3D_ERR_CAPACITY, "too many segments (%llu)", (unsigned long long)S);
     ctx->S = (uint32_t)S;
     const uint32_t V = (uint32_t)ctx->views.size();
-    // pinned staging: one H2D copy of all segments
-    std::vector<uint32_t> seg_view(S);
-    float4* hseg = nullptr;
-    CK(cudaMallocHost((void**)&hseg, std::max<size_t>(S, 1) * sizeof(float4)));
+    // pinned staging (kept by the context): one H2D copy of all segments and of their view ids
+    const size_t need = std::max<size_t>(S, 1) * (sizeof(float4) + sizeof(uint32_t));
+    if (need > ctx->pinned_cap) {
+        if (ctx->pinned) cudaFreeHost(ctx->pinned);
+        ctx->pinned = nullptr;
+        ctx->pinned_cap = 0;
+        CK(cudaMallocHost(&ctx->pinned, need + need / 2));
+        ctx->pinned_cap = need + need / 2;
+    }
+    float4* hseg = (float4*)ctx->pinned;
+    uint32_t* seg_view = (uint32_t*)(hseg + std::max<size_t>(S, 1));
     for (uint32_t v = 0; v < V; ++v) {
         const HostView& hv = ctx->views[v];
         memcpy(hseg + hv.seg_off, hv.segs.data(), hv.segs.size() * sizeof(float));
-        std::fill(seg_view.begin() + hv.seg_off, seg_view.begin() + hv.seg_off + hv.v.num_segs, v);
+        std::fill(seg_view + hv.seg_off, seg_view + hv.seg_off + hv.v.num_segs, v);
     }
     CK(ctx->d_segs.ensure(S));
     CK(ctx->d_seg_view.ensure(S));
@@ -125,9 +132,8 @@ int l3d_scene_commit(l3d_ctx* ctx)
     CK(ctx->d_view_xb.ensure(V));
     CK(ctx->d_views.ensure(V));
     CK(cudaMemcpyAsync(ctx->d_segs.p, hseg, S * sizeof(float4), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(ctx->d_seg_view.p, seg_view.data(), S * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_seg_view.p, seg_view, S * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     CK(cudaStreamSynchronize(st));
-    CK(cudaFreeHost(hseg));
     ctx->committed = true;
     ctx->stage = 0;
     return L3D_OK;

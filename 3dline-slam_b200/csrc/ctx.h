@@ -195,6 +195,13 @@ struct l3d_ctx {
     bool raw_mode = false;        // l3d_match_lines: cameras given as (RtKinv, C), F given, no translation
     double F_override[9] = {0};
 
+    void* pinned = nullptr;  // pinned host staging of the segment upload
+    size_t pinned_cap = 0;
+    ~l3d_ctx()
+    {
+        if (pinned) cudaFreeHost(pinned);
+    }
+
     // device tables
     DevBuf<float4> d_segs;
     DevBuf<uint32_t> d_seg_view;

@@ -14,13 +14,13 @@
 //          (M, sibling) pair that can be non-zero; emit the row's "fold program": per match M
 //          with at least one such sibling a head record and the sibling records (record index whose
 //          score decides presence, similarity, camera block).
-//   fold   (one persistent kernel, rows handed out in (view, segment) order by a ticket counter):
-//          Line3D::scoringCPU's accumulation (src/line3D.cc:1515-1543) over the siblings that are
-//          present; a sibling that is an inverse match waits (spins) on the score of its forward
-//          record, which an earlier ticket produces.  Tickets are taken in order by resident warps
-//          and a row only ever waits on rows of earlier views, so the smallest unfinished ticket
-//          never waits: no deadlock, no grid-wide barrier, and the critical path is the longest
-//          dependency chain instead of the number of views.
+//   fold   (one persistent kernel, rows dealt round-robin to the resident warps in (view, segment)
+//          order): Line3D::scoringCPU's accumulation (src/line3D.cc:1515-1543) over the siblings
+//          that are present; a sibling that is an inverse match waits (spins) on the score of its
+//          forward record, which a row of an earlier view produces.  Every warp takes its rows in
+//          ascending order and a row only ever waits on rows of earlier views, so the smallest
+//          unfinished row never waits: no deadlock, no grid-wide barrier, and the critical path is
+//          the longest dependency chain instead of the number of views.
 //   finish (all rows at once, one warp per segment): which potential entries exist, the scored
 //          lists (optional), Line3D::filterMatches (src/line3D.cc:1911-1983) and the
 //          estimated_position3D_ row.
@@ -28,6 +28,8 @@
 // A sibling with similarity 0 never changes score3D_ (x + 0 = x; 0 > stored is false; a later
 // s > 0 of the same camera gives (score - 0) + s, the same value as a first add), so only pairs
 // that pass the cheap certain-reject test are evaluated and folded.
+#include <cstdlib>
+
 #include "internal.h"
 #include "score_core.cuh"
 
@@ -509,16 +511,16 @@ struct FoldArgs {
     uint32_t* view_max;  // [V] ordered-uint maximum score of the view
     WfStats* stats;
     uint32_t S;
-    uint32_t chunk;  // rows per ticket (power of two <= 32)
+    uint32_t sleep_ns;  // back-off between two polls of a pending score
 };
 
-__device__ __forceinline__ float wait_score(FwdRec* fwd_rec, uint32_t f, WfStats* stats)
+__device__ __forceinline__ float wait_score(FwdRec* fwd_rec, uint32_t f, WfStats* stats, uint32_t sleep_ns)
 {
     const volatile float* p = &fwd_rec[f].score;
     float s = *p;
     uint32_t spins = 0;
     while (s < 0.0f) {
-        __nanosleep(40);
+        if (sleep_ns) __nanosleep(sleep_ns);
         s = *p;
         if (++spins > DF_SPIN_LIMIT) {  // cannot happen (see the header); never hang the device
             atomicOr(&stats->err, 8u);
@@ -559,26 +561,17 @@ __global__ void __launch_bounds__(FOLD_WARPS * 32) k3_fold_kernel(const FoldArgs
     __shared__ uint4 sprog[FOLD_WARPS][FOLD_CAP];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint4* sp = sprog[warp];
-    for (;;) {
-        uint32_t chunk = 0;
-        if (lane == 0) chunk = atomicAdd(&a.stats->ticket, 1u);
-        chunk = __shfl_sync(0xffffffffu, chunk, 0);
-        const uint64_t g0 = (uint64_t)chunk * a.chunk;
-        if (g0 >= a.S) break;
-        const uint32_t gl = (uint32_t)g0 + lane;
-        const bool mine = lane < a.chunk && gl < a.S;
-        const uint32_t nh_l = mine ? a.prog_nh[gl] : 0u;
-        const uint32_t po_l = mine ? a.prog_off[gl] : 0u;
-        const uint32_t lo_l = mine ? a.L_off[gl] : 0u;
-        const uint32_t vw_l = mine ? a.seg_view[gl] : 0u;
-        uint32_t todo = __ballot_sync(0xffffffffu, nh_l != 0u);
-        while (todo) {
-            const uint32_t l = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const uint32_t NH = __shfl_sync(0xffffffffu, nh_l, l);
-            const uint4* __restrict__ prog = a.prog + __shfl_sync(0xffffffffu, po_l, l);
-            const size_t lbase = __shfl_sync(0xffffffffu, lo_l, l);
-            const uint32_t view = __shfl_sync(0xffffffffu, vw_l, l);
+    // Rows are dealt round-robin to the resident warps, each warp takes its rows in ascending order.
+    // The smallest unfinished row of the grid is then always the current row of its warp and all the
+    // rows it waits on are finished: it never blocks, so the grid always makes progress.
+    const uint32_t n_warps = gridDim.x * FOLD_WARPS;
+    for (uint32_t g = blockIdx.x * FOLD_WARPS + warp; g < a.S; g += n_warps) {
+        const uint32_t NH = a.prog_nh[g];
+        if (NH == 0) continue;  // warp-uniform
+        {
+            const uint4* __restrict__ prog = a.prog + a.prog_off[g];
+            const size_t lbase = a.L_off[g];
+            const uint32_t view = a.seg_view[g];
             const uint32_t T = prog[0].y;
             const uint4* __restrict__ heads = prog + 1;
             const uint4* __restrict__ prs = heads + NH;
@@ -591,9 +584,9 @@ __global__ void __launch_bounds__(FOLD_WARPS * 32) k3_fold_kernel(const FoldArgs
                     uint4 r = heads[x];
                     if (x < NH) {
                         // an inverse match exists iff its forward record scored > 0 (src/line3D.cc:1994-1996)
-                        if ((r.x >> 31) && !(wait_score(a.fwd_rec, r.w, a.stats) > 0.0f)) r.z = 0xffffffffu;
+                        if ((r.x >> 31) && !(wait_score(a.fwd_rec, r.w, a.stats, a.sleep_ns) > 0.0f)) r.z = 0xffffffffu;
                     } else if (__uint_as_float(r.y) > 0.0f && r.x != NOIDX) {
-                        if (!(wait_score(a.fwd_rec, r.x, a.stats) > 0.0f)) r.y = 0u;
+                        if (!(wait_score(a.fwd_rec, r.x, a.stats, a.sleep_ns) > 0.0f)) r.y = 0u;
                     }
                     sp[x] = r;
                 }
@@ -610,14 +603,14 @@ __global__ void __launch_bounds__(FOLD_WARPS * 32) k3_fold_kernel(const FoldArgs
                 for (uint32_t h = lane; h < NH; h += 32) {
                     const uint4 H = heads[h];
                     const uint32_t e = H.x & 0x7fffffffu, inv = H.x >> 31;
-                    if (inv && !(wait_score(a.fwd_rec, H.w, a.stats) > 0.0f)) continue;
+                    if (inv && !(wait_score(a.fwd_rec, H.w, a.stats, a.sleep_ns) > 0.0f)) continue;
                     float score = 0.0f, stored = 0.0f;
                     uint32_t cur_run = NOIDX;
                     for (uint32_t t = H.y; t < H.y + H.z; ++t) {
                         const uint4 pr = prs[t];
                         const float sim = __uint_as_float(pr.y);
                         if (!(sim > 0.0f)) continue;
-                        if (pr.x != NOIDX && !(wait_score(a.fwd_rec, pr.x, a.stats) > 0.0f)) continue;
+                        if (pr.x != NOIDX && !(wait_score(a.fwd_rec, pr.x, a.stats, a.sleep_ns) > 0.0f)) continue;
                         const uint32_t run = pr.w >> 24;
                         if (run != cur_run) {
                             score = fa(score, sim);
@@ -922,15 +915,16 @@ int launch_k3_dataflow(const ViewDev* views, const uint32_t* seg_view, const Pai
         *err = (int)e;
         return -1;
     }
-    // every CTA must be resident (the ticket argument needs running warps): at most one wave.
-    // One row per ticket: rows of one view sit at the same dependency level, so a warp that held
-    // several of them would serialise the level; larger tickets only bound the atomic traffic.
+    // every CTA must be resident (the progress argument needs running warps): at most one wave
     uint32_t grid = (uint32_t)(sms * per_sm);
-    uint32_t chunk = 1;
-    while (chunk < 32 && (uint64_t)S > (4ull << 20) * chunk) chunk <<= 1;
-    f.chunk = chunk;
-    const uint32_t want = (S + chunk * 8 - 1) / (chunk * 8);
+    const uint32_t want = (S + FOLD_WARPS - 1) / FOLD_WARPS;
     if (want < grid) grid = want ? want : 1u;
+    static int sleep_ns = -1;
+    if (sleep_ns < 0) {
+        const char* e = getenv("L3D_FOLD_SLEEP_NS");  // tuning hook
+        sleep_ns = e ? atoi(e) : 40;
+    }
+    f.sleep_ns = (uint32_t)sleep_ns;
     k3_fold_kernel<<<grid, FOLD_WARPS * 32, 0, st>>>(f);
 
     FinishArgs c;

@@ -56,7 +56,7 @@ class ClockSampler:
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "10"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -138,7 +138,7 @@ def bench_reference(args, scene_mod):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2")
@@ -262,27 +262,32 @@ def main():
     views_per_s = scene.num_views * args.steps / (total_ms * 1e-3)
 
     # ---- end to end through the public API with host buffers (H2D of the scene, D2H of A_) ----
-    e2e = None
-    if n_gpus == 1:
-        h2d = scene.total_segments() * 16 + scene.num_views * (8 * 21 + 20) + sum(4 * len(v.neighbors) for v in scene.views)
-        d2h = 0
-        t_e2e = 0.0
-        for i in range(2 + args.steps):
-            flush.zero_()
-            torch.cuda.synchronize(dev)
-            t0 = time.perf_counter()
-            l3.upload()                      # host -> device: segments, cameras, neighbour lists
-            step()
-            ij, w = l3.edges()               # device -> host: A_ (what the CPU clustering consumes)
-            l2g = l3.local2global()
-            torch.cuda.synchronize(dev)
-            dt = time.perf_counter() - t0
-            if i >= 2:
-                t_e2e += dt
-            d2h = ij.nbytes + w.nbytes + l2g.nbytes
-        e2e = {"value": tests_per_step * args.steps / t_e2e, "unit": "tests/s", "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * t_e2e / args.steps,
-               "views_per_s": scene.num_views * args.steps / t_e2e}
+    # every rank uploads the (replicated) tables and reads back A_; wall clock, max over ranks
+    h2d = scene.total_segments() * 16 + scene.num_views * (8 * 21 + 20) + sum(4 * len(v.neighbors) for v in scene.views)
+    d2h = 0
+    t_e2e = 0.0
+    e2e_steps = min(args.steps, 20)
+    for i in range(2 + e2e_steps):
+        flush.zero_()
+        barrier()
+        t0 = time.perf_counter()
+        l3.upload()                      # host -> device: segments, cameras, neighbour lists
+        step()
+        ij, w = l3.edges()               # device -> host: A_ (what the CPU clustering consumes)
+        l2g = l3.local2global()
+        barrier()
+        dt = time.perf_counter() - t0
+        if i >= 2:
+            t_e2e += dt
+        d2h = ij.nbytes + w.nbytes + l2g.nbytes
+    if dist is not None:
+        t = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_e2e = float(t.item())
+    e2e = {"value": tests_per_step * e2e_steps / t_e2e, "unit": "tests/s", "h2d_bytes_per_step": int(h2d) * n_gpus,
+           "d2h_bytes_per_step": int(d2h) * n_gpus, "ms_per_step": 1e3 * t_e2e / e2e_steps, "steps": e2e_steps,
+           "views_per_s": scene.num_views * e2e_steps / t_e2e,
+           "what": "Line3D.upload (pageable host arrays -> HBM) + matchImages + affinity + edges()/local2global() D2H, per rank"}
 
     if rank != 0:
         if dist is not None:
@@ -308,8 +313,17 @@ def main():
         "peak_nominal": fp32_nominal, "frac_of_nominal": achieved / fp32_nominal,
         "algorithmic_flop_per_test": FLOP_PER_TEST, "tests_per_launch": k1_tests / max(t12["k1_launches"], 1),
         "launch_ms": 1e3 * k1_s / max(t12["k1_launches"], 1), "k1_tests_per_s": k1_tests / k1_s,
-        "hbm_peak_gbs": peaks.get("hbm_gbs"), "traffic": None,
+        # dram__bytes_read.sum + dram__bytes_write.sum of one K1 launch on C2 (ncu --set full,
+        # profiles/r1d_ncu_full_c2.md); the 31 MB bit mask stays in the 126 MB L2
+        "traffic": 2424832 if wname == "c2" else None,
     }
+    n_pairs_local = max(c12["num_pairs_local"], 1)
+    seg_n = scene.views[0].segs.shape[0]
+    k1_bytes = n_pairs_local * (32.0 + 16.0) * seg_n + k1_tests / 8.0 + 4.0 * n_pairs_local * seg_n
+    roofline["hbm"] = {"algorithmic_bytes_per_launch": k1_bytes / max(t12["k1_launches"], 1),
+                       "achieved_gbs": k1_bytes / k1_s / 1e9, "peak_gbs": peaks.get("hbm_gbs"),
+                       "frac": (k1_bytes / k1_s / 1e9) / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None,
+                       "note": "descriptors + segments + 1 bit per test + counts; the kernel is FP32-pipe bound, not HBM bound"}
 
     cpu_baseline = None
     if not args.no_cpu_baseline:
