@@ -113,9 +113,13 @@ def lib():
         L.l3d_get_cluster_ids.argtypes = [vp, vp, u32]
         L.l3d_get_view_info.argtypes = [vp, u32, vp, vp]
         L.l3d_get_med_scene_depth_lines.argtypes = [vp, vp]
-        L.l3d_forward_blob_size.argtypes = [vp, C.POINTER(u64)]
-        L.l3d_export_forward.argtypes = [vp, vp, u64, C.c_int]
-        L.l3d_import_forward.argtypes = [vp, vp, u64, C.c_int, C.c_int]
+        L.l3d_score_build.argtypes = [vp]
+        L.l3d_score_fold.argtypes = [vp]
+        L.l3d_affinity_edges.argtypes = [vp]
+        L.l3d_affinity_ids.argtypes = [vp]
+        L.l3d_shard_blob_size.argtypes = [vp, C.c_int, C.POINTER(u64)]
+        L.l3d_shard_export.argtypes = [vp, C.c_int, vp, u64, C.c_int]
+        L.l3d_shard_import.argtypes = [vp, C.c_int, vp, u64, C.c_int, vp, C.c_int]
         L.l3d_test_expf.argtypes = [vp, vp, vp, u32]
         L.l3d_test_acos.argtypes = [vp, vp, vp, u32]
         L.l3d_bench_fp32_peak.argtypes = [vp, vp]
@@ -385,17 +389,34 @@ class Line3D:
         self._ck(self.L.l3d_get_med_scene_depth_lines(self.h, C.byref(v)))
         return float(v.value)
 
-    # ---- multi-GPU plumbing ----
-    def forward_blob_size(self):
+    # ---- multi-GPU: phases and exchanges of a sharded run (include/l3dpp_b200.h) ----
+    def score_build(self):
+        self._ck(self.L.l3d_score_build(self.h))
+
+    def score_fold(self):
+        self._ck(self.L.l3d_score_fold(self.h))
+
+    def affinity_edges(self):
+        self._ck(self.L.l3d_affinity_edges(self.h))
+
+    def affinity_ids(self):
+        self._ck(self.L.l3d_affinity_ids(self.h))
+
+    def shard_blob_size(self, kind):
         n = C.c_uint64(0)
-        self._ck(self.L.l3d_forward_blob_size(self.h, C.byref(n)))
+        self._ck(self.L.l3d_shard_blob_size(self.h, int(kind), C.byref(n)))
         return int(n.value)
 
-    def export_forward(self, ptr, cap_bytes, device_ptr):
-        self._ck(self.L.l3d_export_forward(self.h, C.c_void_p(ptr), cap_bytes, int(device_ptr)))
+    def shard_export(self, kind, ptr, cap_bytes, device_ptr):
+        self._ck(self.L.l3d_shard_export(self.h, int(kind), C.c_void_p(ptr), cap_bytes, int(device_ptr)))
 
-    def import_forward(self, ptr, stride_bytes, world, device_ptr):
-        self._ck(self.L.l3d_import_forward(self.h, C.c_void_p(ptr), stride_bytes, int(world), int(device_ptr)))
+    def shard_import(self, kind, ptr, stride_bytes, world, sizes, device_ptr):
+        sz = np.ascontiguousarray(sizes, dtype=np.uint64)
+        self._ck(self.L.l3d_shard_import(self.h, int(kind), C.c_void_p(ptr), stride_bytes, int(world), _p(sz),
+                                         int(device_ptr)))
+
+
+X_FORWARD, X_PROGRAMS, X_HYPOTHESES, X_EDGES = 0, 1, 2, 3
 
 
 def cluster_edges(ij, w, n):

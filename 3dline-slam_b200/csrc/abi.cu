@@ -165,82 +165,279 @@ int l3d_score_matches(l3d_ctx* ctx, const float* lines, uint32_t n_lines, const 
 }
 
 // ------------------------------------------------------------------------------------------
-// multi-GPU: forward lists of this shard as one blob:  uint32 cnt[rows_pad] | FwdRec recs[total]
-// (rows_pad = total_rows rounded up to 8 so that the records are 32-byte aligned)
+// multi-GPU: the four exchange points of a sharded run (one process per GPU; the collective itself
+// is torch.distributed / NCCL, see 3dline-slam_b200/sharding.py).  Every rank exports one blob,
+// the blobs are all-gathered `stride` bytes apart, every rank imports all of them.
+//   FORWARD     u32 cnt[rows_pad8] | FwdRec recs[]                       rows = pair rows of the slice
+//   PROGRAMS    u32 nh[rows_pad4] | u32 off[rows_pad4] | uint4 rec[]     rows = segments of the slice
+//   HYPOTHESES  ShardHypHdr | u32 filt_cnt[rows_pad4] | u32 filt_off[rows_pad4] | EntryDev e[rows] | ListRec filt[]
+//   EDGES       {u32 src, u32 tgt, float w}[]
 // ------------------------------------------------------------------------------------------
-static uint64_t rows_pad(const l3d_ctx* ctx) { return ((uint64_t)ctx->total_rows + 7ull) & ~7ull; }
+struct ShardHypHdr {
+    unsigned long long sim_evals, scored;
+    uint32_t filt_n, num_valid, pad0, pad1;
+};
+static_assert(sizeof(ShardHypHdr) == 32, "header must be 32 bytes");
 
-int l3d_forward_blob_size(l3d_ctx* ctx, uint64_t* bytes)
+namespace l3d {
+int launch_hyp_adopt(const void* all, uint64_t stride, int world, const uint32_t* slice_g, const uint32_t* fbase,
+                     uint32_t S, EntryDev* entries, uint32_t* filt_cnt, uint32_t* filt_off, ListRec* filt_all,
+                     cudaStream_t st);
+}
+
+static uint32_t slice_rows(const l3d_ctx* ctx, int kind, int q)
 {
-    if (!ctx || !bytes) return fail(L3D_ERR_ARG, "NULL argument");
-    if (ctx->stage < 1) return fail(L3D_ERR_STATE, "l3d_match_stage12 has not run");
-    *bytes = rows_pad(ctx) * 4 + ctx->total_fwd * sizeof(FwdRec);
+    return kind == L3D_X_FORWARD ? ctx->slice_row[q + 1] - ctx->slice_row[q] : ctx->slice_g[q + 1] - ctx->slice_g[q];
+}
+static uint64_t pad_to(uint64_t x, uint64_t m) { return (x + m - 1) / m * m; }
+
+// fixed part of rank q's blob
+static uint64_t blob_fixed_bytes(const l3d_ctx* ctx, int kind, int q)
+{
+    const uint64_t rows = slice_rows(ctx, kind, q);
+    switch (kind) {
+    case L3D_X_FORWARD: return pad_to(rows, 8) * 4;
+    case L3D_X_PROGRAMS: return 2 * pad_to(rows, 4) * 4;
+    case L3D_X_HYPOTHESES: return sizeof(ShardHypHdr) + 2 * pad_to(rows, 4) * 4 + rows * sizeof(EntryDev);
+    default: return 0;
+    }
+}
+
+static int check_phase(l3d_ctx* ctx, int kind)
+{
+    if (!ctx) return fail(L3D_ERR_ARG, "ctx is NULL");
+    switch (kind) {
+    case L3D_X_FORWARD:
+        if (ctx->stage < 1) return fail(L3D_ERR_STATE, "l3d_match_stage12 has not run");
+        break;
+    case L3D_X_PROGRAMS:
+        if (ctx->stage3_phase < 1) return fail(L3D_ERR_STATE, "l3d_score_build has not run");
+        break;
+    case L3D_X_HYPOTHESES:
+        if (ctx->stage3_phase < 2) return fail(L3D_ERR_STATE, "l3d_score_fold has not run");
+        break;
+    case L3D_X_EDGES:
+        if (ctx->stage4_phase < 1) return fail(L3D_ERR_STATE, "l3d_affinity_edges has not run");
+        break;
+    default: return fail(L3D_ERR_ARG, "unknown exchange kind %d", kind);
+    }
     return L3D_OK;
 }
 
-int l3d_export_forward(l3d_ctx* ctx, void* dst, uint64_t cap_bytes, int device_ptr)
+// variable part of this rank's blob (elements); reads the device cursors, so it synchronises
+static int blob_var_count(l3d_ctx* ctx, int kind, uint64_t* n)
 {
-    if (!ctx || !dst) return fail(L3D_ERR_ARG, "NULL argument");
-    if (ctx->stage < 1) return fail(L3D_ERR_STATE, "l3d_match_stage12 has not run");
-    uint64_t need = 0;
-    l3d_forward_blob_size(ctx, &need);
-    if (cap_bytes < need) return fail(L3D_ERR_CAPACITY, "need %llu bytes", (unsigned long long)need);
+    cudaStream_t st = ctx->stream;
+    switch (kind) {
+    case L3D_X_FORWARD: *n = ctx->local_fwd; return L3D_OK;
+    case L3D_X_EDGES: *n = ctx->n_edges_local; return L3D_OK;
+    case L3D_X_PROGRAMS:
+        for (int attempt = 0;; ++attempt) {
+            uint32_t w[2] = {0, 0};  // WfStats::err, WfStats::prog_cursor
+            CK(cudaMemcpyAsync(w, ctx->d_stats.p + 24, 8, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            if (!(w[0] & 4u)) {
+                *n = w[1];
+                return L3D_OK;
+            }
+            if (attempt >= 8) return fail(L3D_ERR_CAPACITY, "fold program store overflow");
+            int rc = score_rebuild(ctx, w[1]);
+            if (rc) return rc;
+        }
+    case L3D_X_HYPOTHESES: {
+        uint32_t w[2] = {0, 0};  // WfStats::filt_cursor, WfStats::err
+        CK(cudaMemcpyAsync(w, ctx->d_stats.p + 20, 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (w[1] & 2u) return fail(L3D_ERR_CAPACITY, "filtered-match store overflow");
+        if (w[1] & 8u) return fail(L3D_ERR_STATE, "internal: scoring dependency wait timed out");
+        *n = w[0];
+        return L3D_OK;
+    }
+    }
+    return fail(L3D_ERR_ARG, "unknown exchange kind %d", kind);
+}
+
+static uint64_t var_elem_bytes(int kind)
+{
+    switch (kind) {
+    case L3D_X_FORWARD: return sizeof(FwdRec);
+    case L3D_X_PROGRAMS: return 16;
+    case L3D_X_HYPOTHESES: return sizeof(ListRec);
+    default: return 12;
+    }
+}
+
+int l3d_shard_blob_size(l3d_ctx* ctx, int kind, uint64_t* bytes)
+{
+    int rc = check_phase(ctx, kind);
+    if (rc) return rc;
+    if (!bytes) return fail(L3D_ERR_ARG, "NULL argument");
+    CK(cudaSetDevice(ctx->device));
+    uint64_t n = 0;
+    rc = blob_var_count(ctx, kind, &n);
+    if (rc) return rc;
+    ctx->xchg_var[kind] = n;
+    *bytes = blob_fixed_bytes(ctx, kind, ctx->rank) + n * var_elem_bytes(kind);
+    return L3D_OK;
+}
+
+int l3d_shard_export(l3d_ctx* ctx, int kind, void* dst, uint64_t cap_bytes, int device_ptr)
+{
+    int rc = check_phase(ctx, kind);
+    if (rc) return rc;
+    if (!dst) return fail(L3D_ERR_ARG, "NULL argument");
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
-    const cudaMemcpyKind kind = device_ptr ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    const uint64_t n = ctx->xchg_var[kind];
+    const uint64_t need = blob_fixed_bytes(ctx, kind, ctx->rank) + n * var_elem_bytes(kind);
+    if (cap_bytes < need) return fail(L3D_ERR_CAPACITY, "need %llu bytes", (unsigned long long)need);
+    const cudaMemcpyKind ck = device_ptr ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
     unsigned char* d = (unsigned char*)dst;
-    if (device_ptr)
-        CK(cudaMemsetAsync(d, 0, rows_pad(ctx) * 4, st));
-    else
-        memset(d, 0, rows_pad(ctx) * 4);
-    CK(cudaMemcpyAsync(d, ctx->d_fwd_cnt.p, (size_t)ctx->total_rows * 4, kind, st));
-    if (ctx->total_fwd)
-        CK(cudaMemcpyAsync(d + rows_pad(ctx) * 4, ctx->d_fwd_rec.p, ctx->total_fwd * sizeof(FwdRec), kind, st));
-    CK(cudaStreamSynchronize(st));
+    const uint32_t rows = slice_rows(ctx, kind, ctx->rank);
+    switch (kind) {
+    case L3D_X_FORWARD: {
+        const uint32_t r0 = ctx->slice_row[ctx->rank];
+        if (rows) CK(cudaMemcpyAsync(d, ctx->d_fwd_cnt.p + r0, (size_t)rows * 4, ck, st));
+        if (n) CK(cudaMemcpyAsync(d + pad_to(rows, 8) * 4, ctx->d_fwd_rec.p, n * sizeof(FwdRec), ck, st));
+        break;
+    }
+    case L3D_X_PROGRAMS: {
+        const uint32_t g0 = ctx->slice_g[ctx->rank];
+        const uint64_t rp = pad_to(rows, 4);
+        if (rows) {
+            CK(cudaMemcpyAsync(d, ctx->d_prog_nh.p + g0, (size_t)rows * 4, ck, st));
+            CK(cudaMemcpyAsync(d + rp * 4, ctx->d_prog_off.p + g0, (size_t)rows * 4, ck, st));
+        }
+        if (n) CK(cudaMemcpyAsync(d + 2 * rp * 4, ctx->d_prog.p, n * 16, ck, st));
+        break;
+    }
+    case L3D_X_HYPOTHESES: {
+        const uint32_t g0 = ctx->slice_g[ctx->rank];
+        const uint64_t rp = pad_to(rows, 4);
+        // header = the first 32 bytes of WfStats with filt_cursor in the filt_n slot
+        CK(cudaMemcpyAsync(d, ctx->d_stats.p, 16, ck, st));
+        CK(cudaMemcpyAsync(d + 16, ctx->d_stats.p + 20, 4, ck, st));
+        CK(cudaMemcpyAsync(d + 20, ctx->d_stats.p + 16, 4, ck, st));
+        unsigned char* p = d + sizeof(ShardHypHdr);
+        if (rows) {
+            CK(cudaMemcpyAsync(p, ctx->d_filt_cnt.p + g0, (size_t)rows * 4, ck, st));
+            CK(cudaMemcpyAsync(p + rp * 4, ctx->d_filt_off.p + g0, (size_t)rows * 4, ck, st));
+            CK(cudaMemcpyAsync(p + 2 * rp * 4, ctx->d_entries.p + g0, (size_t)rows * sizeof(EntryDev), ck, st));
+        }
+        if (n) CK(cudaMemcpyAsync(p + 2 * rp * 4 + (size_t)rows * sizeof(EntryDev), ctx->d_filt_rec.p, n * sizeof(ListRec), ck, st));
+        break;
+    }
+    case L3D_X_EDGES:
+        if (n) CK(cudaMemcpyAsync(d, ctx->d_edges.p, n * 12, ck, st));
+        break;
+    }
+    if (!device_ptr) CK(cudaStreamSynchronize(st));
     return L3D_OK;
 }
 
-// blobs: `world` blobs of `stride_bytes` each (the all-gathered exports, own shard included)
-int l3d_import_forward(l3d_ctx* ctx, const void* blobs, uint64_t stride_bytes, int world, int device_ptr)
+// all: `world` blobs `stride_bytes` apart (own blob included); sizes[q] = l3d_shard_blob_size of rank q.
+// Device pointers must stay valid until the next exchange of the same kind (PROGRAMS is read in place).
+int l3d_shard_import(l3d_ctx* ctx, int kind, const void* all, uint64_t stride_bytes, int world, const uint64_t* sizes,
+                     int device_ptr)
 {
-    if (!ctx || !blobs || world < 1) return fail(L3D_ERR_ARG, "bad argument");
-    if (ctx->stage < 1) return fail(L3D_ERR_STATE, "l3d_match_stage12 has not run");
+    int rc = check_phase(ctx, kind);
+    if (rc) return rc;
+    if (!all || !sizes) return fail(L3D_ERR_ARG, "NULL argument");
+    if (world != ctx->world) return fail(L3D_ERR_ARG, "world %d does not match the plan (%d)", world, ctx->world);
     if (stride_bytes % 32) return fail(L3D_ERR_ARG, "stride must be a multiple of 32 bytes");
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
-    const uint32_t R = ctx->total_rows;
-    DevBuf<unsigned char> stage;
-    const uint32_t* dblobs = (const uint32_t*)blobs;
-    if (!device_ptr) {
-        CK(stage.ensure(stride_bytes * world));
-        CK(cudaMemcpyAsync(stage.p, blobs, stride_bytes * world, cudaMemcpyHostToDevice, st));
-        dblobs = (const uint32_t*)stage.p;
+    const unsigned char* src = (const unsigned char*)all;
+    if (!device_ptr) {  // host blobs (tests): stage them on the device, one buffer per kind
+        DevBuf<unsigned char>& stg = ctx->d_xchg_stage[kind];
+        CK(stg.ensure(stride_bytes * world));
+        CK(cudaMemcpyAsync(stg.p, all, stride_bytes * world, cudaMemcpyHostToDevice, st));
+        src = stg.p;
     }
-    const uint64_t stride_words = stride_bytes / 4;
-    // per-shard exclusive scans (source offsets) and the merged counts / offsets
-    DevBuf<uint32_t> shard_off;
-    CK(shard_off.ensure((size_t)world * (R + 1)));
-    CK(ctx->d_scan.ensure(scan_scratch_words(R + 1) + 64));
-    for (int w = 0; w < world; ++w)
-        ctx->cnt.gpu_launches += launch_scan_u32(dblobs + (size_t)w * stride_words, shard_off.p + (size_t)w * (R + 1),
-                                                 R, ctx->d_scan.p, ctx->d_scan.cap, st);
-    ctx->cnt.gpu_launches += launch_fwd_merge_cnt(dblobs, stride_words, world, R, ctx->d_fwd_cnt.p, st);
-    DevBuf<uint32_t> new_off;
-    CK(new_off.ensure((size_t)R + 2));
-    ctx->cnt.gpu_launches += launch_scan_u32(ctx->d_fwd_cnt.p, new_off.p, R, ctx->d_scan.p, ctx->d_scan.cap, st);
-    uint32_t total = 0;
-    CK(cudaMemcpyAsync(&total, new_off.p + R, 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    // the merged records go to a fresh buffer (the own shard is one of the sources)
-    DevBuf<FwdRec> merged;
-    CK(merged.ensure((size_t)total + 1));
-    ctx->cnt.gpu_launches +=
-        launch_fwd_merge_copy(dblobs, stride_words, world, R, shard_off.p, new_off.p, merged.p, st);
-    CK(cudaMemcpyAsync(ctx->d_fwd_off.p, new_off.p, ((size_t)R + 1) * 4, cudaMemcpyDeviceToDevice, st));
-    CK(cudaStreamSynchronize(st));
-    std::swap(ctx->d_fwd_rec.p, merged.p);
-    std::swap(ctx->d_fwd_rec.cap, merged.cap);
-    ctx->total_fwd = total;
-    ctx->cnt.forward_matches = total;
-    return refresh_pair_totals(ctx);
+    std::vector<uint64_t> nvar(world);
+    for (int q = 0; q < world; ++q) {
+        const uint64_t fx = blob_fixed_bytes(ctx, kind, q);
+        if (sizes[q] < fx || sizes[q] > stride_bytes || (sizes[q] - fx) % var_elem_bytes(kind))
+            return fail(L3D_ERR_ARG, "blob %d has an impossible size (%llu bytes)", q, (unsigned long long)sizes[q]);
+        nvar[q] = (sizes[q] - fx) / var_elem_bytes(kind);
+    }
+    const uint32_t S = ctx->S;
+    switch (kind) {
+    case L3D_X_FORWARD: {
+        uint64_t total = 0;
+        for (int q = 0; q < world; ++q) total += nvar[q];
+        if (total > 0xfffffff0ull) return fail(L3D_ERR_CAPACITY, "too many forward matches");
+        // slices are contiguous in pair rows and in rank order: the merged tables are concatenations
+        CK(ctx->d_fwd_alt.ensure((size_t)total + 1));
+        uint64_t at = 0;
+        for (int q = 0; q < world; ++q) {
+            const uint32_t rows = slice_rows(ctx, kind, q);
+            const unsigned char* b = src + (uint64_t)q * stride_bytes;
+            if (rows)
+                CK(cudaMemcpyAsync(ctx->d_fwd_cnt.p + ctx->slice_row[q], b, (size_t)rows * 4, cudaMemcpyDeviceToDevice, st));
+            if (nvar[q])
+                CK(cudaMemcpyAsync(ctx->d_fwd_alt.p + at, b + pad_to(rows, 8) * 4, nvar[q] * sizeof(FwdRec),
+                                   cudaMemcpyDeviceToDevice, st));
+            at += nvar[q];
+        }
+        std::swap(ctx->d_fwd_rec.p, ctx->d_fwd_alt.p);
+        std::swap(ctx->d_fwd_rec.cap, ctx->d_fwd_alt.cap);
+        CK(ctx->d_scan.ensure(scan_scratch_words(ctx->total_rows + 1) + 64));
+        ctx->cnt.gpu_launches += launch_scan_u32(ctx->d_fwd_cnt.p, ctx->d_fwd_off.p, ctx->total_rows, ctx->d_scan.p,
+                                                 ctx->d_scan.cap, st);
+        ctx->total_fwd = total;
+        ctx->cnt.forward_matches = total;
+        return refresh_pair_totals(ctx);
+    }
+    case L3D_X_PROGRAMS: {
+        CK(ctx->d_slice_g.ensure(L3D_MAX_WORLD + 1));
+        CK(cudaMemcpyAsync(ctx->d_slice_g.p, ctx->slice_g.data(), ((size_t)world + 1) * 4, cudaMemcpyHostToDevice, st));
+        if (stride_bytes * (uint64_t)world / 16 > 0xfffffff0ull) return fail(L3D_ERR_CAPACITY, "fold programs too large");
+        ctx->cnt.gpu_launches += launch_k3_adopt_programs(src, stride_bytes, world, ctx->d_slice_g.p, S,
+                                                          ctx->d_prog_off.p, ctx->d_prog_nh.p, ctx->d_fwd_rec.p, st);
+        ctx->prog_all = src;
+        return L3D_OK;
+    }
+    case L3D_X_HYPOTHESES: {
+        std::vector<uint32_t> fbase(world + 1, 0);
+        for (int q = 0; q < world; ++q) fbase[q + 1] = fbase[q] + (uint32_t)nvar[q];
+        CK(ctx->d_slice_g.ensure(2 * (L3D_MAX_WORLD + 1)));
+        CK(cudaMemcpyAsync(ctx->d_slice_g.p, ctx->slice_g.data(), ((size_t)world + 1) * 4, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ctx->d_slice_g.p + L3D_MAX_WORLD + 1, fbase.data(), ((size_t)world + 1) * 4,
+                           cudaMemcpyHostToDevice, st));
+        CK(ctx->d_filt_all.ensure((size_t)fbase[world] + 1));
+        ctx->cnt.gpu_launches += launch_hyp_adopt(src, stride_bytes, world, ctx->d_slice_g.p,
+                                                  ctx->d_slice_g.p + L3D_MAX_WORLD + 1, S, ctx->d_entries.p,
+                                                  ctx->d_filt_cnt.p, ctx->d_filt_off.p, ctx->d_filt_all.p, st);
+        ctx->filt_all = ctx->d_filt_all.p;
+        std::vector<ShardHypHdr> hdr(world);
+        for (int q = 0; q < world; ++q)
+            CK(cudaMemcpyAsync(&hdr[q], src + (uint64_t)q * stride_bytes, sizeof(ShardHypHdr), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        ctx->shard_sim_evals = ctx->shard_scored = ctx->shard_filtered = 0;
+        for (int q = 0; q < world; ++q) {
+            ctx->shard_sim_evals += hdr[q].sim_evals;
+            ctx->shard_scored += hdr[q].scored;
+            ctx->shard_filtered += hdr[q].filt_n;
+        }
+        return score_hypotheses_ready(ctx, nullptr, nullptr);
+    }
+    case L3D_X_EDGES: {
+        uint64_t total = 0;
+        for (int q = 0; q < world; ++q) total += nvar[q];
+        if (total > 0x7ffffff0ull) return fail(L3D_ERR_CAPACITY, "too many edges");
+        CK(ctx->d_edges_all.ensure(total * 12 + 16));
+        uint64_t at = 0;
+        for (int q = 0; q < world; ++q) {
+            if (nvar[q])
+                CK(cudaMemcpyAsync(ctx->d_edges_all.p + at * 12, src + (uint64_t)q * stride_bytes, nvar[q] * 12,
+                                   cudaMemcpyDeviceToDevice, st));
+            at += nvar[q];
+        }
+        ctx->edges_all = ctx->d_edges_all.p;
+        ctx->n_edges_all = (uint32_t)total;
+        return L3D_OK;
+    }
+    }
+    return fail(L3D_ERR_ARG, "unknown exchange kind %d", kind);
 }

@@ -256,21 +256,38 @@ int plan_pairs(l3d_ctx* ctx)
     const int world = prm.shard_world > 1 ? prm.shard_world : 1;
     const int rank = world > 1 ? prm.shard_rank : 0;
     ctx->pairs_h.assign(P, PairDev{});
-    // shard = a contiguous block of pairs (pairs are ordered by source view, so a block is a slice of
-    // reference views), balanced by the number of segment-pair tests
-    std::vector<uint64_t> cum(P + 1, 0);
+    // shard = a contiguous slice of reference (source) views, balanced by the number of segment-pair
+    // tests of the pairs they own; pairs are ordered by source view, so a slice owns a contiguous
+    // block of pairs, of pair rows and of segments
+    if (world > L3D_MAX_WORLD) return fail(L3D_ERR_ARG, "at most %d shards", L3D_MAX_WORLD);
+    std::vector<uint64_t> vtests(V + 1, 0);
     for (uint32_t p = 0; p < P; ++p)
-        cum[p + 1] = cum[p] + (uint64_t)ctx->views[ctx->pairs[p].src].v.num_segs *
-                                  ctx->views[ctx->pairs[p].tgt].v.num_segs;
-    const uint64_t total_tests = cum[P];
+        vtests[ctx->pairs[p].src + 1] += (uint64_t)ctx->views[ctx->pairs[p].src].v.num_segs *
+                                         ctx->views[ctx->pairs[p].tgt].v.num_segs;
+    for (uint32_t v = 0; v < V; ++v) vtests[v + 1] += vtests[v];
+    const uint64_t total_tests = vtests[V];
+    ctx->world = world;
+    ctx->rank = rank;
+    ctx->slice_view.assign(world + 1, V);
+    ctx->slice_view[0] = 0;
+    for (int q = 1; q < world; ++q) {
+        const uint64_t want = total_tests / (uint64_t)world * (uint64_t)q;
+        uint32_t v = ctx->slice_view[q - 1];
+        // first view whose cumulative test count (up to its middle) passes the q-th share
+        while (v < V && vtests[v] + (vtests[v + 1] - vtests[v]) / 2 < want) ++v;
+        ctx->slice_view[q] = v;
+    }
+    auto owner_of = [&](uint32_t v) {
+        int q = 0;
+        while (q + 1 < world && ctx->slice_view[q + 1] <= v) ++q;
+        return q;
+    };
     uint64_t row = 0, trow = 0;
     ctx->cnt.pair_tests = 0;
     ctx->cnt.num_pairs_local = 0;
     for (uint32_t p = 0; p < P; ++p) {
         HostPair& hp = ctx->pairs[p];
-        const uint64_t mid = cum[p] + (cum[p + 1] - cum[p]) / 2;
-        const int owner = total_tests ? (int)std::min<uint64_t>((uint64_t)world - 1, mid * (uint64_t)world / total_tests) : 0;
-        hp.local = (owner == rank);
+        hp.local = (owner_of(hp.src) == rank);
         const HostView& vs = ctx->views[hp.src];
         const HostView& vt = ctx->views[hp.tgt];
         PairDev& d = ctx->pairs_h[p];
@@ -301,6 +318,20 @@ int plan_pairs(l3d_ctx* ctx)
         return fail(L3D_ERR_CAPACITY, "row index space exhausted (%llu rows)", (unsigned long long)row);
     ctx->total_rows = (uint32_t)row;
     ctx->total_tgt_rows = (uint32_t)trow;
+    // slice boundaries in segments and in pair rows
+    ctx->slice_g.assign(world + 1, ctx->S);
+    ctx->slice_row.assign(world + 1, ctx->total_rows);
+    for (int q = 0; q <= world; ++q) {
+        const uint32_t v = ctx->slice_view[q];
+        ctx->slice_g[q] = v < V ? ctx->views[v].seg_off : ctx->S;
+        uint32_t r = ctx->total_rows;
+        for (uint32_t p = 0; p < P; ++p)
+            if (ctx->pairs[p].src >= v) {
+                r = ctx->pairs_h[p].row_base;
+                break;
+            }
+        ctx->slice_row[q] = r;
+    }
 
     // batches over local pairs: bounded bit-mask size
     const uint64_t max_words = 1ull << 27;  // 512 MB of mask
@@ -489,6 +520,11 @@ int l3d_match_stage12(l3d_ctx* ctx, const l3d_params* params)
         rec_base += n_fin;
     }
     ctx->total_fwd = rec_base;
+    ctx->local_fwd = rec_base;
+    ctx->prog_all = nullptr;
+    ctx->filt_all = nullptr;
+    ctx->edges_all = nullptr;
+    ctx->stage3_phase = ctx->stage4_phase = 0;
 
     rc = refresh_pair_totals(ctx);
     if (rc) return rc;
@@ -503,23 +539,55 @@ int l3d_match_stage12(l3d_ctx* ctx, const l3d_params* params)
 // ------------------------------------------------------------------------------------------
 // stage 3: scoring wavefront
 // ------------------------------------------------------------------------------------------
-int l3d_match_stage3(l3d_ctx* ctx)
+// stage 3: scoring (k3_dataflow.cu) in three phases: build (rows of this rank's view slice),
+// fold (all rows, replicated), finish (rows of the slice).  With one rank the phases run back to
+// back; with several the fold programs are exchanged between build and fold, and the hypotheses
+// between finish and the affinity stage (abi.cu: l3d_shard_export / l3d_shard_import).
+// ------------------------------------------------------------------------------------------
+static K3Tables k3_tables(l3d_ctx* ctx)
+{
+    K3Tables t;
+    t.views = ctx->d_views.p; t.seg_view = ctx->d_seg_view.p; t.pairs = ctx->d_pairs.p; t.inc = ctx->d_inc.p;
+    t.inc_off = ctx->d_inc_off.p; t.rays = ctx->d_rays.p; t.fwd_off = ctx->d_fwd_off.p; t.fwd_cnt = ctx->d_fwd_cnt.p;
+    t.fwd_rec = ctx->d_fwd_rec.p; t.fwd_row = ctx->d_fwd_row.p; t.G_fwd = ctx->d_G_fwd.p; t.G_inv = ctx->d_G_inv.p;
+    t.inv_off = ctx->d_inv_off.p; t.inv_fill = ctx->d_inv_fill.p; t.inv_ent = ctx->d_inv_ent.p;
+    t.L_off = ctx->d_L_off.p; t.L_f = ctx->d_L_f.p; t.L_meta = ctx->d_L_meta.p; t.L_score = ctx->d_L_score.p;
+    const bool big = ctx->k3_big_rows;
+    t.L_sib = big ? ctx->d_L_sib.p : nullptr; t.L_dir = big ? ctx->d_L_dir.p : nullptr;
+    t.L_reg = big ? ctx->d_L_reg.p : nullptr; t.L_c = big ? ctx->d_L_c.p : nullptr; t.L_h = big ? ctx->d_L_h.p : nullptr;
+    t.prog_off = ctx->d_prog_off.p; t.prog_nh = ctx->d_prog_nh.p;
+    t.prog = ctx->prog_all ? const_cast<void*>(ctx->prog_all) : (void*)ctx->d_prog.p;
+    t.prog_cap = (uint32_t)ctx->prog_cap;
+    t.L_cnt = ctx->d_L_cnt.p; t.L_rec = ctx->prm.keep_scored ? ctx->d_L_rec.p : nullptr;
+    t.view_max = ctx->d_view_max.p; t.filt_rec = ctx->d_filt_rec.p; t.filt_cap = (uint32_t)ctx->filt_cap;
+    t.filt_off = ctx->d_filt_off.p; t.filt_cnt = ctx->d_filt_cnt.p; t.entries = ctx->d_entries.p;
+    t.stats = ctx->d_stats.p; t.S = ctx->S; t.maxm = ctx->k3_maxm; t.two_sigA_sqr = ctx->two_sigA_sqr;
+    t.g_lo = ctx->slice_g[ctx->rank]; t.g_hi = ctx->slice_g[ctx->rank + 1];
+    return t;
+}
+
+static int launch_records(l3d_ctx* ctx)
+{
+    return launch_k3_records(ctx->d_pairs.p, (uint32_t)ctx->pairs.size(), (uint32_t)ctx->total_fwd, ctx->d_views.p,
+                             ctx->d_rays.p, ctx->d_fwd_row.p, ctx->d_fwd_rec.p, ctx->d_G_fwd.p, ctx->d_G_inv.p,
+                             ctx->d_inv_off.p, ctx->d_inv_fill.p, ctx->d_inv_ent.p, ctx->slice_view[ctx->rank],
+                             ctx->slice_view[ctx->rank + 1], ctx->stream);
+}
+
+// pre-pass + build
+int l3d_score_build(l3d_ctx* ctx)
 {
     if (!ctx) return fail(L3D_ERR_ARG, "ctx is NULL");
     if (ctx->stage < 1) return fail(L3D_ERR_STATE, "l3d_match_stage12 has not run");
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     const uint32_t V = (uint32_t)ctx->views.size(), P = (uint32_t)ctx->pairs.size(), S = ctx->S;
-    uint32_t max_inc = 0;
-    for (uint32_t v = 0; v < V; ++v) {
-        const uint32_t n = ctx->inc_off_h[v + 1] - ctx->inc_off_h[v];
-        if (n > (uint32_t)k3_wf_max_inc())
+    for (uint32_t v = 0; v < V; ++v)
+        if (ctx->inc_off_h[v + 1] - ctx->inc_off_h[v] > (uint32_t)k3_wf_max_inc())
             return fail(L3D_ERR_CAPACITY, "view %u takes part in more than %d matched pairs", ctx->views[v].v.cam_id,
                         k3_wf_max_inc());
-        max_inc = std::max(max_inc, n);
-    }
-
-    cudaEvent_t ev_total = ctx->tm.begin(L3D_T_TOTAL, st);
+    ctx->prog_all = nullptr;
+    ctx->ev_total3 = ctx->tm.begin(L3D_T_TOTAL, st);
     cudaEvent_t ev = ctx->tm.begin(L3D_T_SCORE, st);
     const size_t F = (size_t)ctx->total_fwd;
     const size_t TR = (size_t)ctx->total_tgt_rows;
@@ -551,10 +619,7 @@ int l3d_match_stage3(l3d_ctx* ctx)
                                                     ctx->d_inv_cap.p, st);
     ctx->cnt.gpu_launches +=
         launch_scan_u32(ctx->d_inv_cap.p, ctx->d_inv_off.p, (uint32_t)TR, ctx->d_scan.p, ctx->d_scan.cap, st);
-    ctx->cnt.gpu_launches +=
-        launch_k3_records(ctx->d_pairs.p, P, (uint32_t)F, ctx->d_views.p, ctx->d_rays.p, ctx->d_fwd_row.p,
-                          ctx->d_fwd_rec.p, ctx->d_G_fwd.p, ctx->d_G_inv.p, ctx->d_inv_off.p, ctx->d_inv_fill.p,
-                          ctx->d_inv_ent.p, st);
+    ctx->cnt.gpu_launches += launch_records(ctx);
     ctx->cnt.gpu_launches +=
         launch_k3_list_capacity(ctx->d_views.p, ctx->d_seg_view.p, S, ctx->d_inc.p, ctx->d_inc_off.p, ctx->d_pairs.p,
                                 ctx->d_fwd_cnt.p, ctx->d_inv_cap.p, ctx->d_L_ub.p, ctx->d_stats.p, st);
@@ -574,6 +639,7 @@ int l3d_match_stage3(l3d_ctx* ctx)
         ctx->L_base_h[v] = Lcap;  // == L_off[first segment of v]
         Lcap += cap[v];
     }
+    ctx->L_total = Lcap;
     if (Lcap > 0xfffffff0ull || 2 * F > 0xfffffff0ull) return fail(L3D_ERR_CAPACITY, "match lists too large");
     CK(ctx->d_L_f.ensure(Lcap + 1));
     CK(ctx->d_L_meta.ensure(Lcap + 1));
@@ -602,8 +668,10 @@ int l3d_match_stage3(l3d_ctx* ctx)
         CK(ctx->d_L_c.ensure(Lcap + S + 2));
         CK(ctx->d_L_h.ensure(Lcap + S + 2));
     }
-    const size_t filt_cap = 2 * F + 1;
-    CK(ctx->d_filt_rec.ensure(filt_cap));
+    ctx->k3_maxm = maxm;
+    ctx->k3_big_rows = big_rows;
+    ctx->filt_cap = 2 * F + 1;
+    CK(ctx->d_filt_rec.ensure(ctx->filt_cap));
     CK(ctx->d_filt_off.ensure((size_t)S + 1));
     CK(ctx->d_filt_cnt.ensure((size_t)S + 1));
     CK(ctx->d_view_max.ensure((size_t)V + 1));
@@ -613,72 +681,107 @@ int l3d_match_stage3(l3d_ctx* ctx)
     CK(ctx->d_entries.ensure((size_t)S + 1));
     CK(ctx->d_prog_off.ensure((size_t)S + 1));
     CK(ctx->d_prog_nh.ensure((size_t)S + 1));
-    if (ctx->prog_cap == 0) ctx->prog_cap = std::max<uint64_t>(24ull * S + 1024, 4096);
+    const uint32_t my_rows = ctx->slice_g[ctx->rank + 1] - ctx->slice_g[ctx->rank];
+    if (ctx->prog_cap == 0) ctx->prog_cap = std::max<uint64_t>(24ull * my_rows + 1024, 4096);
+    if (ctx->prog_cap > 0xfffffff0ull) return fail(L3D_ERR_CAPACITY, "fold programs too large");
+    CK(ctx->d_prog.ensure(ctx->prog_cap * 16));
+    int cuerr = 0;
+    const int nl = launch_k3_build(k3_tables(ctx), st, &cuerr);
+    if (nl < 0) return fail(L3D_ERR_CUDA, "launch of the build kernel failed: %s", cudaGetErrorString((cudaError_t)cuerr));
+    ctx->cnt.gpu_launches += nl;
+    ctx->tm.end(ev, st);
+    ctx->stage3_phase = 1;
+    return L3D_OK;
+}
 
+// the fold programs did not fit: grow the store and build again (the record kernel resets the
+// scores and inverse slots the aborted pass left behind)
+int score_rebuild(l3d_ctx* ctx, uint32_t needed_units)
+{
+    cudaStream_t st = ctx->stream;
+    const uint32_t V = (uint32_t)ctx->views.size();
+    ctx->prog_cap = std::max<uint64_t>(2 * ctx->prog_cap, (uint64_t)needed_units + 1024);
+    if (ctx->prog_cap > 0xfffffff0ull) return fail(L3D_ERR_CAPACITY, "fold programs too large");
+    CK(ctx->d_prog.ensure(ctx->prog_cap * 16));
+    cudaEvent_t ev = ctx->tm.begin(L3D_T_SCORE, st);
+    CK(cudaMemsetAsync(ctx->d_stats.p, 0, k3_wf_stats_bytes(), st));
+    CK(cudaMemsetAsync(ctx->d_inv_fill.p, 0, ((size_t)ctx->total_tgt_rows + 1) * 4, st));
+    CK(cudaMemsetAsync(ctx->d_L_score.p, 0, (ctx->L_total + 1) * 4, st));
+    CK(cudaMemsetAsync(ctx->d_view_max.p, 0, ((size_t)V + 1) * 4, st));
+    CK(cudaMemsetAsync(ctx->d_small.p, 0, 16 * 4, st));
+    ctx->prog_all = nullptr;
+    ctx->cnt.gpu_launches += launch_records(ctx);
+    int cuerr = 0;
+    const int nl = launch_k3_build(k3_tables(ctx), st, &cuerr);
+    if (nl < 0) return fail(L3D_ERR_CUDA, "launch of the build kernel failed: %s", cudaGetErrorString((cudaError_t)cuerr));
+    ctx->cnt.gpu_launches += nl;
+    ctx->tm.end(ev, st);
+    return L3D_OK;
+}
+
+// fold (all rows) + finish (rows of the slice)
+int l3d_score_fold(l3d_ctx* ctx)
+{
+    if (!ctx) return fail(L3D_ERR_ARG, "ctx is NULL");
+    if (ctx->stage < 1 || ctx->stage3_phase < 1) return fail(L3D_ERR_STATE, "l3d_score_build has not run");
+    if (ctx->world > 1 && !ctx->prog_all) return fail(L3D_ERR_STATE, "the fold programs have not been exchanged");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    cudaEvent_t ev = ctx->tm.begin(L3D_T_SCORE, st);
+    int cuerr = 0;
+    const K3Tables t = k3_tables(ctx);
+    int nl = launch_k3_fold(t, st, &cuerr);
+    if (nl < 0) return fail(L3D_ERR_CUDA, "launch of the fold kernel failed: %s", cudaGetErrorString((cudaError_t)cuerr));
+    ctx->cnt.gpu_launches += nl;
+    ctx->cnt.gpu_launches += launch_k3_finish(t, st);
+    ctx->tm.end(ev, st);
+    ctx->stage3_phase = 2;
+    return L3D_OK;
+}
+
+// hypothesis index, per-view median depths, counters: needs the hypotheses of every view
+int score_hypotheses_ready(l3d_ctx* ctx, bool* prog_overflow, uint32_t* prog_needed)
+{
+    cudaStream_t st = ctx->stream;
+    const uint32_t V = (uint32_t)ctx->views.size(), S = ctx->S;
+    cudaEvent_t ev = ctx->tm.begin(L3D_T_SCORE, st);
+    // estimated_position3D_ index (canonical order = global segment order) and median depths
+    CK(ctx->d_has.ensure((size_t)S + 1));
+    CK(ctx->d_entry_idx.ensure((size_t)S + 2));
+    ctx->cnt.gpu_launches += launch_k4_has(ctx->d_entries.p, S, ctx->d_has.p, st);
+    ctx->cnt.gpu_launches += launch_scan_u32(ctx->d_has.p, ctx->d_entry_idx.p, S, ctx->d_scan.p, ctx->d_scan.cap, st);
+    ctx->cnt.gpu_launches += launch_k4_median(ctx->d_views.p, V, ctx->d_entries.p, ctx->d_small.p + 2, st);
     uint32_t small[4] = {0, 0, 0, 0};
     uint32_t n_entries = 0;
     std::vector<unsigned char> acc(k3_wf_stats_bytes());
     std::vector<ViewDev> vd(V);
-    for (int attempt = 0;; ++attempt) {
-        if (ctx->prog_cap > 0xfffffff0ull) return fail(L3D_ERR_CAPACITY, "fold programs too large");
-        CK(ctx->d_prog.ensure(ctx->prog_cap * 16));
-        int cuerr = 0;
-        const int nl = launch_k3_dataflow(
-            ctx->d_views.p, ctx->d_seg_view.p, ctx->d_pairs.p, ctx->d_inc.p, ctx->d_inc_off.p, ctx->d_rays.p,
-            ctx->d_fwd_off.p, ctx->d_fwd_cnt.p, ctx->d_fwd_rec.p, ctx->d_fwd_row.p, ctx->d_G_fwd.p, ctx->d_G_inv.p,
-            ctx->d_inv_off.p, ctx->d_inv_fill.p, ctx->d_inv_ent.p, ctx->d_L_off.p, ctx->d_L_f.p, ctx->d_L_meta.p,
-            ctx->d_L_score.p, big_rows ? ctx->d_L_sib.p : nullptr, big_rows ? ctx->d_L_dir.p : nullptr,
-            big_rows ? ctx->d_L_reg.p : nullptr, big_rows ? ctx->d_L_c.p : nullptr, big_rows ? ctx->d_L_h.p : nullptr,
-            ctx->d_prog_off.p, ctx->d_prog_nh.p, ctx->d_prog.p, (uint32_t)ctx->prog_cap, ctx->d_L_cnt.p,
-            keep ? ctx->d_L_rec.p : nullptr, ctx->d_view_max.p, ctx->d_filt_rec.p, (uint32_t)filt_cap,
-            ctx->d_filt_off.p, ctx->d_filt_cnt.p, ctx->d_entries.p, ctx->d_stats.p, S, maxm, ctx->two_sigA_sqr, st,
-            &cuerr);
-        if (nl < 0)
-            return fail(L3D_ERR_CUDA, "launch of the scoring kernels failed: %s", cudaGetErrorString((cudaError_t)cuerr));
-        ctx->cnt.gpu_launches += nl;
-
-        // estimated_position3D_ index (canonical order = global segment order) and median depths
-        CK(ctx->d_has.ensure((size_t)S + 1));
-        CK(ctx->d_entry_idx.ensure((size_t)S + 2));
-        ctx->cnt.gpu_launches += launch_k4_has(ctx->d_entries.p, S, ctx->d_has.p, st);
-        ctx->cnt.gpu_launches +=
-            launch_scan_u32(ctx->d_has.p, ctx->d_entry_idx.p, S, ctx->d_scan.p, ctx->d_scan.cap, st);
-        ctx->cnt.gpu_launches += launch_k4_median(ctx->d_views.p, V, ctx->d_entries.p, ctx->d_small.p + 2, st);
-        CK(cudaMemcpyAsync(small, ctx->d_small.p, sizeof(small), cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(&n_entries, ctx->d_entry_idx.p + S, 4, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(acc.data(), ctx->d_stats.p, acc.size(), cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(vd.data(), ctx->d_views.p, V * sizeof(ViewDev), cudaMemcpyDeviceToHost, st));
-        if (attempt == 0) {
-            ctx->tm.end(ev, st);
-            ctx->tm.end(ev_total, st);
-        }
-        CK(cudaStreamSynchronize(st));
-        const uint32_t* a32 = (const uint32_t*)(acc.data() + 16);
-        if (!(a32[2] & 4u)) break;
-        // the fold programs did not fit: grow the store and run the scoring kernels again
-        // (the record kernel resets the scores the aborted pass may have left behind)
-        if (attempt >= 8) return fail(L3D_ERR_CAPACITY, "fold program store overflow");
-        ctx->prog_cap = std::max<uint64_t>(2 * ctx->prog_cap, (uint64_t)a32[3] + 1024);
-        CK(cudaMemsetAsync(ctx->d_stats.p, 0, k3_wf_stats_bytes(), st));
-        CK(cudaMemsetAsync(ctx->d_inv_fill.p, 0, (TR + 1) * 4, st));
-        CK(cudaMemsetAsync(ctx->d_L_score.p, 0, (Lcap + 1) * 4, st));
-        CK(cudaMemsetAsync(ctx->d_view_max.p, 0, ((size_t)V + 1) * 4, st));
-        CK(cudaMemsetAsync(ctx->d_small.p, 0, 16 * 4, st));
-        ctx->cnt.gpu_launches +=
-            launch_k3_records(ctx->d_pairs.p, P, (uint32_t)F, ctx->d_views.p, ctx->d_rays.p, ctx->d_fwd_row.p,
-                              ctx->d_fwd_rec.p, ctx->d_G_fwd.p, ctx->d_G_inv.p, ctx->d_inv_off.p, ctx->d_inv_fill.p,
-                              ctx->d_inv_ent.p, st);
+    CK(cudaMemcpyAsync(small, ctx->d_small.p, sizeof(small), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&n_entries, ctx->d_entry_idx.p + S, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(acc.data(), ctx->d_stats.p, acc.size(), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(vd.data(), ctx->d_views.p, V * sizeof(ViewDev), cudaMemcpyDeviceToHost, st));
+    ctx->tm.end(ev, st);
+    if (ctx->ev_total3) ctx->tm.end(ctx->ev_total3, st);
+    ctx->ev_total3 = nullptr;
+    CK(cudaStreamSynchronize(st));
+    const unsigned long long* a64 = (const unsigned long long*)acc.data();
+    const uint32_t* a32 = (const uint32_t*)(acc.data() + 16);
+    if (prog_overflow) {
+        *prog_overflow = (a32[2] & 4u) != 0;
+        *prog_needed = a32[3];
+        if (*prog_overflow) return L3D_OK;
     }
     ctx->tm.collect();
-    {
-        const unsigned long long* a64 = (const unsigned long long*)acc.data();
-        const uint32_t* a32 = (const uint32_t*)(acc.data() + 16);
+    if (ctx->world > 1) {  // the slices' counters were summed when the hypotheses were imported
+        ctx->cnt.sim_evals = ctx->shard_sim_evals;
+        ctx->cnt.scored_entries = ctx->shard_scored;
+        ctx->cnt.filtered_entries = ctx->shard_filtered;
+    } else {
         ctx->cnt.sim_evals = a64[0];
         ctx->cnt.scored_entries = a64[1];
         ctx->cnt.filtered_entries = a32[1];  // filt_cursor
-        if (a32[2] & 2u) return fail(L3D_ERR_CAPACITY, "filtered-match store overflow");
-        if (a32[2] & 8u) return fail(L3D_ERR_STATE, "internal: scoring dependency wait timed out");
     }
+    if (a32[2] & 2u) return fail(L3D_ERR_CAPACITY, "filtered-match store overflow");
+    if (a32[2] & 8u) return fail(L3D_ERR_STATE, "internal: scoring dependency wait timed out");
     if (small[2]) return fail(L3D_ERR_CAPACITY, "more than 8192 hypotheses in one view (median-depth kernel)");
     ctx->cnt.num_entries = n_entries;
     for (uint32_t v = 0; v < V; ++v) {
@@ -692,7 +795,29 @@ int l3d_match_stage3(l3d_ctx* ctx)
         for (auto& hv : ctx->views) hv.cam.translate(tv);  // untranslate()
     }
     ctx->stage = 2;
+    ctx->stage3_phase = 3;
     return L3D_OK;
+}
+
+int l3d_match_stage3(l3d_ctx* ctx)
+{
+    if (!ctx) return fail(L3D_ERR_ARG, "ctx is NULL");
+    if (ctx->world > 1)
+        return fail(L3D_ERR_STATE, "sharded run: use l3d_score_build / l3d_shard_* / l3d_score_fold");
+    int rc = l3d_score_build(ctx);
+    if (rc) return rc;
+    for (int attempt = 0;; ++attempt) {
+        rc = l3d_score_fold(ctx);
+        if (rc) return rc;
+        bool overflow = false;
+        uint32_t needed = 0;
+        rc = score_hypotheses_ready(ctx, &overflow, &needed);
+        if (rc) return rc;
+        if (!overflow) return L3D_OK;
+        if (attempt >= 8) return fail(L3D_ERR_CAPACITY, "fold program store overflow");
+        rc = score_rebuild(ctx, needed);
+        if (rc) return rc;
+    }
 }
 
 int l3d_match_images(l3d_ctx* ctx, const l3d_params* params)
@@ -703,20 +828,24 @@ int l3d_match_images(l3d_ctx* ctx, const l3d_params* params)
 }
 
 // ------------------------------------------------------------------------------------------
-// stage 4: affinity + clustering
+// stage 4: affinity (edges of this rank's slice, then ids over all edges) + clustering
 // ------------------------------------------------------------------------------------------
-int l3d_affinity(l3d_ctx* ctx)
+int l3d_affinity_edges(l3d_ctx* ctx)
 {
     if (!ctx) return fail(L3D_ERR_ARG, "ctx is NULL");
     if (ctx->stage < 2) return fail(L3D_ERR_STATE, "l3d_match_images has not run");
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
-    const uint32_t V = (uint32_t)ctx->views.size(), S = ctx->S;
+    const uint32_t S = ctx->S;
     ctx->cnt.num_edges = 0;
     ctx->cnt.num_local_ids = 0;
     ctx->cluster_ids.clear();
+    ctx->n_edges_local = 0;
+    ctx->n_edges_all = 0;
+    ctx->edges_all = nullptr;
     if (ctx->cnt.num_entries == 0) {  // "no clusterable segments" (src/line3D.cc:2028-2034)
         ctx->stage = 3;
+        ctx->stage4_phase = 1;
         return L3D_OK;
     }
     // translate() again (src/line3D.cc:2065); only the camera centres move
@@ -732,27 +861,54 @@ int l3d_affinity(l3d_ctx* ctx)
     } else
         ctx->med_scene_depth_lines = 0.0f;
 
-    cudaEvent_t ev_total = ctx->tm.begin(L3D_T_TOTAL, st);
+    ctx->ev_total4 = ctx->tm.begin(L3D_T_TOTAL, st);
     cudaEvent_t ev = ctx->tm.begin(L3D_T_AFFINITY, st);
+    const ListRec* filt = ctx->filt_all ? ctx->filt_all : ctx->d_filt_rec.p;
     const size_t nf = (size_t)ctx->cnt.filtered_entries;
+    const uint32_t g_lo = ctx->slice_g[ctx->rank], g_hi = ctx->slice_g[ctx->rank + 1];
     CK(ctx->d_filt_sim.ensure(nf + 1));
     CK(ctx->d_E_cnt.ensure((size_t)S + 1));
     CK(ctx->d_E_off.ensure((size_t)S + 2));
+    CK(cudaMemsetAsync(ctx->d_E_cnt.p, 0, ((size_t)S + 1) * 4, st));
     CK(ctx->d_tests.ensure(2));
     CK(cudaMemsetAsync(ctx->d_tests.p, 0, 16, st));
-    CK(ctx->d_first_touch.ensure((size_t)S + 1));
-    CK(cudaMemsetAsync(ctx->d_first_touch.p, 0xff, ((size_t)S + 1) * 4, st));
     ctx->cnt.gpu_launches +=
         launch_k4_edges_count(ctx->d_views.p, ctx->d_seg_view.p, ctx->d_entries.p, S, ctx->d_filt_off.p,
-                              ctx->d_filt_cnt.p, ctx->d_filt_rec.p, ctx->two_sigA_sqr, ctx->med_scene_depth_lines,
-                              ctx->d_filt_sim.p, ctx->d_E_cnt.p, ctx->d_tests.p, st);
+                              ctx->d_filt_cnt.p, filt, ctx->two_sigA_sqr, ctx->med_scene_depth_lines,
+                              ctx->d_filt_sim.p, ctx->d_E_cnt.p, ctx->d_tests.p, g_lo, g_hi, st);
     ctx->cnt.gpu_launches += launch_scan_u32(ctx->d_E_cnt.p, ctx->d_E_off.p, S, ctx->d_scan.p, ctx->d_scan.cap, st);
     uint32_t n_edges = 0;
     CK(cudaMemcpyAsync(&n_edges, ctx->d_E_off.p + S, 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    uint32_t n_local = 0;
     if (n_edges) {
         CK(ctx->d_edges.ensure((size_t)n_edges * k4_edge_bytes()));
+        ctx->cnt.gpu_launches +=
+            launch_k4_edges_write(ctx->d_views.p, S, ctx->d_filt_off.p, ctx->d_filt_cnt.p, filt, ctx->d_filt_sim.p,
+                                  ctx->d_E_off.p, ctx->d_edges.p, g_lo, g_hi, st);
+    }
+    ctx->n_edges_local = n_edges;
+    ctx->tm.end(ev, st);
+    ctx->stage4_phase = 1;
+    return L3D_OK;
+}
+
+int l3d_affinity_ids(l3d_ctx* ctx)
+{
+    if (!ctx) return fail(L3D_ERR_ARG, "ctx is NULL");
+    if (ctx->stage < 2 || ctx->stage4_phase < 1) return fail(L3D_ERR_STATE, "l3d_affinity_edges has not run");
+    if (ctx->stage == 3 && ctx->cnt.num_entries == 0) return L3D_OK;
+    if (ctx->world > 1 && !ctx->edges_all && ctx->stage4_phase < 2)
+        return fail(L3D_ERR_STATE, "the edges have not been exchanged");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const uint32_t S = ctx->S;
+    const uint32_t n_edges = ctx->world > 1 ? ctx->n_edges_all : ctx->n_edges_local;
+    const void* edges = ctx->world > 1 ? ctx->edges_all : (const void*)ctx->d_edges.p;
+    cudaEvent_t ev = ctx->tm.begin(L3D_T_AFFINITY, st);
+    uint32_t n_local = 0;
+    if (n_edges) {
+        CK(ctx->d_first_touch.ensure((size_t)S + 1));
+        CK(cudaMemsetAsync(ctx->d_first_touch.p, 0xff, ((size_t)S + 1) * 4, st));
         CK(ctx->d_flags.ensure(2 * (size_t)n_edges + 1));
         CK(ctx->d_flag_scan.ensure(2 * (size_t)n_edges + 2));
         CK(ctx->d_A_ij.ensure(2 * (size_t)n_edges));
@@ -760,23 +916,31 @@ int l3d_affinity(l3d_ctx* ctx)
         CK(ctx->d_l2g.ensure(2 * (size_t)n_edges));
         CK(ctx->d_scan.ensure(scan_scratch_words(2 * n_edges + 2) + 64));
         ctx->cnt.gpu_launches +=
-            launch_k4_edges_write(ctx->d_views.p, S, ctx->d_filt_off.p, ctx->d_filt_cnt.p, ctx->d_filt_rec.p,
-                                  ctx->d_filt_sim.p, ctx->d_E_off.p, ctx->d_edges.p, ctx->d_first_touch.p, st);
-        ctx->cnt.gpu_launches +=
-            launch_k4_ids(ctx->d_edges.p, n_edges, ctx->d_first_touch.p, ctx->d_flags.p, ctx->d_flag_scan.p,
-                          ctx->d_scan.p, ctx->d_scan.cap, ctx->d_A_ij.p, ctx->d_A_w.p, ctx->d_l2g.p, st);
+            launch_k4_ids(edges, n_edges, ctx->d_first_touch.p, ctx->d_flags.p, ctx->d_flag_scan.p, ctx->d_scan.p,
+                          ctx->d_scan.cap, ctx->d_A_ij.p, ctx->d_A_w.p, ctx->d_l2g.p, st);
         CK(cudaMemcpyAsync(&n_local, ctx->d_flag_scan.p + 2 * (size_t)n_edges, 4, cudaMemcpyDeviceToHost, st));
     }
     ctx->tm.end(ev, st);
-    ctx->tm.end(ev_total, st);
+    if (ctx->ev_total4) ctx->tm.end(ctx->ev_total4, st);
+    ctx->ev_total4 = nullptr;
     CK(cudaStreamSynchronize(st));
     ctx->tm.collect();
     ctx->cnt.num_edges = 2 * n_edges;  // A_ holds both directions
     ctx->cnt.num_local_ids = n_local;
     apply_translation(ctx, +1.0);  // untranslate() (src/line3D.cc:2140)
     ctx->stage = 3;
-    (void)V;
+    ctx->stage4_phase = 2;
     return L3D_OK;
+}
+
+int l3d_affinity(l3d_ctx* ctx)
+{
+    if (!ctx) return fail(L3D_ERR_ARG, "ctx is NULL");
+    if (ctx->world > 1)
+        return fail(L3D_ERR_STATE, "sharded run: use l3d_affinity_edges / l3d_shard_* / l3d_affinity_ids");
+    int rc = l3d_affinity_edges(ctx);
+    if (rc) return rc;
+    return l3d_affinity_ids(ctx);
 }
 
 // Felzenszwalb-Huttenlocher clustering, src/clustering.cc:7-48 + include/universe.h:59-117
@@ -896,6 +1060,8 @@ int l3d_get_view_lists(l3d_ctx* ctx, uint32_t cam_id, int which, uint32_t* row_o
     uint64_t region = 0;
     if (which == 0) {
         if (!ctx->prm.keep_scored) return fail(L3D_ERR_STATE, "keep_scored was not set");
+        if (v < ctx->slice_view[ctx->rank] || v >= ctx->slice_view[ctx->rank + 1])
+            return fail(L3D_ERR_STATE, "the scored lists of camera %u are held by another rank", cam_id);
         CK(cudaMemcpyAsync(off.data(), ctx->d_L_off.p + hv.seg_off, ((size_t)N + 1) * 4, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(cnt.data(), ctx->d_L_cnt.p + hv.seg_off, (size_t)N * 4, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
@@ -915,7 +1081,7 @@ int l3d_get_view_lists(l3d_ctx* ctx, uint32_t cam_id, int which, uint32_t* row_o
             }
         if (lo == 0xffffffffu) lo = hi = 0;
         for (uint32_t i = 0; i < N; ++i) off[i] = cnt[i] ? off[i] - lo : 0;
-        src = ctx->d_filt_rec.p + lo;
+        src = (ctx->filt_all ? ctx->filt_all : ctx->d_filt_rec.p) + lo;
         region = hi - lo;
     }
     uint64_t total = 0;

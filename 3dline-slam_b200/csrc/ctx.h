@@ -31,14 +31,8 @@ int launch_k3_inv_capacity(const PairDev*, uint32_t, uint32_t, const uint32_t*, 
 int launch_k3_list_capacity(const ViewDev*, const uint32_t*, uint32_t, const IncDev*, const uint32_t*, const PairDev*,
                             const uint32_t*, const uint32_t*, uint32_t*, void*, cudaStream_t);
 int launch_k3_records(const PairDev*, uint32_t, uint32_t, const ViewDev*, const SegRays*, const uint32_t*, FwdRec*,
-                      void*, void*, const uint32_t*, uint32_t*, uint2*, cudaStream_t);
+                      void*, void*, const uint32_t*, uint32_t*, uint2*, uint32_t, uint32_t, cudaStream_t);
 size_t k3_geo_bytes();
-int launch_k3_dataflow(const ViewDev*, const uint32_t*, const PairDev*, const IncDev*, const uint32_t*, const SegRays*,
-                       const uint32_t*, const uint32_t*, FwdRec*, const uint32_t*, const void*, const void*,
-                       const uint32_t*, const uint32_t*, const uint2*, const uint32_t*, uint32_t*, unsigned char*,
-                       float*, void*, double*, float2*, uint32_t*, uint32_t*, uint32_t*, uint32_t*, void*, uint32_t,
-                       uint32_t*, ListRec*, uint32_t*, ListRec*, uint32_t, uint32_t*, uint32_t*, EntryDev*, void*,
-                       uint32_t, uint32_t, float, cudaStream_t, int*);
 size_t k3_wf_stats_bytes();
 size_t k3_sib_bytes();
 int k3_wf_max_inc();
@@ -47,10 +41,11 @@ size_t k3_stats_bytes();
 int launch_k4_has(const EntryDev*, uint32_t, uint32_t*, cudaStream_t);
 int launch_k4_median(ViewDev*, uint32_t, const EntryDev*, uint32_t*, cudaStream_t);
 int launch_k4_edges_count(const ViewDev*, const uint32_t*, const EntryDev*, uint32_t, const uint32_t*, const uint32_t*,
-                          const ListRec*, float, float, float*, uint32_t*, unsigned long long*, cudaStream_t);
+                          const ListRec*, float, float, float*, uint32_t*, unsigned long long*, uint32_t, uint32_t,
+                          cudaStream_t);
 int launch_k4_edges_write(const ViewDev*, uint32_t, const uint32_t*, const uint32_t*, const ListRec*, const float*,
-                          const uint32_t*, void*, uint32_t*, cudaStream_t);
-int launch_k4_ids(const void*, uint32_t, const uint32_t*, uint32_t*, uint32_t*, uint32_t*, size_t, int2*, float*,
+                          const uint32_t*, void*, uint32_t, uint32_t, cudaStream_t);
+int launch_k4_ids(const void*, uint32_t, uint32_t*, uint32_t*, uint32_t*, uint32_t*, size_t, int2*, float*,
                   uint32_t*, cudaStream_t);
 size_t k4_edge_bytes();
 int launch_test_expf(const float*, float*, uint32_t, cudaStream_t);
@@ -58,9 +53,6 @@ int launch_test_acos(const double*, double*, uint32_t, cudaStream_t);
 int launch_fp32_peak(float*, int, int, cudaStream_t);
 int launch_score_prep(const float4*, uint32_t, const float4*, const float2*, const double*, const double*, float,
                       const uint32_t*, ListRec*, ListGeo*, cudaStream_t);
-int launch_fwd_merge_cnt(const uint32_t*, uint64_t, int, uint32_t, uint32_t*, cudaStream_t);
-int launch_fwd_merge_copy(const uint32_t*, uint64_t, int, uint32_t, const uint32_t*, const uint32_t*, FwdRec*,
-                          cudaStream_t);
 }  // namespace l3d
 
 using namespace l3d;
@@ -233,6 +225,27 @@ struct l3d_ctx {
     DevBuf<unsigned char> d_L_meta, d_prog;
     DevBuf<float> d_L_score;
     uint64_t prog_cap = 0;  // fold-program store, 16-byte units (grown on overflow)
+    uint64_t L_total = 0, filt_cap = 0;
+    uint32_t k3_maxm = 0;
+    bool k3_big_rows = false;
+    int stage3_phase = 0, stage4_phase = 0;
+    cudaEvent_t ev_total3 = nullptr, ev_total4 = nullptr;
+
+    // sharding: contiguous view slices (see plan_pairs), buffers adopted from the exchanges
+    int world = 1, rank = 0;
+    std::vector<uint32_t> slice_view{0, 0}, slice_g{0, 0}, slice_row{0, 0};
+    const void* prog_all = nullptr;      // all-gathered fold programs (caller-owned until the next exchange)
+    const ListRec* filt_all = nullptr;   // filtered lists of every slice (d_filt_all)
+    const void* edges_all = nullptr;     // edges of every slice in traversal order (d_edges_all)
+    DevBuf<ListRec> d_filt_all;
+    DevBuf<unsigned char> d_edges_all;
+    DevBuf<FwdRec> d_fwd_alt;
+    uint32_t n_edges_local = 0, n_edges_all = 0;
+    uint64_t local_fwd = 0;      // forward records produced by this rank's pairs
+    uint64_t xchg_var[4] = {0, 0, 0, 0};
+    DevBuf<unsigned char> d_xchg_stage[4];
+    DevBuf<uint32_t> d_slice_g;
+    uint64_t shard_sim_evals = 0, shard_scored = 0, shard_filtered = 0;
     DevBuf<unsigned char> d_G_fwd, d_G_inv;
     std::vector<uint64_t> L_cap_h;   // per-view list capacity
     DevBuf<ListRec> d_filt_rec;
@@ -261,3 +274,6 @@ int refresh_pair_totals(l3d_ctx* ctx);
 int plan_pairs(l3d_ctx* ctx);
 int upload_views(l3d_ctx* ctx);
 int set_params(l3d_ctx* ctx, const l3d_params* params);
+int score_rebuild(l3d_ctx* ctx, uint32_t needed_units);
+int score_hypotheses_ready(l3d_ctx* ctx, bool* prog_overflow, uint32_t* prog_needed);
+#define L3D_MAX_WORLD 16

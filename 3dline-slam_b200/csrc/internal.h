@@ -103,6 +103,25 @@ struct IncDev {  // one incident pair of a view, in list order
     uint32_t inverse;  // 1: this view is the pair's target (entries come from the inverse CSR)
 };
 
+// device tables of the scoring stage (K3), filled from the context by ctx.cu
+struct K3Tables {
+    const ViewDev* views; const uint32_t* seg_view; const PairDev* pairs; const IncDev* inc; const uint32_t* inc_off;
+    const SegRays* rays; const uint32_t* fwd_off; const uint32_t* fwd_cnt; FwdRec* fwd_rec; const uint32_t* fwd_row;
+    const void* G_fwd; const void* G_inv; const uint32_t* inv_off; const uint32_t* inv_fill; const uint2* inv_ent;
+    const uint32_t* L_off; uint32_t* L_f; unsigned char* L_meta; float* L_score;
+    void* L_sib; double* L_dir; float2* L_reg; uint32_t* L_c; uint32_t* L_h;
+    uint32_t* prog_off; uint32_t* prog_nh; void* prog; uint32_t prog_cap;
+    uint32_t* L_cnt; ListRec* L_rec; uint32_t* view_max; ListRec* filt_rec; uint32_t filt_cap;
+    uint32_t* filt_off; uint32_t* filt_cnt; EntryDev* entries; void* stats;
+    uint32_t S, maxm; float two_sigA_sqr;
+    uint32_t g_lo, g_hi;  // rows (global segment indices) this rank builds and finishes
+};
+int launch_k3_build(const K3Tables& t, cudaStream_t st, int* err);
+int launch_k3_fold(const K3Tables& t, cudaStream_t st, int* err);
+int launch_k3_finish(const K3Tables& t, cudaStream_t st);
+int launch_k3_adopt_programs(const void* all, uint64_t stride, int world, const uint32_t* slice_g, uint32_t S,
+                             uint32_t* prog_off, uint32_t* prog_nh, FwdRec* fwd_rec, cudaStream_t st);
+
 // ---------------- launchers (each returns the number of kernels launched) ----------------
 int launch_scan_u32(const uint32_t* in, uint32_t* out, uint32_t n, uint32_t* scratch,
                     size_t scratch_words, cudaStream_t st);

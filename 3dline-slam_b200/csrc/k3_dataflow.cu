@@ -164,21 +164,27 @@ __global__ void __launch_bounds__(128) k3_record_kernel(const PairDev* __restric
                                                         FwdRec* __restrict__ fwd_rec, GeoRec* __restrict__ G_fwd,
                                                         GeoRec* __restrict__ G_inv,
                                                         const uint32_t* __restrict__ inv_off,
-                                                        uint32_t* __restrict__ inv_fill, uint2* __restrict__ inv_ent)
+                                                        uint32_t* __restrict__ inv_fill, uint2* __restrict__ inv_ent,
+                                                        uint32_t v_lo, uint32_t v_hi)
 {
     const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= F) return;
     const uint32_t row = fwd_row[f];
     const PairDev& D = pairs[pair_of_row(pairs, P, row)];
     const uint32_t i = row - D.row_base;
+    fwd_rec[f].score = 0.0f;
+    // the geometry of a record is read by the rows of its source view (G_fwd) and, as an inverse
+    // match, by the rows of its target view (G_inv): views [v_lo, v_hi) are built by this rank
+    const bool need_fwd = D.src_view >= v_lo && D.src_view < v_hi;
+    const bool need_inv = D.emit_inverse && D.tgt_view >= v_lo && D.tgt_view < v_hi;
+    if (!need_fwd && !need_inv) return;
     const ViewDev& vs = views[D.src_view];
     const ViewDev& vt = views[D.tgt_view];
     const D3 Cs = ld3w(vs.C), Ct = ld3w(vt.C);
     const SegRays sr = rays[D.src_off + i];
     const FwdRec rec = fwd_rec[f];
-    fwd_rec[f].score = 0.0f;
-    G_fwd[f] = make_geo(Cs, ld3w(sr.r1), ld3w(sr.r2), rec.d_p1, rec.d_p2, vs.k, Ct, vt.k);
-    if (D.emit_inverse) {
+    if (need_fwd) G_fwd[f] = make_geo(Cs, ld3w(sr.r1), ld3w(sr.r2), rec.d_p1, rec.d_p2, vs.k, Ct, vt.k);
+    if (need_inv) {
         const SegRays tr = rays[D.tgt_off + rec.c];
         G_inv[f] = make_geo(Ct, ld3w(tr.r1), ld3w(tr.r2), rec.d_q1, rec.d_q2, vt.k, Cs, vs.k);
         const uint32_t tr_row = D.tgt_base + rec.c;
@@ -219,6 +225,7 @@ struct BuildArgs {
     uint32_t prog_cap;
     WfStats* stats;
     uint32_t S;
+    uint32_t g_lo, g_hi;  // rows built by this rank (global segment indices)
     uint32_t maxm;
     float two_sigA_sqr;
     float dotcut;  // see score_core.cuh
@@ -252,8 +259,8 @@ __global__ void __launch_bounds__(DF_THREADS) k3_build_kernel(const BuildArgs a)
     extern __shared__ __align__(16) unsigned char df_smem[];
     __shared__ BlockTab bt;
     __shared__ uint32_t s_tot[2], s_base;
-    const uint32_t g = blockIdx.x;
-    if (g >= a.S) return;
+    const uint32_t g = a.g_lo + blockIdx.x;
+    if (g >= a.g_hi) return;
     const uint32_t v = a.seg_view[g];
     const ViewDev& va = a.views[v];
     const uint32_t i = g - va.seg_off;
@@ -660,6 +667,7 @@ struct FinishArgs {
     EntryDev* entries;   // [S]
     WfStats* stats;
     uint32_t S;
+    uint32_t g_lo, g_hi;  // rows finished by this rank
 };
 
 __device__ __forceinline__ ListRec make_list_rec(const FinishArgs& a, uint32_t i0, uint32_t f, uint32_t meta, float score)
@@ -697,8 +705,8 @@ __global__ void __launch_bounds__(FIN_WARPS * 32) k3_finish_kernel(const FinishA
 {
     __shared__ uint32_t blkcnt[FIN_WARPS][DF_MAXINC];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t g = blockIdx.x * FIN_WARPS + warp;
-    if (g >= a.S) return;
+    const uint32_t g = a.g_lo + blockIdx.x * FIN_WARPS + warp;
+    if (g >= a.g_hi) return;
     const uint32_t lt_mask = (1u << lane) - 1u;
     const size_t lbase = a.L_off[g];
     const uint32_t m = a.L_off[g + 1] - a.L_off[g];
@@ -850,11 +858,11 @@ int launch_k3_list_capacity(const ViewDev* views, const uint32_t* seg_view, uint
 
 int launch_k3_records(const PairDev* pairs, uint32_t P, uint32_t F, const ViewDev* views, const SegRays* rays,
                       const uint32_t* fwd_row, FwdRec* fwd_rec, void* G_fwd, void* G_inv, const uint32_t* inv_off,
-                      uint32_t* inv_fill, uint2* inv_ent, cudaStream_t st)
+                      uint32_t* inv_fill, uint2* inv_ent, uint32_t v_lo, uint32_t v_hi, cudaStream_t st)
 {
     if (!F || !P) return 0;
     k3_record_kernel<<<(F + 127) / 128, 128, 0, st>>>(pairs, P, F, views, rays, fwd_row, fwd_rec, (GeoRec*)G_fwd,
-                                                       (GeoRec*)G_inv, inv_off, inv_fill, inv_ent);
+                                                       (GeoRec*)G_inv, inv_off, inv_fill, inv_ent, v_lo, v_hi);
     return 1;
 }
 
@@ -870,75 +878,122 @@ static size_t build_smem_bytes(uint32_t maxm)
            (size_t)(maxm < (uint32_t)DF_MASKM ? maxm : (uint32_t)DF_MASKM) * DF_MASKW * 4 + 16;
 }
 
-// build + fold + finish; returns the number of launches or a negative value (CUDA error in *err)
-int launch_k3_dataflow(const ViewDev* views, const uint32_t* seg_view, const PairDev* pairs, const IncDev* inc,
-                       const uint32_t* inc_off, const SegRays* rays, const uint32_t* fwd_off, const uint32_t* fwd_cnt,
-                       FwdRec* fwd_rec, const uint32_t* fwd_row, const void* G_fwd, const void* G_inv,
-                       const uint32_t* inv_off, const uint32_t* inv_fill, const uint2* inv_ent, const uint32_t* L_off,
-                       uint32_t* L_f, unsigned char* L_meta, float* L_score, void* L_sib, double* L_dir, float2* L_reg,
-                       uint32_t* L_c, uint32_t* L_h, uint32_t* prog_off, uint32_t* prog_nh, void* prog,
-                       uint32_t prog_cap, uint32_t* L_cnt, ListRec* L_rec, uint32_t* view_max, ListRec* filt_rec,
-                       uint32_t filt_cap, uint32_t* filt_off, uint32_t* filt_cnt, EntryDev* entries, void* stats,
-                       uint32_t S, uint32_t maxm, float two_sigA_sqr, cudaStream_t st, int* err)
+static BuildArgs build_args(const K3Tables& t, uint32_t maxm)
 {
-    if (!S) return 0;
+    BuildArgs b;
+    b.views = t.views; b.seg_view = t.seg_view; b.pairs = t.pairs; b.inc = t.inc; b.inc_off = t.inc_off;
+    b.fwd_off = t.fwd_off; b.fwd_cnt = t.fwd_cnt; b.fwd_rec = t.fwd_rec;
+    b.G_fwd = (const GeoRec*)t.G_fwd; b.G_inv = (const GeoRec*)t.G_inv;
+    b.inv_off = t.inv_off; b.inv_fill = t.inv_fill; b.inv_ent = t.inv_ent;
+    b.L_off = t.L_off; b.L_f = t.L_f; b.L_meta = t.L_meta;
+    b.L_sib = (Sib*)t.L_sib; b.L_dir = t.L_dir; b.L_reg = t.L_reg; b.L_c = t.L_c; b.L_h = t.L_h;
+    b.prog_off = t.prog_off; b.prog_nh = t.prog_nh; b.prog = (uint4*)t.prog; b.prog_cap = t.prog_cap;
+    b.stats = (WfStats*)t.stats; b.S = t.S; b.g_lo = t.g_lo; b.g_hi = t.g_hi; b.maxm = maxm;
+    b.two_sigA_sqr = t.two_sigA_sqr;
+    b.dotcut = score_dotcut(t.two_sigA_sqr, 0.5f);
+    return b;
+}
+
+// build: potential lists and fold programs of the rows [g_lo, g_hi)
+int launch_k3_build(const K3Tables& t, cudaStream_t st, int* err)
+{
+    if (t.g_hi <= t.g_lo) return 0;
+    uint32_t maxm = t.maxm;
     if (maxm > (uint32_t)DF_MAXM_CAP) maxm = DF_MAXM_CAP;
     maxm = (maxm + 3u) & ~3u;  // keeps the shared-memory arrays 16-byte aligned
     if (maxm < 4) maxm = 4;
-    BuildArgs b;
-    b.views = views; b.seg_view = seg_view; b.pairs = pairs; b.inc = inc; b.inc_off = inc_off;
-    b.fwd_off = fwd_off; b.fwd_cnt = fwd_cnt; b.fwd_rec = fwd_rec;
-    b.G_fwd = (const GeoRec*)G_fwd; b.G_inv = (const GeoRec*)G_inv;
-    b.inv_off = inv_off; b.inv_fill = inv_fill; b.inv_ent = inv_ent;
-    b.L_off = L_off; b.L_f = L_f; b.L_meta = L_meta;
-    b.L_sib = (Sib*)L_sib; b.L_dir = L_dir; b.L_reg = L_reg; b.L_c = L_c; b.L_h = L_h;
-    b.prog_off = prog_off; b.prog_nh = prog_nh; b.prog = (uint4*)prog; b.prog_cap = prog_cap;
-    b.stats = (WfStats*)stats; b.S = S; b.maxm = maxm; b.two_sigA_sqr = two_sigA_sqr;
-    b.dotcut = score_dotcut(two_sigA_sqr, 0.5f);
+    const BuildArgs b = build_args(t, maxm);
     const size_t smem = build_smem_bytes(maxm);
     cudaError_t e = cudaFuncSetAttribute(k3_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
         *err = (int)e;
         return -1;
     }
-    k3_build_kernel<<<S, DF_THREADS, smem, st>>>(b);
+    k3_build_kernel<<<t.g_hi - t.g_lo, DF_THREADS, smem, st>>>(b);
+    return 1;
+}
 
+// fold: every row of the scene (replicated on every rank: the scores of all views are needed)
+int launch_k3_fold(const K3Tables& t, cudaStream_t st, int* err)
+{
+    if (!t.S) return 0;
     FoldArgs f;
-    f.seg_view = seg_view; f.L_off = L_off; f.L_score = L_score; f.fwd_rec = fwd_rec;
-    f.prog_off = prog_off; f.prog_nh = prog_nh; f.prog = (const uint4*)prog; f.view_max = view_max;
-    f.stats = (WfStats*)stats; f.S = S;
+    f.seg_view = t.seg_view; f.L_off = t.L_off; f.L_score = t.L_score; f.fwd_rec = t.fwd_rec;
+    f.prog_off = t.prog_off; f.prog_nh = t.prog_nh; f.prog = (const uint4*)t.prog; f.view_max = t.view_max;
+    f.stats = (WfStats*)t.stats; f.S = t.S;
     int dev = 0, sms = 0, per_sm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k3_fold_kernel, FOLD_WARPS * 32, 0);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k3_fold_kernel, FOLD_WARPS * 32, 0);
     if (e != cudaSuccess || per_sm < 1) {
         *err = (int)e;
         return -1;
     }
     // every CTA must be resident (the progress argument needs running warps): at most one wave
     uint32_t grid = (uint32_t)(sms * per_sm);
-    const uint32_t want = (S + FOLD_WARPS - 1) / FOLD_WARPS;
+    const uint32_t want = (t.S + FOLD_WARPS - 1) / FOLD_WARPS;
     if (want < grid) grid = want ? want : 1u;
     static int sleep_ns = -1;
     if (sleep_ns < 0) {
-        const char* e = getenv("L3D_FOLD_SLEEP_NS");  // tuning hook
-        sleep_ns = e ? atoi(e) : 40;
+        const char* ev = getenv("L3D_FOLD_SLEEP_NS");  // tuning hook
+        sleep_ns = ev ? atoi(ev) : 40;
     }
     f.sleep_ns = (uint32_t)sleep_ns;
     k3_fold_kernel<<<grid, FOLD_WARPS * 32, 0, st>>>(f);
+    return 1;
+}
 
+// finish: lists, filterMatches and hypotheses of the rows [g_lo, g_hi)
+int launch_k3_finish(const K3Tables& t, cudaStream_t st)
+{
+    if (t.g_hi <= t.g_lo) return 0;
     FinishArgs c;
-    c.views = views; c.seg_view = seg_view; c.pairs = pairs; c.inc = inc; c.inc_off = inc_off; c.rays = rays;
-    c.fwd_rec = fwd_rec; c.fwd_row = fwd_row; c.L_off = L_off; c.L_f = L_f; c.L_meta = L_meta; c.L_score = L_score;
-    c.L_cnt = L_cnt; c.L_rec = L_rec; c.view_max = view_max; c.filt_rec = filt_rec; c.filt_cap = filt_cap;
-    c.filt_off = filt_off; c.filt_cnt = filt_cnt; c.entries = entries; c.stats = (WfStats*)stats; c.S = S;
-    k3_finish_kernel<<<(S + FIN_WARPS - 1) / FIN_WARPS, FIN_WARPS * 32, 0, st>>>(c);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) {
-        *err = (int)e;
-        return -1;
+    c.views = t.views; c.seg_view = t.seg_view; c.pairs = t.pairs; c.inc = t.inc; c.inc_off = t.inc_off;
+    c.rays = t.rays; c.fwd_rec = t.fwd_rec; c.fwd_row = t.fwd_row; c.L_off = t.L_off; c.L_f = t.L_f;
+    c.L_meta = t.L_meta; c.L_score = t.L_score; c.L_cnt = t.L_cnt; c.L_rec = t.L_rec; c.view_max = t.view_max;
+    c.filt_rec = t.filt_rec; c.filt_cap = t.filt_cap; c.filt_off = t.filt_off; c.filt_cnt = t.filt_cnt;
+    c.entries = t.entries; c.stats = (WfStats*)t.stats; c.S = t.S; c.g_lo = t.g_lo; c.g_hi = t.g_hi;
+    k3_finish_kernel<<<(t.g_hi - t.g_lo + FIN_WARPS - 1) / FIN_WARPS, FIN_WARPS * 32, 0, st>>>(c);
+    return 1;
+}
+
+// multi-GPU: adopt the all-gathered fold programs.  Blob of rank q (stride bytes apart):
+//   u32 nh[rows_pad_q] | u32 off[rows_pad_q] | uint4 records[]   (rows_pad = rows of the slice rounded up to 4)
+// prog_off becomes an index into the gathered buffer; the forward heads are marked pending.
+__global__ void __launch_bounds__(256) k3_adopt_programs_kernel(const unsigned char* __restrict__ all, uint64_t stride,
+                                                                int world, const uint32_t* __restrict__ slice_g,
+                                                                uint32_t S, uint32_t* __restrict__ prog_off,
+                                                                uint32_t* __restrict__ prog_nh,
+                                                                FwdRec* __restrict__ fwd_rec)
+{
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= S) return;
+    int q = 0;
+    while (q + 1 < world && slice_g[q + 1] <= g) ++q;
+    const uint32_t rows = slice_g[q + 1] - slice_g[q], rows_pad = (rows + 3u) & ~3u;
+    const unsigned char* blob = all + (uint64_t)q * stride;
+    const uint32_t* hdr = reinterpret_cast<const uint32_t*>(blob);
+    const uint32_t nh = hdr[g - slice_g[q]];
+    const uint32_t off = hdr[rows_pad + (g - slice_g[q])];
+    const uint64_t rec0 = ((uint64_t)q * stride + 8ull * rows_pad) / 16ull;  // first record of the blob, 16-byte units
+    prog_nh[g] = nh;
+    prog_off[g] = nh ? (uint32_t)(rec0 + off) : 0u;
+    if (nh) {
+        const uint4* heads = reinterpret_cast<const uint4*>(all) + rec0 + off + 1;
+        for (uint32_t h = 0; h < nh; ++h) {
+            const uint4 H = heads[h];
+            if (!(H.x >> 31)) fwd_rec[H.w].score = -1.0f;
+        }
     }
-    return 3;
+}
+
+int launch_k3_adopt_programs(const void* all, uint64_t stride, int world, const uint32_t* slice_g, uint32_t S,
+                             uint32_t* prog_off, uint32_t* prog_nh, FwdRec* fwd_rec, cudaStream_t st)
+{
+    if (!S) return 0;
+    k3_adopt_programs_kernel<<<(S + 255) / 256, 256, 0, st>>>((const unsigned char*)all, stride, world, slice_g, S,
+                                                               prog_off, prog_nh, fwd_rec);
+    return 1;
 }
 
 }  // namespace l3d

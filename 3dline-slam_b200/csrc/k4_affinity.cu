@@ -136,10 +136,10 @@ __global__ void __launch_bounds__(128) k4_edges_count_kernel(
     const ViewDev* __restrict__ views, const uint32_t* __restrict__ seg_view, const EntryDev* __restrict__ entries,
     uint32_t S, const uint32_t* __restrict__ filt_off, const uint32_t* __restrict__ filt_cnt,
     const ListRec* __restrict__ filt_rec, float two_sigA_sqr, float msdl, float* __restrict__ filt_sim,
-    uint32_t* __restrict__ E_cnt, unsigned long long* __restrict__ tests)
+    uint32_t* __restrict__ E_cnt, unsigned long long* __restrict__ tests, uint32_t g_lo, uint32_t g_hi)
 {
-    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= S) return;
+    const uint32_t g = g_lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= g_hi) return;
     uint32_t kept = 0;
     const uint32_t n = filt_cnt[g];
     const uint32_t b = filt_off[g];
@@ -186,10 +186,10 @@ struct EdgeDev {
 __global__ void __launch_bounds__(128) k4_edges_write_kernel(
     const ViewDev* __restrict__ views, uint32_t S, const uint32_t* __restrict__ filt_off,
     const uint32_t* __restrict__ filt_cnt, const ListRec* __restrict__ filt_rec, const float* __restrict__ filt_sim,
-    const uint32_t* __restrict__ E_off, EdgeDev* __restrict__ edges, uint32_t* __restrict__ first_touch)
+    const uint32_t* __restrict__ E_off, EdgeDev* __restrict__ edges, uint32_t g_lo, uint32_t g_hi)
 {
-    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= S) return;
+    const uint32_t g = g_lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= g_hi) return;
     uint32_t k = E_off[g];
     if (E_off[g + 1] == k) return;
     const uint32_t n = filt_cnt[g], b = filt_off[g];
@@ -199,11 +199,20 @@ __global__ void __launch_bounds__(128) k4_edges_write_kernel(
             const ListRec m2 = filt_rec[b + z];
             const uint32_t t = views[m2.tgt_view].seg_off + m2.tgt_seg;
             edges[k] = EdgeDev{g, t, sim};
-            atomicMin(&first_touch[g], 2 * k);
-            atomicMin(&first_touch[t], 2 * k + 1);
             ++k;
         }
     }
+}
+
+// first touch position of every segment: edge k touches its source at 2k and its target at 2k+1
+__global__ void __launch_bounds__(256) k4_touch_kernel(const EdgeDev* __restrict__ edges, uint32_t n_edges,
+                                                       uint32_t* __restrict__ first_touch)
+{
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_edges) return;
+    const EdgeDev e = edges[k];
+    atomicMin(&first_touch[e.src], 2 * k);
+    atomicMin(&first_touch[e.tgt], 2 * k + 1);
 }
 
 // flag[p] = 1 iff touch position p is the first touch of its segment
@@ -259,30 +268,33 @@ int launch_k4_median(ViewDev* views, uint32_t V, const EntryDev* entries, uint32
 int launch_k4_edges_count(const ViewDev* views, const uint32_t* seg_view, const EntryDev* entries, uint32_t S,
                           const uint32_t* filt_off, const uint32_t* filt_cnt, const ListRec* filt_rec,
                           float two_sigA_sqr, float msdl, float* filt_sim, uint32_t* E_cnt,
-                          unsigned long long* tests, cudaStream_t st)
+                          unsigned long long* tests, uint32_t g_lo, uint32_t g_hi, cudaStream_t st)
 {
-    if (!S) return 0;
-    k4_edges_count_kernel<<<(S + 127) / 128, 128, 0, st>>>(views, seg_view, entries, S, filt_off, filt_cnt, filt_rec,
-                                                            two_sigA_sqr, msdl, filt_sim, E_cnt, tests);
+    if (g_hi <= g_lo) return 0;
+    k4_edges_count_kernel<<<(g_hi - g_lo + 127) / 128, 128, 0, st>>>(views, seg_view, entries, S, filt_off, filt_cnt,
+                                                                      filt_rec, two_sigA_sqr, msdl, filt_sim, E_cnt,
+                                                                      tests, g_lo, g_hi);
     return 1;
 }
 
 int launch_k4_edges_write(const ViewDev* views, uint32_t S, const uint32_t* filt_off, const uint32_t* filt_cnt,
                           const ListRec* filt_rec, const float* filt_sim, const uint32_t* E_off, void* edges,
-                          uint32_t* first_touch, cudaStream_t st)
+                          uint32_t g_lo, uint32_t g_hi, cudaStream_t st)
 {
-    if (!S) return 0;
-    k4_edges_write_kernel<<<(S + 127) / 128, 128, 0, st>>>(views, S, filt_off, filt_cnt, filt_rec, filt_sim, E_off,
-                                                            (EdgeDev*)edges, first_touch);
+    if (g_hi <= g_lo) return 0;
+    k4_edges_write_kernel<<<(g_hi - g_lo + 127) / 128, 128, 0, st>>>(views, S, filt_off, filt_cnt, filt_rec, filt_sim,
+                                                                      E_off, (EdgeDev*)edges, g_lo, g_hi);
     return 1;
 }
 
-int launch_k4_ids(const void* edges, uint32_t n_edges, const uint32_t* first_touch, uint32_t* flags,
+int launch_k4_ids(const void* edges, uint32_t n_edges, uint32_t* first_touch, uint32_t* flags,
                   uint32_t* flag_scan, uint32_t* scan_scratch, size_t scan_words, int2* A_ij, float* A_w,
                   uint32_t* local2global, cudaStream_t st)
 {
     if (!n_edges) return 0;
     int launches = 0;
+    k4_touch_kernel<<<(n_edges + 255) / 256, 256, 0, st>>>((const EdgeDev*)edges, n_edges, (uint32_t*)first_touch);
+    ++launches;
     k4_touch_flags_kernel<<<(2 * n_edges + 255) / 256, 256, 0, st>>>((const EdgeDev*)edges, n_edges, first_touch,
                                                                       flags);
     ++launches;

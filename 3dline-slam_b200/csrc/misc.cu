@@ -119,47 +119,41 @@ int launch_score_prep(const float4* lines, uint32_t n_lines, const float4* match
     return 1;
 }
 
-// merge of per-shard forward lists into the canonical layout (multi-GPU import)
-__global__ void __launch_bounds__(256) fwd_merge_cnt_kernel(const uint32_t* __restrict__ blobs, uint64_t stride_words,
-                                                            int world, uint32_t n_rows, uint32_t* __restrict__ cnt)
+// multi-GPU: adopt the all-gathered hypotheses (abi.cu, L3D_X_HYPOTHESES): entries, filtered-list
+// counts and offsets of every row, and the filtered records of every slice packed into one store
+struct HypHdr32 {
+    unsigned long long a, b;
+    uint32_t c, d, e, f;
+};
+__global__ void __launch_bounds__(128) hyp_adopt_kernel(const unsigned char* __restrict__ all, uint64_t stride, int world,
+                                                        const uint32_t* __restrict__ slice_g,
+                                                        const uint32_t* __restrict__ fbase, uint32_t S,
+                                                        EntryDev* __restrict__ entries, uint32_t* __restrict__ filt_cnt,
+                                                        uint32_t* __restrict__ filt_off, ListRec* __restrict__ filt_all)
 {
-    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n_rows) return;
-    uint32_t s = 0;
-    for (int w = 0; w < world; ++w) s += blobs[(size_t)w * stride_words + r];
-    cnt[r] = s;
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= S) return;
+    int q = 0;
+    while (q + 1 < world && slice_g[q + 1] <= g) ++q;
+    const uint32_t rows = slice_g[q + 1] - slice_g[q], rp = (rows + 3u) & ~3u, i = g - slice_g[q];
+    const unsigned char* blob = all + (uint64_t)q * stride + sizeof(HypHdr32);
+    const uint32_t* cnt = reinterpret_cast<const uint32_t*>(blob);
+    const uint32_t* off = cnt + rp;
+    const EntryDev* ent = reinterpret_cast<const EntryDev*>(blob + 8ull * rp);
+    const ListRec* rec = reinterpret_cast<const ListRec*>(blob + 8ull * rp + (uint64_t)rows * sizeof(EntryDev));
+    const uint32_t n = cnt[i], o = off[i];
+    entries[g] = ent[i];
+    filt_cnt[g] = n;
+    filt_off[g] = fbase[q] + o;
+    for (uint32_t z = 0; z < n; ++z) filt_all[fbase[q] + o + z] = rec[o + z];
 }
-__global__ void __launch_bounds__(256) fwd_merge_copy_kernel(const uint32_t* __restrict__ blobs, uint64_t stride_words,
-                                                             int world, uint32_t n_rows,
-                                                             const uint32_t* __restrict__ shard_off,
-                                                             const uint32_t* __restrict__ fwd_off,
-                                                             FwdRec* __restrict__ fwd_rec)
+int launch_hyp_adopt(const void* all, uint64_t stride, int world, const uint32_t* slice_g, const uint32_t* fbase,
+                     uint32_t S, EntryDev* entries, uint32_t* filt_cnt, uint32_t* filt_off, ListRec* filt_all,
+                     cudaStream_t st)
 {
-    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n_rows) return;
-    const uint32_t rows_pad = (n_rows + 7u) & ~7u;  // records start 32-byte aligned after the counts
-    for (int w = 0; w < world; ++w) {
-        const uint32_t* base = blobs + (size_t)w * stride_words;
-        const uint32_t n = base[r];
-        if (!n) continue;
-        const FwdRec* src = (const FwdRec*)(base + rows_pad) + shard_off[(size_t)w * (n_rows + 1) + r];
-        FwdRec* dst = fwd_rec + fwd_off[r];
-        for (uint32_t i = 0; i < n; ++i) dst[i] = src[i];
-    }
-}
-int launch_fwd_merge_cnt(const uint32_t* blobs, uint64_t stride_words, int world, uint32_t n_rows, uint32_t* cnt,
-                         cudaStream_t st)
-{
-    if (!n_rows) return 0;
-    fwd_merge_cnt_kernel<<<(n_rows + 255) / 256, 256, 0, st>>>(blobs, stride_words, world, n_rows, cnt);
-    return 1;
-}
-int launch_fwd_merge_copy(const uint32_t* blobs, uint64_t stride_words, int world, uint32_t n_rows,
-                          const uint32_t* shard_off, const uint32_t* fwd_off, FwdRec* fwd_rec, cudaStream_t st)
-{
-    if (!n_rows) return 0;
-    fwd_merge_copy_kernel<<<(n_rows + 255) / 256, 256, 0, st>>>(blobs, stride_words, world, n_rows, shard_off, fwd_off,
-                                                                 fwd_rec);
+    if (!S) return 0;
+    hyp_adopt_kernel<<<(S + 127) / 128, 128, 0, st>>>((const unsigned char*)all, stride, world, slice_g, fbase, S,
+                                                       entries, filt_cnt, filt_off, filt_all);
     return 1;
 }
 

@@ -1,60 +1,121 @@
-"""Multi-GPU plumbing: one process per GPU, pairs sharded in contiguous blocks (slices of reference views, balanced by test count) for stages 1-2, the
-forward-match lists of all shards all-gathered (NCCL over NVLink on the GPU box, gloo in the CPU
-tests) and merged into the canonical layout before the scoring wavefront.
+"""Multi-GPU plumbing: one process per GPU, reference views split into contiguous slices.
 
-Blob layout of one shard (l3d_export_forward): `uint32 cnt[rows_pad] | FwdRec recs[total]` with
-rows_pad = total rows rounded up to 8 (records 32-byte aligned); rows the shard does not own have
-cnt = 0; records are in row order.
+A rank matches the pairs whose source view it owns (stages 1-2), builds and finishes the scoring
+rows of its views and computes their affinity edges; four exchanges (all-gather over NCCL / NVLink
+on the GPU box, gloo in the CPU tests) make every result whole on every rank:
+
+    match_stage12 -> FORWARD -> score_build -> PROGRAMS -> score_fold -> HYPOTHESES
+                  -> affinity_edges -> EDGES -> affinity_ids
+
+Each exchange is an all-gather-v by padding: the blob sizes are gathered first (8 bytes per rank),
+then the blobs, `stride` bytes apart, into a buffer that persists between steps (the fold programs
+are read in place by the next phase).  The blob layouts are documented in csrc/abi.cu.
 """
 from __future__ import annotations
 
 import numpy as np
 
-FWD_DTYPE = np.dtype([("c", "<u4"), ("overlap", "<f4"), ("d_p1", "<f4"), ("d_p2", "<f4"), ("d_q1", "<f4"),
-                      ("d_q2", "<f4"), ("score", "<f4"), ("flags", "<u4")])
+X_FORWARD, X_PROGRAMS, X_HYPOTHESES, X_EDGES = 0, 1, 2, 3
+KINDS = ("forward", "programs", "hypotheses", "edges")
 
 
-def exchange_forward(shard, dist, torch, device):
-    """All-gather the forward-match blobs of every rank and import the merged lists.
+class Exchanger:
+    """Persistent send / receive buffers of the four exchanges of one rank."""
 
-    `shard` offers forward_blob_size() / export_forward(ptr, cap, device_ptr) /
-    import_forward(ptr, stride, world, device_ptr) (api.Line3D does).  Returns the bytes gathered."""
-    world = dist.get_world_size()
-    on_gpu = device.type == "cuda"
-    nbytes = shard.forward_blob_size()
-    sz = torch.tensor([nbytes], dtype=torch.int64, device=device)
-    szs = [torch.zeros_like(sz) for _ in range(world)]
-    dist.all_gather(szs, sz)                      # blob sizes differ per rank: all-gather-v by padding
-    stride = max(int(s.item()) for s in szs)
-    stride = (stride + 31) // 32 * 32
-    mine = torch.zeros(stride, dtype=torch.uint8, device=device)
-    shard.export_forward(mine.data_ptr(), stride, on_gpu)
-    allb = torch.empty(stride * world, dtype=torch.uint8, device=device)
-    if on_gpu:
-        dist.all_gather_into_tensor(allb, mine)
-        torch.cuda.current_stream(device).synchronize()
-    else:
-        parts = [torch.empty(stride, dtype=torch.uint8) for _ in range(world)]
-        dist.all_gather(parts, mine)
-        allb = torch.cat(parts)
-    shard.import_forward(allb.data_ptr(), stride, world, on_gpu)
-    return stride * world
+    def __init__(self, dist, torch, device):
+        self.dist, self.torch, self.device = dist, torch, device
+        self.world = dist.get_world_size()
+        self.on_gpu = device.type == "cuda"
+        self.mine = {}
+        self.all = {}
+        self.bytes_gathered = 0
+
+    def _buf(self, store, kind, nbytes):
+        t = store.get(kind)
+        if t is None or t.numel() < nbytes:
+            t = self.torch.empty(int(nbytes * 1.25) + 64, dtype=self.torch.uint8, device=self.device)
+            store[kind] = t
+        return t
+
+    def exchange(self, shard, kind):
+        """shard offers shard_blob_size(kind) / shard_export(kind, ptr, cap, device_ptr) /
+        shard_import(kind, ptr, stride, world, sizes, device_ptr) (api.Line3D does)."""
+        torch, dist, world = self.torch, self.dist, self.world
+        nbytes = shard.shard_blob_size(kind)
+        sz = torch.tensor([nbytes], dtype=torch.int64, device=self.device)
+        if self.on_gpu:
+            szs = torch.empty(world, dtype=torch.int64, device=self.device)
+            dist.all_gather_into_tensor(szs, sz)
+            sizes = szs.cpu().numpy().astype(np.uint64)
+        else:
+            parts = [torch.zeros_like(sz) for _ in range(world)]
+            dist.all_gather(parts, sz)
+            sizes = np.array([int(p.item()) for p in parts], dtype=np.uint64)
+        stride = (int(sizes.max()) + 31) // 32 * 32
+        stride = max(stride, 32)
+        mine = self._buf(self.mine, kind, stride)
+        allb = self._buf(self.all, kind, stride * world)
+        shard.shard_export(kind, mine.data_ptr(), stride, self.on_gpu)
+        if self.on_gpu:
+            dist.all_gather_into_tensor(allb[:stride * world], mine[:stride])
+        else:
+            parts = [torch.empty(stride, dtype=torch.uint8) for _ in range(world)]
+            dist.all_gather(parts, mine[:stride])
+            allb[:stride * world] = torch.cat(parts)
+        shard.shard_import(kind, allb.data_ptr(), stride, world, sizes, self.on_gpu)
+        self.bytes_gathered += stride * world
+        return sizes
 
 
-def merge_blobs_numpy(blobs, n_rows):
-    """Reference merge of per-shard blobs (host, numpy): returns (cnt[n_rows], recs in row order).
-    This is what l3d_import_forward does on the device."""
-    rows_pad = (n_rows + 7) // 8 * 8
-    cnts = [np.frombuffer(b, dtype=np.uint32, count=n_rows) for b in blobs]
-    total = np.sum(cnts, axis=0).astype(np.uint32)
-    recs = [np.frombuffer(b, dtype=FWD_DTYPE, offset=rows_pad * 4, count=int(c.sum())) for b, c in zip(blobs, cnts)]
-    offs = [np.concatenate([[0], np.cumsum(c.astype(np.int64))]) for c in cnts]
-    out = np.zeros(int(total.sum()), dtype=FWD_DTYPE)
-    pos = 0
-    for r in range(n_rows):
-        for c, o, rr in zip(cnts, offs, recs):
-            n = int(c[r])
-            if n:
-                out[pos:pos + n] = rr[o[r]:o[r] + n]
-                pos += n
-    return total, out
+def run_sharded(l3, xch, params):
+    """One full pass of stages 1-4 on this rank's slice with the four exchanges."""
+    p = params
+    l3.match_stage12(p["sigma_p"], p["sigma_a"], p["num_neighbors"], p["epipolar_overlap"], p["knn"],
+                     p["const_reg_depth"])
+    xch.exchange(l3, X_FORWARD)
+    l3.score_build()
+    xch.exchange(l3, X_PROGRAMS)
+    l3.score_fold()
+    xch.exchange(l3, X_HYPOTHESES)
+    l3.affinity_edges()
+    xch.exchange(l3, X_EDGES)
+    l3.affinity_ids()
+
+
+class LocalGroup:
+    """Several shards living in one process (tests on one GPU / on the CPU): the same exchange with
+    host buffers instead of a collective."""
+
+    def __init__(self, shards):
+        self.shards = shards
+        self.keep = {}
+
+    def exchange(self, kind):
+        world = len(self.shards)
+        sizes = np.array([s.shard_blob_size(kind) for s in self.shards], dtype=np.uint64)
+        stride = max((int(sizes.max()) + 31) // 32 * 32, 32)
+        buf = np.zeros(stride * world, dtype=np.uint8)
+        for r, s in enumerate(self.shards):
+            s.shard_export(kind, buf[r * stride:].ctypes.data, stride, False)
+        self.keep[kind] = buf
+        for s in self.shards:
+            s.shard_import(kind, buf.ctypes.data, stride, world, sizes, False)
+        return sizes
+
+    def run(self, params):
+        p = params
+        for s in self.shards:
+            s.match_stage12(p["sigma_p"], p["sigma_a"], p["num_neighbors"], p["epipolar_overlap"], p["knn"],
+                            p["const_reg_depth"])
+        self.exchange(X_FORWARD)
+        for s in self.shards:
+            s.score_build()
+        self.exchange(X_PROGRAMS)
+        for s in self.shards:
+            s.score_fold()
+        self.exchange(X_HYPOTHESES)
+        for s in self.shards:
+            s.affinity_edges()
+        self.exchange(X_EDGES)
+        for s in self.shards:
+            s.affinity_ids()

@@ -7,9 +7,9 @@ synthetic scene.
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2]
 
 N=1: BASELINE config[1] (50 views x 1000 segments x 10 neighbours, 640x480).  N>1 (torchrun, one
-process per GPU): the scene grows with N (50*N views, weak scaling); pairs are sharded over the
-ranks for stages 1-2, the forward-match lists are all-gathered with NCCL, stages 3-4 run replicated
-on every rank.
+process per GPU): the scene grows with N (50*N views, weak scaling); every rank owns a contiguous
+slice of reference views (matching, scoring rows, hypotheses, affinity edges), four NCCL
+all-gathers per step make the results whole on every rank.
 """
 import argparse
 import importlib
@@ -181,21 +181,17 @@ def main():
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
 
     sharding = importlib.import_module("3dline-slam_b200.sharding")
-
-    def exchange():
-        """all-gather of the per-shard forward-match lists (NCCL over NVLink)."""
-        return sharding.exchange_forward(l3, dist, torch, dev)
+    xch = sharding.Exchanger(dist, torch, dev) if n_gpus > 1 else None
 
     def step():
         if n_gpus == 1:
             l3.matchImages(prm["sigma_p"], prm["sigma_a"], prm["num_neighbors"], prm["epipolar_overlap"], prm["knn"],
                            prm["const_reg_depth"])
+            l3.affinity()
         else:
-            l3.match_stage12(prm["sigma_p"], prm["sigma_a"], prm["num_neighbors"], prm["epipolar_overlap"],
-                             prm["knn"], prm["const_reg_depth"])
-            exchange()
-            l3.match_stage3()
-        l3.affinity()
+            # view slices per rank; forward matches, fold programs, hypotheses and edges are
+            # all-gathered with NCCL (3dline-slam_b200/sharding.py)
+            sharding.run_sharded(l3, xch, prm)
 
     def barrier():
         if dist is not None:
@@ -244,16 +240,19 @@ def main():
         tests_per_step = float(cnt["pair_tests"])
 
     # ---- separate instrumented passes for the per-stage / K1 numbers (same workload) ----
-    l3.match_stage12(prm["sigma_p"], prm["sigma_a"], prm["num_neighbors"], prm["epipolar_overlap"], prm["knn"],
-                     prm["const_reg_depth"])
-    t12 = l3.timings()
-    c12 = l3.counts()
-    if n_gpus > 1:
-        exchange()
-    l3.match_stage3()
-    t3 = l3.timings()
-    l3.affinity()
-    t4 = l3.timings()
+    if n_gpus == 1:
+        l3.match_stage12(prm["sigma_p"], prm["sigma_a"], prm["num_neighbors"], prm["epipolar_overlap"], prm["knn"],
+                         prm["const_reg_depth"])
+        t12 = l3.timings()
+        c12 = l3.counts()
+        l3.match_stage3()
+        t3 = l3.timings()
+        l3.affinity()
+        t4 = l3.timings()
+    else:
+        step()
+        t12 = t3 = t4 = l3.timings()   # the stage timers accumulate over the phases of one step
+        c12 = l3.counts()
     cfin = l3.counts()
     k1_s = max(t12["k1_kernel"], 1e-9) * 1e-3
     k1_tests = float(c12["pair_tests"])
@@ -350,7 +349,9 @@ def main():
         "config": {"workload": wname, "views": scene.num_views, "segments_per_view": scene.views[0].segs.shape[0],
                    "neighbours": prm["num_neighbors"], "image": "%dx%d" % (scene.views[0].width, scene.views[0].height),
                    "l2": "flushed between timed iterations (256 MB write)",
-                   "parallelism": "pairs sharded over %d rank(s), stages 3-4 replicated" % n_gpus},
+                   "parallelism": ("1 rank" if n_gpus == 1 else
+                                   "%d contiguous view slices: matching, scoring rows, hypotheses and edges per slice; "
+                                   "4 NCCL all-gathers per step; the score fold is replicated" % n_gpus)},
         "views_per_s": views_per_s,
         "stage1_tests_per_s": k1_tests / max((t12["pairtest"] + t12["exact"]) * 1e-3, 1e-9),
         "stage_ms": {"prep": t12["prep"], "k1_pairtest": t12["pairtest"], "k2_exact": t12["exact"],

@@ -82,7 +82,7 @@ typedef struct {
     int32_t max_image_width; /* Line3D::max_image_width_, used by the bounds test line3D.cc:1142-1148 */
     int32_t filter_mode;     /* 0: FP32 guard-banded pre-filter (default); 1: none (every pair exact) */
     int32_t keep_scored;     /* 1: keep the pre-filter lists of every view (parity tests) */
-    int32_t shard_rank;      /* multi-GPU: this process matches the shard_rank-th of shard_world contiguous pair blocks */
+    int32_t shard_rank;      /* multi-GPU: this process owns the shard_rank-th of shard_world contiguous view slices */
     int32_t shard_world;     /* 0 or 1: no sharding */
 } l3d_params;
 
@@ -103,7 +103,7 @@ enum {
     L3D_T_PREP = 0,    /* per-segment descriptors + rays */
     L3D_T_PAIRTEST,    /* K1: FP32 pair test + compaction */
     L3D_T_EXACT,       /* K2: exact re-test, triangulation, kNN, orientation filter */
-    L3D_T_SCORE,       /* K3: list assembly + scoring wavefront + inverse matches + filtering */
+    L3D_T_SCORE,       /* K3: potential lists, similarities, data-flow scoring, filtering */
     L3D_T_AFFINITY,    /* K4 */
     L3D_T_TOTAL,
     L3D_T_K1_KERNEL,   /* sum of K1 kernel launches alone */
@@ -164,9 +164,8 @@ int l3d_scene_commit(l3d_ctx* ctx);
 
 /* replaces Line3D::matchImages (src/line3D.cc:496-640): translate(), spatial regularisers,
  * computeMatches() (matching, orientation filter, scoring, inverse matches, filtering) and the
- * estimated_position3D_ table, all on the device.  Stage-wise variants for multi-GPU runs:
- * l3d_match_stage12 runs matching only (this shard's pairs), l3d_export/import_forward move the
- * forward-match lists between processes, l3d_match_stage3 runs the scoring wavefront. */
+ * estimated_position3D_ table, all on the device.  l3d_match_stage12 runs matching only (this
+ * shard's pairs), l3d_match_stage3 the scoring; see the multi-GPU section for sharded runs. */
 int l3d_match_images(l3d_ctx* ctx, const l3d_params* params);
 int l3d_match_stage12(l3d_ctx* ctx, const l3d_params* params);
 int l3d_match_stage3(l3d_ctx* ctx);
@@ -201,12 +200,26 @@ int l3d_get_cluster_ids(l3d_ctx* ctx, int32_t* out, uint32_t cap);
 int l3d_get_view_info(l3d_ctx* ctx, uint32_t cam_id, double* C, float* kmm);
 int l3d_get_med_scene_depth_lines(l3d_ctx* ctx, float* out);
 
-/* Multi-GPU plumbing (one process per GPU; the collective itself is torch.distributed / NCCL):
- * forward-match lists of this shard as one flat device/host blob of 32-byte records preceded by
- * per-row counts; `device_ptr` != 0 means the pointers are device pointers. */
-int l3d_forward_blob_size(l3d_ctx* ctx, uint64_t* bytes);
-int l3d_export_forward(l3d_ctx* ctx, void* dst, uint64_t cap_bytes, int device_ptr);
-int l3d_import_forward(l3d_ctx* ctx, const void* src, uint64_t bytes, int shard_rank, int device_ptr);
+/* Multi-GPU (one process per GPU; the collective itself is torch.distributed / NCCL).  Reference
+ * views are split into `shard_world` contiguous slices (l3d_params); a rank matches the pairs whose
+ * source view it owns, builds / finishes the scoring rows and the affinity edges of its views, and
+ * four exchanges make the results whole again on every rank:
+ *   l3d_match_stage12 -> FORWARD -> l3d_score_build -> PROGRAMS -> l3d_score_fold -> HYPOTHESES
+ *   -> l3d_affinity_edges -> EDGES -> l3d_affinity_ids (-> l3d_cluster).
+ * Per exchange: every rank calls l3d_shard_blob_size + l3d_shard_export, the blobs are all-gathered
+ * `stride` bytes apart (stride >= the largest size, multiple of 32), every rank calls
+ * l3d_shard_import with all blobs and all sizes.  `device_ptr` != 0: device pointers (they must
+ * stay valid until the next exchange of the same kind).  With one rank l3d_match_stage3 /
+ * l3d_affinity run the same phases back to back. */
+enum { L3D_X_FORWARD = 0, L3D_X_PROGRAMS = 1, L3D_X_HYPOTHESES = 2, L3D_X_EDGES = 3 };
+int l3d_score_build(l3d_ctx* ctx);
+int l3d_score_fold(l3d_ctx* ctx);
+int l3d_affinity_edges(l3d_ctx* ctx);
+int l3d_affinity_ids(l3d_ctx* ctx);
+int l3d_shard_blob_size(l3d_ctx* ctx, int kind, uint64_t* bytes);
+int l3d_shard_export(l3d_ctx* ctx, int kind, void* dst, uint64_t cap_bytes, int device_ptr);
+int l3d_shard_import(l3d_ctx* ctx, int kind, const void* all_blobs, uint64_t stride_bytes, int world,
+                     const uint64_t* sizes, int device_ptr);
 
 /* deterministic device math exposed for parity tests (n values, host pointers) */
 int l3d_test_expf(l3d_ctx* ctx, const float* x, float* y, uint32_t n);

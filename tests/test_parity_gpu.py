@@ -78,31 +78,29 @@ def test_device_math_bit_exact(api, oracle):
     assert (gotd.view(np.uint64) == expd.view(np.uint64)).all()
 
 
-def test_sharded_stage12_merges_to_the_same_result(api, oracle, scene_mod):
-    """Two shard contexts on one GPU (two contiguous pair blocks): export, merge, import -> stage 3/4 results
-    identical to the unsharded run and to the oracle."""
-    import ctypes as C
-    sc = scene_mod.make_scene("tiny", seed=31, n_views=7, n_seg=140, nbrs=4)
-    p = sc.params
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_run_matches_the_oracle(api, oracle, scene_mod, world):
+    """`world` shard contexts on one GPU (contiguous view slices): matching, scoring rows, hypotheses
+    and edges are computed per slice and exchanged (host buffers); every rank ends with the result
+    of the unsharded run = the oracle's, bit for bit."""
+    import importlib
+    shd = importlib.import_module("3dline-slam_b200.sharding")
+    sc = scene_mod.make_scene("tiny", seed=31, n_views=9, n_seg=140, nbrs=4)
     shards = []
-    for r in range(2):
+    for r in range(world):
         l3 = api.Line3D("", False, sc.max_image_width)
-        l3.keep_scored = True
-        l3.shard = (r, 2)
+        l3.keep_scored = False
+        l3.shard = (r, world)
         l3.load_scene(sc)
-        l3.match_stage12(p["sigma_p"], p["sigma_a"], p["num_neighbors"], p["epipolar_overlap"], p["knn"],
-                         p["const_reg_depth"])
         shards.append(l3)
-    sizes = [s.forward_blob_size() for s in shards]
-    stride = (max(sizes) + 31) // 32 * 32
-    buf = np.zeros(2 * stride, dtype=np.uint8)
-    for r, s in enumerate(shards):
-        s.export_forward(buf[r * stride:].ctypes.data, stride, False)
-    total_tests = sum(s.counts()["pair_tests"] for s in shards)
+    shd.LocalGroup(shards).run(sc.params)
     orc = oracle.run_scene(sc)
-    assert total_tests == orc.pair_tests()
+    assert sum(s.counts()["pair_tests"] for s in shards) == orc.pair_tests()
+    assert sum(s.counts()["num_pairs_local"] for s in shards) == len(orc.pairs())
+    ref = api.run_scene(sc, reconstruct=False)
     for s in shards:
-        s.import_forward(buf.ctypes.data, stride, 2, False)
-        s.match_stage3()
-        s.reconstruct3Dlines()
-        compare_full(s, orc, sc)
+        s._ck(s.L.l3d_cluster(s.h))
+        sizes = compare_full(s, orc, sc, check_scored=False)
+        assert sizes["edges"] > 0 and sizes["clusters"] > 1
+        for k in ("forward_matches", "scored_entries", "sim_evals", "filtered_entries", "num_entries"):
+            assert s.counts()[k] == ref.counts()[k], k

@@ -1,5 +1,7 @@
-"""CPU, world_size 2 over gloo: the host-side exchange of the per-shard forward-match lists
-(all-gather-v by padding + merge into the canonical row order)."""
+"""CPU, world_size 2 over gloo: the host-side exchange logic of a sharded run (sizes all-gather,
+all-gather-v by padding, import with every rank's blob and size), with fake shards standing in for
+the GPU contexts."""
+import ctypes
 import importlib
 import os
 import socket
@@ -13,39 +15,34 @@ shd = importlib.import_module("3dline-slam_b200.sharding")
 
 
 class FakeShard:
-    """Stands in for api.Line3D on a box without a GPU: owns rows r with (r // 3) % world == rank."""
+    """Stands in for api.Line3D on a box without a GPU: every exchange kind carries a blob whose
+    length and content depend on (rank, kind); import checks that all blobs arrive intact."""
 
-    def __init__(self, rank, world, n_rows=37):
-        self.rank, self.world, self.n_rows = rank, world, n_rows
-        rng = np.random.default_rng(123)            # same stream on every rank: the "global truth"
-        self.cnt_all = rng.integers(0, 4, size=n_rows).astype(np.uint32)
-        self.recs_all = np.zeros(int(self.cnt_all.sum()), dtype=shd.FWD_DTYPE)
-        self.recs_all["c"] = np.arange(len(self.recs_all))
-        self.recs_all["overlap"] = rng.random(len(self.recs_all)).astype(np.float32)
-        own = (np.arange(n_rows) // 3) % world == rank
-        self.cnt = np.where(own, self.cnt_all, 0).astype(np.uint32)
-        off = np.concatenate([[0], np.cumsum(self.cnt_all.astype(np.int64))])
-        self.recs = np.concatenate([self.recs_all[off[r]:off[r + 1]] for r in range(n_rows) if own[r]] or
-                                   [np.zeros(0, dtype=shd.FWD_DTYPE)])
-        self.merged = None
+    def __init__(self, rank, world):
+        self.rank, self.world = rank, world
+        self.seen = {}
 
-    def forward_blob_size(self):
-        return (self.n_rows + 7) // 8 * 8 * 4 + self.recs.nbytes
+    @staticmethod
+    def blob(rank, kind):
+        rng = np.random.default_rng(1000 * kind + rank)
+        return rng.integers(0, 256, size=37 + 101 * rank + 13 * kind, dtype=np.uint8)
 
-    def export_forward(self, ptr, cap, device_ptr):
-        assert not device_ptr and cap >= self.forward_blob_size()
-        buf = (np.ctypeslib.as_array((__import__("ctypes").c_uint8 * cap).from_address(ptr)))
-        rows_pad = (self.n_rows + 7) // 8 * 8
-        head = np.zeros(rows_pad, dtype=np.uint32)
-        head[:self.n_rows] = self.cnt
-        blob = head.tobytes() + self.recs.tobytes()
-        buf[:len(blob)] = np.frombuffer(blob, dtype=np.uint8)
+    def shard_blob_size(self, kind):
+        return int(self.blob(self.rank, kind).size)
 
-    def import_forward(self, ptr, stride, world, device_ptr):
-        assert not device_ptr
-        raw = bytes((__import__("ctypes").c_uint8 * (stride * world)).from_address(ptr))
-        blobs = [raw[i * stride:(i + 1) * stride] for i in range(world)]
-        self.merged = shd.merge_blobs_numpy(blobs, self.n_rows)
+    def shard_export(self, kind, ptr, cap, device_ptr):
+        b = self.blob(self.rank, kind)
+        assert not device_ptr and cap >= b.size
+        np.ctypeslib.as_array((ctypes.c_uint8 * cap).from_address(ptr))[:b.size] = b
+
+    def shard_import(self, kind, ptr, stride, world, sizes, device_ptr):
+        assert not device_ptr and world == self.world and stride % 32 == 0
+        raw = np.ctypeslib.as_array((ctypes.c_uint8 * (stride * world)).from_address(ptr))
+        ok = True
+        for q in range(world):
+            b = self.blob(q, kind)
+            ok &= int(sizes[q]) == b.size and bool((raw[q * stride:q * stride + b.size] == b).all())
+        self.seen[kind] = ok
 
 
 def _worker(rank, world, port, q):
@@ -53,14 +50,15 @@ def _worker(rank, world, port, q):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     s = FakeShard(rank, world)
-    shd.exchange_forward(s, dist, torch, torch.device("cpu"))
-    cnt, recs = s.merged
-    ok = bool((cnt == s.cnt_all).all() and recs.tobytes() == s.recs_all.tobytes())
-    q.put((rank, ok, int(cnt.sum())))
+    xch = shd.Exchanger(dist, torch, torch.device("cpu"))
+    for rep in range(2):                    # buffers persist and are reused
+        for kind in (shd.X_FORWARD, shd.X_PROGRAMS, shd.X_HYPOTHESES, shd.X_EDGES):
+            xch.exchange(s, kind)
+    q.put((rank, all(s.seen.get(k, False) for k in range(4)), xch.bytes_gathered))
     dist.destroy_process_group()
 
 
-def test_exchange_forward_world2_gloo():
+def test_exchanger_world2_gloo():
     with socket.socket() as sk:
         sk.bind(("127.0.0.1", 0))
         port = sk.getsockname()[1]
@@ -75,3 +73,11 @@ def test_exchange_forward_world2_gloo():
     assert sorted(r[0] for r in res) == [0, 1]
     assert all(r[1] for r in res), res
     assert res[0][2] == res[1][2] > 0
+
+
+def test_local_group_uses_the_same_protocol():
+    shards = [FakeShard(r, 3) for r in range(3)]
+    g = shd.LocalGroup(shards)
+    for kind in range(4):
+        g.exchange(kind)
+    assert all(all(s.seen[k] for k in range(4)) for s in shards)
