@@ -67,19 +67,31 @@ class Exchanger:
         return sizes
 
 
-def run_sharded(l3, xch, params):
-    """One full pass of stages 1-4 on this rank's slice with the four exchanges."""
+def run_sharded(l3, xch, params, trace=None):
+    """One full pass of stages 1-4 on this rank's slice with the four exchanges.
+    trace: optional dict, receives the wall time of every phase (adds a device sync per phase)."""
     p = params
-    l3.match_stage12(p["sigma_p"], p["sigma_a"], p["num_neighbors"], p["epipolar_overlap"], p["knn"],
-                     p["const_reg_depth"])
-    xch.exchange(l3, X_FORWARD)
-    l3.score_build()
-    xch.exchange(l3, X_PROGRAMS)
-    l3.score_fold()
-    xch.exchange(l3, X_HYPOTHESES)
-    l3.affinity_edges()
-    xch.exchange(l3, X_EDGES)
-    l3.affinity_ids()
+    steps = [("match_stage12", lambda: l3.match_stage12(p["sigma_p"], p["sigma_a"], p["num_neighbors"],
+                                                        p["epipolar_overlap"], p["knn"], p["const_reg_depth"])),
+             ("x_forward", lambda: xch.exchange(l3, X_FORWARD)),
+             ("score_build", l3.score_build),
+             ("x_programs", lambda: xch.exchange(l3, X_PROGRAMS)),
+             ("score_fold", l3.score_fold),
+             ("x_hypotheses", lambda: xch.exchange(l3, X_HYPOTHESES)),
+             ("affinity_edges", l3.affinity_edges),
+             ("x_edges", lambda: xch.exchange(l3, X_EDGES)),
+             ("affinity_ids", l3.affinity_ids)]
+    if trace is None:
+        for _, fn in steps:
+            fn()
+        return
+    import time
+    for name, fn in steps:
+        t0 = time.perf_counter()
+        fn()
+        if xch.on_gpu:
+            xch.torch.cuda.synchronize(xch.device)
+        trace[name] = trace.get(name, 0.0) + (time.perf_counter() - t0)
 
 
 class LocalGroup:

@@ -144,6 +144,7 @@ def main():
     ap.add_argument("--workload", default="c2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--check", action="store_true", help="also verify the result against the CPU oracle")
+    ap.add_argument("--trace-phases", action="store_true", help="N>1: wall time per phase/exchange (stderr)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -254,6 +255,14 @@ def main():
         t12 = t3 = t4 = l3.timings()   # the stage timers accumulate over the phases of one step
         c12 = l3.counts()
     cfin = l3.counts()
+    if args.trace_phases and n_gpus > 1:
+        tr = {}
+        for _ in range(10):
+            barrier()
+            sharding.run_sharded(l3, xch, prm, trace=tr)
+        if rank == 0:
+            print("phase ms (rank 0, synchronised after every phase): " +
+                  ", ".join("%s %.3f" % (k, 1e2 * v) for k, v in tr.items()), file=sys.stderr)
     k1_s = max(t12["k1_kernel"], 1e-9) * 1e-3
     k1_tests = float(c12["pair_tests"])
 
