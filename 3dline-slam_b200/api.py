@@ -120,6 +120,8 @@ def lib():
         L.l3d_shard_blob_size.argtypes = [vp, C.c_int, C.POINTER(u64)]
         L.l3d_shard_export.argtypes = [vp, C.c_int, vp, u64, C.c_int]
         L.l3d_shard_import.argtypes = [vp, C.c_int, vp, u64, C.c_int, vp, C.c_int]
+        L.l3d_shard_export_hdr.argtypes = [vp, C.c_int, vp, u64]
+        L.l3d_shard_import_hdr.argtypes = [vp, C.c_int, vp, u64, C.c_int, vp, C.POINTER(C.c_int)]
         L.l3d_test_expf.argtypes = [vp, vp, vp, u32]
         L.l3d_test_acos.argtypes = [vp, vp, vp, u32]
         L.l3d_bench_fp32_peak.argtypes = [vp, vp]
@@ -414,6 +416,18 @@ class Line3D:
         sz = np.ascontiguousarray(sizes, dtype=np.uint64)
         self._ck(self.L.l3d_shard_import(self.h, int(kind), C.c_void_p(ptr), stride_bytes, int(world), _p(sz),
                                          int(device_ptr)))
+
+
+    def shard_export_hdr(self, kind, ptr, stride_bytes):
+        self._ck(self.L.l3d_shard_export_hdr(self.h, int(kind), C.c_void_p(ptr), stride_bytes))
+
+    def shard_import_hdr(self, kind, ptr, stride_bytes, world):
+        """Returns (redo, sizes): redo=True means nothing was imported (a blob did not fit)."""
+        sz = np.zeros(world, dtype=np.uint64)
+        redo = C.c_int(0)
+        self._ck(self.L.l3d_shard_import_hdr(self.h, int(kind), C.c_void_p(ptr), stride_bytes, int(world), _p(sz),
+                                             C.byref(redo)))
+        return bool(redo.value), sz
 
 
 X_FORWARD, X_PROGRAMS, X_HYPOTHESES, X_EDGES = 0, 1, 2, 3

@@ -281,18 +281,10 @@ int l3d_shard_blob_size(l3d_ctx* ctx, int kind, uint64_t* bytes)
     return L3D_OK;
 }
 
-int l3d_shard_export(l3d_ctx* ctx, int kind, void* dst, uint64_t cap_bytes, int device_ptr)
+// payload of this rank's blob; n_var = elements of the variable part to copy
+static int export_payload(l3d_ctx* ctx, int kind, unsigned char* d, uint64_t n, cudaMemcpyKind ck)
 {
-    int rc = check_phase(ctx, kind);
-    if (rc) return rc;
-    if (!dst) return fail(L3D_ERR_ARG, "NULL argument");
-    CK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
-    const uint64_t n = ctx->xchg_var[kind];
-    const uint64_t need = blob_fixed_bytes(ctx, kind, ctx->rank) + n * var_elem_bytes(kind);
-    if (cap_bytes < need) return fail(L3D_ERR_CAPACITY, "need %llu bytes", (unsigned long long)need);
-    const cudaMemcpyKind ck = device_ptr ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
-    unsigned char* d = (unsigned char*)dst;
     const uint32_t rows = slice_rows(ctx, kind, ctx->rank);
     switch (kind) {
     case L3D_X_FORWARD: {
@@ -324,15 +316,82 @@ int l3d_shard_export(l3d_ctx* ctx, int kind, void* dst, uint64_t cap_bytes, int 
             CK(cudaMemcpyAsync(p + rp * 4, ctx->d_filt_off.p + g0, (size_t)rows * 4, ck, st));
             CK(cudaMemcpyAsync(p + 2 * rp * 4, ctx->d_entries.p + g0, (size_t)rows * sizeof(EntryDev), ck, st));
         }
-        if (n) CK(cudaMemcpyAsync(p + 2 * rp * 4 + (size_t)rows * sizeof(EntryDev), ctx->d_filt_rec.p, n * sizeof(ListRec), ck, st));
+        if (n)
+            CK(cudaMemcpyAsync(p + 2 * rp * 4 + (size_t)rows * sizeof(EntryDev), ctx->d_filt_rec.p, n * sizeof(ListRec),
+                               ck, st));
         break;
     }
     case L3D_X_EDGES:
         if (n) CK(cudaMemcpyAsync(d, ctx->d_edges.p, n * 12, ck, st));
         break;
     }
-    if (!device_ptr) CK(cudaStreamSynchronize(st));
     return L3D_OK;
+}
+
+int l3d_shard_export(l3d_ctx* ctx, int kind, void* dst, uint64_t cap_bytes, int device_ptr)
+{
+    int rc = check_phase(ctx, kind);
+    if (rc) return rc;
+    if (!dst) return fail(L3D_ERR_ARG, "NULL argument");
+    CK(cudaSetDevice(ctx->device));
+    const uint64_t n = ctx->xchg_var[kind];
+    const uint64_t need = blob_fixed_bytes(ctx, kind, ctx->rank) + n * var_elem_bytes(kind);
+    if (cap_bytes < need) return fail(L3D_ERR_CAPACITY, "need %llu bytes", (unsigned long long)need);
+    rc = export_payload(ctx, kind, (unsigned char*)dst, n, device_ptr ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost);
+    if (rc) return rc;
+    if (!device_ptr) CK(cudaStreamSynchronize(ctx->stream));
+    return L3D_OK;
+}
+
+// ---- self-describing blobs (device pointers only): {ShardBlobHdr | payload}.  The sender does not
+// wait for its cursors: the header is written by the device, the variable part is copied up to what
+// the stride holds.  Every receiver reads all headers; a blob that did not fit (or an overflowed
+// program store) makes every rank fall back to the size exchange. ----
+struct ShardBlobHdr {
+    unsigned long long payload_bytes;
+    uint32_t flags;  // WfStats::err of the sender
+    uint32_t kind;
+    unsigned long long pad[2];
+};
+static_assert(sizeof(ShardBlobHdr) == 32, "blob header must be 32 bytes");
+
+namespace l3d {
+int launch_blob_hdr(void* dst, uint64_t fixed_bytes, uint64_t elem_bytes, const uint32_t* n_dev, uint64_t n_imm,
+                    const uint32_t* flags_dev, uint32_t kind, cudaStream_t st);
+}
+
+int l3d_shard_export_hdr(l3d_ctx* ctx, int kind, void* dst, uint64_t stride_bytes)
+{
+    int rc = check_phase(ctx, kind);
+    if (rc) return rc;
+    if (!dst) return fail(L3D_ERR_ARG, "NULL argument");
+    CK(cudaSetDevice(ctx->device));
+    const uint64_t fixed = blob_fixed_bytes(ctx, kind, ctx->rank), eb = var_elem_bytes(kind);
+    if (stride_bytes % 32 || stride_bytes < sizeof(ShardBlobHdr))
+        return fail(L3D_ERR_CAPACITY, "stride %llu too small", (unsigned long long)stride_bytes);
+    // a stride that cannot even hold the fixed part: send the header alone, the receivers fall back
+    const bool header_only = stride_bytes < sizeof(ShardBlobHdr) + fixed;
+    uint64_t room = header_only ? 0 : (stride_bytes - sizeof(ShardBlobHdr) - fixed) / eb, have = 0;
+    const uint32_t* n_dev = nullptr;
+    const uint32_t* f_dev = nullptr;
+    switch (kind) {
+    case L3D_X_FORWARD: have = ctx->local_fwd; break;
+    case L3D_X_EDGES: have = ctx->n_edges_local; break;
+    case L3D_X_PROGRAMS:
+        have = ctx->prog_cap;
+        n_dev = (const uint32_t*)(ctx->d_stats.p + 28);
+        f_dev = (const uint32_t*)(ctx->d_stats.p + 24);
+        break;
+    case L3D_X_HYPOTHESES:
+        have = ctx->filt_cap;
+        n_dev = (const uint32_t*)(ctx->d_stats.p + 20);
+        f_dev = (const uint32_t*)(ctx->d_stats.p + 24);
+        break;
+    }
+    ctx->cnt.gpu_launches += launch_blob_hdr(dst, fixed, eb, n_dev, have, f_dev, (uint32_t)kind, ctx->stream);
+    if (header_only) return L3D_OK;
+    return export_payload(ctx, kind, (unsigned char*)dst + sizeof(ShardBlobHdr), std::min(room, have),
+                          cudaMemcpyDeviceToDevice);
 }
 
 // all: `world` blobs `stride_bytes` apart (own blob included); sizes[q] = l3d_shard_blob_size of rank q.
@@ -440,4 +499,29 @@ int l3d_shard_import(l3d_ctx* ctx, int kind, const void* all, uint64_t stride_by
     }
     }
     return fail(L3D_ERR_ARG, "unknown exchange kind %d", kind);
+}
+
+// sizes_out[q] = payload bytes of rank q; *redo != 0: some blob did not fit / some program store
+// overflowed -- nothing was imported, every rank must repeat the exchange with l3d_shard_blob_size
+int l3d_shard_import_hdr(l3d_ctx* ctx, int kind, const void* all, uint64_t stride_bytes, int world, uint64_t* sizes_out,
+                         int* redo)
+{
+    int rc = check_phase(ctx, kind);
+    if (rc) return rc;
+    if (!all || !sizes_out || !redo) return fail(L3D_ERR_ARG, "NULL argument");
+    if (world != ctx->world || world > L3D_MAX_WORLD) return fail(L3D_ERR_ARG, "world %d does not match the plan", world);
+    CK(cudaSetDevice(ctx->device));
+    ShardBlobHdr hdr[L3D_MAX_WORLD];
+    CK(cudaMemcpy2DAsync(hdr, sizeof(ShardBlobHdr), all, stride_bytes, sizeof(ShardBlobHdr), (size_t)world,
+                         cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    *redo = 0;
+    for (int q = 0; q < world; ++q) {
+        if (hdr[q].kind != (uint32_t)kind) return fail(L3D_ERR_ARG, "blob %d is of kind %u, expected %d", q, hdr[q].kind, kind);
+        sizes_out[q] = hdr[q].payload_bytes;
+        if (hdr[q].payload_bytes + sizeof(ShardBlobHdr) > stride_bytes) *redo = 1;
+        if (kind == L3D_X_PROGRAMS && (hdr[q].flags & 4u)) *redo = 1;
+    }
+    if (*redo) return L3D_OK;
+    return l3d_shard_import(ctx, kind, (const unsigned char*)all + sizeof(ShardBlobHdr), stride_bytes, world, sizes_out, 1);
 }

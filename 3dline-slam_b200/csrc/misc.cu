@@ -119,6 +119,23 @@ int launch_score_prep(const float4* lines, uint32_t n_lines, const float4* match
     return 1;
 }
 
+// header of a self-describing exchange blob (abi.cu): payload size from the device-side cursor
+__global__ void blob_hdr_kernel(unsigned long long* dst, uint64_t fixed_bytes, uint64_t elem_bytes,
+                                const uint32_t* n_dev, uint64_t n_imm, const uint32_t* flags_dev, uint32_t kind)
+{
+    const uint64_t n = n_dev ? (uint64_t)*n_dev : n_imm;
+    dst[0] = fixed_bytes + n * elem_bytes;
+    dst[1] = (uint64_t)(flags_dev ? *flags_dev : 0u) | ((uint64_t)kind << 32);
+    dst[2] = 0;
+    dst[3] = 0;
+}
+int launch_blob_hdr(void* dst, uint64_t fixed_bytes, uint64_t elem_bytes, const uint32_t* n_dev, uint64_t n_imm,
+                    const uint32_t* flags_dev, uint32_t kind, cudaStream_t st)
+{
+    blob_hdr_kernel<<<1, 1, 0, st>>>((unsigned long long*)dst, fixed_bytes, elem_bytes, n_dev, n_imm, flags_dev, kind);
+    return 1;
+}
+
 // multi-GPU: adopt the all-gathered hypotheses (abi.cu, L3D_X_HYPOTHESES): entries, filtered-list
 // counts and offsets of every row, and the filtered records of every slice packed into one store
 struct HypHdr32 {

@@ -7,9 +7,12 @@ on the GPU box, gloo in the CPU tests) make every result whole on every rank:
     match_stage12 -> FORWARD -> score_build -> PROGRAMS -> score_fold -> HYPOTHESES
                   -> affinity_edges -> EDGES -> affinity_ids
 
-Each exchange is an all-gather-v by padding: the blob sizes are gathered first (8 bytes per rank),
-then the blobs, `stride` bytes apart, into a buffer that persists between steps (the fold programs
-are read in place by the next phase).  The blob layouts are documented in csrc/abi.cu.
+Each exchange is an all-gather-v by padding into a buffer that persists between steps (the fold
+programs are read in place by the next phase).  The first time, the blob sizes are gathered first
+(8 bytes per rank) to fix the stride; afterwards the blobs describe themselves (32-byte header
+written by the device), the stride of the previous step is reused and the size exchange -- and the
+sender's wait for its own cursors -- disappears; a blob that does not fit makes every rank fall
+back to the size exchange for that step.  The blob layouts are documented in csrc/abi.cu.
 """
 from __future__ import annotations
 
@@ -28,6 +31,8 @@ class Exchanger:
         self.on_gpu = device.type == "cuda"
         self.mine = {}
         self.all = {}
+        self.stride = {}       # kind -> stride of the self-describing exchange
+        self.fallbacks = 0
         self.bytes_gathered = 0
 
     def _buf(self, store, kind, nbytes):
@@ -41,6 +46,19 @@ class Exchanger:
         """shard offers shard_blob_size(kind) / shard_export(kind, ptr, cap, device_ptr) /
         shard_import(kind, ptr, stride, world, sizes, device_ptr) (api.Line3D does)."""
         torch, dist, world = self.torch, self.dist, self.world
+        if self.on_gpu and kind in self.stride and hasattr(shard, "shard_export_hdr"):
+            stride = self.stride[kind]
+            mine = self._buf(self.mine, kind, stride)
+            allb = self._buf(self.all, kind, stride * world)
+            shard.shard_export_hdr(kind, mine.data_ptr(), stride)
+            dist.all_gather_into_tensor(allb[:stride * world], mine[:stride])
+            redo, sizes = shard.shard_import_hdr(kind, allb.data_ptr(), stride, world)
+            self.bytes_gathered += stride * world
+            if not redo:
+                if int(sizes.max()) * 2 < stride:      # the blobs shrank a lot: tighten the stride
+                    self.stride[kind] = self._stride_for(int(sizes.max()))
+                return sizes
+            self.fallbacks += 1
         nbytes = shard.shard_blob_size(kind)
         sz = torch.tensor([nbytes], dtype=torch.int64, device=self.device)
         if self.on_gpu:
@@ -64,7 +82,13 @@ class Exchanger:
             allb[:stride * world] = torch.cat(parts)
         shard.shard_import(kind, allb.data_ptr(), stride, world, sizes, self.on_gpu)
         self.bytes_gathered += stride * world
+        self.stride[kind] = self._stride_for(int(sizes.max()))
         return sizes
+
+    @staticmethod
+    def _stride_for(max_payload):
+        """Stride of the self-describing exchange: 25 % head room over the largest blob seen."""
+        return (int(max_payload * 1.25) + 64 + 32 + 31) // 32 * 32
 
 
 def run_sharded(l3, xch, params, trace=None):
@@ -98,12 +122,26 @@ class LocalGroup:
     """Several shards living in one process (tests on one GPU / on the CPU): the same exchange with
     host buffers instead of a collective."""
 
-    def __init__(self, shards):
+    def __init__(self, shards, torch=None, device=None):
         self.shards = shards
         self.keep = {}
+        self.torch, self.device = torch, device   # given: also exercise the self-describing exchange
+        self.stride = {}
+        self.fallbacks = 0
 
     def exchange(self, kind):
         world = len(self.shards)
+        if self.torch is not None and kind in self.stride:
+            stride = self.stride[kind]
+            buf = self.torch.zeros(stride * world, dtype=self.torch.uint8, device=self.device)
+            for r, s in enumerate(self.shards):
+                s.shard_export_hdr(kind, buf.data_ptr() + r * stride, stride)
+            self.keep[kind] = buf
+            res = [s.shard_import_hdr(kind, buf.data_ptr(), stride, world) for s in self.shards]
+            assert len({r[0] for r in res}) == 1, "ranks disagree on redo"
+            if not res[0][0]:
+                return res[0][1]
+            self.fallbacks += 1
         sizes = np.array([s.shard_blob_size(kind) for s in self.shards], dtype=np.uint64)
         stride = max((int(sizes.max()) + 31) // 32 * 32, 32)
         buf = np.zeros(stride * world, dtype=np.uint8)
@@ -112,6 +150,7 @@ class LocalGroup:
         self.keep[kind] = buf
         for s in self.shards:
             s.shard_import(kind, buf.ctypes.data, stride, world, sizes, False)
+        self.stride[kind] = Exchanger._stride_for(int(sizes.max()))
         return sizes
 
     def run(self, params):

@@ -220,6 +220,13 @@ int l3d_shard_blob_size(l3d_ctx* ctx, int kind, uint64_t* bytes);
 int l3d_shard_export(l3d_ctx* ctx, int kind, void* dst, uint64_t cap_bytes, int device_ptr);
 int l3d_shard_import(l3d_ctx* ctx, int kind, const void* all_blobs, uint64_t stride_bytes, int world,
                      const uint64_t* sizes, int device_ptr);
+/* Steady-state variant without the size exchange (device pointers only): the blob carries a 32-byte
+ * header with its own size, written by the device, so the sender never waits for its cursors; the
+ * stride comes from the previous step.  *redo != 0 after the import: a blob did not fit -- nothing
+ * was imported and every rank repeats the exchange with the three calls above. */
+int l3d_shard_export_hdr(l3d_ctx* ctx, int kind, void* dst, uint64_t stride_bytes);
+int l3d_shard_import_hdr(l3d_ctx* ctx, int kind, const void* all_blobs, uint64_t stride_bytes, int world,
+                         uint64_t* sizes_out, int* redo);
 
 /* deterministic device math exposed for parity tests (n values, host pointers) */
 int l3d_test_expf(l3d_ctx* ctx, const float* x, float* y, uint32_t n);

@@ -93,7 +93,14 @@ def test_sharded_run_matches_the_oracle(api, oracle, scene_mod, world):
         l3.shard = (r, world)
         l3.load_scene(sc)
         shards.append(l3)
-    shd.LocalGroup(shards).run(sc.params)
+    import torch
+    grp = shd.LocalGroup(shards, torch, torch.device("cuda", 0))
+    grp.run(sc.params)          # first pass: size exchange + host buffers
+    grp.run(sc.params)          # second pass: self-describing blobs in device buffers
+    assert grp.fallbacks == 0
+    grp.stride[shd.X_PROGRAMS] = 64   # far too small: every rank must detect it and fall back
+    grp.run(sc.params)
+    assert grp.fallbacks == 1
     orc = oracle.run_scene(sc)
     assert sum(s.counts()["pair_tests"] for s in shards) == orc.pair_tests()
     assert sum(s.counts()["num_pairs_local"] for s in shards) == len(orc.pairs())
