@@ -226,6 +226,7 @@ struct BuildArgs {
     WfStats* stats;
     uint32_t S;
     uint32_t g_lo, g_hi;  // rows built by this rank (global segment indices)
+    uint32_t m_lo, m_hi;  // this launch builds the rows with m_lo < length <= m_hi
     uint32_t maxm;
     float two_sigA_sqr;
     float dotcut;  // see score_core.cuh
@@ -251,8 +252,9 @@ __device__ __forceinline__ bool pair_flagged(const Sib& M, bool Mok, float t1, f
     return Mok & ((S2.flags & 2u) != 0) & (S2.cam != M.cam) & !rej;
 }
 
-static constexpr int DF_MASKM = 256;            // rows up to this length keep their flag bits
-static constexpr int DF_MASKW = DF_MASKM / 32;  // in shared memory between the count and emit passes
+static constexpr int DF_MASKM = 256;  // rows up to this length keep their flag bits in shared memory
+                                      // between the count and emit passes (maskw words per entry)
+static constexpr int DF_SMALL = 128;  // rows up to this length are built by a launch with small staging
 
 __global__ void __launch_bounds__(DF_THREADS) k3_build_kernel(const BuildArgs a)
 {
@@ -261,6 +263,13 @@ __global__ void __launch_bounds__(DF_THREADS) k3_build_kernel(const BuildArgs a)
     __shared__ uint32_t s_tot[2], s_base;
     const uint32_t g = a.g_lo + blockIdx.x;
     if (g >= a.g_hi) return;
+    {
+        const uint32_t len = a.L_off[g + 1] - a.L_off[g];
+        if (len <= a.m_lo || len > a.m_hi) {
+            if (len == 0 && a.m_lo == 0 && threadIdx.x == 0) a.prog_nh[g] = 0u;
+            return;  // another launch (or nothing) handles this row
+        }
+    }
     const uint32_t v = a.seg_view[g];
     const ViewDev& va = a.views[v];
     const uint32_t i = g - va.seg_off;
@@ -274,8 +283,12 @@ __global__ void __launch_bounds__(DF_THREADS) k3_build_kernel(const BuildArgs a)
     Sib* sm_sib = reinterpret_cast<Sib*>(sm_dir + 3 * (size_t)maxm);
     float2* sm_reg = reinterpret_cast<float2*>(sm_sib + maxm);
     uint32_t* sm_c = reinterpret_cast<uint32_t*>(sm_reg + maxm);
-    uint32_t* sm_h = sm_c + (maxm + 1);
-    uint32_t* sm_mask = sm_h + (maxm + 1);  // min(maxm, DF_MASKM) x DF_MASKW words
+    uint32_t* sm_h = sm_c + (maxm + 2);
+    uint32_t* sm_mask = sm_h + (maxm + 2);  // maskm x maskw words (16-byte aligned: maxm is a multiple of 4)
+    const uint32_t maskm = maxm < (uint32_t)DF_MASKM ? maxm : (uint32_t)DF_MASKM;
+    const uint32_t maskw = (maskm + 31u) >> 5;
+    uint32_t* sm_ukey = sm_mask + (((size_t)maskm * maskw + 3) & ~(size_t)3);  // depth keys, list order
+    uint32_t* sm_skey = sm_ukey + ((maskm + 3u) & ~3u);                          // sorted ascending
 
     // block table (n_inc <= DF_MAXINC is checked on the host)
     if (tid < (int)n_inc) {
@@ -373,38 +386,64 @@ __global__ void __launch_bounds__(DF_THREADS) k3_build_kernel(const BuildArgs a)
     __threadfence_block();
     __syncthreads();
 
-    // ---- count the (M, sibling) pairs that need the full similarity ----
+    // ---- find the (M, sibling) pairs that need the full similarity ----
+    // Rows staged in shared memory: the entries are ranked by their first depth, so the siblings that
+    // can pass |d_p1 - d_p1'| <= t1 form a window of the sorted order (found by binary search); only
+    // they get the complete cheap test.  Flag bits are kept for the emit pass.
     const bool use_mask = m <= (uint32_t)DF_MASKM && m <= maxm;
+    if (use_mask) {
+        // key = bits of the (positive) first depth with the list position in the low byte: unique,
+        // ordered like the depths up to 256 ulps (the window below is widened by more than that);
+        // invalid 3-D segments sort last
+        for (uint32_t e = tid; e < m; e += DF_THREADS) {
+            const Sib sb = sm_sib[e];
+            const uint32_t kb = (sb.flags & 2u) ? (__float_as_uint(fmaxf(sb.d_p1, 0.0f)) & 0xffffff00u) : 0x7f800000u;
+            sm_ukey[e] = kb | e;
+        }
+        __syncthreads();
+        for (uint32_t e = tid; e < m; e += DF_THREADS) {
+            const uint32_t ke = sm_ukey[e];
+            uint32_t r = 0;
+            uint32_t j = 0;
+            for (; j + 4 <= m; j += 4) {  // sm_ukey is 16-byte aligned
+                const uint4 k4 = *reinterpret_cast<const uint4*>(sm_ukey + j);
+                r += (k4.x < ke) + (k4.y < ke) + (k4.z < ke) + (k4.w < ke);
+            }
+            for (; j < m; ++j) r += sm_ukey[j] < ke;
+            sm_skey[r] = ke;
+        }
+        __syncthreads();
+    }
     for (uint32_t e = tid; e < m; e += DF_THREADS) {
         const Sib M = sib[e];
         const float2 rg = regs[e];
         const float t1 = reject_threshold(rg.x), t2 = reject_threshold(rg.y);
         const bool Mok = (M.flags & 2u) != 0;
         uint32_t c = 0;
-        if (!Mok) {  // an invalid 3-D segment has similarity 0 with everything
-            if (use_mask)
-                for (uint32_t w = 0; w < ((m + 31) >> 5); ++w) sm_mask[e * DF_MASKW + w] = 0u;
-            cnt[e] = 0;
-            continue;
-        }
-        if (use_mask) {  // shared-memory staging: typed pointers, constant bit positions
-            const uint32_t full = m >> 5;
-            for (uint32_t w = 0; w < full; ++w) {
-                uint32_t bits = 0;
-                const Sib* __restrict__ sw = sm_sib + (w << 5);
-#pragma unroll
-                for (uint32_t jj = 0; jj < 32; ++jj) bits |= (pair_flagged(M, Mok, t1, t2, sw[jj]) ? 1u : 0u) << jj;
-                sm_mask[e * DF_MASKW + w] = bits;
-                c += __popc(bits);
+        if (use_mask) {
+            const uint32_t words = (m + 31) >> 5;
+            for (uint32_t w = 0; w < words; ++w) sm_mask[e * maskw + w] = 0u;
+            if (Mok) {
+                // window of first depths that can pass, widened beyond every rounding of the test and
+                // of the key (256 ulps = 1.6e-5 relative)
+                const float slack = fmaf(1.0e-4f, t1, 1.0e-4f * fabsf(M.d_p1));
+                const float flo = fmaxf(M.d_p1 - t1 - slack, 0.0f), fhi = M.d_p1 + t1 + slack;
+                const uint32_t klo = __float_as_uint(flo) & 0xffffff00u;
+                const uint32_t khi = (fhi >= 0.0f ? __float_as_uint(fhi) : 0u) | 0xffu;  // +inf: everything
+                uint32_t lo = 0, hi = m;  // first sorted position with key >= klo
+                while (lo < hi) {
+                    const uint32_t mid = (lo + hi) >> 1;
+                    if (sm_skey[mid] < klo) lo = mid + 1; else hi = mid;
+                }
+                for (uint32_t r = lo; r < m && sm_skey[r] <= khi; ++r) {
+                    const uint32_t j = sm_skey[r] & 0xffu;
+                    if (pair_flagged(M, true, t1, t2, sm_sib[j])) {
+                        sm_mask[e * maskw + (j >> 5)] |= 1u << (j & 31u);
+                        ++c;
+                    }
+                }
             }
-            if (m & 31u) {
-                uint32_t bits = 0;
-                const Sib* __restrict__ sw = sm_sib + (full << 5);
-                for (uint32_t jj = 0; jj < (m & 31u); ++jj) bits |= (pair_flagged(M, Mok, t1, t2, sw[jj]) ? 1u : 0u) << jj;
-                sm_mask[e * DF_MASKW + full] = bits;
-                c += __popc(bits);
-            }
-        } else {
+        } else if (Mok) {  // an invalid 3-D segment has similarity 0 with everything
 #pragma unroll 4
             for (uint32_t j = 0; j < m; ++j) c += pair_flagged(M, Mok, t1, t2, sib[j]) ? 1u : 0u;
         }
@@ -469,7 +508,7 @@ __global__ void __launch_bounds__(DF_THREADS) k3_build_kernel(const BuildArgs a)
         if (use_mask) {
             const uint32_t words = (m + 31) >> 5;
             for (uint32_t w = 0; w < words; ++w) {
-                uint32_t bits = sm_mask[e * DF_MASKW + w];
+                uint32_t bits = sm_mask[e * maskw + w];
                 while (bits) {
                     const uint32_t j = (w << 5) + (__ffs(bits) - 1);
                     bits &= bits - 1;
@@ -874,8 +913,9 @@ int k3_max_staged() { return DF_MAXM_CAP; }
 
 static size_t build_smem_bytes(uint32_t maxm)
 {
-    return (size_t)maxm * (24 + sizeof(Sib) + sizeof(float2)) + 2 * ((size_t)maxm + 1) * 4 +
-           (size_t)(maxm < (uint32_t)DF_MASKM ? maxm : (uint32_t)DF_MASKM) * DF_MASKW * 4 + 16;
+    const size_t maskm = maxm < (uint32_t)DF_MASKM ? maxm : (uint32_t)DF_MASKM, maskw = (maskm + 31) / 32;
+    return (size_t)maxm * (24 + sizeof(Sib) + sizeof(float2)) + 2 * ((size_t)maxm + 2) * 4 +
+           (((maskm * maskw + 3) & ~(size_t)3) + 2 * ((maskm + 3) & ~(size_t)3)) * 4 + 16;
 }
 
 static BuildArgs build_args(const K3Tables& t, uint32_t maxm)
@@ -894,7 +934,9 @@ static BuildArgs build_args(const K3Tables& t, uint32_t maxm)
     return b;
 }
 
-// build: potential lists and fold programs of the rows [g_lo, g_hi)
+// build: potential lists and fold programs of the rows [g_lo, g_hi).  Two launches by row length:
+// the many short rows get a small shared-memory staging (more rows in flight per SM: the kernel is
+// bound by the latency of its dependent gathers), the few long ones the full-size staging.
 int launch_k3_build(const K3Tables& t, cudaStream_t st, int* err)
 {
     if (t.g_hi <= t.g_lo) return 0;
@@ -902,15 +944,25 @@ int launch_k3_build(const K3Tables& t, cudaStream_t st, int* err)
     if (maxm > (uint32_t)DF_MAXM_CAP) maxm = DF_MAXM_CAP;
     maxm = (maxm + 3u) & ~3u;  // keeps the shared-memory arrays 16-byte aligned
     if (maxm < 4) maxm = 4;
-    const BuildArgs b = build_args(t, maxm);
-    const size_t smem = build_smem_bytes(maxm);
-    cudaError_t e = cudaFuncSetAttribute(k3_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) {
-        *err = (int)e;
-        return -1;
+    int launches = 0;
+    const uint32_t small = maxm < (uint32_t)DF_SMALL ? maxm : (uint32_t)DF_SMALL;
+    for (int cls = 0; cls < 2; ++cls) {
+        if (cls == 1 && t.maxm <= small && t.L_sib == nullptr) break;  // no row is longer than the small staging
+        const uint32_t mm = cls == 0 ? small : maxm;
+        BuildArgs b = build_args(t, mm);
+        b.m_lo = cls == 0 ? 0u : small;
+        b.m_hi = cls == 0 ? small : 0xffffffffu;
+        const size_t smem = build_smem_bytes(mm);
+        cudaError_t e = cudaFuncSetAttribute(k3_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)build_smem_bytes(maxm));
+        if (e != cudaSuccess) {
+            *err = (int)e;
+            return -1;
+        }
+        k3_build_kernel<<<t.g_hi - t.g_lo, DF_THREADS, smem, st>>>(b);
+        ++launches;
     }
-    k3_build_kernel<<<t.g_hi - t.g_lo, DF_THREADS, smem, st>>>(b);
-    return 1;
+    return launches;
 }
 
 // fold: every row of the scene (replicated on every rank: the scores of all views are needed)
