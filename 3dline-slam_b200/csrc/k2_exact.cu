@@ -192,7 +192,7 @@ static constexpr int K2_WARPS = 4;     // warps per CTA, one row per warp at a t
 static constexpr int K2_SUB = 64;      // rows per CTA (a quarter of a K1 tile)
 static constexpr int K2_CHUNK = 1024;  // target segments per enumeration chunk (32 mask words)
 
-struct K2WarpSmem {
+struct __align__(16) K2WarpSmem {
     float ps[K2_CHUNK];        // exact overlap of the candidates that pass the overlap test
     unsigned short cl[K2_CHUNK];  // chunk-local target index: candidates, then (in place) the passing ones
 };
@@ -269,48 +269,19 @@ __global__ void __launch_bounds__(K2_WARPS * 32, MINB) k2_row_kernel(
             }
             __syncwarp();
 
-            // ---- phase A: the pair test in the reference's double sequence (src/line3D.cc:1131-1158) ----
-            uint32_t npass = 0;
+            // ---- phase V: which candidates triangulate to four positive depths (src/line3D.cc:1160-1168,
+            // 1365-1390)?  A match is pushed iff it passes the pair test AND has four positive depths; the
+            // depth signs are the cheaper half (no division: see depth_positive), so they go first and
+            // the pair test only runs on the ~half of the candidates that survive.  The divisions are
+            // done for the matches that survive the kNN selection. ----
+            uint32_t nval = 0;
             for (uint32_t k0 = 0; k0 < total; k0 += 32) {
                 const uint32_t k = k0 + lane;
                 const bool active = k < total;
                 const uint32_t cidx = active ? (uint32_t)sm.cl[k] : 0u;
-                float score = 0.0f;
-                bool pass = false;
-                if (active) {
-                    const float4 tg = segs[P.tgt_off + cb + cidx];
-                    const D3 q1 = d3((double)tg.x, (double)tg.y, 1.0), q2 = d3((double)tg.z, (double)tg.w, 1.0);
-                    const D3 l2 = cross3(q1, q2);
-                    const D3 a = cross3(l2, e1), b = cross3(l2, e2);
-                    if (fabs(a.z) > L3D_EPS && fabs(b.z) > L3D_EPS) {
-                        const double ax = dd(a.x, a.z), ay = dd(a.y, a.z), bx = dd(b.x, b.z), by = dd(b.y, b.z);
-                        if (!(ax < 0 || ax > W || ay < 0 || ay > W || bx < 0 || bx > W || by < 0 || by > W)) {
-                            score = mutual_overlap_xy(ax, ay, bx, by, q1.x, q1.y, q2.x, q2.y);
-                            pass = score > thr;
-                        }
-                    }
-                }
-                __syncwarp();  // every lane has read its cl[k] before the in-place compaction
-                const uint32_t bal = __ballot_sync(0xffffffffu, pass);
-                if (pass) {
-                    const uint32_t pos = npass + __popc(bal & lt_mask);
-                    sm.cl[pos] = (unsigned short)cidx;
-                    sm.ps[pos] = score;
-                }
-                npass += __popc(bal);
-                __syncwarp();
-            }
-            if (npass == 0) continue;
-
-            // ---- phase B: which candidates triangulate to four positive depths (src/line3D.cc:1160-1168,
-            // 1365-1390).  Only the sign of every depth is needed here; the divisions are done for the
-            // matches that survive the kNN selection. ----
-            for (uint32_t k0 = 0; k0 < npass; k0 += 32) {
-                const uint32_t k = k0 + lane;
                 bool valid = false;
-                uint32_t c = 0;
-                if (k < npass) {
-                    c = cb + (uint32_t)sm.cl[k];
+                if (active) {
+                    const uint32_t c = cb + cidx;
                     const SegRays tr = rays[P.tgt_off + c];
                     const SegPlane plA = planes[P.tgt_off + c];
                     const D3 nA = ld3(plA.n);
@@ -322,9 +293,36 @@ __global__ void __launch_bounds__(K2_WARPS * 32, MINB) k2_row_kernel(
                                 depth_positive(numB, b2);
                     }
                 }
+                __syncwarp();  // every lane has read its cl[k] before the in-place compaction
                 const uint32_t bal = __ballot_sync(0xffffffffu, valid);
-                if (valid)
-                    stage[n_valid + __popc(bal & lt_mask)] = ((unsigned long long)__float_as_uint(sm.ps[k]) << 32) | c;
+                if (valid) sm.cl[nval + __popc(bal & lt_mask)] = (unsigned short)cidx;
+                nval += __popc(bal);
+                __syncwarp();
+            }
+            if (nval == 0) continue;
+
+            // ---- phase A: the pair test in the reference's double sequence (src/line3D.cc:1131-1158) ----
+            for (uint32_t k0 = 0; k0 < nval; k0 += 32) {
+                const uint32_t k = k0 + lane;
+                uint32_t c = 0;
+                float score = 0.0f;
+                bool pass = false;
+                if (k < nval) {
+                    c = cb + (uint32_t)sm.cl[k];
+                    const float4 tg = segs[P.tgt_off + c];
+                    const D3 q1 = d3((double)tg.x, (double)tg.y, 1.0), q2 = d3((double)tg.z, (double)tg.w, 1.0);
+                    const D3 l2 = cross3(q1, q2);
+                    const D3 a = cross3(l2, e1), b = cross3(l2, e2);
+                    if (fabs(a.z) > L3D_EPS && fabs(b.z) > L3D_EPS) {
+                        const double ax = dd(a.x, a.z), ay = dd(a.y, a.z), bx = dd(b.x, b.z), by = dd(b.y, b.z);
+                        if (!(ax < 0 || ax > W || ay < 0 || ay > W || bx < 0 || bx > W || by < 0 || by > W)) {
+                            score = mutual_overlap_xy(ax, ay, bx, by, q1.x, q1.y, q2.x, q2.y);
+                            pass = score > thr;
+                        }
+                    }
+                }
+                const uint32_t bal = __ballot_sync(0xffffffffu, pass);
+                if (pass) stage[n_valid + __popc(bal & lt_mask)] = ((unsigned long long)__float_as_uint(score) << 32) | c;
                 n_valid += __popc(bal);
             }
             __syncwarp();
@@ -342,12 +340,21 @@ __global__ void __launch_bounds__(K2_WARPS * 32, MINB) k2_row_kernel(
                 // distinct overlaps pop in descending order: rank = number of strictly larger overlaps;
                 // equal overlaps among the popped ones show up as fewer than npop distinct ranks below npop
                 for (uint32_t k = lane; k < n_valid; k += 32) sm.ps[k] = key_overlap(stage[k]);
+                if (lane < 4 && n_valid + lane < K2_CHUNK) sm.ps[n_valid + lane] = -1.0f;  // pad: never larger
                 __syncwarp();
                 uint32_t seen = 0, rankbits = 0;
+                const uint32_t n4 = (n_valid + 3u) >> 2;
                 for (uint32_t k = lane; k < n_valid; k += 32) {
                     const float ov = sm.ps[k];
                     uint32_t rank = 0;
-                    for (uint32_t j = 0; j < n_valid; ++j) rank += (sm.ps[j] > ov) ? 1u : 0u;
+                    if (n4 * 4 <= K2_CHUNK) {
+                        for (uint32_t j = 0; j < n4; ++j) {
+                            const float4 o = reinterpret_cast<const float4*>(sm.ps)[j];
+                            rank += (o.x > ov) + (o.y > ov) + (o.z > ov) + (o.w > ov);
+                        }
+                    } else {
+                        for (uint32_t j = 0; j < n_valid; ++j) rank += (sm.ps[j] > ov) ? 1u : 0u;
+                    }
                     if (rank < npop) {
                         sm.cl[rank] = (unsigned short)k;  // colliding ranks are detected below
                         rankbits |= 1u << (rank & 31u);
