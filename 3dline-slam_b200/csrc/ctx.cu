@@ -136,6 +136,7 @@ int l3d_scene_commit(l3d_ctx* ctx)
     CK(cudaStreamSynchronize(st));
     ctx->committed = true;
     ctx->stage = 0;
+    ctx->k3_list_max = 0;
     return L3D_OK;
 }
 
@@ -158,8 +159,8 @@ int upload_views(l3d_ctx* ctx)
         d.order = v;
         d.pad = 0;
     }
+    // pageable source: the runtime stages it before the call returns, no synchronisation needed
     CK(cudaMemcpyAsync(ctx->d_views.p, vd.data(), V * sizeof(ViewDev), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
     return L3D_OK;
 }
 
@@ -648,15 +649,19 @@ int l3d_score_build(l3d_ctx* ctx)
     if (keep) CK(ctx->d_L_rec.ensure(Lcap + 1));
     // rows are staged in shared memory up to maxm entries (an inverse block is not bounded by kNN:
     // any number of source segments may match the same target segment): read the longest list back
+    // (the value is kept while the same committed scene is re-matched: a longer row than expected
+    // makes the build kernel flag the program store as overflowed and the retry reads the new maximum)
     uint32_t maxm = (uint32_t)k3_max_staged();
     bool big_rows = true;
-    {
+    if (ctx->k3_list_max == 0 || ctx->force_list_max) {
         uint32_t dev_max = 0;  // WfStats::max_list
         CK(cudaMemcpyAsync(&dev_max, ctx->d_stats.p + 36, 4, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
-        big_rows = dev_max > maxm;
-        maxm = std::max<uint32_t>(std::min(dev_max, maxm), 1u);
+        ctx->k3_list_max = std::max(dev_max, 1u);
+        ctx->force_list_max = false;
     }
+    big_rows = ctx->k3_list_max > maxm;
+    maxm = std::max<uint32_t>(std::min(ctx->k3_list_max, maxm), 1u);
     if (const char* ov = getenv("L3D_K3_MAXM")) {  // test hook: force the long-row path
         maxm = (uint32_t)std::max(1, atoi(ov));
         big_rows = true;
@@ -700,6 +705,25 @@ int score_rebuild(l3d_ctx* ctx, uint32_t needed_units)
 {
     cudaStream_t st = ctx->stream;
     const uint32_t V = (uint32_t)ctx->views.size();
+    {   // the longest list may have grown past the cached value: re-read it and re-size the staging
+        uint32_t dev_max = 0;
+        CK(cudaMemcpyAsync(&dev_max, ctx->d_stats.p + 36, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (dev_max > ctx->k3_list_max) {
+            ctx->k3_list_max = dev_max;
+            const uint32_t cap = (uint32_t)k3_max_staged();
+            ctx->k3_maxm = std::min(dev_max, cap);
+            if (dev_max > cap && !ctx->k3_big_rows) {
+                const uint64_t Lcap = ctx->L_total;
+                CK(ctx->d_L_sib.ensure((Lcap + 1) * k3_sib_bytes()));
+                CK(ctx->d_L_dir.ensure(3 * (Lcap + 1)));
+                CK(ctx->d_L_reg.ensure(Lcap + 1));
+                CK(ctx->d_L_c.ensure(Lcap + ctx->S + 2));
+                CK(ctx->d_L_h.ensure(Lcap + ctx->S + 2));
+                ctx->k3_big_rows = true;
+            }
+        }
+    }
     ctx->prog_cap = std::max<uint64_t>(2 * ctx->prog_cap, (uint64_t)needed_units + 1024);
     if (ctx->prog_cap > 0xfffffff0ull) return fail(L3D_ERR_CAPACITY, "fold programs too large");
     CK(ctx->d_prog.ensure(ctx->prog_cap * 16));
@@ -877,17 +901,17 @@ int l3d_affinity_edges(l3d_ctx* ctx)
                               ctx->d_filt_cnt.p, filt, ctx->two_sigA_sqr, ctx->med_scene_depth_lines,
                               ctx->d_filt_sim.p, ctx->d_E_cnt.p, ctx->d_tests.p, g_lo, g_hi, st);
     ctx->cnt.gpu_launches += launch_scan_u32(ctx->d_E_cnt.p, ctx->d_E_off.p, S, ctx->d_scan.p, ctx->d_scan.cap, st);
+    // every filtered list entry yields at most one edge: size the store from that bound and read the
+    // count back while the write kernel runs
     uint32_t n_edges = 0;
+    CK(ctx->d_edges.ensure((nf + 1) * k4_edge_bytes()));
     CK(cudaMemcpyAsync(&n_edges, ctx->d_E_off.p + S, 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    if (n_edges) {
-        CK(ctx->d_edges.ensure((size_t)n_edges * k4_edge_bytes()));
-        ctx->cnt.gpu_launches +=
-            launch_k4_edges_write(ctx->d_views.p, S, ctx->d_filt_off.p, ctx->d_filt_cnt.p, filt, ctx->d_filt_sim.p,
-                                  ctx->d_E_off.p, ctx->d_edges.p, g_lo, g_hi, st);
-    }
-    ctx->n_edges_local = n_edges;
+    ctx->cnt.gpu_launches +=
+        launch_k4_edges_write(ctx->d_views.p, S, ctx->d_filt_off.p, ctx->d_filt_cnt.p, filt, ctx->d_filt_sim.p,
+                              ctx->d_E_off.p, ctx->d_edges.p, g_lo, g_hi, st);
     ctx->tm.end(ev, st);
+    CK(cudaStreamSynchronize(st));
+    ctx->n_edges_local = n_edges;
     ctx->stage4_phase = 1;
     return L3D_OK;
 }

@@ -227,6 +227,8 @@ struct l3d_ctx {
     uint64_t prog_cap = 0;  // fold-program store, 16-byte units (grown on overflow)
     uint64_t L_total = 0, filt_cap = 0;
     uint32_t k3_maxm = 0;
+    uint32_t k3_list_max = 0;   // longest potential list of the committed scene (0: not read yet)
+    bool force_list_max = false;
     bool k3_big_rows = false;
     int stage3_phase = 0, stage4_phase = 0;
     cudaEvent_t ev_total3 = nullptr, ev_total4 = nullptr;
