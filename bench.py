@@ -322,8 +322,8 @@ def main():
         "algorithmic_flop_per_test": FLOP_PER_TEST, "tests_per_launch": k1_tests / max(t12["k1_launches"], 1),
         "launch_ms": 1e3 * k1_s / max(t12["k1_launches"], 1), "k1_tests_per_s": k1_tests / k1_s,
         # dram__bytes_read.sum + dram__bytes_write.sum of one K1 launch on C2 (ncu --set full,
-        # profiles/r1d_ncu_full_c2.md); the 31 MB bit mask stays in the 126 MB L2
-        "traffic": 2424832 if wname == "c2" else None,
+        # profiles/r1z_ncu_full_c2.md); the 31 MB bit mask stays in the 126 MB L2
+        "traffic": 2508800 if wname == "c2" else None,
     }
     n_pairs_local = max(c12["num_pairs_local"], 1)
     seg_n = scene.views[0].segs.shape[0]
@@ -332,6 +332,24 @@ def main():
                        "achieved_gbs": k1_bytes / k1_s / 1e9, "peak_gbs": peaks.get("hbm_gbs"),
                        "frac": (k1_bytes / k1_s / 1e9) / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None,
                        "note": "descriptors + segments + 1 bit per test + counts; the kernel is FP32-pipe bound, not HBM bound"}
+
+    # the other stages against the roofline that bounds them (SURVEY.md 8d figures); they are
+    # latency / dependency bound at this scene size, which is what the small fractions say
+    fp64_nominal = n_sm * 64 * 2 * sm_max * 1e6 / 1e12
+    k2_flop = 330.0 * float(c12["candidates"])
+    stage_rooflines = {
+        "k2_exact": {"bound": "fp64", "algorithmic_flop_per_candidate": 330.0, "candidates": c12["candidates"],
+                     "achieved_tflops": k2_flop / max(t12["exact"] * 1e-3, 1e-9) / 1e12, "peak_tflops": fp64_nominal,
+                     "frac": k2_flop / max(t12["exact"] * 1e-3, 1e-9) / 1e12 / fp64_nominal},
+        "k3_score": {"bound": "fp32+sfu, dependency chain over the views",
+                     "sim_evals_per_s": float(cfin["sim_evals"]) / max(t3["score"] * 1e-3, 1e-9),
+                     "algorithmic_flop_per_sim_eval": 40.0,
+                     "achieved_tflops": 40.0 * float(cfin["sim_evals"]) / max(t3["score"] * 1e-3, 1e-9) / 1e12},
+        "k4_affinity": {"bound": "hbm gather", "algorithmic_bytes_per_edge_test": 160.0,
+                        "edge_tests": cfin["filtered_entries"],
+                        "achieved_gbs": 160.0 * float(cfin["filtered_entries"]) / max(t4["affinity"] * 1e-3, 1e-9) / 1e9,
+                        "peak_gbs": peaks.get("hbm_gbs")},
+    }
 
     cpu_baseline = None
     if not args.no_cpu_baseline:
@@ -367,7 +385,7 @@ def main():
                      "k3_score": t3["score"], "k4_affinity": t4["affinity"]},
         "counts": {k: cfin[k] for k in ("pair_tests", "candidates", "forward_matches", "scored_entries", "sim_evals",
                                          "filtered_entries", "num_pairs", "num_entries", "num_edges", "num_local_ids")},
-        "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+        "roofline": roofline, "stage_rooflines": stage_rooflines, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
     }
     print(json.dumps(line))
     if dist is not None:
