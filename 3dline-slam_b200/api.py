@@ -96,6 +96,7 @@ def lib():
         L.l3d_scene_begin.argtypes = [vp]
         L.l3d_scene_add_view.argtypes = [vp, C.POINTER(View), vp, vp, u32]
         L.l3d_scene_commit.argtypes = [vp]
+        L.l3d_scene_set.argtypes = [vp, vp, u32, vp, vp, vp]
         L.l3d_match_images.argtypes = [vp, C.POINTER(Params)]
         L.l3d_match_stage12.argtypes = [vp, C.POINTER(Params)]
         L.l3d_match_stage3.argtypes = [vp]
@@ -234,6 +235,7 @@ class Line3D:
         self.max_img_width = int(max_img_width)
         self.max_line_segments = int(max_line_segments)
         self._views = {}
+        self._packed = None
         self._dirty = True
         self.params = None
         self.filter_mode = 0
@@ -269,18 +271,28 @@ class Line3D:
         for v in scene.views:
             self.UpdataImage(v.cam_id, v.R, v.t, v.median_depth, v.neighbors)
 
-    def upload(self):
-        """Host -> device transfer of the scene tables (what DataArray::upload does per view)."""
-        self._ck(self.L.l3d_scene_begin(self.h))
-        for cam, v in self._views.items():
-            vv = View()
+    def _pack(self):
+        """Host-side packing of the scene for l3d_scene_set (kept until a view changes)."""
+        cams = list(self._views.items())
+        arr = (View * max(len(cams), 1))()
+        for i, (cam, v) in enumerate(cams):
+            vv = arr[i]
             vv.cam_id, vv.width, vv.height, vv.num_segs = cam, v["w"], v["h"], v["segs"].shape[0]
             vv.K[:] = v["K"].tolist()
             vv.R[:] = v["R"].tolist()
             vv.t[:] = v["t"].tolist()
             vv.median_depth = v["md"]
-            self._ck(self.L.l3d_scene_add_view(self.h, C.byref(vv), _p(v["segs"]), _p(v["nb"]), v["nb"].size))
-        self._ck(self.L.l3d_scene_commit(self.h))
+        segs = np.ascontiguousarray(np.concatenate([v["segs"] for _, v in cams]) if cams else np.zeros((0, 4), np.float32))
+        nb = np.ascontiguousarray(np.concatenate([v["nb"] for _, v in cams]) if cams else np.zeros(0, np.uint32))
+        cnt = np.array([v["nb"].size for _, v in cams], dtype=np.uint32)
+        self._packed = (arr, len(cams), segs, nb.astype(np.uint32), cnt)
+
+    def upload(self):
+        """Host -> device transfer of the scene tables (what DataArray::upload does per view)."""
+        if self._dirty or self._packed is None:
+            self._pack()
+        arr, n, segs, nb, cnt = self._packed
+        self._ck(self.L.l3d_scene_set(self.h, C.cast(arr, C.c_void_p), n, _p(segs), _p(nb), _p(cnt)))
         self._dirty = False
 
     def _params(self, sigma_position, sigma_angle, num_neighbors, epipolar_overlap, kNN, const_regularization_depth):

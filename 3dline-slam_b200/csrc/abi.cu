@@ -168,7 +168,9 @@ int l3d_score_matches(l3d_ctx* ctx, const float* lines, uint32_t n_lines, const 
 // multi-GPU: the four exchange points of a sharded run (one process per GPU; the collective itself
 // is torch.distributed / NCCL, see 3dline-slam_b200/sharding.py).  Every rank exports one blob,
 // the blobs are all-gathered `stride` bytes apart, every rank imports all of them.
-//   FORWARD     u32 cnt[rows_pad8] | FwdRec recs[]                       rows = pair rows of the slice
+//   FORWARD     u32 cnt[rows_pad8] | FwdRec recs[] of the boundary pairs  rows = pair rows of the slice
+//               (only the matches whose target view belongs to another slice travel: nobody else reads
+//               the rest; every rank still learns all per-row counts, i.e. the global record numbering)
 //   PROGRAMS    u32 nh[rows_pad4] | u32 off[rows_pad4] | uint4 rec[]     rows = segments of the slice
 //   HYPOTHESES  ShardHypHdr | u32 filt_cnt[rows_pad4] | u32 filt_off[rows_pad4] | EntryDev e[rows] | ListRec filt[]
 //   EDGES       {u32 src, u32 tgt, float w}[]
@@ -224,12 +226,43 @@ static int check_phase(l3d_ctx* ctx, int kind)
     return L3D_OK;
 }
 
+// FORWARD: the records of this rank's boundary pairs, gathered into d_bx_rec; count at d_bx_off[rows]
+static int prepare_forward_export(l3d_ctx* ctx)
+{
+    cudaStream_t st = ctx->stream;
+    const uint32_t r0 = ctx->slice_row[ctx->rank], r1 = ctx->slice_row[ctx->rank + 1], rows = r1 - r0;
+    CK(ctx->d_bx_cnt.ensure((size_t)rows + 1));
+    CK(ctx->d_bx_off.ensure((size_t)rows + 2));
+    CK(ctx->d_bx_rec.ensure((size_t)ctx->local_fwd + 1));
+    CK(ctx->d_scan.ensure(scan_scratch_words(rows + 1) + 64));
+    if (!rows) {
+        CK(cudaMemsetAsync(ctx->d_bx_off.p, 0, 8, st));
+        return L3D_OK;
+    }
+    ctx->cnt.gpu_launches += launch_fwd_bmask(ctx->d_pairs.p, (uint32_t)ctx->pairs.size(), ctx->d_fwd_cnt.p, r0, r1,
+                                              ctx->d_bx_cnt.p, st);
+    ctx->cnt.gpu_launches += launch_scan_u32(ctx->d_bx_cnt.p, ctx->d_bx_off.p, rows, ctx->d_scan.p, ctx->d_scan.cap, st);
+    // d_fwd_off still holds the local offsets of this rank's rows
+    ctx->cnt.gpu_launches += launch_fwd_bgather(ctx->d_bx_cnt.p, ctx->d_bx_off.p, ctx->d_fwd_off.p, r0, r1,
+                                                ctx->d_fwd_rec.p, ctx->d_bx_rec.p, st);
+    return L3D_OK;
+}
+
 // variable part of this rank's blob (elements); reads the device cursors, so it synchronises
 static int blob_var_count(l3d_ctx* ctx, int kind, uint64_t* n)
 {
     cudaStream_t st = ctx->stream;
     switch (kind) {
-    case L3D_X_FORWARD: *n = ctx->local_fwd; return L3D_OK;
+    case L3D_X_FORWARD: {
+        int rc = prepare_forward_export(ctx);
+        if (rc) return rc;
+        uint32_t nb = 0;
+        const uint32_t rows = ctx->slice_row[ctx->rank + 1] - ctx->slice_row[ctx->rank];
+        CK(cudaMemcpyAsync(&nb, ctx->d_bx_off.p + rows, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        *n = nb;
+        return L3D_OK;
+    }
     case L3D_X_EDGES: *n = ctx->n_edges_local; return L3D_OK;
     case L3D_X_PROGRAMS:
         for (int attempt = 0;; ++attempt) {
@@ -290,7 +323,7 @@ static int export_payload(l3d_ctx* ctx, int kind, unsigned char* d, uint64_t n, 
     case L3D_X_FORWARD: {
         const uint32_t r0 = ctx->slice_row[ctx->rank];
         if (rows) CK(cudaMemcpyAsync(d, ctx->d_fwd_cnt.p + r0, (size_t)rows * 4, ck, st));
-        if (n) CK(cudaMemcpyAsync(d + pad_to(rows, 8) * 4, ctx->d_fwd_rec.p, n * sizeof(FwdRec), ck, st));
+        if (n) CK(cudaMemcpyAsync(d + pad_to(rows, 8) * 4, ctx->d_bx_rec.p, n * sizeof(FwdRec), ck, st));
         break;
     }
     case L3D_X_PROGRAMS: {
@@ -375,7 +408,13 @@ int l3d_shard_export_hdr(l3d_ctx* ctx, int kind, void* dst, uint64_t stride_byte
     const uint32_t* n_dev = nullptr;
     const uint32_t* f_dev = nullptr;
     switch (kind) {
-    case L3D_X_FORWARD: have = ctx->local_fwd; break;
+    case L3D_X_FORWARD: {
+        rc = prepare_forward_export(ctx);
+        if (rc) return rc;
+        have = ctx->local_fwd;  // upper bound of the boundary records; the exact count is on the device
+        n_dev = ctx->d_bx_off.p + (ctx->slice_row[ctx->rank + 1] - ctx->slice_row[ctx->rank]);
+        break;
+    }
     case L3D_X_EDGES: have = ctx->n_edges_local; break;
     case L3D_X_PROGRAMS:
         have = ctx->prog_cap;
@@ -423,30 +462,41 @@ int l3d_shard_import(l3d_ctx* ctx, int kind, const void* all, uint64_t stride_by
     const uint32_t S = ctx->S;
     switch (kind) {
     case L3D_X_FORWARD: {
-        uint64_t total = 0;
-        for (int q = 0; q < world; ++q) total += nvar[q];
-        if (total > 0xfffffff0ull) return fail(L3D_ERR_CAPACITY, "too many forward matches");
-        // slices are contiguous in pair rows and in rank order: the merged tables are concatenations
-        CK(ctx->d_fwd_alt.ensure((size_t)total + 1));
-        uint64_t at = 0;
+        const uint32_t R = ctx->total_rows, P = (uint32_t)ctx->pairs.size();
+        const uint32_t r0 = ctx->slice_row[ctx->rank], r1 = ctx->slice_row[ctx->rank + 1];
+        // the local offsets of this rank's rows, before the canonical offsets replace them
+        CK(ctx->d_fwd_off_local.ensure((size_t)R + 1));
+        if (r1 > r0)
+            CK(cudaMemcpyAsync(ctx->d_fwd_off_local.p + r0, ctx->d_fwd_off.p + r0, (size_t)(r1 - r0) * 4,
+                               cudaMemcpyDeviceToDevice, st));
+        // per-row counts of every slice (contiguous in pair rows and in rank order) -> canonical offsets
         for (int q = 0; q < world; ++q) {
             const uint32_t rows = slice_rows(ctx, kind, q);
-            const unsigned char* b = src + (uint64_t)q * stride_bytes;
             if (rows)
-                CK(cudaMemcpyAsync(ctx->d_fwd_cnt.p + ctx->slice_row[q], b, (size_t)rows * 4, cudaMemcpyDeviceToDevice, st));
-            if (nvar[q])
-                CK(cudaMemcpyAsync(ctx->d_fwd_alt.p + at, b + pad_to(rows, 8) * 4, nvar[q] * sizeof(FwdRec),
+                CK(cudaMemcpyAsync(ctx->d_fwd_cnt.p + ctx->slice_row[q], src + (uint64_t)q * stride_bytes, (size_t)rows * 4,
                                    cudaMemcpyDeviceToDevice, st));
-            at += nvar[q];
         }
+        CK(ctx->d_scan.ensure(scan_scratch_words(R + 1) + 64));
+        ctx->cnt.gpu_launches += launch_scan_u32(ctx->d_fwd_cnt.p, ctx->d_fwd_off.p, R, ctx->d_scan.p, ctx->d_scan.cap, st);
+        // where the boundary records of every rank sit inside its blob
+        CK(ctx->d_bx_cnt_all.ensure((size_t)R + 1));
+        CK(ctx->d_bx_off_all.ensure((size_t)R + 2));
+        ctx->cnt.gpu_launches += launch_fwd_bmask(ctx->d_pairs.p, P, ctx->d_fwd_cnt.p, 0, R, ctx->d_bx_cnt_all.p, st);
+        ctx->cnt.gpu_launches += launch_scan_u32(ctx->d_bx_cnt_all.p, ctx->d_bx_off_all.p, R, ctx->d_scan.p, ctx->d_scan.cap, st);
+        rc = refresh_pair_totals(ctx);  // synchronises: record totals per pair and overall
+        if (rc) return rc;
+        const uint64_t total = ctx->pair_total_sum;
+        if (total > 0xfffffff0ull) return fail(L3D_ERR_CAPACITY, "too many forward matches");
+        CK(ctx->d_fwd_alt.ensure((size_t)total + 1));
+        ctx->cnt.gpu_launches += launch_fwd_place(src, stride_bytes, world, ctx->slice_row.data(), ctx->rank, R,
+                                                  ctx->d_fwd_cnt.p, ctx->d_fwd_off.p, ctx->d_bx_cnt_all.p,
+                                                  ctx->d_bx_off_all.p, ctx->d_fwd_rec.p, ctx->d_fwd_off_local.p,
+                                                  ctx->d_fwd_alt.p, st);
         std::swap(ctx->d_fwd_rec.p, ctx->d_fwd_alt.p);
         std::swap(ctx->d_fwd_rec.cap, ctx->d_fwd_alt.cap);
-        CK(ctx->d_scan.ensure(scan_scratch_words(ctx->total_rows + 1) + 64));
-        ctx->cnt.gpu_launches += launch_scan_u32(ctx->d_fwd_cnt.p, ctx->d_fwd_off.p, ctx->total_rows, ctx->d_scan.p,
-                                                 ctx->d_scan.cap, st);
         ctx->total_fwd = total;
         ctx->cnt.forward_matches = total;
-        return refresh_pair_totals(ctx);
+        return L3D_OK;
     }
     case L3D_X_PROGRAMS: {
         CK(ctx->d_slice_g.ensure(L3D_MAX_WORLD + 1));

@@ -89,6 +89,23 @@ int l3d_scene_add_view(l3d_ctx* ctx, const l3d_view* view, const float* segs, co
     return L3D_OK;
 }
 
+// begin + add_view x n + commit in one call (the views' segments / neighbour lists are concatenated)
+int l3d_scene_set(l3d_ctx* ctx, const l3d_view* views, uint32_t n_views, const float* segs_concat,
+                  const uint32_t* nbrs_concat, const uint32_t* nbr_counts)
+{
+    if (!ctx || !views || !segs_concat || !nbrs_concat || !nbr_counts) return fail(L3D_ERR_ARG, "NULL argument");
+    int rc = l3d_scene_begin(ctx);
+    if (rc) return rc;
+    size_t so = 0, no = 0;
+    for (uint32_t i = 0; i < n_views; ++i) {
+        rc = l3d_scene_add_view(ctx, &views[i], segs_concat + 4 * so, nbrs_concat + no, nbr_counts[i]);
+        if (rc) return rc;
+        so += views[i].num_segs;
+        no += nbr_counts[i];
+    }
+    return l3d_scene_commit(ctx);
+}
+
 int l3d_scene_commit(l3d_ctx* ctx)
 {
     if (!ctx) return fail(L3D_ERR_ARG, "ctx is NULL");
@@ -103,6 +120,15 @@ int l3d_scene_commit(l3d_ctx* ctx)
         ctx->cam2view[ctx->views[i].v.cam_id] = (uint32_t)i;
         ctx->views[i].seg_off = (uint32_t)S;
         S += ctx->views[i].v.num_segs;
+    }
+    for (auto& hv : ctx->views) {  // neighbour camera ids -> ascending, unique view indices
+        hv.nb_views.clear();
+        for (uint32_t cam : hv.nbrs) {
+            auto f = ctx->cam2view.find(cam);
+            if (f != ctx->cam2view.end()) hv.nb_views.push_back(f->second);
+        }
+        std::sort(hv.nb_views.begin(), hv.nb_views.end());
+        hv.nb_views.erase(std::unique(hv.nb_views.begin(), hv.nb_views.end()), hv.nb_views.end());
     }
     if (S > 0xfffffff0ull) return fail(L3D_ERR_CAPACITY, "too many segments (%llu)", (unsigned long long)S);
     ctx->S = (uint32_t)S;
@@ -157,7 +183,7 @@ int upload_views(l3d_ctx* ctx)
         d.cam_id = hv.v.cam_id;
         d.xb = 0.0f;
         d.order = v;
-        d.pad = 0;
+        d.needed = (ctx->view_needed.size() == V) ? ctx->view_needed[v] : 1u;
     }
     // pageable source: the runtime stages it before the call returns, no synchronisation needed
     CK(cudaMemcpyAsync(ctx->d_views.p, vd.data(), V * sizeof(ViewDev), cudaMemcpyHostToDevice, ctx->stream));
@@ -222,6 +248,7 @@ int refresh_pair_totals(l3d_ctx* ctx)
         ctx->pairs[p].rec_start = (uint32_t)run;
         run += tot[p];
     }
+    ctx->pair_total_sum = run;
     return L3D_OK;
 }
 
@@ -232,27 +259,21 @@ int plan_pairs(l3d_ctx* ctx)
 {
     const l3d_params& prm = ctx->prm;
     const uint32_t V = (uint32_t)ctx->views.size();
-    // visual neighbours = fixed neighbours that exist (src/line3D.cc:604-616)
-    std::vector<std::set<uint32_t>> nb(V);
-    for (uint32_t v = 0; v < V; ++v)
-        for (uint32_t cam : ctx->views[v].nbrs) {
-            auto f = ctx->cam2view.find(cam);
-            if (f != ctx->cam2view.end()) nb[v].insert(f->second);  // view index order == cam id order
-        }
-    // computeMatches pair order (src/line3D.cc:848-887)
-    std::vector<std::set<uint32_t>> matched(V);
+    // visual neighbours = fixed neighbours that exist (src/line3D.cc:604-616); nb_views is the
+    // ascending list of their view indices (view index order == camera id order), made at commit.
+    // computeMatches pair order (src/line3D.cc:848-887): (s, t) is skipped iff the pair was already
+    // created from the other side, i.e. t < s and s is a neighbour of t.
     ctx->pairs.clear();
     for (uint32_t s = 0; s < V; ++s)
-        for (uint32_t t : nb[s])
-            if (!matched[s].count(t)) {
-                HostPair hp;
-                hp.src = s;
-                hp.tgt = t;
-                hp.batch = 0;
-                ctx->pairs.push_back(hp);
-                matched[s].insert(t);
-                matched[t].insert(s);
-            }
+        for (uint32_t t : ctx->views[s].nb_views) {
+            const std::vector<uint32_t>& nt = ctx->views[t].nb_views;
+            if (t < s && std::binary_search(nt.begin(), nt.end(), s)) continue;
+            HostPair hp;
+            hp.src = s;
+            hp.tgt = t;
+            hp.batch = 0;
+            ctx->pairs.push_back(hp);
+        }
     const uint32_t P = (uint32_t)ctx->pairs.size();
     const int world = prm.shard_world > 1 ? prm.shard_world : 1;
     const int rank = world > 1 ? prm.shard_rank : 0;
@@ -308,6 +329,7 @@ int plan_pairs(l3d_ctx* ctx)
         d.tgt_base = (uint32_t)trow;
         d.words = (d.n_tgt + 31) / 32;
         d.emit_inverse = hp.tgt > hp.src ? 1u : 0u;  // !processed_[tgt] (src/line3D.cc:1994)
+        d.xflag = (owner_of(hp.tgt) != owner_of(hp.src)) ? 1u : 0u;
         row += d.n_src;
         trow += d.n_tgt;
         if (hp.local) {
@@ -319,6 +341,16 @@ int plan_pairs(l3d_ctx* ctx)
         return fail(L3D_ERR_CAPACITY, "row index space exhausted (%llu rows)", (unsigned long long)row);
     ctx->total_rows = (uint32_t)row;
     ctx->total_tgt_rows = (uint32_t)trow;
+    // views whose per-segment tables this rank reads: both views of every pair incident to its slice
+    ctx->view_needed.assign(V, world > 1 ? 0u : 1u);
+    if (world > 1) {
+        const uint32_t lo = ctx->slice_view[rank], hi = ctx->slice_view[rank + 1];
+        for (uint32_t v = lo; v < hi; ++v) ctx->view_needed[v] = 1u;
+        for (uint32_t p = 0; p < P; ++p) {
+            const uint32_t a = ctx->pairs[p].src, b = ctx->pairs[p].tgt;
+            if ((a >= lo && a < hi) || (b >= lo && b < hi)) ctx->view_needed[a] = ctx->view_needed[b] = 1u;
+        }
+    }
     // slice boundaries in segments and in pair rows
     ctx->slice_g.assign(world + 1, ctx->S);
     ctx->slice_row.assign(world + 1, ctx->total_rows);
@@ -617,7 +649,8 @@ int l3d_score_build(l3d_ctx* ctx)
     // pre-pass: row of every forward record, the (static) inverse-match slots, the potential lists
     ctx->cnt.gpu_launches += launch_k3_inv_capacity(ctx->d_pairs.p, P, ctx->total_rows, ctx->d_fwd_off.p,
                                                     ctx->d_fwd_cnt.p, ctx->d_fwd_rec.p, ctx->d_fwd_row.p,
-                                                    ctx->d_inv_cap.p, st);
+                                                    ctx->d_inv_cap.p, ctx->slice_view[ctx->rank],
+                                                    ctx->slice_view[ctx->rank + 1], st);
     ctx->cnt.gpu_launches +=
         launch_scan_u32(ctx->d_inv_cap.p, ctx->d_inv_off.p, (uint32_t)TR, ctx->d_scan.p, ctx->d_scan.cap, st);
     ctx->cnt.gpu_launches += launch_records(ctx);
@@ -1091,7 +1124,7 @@ int l3d_get_view_lists(l3d_ctx* ctx, uint32_t cam_id, int which, uint32_t* row_o
         CK(cudaStreamSynchronize(st));
         const uint32_t o0 = off[0];
         for (uint32_t i = 0; i <= N; ++i) off[i] -= o0;
-        src = ctx->d_L_rec.p + ctx->L_base_h[v];
+        src = ctx->d_L_rec.p + o0;  // rows live at their L_off
         region = off[N];
     } else {
         CK(cudaMemcpyAsync(off.data(), ctx->d_filt_off.p + hv.seg_off, (size_t)N * 4, cudaMemcpyDeviceToHost, st));

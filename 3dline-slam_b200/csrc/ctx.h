@@ -27,7 +27,13 @@ int launch_k2_compact(const uint32_t*, const uint32_t*, const uint32_t*, uint32_
                       uint32_t, cudaStream_t);
 int launch_k3_score(uint32_t, const uint32_t*, ListRec*, const ListGeo*, float, float, void*, cudaStream_t);
 int launch_k3_inv_capacity(const PairDev*, uint32_t, uint32_t, const uint32_t*, const uint32_t*, const FwdRec*,
-                           uint32_t*, uint32_t*, cudaStream_t);
+                           uint32_t*, uint32_t*, uint32_t, uint32_t, cudaStream_t);
+int launch_fwd_bmask(const PairDev*, uint32_t, const uint32_t*, uint32_t, uint32_t, uint32_t*, cudaStream_t);
+int launch_fwd_bgather(const uint32_t*, const uint32_t*, const uint32_t*, uint32_t, uint32_t, const FwdRec*, FwdRec*,
+                       cudaStream_t);
+int launch_fwd_place(const unsigned char*, uint64_t, int, const uint32_t*, int, uint32_t, const uint32_t*,
+                     const uint32_t*, const uint32_t*, const uint32_t*, const FwdRec*, const uint32_t*, FwdRec*,
+                     cudaStream_t);
 int launch_k3_list_capacity(const ViewDev*, const uint32_t*, uint32_t, const IncDev*, const uint32_t*, const PairDev*,
                             const uint32_t*, const uint32_t*, uint32_t*, void*, cudaStream_t);
 int launch_k3_records(const PairDev*, uint32_t, uint32_t, const ViewDev*, const SegRays*, const uint32_t*, FwdRec*,
@@ -106,6 +112,7 @@ struct HostView {
     l3d_view v;
     std::vector<float> segs;
     std::vector<uint32_t> nbrs;
+    std::vector<uint32_t> nb_views;  // neighbours as ascending view indices (l3d_scene_commit)
     hg::Camera cam;
     float k = 0.0f, median_depth = 0.0f, median_sigma = 0.0f;
     uint32_t seg_off = 0;
@@ -236,12 +243,15 @@ struct l3d_ctx {
     // sharding: contiguous view slices (see plan_pairs), buffers adopted from the exchanges
     int world = 1, rank = 0;
     std::vector<uint32_t> slice_view{0, 0}, slice_g{0, 0}, slice_row{0, 0};
+    std::vector<uint32_t> view_needed;  // per view: some pair incident to this rank's slice touches it
     const void* prog_all = nullptr;      // all-gathered fold programs (caller-owned until the next exchange)
     const ListRec* filt_all = nullptr;   // filtered lists of every slice (d_filt_all)
     const void* edges_all = nullptr;     // edges of every slice in traversal order (d_edges_all)
     DevBuf<ListRec> d_filt_all;
     DevBuf<unsigned char> d_edges_all;
-    DevBuf<FwdRec> d_fwd_alt;
+    DevBuf<FwdRec> d_fwd_alt, d_bx_rec;
+    DevBuf<uint32_t> d_bx_cnt, d_bx_off, d_bx_cnt_all, d_bx_off_all, d_fwd_off_local;
+    uint64_t pair_total_sum = 0;  // forward records over all pairs (refresh_pair_totals)
     uint32_t n_edges_local = 0, n_edges_all = 0;
     uint64_t local_fwd = 0;      // forward records produced by this rank's pairs
     uint64_t xchg_var[4] = {0, 0, 0, 0};

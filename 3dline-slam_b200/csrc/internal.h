@@ -38,7 +38,8 @@ struct ViewDev {
     uint32_t seg_off, n_seg;
     uint32_t cam_id;
     float xb;  // max |x1|+|y1| over the view's segments (K1 guard)
-    uint32_t order, pad;
+    uint32_t order;
+    uint32_t needed;  // 0: no pair of this rank touches the view (its per-segment tables are skipped)
 };
 
 struct PairDev {
@@ -52,7 +53,7 @@ struct PairDev {
     uint32_t emit_inverse;  // tgt view is processed after src view (line3D.cc:1994)
     uint64_t mask_base;  // word offset of this pair's bit mask inside the batch buffer
     uint32_t batch_row0; // first row of the batch this pair belongs to
-    uint32_t pad;
+    uint32_t xflag;      // multi-GPU: the target view belongs to another rank's slice (boundary pair)
 };
 
 // forward match record, 32 B (matches_ entries produced by matching, line3D.cc:1169-1181)

@@ -21,8 +21,9 @@ __global__ void __launch_bounds__(256) k0_prep_kernel(const float4* __restrict__
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= S) return;
-    const float4 sg = segs[i];
     const uint32_t v = seg_view[i];
+    if (!views[v].needed) return;  // multi-GPU: a view none of this rank's pairs touches
+    const float4 sg = segs[i];
     const double x1 = (double)sg.x, y1 = (double)sg.y, x2 = (double)sg.z, y2 = (double)sg.w;
 
     // ---- rays (exact) ----

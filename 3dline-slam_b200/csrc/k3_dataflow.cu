@@ -85,7 +85,8 @@ __global__ void __launch_bounds__(256) k3_inv_capacity_kernel(const PairDev* __r
                                                               const uint32_t* __restrict__ fwd_cnt,
                                                               const FwdRec* __restrict__ fwd_rec,
                                                               uint32_t* __restrict__ fwd_row,
-                                                              uint32_t* __restrict__ inv_cap)
+                                                              uint32_t* __restrict__ inv_cap, uint32_t v_lo,
+                                                              uint32_t v_hi)
 {
     const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= n_rows) return;
@@ -93,9 +94,12 @@ __global__ void __launch_bounds__(256) k3_inv_capacity_kernel(const PairDev* __r
     if (!n) return;
     const PairDev& D = pairs[pair_of_row(pairs, P, row)];
     const uint32_t b = fwd_off[row];
+    // inverse slots are only needed (and, in a sharded run, the records only present) for the
+    // target views [v_lo, v_hi) this rank builds
+    const bool slots = D.emit_inverse && D.tgt_view >= v_lo && D.tgt_view < v_hi;
     for (uint32_t e = 0; e < n; ++e) {
         fwd_row[b + e] = row;
-        if (D.emit_inverse) atomicAdd(&inv_cap[D.tgt_base + fwd_rec[b + e].c], 1u);
+        if (slots) atomicAdd(&inv_cap[D.tgt_base + fwd_rec[b + e].c], 1u);
     }
 }
 
@@ -557,7 +561,8 @@ struct FoldArgs {
     uint32_t* view_max;  // [V] ordered-uint maximum score of the view
     WfStats* stats;
     uint32_t S;
-    uint32_t sleep_ns;  // back-off between two polls of a pending score
+    uint32_t g_lo, g_hi;  // L_score is kept for the rows this rank finishes
+    uint32_t sleep_ns;    // back-off between two polls of a pending score
 };
 
 __device__ __forceinline__ float wait_score(FwdRec* fwd_rec, uint32_t f, WfStats* stats, uint32_t sleep_ns)
@@ -618,6 +623,7 @@ __global__ void __launch_bounds__(FOLD_WARPS * 32) k3_fold_kernel(const FoldArgs
             const uint4* __restrict__ prog = a.prog + a.prog_off[g];
             const size_t lbase = a.L_off[g];
             const uint32_t view = a.seg_view[g];
+            const bool mine = g >= a.g_lo && g < a.g_hi;
             const uint32_t T = prog[0].y;
             const uint4* __restrict__ heads = prog + 1;
             const uint4* __restrict__ prs = heads + NH;
@@ -642,7 +648,7 @@ __global__ void __launch_bounds__(FOLD_WARPS * 32) k3_fold_kernel(const FoldArgs
                     if (H.z == 0xffffffffu) continue;  // absent inverse match
                     const float score = fold_siblings(sp + NH, H.y, H.z);
                     if (!(H.x >> 31)) *(volatile float*)&a.fwd_rec[H.w].score = score;
-                    a.L_score[lbase + (H.x & 0x7fffffffu)] = score;
+                    if (mine) a.L_score[lbase + (H.x & 0x7fffffffu)] = score;
                     wmax = fmaxf(wmax, score);
                 }
             } else {
@@ -669,7 +675,7 @@ __global__ void __launch_bounds__(FOLD_WARPS * 32) k3_fold_kernel(const FoldArgs
                         }
                     }
                     if (!inv) *(volatile float*)&a.fwd_rec[H.w].score = score;
-                    a.L_score[lbase + e] = score;
+                    if (mine) a.L_score[lbase + e] = score;
                     wmax = fmaxf(wmax, score);
                 }
             }
@@ -877,11 +883,11 @@ __global__ void __launch_bounds__(FIN_WARPS * 32) k3_finish_kernel(const FinishA
 // ------------------------------------------------------------------------------------------
 int launch_k3_inv_capacity(const PairDev* pairs, uint32_t P, uint32_t n_rows, const uint32_t* fwd_off,
                            const uint32_t* fwd_cnt, const FwdRec* fwd_rec, uint32_t* fwd_row, uint32_t* inv_cap,
-                           cudaStream_t st)
+                           uint32_t v_lo, uint32_t v_hi, cudaStream_t st)
 {
     if (!n_rows || !P) return 0;
     k3_inv_capacity_kernel<<<(n_rows + 255) / 256, 256, 0, st>>>(pairs, P, n_rows, fwd_off, fwd_cnt, fwd_rec, fwd_row,
-                                                                  inv_cap);
+                                                                  inv_cap, v_lo, v_hi);
     return 1;
 }
 
@@ -972,7 +978,7 @@ int launch_k3_fold(const K3Tables& t, cudaStream_t st, int* err)
     FoldArgs f;
     f.seg_view = t.seg_view; f.L_off = t.L_off; f.L_score = t.L_score; f.fwd_rec = t.fwd_rec;
     f.prog_off = t.prog_off; f.prog_nh = t.prog_nh; f.prog = (const uint4*)t.prog; f.view_max = t.view_max;
-    f.stats = (WfStats*)t.stats; f.S = t.S;
+    f.stats = (WfStats*)t.stats; f.S = t.S; f.g_lo = t.g_lo; f.g_hi = t.g_hi;
     int dev = 0, sms = 0, per_sm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

@@ -119,6 +119,102 @@ int launch_score_prep(const float4* lines, uint32_t n_lines, const float4* match
     return 1;
 }
 
+// ---- multi-GPU FORWARD exchange (abi.cu): only the records of boundary pairs (target view in
+// another rank's slice) travel; every rank gets all per-row counts ----
+__device__ __forceinline__ uint32_t pair_of_row_m(const PairDev* __restrict__ pairs, uint32_t P, uint32_t row)
+{
+    uint32_t lo = 0, hi = P;  // largest p with row_base <= row
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (pairs[mid].row_base <= row) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+// bcnt[row - row_lo] = records of the row that travel
+__global__ void __launch_bounds__(256) fwd_bmask_kernel(const PairDev* __restrict__ pairs, uint32_t P,
+                                                        const uint32_t* __restrict__ fwd_cnt, uint32_t row_lo,
+                                                        uint32_t row_hi, uint32_t* __restrict__ bcnt)
+{
+    const uint32_t row = row_lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= row_hi) return;
+    const uint32_t n = fwd_cnt[row];
+    bcnt[row - row_lo] = (n && pairs[pair_of_row_m(pairs, P, row)].xflag) ? n : 0u;
+}
+// sender: boundary records of the rows [row_lo, row_hi) (local layout) -> contiguous export buffer
+__global__ void __launch_bounds__(256) fwd_bgather_kernel(const uint32_t* __restrict__ bcnt,
+                                                          const uint32_t* __restrict__ boff,
+                                                          const uint32_t* __restrict__ fwd_off_local, uint32_t row_lo,
+                                                          uint32_t row_hi, const FwdRec* __restrict__ fwd_rec,
+                                                          FwdRec* __restrict__ out)
+{
+    const uint32_t row = row_lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= row_hi) return;
+    const uint32_t n = bcnt[row - row_lo];
+    if (!n) return;
+    const FwdRec* src = fwd_rec + fwd_off_local[row];
+    FwdRec* dst = out + boff[row - row_lo];
+    for (uint32_t e = 0; e < n; ++e) dst[e] = src[e];
+}
+// receiver: own records (local layout) and the boundary records of the other ranks -> canonical layout
+struct SliceRows {
+    uint32_t row[17];
+};
+__global__ void __launch_bounds__(256) fwd_place_kernel(const unsigned char* __restrict__ all, uint64_t stride, int world,
+                                                        SliceRows sl, int rank, uint32_t n_rows,
+                                                        const uint32_t* __restrict__ fwd_cnt,
+                                                        const uint32_t* __restrict__ fwd_off,
+                                                        const uint32_t* __restrict__ bcnt_all,
+                                                        const uint32_t* __restrict__ boff_all,
+                                                        const FwdRec* __restrict__ own_rec,
+                                                        const uint32_t* __restrict__ own_off_local,
+                                                        FwdRec* __restrict__ out)
+{
+    const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n_rows) return;
+    const uint32_t n = fwd_cnt[row];
+    if (!n) return;
+    int q = 0;
+    while (q + 1 < world && sl.row[q + 1] <= row) ++q;
+    const FwdRec* src = nullptr;
+    if (q == rank) {
+        src = own_rec + own_off_local[row];
+    } else if (bcnt_all[row]) {
+        const uint32_t rows_q = sl.row[q + 1] - sl.row[q];
+        const unsigned char* blob = all + (uint64_t)q * stride + (((uint64_t)rows_q + 7ull) & ~7ull) * 4ull;
+        src = reinterpret_cast<const FwdRec*>(blob) + (boff_all[row] - boff_all[sl.row[q]]);
+    }
+    if (!src) return;
+    FwdRec* dst = out + fwd_off[row];
+    for (uint32_t e = 0; e < n; ++e) dst[e] = src[e];
+}
+int launch_fwd_bmask(const PairDev* pairs, uint32_t P, const uint32_t* fwd_cnt, uint32_t row_lo, uint32_t row_hi,
+                     uint32_t* bcnt, cudaStream_t st)
+{
+    if (row_hi <= row_lo) return 0;
+    fwd_bmask_kernel<<<(row_hi - row_lo + 255) / 256, 256, 0, st>>>(pairs, P, fwd_cnt, row_lo, row_hi, bcnt);
+    return 1;
+}
+int launch_fwd_bgather(const uint32_t* bcnt, const uint32_t* boff, const uint32_t* fwd_off_local, uint32_t row_lo,
+                       uint32_t row_hi, const FwdRec* fwd_rec, FwdRec* out, cudaStream_t st)
+{
+    if (row_hi <= row_lo) return 0;
+    fwd_bgather_kernel<<<(row_hi - row_lo + 255) / 256, 256, 0, st>>>(bcnt, boff, fwd_off_local, row_lo, row_hi,
+                                                                       fwd_rec, out);
+    return 1;
+}
+int launch_fwd_place(const unsigned char* all, uint64_t stride, int world, const uint32_t* slice_row, int rank,
+                     uint32_t n_rows, const uint32_t* fwd_cnt, const uint32_t* fwd_off, const uint32_t* bcnt_all,
+                     const uint32_t* boff_all, const FwdRec* own_rec, const uint32_t* own_off_local, FwdRec* out,
+                     cudaStream_t st)
+{
+    if (!n_rows) return 0;
+    SliceRows sl;
+    for (int q = 0; q <= world && q < 17; ++q) sl.row[q] = slice_row[q];
+    fwd_place_kernel<<<(n_rows + 255) / 256, 256, 0, st>>>(all, stride, world, sl, rank, n_rows, fwd_cnt, fwd_off,
+                                                           bcnt_all, boff_all, own_rec, own_off_local, out);
+    return 1;
+}
+
 // header of a self-describing exchange blob (abi.cu): payload size from the device-side cursor
 __global__ void blob_hdr_kernel(unsigned long long* dst, uint64_t fixed_bytes, uint64_t elem_bytes,
                                 const uint32_t* n_dev, uint64_t n_imm, const uint32_t* flags_dev, uint32_t kind)

@@ -161,6 +161,10 @@ int l3d_scene_begin(l3d_ctx* ctx);
 int l3d_scene_add_view(l3d_ctx* ctx, const l3d_view* view, const float* segs_xyxy,
                        const uint32_t* neighbor_cam_ids, uint32_t num_neighbors);
 int l3d_scene_commit(l3d_ctx* ctx);
+/* the three calls above for n_views views at once: segs_concat holds the views' segments back to
+ * back (views[i].num_segs each), nbrs_concat their neighbour camera ids (nbr_counts[i] each). */
+int l3d_scene_set(l3d_ctx* ctx, const l3d_view* views, uint32_t n_views, const float* segs_concat,
+                  const uint32_t* neighbor_cam_ids_concat, const uint32_t* nbr_counts);
 
 /* replaces Line3D::matchImages (src/line3D.cc:496-640): translate(), spatial regularisers,
  * computeMatches() (matching, orientation filter, scoring, inverse matches, filtering) and the
