@@ -15,8 +15,6 @@
 //            sift-down steps follow the textbook algorithm libstdc++ uses, so equal overlaps pop in
 //            the same order), pops min(kNN, n) (src/line3D.cc:1198-1206), drops the ones that fail
 //            the orientation test and leaves the survivors, in list order, in fin_rec.
-#include <cstdlib>
-
 #include "detmath.cuh"
 #include "exact.cuh"
 #include "internal.h"
@@ -202,8 +200,7 @@ struct __align__(16) K2WarpSmem {
 // candidate, phase B: triangulation + orientation test of the ones that pass (dense lanes again),
 // then the kNN selection in priority-queue pop order and the orientation filter.  Only matches with
 // four positive depths are ever written to memory. ----
-template <int MINB>
-__global__ void __launch_bounds__(K2_WARPS * 32, MINB) k2_row_kernel(
+__global__ void __launch_bounds__(K2_WARPS * 32) k2_row_kernel(
     const PairDev* __restrict__ pairs, const K1Cta* __restrict__ ctas, const uint32_t* __restrict__ mask,
     const uint32_t* __restrict__ cand_off, const float4* __restrict__ segs, const SegRays* __restrict__ rays,
     const double* __restrict__ midray, const SegPlane* __restrict__ planes, const ViewDev* __restrict__ views,
@@ -476,20 +473,11 @@ int launch_k2_exact(const PairDev* pairs, const K1Cta* ctas, uint32_t n_ctas, ui
     if (n_ctas == 0) return 0;
     (void)n_rows;
     (void)n_cand;
-    static int minb = -1;
-    if (minb < 0) {
-        const char* e = getenv("L3D_K2_MINB");  // tuning hook: resident CTAs per SM the kernel is compiled for
-        minb = e ? atoi(e) : 4;
-    }
-    const dim3 grid(n_ctas * (K2_ROWS / K2_SUB)), block(K2_WARPS * 32);
-#define K2_LAUNCH(MB)                                                                                             \
-    k2_row_kernel<MB><<<grid, block, 0, st>>>(pairs, ctas, mask, cand_off, segs, rays, midray, planes, views, heap, \
-                                              cand_rec, fin_rec, fin_cnt, thr, (double)max_image_width, knn,       \
-                                              apply_orient)
-    if (minb >= 8) K2_LAUNCH(8);
-    else if (minb >= 6) K2_LAUNCH(6);
-    else K2_LAUNCH(4);
-#undef K2_LAUNCH
+    // 128 registers, 4 CTAs = 16 warps per SM: compiling for more resident warps (80 / 64 registers)
+    // spills and was measured slower (1.11 ms -> 1.11 / 1.39 ms on C2)
+    k2_row_kernel<<<n_ctas * (K2_ROWS / K2_SUB), K2_WARPS * 32, 0, st>>>(pairs, ctas, mask, cand_off, segs, rays, midray,
+                                                                        planes, views, heap, cand_rec, fin_rec, fin_cnt,
+                                                                        thr, (double)max_image_width, knn, apply_orient);
     return 1;
 }
 
