@@ -97,6 +97,10 @@ def lib():
         L.l3d_scene_add_view.argtypes = [vp, C.POINTER(View), vp, vp, u32]
         L.l3d_scene_commit.argtypes = [vp]
         L.l3d_scene_set.argtypes = [vp, vp, u32, vp, vp, vp]
+        L.l3d_scene_set_wps.argtypes = [vp, vp, u32, vp, vp, vp]
+        L.l3d_scene_add_view_wps.argtypes = [vp, C.POINTER(View), vp, vp, u32]
+        L.l3d_neighbors_from_worldpoints.argtypes = [vp, u32, vp, vp, u32, vp, vp]
+        L.l3d_get_neighbors.argtypes = [vp, u32, vp, u32, C.POINTER(u32)]
         L.l3d_match_images.argtypes = [vp, C.POINTER(Params)]
         L.l3d_match_stage12.argtypes = [vp, C.POINTER(Params)]
         L.l3d_match_stage3.argtypes = [vp]
@@ -227,8 +231,7 @@ class Line3D:
                  device: int = -1, stream: int = 0):
         if not use_GPU:
             raise L3DError("l3dpp-b200 has no CPU path (use_GPU must be True)")
-        if neighbors_by_worldpoints:
-            raise L3DError("neighbors_by_worldpoints=True is not supported yet: pass explicit neighbour lists")
+        self.neighbors_by_worldpoints = bool(neighbors_by_worldpoints)
         self.ctx = Context(device, stream)
         self.L = self.ctx.L
         self.h = self.ctx.h
@@ -266,10 +269,18 @@ class Line3D:
         self._dirty = True
 
     def load_scene(self, scene):
+        wn = (lambda v: v.worldpoints) if self.neighbors_by_worldpoints else (lambda v: v.neighbors)
         for v in scene.views:
-            self.addImage(v.cam_id, (v.width, v.height), v.K, v.R, v.t, v.median_depth, v.neighbors, v.segs)
+            self.addImage(v.cam_id, (v.width, v.height), v.K, v.R, v.t, v.median_depth, wn(v), v.segs)
         for v in scene.views:
-            self.UpdataImage(v.cam_id, v.R, v.t, v.median_depth, v.neighbors)
+            self.UpdataImage(v.cam_id, v.R, v.t, v.median_depth, wn(v))
+
+    def neighbors(self, cam_id, cap=1024):
+        """Visual neighbours used by the last matchImages (camera ids, ascending)."""
+        out = np.zeros(cap, dtype=np.uint32)
+        n = C.c_uint32(0)
+        self._ck(self.L.l3d_get_neighbors(self.h, int(cam_id), _p(out), cap, C.byref(n)))
+        return out[:n.value].tolist()
 
     def _pack(self):
         """Host-side packing of the scene for l3d_scene_set (kept until a view changes)."""
@@ -292,7 +303,8 @@ class Line3D:
         if self._dirty or self._packed is None:
             self._pack()
         arr, n, segs, nb, cnt = self._packed
-        self._ck(self.L.l3d_scene_set(self.h, C.cast(arr, C.c_void_p), n, _p(segs), _p(nb), _p(cnt)))
+        fn = self.L.l3d_scene_set_wps if self.neighbors_by_worldpoints else self.L.l3d_scene_set
+        self._ck(fn(self.h, C.cast(arr, C.c_void_p), n, _p(segs), _p(nb), _p(cnt)))
         self._dirty = False
 
     def _params(self, sigma_position, sigma_angle, num_neighbors, epipolar_overlap, kNN, const_regularization_depth):
@@ -445,6 +457,34 @@ class Line3D:
 X_FORWARD, X_PROGRAMS, X_HYPOTHESES, X_EDGES = 0, 1, 2, 3
 
 
+def _pack_views(views):
+    arr = (View * max(len(views), 1))()
+    for i, v in enumerate(views):
+        vv = arr[i]
+        vv.cam_id, vv.width, vv.height, vv.num_segs = v.cam_id, v.width, v.height, v.segs.shape[0]
+        vv.K[:] = _f64(v.K).reshape(9).tolist()
+        vv.R[:] = _f64(v.R).reshape(9).tolist()
+        vv.t[:] = _f64(v.t).reshape(3).tolist()
+        vv.median_depth = v.median_depth
+    return arr
+
+
+def neighbors_from_worldpoints(scene, num_neighbors):
+    """Host-only (no GPU needed): {cam_id: [neighbour cam ids]} chosen from the views' world-point lists
+    like Line3D::findVisualNeighborsFromWPs (reference src/line3D.cc:723-843)."""
+    L = lib()
+    arr = _pack_views(scene.views)
+    wps = np.ascontiguousarray(np.concatenate([np.asarray(v.worldpoints, dtype=np.uint32) for v in scene.views]))
+    cnt = np.array([len(v.worldpoints) for v in scene.views], dtype=np.uint32)
+    nn = max(int(num_neighbors), 2)
+    out = np.zeros((len(scene.views), nn), dtype=np.uint32)
+    oc = np.zeros(len(scene.views), dtype=np.uint32)
+    rc = L.l3d_neighbors_from_worldpoints(C.cast(arr, C.c_void_p), len(scene.views), _p(wps), _p(cnt), nn, _p(out), _p(oc))
+    if rc:
+        raise L3DError(L.l3d_last_error().decode())
+    return {v.cam_id: out[i, :oc[i]].tolist() for i, v in enumerate(scene.views)}
+
+
 def cluster_edges(ij, w, n):
     """Stand-alone F-H clustering (host; src/clustering.cc:7-48)."""
     L = lib()
@@ -458,7 +498,7 @@ def cluster_edges(ij, w, n):
 
 
 def run_scene(scene, filter_mode=0, keep_scored=False, reconstruct=True, device=-1, stream=0):
-    l3 = Line3D("", False, scene.max_image_width, 3000, False, True, device, stream)
+    l3 = Line3D("", False, scene.max_image_width, 3000, scene.neighbors_by_worldpoints, True, device, stream)
     l3.filter_mode = filter_mode
     l3.keep_scored = keep_scored
     l3.load_scene(scene)

@@ -62,43 +62,75 @@ int l3d_scene_begin(l3d_ctx* ctx)
     if (!ctx) return fail(L3D_ERR_ARG, "ctx is NULL");
     ctx->views.clear();
     ctx->cam2view.clear();
+    ctx->by_worldpoints = false;
     ctx->committed = false;
     ctx->stage = 0;
     ctx->pairs.clear();
     return L3D_OK;
 }
 
+static int add_view(l3d_ctx* ctx, const l3d_view* view, const float* segs, const uint32_t* nbrs, uint32_t nn, bool wps);
+
 int l3d_scene_add_view(l3d_ctx* ctx, const l3d_view* view, const float* segs, const uint32_t* nbrs, uint32_t nn)
+{
+    return add_view(ctx, view, segs, nbrs, nn, false);
+}
+
+// neighbors_by_worldpoints = true (Line3D::Line3D, src/line3D.cc:60-75): the list holds the world
+// points the view observes; the visual neighbours are chosen by l3d_match_images
+int l3d_scene_add_view_wps(l3d_ctx* ctx, const l3d_view* view, const float* segs, const uint32_t* wps, uint32_t nw)
+{
+    return add_view(ctx, view, segs, wps, nw, true);
+}
+
+static int add_view(l3d_ctx* ctx, const l3d_view* view, const float* segs, const uint32_t* nbrs, uint32_t nn, bool wps)
 {
     if (!ctx || !view) return fail(L3D_ERR_ARG, "NULL argument");
     if (ctx->committed) return fail(L3D_ERR_STATE, "scene already committed; call l3d_scene_begin");
+    if (!ctx->views.empty() && ctx->by_worldpoints != wps)
+        return fail(L3D_ERR_ARG, "explicit neighbour lists and world-point lists cannot be mixed in one scene");
+    ctx->by_worldpoints = wps;
     // same argument checks as Line3D::addImage (src/line3D.cc:123-205)
     if (std::max(view->width, view->height) < 400)
         return fail(L3D_ERR_ARG, "image is too small for reliable results: %u px (larger side should be >= 400px)",
                     std::max(view->width, view->height));
     for (auto& hv : ctx->views)
         if (hv.v.cam_id == view->cam_id) return fail(L3D_ERR_ARG, "camera ID [%u] already in use!", view->cam_id);
-    if (nn == 0) return fail(L3D_ERR_ARG, "view [%u] has no visual neighbors!", view->cam_id);
+    if (nn == 0 && !wps) return fail(L3D_ERR_ARG, "view [%u] has no visual neighbors!", view->cam_id);
+    if (nn && !nbrs) return fail(L3D_ERR_ARG, "NULL argument");
     if (view->num_segs == 0 || !segs) return fail(L3D_ERR_ARG, "no line segments found in image [%u]!", view->cam_id);
     HostView hv;
     hv.v = *view;
     hv.segs.assign(segs, segs + 4 * (size_t)view->num_segs);
-    hv.nbrs.assign(nbrs, nbrs + nn);
+    if (wps) hv.wps.assign(nbrs, nbrs + nn);
+    else hv.nbrs.assign(nbrs, nbrs + nn);
     hv.cam.init(view->K, view->R, view->t);
     ctx->views.push_back(std::move(hv));
     return L3D_OK;
 }
 
 // begin + add_view x n + commit in one call (the views' segments / neighbour lists are concatenated)
+static int scene_set(l3d_ctx* ctx, const l3d_view* views, uint32_t n_views, const float* segs_concat,
+                     const uint32_t* nbrs_concat, const uint32_t* nbr_counts, bool wps);
 int l3d_scene_set(l3d_ctx* ctx, const l3d_view* views, uint32_t n_views, const float* segs_concat,
                   const uint32_t* nbrs_concat, const uint32_t* nbr_counts)
+{
+    return scene_set(ctx, views, n_views, segs_concat, nbrs_concat, nbr_counts, false);
+}
+int l3d_scene_set_wps(l3d_ctx* ctx, const l3d_view* views, uint32_t n_views, const float* segs_concat,
+                      const uint32_t* wps_concat, const uint32_t* wp_counts)
+{
+    return scene_set(ctx, views, n_views, segs_concat, wps_concat, wp_counts, true);
+}
+static int scene_set(l3d_ctx* ctx, const l3d_view* views, uint32_t n_views, const float* segs_concat,
+                     const uint32_t* nbrs_concat, const uint32_t* nbr_counts, bool wps)
 {
     if (!ctx || !views || !segs_concat || !nbrs_concat || !nbr_counts) return fail(L3D_ERR_ARG, "NULL argument");
     int rc = l3d_scene_begin(ctx);
     if (rc) return rc;
     size_t so = 0, no = 0;
     for (uint32_t i = 0; i < n_views; ++i) {
-        rc = l3d_scene_add_view(ctx, &views[i], segs_concat + 4 * so, nbrs_concat + no, nbr_counts[i]);
+        rc = add_view(ctx, &views[i], segs_concat + 4 * so, nbrs_concat + no, nbr_counts[i], wps);
         if (rc) return rc;
         so += views[i].num_segs;
         no += nbr_counts[i];
@@ -263,6 +295,18 @@ int plan_pairs(l3d_ctx* ctx)
     // ascending list of their view indices (view index order == camera id order), made at commit.
     // computeMatches pair order (src/line3D.cc:848-887): (s, t) is skipped iff the pair was already
     // created from the other side, i.e. t < s and s is a neighbour of t.
+    if (ctx->by_worldpoints) {  // Line3D::matchImages, src/line3D.cc:604-625 (after translate())
+        std::vector<const hg::Camera*> cams(V);
+        std::vector<float> md(V);
+        std::vector<std::vector<uint32_t>> wps(V), nb;
+        for (uint32_t v = 0; v < V; ++v) {
+            cams[v] = &ctx->views[v].cam;
+            md[v] = ctx->views[v].median_depth;
+            wps[v] = ctx->views[v].wps;
+        }
+        hg::visual_neighbors_from_worldpoints(cams, md, wps, prm.num_neighbors, nb);
+        for (uint32_t v = 0; v < V; ++v) ctx->views[v].nb_views = nb[v];
+    }
     ctx->pairs.clear();
     for (uint32_t s = 0; s < V; ++s)
         for (uint32_t t : ctx->views[s].nb_views) {
@@ -998,6 +1042,57 @@ int l3d_affinity(l3d_ctx* ctx)
     int rc = l3d_affinity_edges(ctx);
     if (rc) return rc;
     return l3d_affinity_ids(ctx);
+}
+
+// Host-only: the visual neighbours Line3D::matchImages would choose from world-point lists
+// (Line3D::findVisualNeighborsFromWPs, src/line3D.cc:723-843, after Line3D::translate).  No device needed.
+int l3d_neighbors_from_worldpoints(const l3d_view* views, uint32_t n_views, const uint32_t* wps_concat,
+                                   const uint32_t* wp_counts, uint32_t num_neighbors, uint32_t* out_cam_ids,
+                                   uint32_t* out_counts)
+{
+    if (!views || !wps_concat || !wp_counts || !out_cam_ids || !out_counts) return fail(L3D_ERR_ARG, "NULL argument");
+    l3d_ctx t;
+    size_t no = 0;
+    for (uint32_t i = 0; i < n_views; ++i) {
+        HostView hv;
+        hv.v = views[i];
+        hv.wps.assign(wps_concat + no, wps_concat + no + wp_counts[i]);
+        no += wp_counts[i];
+        hv.cam.init(views[i].K, views[i].R, views[i].t);
+        t.views.push_back(std::move(hv));
+    }
+    std::sort(t.views.begin(), t.views.end(), [](const HostView& a, const HostView& b) { return a.v.cam_id < b.v.cam_id; });
+    compute_translation(&t);
+    apply_translation(&t, -1.0);
+    std::vector<const hg::Camera*> cams(n_views);
+    std::vector<float> md(n_views, 0.0f);  // View::median_depth_ starts at 0 (src/view.cc:13)
+    std::vector<std::vector<uint32_t>> wps(n_views), nb;
+    for (uint32_t v = 0; v < n_views; ++v) {
+        cams[v] = &t.views[v].cam;
+        wps[v] = t.views[v].wps;
+    }
+    hg::visual_neighbors_from_worldpoints(cams, md, wps, (unsigned)std::max((int)num_neighbors, 2), nb);
+    // output rows follow the order of `views` as given
+    for (uint32_t i = 0; i < n_views; ++i) {
+        uint32_t v = 0;
+        while (t.views[v].v.cam_id != views[i].cam_id) ++v;
+        out_counts[i] = (uint32_t)nb[v].size();
+        for (size_t k = 0; k < nb[v].size(); ++k) out_cam_ids[(size_t)i * num_neighbors + k] = t.views[nb[v][k]].v.cam_id;
+    }
+    return L3D_OK;
+}
+
+// neighbours of a view as used by the last l3d_match_images (camera ids, ascending)
+int l3d_get_neighbors(l3d_ctx* ctx, uint32_t cam_id, uint32_t* out, uint32_t cap, uint32_t* count)
+{
+    if (!ctx || !count) return fail(L3D_ERR_ARG, "NULL argument");
+    auto f = ctx->cam2view.find(cam_id);
+    if (f == ctx->cam2view.end()) return fail(L3D_ERR_ARG, "unknown camera %u", cam_id);
+    const std::vector<uint32_t>& nb = ctx->views[f->second].nb_views;
+    *count = (uint32_t)nb.size();
+    if (cap < nb.size()) return fail(L3D_ERR_CAPACITY, "need %zu ids", nb.size());
+    for (size_t k = 0; k < nb.size(); ++k) out[k] = ctx->views[nb[k]].v.cam_id;
+    return L3D_OK;
 }
 
 // Felzenszwalb-Huttenlocher clustering, src/clustering.cc:7-48 + include/universe.h:59-117

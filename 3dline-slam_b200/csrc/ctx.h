@@ -112,7 +112,8 @@ struct HostView {
     l3d_view v;
     std::vector<float> segs;
     std::vector<uint32_t> nbrs;
-    std::vector<uint32_t> nb_views;  // neighbours as ascending view indices (l3d_scene_commit)
+    std::vector<uint32_t> nb_views;  // neighbours as ascending view indices (l3d_scene_commit / plan_pairs)
+    std::vector<uint32_t> wps;       // observed world points (neighbors_by_worldpoints mode)
     hg::Camera cam;
     float k = 0.0f, median_depth = 0.0f, median_sigma = 0.0f;
     uint32_t seg_off = 0;
@@ -177,6 +178,7 @@ struct l3d_ctx {
     std::vector<HostView> views;  // sorted by cam id at commit
     std::map<uint32_t, uint32_t> cam2view;
     bool committed = false;
+    bool by_worldpoints = false;  // neighbours are chosen from world-point lists at match time
     uint32_t S = 0;  // total segments
     hg::V3 translation{0, 0, 0};
     float two_sigA_sqr = 200.0f, epi_overlap = 0.25f;

@@ -1,6 +1,9 @@
 // host_geom.cpp -- see host_geom.h.  Compile with -ffp-contract=off.
 #include "host_geom.h"
 
+#include <algorithm>
+#include <unordered_map>
+
 #include <cstring>
 
 namespace l3d {
@@ -91,6 +94,82 @@ M3 fundamental(const Camera& s, const Camera& tg)
     T.m[6] = -tt.y; T.m[7] = tt.x;  T.m[8] = 0.0;
     const M3 E = matmul(T, R);
     return matmul(matmul(inverse(transpose(tg.K)), E), inverse(s.K));
+}
+
+void visual_neighbors_from_worldpoints(const std::vector<const Camera*>& cams, const std::vector<float>& median_depth,
+                                       const std::vector<std::vector<uint32_t>>& wps, unsigned num_neighbors,
+                                       std::vector<std::vector<uint32_t>>& out)
+{
+    const uint32_t V = (uint32_t)cams.size();
+    out.assign(V, std::vector<uint32_t>());
+    // worldpoints2views_: one entry per observation, in view order (the order addImage ran)
+    std::unordered_map<uint32_t, std::vector<uint32_t>> wp2views;
+    for (uint32_t v = 0; v < V; ++v)
+        for (uint32_t wp : wps[v]) wp2views[wp].push_back(v);
+    struct VN {
+        uint32_t view;
+        float score, axis_angle, dist_score;
+    };
+    std::vector<uint32_t> common(V);
+    for (uint32_t v = 0; v < V; ++v) {
+        std::fill(common.begin(), common.end(), 0u);
+        bool any = false;
+        for (uint32_t wp : wps[v])
+            for (uint32_t o : wp2views[wp])
+                if (o != v) {
+                    ++common[o];
+                    any = true;
+                }
+        if (!any) continue;
+        const Camera& cv = *cams[v];
+        const V3 ray_v = normalized(mul(cv.RtKinv, cv.pp));
+        std::vector<VN> nb;  // candidates in ascending view order (std::map iteration order)
+        for (uint32_t o = 0; o < V; ++o) {
+            if (!common[o]) continue;
+            const Camera& co = *cams[o];
+            VN vn;
+            vn.view = o;
+            vn.score = 2.0f * float(common[o]) / float(wps[v].size() + wps[o].size());
+            // View::opticalAxesAngle (src/view.cc:486-492)
+            vn.axis_angle = (float)det_acos(std::fmin(std::fmax(dot(ray_v, normalized(mul(co.RtKinv, co.pp))), -1.0), 1.0));
+            // View::distanceVisualNeighborScore (src/view.cc:516-530): |x| + |y| of the other centre in this camera
+            const V3 c = mul(cv.R, co.C) + cv.t;
+            const float d1 = (float)std::fabs(1.0 * c.x + 0.0 * c.y + 0.0 * c.z);
+            const float d2 = (float)std::fabs(0.0 * c.x + 1.0 * c.y + 0.0 * c.z);
+            vn.dist_score = d1 + d2;
+            if (vn.axis_angle < 1.571f && common[o] > 4) nb.push_back(vn);
+        }
+        // std::list::sort is a stable merge sort
+        std::stable_sort(nb.begin(), nb.end(), [](const VN& a, const VN& b) { return a.score > b.score; });
+        if (nb.size() > num_neighbors) {
+            const std::vector<VN> tmp = nb;
+            const float score_t = 0.80f * nb.front().score;
+            size_t bigger = 0;
+            while (bigger < nb.size() && nb[bigger].score > score_t) ++bigger;
+            nb.resize(bigger);
+            std::stable_sort(nb.begin(), nb.end(), [](const VN& a, const VN& b) { return a.dist_score > b.dist_score; });
+            if (nb.size() > num_neighbors / 2) nb.resize(num_neighbors / 2);
+            nb.insert(nb.end(), tmp.begin(), tmp.end());
+        }
+        auto baseline = [&](uint32_t o) {
+            const V3 d = cv.C - cams[o]->C;
+            return (float)std::sqrt(dot(d, d));
+        };
+        const float min_baseline = cv.spatial_regularizer(0.5f) * median_depth[v];
+        std::vector<uint32_t> used;  // kept ascending (std::set)
+        for (size_t i = 0; i < nb.size() && used.size() < num_neighbors; ++i) {
+            const uint32_t o = nb[i].view;
+            if (std::binary_search(used.begin(), used.end(), o) || !(baseline(o) > min_baseline)) continue;
+            bool valid = true;
+            for (uint32_t u : used)
+                if (!(baseline(u) > min_baseline)) {
+                    valid = false;
+                    break;
+                }
+            if (valid) used.insert(std::lower_bound(used.begin(), used.end(), o), o);
+        }
+        out[v] = used;
+    }
 }
 
 }  // namespace hg

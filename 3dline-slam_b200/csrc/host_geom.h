@@ -5,6 +5,7 @@
 #pragma once
 #include <cmath>
 #include <cstdint>
+#include <vector>
 
 namespace l3d {
 namespace hg {
@@ -75,6 +76,13 @@ struct Camera {
 };
 
 M3 fundamental(const Camera& src, const Camera& tgt);
+
+// Line3D::findVisualNeighborsFromWPs (src/line3D.cc:723-843) for every view: wps[v] = the world
+// points view v observes (processWPlist, src/line3D.cc:230-241), median_depth[v] = View::median_depth()
+// (0 for a freshly added view, src/view.cc:13).  out[v] = ascending view indices of its neighbours.
+void visual_neighbors_from_worldpoints(const std::vector<const Camera*>& cams, const std::vector<float>& median_depth,
+                                       const std::vector<std::vector<uint32_t>>& wps, unsigned num_neighbors,
+                                       std::vector<std::vector<uint32_t>>& out);
 
 }  // namespace hg
 }  // namespace l3d

@@ -165,6 +165,21 @@ int l3d_scene_commit(l3d_ctx* ctx);
  * back (views[i].num_segs each), nbrs_concat their neighbour camera ids (nbr_counts[i] each). */
 int l3d_scene_set(l3d_ctx* ctx, const l3d_view* views, uint32_t n_views, const float* segs_concat,
                   const uint32_t* neighbor_cam_ids_concat, const uint32_t* nbr_counts);
+/* neighbors_by_worldpoints = true (Line3D::Line3D src/line3D.cc:60-75, processWPlist :230-241): the
+ * lists hold the world-point ids each view observes (VisualSfM .nvm input); l3d_match_images then
+ * chooses the visual neighbours like Line3D::findVisualNeighborsFromWPs (src/line3D.cc:723-843).
+ * All views of a scene use the same kind of list. */
+int l3d_scene_add_view_wps(l3d_ctx* ctx, const l3d_view* view, const float* segs_xyxy,
+                           const uint32_t* worldpoint_ids, uint32_t num_worldpoints);
+int l3d_scene_set_wps(l3d_ctx* ctx, const l3d_view* views, uint32_t n_views, const float* segs_concat,
+                      const uint32_t* worldpoint_ids_concat, const uint32_t* wp_counts);
+/* host-only (no device): the neighbours the call above would choose; out_cam_ids has
+ * n_views x num_neighbors slots, out_counts[i] of row i are filled (camera ids, ascending) */
+int l3d_neighbors_from_worldpoints(const l3d_view* views, uint32_t n_views, const uint32_t* wps_concat,
+                                   const uint32_t* wp_counts, uint32_t num_neighbors,
+                                   uint32_t* out_cam_ids, uint32_t* out_counts);
+/* visual neighbours of a view as used by the last l3d_match_images (camera ids, ascending) */
+int l3d_get_neighbors(l3d_ctx* ctx, uint32_t cam_id, uint32_t* out, uint32_t cap, uint32_t* count);
 
 /* replaces Line3D::matchImages (src/line3D.cc:496-640): translate(), spatial regularisers,
  * computeMatches() (matching, orientation filter, scoring, inverse matches, filtering) and the

@@ -8,6 +8,9 @@
                      derives from the world points (Line3D::findVisualNeighborsFromWPs,
                      src/line3D.cc:723-843).  /root/reference does not exist on the GPU box, hence
                      the committed copy.
+  c1_nvm_wps.npz     the world-point ids every camera of that dump observes (input of the
+                     neighbors_by_worldpoints mode; with them the product must choose exactly the
+                     neighbours frozen in c1_nvm_scene.npz)
   c1_nvm_expected.npz / tiny_expected.npz
                      outputs of the oracle on those inputs (pairs, filtered lists, hypotheses,
                      affinity edges, cluster ids), the regression pin for both the oracle (CPU test)
@@ -72,6 +75,9 @@ def main():
     o.load_scene(sc)
     p = sc.params
     o.match_images(p["sigma_p"], p["sigma_a"], p["num_neighbors"], p["epipolar_overlap"], p["knn"], p["const_reg_depth"])
+    # the world-point lists themselves (neighbors_by_worldpoints input of the product / of the oracle)
+    np.savez_compressed(os.path.join(HERE, "c1_nvm_wps.npz"),
+                        **{"wps_%d" % v.cam_id: np.asarray(v.worldpoints, np.uint32) for v in sc.views})
     for v in sc.views:                       # freeze the world-point neighbours as explicit lists
         v.neighbors = o.neighbors(v.cam_id)
         v.worldpoints = None

@@ -137,5 +137,15 @@ def test_error_behaviour_mirrors_addImage(api, scene_mod):
     p.sigma_p, p.sigma_a, p.num_neighbors, p.epipolar_overlap, p.knn, p.max_image_width = 5, 10, 10, 0.25, 10, -1
     assert L.l3d_scene_commit(h) == 0
     assert L.l3d_match_images(h, C.byref(p)) == -1 and b"max_image_width" in L.l3d_last_error()
+    # explicit neighbour lists and world-point lists cannot be mixed in one scene
+    assert L.l3d_scene_begin(h) == 0
+    assert add(0, 640, 480, v.segs, [1]) == 0
+    vv = api.View()
+    vv.cam_id, vv.width, vv.height, vv.num_segs = 1, 640, 480, len(v.segs)
+    vv.K[:] = v.K.ravel().tolist(); vv.R[:] = v.R.ravel().tolist(); vv.t[:] = v.t.tolist()
+    wps = np.arange(8, dtype=np.uint32)
+    segs = np.ascontiguousarray(v.segs, np.float32)
+    assert L.l3d_scene_add_view_wps(h, C.byref(vv), segs.ctypes.data, wps.ctypes.data, wps.size) == -1
+    assert b"cannot be mixed" in L.l3d_last_error()
     with pytest.raises(api.L3DError):
-        api.Line3D("", False, 640, 3000, True)      # neighbors_by_worldpoints is not supported
+        api.Line3D("", False, 640, 3000, False, False)   # use_GPU=False: there is no CPU path

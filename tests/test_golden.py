@@ -1,9 +1,40 @@
 """Golden fixtures (tests/golden): BASELINE config 1 (cameras + world-point visibility of the
 reference's NVM dump, frozen neighbour lists) and the tiny synthetic scene.  CPU: the oracle
 reproduces the committed expectation; GPU: so does the CUDA path, through the C ABI."""
+import os
+
+import numpy as np
 import pytest
 
 import golden_utils
+
+
+def _c1_with_worldpoints():
+    sc = golden_utils.load_scene("c1_nvm_scene.npz")
+    wps = np.load(os.path.join(golden_utils.HERE, "c1_nvm_wps.npz"))
+    for v in sc.views:
+        v.worldpoints = wps["wps_%d" % v.cam_id].tolist()
+    return sc
+
+
+def test_world_point_neighbours_match_golden_c1(api, oracle):
+    """Host-only part of the nvm input path (Line3D::findVisualNeighborsFromWPs): from the world-point
+    lists of the reference's NVM dump the product chooses exactly the frozen neighbour lists, for the
+    reference's num_neighbors and for others (against the oracle)."""
+    sc = _c1_with_worldpoints()
+    got = api.neighbors_from_worldpoints(sc, 10)
+    for v in sc.views:
+        assert got[v.cam_id] == list(v.neighbors), v.cam_id
+    sc.neighbors_by_worldpoints = True
+    p = sc.params
+    for nn in (2, 5, 16):
+        o = oracle.OracleLine3D(sc.max_image_width, True)
+        o.load_scene(sc)
+        o.match_images(p["sigma_p"], p["sigma_a"], nn, p["epipolar_overlap"], p["knn"], p["const_reg_depth"])
+        got = api.neighbors_from_worldpoints(sc, nn)
+        for v in sc.views:
+            assert got[v.cam_id] == list(o.neighbors(v.cam_id)), (nn, v.cam_id)
+        o.close()
 
 
 def test_oracle_reproduces_golden_c1(oracle):
@@ -31,3 +62,15 @@ def test_cuda_reproduces_golden_c1(api):
 def test_cuda_reproduces_golden_tiny(api, scene_mod):
     sc = scene_mod.make_scene("tiny")
     golden_utils.check_against_golden(api.run_scene(sc), sc, "tiny_expected.npz")
+
+
+@pytest.mark.gpu
+def test_cuda_world_point_mode_reproduces_golden_c1(api):
+    """neighbors_by_worldpoints=True through the C ABI: same neighbours, same everything."""
+    sc = _c1_with_worldpoints()
+    frozen = {v.cam_id: list(v.neighbors) for v in sc.views}
+    sc.neighbors_by_worldpoints = True
+    l3 = api.run_scene(sc)
+    for v in sc.views:
+        assert l3.neighbors(v.cam_id) == frozen[v.cam_id]
+    golden_utils.check_against_golden(l3, sc, "c1_nvm_expected.npz")
