@@ -70,11 +70,18 @@ __device__ __forceinline__ float rcp_approx(float x)
 
 struct RowEpi {
     float A1, B1, C1, A2, B2, C2;  // epipolar lines of both endpoints, |(A,B)| = 1
-    float cN1, cN2;                // numerator error bounds
+    float cN;                      // numerator error bound (the larger of the two lines')
     bool degenerate;
 };
 
 // one pair test; returns true if the pair may be a match (candidate)
+//
+// Every test is a rejection ("reject if ..."), so NaN never rejects.  A denominator close to 0
+// needs no special case: the error bound grows like 1/|D| -- for |D| below ~10 u the bound exceeds
+// |s| itself (cD/|D| > 3) and the numerator part exceeds every image coordinate (cN/|D| > 800 px),
+// so nothing can be rejected; D = 0 (or a denormal, flushed by the .ftz reciprocal) gives inf/NaN in
+// every comparison.  The reference's "outer distance < 1 px => overlap 0" rule is left to the exact
+// kernel: it cannot fire for segments longer than a pixel.
 __device__ __forceinline__ bool pair_candidate(const RowEpi& e, const float4 d0, const float4 d1, float thr,
                                                float k2thr)
 {
@@ -87,21 +94,17 @@ __device__ __forceinline__ bool pair_candidate(const RowEpi& e, const float4 d0,
     const float r2 = rcp_approx(D2);
     const float s1 = -N1 * r1;
     const float s2 = -N2 * r2;
-    const float e1 = fmaf(fabsf(s1), cD, e.cN1) * fabsf(r1);
-    const float e2 = fmaf(fabsf(s2), cD, e.cN2) * fabsf(r2);
-    const float D = fmaxf(e1, e2);
     const float lo = fminf(s1, s2), hi = fmaxf(s1, s2);
+    // one bound for both intersection parameters: (cN + cD max|s|) max|1/D|
+    const float D = fmaf(fmaxf(fabsf(lo), fabsf(hi)), cD, e.cN) * fmaxf(fabsf(r1), fabsf(r2));
     const float L = d1.x, slo = d1.y, shi = d1.z, g = d1.w;
-    // rejection tests (NaN never rejects)
     bool rej = (hi - D > shi) | (lo + D < slo);
     const float inner = fminf(hi, L) - fmaxf(lo, 0.0f);
     const float outer = fmaxf(hi, L) - fminf(lo, 0.0f);
     const float margin = fmaf(-thr, outer, inner);
     const float G = fmaf(D, k2thr, fmaf(outer, 1.0e-6f, g));
     rej |= (margin < -G);
-    rej |= (outer + 2.0f * D + g < 0.999f);
-    const bool force = (fabsf(D1) < 1.0e-20f) | (fabsf(D2) < 1.0e-20f);
-    return force | !rej;
+    return !rej;
 }
 
 __global__ void __launch_bounds__(K1_ROWS) k1_pairtest_kernel(const PairDev* __restrict__ pairs,
@@ -141,7 +144,7 @@ __global__ void __launch_bounds__(K1_ROWS) k1_pairtest_kernel(const PairDev* __r
     RowEpi e;
     e.degenerate = false;
     e.A1 = e.B1 = e.C1 = e.A2 = e.B2 = e.C2 = 0.0f;
-    e.cN1 = e.cN2 = 0.0f;
+    e.cN = 0.0f;
     if (row_ok) {
         const float4 sg = segs[P.src_off + r];
         const double p1x = sg.x, p1y = sg.y, p2x = sg.z, p2y = sg.w;
@@ -155,8 +158,7 @@ __global__ void __launch_bounds__(K1_ROWS) k1_pairtest_kernel(const PairDev* __r
         e.A2 = (float)(a2 / n2); e.B2 = (float)(b2 / n2); e.C2 = (float)(c2 / n2);
         const float xb = view_xb[P.tgt_view];
         const float u8 = 8.0f * 5.9604645e-08f;
-        e.cN1 = u8 * (xb + fabsf(e.C1));
-        e.cN2 = u8 * (xb + fabsf(e.C2));
+        e.cN = u8 * (xb + fmaxf(fabsf(e.C1), fabsf(e.C2)));
         const float chk = e.A1 + e.B1 + e.C1 + e.A2 + e.B2 + e.C2;
         e.degenerate = !(fabsf(chk) < 3.0e38f);  // NaN or Inf anywhere
     }
