@@ -19,13 +19,13 @@ struct __align__(16) SegDesc {
 };
 static_assert(sizeof(SegDesc) == 32, "SegDesc must be 32 bytes");
 
-struct SegRays {
+struct __align__(16) SegRays {  // 16-byte aligned: gathered with three 128-bit loads per lane
     double r1[3], r2[3];
 };
 
 // plane through the camera centre spanned by the two endpoint rays (Line3D::triangulationDepths,
 // src/line3D.cc:1373-1378): unit normal and its dot product with the (translated) camera centre
-struct SegPlane {
+struct __align__(16) SegPlane {
     double n[3];
     double cn;
 };
@@ -66,8 +66,8 @@ struct __align__(16) FwdRec {
 };
 static_assert(sizeof(FwdRec) == 32, "FwdRec must be 32 bytes");
 
-// list entry at scoring / after filtering, 40 B
-struct ListRec {
+// list entry at scoring / after filtering, 40 B (8-byte aligned: five 64-bit loads per record)
+struct __align__(8) ListRec {
     uint32_t tgt_view, tgt_seg;
     float overlap, score;
     float d_p1, d_p2, d_q1, d_q2;
