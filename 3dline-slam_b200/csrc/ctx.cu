@@ -626,7 +626,7 @@ static K3Tables k3_tables(l3d_ctx* ctx)
     K3Tables t;
     t.views = ctx->d_views.p; t.seg_view = ctx->d_seg_view.p; t.pairs = ctx->d_pairs.p; t.inc = ctx->d_inc.p;
     t.inc_off = ctx->d_inc_off.p; t.rays = ctx->d_rays.p; t.fwd_off = ctx->d_fwd_off.p; t.fwd_cnt = ctx->d_fwd_cnt.p;
-    t.fwd_rec = ctx->d_fwd_rec.p; t.fwd_row = ctx->d_fwd_row.p; t.G_fwd = ctx->d_G_fwd.p; t.G_inv = ctx->d_G_inv.p;
+    t.fwd_rec = ctx->d_fwd_rec.p; t.fwd_row = ctx->d_fwd_row.p;
     t.inv_off = ctx->d_inv_off.p; t.inv_fill = ctx->d_inv_fill.p; t.inv_ent = ctx->d_inv_ent.p;
     t.L_off = ctx->d_L_off.p; t.L_f = ctx->d_L_f.p; t.L_meta = ctx->d_L_meta.p; t.L_score = ctx->d_L_score.p;
     const bool big = ctx->k3_big_rows;
@@ -645,10 +645,9 @@ static K3Tables k3_tables(l3d_ctx* ctx)
 
 static int launch_records(l3d_ctx* ctx)
 {
-    return launch_k3_records(ctx->d_pairs.p, (uint32_t)ctx->pairs.size(), (uint32_t)ctx->total_fwd, ctx->d_views.p,
-                             ctx->d_rays.p, ctx->d_fwd_row.p, ctx->d_fwd_rec.p, ctx->d_G_fwd.p, ctx->d_G_inv.p,
-                             ctx->d_inv_off.p, ctx->d_inv_fill.p, ctx->d_inv_ent.p, ctx->slice_view[ctx->rank],
-                             ctx->slice_view[ctx->rank + 1], ctx->stream);
+    return launch_k3_records(ctx->d_pairs.p, (uint32_t)ctx->pairs.size(), (uint32_t)ctx->total_fwd, ctx->d_fwd_row.p,
+                             ctx->d_fwd_rec.p, ctx->d_inv_off.p, ctx->d_inv_fill.p, ctx->d_inv_ent.p,
+                             ctx->slice_view[ctx->rank], ctx->slice_view[ctx->rank + 1], ctx->stream);
 }
 
 // pre-pass + build
@@ -687,8 +686,6 @@ int l3d_score_build(l3d_ctx* ctx)
     CK(ctx->d_L_cnt.ensure((size_t)S + 1));
     CK(ctx->d_stats.ensure(k3_wf_stats_bytes()));
     CK(cudaMemsetAsync(ctx->d_stats.p, 0, k3_wf_stats_bytes(), st));
-    CK(ctx->d_G_fwd.ensure((F + 1) * k3_geo_bytes()));
-    CK(ctx->d_G_inv.ensure((F + 1) * k3_geo_bytes()));
 
     // pre-pass: row of every forward record, the (static) inverse-match slots, the potential lists
     ctx->cnt.gpu_launches += launch_k3_inv_capacity(ctx->d_pairs.p, P, ctx->total_rows, ctx->d_fwd_off.p,

@@ -36,9 +36,8 @@ int launch_fwd_place(const unsigned char*, uint64_t, int, const uint32_t*, int, 
                      cudaStream_t);
 int launch_k3_list_capacity(const ViewDev*, const uint32_t*, uint32_t, const IncDev*, const uint32_t*, const PairDev*,
                             const uint32_t*, const uint32_t*, uint32_t*, void*, cudaStream_t);
-int launch_k3_records(const PairDev*, uint32_t, uint32_t, const ViewDev*, const SegRays*, const uint32_t*, FwdRec*,
-                      void*, void*, const uint32_t*, uint32_t*, uint2*, uint32_t, uint32_t, cudaStream_t);
-size_t k3_geo_bytes();
+int launch_k3_records(const PairDev*, uint32_t, uint32_t, const uint32_t*, FwdRec*, const uint32_t*, uint32_t*, uint2*,
+                      uint32_t, uint32_t, cudaStream_t);
 size_t k3_wf_stats_bytes();
 size_t k3_sib_bytes();
 int k3_wf_max_inc();
@@ -260,7 +259,6 @@ struct l3d_ctx {
     DevBuf<unsigned char> d_xchg_stage[4];
     DevBuf<uint32_t> d_slice_g;
     uint64_t shard_sim_evals = 0, shard_scored = 0, shard_filtered = 0;
-    DevBuf<unsigned char> d_G_fwd, d_G_inv;
     std::vector<uint64_t> L_cap_h;   // per-view list capacity
     DevBuf<ListRec> d_filt_rec;
     DevBuf<uint32_t> d_filt_off, d_filt_cnt, d_small;  // d_small: [0]=filt_total [1]=err [2]=median overflow

@@ -108,7 +108,7 @@ struct IncDev {  // one incident pair of a view, in list order
 struct K3Tables {
     const ViewDev* views; const uint32_t* seg_view; const PairDev* pairs; const IncDev* inc; const uint32_t* inc_off;
     const SegRays* rays; const uint32_t* fwd_off; const uint32_t* fwd_cnt; FwdRec* fwd_rec; const uint32_t* fwd_row;
-    const void* G_fwd; const void* G_inv; const uint32_t* inv_off; const uint32_t* inv_fill; const uint2* inv_ent;
+    const uint32_t* inv_off; const uint32_t* inv_fill; const uint2* inv_ent;
     const uint32_t* L_off; uint32_t* L_f; unsigned char* L_meta; float* L_score;
     void* L_sib; double* L_dir; float2* L_reg; uint32_t* L_c; uint32_t* L_h;
     uint32_t* prog_off; uint32_t* prog_nh; void* prog; uint32_t prog_cap;

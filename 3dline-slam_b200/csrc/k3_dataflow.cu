@@ -54,8 +54,8 @@ struct WfStats {
     uint32_t pad[2];
 };
 
-// per forward record: 3-D direction and regularisers of the match seen from its source view
-// (G_fwd) and, for inverse-emitting pairs, seen from its target view (G_inv)
+// 3-D direction and regularisers of a list entry (a forward match seen from its source view, or an
+// inverse match seen from its target view), computed while the row is assembled
 struct GeoRec {
     double dir[3];
     float reg1, reg2;
@@ -159,42 +159,24 @@ __device__ __forceinline__ GeoRec make_geo(const D3& C, const D3& r1, const D3& 
     return G;
 }
 
-// one thread per forward record: 3-D geometry seen from both views, the (static) inverse-match
-// slot of its target segment, score reset
-__global__ void __launch_bounds__(128) k3_record_kernel(const PairDev* __restrict__ pairs, uint32_t P, uint32_t F,
-                                                        const ViewDev* __restrict__ views,
-                                                        const SegRays* __restrict__ rays,
+// one thread per forward record: score reset and the (static) inverse-match slot of its target
+// segment (only for the target views [v_lo, v_hi) this rank builds)
+__global__ void __launch_bounds__(256) k3_record_kernel(const PairDev* __restrict__ pairs, uint32_t P, uint32_t F,
                                                         const uint32_t* __restrict__ fwd_row,
-                                                        FwdRec* __restrict__ fwd_rec, GeoRec* __restrict__ G_fwd,
-                                                        GeoRec* __restrict__ G_inv,
+                                                        FwdRec* __restrict__ fwd_rec,
                                                         const uint32_t* __restrict__ inv_off,
                                                         uint32_t* __restrict__ inv_fill, uint2* __restrict__ inv_ent,
                                                         uint32_t v_lo, uint32_t v_hi)
 {
     const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= F) return;
+    fwd_rec[f].score = 0.0f;
     const uint32_t row = fwd_row[f];
     const PairDev& D = pairs[pair_of_row(pairs, P, row)];
-    const uint32_t i = row - D.row_base;
-    fwd_rec[f].score = 0.0f;
-    // the geometry of a record is read by the rows of its source view (G_fwd) and, as an inverse
-    // match, by the rows of its target view (G_inv): views [v_lo, v_hi) are built by this rank
-    const bool need_fwd = D.src_view >= v_lo && D.src_view < v_hi;
-    const bool need_inv = D.emit_inverse && D.tgt_view >= v_lo && D.tgt_view < v_hi;
-    if (!need_fwd && !need_inv) return;
-    const ViewDev& vs = views[D.src_view];
-    const ViewDev& vt = views[D.tgt_view];
-    const D3 Cs = ld3w(vs.C), Ct = ld3w(vt.C);
-    const SegRays sr = rays[D.src_off + i];
-    const FwdRec rec = fwd_rec[f];
-    if (need_fwd) G_fwd[f] = make_geo(Cs, ld3w(sr.r1), ld3w(sr.r2), rec.d_p1, rec.d_p2, vs.k, Ct, vt.k);
-    if (need_inv) {
-        const SegRays tr = rays[D.tgt_off + rec.c];
-        G_inv[f] = make_geo(Ct, ld3w(tr.r1), ld3w(tr.r2), rec.d_q1, rec.d_q2, vt.k, Cs, vs.k);
-        const uint32_t tr_row = D.tgt_base + rec.c;
-        const uint32_t slot = atomicAdd(&inv_fill[tr_row], 1u);
-        inv_ent[inv_off[tr_row] + slot] = make_uint2(f, i);
-    }
+    if (!(D.emit_inverse && D.tgt_view >= v_lo && D.tgt_view < v_hi)) return;
+    const uint32_t tr_row = D.tgt_base + fwd_rec[f].c;
+    const uint32_t slot = atomicAdd(&inv_fill[tr_row], 1u);
+    inv_ent[inv_off[tr_row] + slot] = make_uint2(f, row - D.row_base);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -209,8 +191,7 @@ struct BuildArgs {
     const uint32_t* fwd_off;
     const uint32_t* fwd_cnt;
     FwdRec* fwd_rec;
-    const GeoRec* G_fwd;
-    const GeoRec* G_inv;
+    const SegRays* rays;
     const uint32_t* inv_off;   // start of the slot of every (pair, tgt segment)
     const uint32_t* inv_fill;  // entries in the slot
     const uint2* inv_ent;      // x: forward record index, y: source row
@@ -260,7 +241,7 @@ static constexpr int DF_MASKM = 256;  // rows up to this length keep their flag 
                                       // between the count and emit passes (maskw words per entry)
 static constexpr int DF_SMALL = 128;  // rows up to this length are built by a launch with small staging
 
-__global__ void __launch_bounds__(DF_THREADS) k3_build_kernel(const BuildArgs a)
+__global__ void __launch_bounds__(DF_THREADS, 16) k3_build_kernel(const BuildArgs a)
 {
     extern __shared__ __align__(16) unsigned char df_smem[];
     __shared__ BlockTab bt;
@@ -349,7 +330,9 @@ __global__ void __launch_bounds__(DF_THREADS) k3_build_kernel(const BuildArgs a)
     uint32_t* __restrict__ Lf = a.L_f + lbase;
     unsigned char* __restrict__ Lm = a.L_meta + lbase;
 
-    // ---- assemble: one thread per potential entry ----
+    // ---- assemble: one thread per potential entry (View::unprojectSegment + regularisers) ----
+    const SegRays sra = a.rays[g];
+    const D3 Ca = ld3w(va.C), ra1 = ld3w(sra.r1), ra2 = ld3w(sra.r2);
     for (uint32_t e = tid; e < m; e += DF_THREADS) {
         uint32_t q = 0;
         while (bt.pos[q + 1] <= e) ++q;  // n_inc is small
@@ -357,7 +340,6 @@ __global__ void __launch_bounds__(DF_THREADS) k3_build_kernel(const BuildArgs a)
         const uint32_t b = bt.b[q], n = bt.n[q];
         uint32_t dst = e, f;
         Sib sb;
-        const GeoRec* gp;
         if (bt.inv[q]) {
             const uint2 ie = a.inv_ent[b + j];
             // append order of the reference = ascending forward-record index: rank sort
@@ -366,17 +348,17 @@ __global__ void __launch_bounds__(DF_THREADS) k3_build_kernel(const BuildArgs a)
             dst = bt.pos[q] + rank;
             f = ie.x;
             const FwdRec r = a.fwd_rec[f];
-            gp = a.G_inv + f;
-            sb.d_p1 = r.d_q1;
+            sb.d_p1 = r.d_q1;  // storeInverseMatches swaps the views and the depths
             sb.d_p2 = r.d_q2;
         } else {
             f = b + j;
             const FwdRec r = a.fwd_rec[f];
-            gp = a.G_fwd + f;
             sb.d_p1 = r.d_p1;
             sb.d_p2 = r.d_p2;
         }
-        const GeoRec G = *gp;
+        // either way the entry is a 3-D segment through THIS row's 2-D segment at the entry's depths
+        const ViewDev& vo = a.views[bt.other[q]];
+        const GeoRec G = make_geo(Ca, ra1, ra2, sb.d_p1, sb.d_p2, va.k, ld3w(vo.C), vo.k);
         sb.cam = bt.other[q];
         sb.flags = G.valid ? 2u : 0u;
         Lf[dst] = f;
@@ -901,17 +883,15 @@ int launch_k3_list_capacity(const ViewDev* views, const uint32_t* seg_view, uint
     return 1;
 }
 
-int launch_k3_records(const PairDev* pairs, uint32_t P, uint32_t F, const ViewDev* views, const SegRays* rays,
-                      const uint32_t* fwd_row, FwdRec* fwd_rec, void* G_fwd, void* G_inv, const uint32_t* inv_off,
-                      uint32_t* inv_fill, uint2* inv_ent, uint32_t v_lo, uint32_t v_hi, cudaStream_t st)
+int launch_k3_records(const PairDev* pairs, uint32_t P, uint32_t F, const uint32_t* fwd_row, FwdRec* fwd_rec,
+                      const uint32_t* inv_off, uint32_t* inv_fill, uint2* inv_ent, uint32_t v_lo, uint32_t v_hi,
+                      cudaStream_t st)
 {
     if (!F || !P) return 0;
-    k3_record_kernel<<<(F + 127) / 128, 128, 0, st>>>(pairs, P, F, views, rays, fwd_row, fwd_rec, (GeoRec*)G_fwd,
-                                                       (GeoRec*)G_inv, inv_off, inv_fill, inv_ent, v_lo, v_hi);
+    k3_record_kernel<<<(F + 255) / 256, 256, 0, st>>>(pairs, P, F, fwd_row, fwd_rec, inv_off, inv_fill, inv_ent, v_lo,
+                                                       v_hi);
     return 1;
 }
-
-size_t k3_geo_bytes() { return sizeof(GeoRec); }
 size_t k3_wf_stats_bytes() { return sizeof(WfStats); }
 size_t k3_sib_bytes() { return sizeof(Sib); }
 int k3_wf_max_inc() { return DF_MAXINC; }
@@ -929,7 +909,7 @@ static BuildArgs build_args(const K3Tables& t, uint32_t maxm)
     BuildArgs b;
     b.views = t.views; b.seg_view = t.seg_view; b.pairs = t.pairs; b.inc = t.inc; b.inc_off = t.inc_off;
     b.fwd_off = t.fwd_off; b.fwd_cnt = t.fwd_cnt; b.fwd_rec = t.fwd_rec;
-    b.G_fwd = (const GeoRec*)t.G_fwd; b.G_inv = (const GeoRec*)t.G_inv;
+    b.rays = t.rays;
     b.inv_off = t.inv_off; b.inv_fill = t.inv_fill; b.inv_ent = t.inv_ent;
     b.L_off = t.L_off; b.L_f = t.L_f; b.L_meta = t.L_meta;
     b.L_sib = (Sib*)t.L_sib; b.L_dir = t.L_dir; b.L_reg = t.L_reg; b.L_c = t.L_c; b.L_h = t.L_h;
