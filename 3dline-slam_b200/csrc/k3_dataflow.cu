@@ -977,7 +977,14 @@ int launch_k3_fold(const K3Tables& t, cudaStream_t st, int* err)
         sleep_ns = ev ? atoi(ev) : 40;
     }
     f.sleep_ns = (uint32_t)sleep_ns;
-    k3_fold_kernel<<<grid, FOLD_WARPS * 32, 0, st>>>(f);
+    // cooperative launch: the runtime guarantees that all CTAs are co-resident (or fails), which the
+    // progress argument of the fold relies on even if another stream is using part of the device
+    void* args[] = {(void*)&f};
+    e = cudaLaunchCooperativeKernel((void*)k3_fold_kernel, dim3(grid), dim3(FOLD_WARPS * 32), args, 0, st);
+    if (e != cudaSuccess) {
+        *err = (int)e;
+        return -1;
+    }
     return 1;
 }
 
