@@ -43,7 +43,9 @@ def make_workload(scene_mod, name, n_gpus):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md).  The query
+    loop is started before the warm-up (nvidia-smi needs a few hundred ms to produce its first line)
+    and every line carries a timestamp, so the samples of the timed region can be picked afterwards."""
 
     def __init__(self, index):
         self.index = index
@@ -51,7 +53,7 @@ class ClockSampler:
         self.lines = []
 
     def start(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+        q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
         try:
@@ -65,32 +67,45 @@ class ClockSampler:
 
     def _read(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.lines.append((time.time(), ln.strip()))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             pass
-        sm, mx, reasons = [], [], set()
+        import datetime
+        rows = []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for seen, ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
-            if len(f) < 7:
+            if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[0]))
-                mx.append(float(f[1]))
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+            except ValueError:
+                ts = seen
+            try:
+                rows.append((ts, float(f[1]), float(f[2]), [n for n, v in zip(names, f[4:8]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for n, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        note = None
+        inside = rows if t0 is None else [r for r in rows if t0 <= r[0] <= t1]
+        if not inside and rows and t0 is not None:
+            # the timed region is shorter than the sampling period: take the samples closest to it
+            mid = 0.5 * (t0 + t1)
+            inside = sorted(rows, key=lambda r: abs(r[0] - mid))[:3]
+            note = "timed region (%.0f ms) shorter than the sampling period; nearest samples" % (1e3 * (t1 - t0))
+        out = {"sm_mhz": float(np.median([r[1] for r in inside])) if inside else None,
+               "sm_max_mhz": max(r[2] for r in inside) if inside else None, "samples": len(inside),
+               "reasons": sorted({n for r in inside for n in r[3]})}
+        if note:
+            out["note"] = note
+        return out
 
 
 def run_cpu_oracle(scene, threads=0, snapshot=False):
@@ -199,18 +214,19 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    sampler = ClockSampler(dev.index)
+    sampler.start()
     for _ in range(args.warmup):
         flush.zero_()
         step()
     barrier()
 
-    sampler = ClockSampler(dev.index)
-    sampler.start()
     l3.reset_counters()
     total_ms = 0.0
     stage_ms = {}
     k1_ms, k1_launches = 0.0, 0
     barrier()
+    wall0 = time.time()
     for _ in range(args.steps):
         flush.zero_()  # flush L2 between timed iterations (inputs are smaller than L2)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -225,7 +241,8 @@ def main():
         for k, v in l3.timings().items():
             stage_ms[k] = stage_ms.get(k, 0.0) + v
     barrier()
-    clocks = sampler.stop()
+    wall1 = time.time()
+    clocks = sampler.stop(wall0, wall1)
     cnt = l3.counts()
     launches = cnt["gpu_launches"]
 
@@ -319,11 +336,15 @@ def main():
         "peak_source": "measured here: dense FFMA micro-benchmark (l3d_bench_fp32_peak); nominal %d SMs x 128 x 2 x %.0f MHz = %.1f TFLOP/s"
                        % (n_sm, sm_max, fp32_nominal),
         "peak_nominal": fp32_nominal, "frac_of_nominal": achieved / fp32_nominal,
+        # the kernel's own formulation issues 35.5 SASS instructions per test (cuobjdump count over the
+        # unrolled loop): fraction of the lane-issue capacity (SMs x 4 schedulers x 32 lanes x clock)
+        "issued_instructions_per_test": 35.5,
+        "lane_issue_frac": 35.5 * k1_tests / k1_s / (n_sm * 128 * sm_max * 1e6),
         "algorithmic_flop_per_test": FLOP_PER_TEST, "tests_per_launch": k1_tests / max(t12["k1_launches"], 1),
         "launch_ms": 1e3 * k1_s / max(t12["k1_launches"], 1), "k1_tests_per_s": k1_tests / k1_s,
         # dram__bytes_read.sum + dram__bytes_write.sum of one K1 launch on C2 (ncu --set full,
-        # profiles/r1z_ncu_full_c2.md); the 31 MB bit mask stays in the 126 MB L2
-        "traffic": 2508800 if wname == "c2" else None,
+        # profiles/r1f_ncu_full_c2.md); the 31 MB bit mask stays in the 126 MB L2
+        "traffic": 2435840 if wname == "c2" else None,
     }
     n_pairs_local = max(c12["num_pairs_local"], 1)
     seg_n = scene.views[0].segs.shape[0]
