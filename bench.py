@@ -126,7 +126,12 @@ def bench_reference(args, scene_mod):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    scene, wname = make_workload(scene_mod, args.workload, 1)
+    # each step is a bounded sample of the arm's workload: the single-GPU scene of the same generator
+    # (at N > 1 the product's scene has N times the views; tests/s of the CPU path does not depend on it)
+    scene, sample_name = make_workload(scene_mod, args.workload, 1)
+    n = max(args.gpus, 1)
+    wname = sample_name if (n == 1 or args.workload != "c2") else "c2x%d" % n
+    full_views = scene.num_views * (n if args.workload == "c2" else 1)
     times, tests, cores = [], 0, 1
     for i in range(args.warmup + args.steps):
         r = run_cpu_oracle(scene)
@@ -135,15 +140,15 @@ def bench_reference(args, scene_mod):
             times.append(r["timers"]["match_images"] + r["timers"]["reconstruct"])
     T = float(np.sum(times))
     value = tests * len(times) / T
+    sample = "%s scene (%d views, same generator and per-view shape), stages 1-4, %d passes" % (sample_name, scene.num_views, len(times))
     line = {
         "impl": "reference", "metric": "segment_pair_tests_per_s", "value": value, "unit": "tests/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * T / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wname, "views": scene.num_views, "segments_per_view": scene.views[0].segs.shape[0],
-                   "neighbours": scene.params["num_neighbors"]},
+        "config": {"workload": wname, "views": full_views, "segments_per_view": scene.views[0].segs.shape[0],
+                   "neighbours": scene.params["num_neighbors"], "sample": sample},
         "views_per_s": scene.num_views * len(times) / T,
-        "cpu_baseline": {"value": value, "unit": "tests/s", "cores": cores, "kind": "port",
-                         "sample": "full %s scene, stages 1-4, %d passes" % (wname, len(times))},
+        "cpu_baseline": {"value": value, "unit": "tests/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "tests/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
