@@ -1,8 +1,8 @@
 // ctx.cu -- context, host orchestration and the C ABI of libl3dpp_b200.so (include/l3dpp_b200.h).
 //
 // Host side of Line3D::matchImages / computeMatches / reconstruct3Dlines (src/line3D.cc:496-640,
-// 846-930, 2018-2118): camera set-up, translation, pair list, per-batch K1/K2, the per-view
-// scoring wavefront, K4, and the (unchanged) clustering on the host.  No CPU fallback: every
+// 846-930, 2018-2118): camera set-up, translation, pair list, per-batch K1/K2, the
+// scoring phases, K4, and the (unchanged) clustering on the host.  No CPU fallback: every
 // compute entry point needs a CUDA device.
 #include "ctx.h"
 
@@ -614,7 +614,7 @@ int l3d_match_stage12(l3d_ctx* ctx, const l3d_params* params)
 }
 
 // ------------------------------------------------------------------------------------------
-// stage 3: scoring wavefront
+// stage 3: scoring
 // ------------------------------------------------------------------------------------------
 // stage 3: scoring (k3_dataflow.cu) in three phases: build (rows of this rank's view slice),
 // fold (all rows, replicated), finish (rows of the slice).  With one rank the phases run back to

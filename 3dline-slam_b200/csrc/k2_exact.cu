@@ -2,19 +2,16 @@
 // two-view triangulation, kNN selection and the orientation filter (exact TU, -fmad=false; every
 // arithmetic step is also an explicit _rn intrinsic).
 //
-// Three launches per batch:
-//   expand : the row's candidate bits -> a list of target indices in ascending order, i.e. the order
-//            Line3D::matchingCPU pushes matches (src/line3D.cc:1124-1196);
-//   K2a    : ONE THREAD PER CANDIDATE (flat, no divergent per-row loops): repeats the pair test
-//            exactly (src/line3D.cc:1131-1158, mutualOverlap :1283-1362), triangulates both
-//            directions (Line3D::triangulationDepths, src/line3D.cc:1365-1390) and evaluates the
-//            orientation test of the would-be match (Line3D::checkMatchOrientation
-//            src/line3D.cc:962-1014, View::segmentQualityAngle src/view.cc:495-513);
-//   K2b    : one thread per row: pushes the valid matches on a binary max-heap keyed by overlap
-//            (std::priority_queue<Match, vector, Match_kNN>, include/commons.h:233-244; the sift-up /
-//            sift-down steps follow the textbook algorithm libstdc++ uses, so equal overlaps pop in
-//            the same order), pops min(kNN, n) (src/line3D.cc:1198-1206), drops the ones that fail
-//            the orientation test and leaves the survivors, in list order, in fin_rec.
+// One kernel per batch, one warp per source row (k2_row_kernel): the row's candidate bits -> target
+// indices in ascending order, i.e. the order Line3D::matchingCPU pushes matches
+// (src/line3D.cc:1124-1196); the sign of the four triangulated depths (Line3D::triangulationDepths,
+// src/line3D.cc:1365-1390); the exact pair test of the survivors (src/line3D.cc:1131-1158,
+// mutualOverlap :1283-1362); the kNN selection in the pop order of
+// std::priority_queue<Match, vector, Match_kNN> (include/commons.h:233-244, src/line3D.cc:1198-1206:
+// rank by overlap, and on equal overlaps a replay of the textbook sift-up / sift-down steps libstdc++
+// uses); depths and the orientation test (Line3D::checkMatchOrientation src/line3D.cc:962-1014,
+// View::segmentQualityAngle src/view.cc:495-513) of the popped matches only.  k2_compact_kernel then
+// packs the rows' survivors into the forward-match store.
 #include "detmath.cuh"
 #include "exact.cuh"
 #include "internal.h"

@@ -1,7 +1,7 @@
 // k3_score.cu -- stand-alone scoring kernel behind l3d_score_matches (the drop-in for
 // L3DPP::score_matches_GPU, include/cudawrapper.h:74-81): Line3D::scoringCPU's new-match branch
 // (src/line3D.cc:1513-1547) over caller-provided lists (exact TU).  The resident pipeline uses the
-// fused wavefront kernel (k3_wavefront.cu) instead.
+// data-flow kernels (k3_dataflow.cu) instead.
 #include "internal.h"
 #include "score_core.cuh"
 

@@ -1,6 +1,6 @@
 // score_core.cuh -- Line3D::similarityForScoring (src/line3D.cc:1685-1716) with
 // Line3D::angleBetweenSeg3D (src/line3D.cc:1841-1853) in the canonical float/double sequence,
-// shared by the wavefront kernel and the l3d_score_matches kernel (exact TUs only).
+// shared by the data-flow scoring kernels and the l3d_score_matches kernel (exact TUs only).
 #pragma once
 #include "detmath.cuh"
 #include <math.h>
