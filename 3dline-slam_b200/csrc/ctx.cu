@@ -442,6 +442,7 @@ int plan_pairs(l3d_ctx* ctx)
         d.mask_base = cur.mask_words;
         d.batch_row0 = cur.row0;
         cur.mask_words += w;
+        cur.max_tgt = std::max(cur.max_tgt, d.n_tgt);
         cur.n_rows += d.n_src;
         cur.pair1 = p + 1;
         ctx->pairs[p].batch = (uint32_t)ctx->batches.size();
@@ -580,7 +581,7 @@ int l3d_match_stage12(l3d_ctx* ctx, const l3d_params* params)
                             ctx->d_rays.p, ctx->d_midray.p, ctx->d_planes.p, ctx->d_views.p, ctx->d_mask.p, ctx->d_cand_off.p,
                             ctx->d_heap.p, ctx->d_cand_rec.p,
                             ctx->d_fin_rec.p, ctx->d_fin_cnt.p, ctx->epi_overlap, ctx->prm.knn,
-                            ctx->prm.max_image_width, ctx->raw_mode ? 0 : 1, st);
+                            ctx->prm.max_image_width, ctx->raw_mode ? 0 : 1, b.max_tgt, st);
         ctx->cnt.gpu_launches +=
             launch_scan_u32(ctx->d_fin_cnt.p, ctx->d_fin_off.p, b.n_rows, ctx->d_scan.p, ctx->d_scan.cap, st);
         uint32_t n_fin = 0;

@@ -22,7 +22,7 @@ int launch_k1_pairtest(const PairDev*, const K1Cta*, uint32_t, const float4*, co
 int k1_rows_per_cta();
 int launch_k2_exact(const PairDev*, const K1Cta*, uint32_t, uint32_t, uint32_t, const float4*, const SegRays*,
                     const double*, const SegPlane*, const ViewDev*, const uint32_t*, const uint32_t*, unsigned long long*, FwdRec*,
-                    FwdRec*, uint32_t*, float, int, int, int, cudaStream_t);
+                    FwdRec*, uint32_t*, float, int, int, int, uint32_t, cudaStream_t);
 int launch_k2_compact(const uint32_t*, const uint32_t*, const uint32_t*, uint32_t, const FwdRec*, FwdRec*, uint32_t*,
                       uint32_t, cudaStream_t);
 int launch_k3_score(uint32_t, const uint32_t*, ListRec*, const ListGeo*, float, float, void*, cudaStream_t);
@@ -131,6 +131,7 @@ struct Batch {
     uint32_t row0, n_rows;
     uint32_t cta0, n_ctas;
     uint64_t mask_words;
+    uint32_t max_tgt;  // largest target view of the batch's pairs (chooses the K2 variant)
 };
 
 struct StageTimer {

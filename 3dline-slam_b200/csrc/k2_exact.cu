@@ -12,9 +12,12 @@
 // uses); depths and the orientation test (Line3D::checkMatchOrientation src/line3D.cc:962-1014,
 // View::segmentQualityAngle src/view.cc:495-513) of the popped matches only.  k2_compact_kernel then
 // packs the rows' survivors into the forward-match store.
+#include <cstdlib>
+
 #include "detmath.cuh"
 #include "exact.cuh"
 #include "internal.h"
+#include "tma.cuh"
 
 namespace l3d {
 
@@ -445,6 +448,318 @@ __global__ void __launch_bounds__(K2_WARPS * 32) k2_row_kernel(
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// K2, tile variant: one CTA = 128 source rows of one pair (8 warps, 16 rows each) and the target
+// tables of the pair -- endpoint rays and plane records of up to 1024 target segments -- staged in
+// shared memory with two 1-D TMA bulk copies per chunk.  The gathers of phase V and of the finishing
+// pass (the stalls of the row kernel) become shared-memory reads.  Same phases, same arithmetic.
+// ------------------------------------------------------------------------------------------
+static constexpr int K2T_WARPS = 8;
+static constexpr int K2T_ROWS = 128;    // rows per CTA (half a K1 tile)
+static constexpr int K2T_TCH = 1024;    // target segments staged per chunk (32 mask words)
+static constexpr int K2T_CL = 256;      // candidates enumerated per pass
+static constexpr int K2T_KEEP = 256;    // matches of one row kept in shared memory for the selection
+
+struct __align__(16) K2TWarp {
+    float ps[K2T_KEEP];           // overlap of the row's matches (ascending target order)
+    uint32_t sc[K2T_KEEP];        // their target segments
+    unsigned short cl[K2T_CL];    // chunk-local candidate indices (compacted in place); later the pop order
+};
+
+struct K2TSmem {
+    SegRays rays[K2T_TCH];
+    SegPlane planes[K2T_TCH];
+    K2TWarp w[K2T_WARPS];
+    uint32_t nv[K2T_ROWS];  // matches per row so far (pairs with more than one chunk)
+    uint64_t bar;
+};
+
+__global__ void __launch_bounds__(K2T_WARPS * 32, 2) k2_tile_kernel(
+    const PairDev* __restrict__ pairs, const K1Cta* __restrict__ ctas, const uint32_t* __restrict__ mask,
+    const uint32_t* __restrict__ cand_off, const float4* __restrict__ segs, const SegRays* __restrict__ rays,
+    const double* __restrict__ midray, const SegPlane* __restrict__ planes, const ViewDev* __restrict__ views,
+    unsigned long long* __restrict__ heap, FwdRec* __restrict__ cand_rec, FwdRec* __restrict__ fin_rec,
+    uint32_t* __restrict__ fin_cnt, float thr, double W, int knn, int apply_orient)
+{
+    extern __shared__ __align__(128) unsigned char k2t_raw[];
+    K2TSmem& S = *reinterpret_cast<K2TSmem*>(k2t_raw);
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    K2TWarp& sm = S.w[warp];
+    const K1Cta cta = ctas[blockIdx.x / (K2_ROWS / K2T_ROWS)];
+    const PairDev& P = pairs[cta.pair];
+    const uint32_t n_src = P.n_src, n_tgt = P.n_tgt, words = P.words;
+    const uint32_t row0 = cta.tile * K2_ROWS + (blockIdx.x % (K2_ROWS / K2T_ROWS)) * K2T_ROWS;
+    if (row0 >= n_src) return;  // uniform
+    const ViewDev& vs = views[P.src_view];
+    const ViewDev& vt = views[P.tgt_view];
+    const D3 Cs = ld3(vs.C), Ct = ld3(vt.C);
+    const bool single = n_tgt <= (uint32_t)K2T_TCH;
+
+    if (threadIdx.x == 0) {
+        mbar_init(&S.bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (uint32_t i = threadIdx.x; i < (uint32_t)K2T_ROWS; i += K2T_WARPS * 32) S.nv[i] = 0u;
+    __syncthreads();
+
+    uint32_t chunk_no = 0;
+    for (uint32_t cb = 0; cb < n_tgt; cb += K2T_TCH, ++chunk_no) {
+        const uint32_t tcnt = min((uint32_t)K2T_TCH, n_tgt - cb);
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(&S.bar, tcnt * (uint32_t)(sizeof(SegRays) + sizeof(SegPlane)));
+            tma_load_1d(S.rays, rays + P.tgt_off + cb, tcnt * (uint32_t)sizeof(SegRays), &S.bar);
+            tma_load_1d(S.planes, planes + P.tgt_off + cb, tcnt * (uint32_t)sizeof(SegPlane), &S.bar);
+        }
+        mbar_wait(&S.bar, chunk_no & 1u);
+
+        for (uint32_t rr = warp; rr < (uint32_t)K2T_ROWS; rr += K2T_WARPS) {
+            const uint32_t r = row0 + rr;
+            if (r >= n_src) break;  // warp-uniform
+            const uint32_t lrow = P.row_base - P.batch_row0 + r;
+            const uint32_t base = cand_off[lrow];
+            unsigned long long* __restrict__ stage = heap + base;
+            unsigned long long* __restrict__ hscr = reinterpret_cast<unsigned long long*>(cand_rec + base);
+            uint32_t* __restrict__ gsel = reinterpret_cast<uint32_t*>(hscr + (cand_off[lrow + 1] - base));
+            FwdRec* __restrict__ frec = fin_rec + base;
+            const uint32_t* __restrict__ mrow = mask + P.mask_base + r;
+
+            // row constants (src/line3D.cc:1113-1121); plane normal and n.C come from k0_prep
+            const float4 sg = segs[P.src_off + r];
+            const D3 p1 = d3((double)sg.x, (double)sg.y, 1.0), p2 = d3((double)sg.z, (double)sg.w, 1.0);
+            const D3 e1 = mul33(P.F, p1), e2 = mul33(P.F, p2);
+            const SegRays sr = rays[P.src_off + r];
+            const D3 rp1 = ld3(sr.r1), rp2 = ld3(sr.r2);
+            const SegPlane plB = planes[P.src_off + r];
+            const D3 nB = ld3(plB.n);
+            const double numB = ds(plB.cn, dot3(nB, Ct));
+            uint32_t n_valid = single ? 0u : S.nv[rr];
+
+            // ---- the chunk's mask words of this row; candidates are enumerated <= K2T_CL at a time ----
+            const uint32_t w = (cb >> 5) + lane;
+            const uint32_t allbits = (w < words) ? mrow[(size_t)w * n_src] : 0u;
+            uint32_t tot_all = __popc(allbits);
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) tot_all += __shfl_xor_sync(0xffffffffu, tot_all, d);
+            if (tot_all) {
+                const uint32_t wstep = tot_all <= (uint32_t)K2T_CL ? 32u : 8u;  // 8 words hold <= 256 candidates
+                for (uint32_t w0 = 0; w0 < 32u; w0 += wstep) {
+                    uint32_t bits = (lane >= w0 && lane < w0 + wstep) ? allbits : 0u;
+                    const uint32_t cnt = __popc(bits);
+                    uint32_t incl = cnt;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+                        if ((int)lane >= d) incl += t;
+                    }
+                    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+                    if (total == 0) continue;  // warp-uniform
+                    uint32_t off = incl - cnt;
+                    while (bits) {
+                        const uint32_t j = __ffs(bits) - 1;
+                        bits &= bits - 1;
+                        sm.cl[off++] = (unsigned short)(lane * 32 + j);
+                    }
+                    __syncwarp();
+
+                    // ---- phase V: four positive depths?  (see k2_row_kernel) target records from shared memory ----
+                    uint32_t nval = 0;
+                    for (uint32_t k0 = 0; k0 < total; k0 += 32) {
+                        const uint32_t k = k0 + lane;
+                        const bool active = k < total;
+                        const uint32_t cidx = active ? (uint32_t)sm.cl[k] : 0u;
+                        bool valid = false;
+                        if (active) {
+                            const SegRays& tr = S.rays[cidx];
+                            const SegPlane& plA = S.planes[cidx];
+                            const D3 nA = ld3(plA.n);
+                            const double a1 = dot3(rp1, nA), a2 = dot3(rp2, nA);
+                            const double b1 = dot3(ld3(tr.r1), nB), b2 = dot3(ld3(tr.r2), nB);
+                            if (!(fabs(a1) < L3D_EPS || fabs(a2) < L3D_EPS || fabs(b1) < L3D_EPS || fabs(b2) < L3D_EPS)) {
+                                const double num = ds(plA.cn, dot3(nA, Cs));
+                                valid = depth_positive(num, a1) && depth_positive(num, a2) &&
+                                        depth_positive(numB, b1) && depth_positive(numB, b2);
+                            }
+                        }
+                        __syncwarp();  // every lane has read its cl[k] before the in-place compaction
+                        const uint32_t bal = __ballot_sync(0xffffffffu, valid);
+                        if (valid) sm.cl[nval + __popc(bal & lt_mask)] = (unsigned short)cidx;
+                        nval += __popc(bal);
+                        __syncwarp();
+                    }
+
+                    // ---- phase A: the pair test in the reference's double sequence (src/line3D.cc:1131-1158) ----
+                    for (uint32_t k0 = 0; k0 < nval; k0 += 32) {
+                        const uint32_t k = k0 + lane;
+                        uint32_t c = 0;
+                        float score = 0.0f;
+                        bool pass = false;
+                        if (k < nval) {
+                            c = cb + (uint32_t)sm.cl[k];
+                            const float4 tg = segs[P.tgt_off + c];
+                            const D3 q1 = d3((double)tg.x, (double)tg.y, 1.0), q2 = d3((double)tg.z, (double)tg.w, 1.0);
+                            const D3 l2 = cross3(q1, q2);
+                            const D3 a = cross3(l2, e1), b = cross3(l2, e2);
+                            if (fabs(a.z) > L3D_EPS && fabs(b.z) > L3D_EPS) {
+                                const double ax = dd(a.x, a.z), ay = dd(a.y, a.z), bx = dd(b.x, b.z), by = dd(b.y, b.z);
+                                if (!(ax < 0 || ax > W || ay < 0 || ay > W || bx < 0 || bx > W || by < 0 || by > W)) {
+                                    score = mutual_overlap_xy(ax, ay, bx, by, q1.x, q1.y, q2.x, q2.y);
+                                    pass = score > thr;
+                                }
+                            }
+                        }
+                        const uint32_t bal = __ballot_sync(0xffffffffu, pass);
+                        if (pass) {
+                            const uint32_t pos = n_valid + __popc(bal & lt_mask);
+                            if (single && pos < (uint32_t)K2T_KEEP) {
+                                sm.ps[pos] = score;
+                                sm.sc[pos] = c;
+                            } else {
+                                stage[pos] = ((unsigned long long)__float_as_uint(score) << 32) | c;
+                            }
+                        }
+                        n_valid += __popc(bal);
+                    }
+                    __syncwarp();
+                }
+            }
+            if (!single) {
+                if (lane == 0) S.nv[rr] = n_valid;
+                if (cb + K2T_TCH < n_tgt) continue;  // more chunks to come for this row
+                // last chunk: bring the row's matches into shared memory for the selection
+                __syncwarp();
+                for (uint32_t k = lane; k < n_valid && k < (uint32_t)K2T_KEEP; k += 32) {
+                    const unsigned long long key = stage[k];
+                    sm.ps[k] = key_overlap(key);
+                    sm.sc[k] = (uint32_t)(key & 0xffffffffu);
+                }
+            }
+            __syncwarp();
+            auto match_key = [&](uint32_t k) -> unsigned long long {
+                return k < (uint32_t)K2T_KEEP ? (((unsigned long long)__float_as_uint(sm.ps[k]) << 32) | sm.sc[k]) : stage[k];
+            };
+
+            // ---- selection: std::priority_queue pop order (include/commons.h:233-244, src/line3D.cc:1198-1206) ----
+            uint32_t npop = n_valid;   // kNN <= 0: every match, ascending target order
+            int sel_mode = 0;          // 0: identity, 1: sm.cl (shared), 2: gsel (global)
+            if (knn > 0 && n_valid) {
+                npop = min((uint32_t)knn, n_valid);
+                bool fast = n_valid + 4 <= (uint32_t)K2T_KEEP && npop <= (uint32_t)K2T_CL;
+                if (fast) {
+                    if (lane < 4) sm.ps[n_valid + lane] = -1.0f;  // pad to a multiple of 4: never larger
+                    __syncwarp();
+                    uint32_t seen = 0, rankbits = 0;
+                    const uint32_t n4 = (n_valid + 3u) >> 2;
+                    for (uint32_t k = lane; k < n_valid; k += 32) {
+                        const float ov = sm.ps[k];
+                        uint32_t rank = 0;
+                        for (uint32_t j = 0; j < n4; ++j) {
+                            const float4 o = reinterpret_cast<const float4*>(sm.ps)[j];
+                            rank += (o.x > ov) + (o.y > ov) + (o.z > ov) + (o.w > ov);
+                        }
+                        if (rank < npop) {
+                            sm.cl[rank] = (unsigned short)k;  // colliding ranks are detected below
+                            rankbits |= 1u << (rank & 31u);
+                            ++seen;
+                        }
+                    }
+                    if (npop <= 32) {  // npop distinct ranks below npop <=> no two of them are equal
+                        fast = (uint32_t)__popc(__reduce_or_sync(0xffffffffu, rankbits)) == npop;
+                    } else {
+#pragma unroll
+                        for (int d = 16; d > 0; d >>= 1) seen += __shfl_xor_sync(0xffffffffu, seen, d);
+                        fast = seen == npop;
+                        __syncwarp();
+                        if (fast) {  // a collision leaves a slot stale: every slot must hold its own rank
+                            uint32_t ok = 1;
+                            for (uint32_t t = lane; t < npop; t += 32) {
+                                const uint32_t kk = sm.cl[t];
+                                uint32_t rank = 0xffffffffu;
+                                if (kk < n_valid) {
+                                    const float ov = sm.ps[kk];
+                                    rank = 0;
+                                    for (uint32_t j = 0; j < n_valid; ++j) rank += (sm.ps[j] > ov) ? 1u : 0u;
+                                }
+                                ok &= (rank == t) ? 1u : 0u;
+                            }
+                            fast = __all_sync(0xffffffffu, ok != 0u);
+                        }
+                    }
+                    __syncwarp();
+                    sel_mode = 1;
+                }
+                if (!fast) {
+                    // equal overlaps (or a very long row): replay the binary heap (push in ascending target
+                    // order, pop kNN)
+                    sel_mode = 2;
+                    if (lane == 0) {
+                        for (uint32_t i = 0; i < n_valid; ++i)
+                            heap_push(hscr, i, (match_key(i) & 0xffffffff00000000ull) | i);
+                        uint32_t hn = n_valid;
+                        for (uint32_t t = 0; t < npop; ++t) {
+                            gsel[t] = (uint32_t)(hscr[0] & 0xffffffffu);
+                            heap_pop(hscr, hn);
+                            --hn;
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+
+            // ---- the popped matches: depths + orientation test (src/line3D.cc:1365-1390, 962-1014), output in
+            // pop order; the target records come from shared memory when the pair has a single chunk ----
+            const D3 rmid = ld3(midray + 3 * (size_t)(P.src_off + r));
+            uint32_t nout = 0;
+            for (uint32_t t0 = 0; t0 < npop; t0 += 32) {
+                const uint32_t t = t0 + lane;
+                bool keep = false;
+                FwdRec rec;
+                rec.flags = 0u;
+                rec.score = 0.0f;
+                if (t < npop) {
+                    const uint32_t k = sel_mode == 0 ? t : (sel_mode == 1 ? (uint32_t)sm.cl[t] : gsel[t]);
+                    const unsigned long long key = match_key(k);
+                    const uint32_t c = (uint32_t)(key & 0xffffffffu);
+                    const SegRays tr = single ? S.rays[c] : rays[P.tgt_off + c];
+                    const SegPlane plA = single ? S.planes[c] : planes[P.tgt_off + c];
+                    const D3 nA = ld3(plA.n);
+                    const double num = ds(plA.cn, dot3(nA, Cs));
+                    // n.ray(p1): the same products in the same order as ray(p1).n
+                    const double ds1 = dd(num, dot3(rp1, nA)), ds2 = dd(num, dot3(rp2, nA));
+                    const double dt1 = dd(numB, dot3(ld3(tr.r1), nB)), dt2 = dd(numB, dot3(ld3(tr.r2), nB));
+                    rec.c = c;
+                    rec.overlap = key_overlap(key);
+                    rec.d_p1 = (float)ds1;
+                    rec.d_p2 = (float)ds2;
+                    rec.d_q1 = (float)dt1;
+                    rec.d_q2 = (float)dt2;
+                    keep = true;
+                    if (apply_orient) {
+                        // |x| < 0.9951 (thresholds: |x| < 0.99518): no sqrt/div/acos needed, see k2_row_kernel
+                        const D3 P1 = add3(Cs, scale3(rp1, (double)rec.d_p1));
+                        const D3 P2 = add3(Cs, scale3(rp2, (double)rec.d_p2));
+                        const D3 vv = sub3(P2, P1);
+                        const double v2 = dot3(vv, vv), sv = dot3(rmid, vv);
+                        if (!(v2 > 1e-20 && sv * sv < 0.99022401 * v2)) {
+                            const float len = (float)norm3(sub3(P1, P2));
+                            D3 dir = d3(0.0, 0.0, 0.0);
+                            if (len > L3D_EPS) dir = normalized3(vv);
+                            const double ang = det_acos(fmin(fmax(dot3(rmid, dir), -1.0), 1.0));
+                            keep = ang > (double)0.098174771f && ang < (double)3.043417886f;
+                        }
+                    }
+                }
+                const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+                if (keep) frec[nout + __popc(bal & lt_mask)] = rec;
+                nout += __popc(bal);
+            }
+            if (lane == 0) fin_cnt[lrow] = nout;
+            __syncwarp();
+        }
+        __syncthreads();  // everyone is done with the staged tables before the next chunk overwrites them
+    }
+}
+
 __global__ void __launch_bounds__(256) k2_compact_kernel(const uint32_t* __restrict__ cand_off,
                                                          const uint32_t* __restrict__ fin_cnt,
                                                          const uint32_t* __restrict__ fin_off, uint32_t rec_base,
@@ -465,11 +780,25 @@ int launch_k2_exact(const PairDev* pairs, const K1Cta* ctas, uint32_t n_ctas, ui
                     const float4* segs, const SegRays* rays, const double* midray, const SegPlane* planes,
                     const ViewDev* views, const uint32_t* mask, const uint32_t* cand_off, unsigned long long* heap, FwdRec* cand_rec,
                     FwdRec* fin_rec, uint32_t* fin_cnt, float thr, int knn, int max_image_width, int apply_orient,
-                    cudaStream_t st)
+                    uint32_t max_tgt, cudaStream_t st)
 {
     if (n_ctas == 0) return 0;
     (void)n_rows;
     (void)n_cand;
+    static int variant = -1;
+    if (variant < 0) {
+        const char* e = getenv("L3D_K2_VARIANT");  // tuning hook: 0 = row kernel, 1 = tile kernel (default)
+        variant = e ? atoi(e) : 1;
+        cudaFuncSetAttribute(k2_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K2TSmem));
+    }
+    // the tile kernel keeps a pair's whole target table in shared memory when it has <= 1024 segments
+    // (C2: 0.93 vs 1.00 ms); with several chunks per pair the row kernel is the faster one (C4 shape)
+    if (variant == 1 && max_tgt <= (uint32_t)K2T_TCH) {
+        k2_tile_kernel<<<n_ctas * (K2_ROWS / K2T_ROWS), K2T_WARPS * 32, sizeof(K2TSmem), st>>>(
+            pairs, ctas, mask, cand_off, segs, rays, midray, planes, views, heap, cand_rec, fin_rec, fin_cnt, thr,
+            (double)max_image_width, knn, apply_orient);
+        return 1;
+    }
     // 128 registers, 4 CTAs = 16 warps per SM: compiling for more resident warps (80 / 64 registers)
     // spills and was measured slower (1.11 ms -> 1.11 / 1.39 ms on C2)
     k2_row_kernel<<<n_ctas * (K2_ROWS / K2_SUB), K2_WARPS * 32, 0, st>>>(pairs, ctas, mask, cand_off, segs, rays, midray,
