@@ -785,15 +785,17 @@ int launch_k2_exact(const PairDev* pairs, const K1Cta* ctas, uint32_t n_ctas, ui
     if (n_ctas == 0) return 0;
     (void)n_rows;
     (void)n_cand;
-    static int variant = -1;
-    if (variant < 0) {
-        const char* e = getenv("L3D_K2_VARIANT");  // tuning hook: 0 = row kernel, 1 = tile kernel (default)
-        variant = e ? atoi(e) : 1;
+    // test / tuning hook: 0 = row kernel always, 1 = by target-view size (default), 2 = tile kernel always
+    const char* ev = getenv("L3D_K2_VARIANT");
+    const int variant = ev ? atoi(ev) : 1;
+    static bool attr_set = false;
+    if (!attr_set) {
         cudaFuncSetAttribute(k2_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K2TSmem));
+        attr_set = true;
     }
     // the tile kernel keeps a pair's whole target table in shared memory when it has <= 1024 segments
     // (C2: 0.93 vs 1.00 ms); with several chunks per pair the row kernel is the faster one (C4 shape)
-    if (variant == 1 && max_tgt <= (uint32_t)K2T_TCH) {
+    if (variant == 2 || (variant == 1 && max_tgt <= (uint32_t)K2T_TCH)) {
         k2_tile_kernel<<<n_ctas * (K2_ROWS / K2T_ROWS), K2T_WARPS * 32, sizeof(K2TSmem), st>>>(
             pairs, ctas, mask, cand_off, segs, rays, midray, planes, views, heap, cand_rec, fin_rec, fin_cnt, thr,
             (double)max_image_width, knn, apply_orient);

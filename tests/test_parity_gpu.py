@@ -49,6 +49,35 @@ def test_knn_variants(api, oracle, scene_mod):
         compare_full(l3, orc, sc)
 
 
+@pytest.mark.parametrize("knn", [-1, 40, 10])
+def test_dense_rows_take_the_rare_kernel_paths(api, oracle, scene_mod, knn):
+    """Without the pre-filter every target is a candidate: more than 256 candidates per mask chunk
+    (enumerated 8 words at a time), rows with more matches than the shared-memory selection holds
+    (heap replay from the global staging), kNN above the warp width and kNN <= 0 (all matches)."""
+    sc = scene_mod.make_scene("tiny", seed=808, n_views=5, n_seg=640, nbrs=3)
+    sc.params["knn"] = knn
+    orc = oracle.run_scene(sc)
+    l3 = api.run_scene(sc, filter_mode=1, keep_scored=True)
+    compare_full(l3, orc, sc)
+    assert l3.counts()["candidates"] == l3.counts()["pair_tests"]
+
+
+@pytest.mark.parametrize("variant", ["0", "1", "2"])
+def test_large_target_views_in_both_k2_kernels(api, oracle, scene_mod, monkeypatch, variant):
+    """More than 1024 segments per view: several mask chunks per row.  The row kernel is the default
+    for such pairs; both kernels (forced through the tuning hook) must give the same result, and so
+    must the row kernel on small views."""
+    monkeypatch.setenv("L3D_K2_VARIANT", variant)
+    sc = scene_mod.make_scene("tiny", seed=909, n_views=4, n_seg=1300, nbrs=3)
+    orc = oracle.run_scene(sc)
+    l3 = api.run_scene(sc, keep_scored=True)
+    compare_full(l3, orc, sc)
+    sc.params["knn"] = -1
+    orc = oracle.run_scene(sc)
+    l3 = api.run_scene(sc, filter_mode=1, keep_scored=True)
+    compare_full(l3, orc, sc)
+
+
 def test_ties_follow_priority_queue_order(api, oracle, scene_mod):
     """Duplicated target segments give exactly equal overlaps: the kNN pop order must be the
     std::priority_queue's (include/commons.h:233-244)."""
