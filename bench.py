@@ -378,7 +378,7 @@ def main():
     }
 
     cpu_baseline = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and n_gpus == 1:   # reported on rank 0 at N=1 only
         base_scene, bname = make_workload(scene_mod, args.workload, 1)
         r = run_cpu_oracle(base_scene)
         tcpu = r["timers"]["match_images"] + r["timers"]["reconstruct"]
