@@ -245,32 +245,19 @@ __global__ void __launch_bounds__(K2_WARPS * 32) k2_row_kernel(
         const D3 rmid = ld3(midray + 3 * (size_t)(P.src_off + r));
         uint32_t n_valid = 0;
 
-        for (uint32_t cb = 0; cb < n_tgt; cb += K2_CHUNK) {
-            // ---- enumerate the candidates of this chunk in ascending target order ----
-            const uint32_t w = (cb >> 5) + lane;
-            uint32_t bits = (w < words) ? mrow[(size_t)w * n_src] : 0u;
-            const uint32_t cnt = __popc(bits);
-            uint32_t incl = cnt;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
-                if ((int)lane >= d) incl += t;
-            }
-            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-            if (total == 0) continue;  // warp-uniform
-            uint32_t off = incl - cnt;
-            while (bits) {
-                const uint32_t j = __ffs(bits) - 1;
-                bits &= bits - 1;
-                sm.cl[off++] = (unsigned short)(lane * 32 + j);
-            }
-            __syncwarp();
-
+        // Candidates of several mask chunks are collected into one list before the two phases run, so
+        // that a row of a large target view (C4: 3 chunks, ~18 candidates each) fills the lanes of one
+        // pass instead of three sparse ones.  cl holds (target - cl_base) as 16 bits: chunks are batched
+        // while the view has <= 65536 segments, otherwise every chunk is flushed on its own.
+        const bool batch_chunks = n_tgt <= 65536u;
+        uint32_t ncl = 0, cl_base = 0;
+        auto flush = [&]() {
             // ---- phase V: which candidates triangulate to four positive depths (src/line3D.cc:1160-1168,
             // 1365-1390)?  A match is pushed iff it passes the pair test AND has four positive depths; the
             // depth signs are the cheaper half (no division: see depth_positive), so they go first and
             // the pair test only runs on the ~half of the candidates that survive.  The divisions are
             // done for the matches that survive the kNN selection. ----
+            const uint32_t total = ncl;
             uint32_t nval = 0;
             for (uint32_t k0 = 0; k0 < total; k0 += 32) {
                 const uint32_t k = k0 + lane;
@@ -278,7 +265,7 @@ __global__ void __launch_bounds__(K2_WARPS * 32) k2_row_kernel(
                 const uint32_t cidx = active ? (uint32_t)sm.cl[k] : 0u;
                 bool valid = false;
                 if (active) {
-                    const uint32_t c = cb + cidx;
+                    const uint32_t c = cl_base + cidx;
                     const SegRays tr = rays[P.tgt_off + c];
                     const SegPlane plA = planes[P.tgt_off + c];
                     const D3 nA = ld3(plA.n);
@@ -296,8 +283,6 @@ __global__ void __launch_bounds__(K2_WARPS * 32) k2_row_kernel(
                 nval += __popc(bal);
                 __syncwarp();
             }
-            if (nval == 0) continue;
-
             // ---- phase A: the pair test in the reference's double sequence (src/line3D.cc:1131-1158) ----
             for (uint32_t k0 = 0; k0 < nval; k0 += 32) {
                 const uint32_t k = k0 + lane;
@@ -305,7 +290,7 @@ __global__ void __launch_bounds__(K2_WARPS * 32) k2_row_kernel(
                 float score = 0.0f;
                 bool pass = false;
                 if (k < nval) {
-                    c = cb + (uint32_t)sm.cl[k];
+                    c = cl_base + (uint32_t)sm.cl[k];
                     const float4 tg = segs[P.tgt_off + c];
                     const D3 q1 = d3((double)tg.x, (double)tg.y, 1.0), q2 = d3((double)tg.z, (double)tg.w, 1.0);
                     const D3 l2 = cross3(q1, q2);
@@ -323,7 +308,34 @@ __global__ void __launch_bounds__(K2_WARPS * 32) k2_row_kernel(
                 n_valid += __popc(bal);
             }
             __syncwarp();
+            ncl = 0;
+        };
+
+        for (uint32_t cb = 0; cb < n_tgt; cb += K2_CHUNK) {
+            // ---- enumerate the candidates of this chunk in ascending target order ----
+            const uint32_t w = (cb >> 5) + lane;
+            uint32_t bits = (w < words) ? mrow[(size_t)w * n_src] : 0u;
+            const uint32_t cnt = __popc(bits);
+            uint32_t incl = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+                if ((int)lane >= d) incl += t;
+            }
+            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+            if (total == 0) continue;  // warp-uniform
+            if (ncl && (!batch_chunks || ncl + total > (uint32_t)K2_CHUNK)) flush();
+            if (!batch_chunks) cl_base = cb;
+            uint32_t off = ncl + incl - cnt;
+            while (bits) {
+                const uint32_t j = __ffs(bits) - 1;
+                bits &= bits - 1;
+                sm.cl[off++] = (unsigned short)(cb - cl_base + lane * 32 + j);
+            }
+            ncl += total;
+            __syncwarp();
         }
+        if (ncl) flush();
 
         // ---- selection: std::priority_queue pop order (include/commons.h:233-244, src/line3D.cc:1198-1206):
         // sel[t] = staging index of the t-th popped match ----
