@@ -131,30 +131,32 @@ __device__ __forceinline__ float affinity_sim(const EntryDev& e1, const ViewDev&
     return fminf(sim_a, sim_p);
 }
 
-// pass 1: similarity of every filtered-list entry of every hypothesis, de-duplication, counts
-__global__ void __launch_bounds__(128) k4_edges_count_kernel(
+// pass 1a: similarity of every filtered-list entry of every hypothesis + de-duplication, one thread
+// per (row, list entry) -- a row has only a handful of entries, one thread per row left the SMs idle
+__global__ void __launch_bounds__(128) k4_edges_sim_kernel(
     const ViewDev* __restrict__ views, const uint32_t* __restrict__ seg_view, const EntryDev* __restrict__ entries,
-    uint32_t S, const uint32_t* __restrict__ filt_off, const uint32_t* __restrict__ filt_cnt,
+    const uint32_t* __restrict__ filt_off, const uint32_t* __restrict__ filt_cnt,
     const ListRec* __restrict__ filt_rec, float two_sigA_sqr, float msdl, float* __restrict__ filt_sim,
-    uint32_t* __restrict__ E_cnt, unsigned long long* __restrict__ tests, uint32_t g_lo, uint32_t g_hi)
+    unsigned long long* __restrict__ tests, uint32_t g_lo, uint32_t g_hi, uint32_t max_cnt)
 {
-    const uint32_t g = g_lo + blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t g = g_lo + blockIdx.x * (blockDim.x / 8) + threadIdx.x / 8;  // 8 threads share a row
     if (g >= g_hi) return;
-    uint32_t kept = 0;
     const uint32_t n = filt_cnt[g];
+    if (!n) return;
     const uint32_t b = filt_off[g];
-    if (entries[g].has) {
-        const EntryDev& e1 = entries[g];
-        const uint32_t v1i = seg_view[g];
-        const ViewDev& v1 = views[v1i];
-        const uint32_t my_seg = g - v1.seg_off;
-        for (uint32_t z = 0; z < n; ++z) {
+    const bool has = entries[g].has != 0u;
+    if (has && (threadIdx.x & 7u) == 0) atomicAdd(tests, (unsigned long long)n);
+    const uint32_t v1i = seg_view[g];
+    const ViewDev& v1 = views[v1i];
+    const uint32_t my_seg = g - v1.seg_off;
+    for (uint32_t z = threadIdx.x & 7u; z < n; z += 8) {
+        float sim = -1.0f;
+        if (has) {
             const ListRec m2 = filt_rec[b + z];
             const ViewDev& v2 = views[m2.tgt_view];
             const uint32_t t = v2.seg_off + m2.tgt_seg;
-            float sim = -1.0f;
             if (entries[t].has) {
-                sim = affinity_sim(e1, v1, entries[t], v2, two_sigA_sqr, msdl);
+                sim = affinity_sim(entries[g], v1, entries[t], v2, two_sigA_sqr, msdl);
                 if (sim > 0.5f && t < g) {
                     // Line3D::unused: inserted before by entry t if its list holds this segment
                     const uint32_t tb = filt_off[t], tn = filt_cnt[t];
@@ -167,13 +169,23 @@ __global__ void __launch_bounds__(128) k4_edges_count_kernel(
                     }
                 }
             }
-            filt_sim[b + z] = sim;
-            if (sim > 0.5f) ++kept;
         }
-        if (n) atomicAdd(tests, (unsigned long long)n);
-    } else {
-        for (uint32_t z = 0; z < n; ++z) filt_sim[b + z] = -1.0f;
+        filt_sim[b + z] = sim;
     }
+    (void)max_cnt;
+}
+
+// pass 1b: edges kept per row
+__global__ void __launch_bounds__(256) k4_edges_count_kernel(const uint32_t* __restrict__ filt_off,
+                                                             const uint32_t* __restrict__ filt_cnt,
+                                                             const float* __restrict__ filt_sim,
+                                                             uint32_t* __restrict__ E_cnt, uint32_t g_lo, uint32_t g_hi)
+{
+    const uint32_t g = g_lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= g_hi) return;
+    const uint32_t n = filt_cnt[g], b = filt_off[g];
+    uint32_t kept = 0;
+    for (uint32_t z = 0; z < n; ++z) kept += filt_sim[b + z] > 0.5f ? 1u : 0u;
     E_cnt[g] = kept;
 }
 
@@ -270,11 +282,13 @@ int launch_k4_edges_count(const ViewDev* views, const uint32_t* seg_view, const 
                           float two_sigA_sqr, float msdl, float* filt_sim, uint32_t* E_cnt,
                           unsigned long long* tests, uint32_t g_lo, uint32_t g_hi, cudaStream_t st)
 {
+    (void)S;
     if (g_hi <= g_lo) return 0;
-    k4_edges_count_kernel<<<(g_hi - g_lo + 127) / 128, 128, 0, st>>>(views, seg_view, entries, S, filt_off, filt_cnt,
-                                                                      filt_rec, two_sigA_sqr, msdl, filt_sim, E_cnt,
-                                                                      tests, g_lo, g_hi);
-    return 1;
+    const uint32_t rows = g_hi - g_lo;
+    k4_edges_sim_kernel<<<(rows + 15) / 16, 128, 0, st>>>(views, seg_view, entries, filt_off, filt_cnt, filt_rec,
+                                                            two_sigA_sqr, msdl, filt_sim, tests, g_lo, g_hi, 0u);
+    k4_edges_count_kernel<<<(rows + 255) / 256, 256, 0, st>>>(filt_off, filt_cnt, filt_sim, E_cnt, g_lo, g_hi);
+    return 2;
 }
 
 int launch_k4_edges_write(const ViewDev* views, uint32_t S, const uint32_t* filt_off, const uint32_t* filt_cnt,
