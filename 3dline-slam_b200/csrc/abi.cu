@@ -503,7 +503,7 @@ int l3d_shard_import(l3d_ctx* ctx, int kind, const void* all, uint64_t stride_by
         CK(cudaMemcpyAsync(ctx->d_slice_g.p, ctx->slice_g.data(), ((size_t)world + 1) * 4, cudaMemcpyHostToDevice, st));
         if (stride_bytes * (uint64_t)world / 16 > 0xfffffff0ull) return fail(L3D_ERR_CAPACITY, "fold programs too large");
         ctx->cnt.gpu_launches += launch_k3_adopt_programs(src, stride_bytes, world, ctx->d_slice_g.p, S,
-                                                          ctx->d_prog_off.p, ctx->d_prog_nh.p, ctx->d_fwd_rec.p, st);
+                                                          ctx->d_prog_off.p, ctx->d_prog_nh.p, ctx->d_fwd_score.p, st);
         ctx->prog_all = src;
         return L3D_OK;
     }

@@ -627,7 +627,7 @@ static K3Tables k3_tables(l3d_ctx* ctx)
     K3Tables t;
     t.views = ctx->d_views.p; t.seg_view = ctx->d_seg_view.p; t.pairs = ctx->d_pairs.p; t.inc = ctx->d_inc.p;
     t.inc_off = ctx->d_inc_off.p; t.rays = ctx->d_rays.p; t.fwd_off = ctx->d_fwd_off.p; t.fwd_cnt = ctx->d_fwd_cnt.p;
-    t.fwd_rec = ctx->d_fwd_rec.p; t.fwd_row = ctx->d_fwd_row.p;
+    t.fwd_rec = ctx->d_fwd_rec.p; t.fwd_score = ctx->d_fwd_score.p; t.fwd_row = ctx->d_fwd_row.p;
     t.inv_off = ctx->d_inv_off.p; t.inv_fill = ctx->d_inv_fill.p; t.inv_ent = ctx->d_inv_ent.p;
     t.L_off = ctx->d_L_off.p; t.L_f = ctx->d_L_f.p; t.L_meta = ctx->d_L_meta.p; t.L_score = ctx->d_L_score.p;
     const bool big = ctx->k3_big_rows;
@@ -647,7 +647,7 @@ static K3Tables k3_tables(l3d_ctx* ctx)
 static int launch_records(l3d_ctx* ctx)
 {
     return launch_k3_records(ctx->d_pairs.p, (uint32_t)ctx->pairs.size(), (uint32_t)ctx->total_fwd, ctx->d_fwd_row.p,
-                             ctx->d_fwd_rec.p, ctx->d_inv_off.p, ctx->d_inv_fill.p, ctx->d_inv_ent.p,
+                             ctx->d_fwd_rec.p, ctx->d_fwd_score.p, ctx->d_inv_off.p, ctx->d_inv_fill.p, ctx->d_inv_ent.p,
                              ctx->slice_view[ctx->rank], ctx->slice_view[ctx->rank + 1], ctx->stream);
 }
 
@@ -679,6 +679,7 @@ int l3d_score_build(l3d_ctx* ctx)
     CK(ctx->d_inv_off.ensure(TR + 2));
     CK(ctx->d_inv_ent.ensure(F + 1));
     CK(ctx->d_fwd_row.ensure(F + 1));
+    CK(ctx->d_fwd_score.ensure(F + 1));
     CK(cudaMemsetAsync(ctx->d_inv_cap.p, 0, (TR + 1) * 4, st));
     CK(cudaMemsetAsync(ctx->d_inv_fill.p, 0, (TR + 1) * 4, st));
     CK(ctx->d_scan.ensure(scan_scratch_words((uint32_t)std::max<size_t>(TR, S) + 2) + 64));

@@ -36,8 +36,8 @@ int launch_fwd_place(const unsigned char*, uint64_t, int, const uint32_t*, int, 
                      cudaStream_t);
 int launch_k3_list_capacity(const ViewDev*, const uint32_t*, uint32_t, const IncDev*, const uint32_t*, const PairDev*,
                             const uint32_t*, const uint32_t*, uint32_t*, void*, cudaStream_t);
-int launch_k3_records(const PairDev*, uint32_t, uint32_t, const uint32_t*, FwdRec*, const uint32_t*, uint32_t*, uint2*,
-                      uint32_t, uint32_t, cudaStream_t);
+int launch_k3_records(const PairDev*, uint32_t, uint32_t, const uint32_t*, const FwdRec*, float*, const uint32_t*,
+                      uint32_t*, uint2*, uint32_t, uint32_t, cudaStream_t);
 size_t k3_wf_stats_bytes();
 size_t k3_sib_bytes();
 int k3_wf_max_inc();
@@ -232,7 +232,7 @@ struct l3d_ctx {
     DevBuf<float2> d_L_reg;
     DevBuf<uint32_t> d_L_f, d_L_c, d_L_h, d_fwd_row, d_prog_off, d_prog_nh;
     DevBuf<unsigned char> d_L_meta, d_prog;
-    DevBuf<float> d_L_score;
+    DevBuf<float> d_L_score, d_fwd_score;
     uint64_t prog_cap = 0;  // fold-program store, 16-byte units (grown on overflow)
     uint64_t L_total = 0, filt_cap = 0;
     uint32_t k3_maxm = 0;

@@ -107,7 +107,7 @@ struct IncDev {  // one incident pair of a view, in list order
 // device tables of the scoring stage (K3), filled from the context by ctx.cu
 struct K3Tables {
     const ViewDev* views; const uint32_t* seg_view; const PairDev* pairs; const IncDev* inc; const uint32_t* inc_off;
-    const SegRays* rays; const uint32_t* fwd_off; const uint32_t* fwd_cnt; FwdRec* fwd_rec; const uint32_t* fwd_row;
+    const SegRays* rays; const uint32_t* fwd_off; const uint32_t* fwd_cnt; FwdRec* fwd_rec; float* fwd_score; const uint32_t* fwd_row;
     const uint32_t* inv_off; const uint32_t* inv_fill; const uint2* inv_ent;
     const uint32_t* L_off; uint32_t* L_f; unsigned char* L_meta; float* L_score;
     void* L_sib; double* L_dir; float2* L_reg; uint32_t* L_c; uint32_t* L_h;
@@ -121,7 +121,7 @@ int launch_k3_build(const K3Tables& t, cudaStream_t st, int* err);
 int launch_k3_fold(const K3Tables& t, cudaStream_t st, int* err);
 int launch_k3_finish(const K3Tables& t, cudaStream_t st);
 int launch_k3_adopt_programs(const void* all, uint64_t stride, int world, const uint32_t* slice_g, uint32_t S,
-                             uint32_t* prog_off, uint32_t* prog_nh, FwdRec* fwd_rec, cudaStream_t st);
+                             uint32_t* prog_off, uint32_t* prog_nh, float* fwd_score, cudaStream_t st);
 
 // ---------------- launchers (each returns the number of kernels launched) ----------------
 int launch_scan_u32(const uint32_t* in, uint32_t* out, uint32_t n, uint32_t* scratch,

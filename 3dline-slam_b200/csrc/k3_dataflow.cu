@@ -163,14 +163,15 @@ __device__ __forceinline__ GeoRec make_geo(const D3& C, const D3& r1, const D3& 
 // segment (only for the target views [v_lo, v_hi) this rank builds)
 __global__ void __launch_bounds__(256) k3_record_kernel(const PairDev* __restrict__ pairs, uint32_t P, uint32_t F,
                                                         const uint32_t* __restrict__ fwd_row,
-                                                        FwdRec* __restrict__ fwd_rec,
+                                                        const FwdRec* __restrict__ fwd_rec,
+                                                        float* __restrict__ fwd_score,
                                                         const uint32_t* __restrict__ inv_off,
                                                         uint32_t* __restrict__ inv_fill, uint2* __restrict__ inv_ent,
                                                         uint32_t v_lo, uint32_t v_hi)
 {
     const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= F) return;
-    fwd_rec[f].score = 0.0f;
+    fwd_score[f] = 0.0f;
     const uint32_t row = fwd_row[f];
     const PairDev& D = pairs[pair_of_row(pairs, P, row)];
     if (!(D.emit_inverse && D.tgt_view >= v_lo && D.tgt_view < v_hi)) return;
@@ -190,7 +191,8 @@ struct BuildArgs {
     const uint32_t* inc_off;  // [V+1]
     const uint32_t* fwd_off;
     const uint32_t* fwd_cnt;
-    FwdRec* fwd_rec;
+    const FwdRec* fwd_rec;
+    float* fwd_score;  // score3D_ of every forward record, dense (doubles as the fold's ready flag)
     const SegRays* rays;
     const uint32_t* inv_off;   // start of the slot of every (pair, tgt segment)
     const uint32_t* inv_fill;  // entries in the slot
@@ -489,7 +491,7 @@ __global__ void __launch_bounds__(DF_THREADS, 16) k3_build_kernel(const BuildArg
         const uint32_t f = Lf[e];
         const uint32_t inv = Lm[e] >> 7;
         heads[hof[e]] = make_uint4(e | (inv << 31), start, c, f);
-        if (!inv) a.fwd_rec[f].score = -1.0f;  // pending: the fold kernel publishes the score
+        if (!inv) a.fwd_score[f] = -1.0f;  // pending: the fold kernel publishes the score
         uint32_t k = start;
         if (use_mask) {
             const uint32_t words = (m + 31) >> 5;
@@ -536,7 +538,7 @@ struct FoldArgs {
     const uint32_t* seg_view;
     const uint32_t* L_off;
     float* L_score;  // per potential entry: score3D_ of the entry as M (0 unless folded)
-    FwdRec* fwd_rec;
+    float* fwd_score;
     const uint32_t* prog_off;
     const uint32_t* prog_nh;
     const uint4* prog;
@@ -547,9 +549,9 @@ struct FoldArgs {
     uint32_t sleep_ns;    // back-off between two polls of a pending score
 };
 
-__device__ __forceinline__ float wait_score(FwdRec* fwd_rec, uint32_t f, WfStats* stats, uint32_t sleep_ns)
+__device__ __forceinline__ float wait_score(float* fwd_score, uint32_t f, WfStats* stats, uint32_t sleep_ns)
 {
-    const volatile float* p = &fwd_rec[f].score;
+    const volatile float* p = fwd_score + f;
     float s = *p;
     uint32_t spins = 0;
     while (s < 0.0f) {
@@ -618,9 +620,9 @@ __global__ void __launch_bounds__(FOLD_WARPS * 32) k3_fold_kernel(const FoldArgs
                     uint4 r = heads[x];
                     if (x < NH) {
                         // an inverse match exists iff its forward record scored > 0 (src/line3D.cc:1994-1996)
-                        if ((r.x >> 31) && !(wait_score(a.fwd_rec, r.w, a.stats, a.sleep_ns) > 0.0f)) r.z = 0xffffffffu;
+                        if ((r.x >> 31) && !(wait_score(a.fwd_score, r.w, a.stats, a.sleep_ns) > 0.0f)) r.z = 0xffffffffu;
                     } else if (__uint_as_float(r.y) > 0.0f && r.x != NOIDX) {
-                        if (!(wait_score(a.fwd_rec, r.x, a.stats, a.sleep_ns) > 0.0f)) r.y = 0u;
+                        if (!(wait_score(a.fwd_score, r.x, a.stats, a.sleep_ns) > 0.0f)) r.y = 0u;
                     }
                     sp[x] = r;
                 }
@@ -629,7 +631,7 @@ __global__ void __launch_bounds__(FOLD_WARPS * 32) k3_fold_kernel(const FoldArgs
                     const uint4 H = sp[h];
                     if (H.z == 0xffffffffu) continue;  // absent inverse match
                     const float score = fold_siblings(sp + NH, H.y, H.z);
-                    if (!(H.x >> 31)) *(volatile float*)&a.fwd_rec[H.w].score = score;
+                    if (!(H.x >> 31)) *(volatile float*)(a.fwd_score + H.w) = score;
                     if (mine) a.L_score[lbase + (H.x & 0x7fffffffu)] = score;
                     wmax = fmaxf(wmax, score);
                 }
@@ -637,14 +639,14 @@ __global__ void __launch_bounds__(FOLD_WARPS * 32) k3_fold_kernel(const FoldArgs
                 for (uint32_t h = lane; h < NH; h += 32) {
                     const uint4 H = heads[h];
                     const uint32_t e = H.x & 0x7fffffffu, inv = H.x >> 31;
-                    if (inv && !(wait_score(a.fwd_rec, H.w, a.stats, a.sleep_ns) > 0.0f)) continue;
+                    if (inv && !(wait_score(a.fwd_score, H.w, a.stats, a.sleep_ns) > 0.0f)) continue;
                     float score = 0.0f, stored = 0.0f;
                     uint32_t cur_run = NOIDX;
                     for (uint32_t t = H.y; t < H.y + H.z; ++t) {
                         const uint4 pr = prs[t];
                         const float sim = __uint_as_float(pr.y);
                         if (!(sim > 0.0f)) continue;
-                        if (pr.x != NOIDX && !(wait_score(a.fwd_rec, pr.x, a.stats, a.sleep_ns) > 0.0f)) continue;
+                        if (pr.x != NOIDX && !(wait_score(a.fwd_score, pr.x, a.stats, a.sleep_ns) > 0.0f)) continue;
                         const uint32_t run = pr.w >> 24;
                         if (run != cur_run) {
                             score = fa(score, sim);
@@ -656,7 +658,7 @@ __global__ void __launch_bounds__(FOLD_WARPS * 32) k3_fold_kernel(const FoldArgs
                             stored = sim;
                         }
                     }
-                    if (!inv) *(volatile float*)&a.fwd_rec[H.w].score = score;
+                    if (!inv) *(volatile float*)(a.fwd_score + H.w) = score;
                     if (mine) a.L_score[lbase + e] = score;
                     wmax = fmaxf(wmax, score);
                 }
@@ -679,6 +681,7 @@ struct FinishArgs {
     const uint32_t* inc_off;
     const SegRays* rays;
     const FwdRec* fwd_rec;
+    const float* fwd_score;
     const uint32_t* fwd_row;
     const uint32_t* L_off;
     const uint32_t* L_f;
@@ -766,7 +769,7 @@ __global__ void __launch_bounds__(FIN_WARPS * 32) k3_finish_kernel(const FinishA
         if (x < m) {
             f = a.L_f[lbase + x];
             meta = a.L_meta[lbase + x];
-            present = !(meta >> 7) || a.fwd_rec[f].score > 0.0f;
+            present = !(meta >> 7) || a.fwd_score[f] > 0.0f;
             if (present) {
                 s = a.L_score[lbase + x];
                 keep = (s > 0.0f) && (s > lim);
@@ -817,7 +820,7 @@ __global__ void __launch_bounds__(FIN_WARPS * 32) k3_finish_kernel(const FinishA
             if (x < m) {
                 f = a.L_f[lbase + x];
                 meta = a.L_meta[lbase + x];
-                if (!(meta >> 7) || a.fwd_rec[f].score > 0.0f) {
+                if (!(meta >> 7) || a.fwd_score[f] > 0.0f) {
                     s = a.L_score[lbase + x];
                     keep = (s > 0.0f) && (s > lim);
                 }
@@ -883,13 +886,13 @@ int launch_k3_list_capacity(const ViewDev* views, const uint32_t* seg_view, uint
     return 1;
 }
 
-int launch_k3_records(const PairDev* pairs, uint32_t P, uint32_t F, const uint32_t* fwd_row, FwdRec* fwd_rec,
-                      const uint32_t* inv_off, uint32_t* inv_fill, uint2* inv_ent, uint32_t v_lo, uint32_t v_hi,
+int launch_k3_records(const PairDev* pairs, uint32_t P, uint32_t F, const uint32_t* fwd_row, const FwdRec* fwd_rec,
+                      float* fwd_score, const uint32_t* inv_off, uint32_t* inv_fill, uint2* inv_ent, uint32_t v_lo, uint32_t v_hi,
                       cudaStream_t st)
 {
     if (!F || !P) return 0;
-    k3_record_kernel<<<(F + 255) / 256, 256, 0, st>>>(pairs, P, F, fwd_row, fwd_rec, inv_off, inv_fill, inv_ent, v_lo,
-                                                       v_hi);
+    k3_record_kernel<<<(F + 255) / 256, 256, 0, st>>>(pairs, P, F, fwd_row, fwd_rec, fwd_score, inv_off, inv_fill,
+                                                       inv_ent, v_lo, v_hi);
     return 1;
 }
 size_t k3_wf_stats_bytes() { return sizeof(WfStats); }
@@ -908,7 +911,7 @@ static BuildArgs build_args(const K3Tables& t, uint32_t maxm)
 {
     BuildArgs b;
     b.views = t.views; b.seg_view = t.seg_view; b.pairs = t.pairs; b.inc = t.inc; b.inc_off = t.inc_off;
-    b.fwd_off = t.fwd_off; b.fwd_cnt = t.fwd_cnt; b.fwd_rec = t.fwd_rec;
+    b.fwd_off = t.fwd_off; b.fwd_cnt = t.fwd_cnt; b.fwd_rec = t.fwd_rec; b.fwd_score = t.fwd_score;
     b.rays = t.rays;
     b.inv_off = t.inv_off; b.inv_fill = t.inv_fill; b.inv_ent = t.inv_ent;
     b.L_off = t.L_off; b.L_f = t.L_f; b.L_meta = t.L_meta;
@@ -956,7 +959,7 @@ int launch_k3_fold(const K3Tables& t, cudaStream_t st, int* err)
 {
     if (!t.S) return 0;
     FoldArgs f;
-    f.seg_view = t.seg_view; f.L_off = t.L_off; f.L_score = t.L_score; f.fwd_rec = t.fwd_rec;
+    f.seg_view = t.seg_view; f.L_off = t.L_off; f.L_score = t.L_score; f.fwd_score = t.fwd_score;
     f.prog_off = t.prog_off; f.prog_nh = t.prog_nh; f.prog = (const uint4*)t.prog; f.view_max = t.view_max;
     f.stats = (WfStats*)t.stats; f.S = t.S; f.g_lo = t.g_lo; f.g_hi = t.g_hi;
     int dev = 0, sms = 0, per_sm = 0;
@@ -994,7 +997,7 @@ int launch_k3_finish(const K3Tables& t, cudaStream_t st)
     if (t.g_hi <= t.g_lo) return 0;
     FinishArgs c;
     c.views = t.views; c.seg_view = t.seg_view; c.pairs = t.pairs; c.inc = t.inc; c.inc_off = t.inc_off;
-    c.rays = t.rays; c.fwd_rec = t.fwd_rec; c.fwd_row = t.fwd_row; c.L_off = t.L_off; c.L_f = t.L_f;
+    c.rays = t.rays; c.fwd_rec = t.fwd_rec; c.fwd_score = t.fwd_score; c.fwd_row = t.fwd_row; c.L_off = t.L_off; c.L_f = t.L_f;
     c.L_meta = t.L_meta; c.L_score = t.L_score; c.L_cnt = t.L_cnt; c.L_rec = t.L_rec; c.view_max = t.view_max;
     c.filt_rec = t.filt_rec; c.filt_cap = t.filt_cap; c.filt_off = t.filt_off; c.filt_cnt = t.filt_cnt;
     c.entries = t.entries; c.stats = (WfStats*)t.stats; c.S = t.S; c.g_lo = t.g_lo; c.g_hi = t.g_hi;
@@ -1009,7 +1012,7 @@ __global__ void __launch_bounds__(256) k3_adopt_programs_kernel(const unsigned c
                                                                 int world, const uint32_t* __restrict__ slice_g,
                                                                 uint32_t S, uint32_t* __restrict__ prog_off,
                                                                 uint32_t* __restrict__ prog_nh,
-                                                                FwdRec* __restrict__ fwd_rec)
+                                                                float* __restrict__ fwd_score)
 {
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= S) return;
@@ -1027,17 +1030,17 @@ __global__ void __launch_bounds__(256) k3_adopt_programs_kernel(const unsigned c
         const uint4* heads = reinterpret_cast<const uint4*>(all) + rec0 + off + 1;
         for (uint32_t h = 0; h < nh; ++h) {
             const uint4 H = heads[h];
-            if (!(H.x >> 31)) fwd_rec[H.w].score = -1.0f;
+            if (!(H.x >> 31)) fwd_score[H.w] = -1.0f;
         }
     }
 }
 
 int launch_k3_adopt_programs(const void* all, uint64_t stride, int world, const uint32_t* slice_g, uint32_t S,
-                             uint32_t* prog_off, uint32_t* prog_nh, FwdRec* fwd_rec, cudaStream_t st)
+                             uint32_t* prog_off, uint32_t* prog_nh, float* fwd_score, cudaStream_t st)
 {
     if (!S) return 0;
     k3_adopt_programs_kernel<<<(S + 255) / 256, 256, 0, st>>>((const unsigned char*)all, stride, world, slice_g, S,
-                                                               prog_off, prog_nh, fwd_rec);
+                                                               prog_off, prog_nh, fwd_score);
     return 1;
 }
 
