@@ -127,6 +127,11 @@ def lib():
         L.l3d_shard_import.argtypes = [vp, C.c_int, vp, u64, C.c_int, vp, C.c_int]
         L.l3d_shard_export_hdr.argtypes = [vp, C.c_int, vp, u64]
         L.l3d_shard_import_hdr.argtypes = [vp, C.c_int, vp, u64, C.c_int, vp, C.POINTER(C.c_int)]
+        L.l3d_stream_begin.argtypes = [vp, C.c_int]
+        L.l3d_stream_begin_cycle.argtypes = [vp]
+        L.l3d_stream_add_image.argtypes = [vp, C.POINTER(View), vp, vp, u32]
+        L.l3d_stream_delete_image.argtypes = [vp, u32]
+        L.l3d_stream_update_image.argtypes = [vp, u32, vp, vp, f32, vp, u32]
         L.l3d_test_expf.argtypes = [vp, vp, vp, u32]
         L.l3d_test_acos.argtypes = [vp, vp, vp, u32]
         L.l3d_bench_fp32_peak.argtypes = [vp, vp]
@@ -452,6 +457,46 @@ class Line3D:
         self._ck(self.L.l3d_shard_import_hdr(self.h, int(kind), C.c_void_p(ptr), stride_bytes, int(world), _p(sz),
                                              C.byref(redo)))
         return bool(redo.value), sz
+
+
+class Line3DStream(Line3D):
+    """The same mirror driven the way L3DPPing::Run (src/L3DPPing.cpp:98-236) drives its Line3D object:
+    per cycle beginCycle(), deleteImage()*, addImage()*, UpdataImage()* for every current view, then
+    matchImages() and reconstruct3Dlines().  The context keeps matched_ / processed_ / the filtered
+    lists with their scores from cycle to cycle (include/l3dpp_b200.h, l3d_stream_*)."""
+
+    def __init__(self, *a, **kw):
+        super().__init__(*a, **kw)
+        self._ck(self.L.l3d_stream_begin(self.h, int(self.neighbors_by_worldpoints)))
+        self._dirty = False
+
+    def beginCycle(self):
+        self._ck(self.L.l3d_stream_begin_cycle(self.h))
+
+    def addImage(self, camID, image_size, K, R, t, median_depth, wps_or_neighbors, line_segments):
+        w, h = image_size
+        segs = np.ascontiguousarray(line_segments, dtype=np.float32).reshape(-1, 4)
+        nb = np.ascontiguousarray(wps_or_neighbors, dtype=np.uint32)
+        vv = View()
+        vv.cam_id, vv.width, vv.height, vv.num_segs = int(camID), int(w), int(h), segs.shape[0]
+        vv.K[:] = _f64(K).reshape(9).tolist()
+        vv.R[:] = _f64(R).reshape(9).tolist()
+        vv.t[:] = _f64(t).reshape(3).tolist()
+        vv.median_depth = float(median_depth)
+        self._ck(self.L.l3d_stream_add_image(self.h, C.byref(vv), _p(segs), _p(nb), nb.size))
+        self._views[int(camID)] = dict(segs=segs)
+
+    def deleteImage(self, camID):
+        rc = self.L.l3d_stream_delete_image(self.h, int(camID))
+        return rc == 0
+
+    def UpdataImage(self, camID, R, t, median_depth, wps_or_neighbors):
+        nb = np.ascontiguousarray(wps_or_neighbors, dtype=np.uint32)
+        R, t = _f64(R).reshape(9), _f64(t).reshape(3)
+        self._ck(self.L.l3d_stream_update_image(self.h, int(camID), _p(R), _p(t), float(median_depth), _p(nb), nb.size))
+
+    def upload(self):
+        pass
 
 
 X_FORWARD, X_PROGRAMS, X_HYPOTHESES, X_EDGES = 0, 1, 2, 3

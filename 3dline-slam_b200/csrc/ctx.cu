@@ -62,6 +62,7 @@ int l3d_scene_begin(l3d_ctx* ctx)
     if (!ctx) return fail(L3D_ERR_ARG, "ctx is NULL");
     ctx->views.clear();
     ctx->cam2view.clear();
+    ctx->stream_mode = false;
     ctx->by_worldpoints = false;
     ctx->committed = false;
     ctx->stage = 0;
@@ -223,13 +224,14 @@ int upload_views(l3d_ctx* ctx)
 }
 
 // Line3D::translate (src/line3D.cc:643-680): per-axis median of the camera centres
-static void compute_translation(l3d_ctx* ctx)
+void compute_translation(l3d_ctx* ctx)
 {
     double* tr[3] = {&ctx->translation.x, &ctx->translation.y, &ctx->translation.z};
     for (int a = 0; a < 3; ++a) {
         *tr[a] = 0.0;
         std::vector<double> c;
         for (auto& hv : ctx->views) {
+            if (!hv.current) continue;  // view_order_ holds the current views only (src/line3D.cc:396-430)
             const double val = a == 0 ? hv.cam.C.x : (a == 1 ? hv.cam.C.y : hv.cam.C.z);
             if (std::fabs(val) > 1e-12) c.push_back(val);
         }
@@ -239,10 +241,11 @@ static void compute_translation(l3d_ctx* ctx)
         }
     }
 }
-static void apply_translation(l3d_ctx* ctx, double sign)
+void apply_translation(l3d_ctx* ctx, double sign)
 {
     const hg::V3 tv{sign * ctx->translation.x, sign * ctx->translation.y, sign * ctx->translation.z};
-    for (auto& hv : ctx->views) hv.cam.translate(tv);
+    for (auto& hv : ctx->views)
+        if (hv.current) hv.cam.translate(tv);
 }
 
 __global__ void pair_totals_kernel(const PairDev* __restrict__ pairs, uint32_t P, const uint32_t* __restrict__ fwd_off,
@@ -282,6 +285,52 @@ int refresh_pair_totals(l3d_ctx* ctx)
     }
     ctx->pair_total_sum = run;
     return L3D_OK;
+}
+
+// batches over local pairs: bounded bit-mask size (fills mask_base / batch_row0 of pairs_h, the
+// K1 CTA list and ctx->batches)
+void plan_batches(l3d_ctx* ctx)
+{
+    const uint32_t P = (uint32_t)ctx->pairs.size();
+    const uint64_t max_words = 1ull << 27;  // 512 MB of mask
+    const uint32_t rows_per_cta = (uint32_t)k1_rows_per_cta();
+    ctx->batches.clear();
+    ctx->ctas_h.clear();
+    Batch cur{};
+    bool open = false;
+    auto close = [&]() {
+        if (open) {
+            cur.n_ctas = (uint32_t)ctx->ctas_h.size() - cur.cta0;
+            ctx->batches.push_back(cur);
+            open = false;
+        }
+    };
+    for (uint32_t p = 0; p < P; ++p) {
+        if (!ctx->pairs[p].local) {
+            close();  // keep batch rows contiguous
+            continue;
+        }
+        PairDev& d = ctx->pairs_h[p];
+        const uint64_t w = (uint64_t)d.words * d.n_src;
+        if (open && cur.mask_words + w > max_words) close();
+        if (!open) {
+            cur = Batch{};
+            cur.pair0 = p;
+            cur.row0 = d.row_base;
+            cur.cta0 = (uint32_t)ctx->ctas_h.size();
+            open = true;
+        }
+        d.mask_base = cur.mask_words;
+        d.batch_row0 = cur.row0;
+        cur.mask_words += w;
+        cur.max_tgt = std::max(cur.max_tgt, d.n_tgt);
+        cur.n_rows += d.n_src;
+        cur.pair1 = p + 1;
+        ctx->pairs[p].batch = (uint32_t)ctx->batches.size();
+        for (uint32_t t = 0; t * rows_per_cta < d.n_src; ++t) ctx->ctas_h.push_back(K1Cta{p, t});
+    }
+    close();
+
 }
 
 // ------------------------------------------------------------------------------------------
@@ -410,45 +459,7 @@ int plan_pairs(l3d_ctx* ctx)
         ctx->slice_row[q] = r;
     }
 
-    // batches over local pairs: bounded bit-mask size
-    const uint64_t max_words = 1ull << 27;  // 512 MB of mask
-    const uint32_t rows_per_cta = (uint32_t)k1_rows_per_cta();
-    ctx->batches.clear();
-    ctx->ctas_h.clear();
-    Batch cur{};
-    bool open = false;
-    auto close = [&]() {
-        if (open) {
-            cur.n_ctas = (uint32_t)ctx->ctas_h.size() - cur.cta0;
-            ctx->batches.push_back(cur);
-            open = false;
-        }
-    };
-    for (uint32_t p = 0; p < P; ++p) {
-        if (!ctx->pairs[p].local) {
-            close();  // keep batch rows contiguous
-            continue;
-        }
-        PairDev& d = ctx->pairs_h[p];
-        const uint64_t w = (uint64_t)d.words * d.n_src;
-        if (open && cur.mask_words + w > max_words) close();
-        if (!open) {
-            cur = Batch{};
-            cur.pair0 = p;
-            cur.row0 = d.row_base;
-            cur.cta0 = (uint32_t)ctx->ctas_h.size();
-            open = true;
-        }
-        d.mask_base = cur.mask_words;
-        d.batch_row0 = cur.row0;
-        cur.mask_words += w;
-        cur.max_tgt = std::max(cur.max_tgt, d.n_tgt);
-        cur.n_rows += d.n_src;
-        cur.pair1 = p + 1;
-        ctx->pairs[p].batch = (uint32_t)ctx->batches.size();
-        for (uint32_t t = 0; t * rows_per_cta < d.n_src; ++t) ctx->ctas_h.push_back(K1Cta{p, t});
-    }
-    close();
+    plan_batches(ctx);
 
     // incident pairs per view in list order: inverse blocks (source views ascending = the order
     // their storeInverseMatches ran), then forward blocks (targets ascending)
@@ -492,30 +503,10 @@ int set_params(l3d_ctx* ctx, const l3d_params* params)
     return L3D_OK;
 }
 
-int l3d_match_stage12(l3d_ctx* ctx, const l3d_params* params)
+// per-segment tables (K0), then K1 + K2 over the planned batches -> forward store
+int run_stage12_batches(l3d_ctx* ctx)
 {
-    if (!ctx) return fail(L3D_ERR_ARG, "ctx is NULL");
-    if (!ctx->committed) return fail(L3D_ERR_STATE, "scene not committed");
-    int rc = set_params(ctx, params);
-    if (rc) return rc;
-    CK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
-    ctx->tm.reset();
-    cudaEvent_t ev_total = ctx->tm.begin(L3D_T_TOTAL, st);
-
-    // translate(), spatial regularisers (src/line3D.cc:568-590)
-    if (!ctx->raw_mode) {
-        compute_translation(ctx);
-        apply_translation(ctx, -1.0);
-        for (auto& hv : ctx->views) {
-            hv.k = hv.cam.spatial_regularizer(ctx->prm.sigma_p);
-            hv.median_depth = 0.0f;
-        }
-    }
-    rc = plan_pairs(ctx);
-    if (rc) return rc;
-    rc = upload_views(ctx);
-    if (rc) return rc;
     const uint32_t V = (uint32_t)ctx->views.size(), P = (uint32_t)ctx->pairs.size(), S = ctx->S;
 
     // per-segment tables
@@ -604,6 +595,35 @@ int l3d_match_stage12(l3d_ctx* ctx, const l3d_params* params)
     ctx->edges_all = nullptr;
     ctx->stage3_phase = ctx->stage4_phase = 0;
 
+    return L3D_OK;
+}
+
+int l3d_match_stage12(l3d_ctx* ctx, const l3d_params* params)
+{
+    if (!ctx) return fail(L3D_ERR_ARG, "ctx is NULL");
+    if (!ctx->committed) return fail(L3D_ERR_STATE, "scene not committed");
+    int rc = set_params(ctx, params);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    ctx->tm.reset();
+    cudaEvent_t ev_total = ctx->tm.begin(L3D_T_TOTAL, st);
+
+    // translate(), spatial regularisers (src/line3D.cc:568-590)
+    if (!ctx->raw_mode) {
+        compute_translation(ctx);
+        apply_translation(ctx, -1.0);
+        for (auto& hv : ctx->views) {
+            hv.k = hv.cam.spatial_regularizer(ctx->prm.sigma_p);
+            hv.median_depth = 0.0f;
+        }
+    }
+    rc = plan_pairs(ctx);
+    if (rc) return rc;
+    rc = upload_views(ctx);
+    if (rc) return rc;
+    rc = run_stage12_batches(ctx);
+    if (rc) return rc;
     rc = refresh_pair_totals(ctx);
     if (rc) return rc;
     ctx->tm.end(ev_total, st);
@@ -922,6 +942,7 @@ int l3d_match_stage3(l3d_ctx* ctx)
 
 int l3d_match_images(l3d_ctx* ctx, const l3d_params* params)
 {
+    if (ctx && ctx->stream_mode) return stream_match_images(ctx, params);
     int rc = l3d_match_stage12(ctx, params);
     if (rc) return rc;
     return l3d_match_stage3(ctx);  // stage timers keep accumulating until the next stage12
@@ -954,7 +975,7 @@ int l3d_affinity_edges(l3d_ctx* ctx)
     // median scene depth of the lines (src/line3D.cc:2074-2091)
     std::vector<float> sd;
     for (auto& hv : ctx->views)
-        if (hv.median_depth > 1e-12) sd.push_back(hv.median_depth);
+        if (hv.median_depth > 1e-12 && hv.current) sd.push_back(hv.median_depth);  // views in view_order_ only
     if (!sd.empty()) {
         std::sort(sd.begin(), sd.end());
         ctx->med_scene_depth_lines = sd[sd.size() / 2];
@@ -964,7 +985,8 @@ int l3d_affinity_edges(l3d_ctx* ctx)
     ctx->ev_total4 = ctx->tm.begin(L3D_T_TOTAL, st);
     cudaEvent_t ev = ctx->tm.begin(L3D_T_AFFINITY, st);
     const ListRec* filt = ctx->filt_all ? ctx->filt_all : ctx->d_filt_rec.p;
-    const size_t nf = (size_t)ctx->cnt.filtered_entries;
+    // stream mode: the filtered lists of a cycle live at per-view bases inside an arena of st_f_extent records
+    const size_t nf = ctx->stream_mode ? (size_t)ctx->st_f_extent : (size_t)ctx->cnt.filtered_entries;
     const uint32_t g_lo = ctx->slice_g[ctx->rank], g_hi = ctx->slice_g[ctx->rank + 1];
     CK(ctx->d_filt_sim.ensure(nf + 1));
     CK(ctx->d_E_cnt.ensure((size_t)S + 1));
@@ -1209,6 +1231,54 @@ int l3d_get_view_lists(l3d_ctx* ctx, uint32_t cam_id, int which, uint32_t* row_o
     std::vector<uint32_t> off(N + 1, 0), cnt(N, 0);
     const ListRec* src = nullptr;
     uint64_t region = 0;
+    if (which == 0 && ctx->stream_mode) {
+        // stream mode: the cycle's working lists; entries to cameras deleted this cycle are flagged dead
+        // (Line3D::updateMatch, src/line3D.cc:1016-1055) and skipped here
+        CK(cudaMemcpyAsync(off.data(), ctx->d_L_off.p + hv.seg_off, (size_t)N * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(cnt.data(), ctx->d_L_cnt.p + hv.seg_off, (size_t)N * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        uint32_t lo = 0xffffffffu, hi = 0;
+        for (uint32_t i = 0; i < N; ++i)
+            if (cnt[i]) {
+                lo = std::min(lo, off[i]);
+                hi = std::max(hi, off[i] + cnt[i]);
+            }
+        if (lo == 0xffffffffu) lo = hi = 0;
+        std::vector<ListRec> tmp(hi - lo);
+        if (hi > lo) {
+            CK(cudaMemcpyAsync(tmp.data(), ctx->d_st_W_rec.p + lo, (size_t)(hi - lo) * sizeof(ListRec),
+                               cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+        }
+        uint64_t total = 0;
+        for (uint32_t i = 0; i < N; ++i) {
+            row_off[i] = (uint32_t)total;
+            for (uint32_t e = 0; e < cnt[i]; ++e)
+                if (!(tmp[(size_t)off[i] - lo + e].flags & 4u)) ++total;
+        }
+        row_off[N] = (uint32_t)total;
+        if (out_count) *out_count = total;
+        if (total > cap) return fail(L3D_ERR_CAPACITY, "need %llu records", (unsigned long long)total);
+        if (total == 0) return L3D_OK;
+        if (!recs) return fail(L3D_ERR_ARG, "recs is NULL");
+        uint64_t n = 0;
+        for (uint32_t i = 0; i < N; ++i)
+            for (uint32_t e = 0; e < cnt[i]; ++e) {
+                const ListRec& L = tmp[(size_t)off[i] - lo + e];
+                if (L.flags & 4u) continue;
+                l3d_list_rec& o = recs[n++];
+                o.tgt_cam = ctx->views[L.tgt_view].v.cam_id;
+                o.tgt_seg = L.tgt_seg;
+                o.overlap_score = L.overlap;
+                o.score3D = L.score;
+                o.depth_p1 = L.d_p1;
+                o.depth_p2 = L.d_p2;
+                o.depth_q1 = L.d_q1;
+                o.depth_q2 = L.d_q2;
+                o.flags = L.flags & 1u;
+            }
+        return L3D_OK;
+    }
     if (which == 0) {
         if (!ctx->prm.keep_scored) return fail(L3D_ERR_STATE, "keep_scored was not set");
         if (v < ctx->slice_view[ctx->rank] || v >= ctx->slice_view[ctx->rank + 1])

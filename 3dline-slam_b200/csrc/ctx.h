@@ -116,6 +116,14 @@ struct HostView {
     hg::Camera cam;
     float k = 0.0f, median_depth = 0.0f, median_sigma = 0.0f;
     uint32_t seg_off = 0;
+    // key-frame stream mode (stream.cu): views are never removed from the table (Line3D::deleteImage
+    // keeps views_[camID], src/line3D.cc:396-430)
+    bool current = true;       // in view_order_ / views_reserved_
+    bool processed = false;    // processed_[camID]
+    bool uploaded = false;     // segments resident on the device
+    uint32_t filt_total = 0;   // entries that survived the view's last filterMatches
+    uint32_t num_wps = 0;      // num_worldpoints_[camID] (kept across cycles)
+    bool has_fixed = false;    // fixed_visual_neighbors_ holds the view (set by UpdataImage)
 };
 
 struct HostPair {
@@ -277,6 +285,17 @@ struct l3d_ctx {
     // host results
     std::vector<int32_t> cluster_ids;
 
+    // key-frame stream mode (stream.cu)
+    bool stream_mode = false;
+    std::set<uint32_t> st_add, st_del;                   // Add_camID_ / Delete_camID_ as view indices
+    std::set<std::pair<uint32_t, uint32_t>> st_matched;  // matched_ (unordered view pairs)
+    uint32_t st_cycle = 0;
+    uint64_t st_w_extent = 0, st_f_extent = 0;  // extents of this cycle's working / filtered arenas
+    DevBuf<ListRec> d_st_filt_old, d_st_W_rec;
+    DevBuf<unsigned char> d_st_W_geo, d_st_pairs, d_st_vflag, d_st_stats;
+    DevBuf<uint32_t> d_st_W_row, d_st_I_cnt, d_st_I_off, d_st_I_fill, d_st_I_key, d_st_W_cnt, d_st_W_off, d_st_F_cnt,
+        d_st_F_off, d_st_best, d_st_view_total;
+
     l3d_counts cnt{};
     StageTimer tm;
 };
@@ -285,6 +304,11 @@ struct l3d_ctx {
 // shared between ctx.cu and abi.cu
 int refresh_pair_totals(l3d_ctx* ctx);
 int plan_pairs(l3d_ctx* ctx);
+void plan_batches(l3d_ctx* ctx);
+int run_stage12_batches(l3d_ctx* ctx);
+void compute_translation(l3d_ctx* ctx);
+void apply_translation(l3d_ctx* ctx, double sign);
+int stream_match_images(l3d_ctx* ctx, const l3d_params* params);
 int upload_views(l3d_ctx* ctx);
 int set_params(l3d_ctx* ctx, const l3d_params* params);
 int score_rebuild(l3d_ctx* ctx, uint32_t needed_units);

@@ -69,6 +69,15 @@ void Camera::init(const double* K9, const double* R9, const double* t3)
     C = mul(Rt, V3{t.x * -1.0, t.y * -1.0, t.z * -1.0});
 }
 
+void Camera::update(const double* R9, const double* t3)
+{
+    std::memcpy(R.m, R9, sizeof(R.m));
+    Rt = transpose(R);
+    RtKinv = matmul(Rt, Kinv);
+    t = V3{t3[0], t3[1], t3[2]};
+    C = mul(Rt, V3{t.x * -1.0, t.y * -1.0, t.z * -1.0});
+}
+
 void Camera::translate(const V3& tv)
 {
     C = C + tv;

@@ -71,6 +71,7 @@ struct Camera {
     M3 K, Kinv, R, Rt, RtKinv;
     V3 t, C, pp;
     void init(const double* K9, const double* R9, const double* t3);
+    void update(const double* R9, const double* t3);  // View::UpdateView (src/view.cc:62-87)
     void translate(const V3& tv);
     float spatial_regularizer(float r) const;
 };

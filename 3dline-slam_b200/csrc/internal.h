@@ -123,6 +123,35 @@ int launch_k3_finish(const K3Tables& t, cudaStream_t st);
 int launch_k3_adopt_programs(const void* all, uint64_t stride, int world, const uint32_t* slice_g, uint32_t S,
                              uint32_t* prog_off, uint32_t* prog_nh, float* fwd_score, cudaStream_t st);
 
+// key-frame stream mode (k3_stream.cu): a new view pair as seen from one of its views -- incoming
+// (the view is the pair's target and receives inverse matches) or outgoing (the view is the source)
+struct StreamPair {
+    uint32_t rec_start, rec_cnt;  // forward records of the pair
+    uint32_t row_base, n_src;     // pair rows
+    uint32_t other;               // the other view
+    uint32_t pad;
+};
+
+// one view's step of the key-frame stream mode (k3_stream.cu)
+struct StreamViewArgs {
+    uint32_t view, n, g0, n_in, n_out, in_total, w_base, f_base, w_cap, f_cap;
+    const void* pairs_in; const void* pairs_out;  // StreamPair[] on the device
+    const FwdRec* fwd_rec; float* fwd_score; const uint32_t* fwd_off; const uint32_t* fwd_cnt;
+    uint32_t* I_off; uint32_t* I_cnt; uint32_t* I_fill; uint32_t* I_key;
+    uint32_t* scan; size_t scan_words;
+    uint32_t* filt_off; uint32_t* filt_cnt; ListRec* filt_old; ListRec* filt_new;
+    uint32_t* W_cnt; uint32_t* W_off; ListRec* W_rec; uint32_t* W_row; ListGeo* W_geo;
+    uint32_t* L_off; uint32_t* L_cnt;
+    const ViewDev* views; const SegRays* rays; const double* midray; const unsigned char* vflag;
+    uint32_t* view_max; uint32_t* F_cnt; uint32_t* F_off; uint32_t* best_e;
+    EntryDev* entries; uint32_t* view_total; void* stats;
+    float two_sigA_sqr;
+};
+int launch_stream_view(const StreamViewArgs& a, cudaStream_t st);
+int launch_stream_update_entries(uint32_t S, const uint32_t* seg_view, const ViewDev* views, const SegRays* rays,
+                                 const SegPlane* planes, EntryDev* entries, cudaStream_t st);
+size_t stream_stats_bytes();
+
 // ---------------- launchers (each returns the number of kernels launched) ----------------
 int launch_scan_u32(const uint32_t* in, uint32_t* out, uint32_t n, uint32_t* scratch,
                     size_t scratch_words, cudaStream_t st);

@@ -1,0 +1,450 @@
+// stream.cu -- the incremental (key-frame stream) mode of the path behind the C ABI: what
+// L3DPPing::Run (src/L3DPPing.cpp:98-236) drives on a Line3D object between two reconstructions --
+// deleteImage (src/line3D.cc:396-430), addImage (src/line3D.cc:117-227), UpdataImage
+// (src/line3D.cc:433-487) -- and the state Line3D::matchImages keeps from one cycle to the next:
+// matched_ (a view pair is matched once), processed_ (inverse matches are stored only into views
+// that have not been scored yet), the filtered match lists with their scores, Add_camID_ /
+// Delete_camID_ (the score deltas of Line3D::scoringCPU, src/line3D.cc:1439-1512).
+//
+// Device side: the view table only grows (a deleted view keeps its segments and its last pose, as
+// views_ does); K0/K1/K2 run over the NEW pairs of the cycle; the scoring walk is per view
+// (k3_stream.cu); K4 and the clustering are the batch mode's.
+#include "ctx.h"
+
+
+int l3d_stream_begin(l3d_ctx* ctx, int neighbors_by_worldpoints)
+{
+    if (!ctx) return fail(L3D_ERR_ARG, "ctx is NULL");
+    int rc = l3d_scene_begin(ctx);
+    if (rc) return rc;
+    ctx->stream_mode = true;
+    ctx->by_worldpoints = neighbors_by_worldpoints != 0;
+    ctx->st_add.clear();
+    ctx->st_del.clear();
+    ctx->st_matched.clear();
+    ctx->st_cycle = 0;
+    ctx->S = 0;
+    ctx->cnt = l3d_counts{};
+    return L3D_OK;
+}
+
+// the resets L3DPPing::Run performs before it deletes / adds / updates (src/L3DPPing.cpp:98-103)
+int l3d_stream_begin_cycle(l3d_ctx* ctx)
+{
+    if (!ctx) return fail(L3D_ERR_ARG, "ctx is NULL");
+    if (!ctx->stream_mode) return fail(L3D_ERR_STATE, "not in stream mode (l3d_stream_begin)");
+    for (auto& hv : ctx->views) hv.wps.clear();  // views2worldpoints_ / worldpoints2views_
+    ctx->st_add.clear();
+    ctx->st_del.clear();
+    return L3D_OK;
+}
+
+// Line3D::addImage (src/line3D.cc:117-227).  As in the reference's fork the list is only checked for
+// emptiness here; world points / neighbours are registered by l3d_stream_update_image.
+int l3d_stream_add_image(l3d_ctx* ctx, const l3d_view* view, const float* segs, const uint32_t* wps_or_nbrs,
+                         uint32_t n_list)
+{
+    if (!ctx || !view) return fail(L3D_ERR_ARG, "NULL argument");
+    if (!ctx->stream_mode) return fail(L3D_ERR_STATE, "not in stream mode (l3d_stream_begin)");
+    if (std::max(view->width, view->height) < 400)
+        return fail(L3D_ERR_ARG, "image is too small for reliable results: %u px (larger side should be >= 400px)",
+                    std::max(view->width, view->height));
+    auto f = ctx->cam2view.find(view->cam_id);
+    if (f != ctx->cam2view.end()) {
+        if (ctx->views[f->second].current) return fail(L3D_ERR_ARG, "camera ID [%u] already in use!", view->cam_id);
+        return fail(L3D_ERR_ARG, "camera ID [%u] was deleted; the stream mode does not re-use camera ids", view->cam_id);
+    }
+    if (!ctx->views.empty() && ctx->views.back().v.cam_id > view->cam_id)
+        return fail(L3D_ERR_ARG, "stream mode: camera ids must be added in ascending order (%u after %u)", view->cam_id,
+                    ctx->views.back().v.cam_id);
+    if (n_list == 0)
+        return fail(L3D_ERR_ARG, ctx->by_worldpoints ? "view [%u] has no worldpoints!" : "view [%u] has no visual neighbors!",
+                    view->cam_id);
+    (void)wps_or_nbrs;
+    if (view->num_segs == 0 || !segs) return fail(L3D_ERR_ARG, "no line segments found in image [%u]!", view->cam_id);
+    if ((uint64_t)ctx->S + view->num_segs > 0xfffffff0ull) return fail(L3D_ERR_CAPACITY, "too many segments");
+    HostView hv;
+    hv.v = *view;
+    hv.segs.assign(segs, segs + 4 * (size_t)view->num_segs);
+    hv.cam.init(view->K, view->R, view->t);
+    hv.seg_off = ctx->S;
+    const uint32_t idx = (uint32_t)ctx->views.size();
+    ctx->S += view->num_segs;
+    ctx->cam2view[view->cam_id] = idx;
+    ctx->views.push_back(std::move(hv));
+    ctx->st_add.insert(idx);
+    return L3D_OK;
+}
+
+// Line3D::deleteImage (src/line3D.cc:396-430)
+int l3d_stream_delete_image(l3d_ctx* ctx, uint32_t cam_id)
+{
+    if (!ctx) return fail(L3D_ERR_ARG, "ctx is NULL");
+    if (!ctx->stream_mode) return fail(L3D_ERR_STATE, "not in stream mode (l3d_stream_begin)");
+    auto f = ctx->cam2view.find(cam_id);
+    if (f == ctx->cam2view.end() || !ctx->views[f->second].current)
+        return fail(L3D_ERR_ARG, "camera ID [%u] non_existent!", cam_id);
+    HostView& hv = ctx->views[f->second];
+    hv.current = false;
+    hv.processed = false;
+    hv.nb_views.clear();  // visual_neighbors_.erase
+    hv.wps.clear();
+    hv.num_wps = 0;
+    ctx->st_del.insert(f->second);
+    return L3D_OK;
+}
+
+// Line3D::UpdataImage (src/line3D.cc:433-487): new pose (View::UpdateView, src/view.cc:62-87) and the
+// world points / neighbours of the cycle
+int l3d_stream_update_image(l3d_ctx* ctx, uint32_t cam_id, const double* R, const double* t, float median_depth,
+                            const uint32_t* wps_or_nbrs, uint32_t n_list)
+{
+    if (!ctx || !R || !t) return fail(L3D_ERR_ARG, "NULL argument");
+    if (!ctx->stream_mode) return fail(L3D_ERR_STATE, "not in stream mode (l3d_stream_begin)");
+    (void)median_depth;  // only seeds View::initial_median_depth_, which the path never reads
+    auto f = ctx->cam2view.find(cam_id);
+    if (f == ctx->cam2view.end()) return L3D_OK;  // unknown ids are ignored (src/line3D.cc:439)
+    HostView& hv = ctx->views[f->second];
+    hv.cam.update(R, t);
+    memcpy(hv.v.R, R, sizeof(hv.v.R));
+    memcpy(hv.v.t, t, sizeof(hv.v.t));
+    if (!hv.current) return fail(L3D_ERR_ARG, "Can not find camID[%u] in views_reserved_", cam_id);
+    if (n_list && !wps_or_nbrs) return fail(L3D_ERR_ARG, "NULL argument");
+    if (ctx->by_worldpoints) {
+        if (n_list == 0) return fail(L3D_ERR_ARG, "view [%u] has no worldpoints!", cam_id);
+        hv.wps.assign(wps_or_nbrs, wps_or_nbrs + n_list);  // processWPlist (src/line3D.cc:230-241)
+        hv.num_wps = n_list;
+    } else {
+        hv.nbrs.assign(wps_or_nbrs, wps_or_nbrs + n_list);  // setVisualNeighbors (src/line3D.cc:244-247)
+        hv.has_fixed = true;
+    }
+    return L3D_OK;
+}
+
+template <typename T>
+static void swap_buf(DevBuf<T>& a, DevBuf<T>& b)
+{
+    std::swap(a.p, b.p);
+    std::swap(a.cap, b.cap);
+}
+
+// Line3D::matchImages (src/line3D.cc:496-640) on the persistent state
+int stream_match_images(l3d_ctx* ctx, const l3d_params* params)
+{
+    int rc = set_params(ctx, params);
+    if (rc) return rc;
+    if (ctx->prm.shard_world > 1) return fail(L3D_ERR_ARG, "the stream mode runs on one GPU (replicas only)");
+    const uint32_t V = (uint32_t)ctx->views.size();
+    std::vector<uint32_t> cur;
+    for (uint32_t v = 0; v < V; ++v)
+        if (ctx->views[v].current) cur.push_back(v);
+    if (V == 0) return fail(L3D_ERR_STATE, "no images to match! forgot to add them?");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    ctx->tm.reset();
+    cudaEvent_t ev_total = ctx->tm.begin(L3D_T_TOTAL, st);
+    const uint32_t S = ctx->S;
+
+    // ---- new segments -> device (the tables of the views already there stay) ----
+    uint32_t S_old = 0;
+    for (auto& hv : ctx->views)
+        if (hv.uploaded) S_old = hv.seg_off + hv.v.num_segs;
+    CK(ctx->d_segs.ensure(S, S_old, st));
+    CK(ctx->d_seg_view.ensure(S, S_old, st));
+    CK(ctx->d_filt_off.ensure((size_t)S + 1, S_old, st));
+    CK(ctx->d_filt_cnt.ensure((size_t)S + 1, S_old, st));
+    if (S > S_old) {
+        CK(cudaMemsetAsync(ctx->d_filt_off.p + S_old, 0, (size_t)(S - S_old) * 4, st));
+        CK(cudaMemsetAsync(ctx->d_filt_cnt.p + S_old, 0, (size_t)(S - S_old) * 4, st));
+    }
+    std::vector<uint32_t> sv;
+    for (uint32_t v = 0; v < V; ++v) {
+        HostView& hv = ctx->views[v];
+        if (hv.uploaded) continue;
+        CK(cudaMemcpyAsync(ctx->d_segs.p + hv.seg_off, hv.segs.data(), (size_t)hv.v.num_segs * sizeof(float4),
+                           cudaMemcpyHostToDevice, st));
+        sv.assign(hv.v.num_segs, v);
+        CK(cudaMemcpyAsync(ctx->d_seg_view.p + hv.seg_off, sv.data(), (size_t)hv.v.num_segs * 4, cudaMemcpyHostToDevice,
+                           st));
+        CK(cudaStreamSynchronize(st));  // sv is reused
+        hv.uploaded = true;
+    }
+    CK(ctx->d_desc.ensure(S));
+    CK(ctx->d_rays.ensure(S));
+    CK(ctx->d_midray.ensure(3 * (size_t)S));
+    CK(ctx->d_planes.ensure(S));
+    CK(ctx->d_view_xb.ensure(V));
+    CK(ctx->d_views.ensure(V));
+    CK(ctx->d_entries.ensure((size_t)S + 1));
+    CK(ctx->d_L_off.ensure((size_t)S + 2));
+    CK(ctx->d_L_cnt.ensure((size_t)S + 1));
+    CK(ctx->d_has.ensure((size_t)S + 1));
+    CK(ctx->d_entry_idx.ensure((size_t)S + 2));
+    CK(ctx->d_view_max.ensure((size_t)V + 1));
+    CK(ctx->d_st_view_total.ensure((size_t)V + 1));
+    CK(ctx->d_small.ensure(16));
+    CK(ctx->d_scan.ensure(scan_scratch_words(S + 2) + 64));
+
+    // ---- translate(), spatial regularisers of the current views (src/line3D.cc:568-590) ----
+    compute_translation(ctx);
+    apply_translation(ctx, -1.0);
+    for (uint32_t v : cur) ctx->views[v].k = ctx->views[v].cam.spatial_regularizer(ctx->prm.sigma_p);
+
+    // ---- visual neighbours (src/line3D.cc:598-620) ----
+    if (ctx->by_worldpoints) {
+        std::vector<const hg::Camera*> cams(cur.size());
+        std::vector<float> md(cur.size());
+        std::vector<std::vector<uint32_t>> wps(cur.size()), nb;
+        for (size_t i = 0; i < cur.size(); ++i) {
+            cams[i] = &ctx->views[cur[i]].cam;
+            md[i] = ctx->views[cur[i]].median_depth;
+            wps[i] = ctx->views[cur[i]].wps;
+        }
+        hg::visual_neighbors_from_worldpoints(cams, md, wps, ctx->prm.num_neighbors, nb);
+        for (size_t i = 0; i < cur.size(); ++i) {
+            std::vector<uint32_t>& out = ctx->views[cur[i]].nb_views;
+            out.clear();
+            for (uint32_t j : nb[i]) out.push_back(cur[j]);  // cur is ascending, so is the image
+        }
+    } else {
+        for (uint32_t v : cur) {
+            HostView& hv = ctx->views[v];
+            if (!hv.has_fixed) {  // no fixed list: the world-point route finds nothing and clears the set
+                hv.nb_views.clear();
+                continue;
+            }
+            if (!hv.nb_views.empty()) continue;  // filled once (src/line3D.cc:606)
+            for (uint32_t cam : hv.nbrs) {
+                auto f = ctx->cam2view.find(cam);  // views_ keeps deleted views
+                if (f != ctx->cam2view.end()) hv.nb_views.push_back(f->second);
+            }
+            std::sort(hv.nb_views.begin(), hv.nb_views.end());
+            hv.nb_views.erase(std::unique(hv.nb_views.begin(), hv.nb_views.end()), hv.nb_views.end());
+        }
+    }
+
+    // ---- new pairs in computeMatches order (src/line3D.cc:846-887): matched_ is never cleared ----
+    ctx->pairs.clear();
+    for (uint32_t s : cur)
+        for (uint32_t t : ctx->views[s].nb_views) {
+            const std::pair<uint32_t, uint32_t> key(std::min(s, t), std::max(s, t));
+            if (ctx->st_matched.count(key)) continue;
+            ctx->st_matched.insert(key);
+            HostPair hp;
+            hp.src = s;
+            hp.tgt = t;
+            hp.batch = 0;
+            hp.local = true;
+            ctx->pairs.push_back(hp);
+        }
+    const uint32_t P = (uint32_t)ctx->pairs.size();
+    ctx->pairs_h.assign(P, PairDev{});
+    uint64_t row = 0, trow = 0;
+    ctx->cnt.pair_tests = 0;
+    for (uint32_t p = 0; p < P; ++p) {
+        const HostPair& hp = ctx->pairs[p];
+        const HostView& vs = ctx->views[hp.src];
+        const HostView& vt = ctx->views[hp.tgt];
+        PairDev& d = ctx->pairs_h[p];
+        const hg::M3 F = hg::fundamental(vs.cam, vt.cam);
+        memcpy(d.F, F.m, sizeof(d.F));
+        d.src_view = hp.src;
+        d.tgt_view = hp.tgt;
+        d.src_off = vs.seg_off;
+        d.n_src = vs.v.num_segs;
+        d.tgt_off = vt.seg_off;
+        d.n_tgt = vt.v.num_segs;
+        d.row_base = (uint32_t)row;
+        d.tgt_base = (uint32_t)trow;
+        d.words = (d.n_tgt + 31) / 32;
+        d.emit_inverse = 0u;
+        d.xflag = 0u;
+        row += d.n_src;
+        trow += d.n_tgt;
+        ctx->cnt.pair_tests += (uint64_t)d.n_src * d.n_tgt;
+    }
+    if (row > 0xfffffff0ull || trow > 0xfffffff0ull) return fail(L3D_ERR_CAPACITY, "row index space exhausted");
+    ctx->total_rows = (uint32_t)row;
+    ctx->total_tgt_rows = (uint32_t)trow;
+    ctx->world = 1;
+    ctx->rank = 0;
+    ctx->slice_view.assign(2, V);
+    ctx->slice_view[0] = 0;
+    ctx->slice_g.assign(2, S);
+    ctx->slice_g[0] = 0;
+    ctx->slice_row.assign(2, ctx->total_rows);
+    ctx->slice_row[0] = 0;
+    ctx->view_needed.assign(V, 1u);
+    ctx->cnt.num_pairs = ctx->cnt.num_pairs_local = P;
+    ctx->cnt.num_views = (uint32_t)cur.size();
+    plan_batches(ctx);
+    rc = upload_views(ctx);
+    if (rc) return rc;
+
+    // ---- K0 (all views: the poses moved), K1 + K2 over the new pairs ----
+    rc = run_stage12_batches(ctx);
+    if (rc) return rc;
+    rc = refresh_pair_totals(ctx);
+    if (rc) return rc;
+    ctx->cnt.forward_matches = ctx->total_fwd;
+    const size_t F = (size_t)ctx->total_fwd;
+    CK(ctx->d_fwd_score.ensure(F + 1));
+    CK(cudaMemsetAsync(ctx->d_fwd_score.p, 0, (F + 1) * sizeof(float), st));
+
+    // ---- the walk over the current views (src/line3D.cc:848-930) ----
+    cudaEvent_t ev = ctx->tm.begin(L3D_T_SCORE, st);
+    std::vector<std::vector<uint32_t>> in_of(V), out_of(V);
+    for (uint32_t p = 0; p < P; ++p) {
+        const HostPair& hp = ctx->pairs[p];
+        out_of[hp.src].push_back(p);
+        const HostView& vt = ctx->views[hp.tgt];
+        // storeInverseMatches (src/line3D.cc:1994): the target has not been scored yet, neither in an
+        // earlier cycle nor earlier in this walk
+        if (vt.current && !vt.processed && hp.tgt > hp.src) in_of[hp.tgt].push_back(p);
+    }
+    std::vector<StreamPair> sp;
+    std::vector<uint32_t> in0(V, 0), out0(V, 0);
+    std::vector<uint64_t> wcap(V, 0), wbase(V, 0);
+    uint64_t extent = 0;
+    uint32_t max_n = 0, max_in = 0;
+    for (uint32_t v : cur) {
+        const HostView& hv = ctx->views[v];
+        uint64_t cap = hv.filt_total;
+        auto desc = [&](uint32_t p, uint32_t other) {
+            const PairDev& d = ctx->pairs_h[p];
+            StreamPair q;
+            q.rec_start = ctx->pairs[p].rec_start;
+            q.rec_cnt = (uint32_t)ctx->pairs[p].fwd_total;
+            q.row_base = d.row_base;
+            q.n_src = d.n_src;
+            q.other = other;
+            q.pad = 0;
+            cap += q.rec_cnt;
+            return q;
+        };
+        in0[v] = (uint32_t)sp.size();
+        uint64_t in_total = 0;
+        for (uint32_t p : in_of[v]) {
+            sp.push_back(desc(p, ctx->pairs[p].src));
+            in_total += ctx->pairs[p].fwd_total;
+        }
+        out0[v] = (uint32_t)sp.size();
+        for (uint32_t p : out_of[v]) sp.push_back(desc(p, ctx->pairs[p].tgt));
+        wcap[v] = cap;
+        wbase[v] = extent;
+        extent += cap;
+        max_n = std::max(max_n, hv.v.num_segs);
+        max_in = std::max<uint64_t>(max_in, in_total);
+    }
+    if (extent > 0xfffffff0ull) return fail(L3D_ERR_CAPACITY, "too many list entries (%llu)", (unsigned long long)extent);
+    ctx->st_w_extent = ctx->st_f_extent = extent;
+    swap_buf(ctx->d_filt_rec, ctx->d_st_filt_old);  // last cycle's filtered lists become the persisted input
+    CK(ctx->d_filt_rec.ensure(extent + 1));
+    CK(ctx->d_st_W_rec.ensure(extent + 1));
+    CK(ctx->d_st_W_row.ensure(extent + 1));
+    CK(ctx->d_st_W_geo.ensure((extent + 1) * sizeof(ListGeo)));
+    CK(ctx->d_st_pairs.ensure((sp.size() + 1) * sizeof(StreamPair)));
+    CK(ctx->d_st_vflag.ensure((size_t)V + 1));
+    CK(ctx->d_st_stats.ensure(stream_stats_bytes()));
+    CK(ctx->d_st_I_cnt.ensure((size_t)max_n + 2));
+    CK(ctx->d_st_I_off.ensure((size_t)max_n + 2));
+    CK(ctx->d_st_I_fill.ensure((size_t)max_n + 2));
+    CK(ctx->d_st_I_key.ensure((size_t)max_in + 1));
+    CK(ctx->d_st_W_cnt.ensure((size_t)max_n + 2));
+    CK(ctx->d_st_W_off.ensure((size_t)max_n + 2));
+    CK(ctx->d_st_F_cnt.ensure((size_t)max_n + 2));
+    CK(ctx->d_st_F_off.ensure((size_t)max_n + 2));
+    CK(ctx->d_st_best.ensure((size_t)max_n + 2));
+    std::vector<unsigned char> vflag(V + 1, 0);
+    for (uint32_t v : ctx->st_add) vflag[v] |= 1u;
+    for (uint32_t v : ctx->st_del) vflag[v] |= 2u;
+    if (!sp.empty())
+        CK(cudaMemcpyAsync(ctx->d_st_pairs.p, sp.data(), sp.size() * sizeof(StreamPair), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_st_vflag.p, vflag.data(), (size_t)V + 1, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));  // sp / vflag are locals
+    CK(cudaMemsetAsync(ctx->d_st_stats.p, 0, stream_stats_bytes(), st));
+    CK(cudaMemsetAsync(ctx->d_view_max.p, 0, ((size_t)V + 1) * 4, st));
+    CK(cudaMemsetAsync(ctx->d_st_view_total.p, 0, ((size_t)V + 1) * 4, st));
+    CK(cudaMemsetAsync(ctx->d_small.p, 0, 16 * 4, st));
+    CK(cudaMemsetAsync(ctx->d_entries.p, 0, ((size_t)S + 1) * sizeof(EntryDev), st));  // estimated_position3D_.clear()
+    CK(cudaMemsetAsync(ctx->d_L_cnt.p, 0, ((size_t)S + 1) * 4, st));
+    for (uint32_t v : ctx->st_del) {  // the lists of a deleted view are never read again
+        const HostView& hv = ctx->views[v];
+        CK(cudaMemsetAsync(ctx->d_filt_cnt.p + hv.seg_off, 0, (size_t)hv.v.num_segs * 4, st));
+        ctx->views[v].filt_total = 0;
+    }
+    for (uint32_t v : cur) {
+        HostView& hv = ctx->views[v];
+        StreamViewArgs a{};
+        a.view = v; a.n = hv.v.num_segs; a.g0 = hv.seg_off;
+        a.n_in = out0[v] - in0[v];
+        a.n_out = (uint32_t)out_of[v].size();
+        a.in_total = 0;
+        for (uint32_t p : in_of[v]) a.in_total += (uint32_t)ctx->pairs[p].fwd_total;
+        a.w_base = a.f_base = (uint32_t)wbase[v];
+        a.w_cap = a.f_cap = (uint32_t)wcap[v];
+        a.pairs_in = (const StreamPair*)ctx->d_st_pairs.p + in0[v];
+        a.pairs_out = (const StreamPair*)ctx->d_st_pairs.p + out0[v];
+        a.fwd_rec = ctx->d_fwd_rec.p; a.fwd_score = ctx->d_fwd_score.p;
+        a.fwd_off = ctx->d_fwd_off.p; a.fwd_cnt = ctx->d_fwd_cnt.p;
+        a.I_off = ctx->d_st_I_off.p; a.I_cnt = ctx->d_st_I_cnt.p; a.I_fill = ctx->d_st_I_fill.p;
+        a.I_key = ctx->d_st_I_key.p;
+        a.scan = ctx->d_scan.p; a.scan_words = ctx->d_scan.cap;
+        a.filt_off = ctx->d_filt_off.p; a.filt_cnt = ctx->d_filt_cnt.p;
+        a.filt_old = ctx->d_st_filt_old.p; a.filt_new = ctx->d_filt_rec.p;
+        a.W_cnt = ctx->d_st_W_cnt.p; a.W_off = ctx->d_st_W_off.p; a.W_rec = ctx->d_st_W_rec.p;
+        a.W_row = ctx->d_st_W_row.p; a.W_geo = (ListGeo*)ctx->d_st_W_geo.p;
+        a.L_off = ctx->d_L_off.p; a.L_cnt = ctx->d_L_cnt.p;
+        a.views = ctx->d_views.p; a.rays = ctx->d_rays.p; a.midray = ctx->d_midray.p; a.vflag = ctx->d_st_vflag.p;
+        a.view_max = ctx->d_view_max.p; a.F_cnt = ctx->d_st_F_cnt.p; a.F_off = ctx->d_st_F_off.p;
+        a.best_e = ctx->d_st_best.p; a.entries = ctx->d_entries.p; a.view_total = ctx->d_st_view_total.p;
+        a.stats = ctx->d_st_stats.p; a.two_sigA_sqr = ctx->two_sigA_sqr;
+        ctx->cnt.gpu_launches += launch_stream_view(a, st);
+        hv.processed = true;
+    }
+
+    // ---- view medians from the hypotheses as filterMatches stored them, then
+    // update_Matches_and_Estimated_position3D, then the index of estimated_position3D_ ----
+    ctx->cnt.gpu_launches += launch_k4_median(ctx->d_views.p, V, ctx->d_entries.p, ctx->d_small.p + 2, st);
+    ctx->cnt.gpu_launches += launch_stream_update_entries(S, ctx->d_seg_view.p, ctx->d_views.p, ctx->d_rays.p,
+                                                          ctx->d_planes.p, ctx->d_entries.p, st);
+    ctx->cnt.gpu_launches += launch_k4_has(ctx->d_entries.p, S, ctx->d_has.p, st);
+    ctx->cnt.gpu_launches += launch_scan_u32(ctx->d_has.p, ctx->d_entry_idx.p, S, ctx->d_scan.p, ctx->d_scan.cap, st);
+    uint32_t small[4] = {0, 0, 0, 0}, n_entries = 0;
+    std::vector<ViewDev> vd(V);
+    std::vector<uint32_t> vtot(V);
+    std::vector<unsigned char> stats(stream_stats_bytes());
+    CK(cudaMemcpyAsync(small, ctx->d_small.p, sizeof(small), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&n_entries, ctx->d_entry_idx.p + S, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(vd.data(), ctx->d_views.p, V * sizeof(ViewDev), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(vtot.data(), ctx->d_st_view_total.p, V * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(stats.data(), ctx->d_st_stats.p, stats.size(), cudaMemcpyDeviceToHost, st));
+    ctx->tm.end(ev, st);
+    ctx->tm.end(ev_total, st);
+    CK(cudaStreamSynchronize(st));
+    ctx->tm.collect();
+    const unsigned long long* s64 = (const unsigned long long*)stats.data();
+    const uint32_t* s32 = (const uint32_t*)(stats.data() + 16);
+    // untranslate() (src/line3D.cc:637) before any early return
+    apply_translation(ctx, +1.0);
+    if (s32[1]) return fail(L3D_ERR_CAPACITY, "internal: stream list arena overflow (%u)", s32[1]);
+    if (small[2]) return fail(L3D_ERR_CAPACITY, "more than 8192 hypotheses in one view (median-depth kernel)");
+    ctx->cnt.sim_evals = s64[0];
+    ctx->cnt.scored_entries = s64[1];
+    ctx->cnt.filtered_entries = s32[2];
+    ctx->cnt.num_entries = n_entries;
+    for (uint32_t v : cur) {
+        HostView& hv = ctx->views[v];
+        hv.median_depth = vd[v].median_depth;
+        hv.median_sigma = hv.k * vd[v].median_depth;  // view.h:122-135
+        hv.filt_total = vtot[v];
+    }
+    ctx->prog_all = nullptr;
+    ctx->filt_all = nullptr;
+    ctx->edges_all = nullptr;
+    ctx->stage = 2;
+    ctx->stage3_phase = 3;
+    ctx->stage4_phase = 0;
+    ctx->st_cycle++;
+    return L3D_OK;
+}

@@ -252,6 +252,144 @@ def make_scene(kind: str = "c2", n_views: Optional[int] = None, n_seg: Optional[
 
 
 # ----------------------------------------------------------------------------------------------
+# Key-frame stream (BASELINE config 3): what L3DPPing::Run feeds its Line3D object, cycle by cycle
+# (reference src/L3DPPing.cpp:98-236): delete the culled key frames, add the new ones, re-pose
+# every current key frame (bundle adjustment moved it), match, reconstruct.
+# ----------------------------------------------------------------------------------------------
+@dataclasses.dataclass
+class StreamCycle:
+    deletes: List[int]                 # camera ids removed before this cycle's matching
+    adds: List[SceneView]              # new key frames (ascending camera id)
+    updates: List[tuple]               # (cam_id, R, t, median_depth, wps_or_neighbors) of every current key frame
+
+
+@dataclasses.dataclass
+class Stream:
+    name: str
+    cycles: List[StreamCycle]
+    max_image_width: int
+    params: Dict[str, float]
+    neighbors_by_worldpoints: bool
+
+
+def _small_rotation(rng, sigma_rad):
+    w = rng.normal(0.0, sigma_rad, size=3)
+    th = float(np.linalg.norm(w))
+    if th < 1e-15:
+        return np.eye(3)
+    k = w / th
+    Kx = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+    return np.eye(3) + math.sin(th) * Kx + (1 - math.cos(th)) * (Kx @ Kx)
+
+
+def make_stream(n_keyframes: int = 300, n_seg: int = 1000, window: int = 20, nbrs: int = 10, init: int = 5,
+                by_worldpoints: bool = True, cull_every: int = 7, jitter: float = 1.0,
+                seed: Optional[int] = None, n_world: int = 600, n_points: int = 2500) -> Stream:
+    """Synthetic 640x480 key-frame stream: a C2-like room, the camera circles it (150 key frames per lap),
+    one new key frame per cycle after `init` initial ones, at most `window` current key frames (the oldest
+    is dropped), every `cull_every`-th cycle additionally culls a key frame from the middle of the window,
+    and every current key frame is re-posed each cycle by a small, shrinking perturbation (`jitter` scales
+    it; 0 = poses never move).  Neighbours come from shared world points (the mode L3DPPing uses) or from
+    explicit lists."""
+    rng = np.random.Generator(np.random.PCG64(seed if seed is not None else BASE_SEED + 2))
+    w, h, f = 640, 480, 517.0
+    lo, hi = np.array([-5.0, -5.0, 0.0]), np.array([5.0, 5.0, 4.0])
+    P1, P2 = _world_segments(rng, n_world, lo, hi, 1.0)
+    pts = rng.uniform(lo, hi, size=(n_points, 3))
+    K = np.array([[f, 0, w / 2.0], [0, f, h / 2.0], [0, 0, 1.0]], dtype=np.float64)
+    base = []
+    for i in range(n_keyframes):
+        a = 2 * math.pi * i / 150.0
+        c = np.array([3.0 * math.cos(a), 3.0 * math.sin(a), 1.6 + 0.2 * math.sin(3 * a)])
+        tgt = np.array([-1.0 * math.cos(a), -1.0 * math.sin(a), 1.8])
+        base.append((c, look_at(c, tgt)))
+
+    def visible_points(R, t):
+        X = pts @ R.T + t
+        z = X[:, 2]
+        ok = z > 0.3
+        u = f * X[:, 0] / np.where(ok, z, 1.0) + w / 2.0
+        v = f * X[:, 1] / np.where(ok, z, 1.0) + h / 2.0
+        ok &= (u >= 0) & (u < w) & (v >= 0) & (v < h)
+        ids = np.nonzero(ok)[0]
+        return ids, z[ids]
+
+    def posed(i, age):
+        """Key frame i as bundle adjustment sees it `age` cycles after it was added."""
+        c, R = base[i]
+        if jitter <= 0.0:
+            return R, -R @ c
+        r = np.random.Generator(np.random.PCG64([BASE_SEED, i, age]))
+        s = jitter / (1.0 + age)
+        Rj = _small_rotation(r, 2.0e-3 * s) @ R
+        cj = c + r.normal(0.0, 5.0e-3 * s, size=3)
+        return Rj, -Rj @ cj
+
+    cycles = []
+    current: List[int] = []
+    born = {}
+    nxt = 0
+    cyc = 0
+    while nxt < n_keyframes:
+        n_add = init if cyc == 0 else 1
+        deletes = []
+        if cyc > 0:
+            while len(current) + n_add > window:
+                deletes.append(current.pop(0))
+            if cull_every and cyc % cull_every == 0 and len(current) > 4:
+                deletes.append(current.pop(len(current) // 2))
+        adds = []
+        for _ in range(n_add):
+            if nxt >= n_keyframes:
+                break
+            i = nxt
+            nxt += 1
+            R, t = posed(i, 0)
+            segs, med = _make_view_segments(rng, P1, P2, K, R, t, w, h, n_seg, 0.5, 15.0, 40.0)
+            ids, z = visible_points(R, t)
+            med_pts = float(np.sort(z)[len(z) // 2]) if len(z) else med
+            lst = ids.tolist() if by_worldpoints else [max(0, i - 1)]
+            adds.append(SceneView(i, K.copy(), R, t, w, h, med_pts, segs, [], lst if by_worldpoints else None))
+            if not by_worldpoints:
+                adds[-1].neighbors = lst
+            current.append(i)
+            born[i] = cyc
+        updates = []
+        for i in current:
+            R, t = posed(i, cyc - born[i])
+            ids, z = visible_points(R, t)
+            med_pts = float(np.sort(z)[len(z) // 2]) if len(z) else 1.0
+            if by_worldpoints:
+                lst = ids.tolist()
+            else:  # the nbrs nearest current key frames (ids may point at frames added later or culled)
+                d = sorted((abs(j - i), j) for j in current if j != i)
+                lst = sorted(j for _, j in d[:nbrs])
+            updates.append((i, R, t, med_pts, lst))
+        cycles.append(StreamCycle(sorted(deletes), adds, updates))
+        cyc += 1
+    params = dict(DEFAULT_PARAMS)
+    params["num_neighbors"] = nbrs
+    return Stream("c3", cycles, max(w, h), params, by_worldpoints)
+
+
+def drive_stream(stream: Stream, begin_cycle, delete, add, update, match, reconstruct, on_cycle=None,
+                 max_cycles: Optional[int] = None):
+    """Replay a stream through the six calls L3DPPing::Run makes (adapters of the object under test)."""
+    for ci, cy in enumerate(stream.cycles[:max_cycles]):
+        begin_cycle()
+        for cam in cy.deletes:
+            delete(cam)
+        for v in cy.adds:
+            add(v, v.worldpoints if stream.neighbors_by_worldpoints else v.neighbors)
+        for cam, R, t, md, lst in cy.updates:
+            update(cam, R, t, md, lst)
+        match(stream.params)
+        reconstruct()
+        if on_cycle is not None:
+            on_cycle(ci, cy)
+
+
+# ----------------------------------------------------------------------------------------------
 # NVM (the reference's own dump format: src/System.cc:459-535, header "NVM_BTREE_Test_v1")
 # ----------------------------------------------------------------------------------------------
 def read_nvm(path: str):

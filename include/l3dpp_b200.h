@@ -181,6 +181,25 @@ int l3d_neighbors_from_worldpoints(const l3d_view* views, uint32_t n_views, cons
 /* visual neighbours of a view as used by the last l3d_match_images (camera ids, ascending) */
 int l3d_get_neighbors(l3d_ctx* ctx, uint32_t cam_id, uint32_t* out, uint32_t cap, uint32_t* count);
 
+/* ---- incremental (key-frame stream) mode: the calls L3DPPing::Run (src/L3DPPing.cpp:98-236) makes
+ * on its Line3D object between two reconstructions.  The context keeps what Line3D keeps from one
+ * matchImages to the next: matched_ (a view pair is matched once), processed_, the filtered match
+ * lists with their scores, and Add_camID_ / Delete_camID_ for the score deltas of
+ * Line3D::scoringCPU (src/line3D.cc:1439-1512).  After l3d_stream_begin, l3d_match_images,
+ * l3d_affinity, l3d_cluster and the getters act on the stream state (one GPU).
+ *   l3d_stream_begin        new Line3D object; neighbors_by_worldpoints as in its constructor
+ *   l3d_stream_begin_cycle  the resets of src/L3DPPing.cpp:98-103 (world-point maps, Add/Delete sets)
+ *   l3d_stream_add_image    Line3D::addImage   (src/line3D.cc:117-227); camera ids ascending
+ *   l3d_stream_delete_image Line3D::deleteImage (src/line3D.cc:396-430)
+ *   l3d_stream_update_image Line3D::UpdataImage (src/line3D.cc:433-487): pose + world points / neighbours */
+int l3d_stream_begin(l3d_ctx* ctx, int neighbors_by_worldpoints);
+int l3d_stream_begin_cycle(l3d_ctx* ctx);
+int l3d_stream_add_image(l3d_ctx* ctx, const l3d_view* view, const float* segs_xyxy,
+                         const uint32_t* wps_or_nbrs, uint32_t n_list);
+int l3d_stream_delete_image(l3d_ctx* ctx, uint32_t cam_id);
+int l3d_stream_update_image(l3d_ctx* ctx, uint32_t cam_id, const double* R, const double* t,
+                            float median_depth, const uint32_t* wps_or_nbrs, uint32_t n_list);
+
 /* replaces Line3D::matchImages (src/line3D.cc:496-640): translate(), spatial regularisers,
  * computeMatches() (matching, orientation filter, scoring, inverse matches, filtering) and the
  * estimated_position3D_ table, all on the device.  l3d_match_stage12 runs matching only (this

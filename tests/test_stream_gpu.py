@@ -1,0 +1,59 @@
+"""GPU: the incremental (key-frame stream) mode against the oracle, cycle by cycle -- SURVEY.md
+section 8f rank 1 / BASELINE config 3.  The oracle restates what Line3D keeps between two
+matchImages calls (matched_, processed_, the filtered lists and their scores, the Add / Delete
+score deltas of Line3D::scoringCPU src/line3D.cc:1439-1512, the per-cycle orientation re-test of
+checkMatchOrientation src/line3D.cc:962-1014 and update_Matches_and_Estimated_position3D
+src/line3D.cc:1857-1908); the CUDA path must reproduce every cycle bit for bit."""
+import numpy as np
+import pytest
+
+import stream_utils
+
+pytestmark = pytest.mark.gpu
+
+
+def test_stream_world_point_neighbours(api, oracle, scene_mod):
+    """The mode L3DPPing uses: neighbours from shared world points, re-chosen every cycle; sliding
+    window with culling from the middle; poses re-estimated every cycle."""
+    st = scene_mod.make_stream(n_keyframes=22, n_seg=400, window=8, nbrs=6, jitter=0.3)
+    tot = stream_utils.run_lockstep(api, oracle, st)
+    assert tot["cycles"] == 18 and tot["deleted"] >= 10 and tot["entries"] > 500 and tot["edges"] > 500
+
+
+def test_stream_fixed_neighbours(api, oracle, scene_mod):
+    """Explicit neighbour lists (setVisualNeighbors): a view's set is filled once and may name key
+    frames that were culled since."""
+    st = scene_mod.make_stream(n_keyframes=18, n_seg=400, window=7, nbrs=4, jitter=0.3, by_worldpoints=False,
+                               cull_every=3)
+    tot = stream_utils.run_lockstep(api, oracle, st)
+    assert tot["cycles"] == 14 and tot["deleted"] >= 8 and tot["entries"] > 300
+
+
+def test_stream_static_poses(api, oracle, scene_mod):
+    """Without pose changes the re-triangulation is the identity and no orientation test flips."""
+    st = scene_mod.make_stream(n_keyframes=12, n_seg=500, window=6, nbrs=5, jitter=0.0)
+    tot = stream_utils.run_lockstep(api, oracle, st)
+    assert tot["entries"] > 300
+
+
+def test_stream_c3_shape(api, oracle, scene_mod):
+    """BASELINE config 3's shape, shortened: 640x480, 1000 segments per key frame, window of 20,
+    10 neighbours, 45 key frames (41 cycles)."""
+    st = scene_mod.make_stream(n_keyframes=45, n_seg=1000, window=20, nbrs=10, jitter=0.3)
+    tot = stream_utils.run_lockstep(api, oracle, st, check_scored=False)
+    assert tot["cycles"] == 41 and tot["entries"] > 10000
+
+
+def test_stream_errors_mirror_the_reference(api, scene_mod):
+    st = scene_mod.make_stream(n_keyframes=6, n_seg=100, window=6, jitter=0.0)
+    l3, calls = stream_utils.cuda_driver(api, st)
+    v = st.cycles[0].adds[0]
+    calls["add"](v, v.worldpoints)
+    with pytest.raises(api.L3DError, match="already in use"):
+        calls["add"](v, v.worldpoints)
+    assert l3.deleteImage(99) is False           # "camera ID [99] non_existent!"
+    assert l3.deleteImage(v.cam_id) is True
+    with pytest.raises(api.L3DError, match="views_reserved_"):
+        l3.UpdataImage(v.cam_id, v.R, v.t, v.median_depth, v.worldpoints)
+    with pytest.raises(api.L3DError, match="has no worldpoints"):
+        calls["add"](st.cycles[0].adds[1], [])
