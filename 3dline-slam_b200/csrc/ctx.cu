@@ -270,7 +270,8 @@ int refresh_pair_totals(l3d_ctx* ctx)
     const uint32_t P = (uint32_t)ctx->pairs.size();
     cudaStream_t st = ctx->stream;
     if (!P) return L3D_OK;
-    CK(ctx->d_scan_tmp.ensure((size_t)std::max(P, ctx->total_tgt_rows) + 2));
+    CK(ctx->stream_mode ? ensure_roomy(ctx->d_scan_tmp, (size_t)std::max(P, ctx->total_tgt_rows) + 2, (size_t)1 << 18)
+                         : ctx->d_scan_tmp.ensure((size_t)std::max(P, ctx->total_tgt_rows) + 2));
     pair_totals_kernel<<<(P + 255) / 256, 256, 0, st>>>(ctx->d_pairs.p, P, ctx->d_fwd_off.p, ctx->d_fwd_cnt.p,
                                                         ctx->d_scan_tmp.p);
     ctx->cnt.gpu_launches++;
@@ -507,6 +508,11 @@ int set_params(l3d_ctx* ctx, const l3d_params* params)
 int run_stage12_batches(l3d_ctx* ctx)
 {
     cudaStream_t st = ctx->stream;
+    // stream mode: the scratch sizes change a little from cycle to cycle; reallocate rarely (ensure_roomy)
+    const bool roomy = ctx->stream_mode;
+    auto grow = [roomy](auto& buf, size_t n, size_t keep = 0, cudaStream_t s2 = 0) {
+        return roomy ? ensure_roomy(buf, n, (size_t)1 << 20, keep, s2) : buf.ensure(n, keep, s2);
+    };
     const uint32_t V = (uint32_t)ctx->views.size(), P = (uint32_t)ctx->pairs.size(), S = ctx->S;
 
     // per-segment tables
@@ -517,8 +523,8 @@ int run_stage12_batches(l3d_ctx* ctx)
                                             ctx->d_view_xb.p, st);
     ctx->tm.end(ev, st);
 
-    CK(ctx->d_fwd_off.ensure((size_t)ctx->total_rows + 1));
-    CK(ctx->d_fwd_cnt.ensure((size_t)ctx->total_rows + 1));
+    CK(grow(ctx->d_fwd_off, (size_t)ctx->total_rows + 1));
+    CK(grow(ctx->d_fwd_cnt, (size_t)ctx->total_rows + 1));
     CK(cudaMemsetAsync(ctx->d_fwd_cnt.p, 0, ((size_t)ctx->total_rows + 1) * sizeof(uint32_t), st));
     CK(cudaMemsetAsync(ctx->d_fwd_off.p, 0, ((size_t)ctx->total_rows + 1) * sizeof(uint32_t), st));
     ctx->total_fwd = 0;
@@ -531,16 +537,16 @@ int run_stage12_batches(l3d_ctx* ctx)
             max_rows = std::max(max_rows, b.n_rows);
             max_words = std::max(max_words, b.mask_words);
         }
-        CK(ctx->d_mask.ensure(max_words));
-        CK(ctx->d_cand_cnt.ensure((size_t)max_rows + 1));
-        CK(ctx->d_cand_off.ensure((size_t)max_rows + 1));
-        CK(ctx->d_fin_cnt.ensure((size_t)max_rows + 1));
-        CK(ctx->d_fin_off.ensure((size_t)max_rows + 1));
-        CK(ctx->d_scan.ensure(scan_scratch_words(std::max(max_rows, ctx->total_tgt_rows) + 1) + 64));
-        CK(ctx->d_ctas.ensure(ctx->ctas_h.size()));
+        CK(grow(ctx->d_mask, max_words));
+        CK(grow(ctx->d_cand_cnt, (size_t)max_rows + 1));
+        CK(grow(ctx->d_cand_off, (size_t)max_rows + 1));
+        CK(grow(ctx->d_fin_cnt, (size_t)max_rows + 1));
+        CK(grow(ctx->d_fin_off, (size_t)max_rows + 1));
+        CK(grow(ctx->d_scan, scan_scratch_words(std::max(max_rows, ctx->total_tgt_rows) + 1) + 64));
+        CK(grow(ctx->d_ctas, ctx->ctas_h.size()));
         CK(cudaMemcpyAsync(ctx->d_ctas.p, ctx->ctas_h.data(), ctx->ctas_h.size() * sizeof(K1Cta),
                            cudaMemcpyHostToDevice, st));
-        CK(ctx->d_pairs.ensure(P));
+        CK(grow(ctx->d_pairs, P));
         CK(cudaMemcpyAsync(ctx->d_pairs.p, ctx->pairs_h.data(), P * sizeof(PairDev), cudaMemcpyHostToDevice, st));
     }
 
@@ -563,9 +569,9 @@ int run_stage12_batches(l3d_ctx* ctx)
         CK(cudaStreamSynchronize(st));
         ctx->cnt.candidates += n_cand;
         // K2
-        CK(ctx->d_heap.ensure((size_t)n_cand + 1));
-        CK(ctx->d_cand_rec.ensure((size_t)n_cand + 1));
-        CK(ctx->d_fin_rec.ensure((size_t)n_cand + 1));
+        CK(grow(ctx->d_heap, (size_t)n_cand + 1));
+        CK(grow(ctx->d_cand_rec, (size_t)n_cand + 1));
+        CK(grow(ctx->d_fin_rec, (size_t)n_cand + 1));
         cudaEvent_t e2 = ctx->tm.begin(L3D_T_EXACT, st);
         ctx->cnt.gpu_launches +=
             launch_k2_exact(ctx->d_pairs.p, ctx->d_ctas.p + b.cta0, b.n_ctas, b.n_rows, n_cand, ctx->d_segs.p,
@@ -579,7 +585,7 @@ int run_stage12_batches(l3d_ctx* ctx)
         CK(cudaMemcpyAsync(&n_fin, ctx->d_fin_off.p + b.n_rows, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         if ((uint64_t)rec_base + n_fin > 0xfffffff0ull) return fail(L3D_ERR_CAPACITY, "too many forward matches");
-        CK(ctx->d_fwd_rec.ensure((size_t)rec_base + n_fin, rec_base, st));
+        CK(grow(ctx->d_fwd_rec, (size_t)rec_base + n_fin, rec_base, st));
         ctx->cnt.gpu_launches +=
             launch_k2_compact(ctx->d_cand_off.p, ctx->d_fin_cnt.p, ctx->d_fin_off.p, rec_base, ctx->d_fin_rec.p,
                               ctx->d_fwd_rec.p, ctx->d_fwd_off.p + b.row0, b.n_rows, st);
@@ -988,6 +994,13 @@ int l3d_affinity_edges(l3d_ctx* ctx)
     // stream mode: the filtered lists of a cycle live at per-view bases inside an arena of st_f_extent records
     const size_t nf = ctx->stream_mode ? (size_t)ctx->st_f_extent : (size_t)ctx->cnt.filtered_entries;
     const uint32_t g_lo = ctx->slice_g[ctx->rank], g_hi = ctx->slice_g[ctx->rank + 1];
+    if (ctx->stream_mode) {  // growing tables: reallocate rarely (ctx.h: ensure_roomy)
+        CK(ensure_roomy(ctx->d_filt_sim, nf + 1, (size_t)1 << 21));
+        CK(ensure_roomy(ctx->d_E_cnt, (size_t)S + 1, (size_t)1 << 18));
+        CK(ensure_roomy(ctx->d_E_off, (size_t)S + 2, (size_t)1 << 18));
+        CK(ensure_roomy(ctx->d_edges, (nf + 1) * k4_edge_bytes(), ((size_t)1 << 21) * k4_edge_bytes()));
+        CK(ensure_roomy(ctx->d_first_touch, (size_t)S + 1, (size_t)1 << 18));
+    }
     CK(ctx->d_filt_sim.ensure(nf + 1));
     CK(ctx->d_E_cnt.ensure((size_t)S + 1));
     CK(ctx->d_E_off.ensure((size_t)S + 2));
@@ -1023,20 +1036,22 @@ int l3d_affinity_ids(l3d_ctx* ctx)
         return fail(L3D_ERR_STATE, "the edges have not been exchanged");
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
+    const bool roomy = ctx->stream_mode;  // see run_stage12_batches
+    auto grow = [roomy](auto& buf, size_t n) { return roomy ? ensure_roomy(buf, n, (size_t)1 << 20) : buf.ensure(n); };
     const uint32_t S = ctx->S;
     const uint32_t n_edges = ctx->world > 1 ? ctx->n_edges_all : ctx->n_edges_local;
     const void* edges = ctx->world > 1 ? ctx->edges_all : (const void*)ctx->d_edges.p;
     cudaEvent_t ev = ctx->tm.begin(L3D_T_AFFINITY, st);
     uint32_t n_local = 0;
     if (n_edges) {
-        CK(ctx->d_first_touch.ensure((size_t)S + 1));
+        CK(grow(ctx->d_first_touch, (size_t)S + 1));
         CK(cudaMemsetAsync(ctx->d_first_touch.p, 0xff, ((size_t)S + 1) * 4, st));
-        CK(ctx->d_flags.ensure(2 * (size_t)n_edges + 1));
-        CK(ctx->d_flag_scan.ensure(2 * (size_t)n_edges + 2));
-        CK(ctx->d_A_ij.ensure(2 * (size_t)n_edges));
-        CK(ctx->d_A_w.ensure(2 * (size_t)n_edges));
+        CK(grow(ctx->d_flags, 2 * (size_t)n_edges + 1));
+        CK(grow(ctx->d_flag_scan, 2 * (size_t)n_edges + 2));
+        CK(grow(ctx->d_A_ij, 2 * (size_t)n_edges));
+        CK(grow(ctx->d_A_w, 2 * (size_t)n_edges));
         CK(ctx->d_l2g.ensure(2 * (size_t)n_edges));
-        CK(ctx->d_scan.ensure(scan_scratch_words(2 * n_edges + 2) + 64));
+        CK(grow(ctx->d_scan, scan_scratch_words(2 * n_edges + 2) + 64));
         ctx->cnt.gpu_launches +=
             launch_k4_ids(edges, n_edges, ctx->d_first_touch.p, ctx->d_flags.p, ctx->d_flag_scan.p, ctx->d_scan.p,
                           ctx->d_scan.cap, ctx->d_A_ij.p, ctx->d_A_w.p, ctx->d_l2g.p, st);

@@ -107,6 +107,15 @@ struct DevBuf {
     }
 };
 
+// stream mode: the tables grow a little every cycle; reallocate rarely (twice the need, never below
+// `floor` elements) so that a steady-state cycle does not stall in cudaMalloc / cudaFree
+template <typename T>
+static inline cudaError_t ensure_roomy(DevBuf<T>& b, size_t n, size_t floor, size_t keep = 0, cudaStream_t st = 0)
+{
+    if (n <= b.cap) return cudaSuccess;
+    return b.ensure(std::max(2 * n, floor), keep, st);
+}
+
 struct HostView {
     l3d_view v;
     std::vector<float> segs;
@@ -294,7 +303,7 @@ struct l3d_ctx {
     DevBuf<ListRec> d_st_filt_old, d_st_W_rec;
     DevBuf<unsigned char> d_st_W_geo, d_st_pairs, d_st_vflag, d_st_stats;
     DevBuf<uint32_t> d_st_W_row, d_st_I_cnt, d_st_I_off, d_st_I_fill, d_st_I_key, d_st_W_cnt, d_st_W_off, d_st_F_cnt,
-        d_st_F_off, d_st_best, d_st_view_total;
+        d_st_F_off, d_st_best, d_st_view_total, d_st_row_g, d_st_vout;
 
     l3d_counts cnt{};
     StageTimer tm;

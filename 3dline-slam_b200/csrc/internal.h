@@ -132,10 +132,13 @@ struct StreamPair {
     uint32_t pad;
 };
 
-// one view's step of the key-frame stream mode (k3_stream.cu)
-struct StreamViewArgs {
-    uint32_t view, n, g0, n_in, n_out, in_total, w_base, f_base, w_cap, f_cap;
-    const void* pairs_in; const void* pairs_out;  // StreamPair[] on the device
+// one step of the key-frame stream walk (k3_stream.cu): the rows of all previously scored views, or
+// the rows of one new view
+struct StreamStepArgs {
+    uint32_t n, n_in, in0, in_total, w_base, f_base, w_cap, f_cap;
+    const uint32_t* row_g; const uint32_t* seg_view;
+    const void* pairs;  // StreamPair[] on the device (all descriptors of the cycle)
+    const uint32_t* vout0; const uint32_t* vnout;
     const FwdRec* fwd_rec; float* fwd_score; const uint32_t* fwd_off; const uint32_t* fwd_cnt;
     uint32_t* I_off; uint32_t* I_cnt; uint32_t* I_fill; uint32_t* I_key;
     uint32_t* scan; size_t scan_words;
@@ -147,7 +150,7 @@ struct StreamViewArgs {
     EntryDev* entries; uint32_t* view_total; void* stats;
     float two_sigA_sqr;
 };
-int launch_stream_view(const StreamViewArgs& a, cudaStream_t st);
+int launch_stream_step(const StreamStepArgs& a, cudaStream_t st);
 int launch_stream_update_entries(uint32_t S, const uint32_t* seg_view, const ViewDev* views, const SegRays* rays,
                                  const SegPlane* planes, EntryDev* entries, cudaStream_t st);
 size_t stream_stats_bytes();

@@ -32,12 +32,21 @@ static constexpr uint32_t LF_DROP = 8u;  // ListRec.flags: failed this cycle's o
 
 __device__ __forceinline__ D3 ld3s(const double* p) { return D3{p[0], p[1], p[2]}; }
 
+// One step of the walk = the rows of a set of views that do not feed each other: all views scored in
+// an earlier cycle go in ONE step (they receive no inverse matches any more, so they are independent),
+// then every new view is a step of its own, in ascending camera id (it receives the inverse matches of
+// the views before it).
 struct StreamStep {
-    uint32_t view, n, g0;        // view index, rows, first global row
-    uint32_t n_in, n_out;        // pair descriptors: in[0..n_in), out[0..n_out)
-    uint32_t in_total;           // forward records over the incoming pairs
-    uint32_t w_base, f_base;     // bases of this view's regions in the working / filtered arenas
+    uint32_t n;                  // rows of the step
+    uint32_t n_in, in_total;     // incoming pair descriptors / their forward records (single-view steps only)
+    uint32_t w_base, f_base;     // bases of the step's regions in the working / filtered arenas
     uint32_t w_cap, f_cap;
+    const uint32_t* row_g;       // global segment index of every step row (views ascending, segments ascending)
+    const uint32_t* seg_view;
+    const ViewDev* views;
+    const StreamPair* pairs;     // all descriptors of the cycle
+    const uint32_t* vout0;       // per view: first outgoing descriptor, and their number
+    const uint32_t* vnout;
 };
 
 // ---- inverse matches received by the view ----
@@ -65,7 +74,7 @@ __global__ void __launch_bounds__(256) st_inv_kernel(StreamStep s, const StreamP
 // the reference stores the copy taken BEFORE it sets match_orientation_, a forward match is tested
 // again with the current pose of its source view each time (inverse matches carry the flag and are
 // not); the ones that fail now are dropped before scoring.
-__global__ void __launch_bounds__(128) st_row_count_kernel(StreamStep s, const StreamPair* __restrict__ out,
+__global__ void __launch_bounds__(128) st_row_count_kernel(StreamStep s,
                                                            const uint32_t* __restrict__ filt_off,
                                                            const uint32_t* __restrict__ filt_cnt,
                                                            ListRec* __restrict__ filt_old,
@@ -78,11 +87,15 @@ __global__ void __launch_bounds__(128) st_row_count_kernel(StreamStep s, const S
 {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= s.n) return;
-    const uint32_t g = s.g0 + r;
+    const uint32_t g = s.row_g[r];
+    const uint32_t v = s.seg_view[g];
+    const uint32_t seg = g - views[v].seg_off;
+    const StreamPair* out = s.pairs + s.vout0[v];
+    const uint32_t n_out = s.vnout[v];
     const uint32_t pn = filt_cnt[g], pb = filt_off[g];
-    uint32_t m = I_cnt[r];
+    uint32_t m = s.n_in ? I_cnt[r] : 0u;
     if (pn) {
-        const D3 C = ld3s(views[s.view].C);
+        const D3 C = ld3s(views[v].C);
         const SegRays sr = rays[g];
         const D3 r1 = ld3s(sr.r1), r2 = ld3s(sr.r2), rmid = ld3s(midray + 3 * (size_t)g);
         for (uint32_t e = 0; e < pn; ++e) {
@@ -101,13 +114,12 @@ __global__ void __launch_bounds__(128) st_row_count_kernel(StreamStep s, const S
             else L.flags |= LF_DROP;
         }
     }
-    for (uint32_t q = 0; q < s.n_out; ++q) m += fwd_cnt[out[q].row_base + r];
+    for (uint32_t q = 0; q < n_out; ++q) m += fwd_cnt[out[q].row_base + seg];
     W_cnt[r] = m;
 }
 
 // one thread per row: the list in reference order
 __global__ void __launch_bounds__(128) st_fill_kernel(StreamStep s, const StreamPair* __restrict__ in,
-                                                      const StreamPair* __restrict__ out,
                                                       const uint32_t* __restrict__ filt_off,
                                                       const uint32_t* __restrict__ filt_cnt,
                                                       const ListRec* __restrict__ filt_old,
@@ -122,7 +134,11 @@ __global__ void __launch_bounds__(128) st_fill_kernel(StreamStep s, const Stream
 {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= s.n) return;
-    const uint32_t g = s.g0 + r;
+    const uint32_t g = s.row_g[r];
+    const uint32_t v = s.seg_view[g];
+    const uint32_t seg = g - s.views[v].seg_off;
+    const StreamPair* out = s.pairs + s.vout0[v];
+    const uint32_t n_out = s.vnout[v];
     const uint32_t lo = W_off[r], m = W_off[r + 1] - lo;
     L_off[g] = s.w_base + lo;
     L_cnt[g] = m;
@@ -145,7 +161,7 @@ __global__ void __launch_bounds__(128) st_fill_kernel(StreamStep s, const Stream
         drow[w++] = r;
     }
     // inverse matches: ascending forward-record index = push order
-    const uint32_t in_n = I_cnt[r], ib = I_off[r];
+    const uint32_t in_n = s.n_in ? I_cnt[r] : 0u, ib = s.n_in ? I_off[r] : 0u;
     for (uint32_t a = 1; a < in_n; ++a) {
         const uint32_t key = I_key[ib + a];
         uint32_t b = a;
@@ -178,8 +194,8 @@ __global__ void __launch_bounds__(128) st_fill_kernel(StreamStep s, const Stream
         drow[w++] = r;
     }
     // new forward matches, targets ascending, kNN pop order
-    for (uint32_t q = 0; q < s.n_out; ++q) {
-        const uint32_t row = out[q].row_base + r;
+    for (uint32_t q = 0; q < n_out; ++q) {
+        const uint32_t row = out[q].row_base + seg;
         const uint32_t fb = fwd_off[row], fn = fwd_cnt[row];
         for (uint32_t e = 0; e < fn; ++e) {
             const FwdRec R = fwd_rec[fb + e];
@@ -209,9 +225,10 @@ __global__ void __launch_bounds__(128) st_geo_kernel(StreamStep s, const uint32_
     if (e >= total) return;
     const ListRec L = W_rec[s.w_base + e];
     const uint32_t r = W_row[s.w_base + e];
-    const ViewDev& va = views[s.view];
+    const uint32_t g = s.row_g[r];
+    const ViewDev& va = views[s.seg_view[g]];
     const ViewDev& vo = views[L.tgt_view];
-    const SegRays sr = rays[s.g0 + r];
+    const SegRays sr = rays[g];
     const D3 C = ld3s(va.C), Co = ld3s(vo.C);
     // View::unprojectSegment (src/view.cc:385-400) + Segment3D ctor (include/segment3D.h:58-77)
     D3 P1 = add3(C, scale3(ld3s(sr.r1), (double)L.d_p1));
@@ -360,7 +377,8 @@ __global__ void __launch_bounds__(256) st_score_kernel(StreamStep s, const uint3
 // write-back (read by the later views' st_inv_kernel), maximum score of the view
 __global__ void __launch_bounds__(256) st_post_kernel(StreamStep s, const uint32_t* __restrict__ W_off,
                                                       const unsigned char* __restrict__ vflag,
-                                                      ListRec* __restrict__ W_rec, float* __restrict__ fwd_score,
+                                                      ListRec* __restrict__ W_rec, const uint32_t* __restrict__ W_row,
+                                                      float* __restrict__ fwd_score,
                                                       uint32_t* __restrict__ view_max, StreamStats* __restrict__ stats)
 {
     const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -372,7 +390,7 @@ __global__ void __launch_bounds__(256) st_post_kernel(StreamStep s, const uint32
         return;
     }
     if (L.src_idx != NOIDX) fwd_score[L.src_idx] = L.score;
-    atomicMax(&view_max[s.view], float_ordered(L.score));
+    atomicMax(&view_max[s.seg_view[s.row_g[W_row[s.w_base + e]]]], float_ordered(L.score));
     atomicAdd(&stats->scored, 1ull);
 }
 
@@ -386,7 +404,7 @@ __global__ void __launch_bounds__(128) st_filter_count_kernel(StreamStep s, cons
     const uint32_t lo = W_off[r];
     uint32_t m = W_off[r + 1] - lo;
     if ((uint64_t)lo + m > s.w_cap) m = 0;
-    const float max_score = fmaxf(0.0f, ordered_to_float(view_max[s.view]));
+    const float max_score = fmaxf(0.0f, ordered_to_float(view_max[s.seg_view[s.row_g[r]]]));
     const float lim = fm(0.10f, max_score);
     const ListRec* rec = W_rec + s.w_base + lo;
     uint32_t kept = 0, bi = NOIDX;
@@ -422,11 +440,12 @@ __global__ void __launch_bounds__(128) st_filter_write_kernel(StreamStep s, cons
 {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= s.n) return;
-    const uint32_t g = s.g0 + r;
+    const uint32_t g = s.row_g[r];
+    const uint32_t v = s.seg_view[g];
     const uint32_t lo = W_off[r];
     uint32_t m = W_off[r + 1] - lo;
     if ((uint64_t)lo + m > s.w_cap) m = 0;
-    const float max_score = fmaxf(0.0f, ordered_to_float(view_max[s.view]));
+    const float max_score = fmaxf(0.0f, ordered_to_float(view_max[v]));
     const float lim = fm(0.10f, max_score);
     const ListRec* rec = W_rec + s.w_base + lo;
     const uint32_t fo = F_off[r], kept = F_off[r + 1] - fo;
@@ -442,7 +461,7 @@ __global__ void __launch_bounds__(128) st_filter_write_kernel(StreamStep s, cons
     filt_off[g] = s.f_base + fo;
     filt_cnt[g] = fits ? kept : 0u;
     if (kept) {
-        atomicAdd(&view_total[s.view], kept);
+        atomicAdd(&view_total[v], kept);
         atomicAdd(&stats->filtered, kept);
     }
     EntryDev& E = entries[g];
@@ -454,7 +473,7 @@ __global__ void __launch_bounds__(128) st_filter_write_kernel(StreamStep s, cons
     // unprojectMatch(best,true) (src/line3D.cc:1826-1838)
     const ListRec B = rec[bi];
     const SegRays sr = rays[g];
-    const D3 Ca = ld3s(views[s.view].C);
+    const D3 Ca = ld3s(views[v].C);
     D3 P1 = add3(Ca, scale3(ld3s(sr.r1), (double)B.d_p1));
     D3 P2 = add3(Ca, scale3(ld3s(sr.r2), (double)B.d_p2));
     float len = (float)norm3(sub3(P1, P2));
@@ -534,36 +553,38 @@ __global__ void __launch_bounds__(128) st_update_entries_kernel(uint32_t S, cons
 // ------------------------------------------------------------------------------------------
 size_t stream_stats_bytes() { return sizeof(StreamStats); }
 
-int launch_stream_view(const StreamViewArgs& a, cudaStream_t st)
+int launch_stream_step(const StreamStepArgs& a, cudaStream_t st)
 {
     StreamStep s;
-    s.view = a.view; s.n = a.n; s.g0 = a.g0; s.n_in = a.n_in; s.n_out = a.n_out; s.in_total = a.in_total;
+    s.n = a.n; s.n_in = a.n_in; s.in_total = a.in_total;
     s.w_base = a.w_base; s.f_base = a.f_base; s.w_cap = a.w_cap; s.f_cap = a.f_cap;
-    const StreamPair* in = (const StreamPair*)a.pairs_in;
-    const StreamPair* out = (const StreamPair*)a.pairs_out;
+    s.row_g = a.row_g; s.seg_view = a.seg_view; s.views = a.views;
+    s.pairs = (const StreamPair*)a.pairs; s.vout0 = a.vout0; s.vnout = a.vnout;
+    const StreamPair* in = (const StreamPair*)a.pairs + a.in0;
     StreamStats* stats = (StreamStats*)a.stats;
     const uint32_t n = a.n;
     if (!n) return 0;
     int launches = 0;
-    // inverse matches received
-    cudaMemsetAsync(a.I_cnt, 0, ((size_t)n + 1) * 4, st);
-    if (a.in_total) {
-        st_inv_kernel<<<(a.in_total + 255) / 256, 256, 0, st>>>(s, in, a.fwd_rec, a.fwd_score, a.I_off, a.I_cnt, a.I_key,
-                                                                 0);
-        ++launches;
+    if (a.n_in) {  // inverse matches received (a new view)
+        cudaMemsetAsync(a.I_cnt, 0, ((size_t)n + 1) * 4, st);
+        if (a.in_total) {
+            st_inv_kernel<<<(a.in_total + 255) / 256, 256, 0, st>>>(s, in, a.fwd_rec, a.fwd_score, a.I_off, a.I_cnt,
+                                                                     a.I_key, 0);
+            ++launches;
+        }
+        launches += launch_scan_u32(a.I_cnt, a.I_off, n, a.scan, a.scan_words, st);
+        if (a.in_total) {
+            cudaMemsetAsync(a.I_fill, 0, ((size_t)n + 1) * 4, st);
+            st_inv_kernel<<<(a.in_total + 255) / 256, 256, 0, st>>>(s, in, a.fwd_rec, a.fwd_score, a.I_off, a.I_fill,
+                                                                     a.I_key, 1);
+            ++launches;
+        }
     }
-    launches += launch_scan_u32(a.I_cnt, a.I_off, n, a.scan, a.scan_words, st);
-    if (a.in_total) {
-        cudaMemsetAsync(a.I_fill, 0, ((size_t)n + 1) * 4, st);
-        st_inv_kernel<<<(a.in_total + 255) / 256, 256, 0, st>>>(s, in, a.fwd_rec, a.fwd_score, a.I_off, a.I_fill,
-                                                                 a.I_key, 1);
-        ++launches;
-    }
-    st_row_count_kernel<<<(n + 127) / 128, 128, 0, st>>>(s, out, a.filt_off, a.filt_cnt, a.filt_old, a.views, a.rays,
+    st_row_count_kernel<<<(n + 127) / 128, 128, 0, st>>>(s, a.filt_off, a.filt_cnt, a.filt_old, a.views, a.rays,
                                                           a.midray, a.I_cnt, a.fwd_cnt, a.W_cnt);
     ++launches;
     launches += launch_scan_u32(a.W_cnt, a.W_off, n, a.scan, a.scan_words, st);
-    st_fill_kernel<<<(n + 127) / 128, 128, 0, st>>>(s, in, out, a.filt_off, a.filt_cnt, a.filt_old, a.I_off, a.I_cnt,
+    st_fill_kernel<<<(n + 127) / 128, 128, 0, st>>>(s, in, a.filt_off, a.filt_cnt, a.filt_old, a.I_off, a.I_cnt,
                                                      a.I_key, a.fwd_off, a.fwd_cnt, a.fwd_rec, a.W_off, a.W_rec,
                                                      a.W_row, a.L_off, a.L_cnt, &stats->err);
     ++launches;
@@ -571,8 +592,8 @@ int launch_stream_view(const StreamViewArgs& a, cudaStream_t st)
         st_geo_kernel<<<(a.w_cap + 127) / 128, 128, 0, st>>>(s, a.W_off, a.views, a.rays, a.W_rec, a.W_row, a.W_geo);
         st_score_kernel<<<(n + 7) / 8, 256, 0, st>>>(s, a.W_off, a.views, a.vflag, a.W_rec, a.W_geo, a.two_sigA_sqr,
                                                       score_dotcut(a.two_sigA_sqr, 0.5f), stats);
-        st_post_kernel<<<(a.w_cap + 255) / 256, 256, 0, st>>>(s, a.W_off, a.vflag, a.W_rec, a.fwd_score, a.view_max,
-                                                               stats);
+        st_post_kernel<<<(a.w_cap + 255) / 256, 256, 0, st>>>(s, a.W_off, a.vflag, a.W_rec, a.W_row, a.fwd_score,
+                                                               a.view_max, stats);
         launches += 3;
     }
     st_filter_count_kernel<<<(n + 127) / 128, 128, 0, st>>>(s, a.W_off, a.W_rec, a.view_max, a.F_cnt, a.best_e);

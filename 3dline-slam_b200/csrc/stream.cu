@@ -121,6 +121,9 @@ int l3d_stream_update_image(l3d_ctx* ctx, uint32_t cam_id, const double* R, cons
     return L3D_OK;
 }
 
+// reservation floors of the growing tables (elements): 256 Ki segments, 1 Ki views, 2 Mi list entries
+static const size_t kSegFloor = 1u << 18, kViewFloor = 1u << 10, kListFloor = 1u << 21;
+
 template <typename T>
 static void swap_buf(DevBuf<T>& a, DevBuf<T>& b)
 {
@@ -149,10 +152,10 @@ int stream_match_images(l3d_ctx* ctx, const l3d_params* params)
     uint32_t S_old = 0;
     for (auto& hv : ctx->views)
         if (hv.uploaded) S_old = hv.seg_off + hv.v.num_segs;
-    CK(ctx->d_segs.ensure(S, S_old, st));
-    CK(ctx->d_seg_view.ensure(S, S_old, st));
-    CK(ctx->d_filt_off.ensure((size_t)S + 1, S_old, st));
-    CK(ctx->d_filt_cnt.ensure((size_t)S + 1, S_old, st));
+    CK(ensure_roomy(ctx->d_segs, S, kSegFloor, S_old, st));
+    CK(ensure_roomy(ctx->d_seg_view, S, kSegFloor, S_old, st));
+    CK(ensure_roomy(ctx->d_filt_off, (size_t)S + 1, kSegFloor, S_old, st));
+    CK(ensure_roomy(ctx->d_filt_cnt, (size_t)S + 1, kSegFloor, S_old, st));
     if (S > S_old) {
         CK(cudaMemsetAsync(ctx->d_filt_off.p + S_old, 0, (size_t)(S - S_old) * 4, st));
         CK(cudaMemsetAsync(ctx->d_filt_cnt.p + S_old, 0, (size_t)(S - S_old) * 4, st));
@@ -169,21 +172,21 @@ int stream_match_images(l3d_ctx* ctx, const l3d_params* params)
         CK(cudaStreamSynchronize(st));  // sv is reused
         hv.uploaded = true;
     }
-    CK(ctx->d_desc.ensure(S));
-    CK(ctx->d_rays.ensure(S));
-    CK(ctx->d_midray.ensure(3 * (size_t)S));
-    CK(ctx->d_planes.ensure(S));
-    CK(ctx->d_view_xb.ensure(V));
-    CK(ctx->d_views.ensure(V));
-    CK(ctx->d_entries.ensure((size_t)S + 1));
-    CK(ctx->d_L_off.ensure((size_t)S + 2));
-    CK(ctx->d_L_cnt.ensure((size_t)S + 1));
-    CK(ctx->d_has.ensure((size_t)S + 1));
-    CK(ctx->d_entry_idx.ensure((size_t)S + 2));
-    CK(ctx->d_view_max.ensure((size_t)V + 1));
-    CK(ctx->d_st_view_total.ensure((size_t)V + 1));
+    CK(ensure_roomy(ctx->d_desc, S, kSegFloor));
+    CK(ensure_roomy(ctx->d_rays, S, kSegFloor));
+    CK(ensure_roomy(ctx->d_midray, 3 * (size_t)S, 3 * kSegFloor));
+    CK(ensure_roomy(ctx->d_planes, S, kSegFloor));
+    CK(ensure_roomy(ctx->d_view_xb, V, kViewFloor));
+    CK(ensure_roomy(ctx->d_views, V, kViewFloor));
+    CK(ensure_roomy(ctx->d_entries, (size_t)S + 1, kSegFloor));
+    CK(ensure_roomy(ctx->d_L_off, (size_t)S + 2, kSegFloor));
+    CK(ensure_roomy(ctx->d_L_cnt, (size_t)S + 1, kSegFloor));
+    CK(ensure_roomy(ctx->d_has, (size_t)S + 1, kSegFloor));
+    CK(ensure_roomy(ctx->d_entry_idx, (size_t)S + 2, kSegFloor));
+    CK(ensure_roomy(ctx->d_view_max, (size_t)V + 1, kViewFloor));
+    CK(ensure_roomy(ctx->d_st_view_total, (size_t)V + 1, kViewFloor));
     CK(ctx->d_small.ensure(16));
-    CK(ctx->d_scan.ensure(scan_scratch_words(S + 2) + 64));
+    CK(ensure_roomy(ctx->d_scan, scan_scratch_words(S + 2) + 64, kSegFloor));
 
     // ---- translate(), spatial regularisers of the current views (src/line3D.cc:568-590) ----
     compute_translation(ctx);
@@ -288,7 +291,7 @@ int stream_match_images(l3d_ctx* ctx, const l3d_params* params)
     if (rc) return rc;
     ctx->cnt.forward_matches = ctx->total_fwd;
     const size_t F = (size_t)ctx->total_fwd;
-    CK(ctx->d_fwd_score.ensure(F + 1));
+    CK(ensure_roomy(ctx->d_fwd_score, F + 1, kListFloor));
     CK(cudaMemsetAsync(ctx->d_fwd_score.p, 0, (F + 1) * sizeof(float), st));
 
     // ---- the walk over the current views (src/line3D.cc:848-930) ----
@@ -302,11 +305,10 @@ int stream_match_images(l3d_ctx* ctx, const l3d_params* params)
         // earlier cycle nor earlier in this walk
         if (vt.current && !vt.processed && hp.tgt > hp.src) in_of[hp.tgt].push_back(p);
     }
+    // descriptors: per view its outgoing pairs (targets ascending), per NEW view its incoming pairs
     std::vector<StreamPair> sp;
-    std::vector<uint32_t> in0(V, 0), out0(V, 0);
-    std::vector<uint64_t> wcap(V, 0), wbase(V, 0);
-    uint64_t extent = 0;
-    uint32_t max_n = 0, max_in = 0;
+    std::vector<uint32_t> in0(V, 0), vout0(V, 0), vnout(V, 0);
+    std::vector<uint64_t> vcap(V, 0), vin(V, 0);
     for (uint32_t v : cur) {
         const HostView& hv = ctx->views[v];
         uint64_t cap = hv.filt_total;
@@ -323,45 +325,90 @@ int stream_match_images(l3d_ctx* ctx, const l3d_params* params)
             return q;
         };
         in0[v] = (uint32_t)sp.size();
-        uint64_t in_total = 0;
         for (uint32_t p : in_of[v]) {
             sp.push_back(desc(p, ctx->pairs[p].src));
-            in_total += ctx->pairs[p].fwd_total;
+            vin[v] += ctx->pairs[p].fwd_total;
         }
-        out0[v] = (uint32_t)sp.size();
+        vout0[v] = (uint32_t)sp.size();
+        vnout[v] = (uint32_t)out_of[v].size();
         for (uint32_t p : out_of[v]) sp.push_back(desc(p, ctx->pairs[p].tgt));
-        wcap[v] = cap;
-        wbase[v] = extent;
-        extent += cap;
-        max_n = std::max(max_n, hv.v.num_segs);
-        max_in = std::max<uint64_t>(max_in, in_total);
+        vcap[v] = cap;
+    }
+    // steps: every view scored in an earlier cycle receives no inverse matches any more, so those views
+    // do not feed each other and go in ONE step; each new view follows in ascending camera id (it
+    // receives the inverse matches of the views before it, src/line3D.cc:1994)
+    struct Step {
+        std::vector<uint32_t> views;
+        uint32_t row0 = 0, n = 0;
+        uint64_t cap = 0, base = 0;
+    };
+    std::vector<Step> steps;
+    {
+        Step old;
+        for (uint32_t v : cur)
+            if (ctx->views[v].processed) old.views.push_back(v);
+        if (!old.views.empty()) steps.push_back(old);
+        for (uint32_t v : cur)
+            if (!ctx->views[v].processed) {
+                Step one;
+                one.views.push_back(v);
+                steps.push_back(one);
+            }
+    }
+    std::vector<uint32_t> row_g;
+    uint64_t extent = 0;
+    uint32_t max_n = 0;
+    uint64_t max_in = 0;
+    for (Step& sx : steps) {
+        sx.row0 = (uint32_t)row_g.size();
+        for (uint32_t v : sx.views) {
+            const HostView& hv = ctx->views[v];
+            for (uint32_t i = 0; i < hv.v.num_segs; ++i) row_g.push_back(hv.seg_off + i);
+            sx.cap += vcap[v];
+            max_in = std::max(max_in, vin[v]);
+        }
+        sx.n = (uint32_t)row_g.size() - sx.row0;
+        sx.base = extent;
+        extent += sx.cap;
+        max_n = std::max(max_n, sx.n);
     }
     if (extent > 0xfffffff0ull) return fail(L3D_ERR_CAPACITY, "too many list entries (%llu)", (unsigned long long)extent);
     ctx->st_w_extent = ctx->st_f_extent = extent;
     swap_buf(ctx->d_filt_rec, ctx->d_st_filt_old);  // last cycle's filtered lists become the persisted input
-    CK(ctx->d_filt_rec.ensure(extent + 1));
-    CK(ctx->d_st_W_rec.ensure(extent + 1));
-    CK(ctx->d_st_W_row.ensure(extent + 1));
-    CK(ctx->d_st_W_geo.ensure((extent + 1) * sizeof(ListGeo)));
+    CK(ensure_roomy(ctx->d_filt_rec, extent + 1, kListFloor));
+    CK(ensure_roomy(ctx->d_st_W_rec, extent + 1, kListFloor));
+    CK(ensure_roomy(ctx->d_st_W_row, extent + 1, kListFloor));
+    CK(ensure_roomy(ctx->d_st_W_geo, (extent + 1) * sizeof(ListGeo), kListFloor * sizeof(ListGeo)));
     CK(ctx->d_st_pairs.ensure((sp.size() + 1) * sizeof(StreamPair)));
-    CK(ctx->d_st_vflag.ensure((size_t)V + 1));
+    CK(ensure_roomy(ctx->d_st_vflag, (size_t)V + 1, kViewFloor));
     CK(ctx->d_st_stats.ensure(stream_stats_bytes()));
-    CK(ctx->d_st_I_cnt.ensure((size_t)max_n + 2));
-    CK(ctx->d_st_I_off.ensure((size_t)max_n + 2));
-    CK(ctx->d_st_I_fill.ensure((size_t)max_n + 2));
-    CK(ctx->d_st_I_key.ensure((size_t)max_in + 1));
-    CK(ctx->d_st_W_cnt.ensure((size_t)max_n + 2));
-    CK(ctx->d_st_W_off.ensure((size_t)max_n + 2));
-    CK(ctx->d_st_F_cnt.ensure((size_t)max_n + 2));
-    CK(ctx->d_st_F_off.ensure((size_t)max_n + 2));
-    CK(ctx->d_st_best.ensure((size_t)max_n + 2));
+    CK(ensure_roomy(ctx->d_st_row_g, row_g.size() + 1, kSegFloor));
+    CK(ensure_roomy(ctx->d_st_vout, 2 * (size_t)V + 2, 2 * kViewFloor));
+    CK(ensure_roomy(ctx->d_st_I_cnt, (size_t)max_n + 2, kSegFloor));
+    CK(ensure_roomy(ctx->d_st_I_off, (size_t)max_n + 2, kSegFloor));
+    CK(ensure_roomy(ctx->d_st_I_fill, (size_t)max_n + 2, kSegFloor));
+    CK(ensure_roomy(ctx->d_st_I_key, (size_t)max_in + 1, kListFloor));
+    CK(ensure_roomy(ctx->d_st_W_cnt, (size_t)max_n + 2, kSegFloor));
+    CK(ensure_roomy(ctx->d_st_W_off, (size_t)max_n + 2, kSegFloor));
+    CK(ensure_roomy(ctx->d_st_F_cnt, (size_t)max_n + 2, kSegFloor));
+    CK(ensure_roomy(ctx->d_st_F_off, (size_t)max_n + 2, kSegFloor));
+    CK(ensure_roomy(ctx->d_st_best, (size_t)max_n + 2, kSegFloor));
+    CK(ensure_roomy(ctx->d_scan, scan_scratch_words(std::max(S, max_n) + 2) + 64, kSegFloor));
     std::vector<unsigned char> vflag(V + 1, 0);
     for (uint32_t v : ctx->st_add) vflag[v] |= 1u;
     for (uint32_t v : ctx->st_del) vflag[v] |= 2u;
+    std::vector<uint32_t> vout(2 * (size_t)V + 2, 0);
+    for (uint32_t v = 0; v < V; ++v) {
+        vout[v] = vout0[v];
+        vout[V + v] = vnout[v];
+    }
     if (!sp.empty())
         CK(cudaMemcpyAsync(ctx->d_st_pairs.p, sp.data(), sp.size() * sizeof(StreamPair), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(ctx->d_st_vflag.p, vflag.data(), (size_t)V + 1, cudaMemcpyHostToDevice, st));
-    CK(cudaStreamSynchronize(st));  // sp / vflag are locals
+    CK(cudaMemcpyAsync(ctx->d_st_vout.p, vout.data(), vout.size() * 4, cudaMemcpyHostToDevice, st));
+    if (!row_g.empty())
+        CK(cudaMemcpyAsync(ctx->d_st_row_g.p, row_g.data(), row_g.size() * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));  // the sources are locals
     CK(cudaMemsetAsync(ctx->d_st_stats.p, 0, stream_stats_bytes(), st));
     CK(cudaMemsetAsync(ctx->d_view_max.p, 0, ((size_t)V + 1) * 4, st));
     CK(cudaMemsetAsync(ctx->d_st_view_total.p, 0, ((size_t)V + 1) * 4, st));
@@ -373,18 +420,21 @@ int stream_match_images(l3d_ctx* ctx, const l3d_params* params)
         CK(cudaMemsetAsync(ctx->d_filt_cnt.p + hv.seg_off, 0, (size_t)hv.v.num_segs * 4, st));
         ctx->views[v].filt_total = 0;
     }
-    for (uint32_t v : cur) {
-        HostView& hv = ctx->views[v];
-        StreamViewArgs a{};
-        a.view = v; a.n = hv.v.num_segs; a.g0 = hv.seg_off;
-        a.n_in = out0[v] - in0[v];
-        a.n_out = (uint32_t)out_of[v].size();
-        a.in_total = 0;
-        for (uint32_t p : in_of[v]) a.in_total += (uint32_t)ctx->pairs[p].fwd_total;
-        a.w_base = a.f_base = (uint32_t)wbase[v];
-        a.w_cap = a.f_cap = (uint32_t)wcap[v];
-        a.pairs_in = (const StreamPair*)ctx->d_st_pairs.p + in0[v];
-        a.pairs_out = (const StreamPair*)ctx->d_st_pairs.p + out0[v];
+    for (const Step& sx : steps) {
+        const bool single_new = sx.views.size() == 1 && !ctx->views[sx.views[0]].processed;
+        const uint32_t v0 = sx.views[0];
+        StreamStepArgs a{};
+        a.n = sx.n;
+        a.n_in = single_new ? vout0[v0] - in0[v0] : 0u;
+        a.in0 = in0[v0];
+        a.in_total = single_new ? (uint32_t)vin[v0] : 0u;
+        a.w_base = a.f_base = (uint32_t)sx.base;
+        a.w_cap = a.f_cap = (uint32_t)sx.cap;
+        a.row_g = ctx->d_st_row_g.p + sx.row0;
+        a.seg_view = ctx->d_seg_view.p;
+        a.pairs = ctx->d_st_pairs.p;
+        a.vout0 = ctx->d_st_vout.p;
+        a.vnout = ctx->d_st_vout.p + V;
         a.fwd_rec = ctx->d_fwd_rec.p; a.fwd_score = ctx->d_fwd_score.p;
         a.fwd_off = ctx->d_fwd_off.p; a.fwd_cnt = ctx->d_fwd_cnt.p;
         a.I_off = ctx->d_st_I_off.p; a.I_cnt = ctx->d_st_I_cnt.p; a.I_fill = ctx->d_st_I_fill.p;
@@ -399,9 +449,9 @@ int stream_match_images(l3d_ctx* ctx, const l3d_params* params)
         a.view_max = ctx->d_view_max.p; a.F_cnt = ctx->d_st_F_cnt.p; a.F_off = ctx->d_st_F_off.p;
         a.best_e = ctx->d_st_best.p; a.entries = ctx->d_entries.p; a.view_total = ctx->d_st_view_total.p;
         a.stats = ctx->d_st_stats.p; a.two_sigA_sqr = ctx->two_sigA_sqr;
-        ctx->cnt.gpu_launches += launch_stream_view(a, st);
-        hv.processed = true;
+        ctx->cnt.gpu_launches += launch_stream_step(a, st);
     }
+    for (uint32_t v : cur) ctx->views[v].processed = true;
 
     // ---- view medians from the hypotheses as filterMatches stored them, then
     // update_Matches_and_Estimated_position3D, then the index of estimated_position3D_ ----

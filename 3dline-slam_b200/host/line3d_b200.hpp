@@ -27,11 +27,10 @@ class Line3D {
     Line3D(const std::string& /*output_folder*/, bool /*load_segments*/ = false, int max_img_width = -1,
            unsigned int max_line_segments = 3000, bool neighbors_by_worldpoints = false, bool use_GPU = true,
            int device = -1)
-        : max_image_width_(max_img_width), max_line_segments_(max_line_segments)
+        : max_image_width_(max_img_width), max_line_segments_(max_line_segments), by_wps_(neighbors_by_worldpoints)
     {
         prefix_ = "[L3D++] ";
-        if (!use_GPU || neighbors_by_worldpoints)
-            std::cerr << prefix_ << "ERROR: l3dpp-b200 needs use_GPU=true and explicit neighbour lists" << std::endl;
+        if (!use_GPU) std::cerr << prefix_ << "ERROR: l3dpp-b200 has no CPU path (use_GPU must be true)" << std::endl;
         if (l3d_ctx_create(&ctx_, device) != L3D_OK) {
             std::cerr << prefix_ << "ERROR: " << l3d_last_error() << std::endl;
             ctx_ = nullptr;
@@ -51,7 +50,8 @@ class Line3D {
             return;
         }
         if (wps_or_neighbors.empty()) {
-            std::cout << prefix_ << "ERROR: view [" << camID << "] has no visual neighbors!" << std::endl;
+            std::cout << prefix_ << "ERROR: view [" << camID << (by_wps_ ? "] has no worldpoints!" : "] has no visual neighbors!")
+                      << std::endl;
             return;
         }
         V v;
@@ -147,8 +147,9 @@ class Line3D {
     {
         if (l3d_scene_begin(ctx_) != L3D_OK) return false;
         for (auto& kv : views_)
-            if (l3d_scene_add_view(ctx_, &kv.second.d, kv.second.segs.data(), kv.second.nbrs.data(),
-                                   (uint32_t)kv.second.nbrs.size()) != L3D_OK) {
+            if ((by_wps_ ? l3d_scene_add_view_wps : l3d_scene_add_view)(ctx_, &kv.second.d, kv.second.segs.data(),
+                                                                        kv.second.nbrs.data(),
+                                                                        (uint32_t)kv.second.nbrs.size()) != L3D_OK) {
                 std::cout << prefix_ << "ERROR: " << l3d_last_error() << std::endl;
                 return false;
             }
@@ -164,6 +165,97 @@ class Line3D {
     bool dirty_ = true;
     int max_image_width_;
     unsigned int max_line_segments_;
+    bool by_wps_ = false;
+    std::string prefix_;
+};
+
+// The same object driven incrementally, the way L3DPPing::Run (src/L3DPPing.cpp:98-236) drives it:
+// per cycle beginCycle(), deleteImage() for the culled key frames, addImage() for the new ones,
+// UpdataImage() for every current one, matchImages(), reconstruct3Dlines().  The context keeps
+// matched_, processed_, the filtered match lists with their scores and the Add / Delete sets
+// (l3d_stream_* in include/l3dpp_b200.h).  Errors are printed, never thrown, as in the reference.
+class Line3DStream {
+  public:
+    Line3DStream(const std::string& /*output_folder*/, bool /*load_segments*/ = false, int max_img_width = -1,
+                 unsigned int /*max_line_segments*/ = 3000, bool neighbors_by_worldpoints = true, bool use_GPU = true,
+                 int device = -1)
+        : max_image_width_(max_img_width)
+    {
+        prefix_ = "[L3D++] ";
+        if (!use_GPU) std::cerr << prefix_ << "ERROR: l3dpp-b200 has no CPU path (use_GPU must be true)" << std::endl;
+        if (l3d_ctx_create(&ctx_, device) != L3D_OK || l3d_stream_begin(ctx_, neighbors_by_worldpoints ? 1 : 0) != L3D_OK) {
+            std::cerr << prefix_ << "ERROR: " << l3d_last_error() << std::endl;
+            l3d_ctx_destroy(ctx_);
+            ctx_ = nullptr;
+        }
+    }
+    ~Line3DStream() { l3d_ctx_destroy(ctx_); }
+    Line3DStream(const Line3DStream&) = delete;
+    Line3DStream& operator=(const Line3DStream&) = delete;
+
+    // the resets at the top of L3DPPing::Run's loop body (src/L3DPPing.cpp:98-103)
+    void beginCycle() { report(ctx_ ? l3d_stream_begin_cycle(ctx_) : L3D_OK); }
+
+    void addImage(unsigned int camID, unsigned int width, unsigned int height, const double K[9], const double R[9],
+                  const double t[3], float median_depth, const std::list<unsigned int>& wps_or_neighbors,
+                  const std::vector<float>& line_segments_xyxy)
+    {
+        if (!ctx_) return;
+        l3d_view v{};
+        v.cam_id = camID;
+        v.width = width;
+        v.height = height;
+        v.num_segs = (uint32_t)(line_segments_xyxy.size() / 4);
+        for (int i = 0; i < 9; ++i) { v.K[i] = K[i]; v.R[i] = R[i]; }
+        for (int i = 0; i < 3; ++i) v.t[i] = t[i];
+        v.median_depth = median_depth;
+        std::vector<uint32_t> l(wps_or_neighbors.begin(), wps_or_neighbors.end());
+        report(l3d_stream_add_image(ctx_, &v, line_segments_xyxy.data(), l.data(), (uint32_t)l.size()));
+    }
+    bool deleteImage(unsigned int camID)
+    {
+        if (!ctx_) return false;
+        return report(l3d_stream_delete_image(ctx_, camID));
+    }
+    void UpdataImage(unsigned int camID, const double R[9], const double t[3], float median_depth,
+                     const std::list<unsigned int>& wps_or_neighbors)
+    {
+        if (!ctx_) return;
+        std::vector<uint32_t> l(wps_or_neighbors.begin(), wps_or_neighbors.end());
+        report(l3d_stream_update_image(ctx_, camID, R, t, median_depth, l.data(), (uint32_t)l.size()));
+    }
+    void matchImages(float sigma_position = 2.5f, float sigma_angle = 10.0f, unsigned int num_neighbors = 10,
+                     float epipolar_overlap = 0.25f, int kNN = 10, float const_regularization_depth = -1.0f)
+    {
+        if (!ctx_) return;
+        l3d_params p{};
+        p.sigma_p = sigma_position;
+        p.sigma_a = sigma_angle;
+        p.num_neighbors = num_neighbors;
+        p.epipolar_overlap = epipolar_overlap;
+        p.knn = kNN;
+        p.const_reg_depth = const_regularization_depth;
+        p.max_image_width = max_image_width_;
+        report(l3d_match_images(ctx_, &p));
+    }
+    void reconstruct3Dlines(unsigned int /*visibility_t*/ = 3, bool perform_diffusion = false,
+                            float collinearity_t = -1.0f, bool use_CERES = false)
+    {
+        if (!ctx_) return;
+        if (perform_diffusion || use_CERES || collinearity_t > 1e-12f)
+            std::cout << prefix_ << "ERROR: diffusion / CERES / collinearity are not part of this path" << std::endl;
+        if (report(l3d_affinity(ctx_))) report(l3d_cluster(ctx_));
+    }
+    l3d_ctx* context() { return ctx_; }
+
+  private:
+    bool report(int rc)
+    {
+        if (rc != L3D_OK) std::cout << prefix_ << "ERROR: " << l3d_last_error() << std::endl;
+        return rc == L3D_OK;
+    }
+    l3d_ctx* ctx_ = nullptr;
+    int max_image_width_;
     std::string prefix_;
 };
 

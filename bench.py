@@ -155,6 +155,122 @@ def bench_reference(args, scene_mod):
     print(json.dumps(line))
 
 
+def bench_stream(args, scene_mod):
+    """--workload c3: BASELINE config[2], the key-frame stream through the incremental mode
+    (l3d_stream_*; 640x480, 1000 segments per key frame, window of 20, 10 neighbours).  One step = one
+    L3DPPing cycle in steady state: delete the culled key frames, add the new one (host buffers),
+    re-pose every current key frame, matchImages, reconstruct3Dlines -- the whole cycle is the public
+    API with host inputs, so the step time IS the end-to-end time; `value` counts the cycle's new
+    segment-pair tests.  Single GPU (the mode does not shard: replicas only)."""
+    import torch
+    api = importlib.import_module("3dline-slam_b200.api")
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import stream_utils
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    fill = 24  # cycles until the window of 20 is full and sliding
+    W, K = max(args.warmup, 3), min(args.steps, 100)
+    st = scene_mod.make_stream(n_keyframes=5 + fill + W + K, n_seg=1000, window=20, nbrs=10, jitter=0.3)
+    l3, calls = stream_utils.cuda_driver(api, st)
+    ts, tests, launches = [], [], []
+    state = {"t0": 0.0}
+
+    parts = []
+
+    def cycle(cy, calls):
+        a = time.perf_counter()
+        calls["begin_cycle"]()
+        for cam in cy.deletes:
+            calls["delete"](cam)
+        for v in cy.adds:
+            calls["add"](v, v.worldpoints)
+        for cam, R, t, md, lst in cy.updates:
+            calls["update"](cam, R, t, md, lst)
+        b = time.perf_counter()
+        calls["match"](st.params)
+        c = time.perf_counter()
+        calls["reconstruct"]()
+        parts.append((b - a, c - b, time.perf_counter() - c))
+
+    sampler = ClockSampler(0)
+    if not os.environ.get("L3D_BENCH_NO_SAMPLER"):
+        sampler.start()
+    wall0 = wall1 = time.time()
+    stage = {}
+    h2d = d2h = 0
+    for ci, cy in enumerate(st.cycles):
+        timed = ci >= fill + W and len(ts) < K
+        if timed and not ts:
+            wall0 = time.time()
+        l3.reset_counters()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        cycle(cy, calls)
+        ij, w = l3.edges()                      # A_ back on the host, like the reference's consumer
+        ids = l3.cluster_ids()
+        torch.cuda.synchronize(dev)
+        dt = time.perf_counter() - t0
+        if timed:
+            c = l3.counts()
+            ts.append(dt)
+            tests.append(c["pair_tests"])
+            launches.append(c["gpu_launches"])
+            for k, v in l3.timings().items():
+                stage[k] = stage.get(k, 0.0) + v
+            h2d += sum(v.segs.nbytes for v in cy.adds) + 96 * len(cy.updates)
+            d2h += ij.nbytes + w.nbytes + ids.nbytes
+            wall1 = time.time()
+    clocks = sampler.stop(wall0, wall1) if not os.environ.get("L3D_BENCH_NO_SAMPLER") else None
+    T = float(np.sum(ts))
+    n = len(ts)
+    if os.environ.get("L3D_BENCH_TRACE"):
+        for i in np.argsort(-np.asarray(ts))[:4]:
+            ci = fill + W + int(i)
+            print("slow cycle %d: %.2f ms (host calls %.2f, match %.2f, reconstruct %.2f)" %
+                  (ci, 1e3 * ts[i], 1e3 * parts[ci][0], 1e3 * parts[ci][1], 1e3 * parts[ci][2]), file=sys.stderr)
+        pm = np.median(np.asarray(parts[fill + W:fill + W + n]), axis=0)
+        print("median parts: host calls %.2f ms, match %.2f ms, reconstruct %.2f ms" % tuple(1e3 * pm), file=sys.stderr)
+    cpu = None
+    if not args.no_cpu_baseline:
+        import oracle_py
+        o, oc = stream_utils.oracle_driver(oracle_py, st)
+        ct, ctests = 0.0, 0
+        for ci, cy in enumerate(st.cycles[:fill + W + min(K, 20)]):
+            before = o.pair_tests()
+            t0 = time.perf_counter()
+            cycle(cy, oc)
+            d = time.perf_counter() - t0
+            if ci >= fill + W:
+                ct += d
+                ctests += o.pair_tests() - before
+        cores = oracle_py.lib().orc_max_threads()
+        o.close()
+        cpu = {"value": ctests / ct, "unit": "tests/s", "cores": cores, "kind": "port",
+               "sample": "the same stream, the first %d timed cycles" % min(K, 20),
+               "ms_per_cycle": 1e3 * ct / min(K, 20)}
+    value = float(np.sum(tests)) / T
+    line = {
+        "metric": "segment_pair_tests_per_s", "value": value, "unit": "tests/s", "n_gpus": 1, "steps": n, "warmup": W,
+        "ms_per_step": 1e3 * T / n, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64",
+        "data": "synthetic",
+        "config": {"workload": "c3", "keyframes": len(st.cycles) + 4, "window": 20, "segments_per_view": 1000,
+                   "neighbours": 10, "new_keyframes_per_cycle": 1, "step": "one L3DPPing cycle in steady state, wall clock",
+                   "l2": "inputs larger than one kernel's footprint are not the bound here: launch-bound"},
+        "views_per_s": 20.0 * n / T,
+        "ms_per_cycle_p50": 1e3 * float(np.median(ts)), "ms_per_cycle_max": 1e3 * float(np.max(ts)),
+        "stage_ms": {k: v / n for k, v in stage.items()},
+        "e2e": {"value": value, "unit": "tests/s", "h2d_bytes_per_step": h2d // n, "d2h_bytes_per_step": d2h // n},
+        "gpu_launches": int(np.sum(launches)), "clocks": clocks,
+    }
+    if cpu:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -171,6 +287,9 @@ def main():
     scene_mod = importlib.import_module("3dline-slam_b200.scene")
     if args.impl == "reference":
         bench_reference(args, scene_mod)
+        return
+    if args.workload == "c3":
+        bench_stream(args, scene_mod)
         return
 
     import torch

@@ -16,6 +16,11 @@
                      affinity edges, cluster ids), the regression pin for both the oracle (CPU test)
                      and the CUDA path (GPU test).
 
+  stream_expected.npz
+                     per-cycle sha256 digests and sizes of the oracle's outputs on the key-frame
+                     stream tests/stream_utils.GOLDEN_STREAM (incremental mode, BASELINE config 3's
+                     call sequence: delete / add / re-pose / match / reconstruct per cycle).
+
 The reference has no golden vectors for this path, so these are oracle
 outputs, not reference outputs: parity stays "unpinned" in the sense of DESIGN.md section 1.
 """
@@ -96,6 +101,14 @@ def main():
     ot = oracle_py.run_scene(st)
     np.savez_compressed(os.path.join(HERE, "tiny_expected.npz"), **expected(ot, st))
     print("tiny: pairs", len(ot.pairs()), "entries", len(ot.entries()), "edges", len(ot.edges()[1]))
+    # ---- key-frame stream (incremental mode) ----
+    sys.path.insert(0, os.path.dirname(HERE))
+    import stream_utils
+    stream = scene_mod.make_stream(**stream_utils.GOLDEN_STREAM)
+    o3, calls = stream_utils.oracle_driver(oracle_py, stream)
+    dig, sizes = stream_utils.stream_digests(stream, o3, calls)
+    np.savez_compressed(os.path.join(HERE, "stream_expected.npz"), digests=dig, sizes=sizes)
+    print("stream: cycles", len(dig), "entries/edges/ids per cycle", sizes.tolist())
 
 
 if __name__ == "__main__":

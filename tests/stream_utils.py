@@ -122,3 +122,42 @@ def run_lockstep(api, oracle, stream, max_cycles=None, check_scored=True):
         tot["tests"] += l3.counts()["pair_tests"]
     o.close()
     return tot
+
+
+GOLDEN_STREAM = dict(n_keyframes=14, n_seg=600, window=10, nbrs=6, jitter=0.2, n_world=1200, cull_every=3)
+
+
+def cycle_digest(obj, cams):
+    """sha256 over everything a cycle produced (canonical field order, independent of who ran it)."""
+    import hashlib
+    import oracle_py
+    h = hashlib.sha256()
+
+    def canon(a, dt):
+        c = np.zeros(len(a), dtype=dt)
+        for f in dt.names:
+            c[f] = a[f]
+        return c.tobytes()
+    for cam in cams:
+        off, rec = obj.lists(cam, 1)
+        h.update(np.asarray(off, dtype=np.uint32).tobytes())
+        h.update(canon(rec, oracle_py.REC_DTYPE))
+        vi = obj.view_info(cam)
+        h.update(np.float32(vi["k"]).tobytes() + np.float32(vi["median_depth"]).tobytes())
+        h.update(np.asarray(sorted(obj.neighbors(cam)), dtype=np.uint32).tobytes())
+    h.update(canon(obj.entries(), oracle_py.ENTRY_DTYPE))
+    ij, w = obj.edges()
+    h.update(np.asarray(ij, dtype=np.int32).tobytes() + np.asarray(w, dtype=np.float32).tobytes())
+    h.update(np.asarray(obj.local2global(), dtype=np.uint32).tobytes())
+    h.update(np.asarray(obj.cluster_ids(), dtype=np.int32).tobytes())
+    return np.frombuffer(h.digest(), dtype=np.uint8).copy()
+
+
+def stream_digests(stream, obj, calls):
+    out, sizes = [], []
+
+    def on_cycle(ci, cy):
+        out.append(cycle_digest(obj, [u[0] for u in cy.updates]))
+        sizes.append((len(obj.entries()), len(obj.edges()[1]), len(obj.cluster_ids())))
+    scene_mod.drive_stream(stream, on_cycle=on_cycle, **calls)
+    return np.stack(out), np.asarray(sizes, dtype=np.int64)

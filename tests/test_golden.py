@@ -74,3 +74,32 @@ def test_cuda_world_point_mode_reproduces_golden_c1(api):
     for v in sc.views:
         assert l3.neighbors(v.cam_id) == frozen[v.cam_id]
     golden_utils.check_against_golden(l3, sc, "c1_nvm_expected.npz")
+
+
+def _stream_expected():
+    return np.load(os.path.join(golden_utils.HERE, "stream_expected.npz"))
+
+
+def test_oracle_reproduces_golden_stream(oracle, scene_mod):
+    """Incremental mode (delete / add / re-pose / match / reconstruct per cycle): every cycle's outputs
+    hash to the committed digests, with one OpenMP thread and with all of them."""
+    import stream_utils
+    g = _stream_expected()
+    stream = scene_mod.make_stream(**stream_utils.GOLDEN_STREAM)
+    for threads in (1, 0):
+        o, calls = stream_utils.oracle_driver(oracle, stream, threads)
+        dig, sizes = stream_utils.stream_digests(stream, o, calls)
+        assert (sizes == g["sizes"]).all()
+        assert (dig == g["digests"]).all(), np.nonzero((dig != g["digests"]).any(axis=1))[0]
+        o.close()
+
+
+@pytest.mark.gpu
+def test_cuda_reproduces_golden_stream(api, scene_mod):
+    import stream_utils
+    g = _stream_expected()
+    stream = scene_mod.make_stream(**stream_utils.GOLDEN_STREAM)
+    l3, calls = stream_utils.cuda_driver(api, stream)
+    dig, sizes = stream_utils.stream_digests(stream, l3, calls)
+    assert (sizes == g["sizes"]).all()
+    assert (dig == g["digests"]).all(), np.nonzero((dig != g["digests"]).any(axis=1))[0]

@@ -22,7 +22,9 @@ def test_cpp_line3d_mirror_links(tmp_path, api):
     api.build()
     src = tmp_path / "t.cpp"
     src.write_text('#include "line3d_b200.hpp"\n'
-                   'int main() { L3DPP_B200::Line3D l("", false, 640); l.matchImages(); return (int)l.numImages(); }\n')
+                   'int main() { L3DPP_B200::Line3D l("", false, 640); l.matchImages();\n'
+                   '  L3DPP_B200::Line3DStream s("", false, 640); s.beginCycle(); s.deleteImage(3); s.matchImages();\n'
+                   '  s.reconstruct3Dlines(); return (int)l.numImages(); }\n')
     exe = tmp_path / "t"
     subprocess.check_call(["/usr/bin/g++", "-std=c++11", "-Wall", "-I", os.path.join(ROOT, "include"), "-I",
                            os.path.join(PKG, "host"), str(src), "-L", PKG, "-ll3dpp_b200", "-Wl,-rpath," + PKG, "-o",

@@ -15,9 +15,9 @@ pytestmark = pytest.mark.gpu
 def test_stream_world_point_neighbours(api, oracle, scene_mod):
     """The mode L3DPPing uses: neighbours from shared world points, re-chosen every cycle; sliding
     window with culling from the middle; poses re-estimated every cycle."""
-    st = scene_mod.make_stream(n_keyframes=22, n_seg=400, window=8, nbrs=6, jitter=0.3)
+    st = scene_mod.make_stream(n_keyframes=22, n_seg=500, window=12, nbrs=6, jitter=0.3, n_world=1200, cull_every=3)
     tot = stream_utils.run_lockstep(api, oracle, st)
-    assert tot["cycles"] == 18 and tot["deleted"] >= 10 and tot["entries"] > 500 and tot["edges"] > 500
+    assert tot["cycles"] == 18 and tot["deleted"] >= 8 and tot["entries"] > 3000 and tot["edges"] > 3000
 
 
 def test_stream_fixed_neighbours(api, oracle, scene_mod):
@@ -42,6 +42,20 @@ def test_stream_c3_shape(api, oracle, scene_mod):
     st = scene_mod.make_stream(n_keyframes=45, n_seg=1000, window=20, nbrs=10, jitter=0.3)
     tot = stream_utils.run_lockstep(api, oracle, st, check_scored=False)
     assert tot["cycles"] == 41 and tot["entries"] > 10000
+
+
+def test_stream_idle_cycle_is_a_fixed_point(api, scene_mod):
+    import test_stream_oracle as props
+    st = scene_mod.make_stream(n_keyframes=8, n_seg=400, window=8, nbrs=5, jitter=0.0, n_world=900, cull_every=0)
+    l3, calls = stream_utils.cuda_driver(api, st)
+    scene_mod.drive_stream(st, **calls)
+    cams = [u[0] for u in st.cycles[-1].updates]
+    before, e0, _ = props.check_idle_cycle_is_a_fixed_point(l3, calls, st, cams)
+    assert len(l3.pairs()) == 0 and l3.counts()["pair_tests"] == 0   # nothing is matched twice
+    for c in cams:
+        off, rec = l3.lists(c, 1)
+        assert (off == before[c][0]).all() and rec.tobytes() == before[c][1].tobytes()
+    assert l3.entries().tobytes() == e0.tobytes() and len(e0) > 100
 
 
 def test_stream_errors_mirror_the_reference(api, scene_mod):
