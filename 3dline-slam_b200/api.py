@@ -105,6 +105,8 @@ def lib():
         L.l3d_match_stage12.argtypes = [vp, C.POINTER(Params)]
         L.l3d_match_stage3.argtypes = [vp]
         L.l3d_affinity.argtypes = [vp]
+        L.l3d_affinity_sparse.argtypes = [vp, C.c_int, f32, vp, vp, u32, u32]
+        L.l3d_get_sparse_device.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
         L.l3d_cluster.argtypes = [vp]
         L.l3d_cluster_edges.argtypes = [vp, vp, u32, u32, vp]
         L.l3d_get_counts.argtypes = [vp, C.POINTER(Counts)]
@@ -352,6 +354,15 @@ class Line3D:
 
     def affinity(self):
         self._ck(self.L.l3d_affinity(self.h))
+
+    def sparse_matrix(self, sort_by_row=False, normalization_factor=1.0):
+        """SparseMatrix(A_, n, norm, sort_by_row) (src/sparsematrix.cc:8-61): (entries (E,4) f32, start_indices (n,) i32)."""
+        c = self.counts()
+        ent = np.zeros((max(c["num_edges"], 1), 4), dtype=np.float32)
+        st = np.zeros(max(c["num_local_ids"], 1), dtype=np.int32)
+        self._ck(self.L.l3d_affinity_sparse(self.h, int(bool(sort_by_row)), float(normalization_factor), _p(ent), _p(st),
+                                            ent.shape[0], st.size))
+        return ent[:c["num_edges"]], st[:c["num_local_ids"]]
 
     # ---- results ----
     def counts(self):

@@ -1080,6 +1080,49 @@ int l3d_affinity(l3d_ctx* ctx)
     return l3d_affinity_ids(ctx);
 }
 
+// SparseMatrix::SparseMatrix (src/sparsematrix.cc:8-61) of A_, built on the device and kept there for a
+// device-side consumer (l3d_get_sparse_device); the host copies are optional.
+int l3d_affinity_sparse(l3d_ctx* ctx, int sort_by_row, float normalization_factor, float* entries_xyzw,
+                        int32_t* start_indices, uint32_t cap_entries, uint32_t cap_rows)
+{
+    if (!ctx) return fail(L3D_ERR_ARG, "ctx is NULL");
+    if (ctx->stage < 3) return fail(L3D_ERR_STATE, "l3d_affinity has not run");
+    if (!(normalization_factor != 0.0f)) return fail(L3D_ERR_ARG, "normalization_factor must not be 0");
+    const uint32_t E = ctx->cnt.num_edges, n = ctx->cnt.num_local_ids;
+    ctx->sparse_ready = false;
+    if ((entries_xyzw && cap_entries < E) || (start_indices && cap_rows < n))
+        return fail(L3D_ERR_CAPACITY, "need %u entries and %u start indices", E, n);
+    if (!E || !n) return L3D_OK;  // SparseMatrix with entries_ == NULL (src/sparsematrix.cc:18-19)
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    CK(ctx->d_sp_hist.ensure((size_t)n + 2));
+    CK(ctx->d_sp_off.ensure((size_t)n + 2));
+    CK(ctx->d_sp_fill.ensure((size_t)n + 2));
+    CK(ctx->d_sp_tmp.ensure(E));
+    CK(ctx->d_sp_entries.ensure(E));
+    CK(ctx->d_sp_start.ensure(n));
+    CK(ctx->d_scan.ensure(scan_scratch_words(n + 2) + 64));
+    ctx->cnt.gpu_launches += launch_k4_sparse(ctx->d_A_ij.p, ctx->d_A_w.p, E, n, sort_by_row ? 1 : 0, normalization_factor,
+                                              ctx->d_sp_hist.p, ctx->d_sp_off.p, ctx->d_sp_fill.p, ctx->d_sp_tmp.p,
+                                              ctx->d_scan.p, ctx->d_scan.cap, ctx->d_sp_entries.p, ctx->d_sp_start.p, st);
+    if (entries_xyzw)
+        CK(cudaMemcpyAsync(entries_xyzw, ctx->d_sp_entries.p, (size_t)E * sizeof(float4), cudaMemcpyDeviceToHost, st));
+    if (start_indices)
+        CK(cudaMemcpyAsync(start_indices, ctx->d_sp_start.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    ctx->sparse_ready = true;
+    return L3D_OK;
+}
+
+int l3d_get_sparse_device(l3d_ctx* ctx, const void** entries_float4, const void** start_indices_int)
+{
+    if (!ctx || !entries_float4 || !start_indices_int) return fail(L3D_ERR_ARG, "NULL argument");
+    if (!ctx->sparse_ready) return fail(L3D_ERR_STATE, "l3d_affinity_sparse has not run (or A_ is empty)");
+    *entries_float4 = ctx->d_sp_entries.p;
+    *start_indices_int = ctx->d_sp_start.p;
+    return L3D_OK;
+}
+
 // Host-only: the visual neighbours Line3D::matchImages would choose from world-point lists
 // (Line3D::findVisualNeighborsFromWPs, src/line3D.cc:723-843, after Line3D::translate).  No device needed.
 int l3d_neighbors_from_worldpoints(const l3d_view* views, uint32_t n_views, const uint32_t* wps_concat,

@@ -53,6 +53,8 @@ int launch_k4_edges_write(const ViewDev*, uint32_t, const uint32_t*, const uint3
 int launch_k4_ids(const void*, uint32_t, uint32_t*, uint32_t*, uint32_t*, uint32_t*, size_t, int2*, float*,
                   uint32_t*, cudaStream_t);
 size_t k4_edge_bytes();
+int launch_k4_sparse(const int2*, const float*, uint32_t, uint32_t, int, float, uint32_t*, uint32_t*, uint32_t*, uint2*,
+                     uint32_t*, size_t, float4*, int*, cudaStream_t);
 int launch_test_expf(const float*, float*, uint32_t, cudaStream_t);
 int launch_test_acos(const double*, double*, uint32_t, cudaStream_t);
 int launch_fp32_peak(float*, int, int, cudaStream_t);
@@ -291,6 +293,12 @@ struct l3d_ctx {
     DevBuf<int2> d_A_ij;
     DevBuf<float> d_A_w;
     DevBuf<unsigned long long> d_tests;
+    // SparseMatrix layout of A_ (l3d_affinity_sparse)
+    DevBuf<uint32_t> d_sp_hist, d_sp_off, d_sp_fill;
+    DevBuf<uint2> d_sp_tmp;
+    DevBuf<float4> d_sp_entries;
+    DevBuf<int> d_sp_start;
+    bool sparse_ready = false;
     // host results
     std::vector<int32_t> cluster_ids;
 

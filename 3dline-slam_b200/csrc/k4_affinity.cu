@@ -321,4 +321,72 @@ int launch_k4_ids(const void* edges, uint32_t n_edges, uint32_t* first_touch, ui
 
 size_t k4_edge_bytes() { return sizeof(EdgeDev); }
 
+// ------------------------------------------------------------------------------------------
+// SparseMatrix::SparseMatrix (src/sparsematrix.cc:8-61): A_ sorted by (column,row) or (row,column)
+// (sortCLEdgesByCol / sortCLEdgesByRow, include/clustering.h:70-78), stored as float4{i,j,w/norm,0}
+// with the start index of every column (row), -1 where it is empty.  A directed pair occurs once in
+// A_ (Line3D::unused), so the order is total: counting sort by the primary key, then every key's
+// handful of entries is ordered by the secondary key.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k4_sparse_hist_kernel(const int2* __restrict__ A_ij, uint32_t E, int by_row,
+                                                             uint32_t* __restrict__ hist)
+{
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    const int2 ij = A_ij[e];
+    atomicAdd(&hist[by_row ? ij.x : ij.y], 1u);
+}
+
+__global__ void __launch_bounds__(256) k4_sparse_scatter_kernel(const int2* __restrict__ A_ij,
+                                                                const float* __restrict__ A_w, uint32_t E, int by_row,
+                                                                const uint32_t* __restrict__ off,
+                                                                uint32_t* __restrict__ fill, uint2* __restrict__ tmp)
+{
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    const int2 ij = A_ij[e];
+    const uint32_t key = by_row ? ij.x : ij.y, other = by_row ? ij.y : ij.x;
+    tmp[off[key] + atomicAdd(&fill[key], 1u)] = make_uint2(other, __float_as_uint(A_w[e]));
+}
+
+__global__ void __launch_bounds__(128) k4_sparse_finish_kernel(uint32_t n, const uint32_t* __restrict__ off,
+                                                               uint2* __restrict__ tmp, float norm, int by_row,
+                                                               float4* __restrict__ entries, int* __restrict__ start)
+{
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const uint32_t b = off[k], m = off[k + 1] - b;
+    start[k] = m ? (int)b : -1;
+    for (uint32_t a = 1; a < m; ++a) {
+        const uint2 x = tmp[b + a];
+        uint32_t c = a;
+        while (c > 0 && tmp[b + c - 1].x > x.x) {
+            tmp[b + c] = tmp[b + c - 1];
+            --c;
+        }
+        tmp[b + c] = x;
+    }
+    for (uint32_t a = 0; a < m; ++a) {
+        const uint2 x = tmp[b + a];
+        const float w = fd(__uint_as_float(x.y), norm);
+        entries[b + a] = by_row ? make_float4((float)k, (float)x.x, w, 0.0f) : make_float4((float)x.x, (float)k, w, 0.0f);
+    }
+}
+
+int launch_k4_sparse(const int2* A_ij, const float* A_w, uint32_t E, uint32_t n, int by_row, float norm, uint32_t* hist,
+                     uint32_t* off, uint32_t* fill, uint2* tmp, uint32_t* scan_scratch, size_t scan_words,
+                     float4* entries, int* start, cudaStream_t st)
+{
+    if (!E || !n) return 0;
+    int launches = 0;
+    cudaMemsetAsync(hist, 0, ((size_t)n + 1) * 4, st);
+    cudaMemsetAsync(fill, 0, ((size_t)n + 1) * 4, st);
+    k4_sparse_hist_kernel<<<(E + 255) / 256, 256, 0, st>>>(A_ij, E, by_row, hist);
+    ++launches;
+    launches += launch_scan_u32(hist, off, n, scan_scratch, scan_words, st);
+    k4_sparse_scatter_kernel<<<(E + 255) / 256, 256, 0, st>>>(A_ij, A_w, E, by_row, off, fill, tmp);
+    k4_sparse_finish_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, off, tmp, norm, by_row, entries, start);
+    return launches + 2;
+}
+
 }  // namespace l3d

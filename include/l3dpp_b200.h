@@ -212,6 +212,16 @@ int l3d_match_stage3(l3d_ctx* ctx);
  * (src/line3D.cc:2074-2091): builds A_ (edge list with first-touch local IDs) on the device. */
 int l3d_affinity(l3d_ctx* ctx);
 
+/* replaces SparseMatrix::SparseMatrix (src/sparsematrix.cc:8-61), the device layout of A_ that
+ * Line3D::performRDD hands to the GPU (src/line3D.cc:2453): entries float4{i, j, w / normalization, 0}
+ * sorted by (column, row) -- or (row, column) with sort_by_row -- and per column (row) the index of
+ * its first entry, -1 if it has none (num_local_ids of them).  Built and kept on the device
+ * (l3d_get_sparse_device: device pointers, valid until the next l3d_affinity* call); the host copies
+ * are made when the output pointers are not NULL. */
+int l3d_affinity_sparse(l3d_ctx* ctx, int sort_by_row, float normalization_factor, float* entries_xyzw,
+                        int32_t* start_indices, uint32_t cap_entries, uint32_t cap_rows);
+int l3d_get_sparse_device(l3d_ctx* ctx, const void** entries_float4, const void** start_indices_int);
+
 /* Unchanged consumer, provided for convenience: Felzenszwalb-Huttenlocher clustering of A_
  * exactly as L3DPP::performClustering (src/clustering.cc:7-48, include/universe.h:59-117), on
  * the host. */

@@ -1275,6 +1275,37 @@ void orc_get_edges(void* h, int* ij, float* w)
         w[i] = L->A_snapshot[i].w;
     }
 }
+// SparseMatrix::SparseMatrix (sparsematrix.cc:8-61) over arbitrary (i,j,w) triples: std::list::sort with
+// sortCLEdgesByCol / sortCLEdgesByRow (clustering.h:70-78), float4{i,j,w/norm,0}, start index of every
+// row/column or -1.  Stand-alone so that the known-answer tests can feed hand-made edge lists.
+void orc_sparse_matrix(const int* ij, const float* w, int ne, int n, float norm, int sort_by_row, float* entries4,
+                       int* start_indices)
+{
+    struct E {
+        int i, j;
+        float w;
+    };
+    std::list<E> l;
+    for (int e = 0; e < ne; ++e) l.push_back({ij[2 * e], ij[2 * e + 1], w[e]});
+    if (sort_by_row)
+        l.sort([](const E& a, const E& b) { return (a.i < b.i) || (a.i == b.i && a.j < b.j); });
+    else
+        l.sort([](const E& a, const E& b) { return (a.j < b.j) || (a.j == b.j && a.i < b.i); });
+    for (int r = 0; r < n; ++r) start_indices[r] = -1;
+    int pos = 0, current = -1;
+    for (const E& e : l) {
+        entries4[4 * pos + 0] = (float)e.i;
+        entries4[4 * pos + 1] = (float)e.j;
+        entries4[4 * pos + 2] = e.w / norm;
+        entries4[4 * pos + 3] = 0.0f;
+        const int rc = sort_by_row ? e.i : e.j;
+        if (current != rc) {
+            start_indices[rc] = pos;
+            current = rc;
+        }
+        ++pos;
+    }
+}
 int orc_num_local(void* h) { return (int)((Line3D*)h)->local2global_snapshot.size(); }
 void orc_get_local2global(void* h, uint32_t* cam_seg)
 {

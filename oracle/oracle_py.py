@@ -265,6 +265,16 @@ def run_scene(scene, threads=0, snapshot=True, reconstruct=True):
     return o
 
 
+def sparse_matrix(ij, w, n, norm=1.0, sort_by_row=False):
+    """SparseMatrix::SparseMatrix (reference src/sparsematrix.cc:8-61): (entries float4[E], start_indices int[n])."""
+    ij = np.ascontiguousarray(ij, dtype=np.int32)
+    w = np.ascontiguousarray(w, dtype=np.float32)
+    ent = np.zeros((max(len(w), 1), 4), dtype=np.float32)
+    st = np.zeros(max(n, 1), dtype=np.int32)
+    lib().orc_sparse_matrix(_p(ij), _p(w), len(w), int(n), C.c_float(norm), int(bool(sort_by_row)), _p(ent), _p(st))
+    return ent[:len(w)], st[:n]
+
+
 def score_packed(lines, matches, ranges, regs_tgt, RtKinv, Cc, two_sigA_sqr, k, min_sim=0.5):
     """Oracle restatement of scoringCPU's new-match branch over scoringGPU's packed buffers."""
     L = lib()

@@ -117,3 +117,24 @@ def test_c2_sharded_equals_unsharded(api, c2, c2_run):
     ref = _digest(c2_run, c2)
     for s in shards:
         assert _digest(s, c2) == ref
+
+
+def test_c2_sparse_matrix_layout(api, oracle, c2_run):
+    """A_ of config 2 in the SparseMatrix layout (src/sparsematrix.cc:8-61)."""
+    ij, w = c2_run.edges()
+    n = len(c2_run.local2global())
+    ge, gs = c2_run.sparse_matrix(False, 1.0)
+    oe, os_ = oracle.sparse_matrix(ij, w, n, 1.0, False)
+    assert len(ge) == len(w) > 20000 and ge.tobytes() == oe.tobytes() and (gs == os_).all()
+
+
+def test_c3_full_stream_bit_exact(api, oracle, scene_mod):
+    """BASELINE config 3 at its full size: 300 key frames, 640x480, 1000 segments each, window of 20,
+    10 neighbours from shared world points, one new key frame per cycle, poses re-estimated every
+    cycle.  Every one of the 296 cycles is compared with the oracle (new pairs, neighbour sets,
+    filtered lists, k / median depth, hypotheses, A_, local ids, cluster ids)."""
+    import stream_utils
+    st = scene_mod.make_stream(n_keyframes=300, n_seg=1000, window=20, nbrs=10, jitter=0.3)
+    tot = stream_utils.run_lockstep(api, oracle, st, check_scored=False)
+    assert tot["cycles"] == 296 and tot["deleted"] >= 280 and tot["pairs"] > 2500
+    assert tot["tests"] > 2.5e9

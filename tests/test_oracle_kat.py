@@ -150,3 +150,18 @@ def test_serial_and_parallel_oracle_identical(oracle, scene_mod):
     assert (a.cluster_ids() == b.cluster_ids()).all()
     for v in sc.views:
         assert a.lists(v.cam_id, 0)[1].tobytes() == b.lists(v.cam_id, 0)[1].tobytes()
+
+
+def test_sparse_matrix_known_answer(oracle):
+    """SparseMatrix::SparseMatrix (src/sparsematrix.cc:8-61) on a hand-made A_: 4 nodes, node 3 isolated.
+    Column sort = (j, i) ascending; start index of a column = position of its first entry, -1 if empty."""
+    ij = np.array([[0, 1], [1, 0], [2, 0], [0, 2], [2, 1], [1, 2]], dtype=np.int32)
+    w = np.array([0.9, 0.9, 0.6, 0.6, 0.75, 0.75], dtype=np.float32)
+    ent, st = oracle.sparse_matrix(ij, w, 4)
+    assert ent[:, :2].tolist() == [[1, 0], [2, 0], [0, 1], [2, 1], [0, 2], [1, 2]]
+    assert ent[:, 2].tolist() == [np.float32(0.9), np.float32(0.6), np.float32(0.9), np.float32(0.75),
+                                  np.float32(0.6), np.float32(0.75)]
+    assert (ent[:, 3] == 0).all() and st.tolist() == [0, 2, 4, -1]
+    ent, st = oracle.sparse_matrix(ij, w, 4, norm=3.0, sort_by_row=True)
+    assert ent[:, :2].tolist() == [[0, 1], [0, 2], [1, 0], [1, 2], [2, 0], [2, 1]]
+    assert ent[0, 2] == np.float32(0.9) / np.float32(3.0) and st.tolist() == [0, 2, 4, -1]

@@ -140,3 +140,19 @@ def test_sharded_run_matches_the_oracle(api, oracle, scene_mod, world):
         assert sizes["edges"] > 0 and sizes["clusters"] > 1
         for k in ("forward_matches", "scored_entries", "sim_evals", "filtered_entries", "num_entries"):
             assert s.counts()[k] == ref.counts()[k], k
+
+
+def test_sparse_matrix_layout_matches_the_oracle(api, oracle, scene_mod):
+    """A_ in the SparseMatrix layout (src/sparsematrix.cc:8-61), column- and row-sorted, with and
+    without normalisation, against the oracle's restatement on the same edge list."""
+    sc = scene_mod.make_scene("tiny")
+    l3 = api.run_scene(sc)
+    ij, w = l3.edges()
+    n = len(l3.local2global())
+    assert len(w) > 100
+    for by_row, norm in ((False, 1.0), (True, 1.0), (False, 2.5)):
+        ge, gs = l3.sparse_matrix(by_row, norm)
+        oe, os_ = oracle.sparse_matrix(ij, w, n, norm, by_row)
+        assert ge.tobytes() == oe.tobytes() and (gs == os_).all()
+        key = ge[:, 0 if by_row else 1]
+        assert (np.diff(key) >= 0).all()
