@@ -107,6 +107,7 @@ def lib():
         L.l3d_affinity.argtypes = [vp]
         L.l3d_affinity_sparse.argtypes = [vp, C.c_int, f32, vp, vp, u32, u32]
         L.l3d_get_sparse_device.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
+        L.l3d_find_collinear.argtypes = [vp, vp, u32, f32, vp, u64]
         L.l3d_cluster.argtypes = [vp]
         L.l3d_cluster_edges.argtypes = [vp, vp, u32, u32, vp]
         L.l3d_get_counts.argtypes = [vp, C.POINTER(Counts)]
@@ -210,6 +211,15 @@ class Context:
                                           _p(scores), _p(regs), _p(M), _p(Cc), float(two_sigA_sqr), float(k),
                                           float(min_similarity)))
         return scores
+
+    def find_collinear(self, lines, dist_t, row_stride=None):
+        """find_collinear_segments_GPU (include/cudawrapper.h:84-86): (n, n) int8 table."""
+        lines = np.ascontiguousarray(lines, dtype=np.float32).reshape(-1, 4)
+        n = lines.shape[0]
+        stride = int(row_stride or n)
+        buf = np.zeros((max(n, 1), stride), dtype=np.int8)
+        self._ck(self.L.l3d_find_collinear(self.h, _p(lines), n, float(dist_t), _p(buf), stride))
+        return buf[:n, :n]
 
     # ---- device math hooks ----
     def test_expf(self, x):

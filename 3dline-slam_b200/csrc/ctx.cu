@@ -1080,6 +1080,25 @@ int l3d_affinity(l3d_ctx* ctx)
     return l3d_affinity_ids(ctx);
 }
 
+// drop-in for L3DPP::find_collinear_segments_GPU (include/cudawrapper.h:84-86): host arrays in and out,
+// blocking.  buffer[r * row_stride_bytes + c] = 1 iff segment c is collinear to segment r.
+int l3d_find_collinear(l3d_ctx* ctx, const float* lines_xyxy, uint32_t n, float dist_t, char* buffer,
+                       uint64_t row_stride_bytes)
+{
+    if (!ctx || (n && (!lines_xyxy || !buffer))) return fail(L3D_ERR_ARG, "NULL argument");
+    if (n == 0) return L3D_OK;
+    if (row_stride_bytes < n) return fail(L3D_ERR_ARG, "row stride %llu < %u", (unsigned long long)row_stride_bytes, n);
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    CK(ctx->d_collin_lines.ensure(n));  // own staging: the resident scene / stream tables stay untouched
+    CK(ctx->d_collin.ensure((size_t)n * n));
+    CK(cudaMemcpyAsync(ctx->d_collin_lines.p, lines_xyxy, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, st));
+    ctx->cnt.gpu_launches += launch_k5_collinear(ctx->d_collin_lines.p, n, dist_t, ctx->d_collin.p, n, st);
+    CK(cudaMemcpy2DAsync(buffer, row_stride_bytes, ctx->d_collin.p, n, n, n, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return L3D_OK;
+}
+
 // SparseMatrix::SparseMatrix (src/sparsematrix.cc:8-61) of A_, built on the device and kept there for a
 // device-side consumer (l3d_get_sparse_device); the host copies are optional.
 int l3d_affinity_sparse(l3d_ctx* ctx, int sort_by_row, float normalization_factor, float* entries_xyzw,

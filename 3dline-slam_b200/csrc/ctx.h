@@ -53,6 +53,7 @@ int launch_k4_edges_write(const ViewDev*, uint32_t, const uint32_t*, const uint3
 int launch_k4_ids(const void*, uint32_t, uint32_t*, uint32_t*, uint32_t*, uint32_t*, size_t, int2*, float*,
                   uint32_t*, cudaStream_t);
 size_t k4_edge_bytes();
+int launch_k5_collinear(const float4*, uint32_t, float, char*, size_t, cudaStream_t);
 int launch_k4_sparse(const int2*, const float*, uint32_t, uint32_t, int, float, uint32_t*, uint32_t*, uint32_t*, uint2*,
                      uint32_t*, size_t, float4*, int*, cudaStream_t);
 int launch_test_expf(const float*, float*, uint32_t, cudaStream_t);
@@ -299,6 +300,8 @@ struct l3d_ctx {
     DevBuf<float4> d_sp_entries;
     DevBuf<int> d_sp_start;
     bool sparse_ready = false;
+    DevBuf<char> d_collin;
+    DevBuf<float4> d_collin_lines;
     // host results
     std::vector<int32_t> cluster_ids;
 

@@ -146,12 +146,23 @@ void score_matches_GPU(DataArray<float4>* lines, DataArray<float4>* matches, Dat
     if (rc != L3D_OK) std::cerr << "score_matches_GPU: " << l3d_last_error() << std::endl;
 }
 
-// include/cudawrapper.h:84-89 -- disabled in the reference configuration (collinearity=-1,
-// diffusion=false: include/L3DPPing.h:80-82); kept as loud stubs so the reference links.
-void find_collinear_segments_GPU(DataArray<char>*, DataArray<float4>*, const float)
+// include/cudawrapper.h:84-86, as View::findCollinGPU calls it (src/view.cc:203-236): C is N x N,
+// C(c, r) = 1 iff segment c is collinear to segment r (View::findCollinCPU, src/view.cc:238-293)
+void find_collinear_segments_GPU(DataArray<char>* C, DataArray<float4>* lines, const float dist_t)
 {
-    std::cerr << "find_collinear_segments_GPU: not part of the l3dpp-b200 path (collinearity is off)" << std::endl;
+    l3d_ctx* ctx = shim_ctx();
+    if (!ctx || !C || !lines || lines->width() == 0) return;
+    const unsigned int n = lines->width();
+    if (C->width() < n || C->height() < n) {
+        std::cerr << "find_collinear_segments_GPU: buffer smaller than " << n << " x " << n << std::endl;
+        return;
+    }
+    const uint64_t stride = n > 1 ? (uint64_t)(C->dataCPU(0, 1) - C->dataCPU(0, 0)) : n;
+    if (l3d_find_collinear(ctx, (const float*)lines->dataCPU(0, 0), n, dist_t, C->dataCPU(0, 0), stride) != L3D_OK)
+        std::cerr << "l3dpp_b200: " << l3d_last_error() << std::endl;
 }
+// include/cudawrapper.h:88-89 -- diffusion is off in the reference configuration
+// (include/L3DPPing.h:80) and the kernel's source is not part of the reference tree; loud stub.
 void replicator_dynamics_diffusion_GPU(SparseMatrix*&, const std::string)
 {
     std::cerr << "replicator_dynamics_diffusion_GPU: not part of the l3dpp-b200 path (RDD is off)" << std::endl;

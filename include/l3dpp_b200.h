@@ -181,6 +181,14 @@ int l3d_neighbors_from_worldpoints(const l3d_view* views, uint32_t n_views, cons
 /* visual neighbours of a view as used by the last l3d_match_images (camera ids, ascending) */
 int l3d_get_neighbors(l3d_ctx* ctx, uint32_t cam_id, uint32_t* out, uint32_t cap, uint32_t* count);
 
+/* replaces L3DPP::find_collinear_segments_GPU (include/cudawrapper.h:84-86) as View::findCollinGPU
+ * calls it (src/view.cc:203-236): the N x N byte table of a view's collinear segments, computed like
+ * View::findCollinCPU (src/view.cc:238-293).  buffer[r * row_stride_bytes + c] = 1 iff c is collinear to
+ * r (the reference reads buffer->dataCPU(c, r)).  Host arrays, blocking.  (The affinity stage with
+ * collinearity_t > 0, src/line3D.cc:2328-2396, is not part of this build: the reference runs with -1.) */
+int l3d_find_collinear(l3d_ctx* ctx, const float* lines_xyxy, uint32_t n, float dist_t, char* buffer,
+                       uint64_t row_stride_bytes);
+
 /* ---- incremental (key-frame stream) mode: the calls L3DPPing::Run (src/L3DPPing.cpp:98-236) makes
  * on its Line3D object between two reconstructions.  The context keeps what Line3D keeps from one
  * matchImages to the next: matched_ (a view pair is matched once), processed_, the filtered match

@@ -1306,6 +1306,36 @@ void orc_sparse_matrix(const int* ij, const float* w, int ne, int n, float norm,
         ++pos;
     }
 }
+// View::findCollinCPU (view.cc:238-293) with View::pointOnSegment (view.cc:321-327) and
+// View::distance_point2line_2D (view.cc:296-299): out[r*n + c] = 1 iff segment c is collinear to r
+// (no mutual overlap, all four point-to-line distances below dist_t).
+void orc_find_collinear(const float* lines, int n, float dist_t, char* out)
+{
+    auto on_seg = [](const V3& p1, const V3& p2, const V3& x) {
+        const double v1x = p1.x - x.x, v1y = p1.y - x.y, v2x = p2.x - x.x, v2y = p2.y - x.y;
+        return (v1x * v2x + v1y * v2y) < EPS;
+    };
+    auto dist = [](const V3& l, const V3& p) {
+        return (float)std::fabs((l.x * p.x + l.y * p.y + l.z) / sqrtf((float)(l.x * l.x + l.y * l.y)));
+    };
+#pragma omp parallel for schedule(dynamic, 8)
+    for (int r = 0; r < n; ++r) {
+        const V3 p0 = {(double)lines[4 * r], (double)lines[4 * r + 1], 1.0};
+        const V3 p1 = {(double)lines[4 * r + 2], (double)lines[4 * r + 3], 1.0};
+        const V3 line1 = cross(p0, p1);
+        for (int c = 0; c < n; ++c) {
+            out[(size_t)r * n + c] = 0;
+            if (r == c) continue;
+            const V3 q0 = {(double)lines[4 * c], (double)lines[4 * c + 1], 1.0};
+            const V3 q1 = {(double)lines[4 * c + 2], (double)lines[4 * c + 3], 1.0};
+            const V3 line2 = cross(q0, q1);
+            if (on_seg(p0, p1, q0) || on_seg(p0, p1, q1) || on_seg(q0, q1, p0) || on_seg(q0, q1, p1)) continue;
+            const float d1 = (float)std::fmax((double)dist(line1, q0), (double)dist(line1, q1));
+            const float d2 = (float)std::fmax((double)dist(line2, p0), (double)dist(line2, p1));
+            if ((float)std::fmax((double)d1, (double)d2) < dist_t) out[(size_t)r * n + c] = 1;
+        }
+    }
+}
 int orc_num_local(void* h) { return (int)((Line3D*)h)->local2global_snapshot.size(); }
 void orc_get_local2global(void* h, uint32_t* cam_seg)
 {

@@ -275,6 +275,15 @@ def sparse_matrix(ij, w, n, norm=1.0, sort_by_row=False):
     return ent[:len(w)], st[:n]
 
 
+def find_collinear(lines, dist_t):
+    """View::findCollinCPU (reference src/view.cc:238-293): (n,n) int8, [r,c] = 1 iff c is collinear to r."""
+    lines = np.ascontiguousarray(lines, dtype=np.float32).reshape(-1, 4)
+    n = lines.shape[0]
+    out = np.zeros((n, n), dtype=np.int8)
+    lib().orc_find_collinear(_p(lines), n, C.c_float(dist_t), _p(out))
+    return out
+
+
 def score_packed(lines, matches, ranges, regs_tgt, RtKinv, Cc, two_sigA_sqr, k, min_sim=0.5):
     """Oracle restatement of scoringCPU's new-match branch over scoringGPU's packed buffers."""
     L = lib()

@@ -149,3 +149,24 @@ def test_error_behaviour_mirrors_addImage(api, scene_mod):
     assert b"cannot be mixed" in L.l3d_last_error()
     with pytest.raises(api.L3DError):
         api.Line3D("", False, 640, 3000, False, False)   # use_GPU=False: there is no CPU path
+
+
+def test_find_collinear_equals_findCollinCPU(api, oracle, scene_mod):
+    """l3d_find_collinear (drop-in for find_collinear_segments_GPU, include/cudawrapper.h:84-86) against
+    the oracle's View::findCollinCPU on a synthetic view (many truly collinear fragments: projected
+    world segments split in two) and with a padded row stride."""
+    sc = scene_mod.make_scene("tiny")
+    rng = np.random.default_rng(5)
+    segs = sc.views[0].segs.copy()
+    # split the first 60 segments into two collinear fragments with a gap, jittered by a fraction of a pixel
+    a, b = segs[:60, :2], segs[:60, 2:]
+    frag1 = np.concatenate([a, a + 0.4 * (b - a)], axis=1)
+    frag2 = np.concatenate([a + 0.6 * (b - a), b], axis=1) + rng.normal(0, 0.3, size=(60, 4)).astype(np.float32)
+    lines = np.concatenate([frag1, frag2, segs[60:]]).astype(np.float32)[:211]     # odd size on purpose
+    ctx = api.Context()
+    for t in (0.5, 2.0):
+        want = oracle.find_collinear(lines, t)
+        got = ctx.find_collinear(lines, t)
+        assert (got == want).all()
+        assert (ctx.find_collinear(lines, t, row_stride=224) == want).all()
+    assert want.sum() > 60

@@ -165,3 +165,21 @@ def test_sparse_matrix_known_answer(oracle):
     ent, st = oracle.sparse_matrix(ij, w, 4, norm=3.0, sort_by_row=True)
     assert ent[:, :2].tolist() == [[0, 1], [0, 2], [1, 0], [1, 2], [2, 0], [2, 1]]
     assert ent[0, 2] == np.float32(0.9) / np.float32(3.0) and st.tolist() == [0, 2, 4, -1]
+
+
+def test_find_collinear_known_answer(oracle):
+    """View::findCollinCPU (src/view.cc:238-293) on hand-made segments:
+    0: (0,0)-(10,0); 1: (20,0)-(30,0): same line, gap -> collinear with 0;
+    2: (5,0)-(25,0): an endpoint of it lies between the endpoints of 0 and of 1 (dot test <= 0) -> overlap,
+       never collinear;
+    3: (20,1.5)-(30,1.5): 1.5 px beside 1 -- the overlap test is a 2-D dot product, (p1-x).(p2-x) = 2.25 > 0
+       for both of its endpoints, so it does NOT count as overlapping 1, and all distances are 1.5;
+    4: (20,0)-(30,2): shares an endpoint with 1 (dot = 0 -> overlap), crosses 3 (dot = -0.75), and the
+       endpoints of 0 are 3.9 px / 1.96 px from its line."""
+    L = np.array([[0, 0, 10, 0], [20, 0, 30, 0], [5, 0, 25, 0], [20, 1.5, 30, 1.5], [20, 0, 30, 2]], dtype=np.float32)
+    t2 = oracle.find_collinear(L, 2.0)
+    assert t2.tolist() == [[0, 1, 0, 1, 0], [1, 0, 0, 1, 0], [0, 0, 0, 0, 0], [1, 1, 0, 0, 0], [0, 0, 0, 0, 0]]
+    assert (t2 == t2.T).all()                       # max(d1, d2) is symmetric in the pair
+    t1 = oracle.find_collinear(L, 1.0)              # the 1.5 px neighbours drop out
+    assert t1.tolist() == [[0, 1, 0, 0, 0], [1, 0, 0, 0, 0], [0] * 5, [0] * 5, [0] * 5]
+    assert (oracle.find_collinear(L, 4.0)[0] == [0, 1, 0, 1, 1]).all()   # 3.92 px < 4 px: segment 4 joins
