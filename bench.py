@@ -172,7 +172,7 @@ def bench_stream(args, scene_mod):
         return
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
-    fill = 24  # cycles until the window of 20 is full and sliding
+    fill = int(os.environ.get("L3D_C3_FILL", "24"))  # cycles until the window of 20 is full and sliding (profiling runs shorten it)
     W, K = max(args.warmup, 3), min(args.steps, 100)
     st = scene_mod.make_stream(n_keyframes=5 + fill + W + K, n_seg=1000, window=20, nbrs=10, jitter=0.3)
     l3, calls = stream_utils.cuda_driver(api, st)
