@@ -111,10 +111,43 @@ void visual_neighbors_from_worldpoints(const std::vector<const Camera*>& cams, c
 {
     const uint32_t V = (uint32_t)cams.size();
     out.assign(V, std::vector<uint32_t>());
-    // worldpoints2views_: one entry per observation, in view order (the order addImage ran)
-    std::unordered_map<uint32_t, std::vector<uint32_t>> wp2views;
-    for (uint32_t v = 0; v < V; ++v)
-        for (uint32_t wp : wps[v]) wp2views[wp].push_back(v);
+    // worldpoints2views_ as a flat inverted index: the observations (world point, view) grouped by
+    // world point; a view's walk over its own list and the groups of its points counts what the
+    // reference's two nested list walks count (src/line3D.cc:733-752), without a hash map.
+    size_t n_obs = 0;
+    uint32_t max_wp = 0;
+    for (uint32_t v = 0; v < V; ++v) {
+        n_obs += wps[v].size();
+        for (uint32_t wp : wps[v]) max_wp = std::max(max_wp, wp);
+    }
+    if (!n_obs) return;
+    std::vector<uint32_t> by_wp(n_obs);  // views, grouped by world point
+    std::vector<uint32_t> start;         // group g = by_wp[start[g] .. start[g+1])
+    std::vector<uint32_t> group_wp;      // sparse ids only: the world point of every group, ascending
+    const bool dense = (size_t)max_wp < 8 * n_obs + 4096;
+    if (dense) {  // counting sort, group index = world point id
+        start.assign((size_t)max_wp + 2, 0u);
+        for (uint32_t v = 0; v < V; ++v)
+            for (uint32_t wp : wps[v]) ++start[(size_t)wp + 1];
+        for (size_t i = 1; i < start.size(); ++i) start[i] += start[i - 1];
+        std::vector<uint32_t> fill(start.begin(), start.end() - 1);
+        for (uint32_t v = 0; v < V; ++v)
+            for (uint32_t wp : wps[v]) by_wp[fill[wp]++] = v;
+    } else {  // sort the (world point, view) keys
+        std::vector<uint64_t> keys;
+        keys.reserve(n_obs);
+        for (uint32_t v = 0; v < V; ++v)
+            for (uint32_t wp : wps[v]) keys.push_back(((uint64_t)wp << 32) | v);
+        std::sort(keys.begin(), keys.end());
+        start.push_back(0u);
+        for (size_t i = 0; i < keys.size(); ++i) {
+            by_wp[i] = (uint32_t)keys[i];
+            if (i + 1 == keys.size() || (keys[i + 1] >> 32) != (keys[i] >> 32)) {
+                start.push_back((uint32_t)i + 1);
+                group_wp.push_back((uint32_t)(keys[i] >> 32));
+            }
+        }
+    }
     struct VN {
         uint32_t view;
         float score, axis_angle, dist_score;
@@ -123,12 +156,15 @@ void visual_neighbors_from_worldpoints(const std::vector<const Camera*>& cams, c
     for (uint32_t v = 0; v < V; ++v) {
         std::fill(common.begin(), common.end(), 0u);
         bool any = false;
-        for (uint32_t wp : wps[v])
-            for (uint32_t o : wp2views[wp])
-                if (o != v) {
-                    ++common[o];
+        for (uint32_t wp : wps[v]) {
+            const size_t g = dense ? (size_t)wp
+                                   : (size_t)(std::lower_bound(group_wp.begin(), group_wp.end(), wp) - group_wp.begin());
+            for (uint32_t i = start[g]; i < start[g + 1]; ++i)
+                if (by_wp[i] != v) {
+                    ++common[by_wp[i]];
                     any = true;
                 }
+        }
         if (!any) continue;
         const Camera& cv = *cams[v];
         const V3 ray_v = normalized(mul(cv.RtKinv, cv.pp));

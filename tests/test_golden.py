@@ -25,6 +25,13 @@ def test_world_point_neighbours_match_golden_c1(api, oracle):
     got = api.neighbors_from_worldpoints(sc, 10)
     for v in sc.views:
         assert got[v.cam_id] == list(v.neighbors), v.cam_id
+    # sparse world-point ids (the inverted index switches from counting sort to key sort): same choice
+    for v in sc.views:
+        v.worldpoints = [(w * 2654435761 + 12345) % (1 << 32) for w in v.worldpoints]
+    got = api.neighbors_from_worldpoints(sc, 10)
+    for v in sc.views:
+        assert got[v.cam_id] == list(v.neighbors), v.cam_id
+    sc = _c1_with_worldpoints()
     sc.neighbors_by_worldpoints = True
     p = sc.params
     for nn in (2, 5, 16):
