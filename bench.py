@@ -126,6 +126,46 @@ def bench_reference(args, scene_mod):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if args.workload == "c3":
+        # the key-frame stream through the oracle's incremental mode, same cycles as the product's arm
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_py
+        import stream_utils
+        fill = int(os.environ.get("L3D_C3_FILL", "24"))
+        W, K = max(args.warmup, 3), min(args.steps, 40)
+        st = scene_mod.make_stream(n_keyframes=5 + fill + W + K, n_seg=1000, window=20, nbrs=10, jitter=0.3)
+        o, oc = stream_utils.oracle_driver(oracle_py, st)
+        ts, tests = [], []
+        for ci, cy in enumerate(st.cycles):
+            before = o.pair_tests()
+            t0 = time.perf_counter()
+            oc["begin_cycle"]()
+            for cam in cy.deletes:
+                oc["delete"](cam)
+            for v in cy.adds:
+                oc["add"](v, v.worldpoints)
+            for cam, R, t, md, lst in cy.updates:
+                oc["update"](cam, R, t, md, lst)
+            oc["match"](st.params)
+            oc["reconstruct"]()
+            dt = time.perf_counter() - t0
+            if ci >= fill + W and len(ts) < K:
+                ts.append(dt)
+                tests.append(o.pair_tests() - before)
+        cores = oracle_py.lib().orc_max_threads()
+        T = float(np.sum(ts))
+        value = float(np.sum(tests)) / T
+        sample = "the same stream, %d steady-state cycles" % len(ts)
+        print(json.dumps({
+            "impl": "reference", "metric": "segment_pair_tests_per_s", "value": value, "unit": "tests/s",
+            "n_gpus": args.gpus, "steps": len(ts), "warmup": W, "ms_per_step": 1e3 * T / len(ts),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "c3", "window": 20, "segments_per_view": 1000, "neighbours": 10, "sample": sample},
+            "views_per_s": 20.0 * len(ts) / T,
+            "cpu_baseline": {"value": value, "unit": "tests/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "tests/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}))
+        return
     # each step is a bounded sample of the arm's workload: the single-GPU scene of the same generator
     # (at N > 1 the product's scene has N times the views; tests/s of the CPU path does not depend on it)
     scene, sample_name = make_workload(scene_mod, args.workload, 1)

@@ -58,6 +58,24 @@ def test_stream_idle_cycle_is_a_fixed_point(api, scene_mod):
     assert l3.entries().tobytes() == e0.tobytes() and len(e0) > 100
 
 
+def test_stream_delete_everything_then_continue(api, oracle, scene_mod):
+    """Edge cases of the cycle: a cycle that deletes every key frame (nothing to match, no hypotheses,
+    empty A_), then new key frames whose explicit neighbour lists still name the deleted ones (views_
+    keeps them, src/line3D.cc:396-430, so they ARE matched against, with their last pose)."""
+    base = scene_mod.make_stream(n_keyframes=9, n_seg=300, window=9, nbrs=4, jitter=0.2, by_worldpoints=False,
+                                 cull_every=0, init=3, n_world=900)
+    c0, c1, c2, c3 = base.cycles[0], base.cycles[1], base.cycles[2], base.cycles[3]
+    wipe = scene_mod.StreamCycle([0, 1, 2, 3], [], [])
+    # after the wipe: key frames 4 and 5 arrive; their lists name 2 and 3 (deleted) and each other
+    c2.deletes, c3.deletes = [], []
+    c2.updates = [(4, c2.updates[-1][1], c2.updates[-1][2], c2.updates[-1][3], [2, 3, 5])]
+    c3.updates = [(4, c3.updates[-2][1], c3.updates[-2][2], c3.updates[-2][3], [2, 3, 5]),
+                  (5, c3.updates[-1][1], c3.updates[-1][2], c3.updates[-1][3], [3, 4])]
+    base.cycles = [c0, c1, wipe, c2, c3]
+    tot = stream_utils.run_lockstep(api, oracle, base)
+    assert tot["cycles"] == 5 and tot["deleted"] == 4 and tot["pairs"] >= 8
+
+
 def test_stream_errors_mirror_the_reference(api, scene_mod):
     st = scene_mod.make_stream(n_keyframes=6, n_seg=100, window=6, jitter=0.0)
     l3, calls = stream_utils.cuda_driver(api, st)
@@ -71,3 +89,8 @@ def test_stream_errors_mirror_the_reference(api, scene_mod):
         l3.UpdataImage(v.cam_id, v.R, v.t, v.median_depth, v.worldpoints)
     with pytest.raises(api.L3DError, match="has no worldpoints"):
         calls["add"](st.cycles[0].adds[1], [])
+    calls["add"](st.cycles[0].adds[3], st.cycles[0].adds[3].worldpoints)
+    with pytest.raises(api.L3DError, match="ascending order"):
+        calls["add"](st.cycles[0].adds[2], st.cycles[0].adds[2].worldpoints)
+    with pytest.raises(api.L3DError, match="was deleted"):
+        calls["add"](v, v.worldpoints)
