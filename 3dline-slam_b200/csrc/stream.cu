@@ -207,6 +207,12 @@ int stream_match_images(l3d_ctx* ctx, const l3d_params* params)
     // ---- translate(), spatial regularisers of the current views (src/line3D.cc:568-590) ----
     compute_translation(ctx);
     apply_translation(ctx, -1.0);
+    // untranslate() (src/line3D.cc:637) on every way out; a cycle that fails half-way leaves matched_ and the
+    // lists in an undefined state -- the caller starts over with l3d_stream_begin
+    struct Untranslate {
+        l3d_ctx* c;
+        ~Untranslate() { apply_translation(c, +1.0); }
+    } untranslate_on_exit{ctx};
     for (uint32_t v : cur) ctx->views[v].k = ctx->views[v].cam.spatial_regularizer(ctx->prm.sigma_p);
 
     lap("translate+k");
@@ -498,8 +504,6 @@ int stream_match_images(l3d_ctx* ctx, const l3d_params* params)
     ctx->tm.collect();
     const unsigned long long* s64 = (const unsigned long long*)stats.data();
     const uint32_t* s32 = (const uint32_t*)(stats.data() + 16);
-    // untranslate() (src/line3D.cc:637) before any early return
-    apply_translation(ctx, +1.0);
     if (s32[1]) return fail(L3D_ERR_CAPACITY, "internal: stream list arena overflow (%u)", s32[1]);
     if (small[2]) return fail(L3D_ERR_CAPACITY, "more than 8192 hypotheses in one view (median-depth kernel)");
     ctx->cnt.sim_evals = s64[0];

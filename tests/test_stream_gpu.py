@@ -58,6 +58,18 @@ def test_stream_idle_cycle_is_a_fixed_point(api, scene_mod):
     assert l3.entries().tobytes() == e0.tobytes() and len(e0) > 100
 
 
+def test_stream_ragged_segment_counts(api, oracle, scene_mod):
+    """Key frames with different numbers of segments (7 ... 400), including one with fewer segments than
+    a warp and one new key frame per cycle receiving inverse matches into short rows."""
+    st = scene_mod.make_stream(n_keyframes=14, n_seg=400, window=9, nbrs=5, jitter=0.2, n_world=1000, cull_every=4)
+    keep = [400, 7, 333, 129, 400, 31, 257, 64, 400, 199, 33, 400, 150, 65]
+    for cy in st.cycles:
+        for v in cy.adds:
+            v.segs = np.ascontiguousarray(v.segs[:keep[v.cam_id % len(keep)]])
+    tot = stream_utils.run_lockstep(api, oracle, st)
+    assert tot["cycles"] == 10 and tot["entries"] > 300
+
+
 def test_stream_delete_everything_then_continue(api, oracle, scene_mod):
     """Edge cases of the cycle: a cycle that deletes every key frame (nothing to match, no hypotheses,
     empty A_), then new key frames whose explicit neighbour lists still name the deleted ones (views_
