@@ -136,6 +136,7 @@ struct HostView {
     uint32_t filt_total = 0;   // entries that survived the view's last filterMatches
     uint32_t num_wps = 0;      // num_worldpoints_[camID] (kept across cycles)
     bool has_fixed = false;    // fixed_visual_neighbors_ holds the view (set by UpdataImage)
+    bool paired_after_delete = false;  // a later key frame named this deleted view as a neighbour
 };
 
 struct HostPair {

@@ -301,7 +301,14 @@ int stream_match_images(l3d_ctx* ctx, const l3d_params* params)
     ctx->slice_g[0] = 0;
     ctx->slice_row.assign(2, ctx->total_rows);
     ctx->slice_row[0] = 0;
-    ctx->view_needed.assign(V, 1u);
+    // K0 refreshes the per-segment tables of the current views (their poses moved) and of the deleted views
+    // that were matched against after their deletion (explicit-neighbour mode only: later cycles still
+    // re-triangulate hypotheses whose target they are); the tables of the other deleted views are dead
+    for (uint32_t p = 0; p < P; ++p)
+        if (!ctx->views[ctx->pairs[p].tgt].current) ctx->views[ctx->pairs[p].tgt].paired_after_delete = true;
+    ctx->view_needed.assign(V, 0u);
+    for (uint32_t v = 0; v < V; ++v)
+        ctx->view_needed[v] = (ctx->views[v].current || ctx->views[v].paired_after_delete) ? 1u : 0u;
     ctx->cnt.num_pairs = ctx->cnt.num_pairs_local = P;
     ctx->cnt.num_views = (uint32_t)cur.size();
     plan_batches(ctx);
