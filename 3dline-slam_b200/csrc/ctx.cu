@@ -34,6 +34,12 @@ int l3d_ctx_create(l3d_ctx** out, int device)
     CK(cudaSetDevice(device));
     l3d_ctx* c = new l3d_ctx();
     c->device = device;
+    if (cudaMallocHost((void**)&c->rb, (size_t)1 << 20) == cudaSuccess) {
+        c->rb_cap = (size_t)1 << 20;
+    } else {
+        delete c;
+        return fail(L3D_ERR_CUDA, "cudaMallocHost of the read-back scratch failed");
+    }
     *out = c;
     return L3D_OK;
 }
@@ -275,8 +281,13 @@ int refresh_pair_totals(l3d_ctx* ctx)
     pair_totals_kernel<<<(P + 255) / 256, 256, 0, st>>>(ctx->d_pairs.p, P, ctx->d_fwd_off.p, ctx->d_fwd_cnt.p,
                                                         ctx->d_scan_tmp.p);
     ctx->cnt.gpu_launches++;
-    std::vector<uint32_t> tot(P);
-    CK(cudaMemcpyAsync(tot.data(), ctx->d_scan_tmp.p, P * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    std::vector<uint32_t> tot_pageable;
+    uint32_t* tot = ctx->rb_at<uint32_t>(l3d_ctx::RB_BIG);
+    if (!ctx->rb_fits((size_t)P * 4)) {
+        tot_pageable.resize(P);
+        tot = tot_pageable.data();
+    }
+    CK(cudaMemcpyAsync(tot, ctx->d_scan_tmp.p, P * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     uint64_t run = 0;
     for (uint32_t p = 0; p < P; ++p) {
@@ -564,9 +575,10 @@ int run_stage12_batches(l3d_ctx* ctx)
         ctx->cnt.gpu_launches += launch_scan_u32(ctx->d_cand_cnt.p, ctx->d_cand_off.p, b.n_rows, ctx->d_scan.p,
                                                  ctx->d_scan.cap, st);
         ctx->tm.end(e1, st);
-        uint32_t n_cand = 0;
-        CK(cudaMemcpyAsync(&n_cand, ctx->d_cand_off.p + b.n_rows, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(ctx->rb_at<uint32_t>(l3d_ctx::RB_NCAND), ctx->d_cand_off.p + b.n_rows, sizeof(uint32_t),
+                           cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
+        const uint32_t n_cand = *ctx->rb_at<uint32_t>(l3d_ctx::RB_NCAND);
         ctx->cnt.candidates += n_cand;
         // K2
         CK(grow(ctx->d_heap, (size_t)n_cand + 1));
@@ -581,9 +593,10 @@ int run_stage12_batches(l3d_ctx* ctx)
                             ctx->prm.max_image_width, ctx->raw_mode ? 0 : 1, b.max_tgt, st);
         ctx->cnt.gpu_launches +=
             launch_scan_u32(ctx->d_fin_cnt.p, ctx->d_fin_off.p, b.n_rows, ctx->d_scan.p, ctx->d_scan.cap, st);
-        uint32_t n_fin = 0;
-        CK(cudaMemcpyAsync(&n_fin, ctx->d_fin_off.p + b.n_rows, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(ctx->rb_at<uint32_t>(l3d_ctx::RB_NFIN), ctx->d_fin_off.p + b.n_rows, sizeof(uint32_t),
+                           cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
+        const uint32_t n_fin = *ctx->rb_at<uint32_t>(l3d_ctx::RB_NFIN);
         if ((uint64_t)rec_base + n_fin > 0xfffffff0ull) return fail(L3D_ERR_CAPACITY, "too many forward matches");
         CK(grow(ctx->d_fwd_rec, (size_t)rec_base + n_fin, rec_base, st));
         ctx->cnt.gpu_launches +=
@@ -756,9 +769,9 @@ int l3d_score_build(l3d_ctx* ctx)
     uint32_t maxm = (uint32_t)k3_max_staged();
     bool big_rows = true;
     if (ctx->k3_list_max == 0 || ctx->force_list_max) {
-        uint32_t dev_max = 0;  // WfStats::max_list
-        CK(cudaMemcpyAsync(&dev_max, ctx->d_stats.p + 36, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(ctx->rb_at<uint32_t>(l3d_ctx::RB_DEVMAX), ctx->d_stats.p + 36, 4, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
+        const uint32_t dev_max = *ctx->rb_at<uint32_t>(l3d_ctx::RB_DEVMAX);  // WfStats::max_list
         ctx->k3_list_max = std::max(dev_max, 1u);
         ctx->force_list_max = false;
     }
@@ -877,20 +890,28 @@ int score_hypotheses_ready(l3d_ctx* ctx, bool* prog_overflow, uint32_t* prog_nee
     ctx->cnt.gpu_launches += launch_k4_has(ctx->d_entries.p, S, ctx->d_has.p, st);
     ctx->cnt.gpu_launches += launch_scan_u32(ctx->d_has.p, ctx->d_entry_idx.p, S, ctx->d_scan.p, ctx->d_scan.cap, st);
     ctx->cnt.gpu_launches += launch_k4_median(ctx->d_views.p, V, ctx->d_entries.p, ctx->d_small.p + 2, st);
-    uint32_t small[4] = {0, 0, 0, 0};
-    uint32_t n_entries = 0;
-    std::vector<unsigned char> acc(k3_wf_stats_bytes());
-    std::vector<ViewDev> vd(V);
-    CK(cudaMemcpyAsync(small, ctx->d_small.p, sizeof(small), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(&n_entries, ctx->d_entry_idx.p + S, 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(acc.data(), ctx->d_stats.p, acc.size(), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(vd.data(), ctx->d_views.p, V * sizeof(ViewDev), cudaMemcpyDeviceToHost, st));
+    // read-backs into the pinned scratch (ctx.h); the view table falls back to pageable memory when it is large
+    uint32_t* small = ctx->rb_at<uint32_t>(l3d_ctx::RB_SMALL);
+    unsigned char* acc = ctx->rb_at<unsigned char>(l3d_ctx::RB_STATS);
+    static_assert(l3d_ctx::RB_NEDGES - l3d_ctx::RB_STATS >= 256, "stats slot");
+    if (k3_wf_stats_bytes() > 256) return fail(L3D_ERR_STATE, "internal: stats larger than their read-back slot");
+    std::vector<ViewDev> vd_pageable;
+    ViewDev* vd = ctx->rb_at<ViewDev>(l3d_ctx::RB_BIG);
+    if (!ctx->rb_fits((size_t)V * sizeof(ViewDev))) {
+        vd_pageable.resize(V);
+        vd = vd_pageable.data();
+    }
+    CK(cudaMemcpyAsync(small, ctx->d_small.p, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(ctx->rb_at<uint32_t>(l3d_ctx::RB_NENT), ctx->d_entry_idx.p + S, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(acc, ctx->d_stats.p, k3_wf_stats_bytes(), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(vd, ctx->d_views.p, V * sizeof(ViewDev), cudaMemcpyDeviceToHost, st));
     ctx->tm.end(ev, st);
     if (ctx->ev_total3) ctx->tm.end(ctx->ev_total3, st);
     ctx->ev_total3 = nullptr;
     CK(cudaStreamSynchronize(st));
-    const unsigned long long* a64 = (const unsigned long long*)acc.data();
-    const uint32_t* a32 = (const uint32_t*)(acc.data() + 16);
+    const uint32_t n_entries = *ctx->rb_at<uint32_t>(l3d_ctx::RB_NENT);
+    const unsigned long long* a64 = (const unsigned long long*)acc;
+    const uint32_t* a32 = (const uint32_t*)(acc + 16);
     if (prog_overflow) {
         *prog_overflow = (a32[2] & 4u) != 0;
         *prog_needed = a32[3];
@@ -1014,14 +1035,14 @@ int l3d_affinity_edges(l3d_ctx* ctx)
     ctx->cnt.gpu_launches += launch_scan_u32(ctx->d_E_cnt.p, ctx->d_E_off.p, S, ctx->d_scan.p, ctx->d_scan.cap, st);
     // every filtered list entry yields at most one edge: size the store from that bound and read the
     // count back while the write kernel runs
-    uint32_t n_edges = 0;
     CK(ctx->d_edges.ensure((nf + 1) * k4_edge_bytes()));
-    CK(cudaMemcpyAsync(&n_edges, ctx->d_E_off.p + S, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(ctx->rb_at<uint32_t>(l3d_ctx::RB_NEDGES), ctx->d_E_off.p + S, 4, cudaMemcpyDeviceToHost, st));
     ctx->cnt.gpu_launches +=
         launch_k4_edges_write(ctx->d_views.p, S, ctx->d_filt_off.p, ctx->d_filt_cnt.p, filt, ctx->d_filt_sim.p,
                               ctx->d_E_off.p, ctx->d_edges.p, g_lo, g_hi, st);
     ctx->tm.end(ev, st);
     CK(cudaStreamSynchronize(st));
+    const uint32_t n_edges = *ctx->rb_at<uint32_t>(l3d_ctx::RB_NEDGES);
     ctx->n_edges_local = n_edges;
     ctx->stage4_phase = 1;
     return L3D_OK;
@@ -1055,7 +1076,8 @@ int l3d_affinity_ids(l3d_ctx* ctx)
         ctx->cnt.gpu_launches +=
             launch_k4_ids(edges, n_edges, ctx->d_first_touch.p, ctx->d_flags.p, ctx->d_flag_scan.p, ctx->d_scan.p,
                           ctx->d_scan.cap, ctx->d_A_ij.p, ctx->d_A_w.p, ctx->d_l2g.p, st);
-        CK(cudaMemcpyAsync(&n_local, ctx->d_flag_scan.p + 2 * (size_t)n_edges, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(ctx->rb_at<uint32_t>(l3d_ctx::RB_NLOCAL), ctx->d_flag_scan.p + 2 * (size_t)n_edges, 4,
+                           cudaMemcpyDeviceToHost, st));
     }
     ctx->tm.end(ev, st);
     if (ctx->ev_total4) ctx->tm.end(ctx->ev_total4, st);
@@ -1063,6 +1085,7 @@ int l3d_affinity_ids(l3d_ctx* ctx)
     CK(cudaStreamSynchronize(st));
     ctx->tm.collect();
     ctx->cnt.num_edges = 2 * n_edges;  // A_ holds both directions
+    if (n_edges) n_local = *ctx->rb_at<uint32_t>(l3d_ctx::RB_NLOCAL);
     ctx->cnt.num_local_ids = n_local;
     apply_translation(ctx, +1.0);  // untranslate() (src/line3D.cc:2140)
     ctx->stage = 3;

@@ -219,9 +219,20 @@ struct l3d_ctx {
 
     void* pinned = nullptr;  // pinned host staging of the segment upload
     size_t pinned_cap = 0;
+    // pinned read-back scratch: the small device->host copies a step synchronises on (counts, cursors,
+    // per-pair totals, the view table) land here -- a pageable target costs an extra staging hop each time
+    unsigned char* rb = nullptr;  // allocated by l3d_ctx_create; a context built on the stack (l3d_match_lines)
+    size_t rb_cap = 0;            // reads back into the pageable fallback below
+    unsigned char rb_fallback[4096] = {0};
+    enum { RB_NCAND = 0, RB_NFIN = 8, RB_DEVMAX = 16, RB_SMALL = 32, RB_NENT = 64, RB_STATS = 128, RB_NEDGES = 512,
+           RB_NLOCAL = 520, RB_BIG = 4096 };
+    template <typename T>
+    T* rb_at(size_t off) { return reinterpret_cast<T*>((rb ? rb : rb_fallback) + off); }
+    bool rb_fits(size_t bytes) const { return rb && RB_BIG + bytes <= rb_cap; }
     ~l3d_ctx()
     {
         if (pinned) cudaFreeHost(pinned);
+        if (rb) cudaFreeHost(rb);
     }
 
     // device tables

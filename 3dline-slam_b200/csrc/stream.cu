@@ -494,23 +494,32 @@ int stream_match_images(l3d_ctx* ctx, const l3d_params* params)
                                                           ctx->d_planes.p, ctx->d_entries.p, st);
     ctx->cnt.gpu_launches += launch_k4_has(ctx->d_entries.p, S, ctx->d_has.p, st);
     ctx->cnt.gpu_launches += launch_scan_u32(ctx->d_has.p, ctx->d_entry_idx.p, S, ctx->d_scan.p, ctx->d_scan.cap, st);
-    uint32_t small[4] = {0, 0, 0, 0}, n_entries = 0;
-    std::vector<ViewDev> vd(V);
-    std::vector<uint32_t> vtot(V);
-    std::vector<unsigned char> stats(stream_stats_bytes());
-    CK(cudaMemcpyAsync(small, ctx->d_small.p, sizeof(small), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(&n_entries, ctx->d_entry_idx.p + S, 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(vd.data(), ctx->d_views.p, V * sizeof(ViewDev), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(vtot.data(), ctx->d_st_view_total.p, V * 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(stats.data(), ctx->d_st_stats.p, stats.size(), cudaMemcpyDeviceToHost, st));
+    // read-backs into the pinned scratch (ctx.h); pageable fallback when the view table outgrows it
+    uint32_t* small = ctx->rb_at<uint32_t>(l3d_ctx::RB_SMALL);
+    unsigned char* stats = ctx->rb_at<unsigned char>(l3d_ctx::RB_STATS);
+    std::vector<unsigned char> big_pageable;
+    unsigned char* big = ctx->rb_at<unsigned char>(l3d_ctx::RB_BIG);
+    const size_t vd_bytes = (size_t)V * sizeof(ViewDev), vt_bytes = (size_t)V * 4;
+    if (!ctx->rb_fits(vd_bytes + vt_bytes)) {
+        big_pageable.resize(vd_bytes + vt_bytes);
+        big = big_pageable.data();
+    }
+    const ViewDev* vd = reinterpret_cast<const ViewDev*>(big);
+    const uint32_t* vtot = reinterpret_cast<const uint32_t*>(big + vd_bytes);
+    CK(cudaMemcpyAsync(small, ctx->d_small.p, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(ctx->rb_at<uint32_t>(l3d_ctx::RB_NENT), ctx->d_entry_idx.p + S, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(big, ctx->d_views.p, vd_bytes, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(big + vd_bytes, ctx->d_st_view_total.p, vt_bytes, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(stats, ctx->d_st_stats.p, stream_stats_bytes(), cudaMemcpyDeviceToHost, st));
     ctx->tm.end(ev, st);
     ctx->tm.end(ev_total, st);
     CK(cudaStreamSynchronize(st));
     lap("finish+sync");
     if (trace) fprintf(stderr, "[l3d stream cycle %u]%s\n", ctx->st_cycle, tr.c_str());
     ctx->tm.collect();
-    const unsigned long long* s64 = (const unsigned long long*)stats.data();
-    const uint32_t* s32 = (const uint32_t*)(stats.data() + 16);
+    const uint32_t n_entries = *ctx->rb_at<uint32_t>(l3d_ctx::RB_NENT);
+    const unsigned long long* s64 = (const unsigned long long*)stats;
+    const uint32_t* s32 = (const uint32_t*)(stats + 16);
     if (s32[1]) return fail(L3D_ERR_CAPACITY, "internal: stream list arena overflow (%u)", s32[1]);
     if (small[2]) return fail(L3D_ERR_CAPACITY, "more than 8192 hypotheses in one view (median-depth kernel)");
     ctx->cnt.sim_evals = s64[0];
