@@ -121,30 +121,52 @@ void visual_neighbors_from_worldpoints(const std::vector<const Camera*>& cams, c
         for (uint32_t wp : wps[v]) max_wp = std::max(max_wp, wp);
     }
     if (!n_obs) return;
-    std::vector<uint32_t> by_wp(n_obs);  // views, grouped by world point
+    std::vector<uint32_t> by_wp;         // views, grouped by world point (counting walk only)
     std::vector<uint32_t> start;         // group g = by_wp[start[g] .. start[g+1])
     std::vector<uint32_t> group_wp;      // sparse ids only: the world point of every group, ascending
     const bool dense = (size_t)max_wp < 8 * n_obs + 4096;
-    if (dense) {  // counting sort, group index = world point id
-        start.assign((size_t)max_wp + 2, 0u);
-        for (uint32_t v = 0; v < V; ++v)
-            for (uint32_t wp : wps[v]) ++start[(size_t)wp + 1];
-        for (size_t i = 1; i < start.size(); ++i) start[i] += start[i - 1];
-        std::vector<uint32_t> fill(start.begin(), start.end() - 1);
-        for (uint32_t v = 0; v < V; ++v)
-            for (uint32_t wp : wps[v]) by_wp[fill[wp]++] = v;
-    } else {  // sort the (world point, view) keys
-        std::vector<uint64_t> keys;
-        keys.reserve(n_obs);
-        for (uint32_t v = 0; v < V; ++v)
-            for (uint32_t wp : wps[v]) keys.push_back(((uint64_t)wp << 32) | v);
-        std::sort(keys.begin(), keys.end());
-        start.push_back(0u);
-        for (size_t i = 0; i < keys.size(); ++i) {
-            by_wp[i] = (uint32_t)keys[i];
-            if (i + 1 == keys.size() || (keys[i + 1] >> 32) != (keys[i] >> 32)) {
-                start.push_back((uint32_t)i + 1);
-                group_wp.push_back((uint32_t)(keys[i] >> 32));
+    // small scenes with dense ids (a key-frame window): one bit per (view, world point); the shared
+    // points of two views are a popcount over the AND of their bit rows.  Only valid when no view lists a
+    // point twice (the counting walk below multiplies the multiplicities, like the reference does).
+    const size_t words = ((size_t)max_wp + 64) / 64;
+    bool use_bits = dense && (size_t)V * V * words < ((size_t)1 << 22);
+    std::vector<uint64_t> bits;
+    if (use_bits) {
+        bits.assign((size_t)V * words, 0ull);
+        for (uint32_t v = 0; v < V && use_bits; ++v)
+            for (uint32_t wp : wps[v]) {
+                uint64_t& w = bits[(size_t)v * words + (wp >> 6)];
+                const uint64_t m = 1ull << (wp & 63);
+                if (w & m) {
+                    use_bits = false;  // duplicate observation
+                    break;
+                }
+                w |= m;
+            }
+    }
+    if (!use_bits) {
+        by_wp.resize(n_obs);
+        if (dense) {  // counting sort, group index = world point id
+            start.assign((size_t)max_wp + 2, 0u);
+            for (uint32_t v = 0; v < V; ++v)
+                for (uint32_t wp : wps[v]) ++start[(size_t)wp + 1];
+            for (size_t i = 1; i < start.size(); ++i) start[i] += start[i - 1];
+            std::vector<uint32_t> fill(start.begin(), start.end() - 1);
+            for (uint32_t v = 0; v < V; ++v)
+                for (uint32_t wp : wps[v]) by_wp[fill[wp]++] = v;
+        } else {  // sort the (world point, view) keys
+            std::vector<uint64_t> keys;
+            keys.reserve(n_obs);
+            for (uint32_t v = 0; v < V; ++v)
+                for (uint32_t wp : wps[v]) keys.push_back(((uint64_t)wp << 32) | v);
+            std::sort(keys.begin(), keys.end());
+            start.push_back(0u);
+            for (size_t i = 0; i < keys.size(); ++i) {
+                by_wp[i] = (uint32_t)keys[i];
+                if (i + 1 == keys.size() || (keys[i + 1] >> 32) != (keys[i] >> 32)) {
+                    start.push_back((uint32_t)i + 1);
+                    group_wp.push_back((uint32_t)(keys[i] >> 32));
+                }
             }
         }
     }
@@ -156,14 +178,26 @@ void visual_neighbors_from_worldpoints(const std::vector<const Camera*>& cams, c
     for (uint32_t v = 0; v < V; ++v) {
         std::fill(common.begin(), common.end(), 0u);
         bool any = false;
-        for (uint32_t wp : wps[v]) {
-            const size_t g = dense ? (size_t)wp
-                                   : (size_t)(std::lower_bound(group_wp.begin(), group_wp.end(), wp) - group_wp.begin());
-            for (uint32_t i = start[g]; i < start[g + 1]; ++i)
-                if (by_wp[i] != v) {
-                    ++common[by_wp[i]];
-                    any = true;
-                }
+        if (use_bits) {
+            const uint64_t* bv = &bits[(size_t)v * words];
+            for (uint32_t o = 0; o < V; ++o) {
+                if (o == v) continue;
+                const uint64_t* bo = &bits[(size_t)o * words];
+                uint32_t c = 0;
+                for (size_t w = 0; w < words; ++w) c += (uint32_t)__builtin_popcountll(bv[w] & bo[w]);
+                common[o] = c;
+                any |= c != 0;
+            }
+        } else {
+            for (uint32_t wp : wps[v]) {
+                const size_t g = dense ? (size_t)wp
+                                       : (size_t)(std::lower_bound(group_wp.begin(), group_wp.end(), wp) - group_wp.begin());
+                for (uint32_t i = start[g]; i < start[g + 1]; ++i)
+                    if (by_wp[i] != v) {
+                        ++common[by_wp[i]];
+                        any = true;
+                    }
+            }
         }
         if (!any) continue;
         const Camera& cv = *cams[v];

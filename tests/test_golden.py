@@ -31,6 +31,20 @@ def test_world_point_neighbours_match_golden_c1(api, oracle):
     got = api.neighbors_from_worldpoints(sc, 10)
     for v in sc.views:
         assert got[v.cam_id] == list(v.neighbors), v.cam_id
+    # a view that lists some points twice: the reference's nested list walks count the multiplicities
+    # (the bit-row popcount path must step aside for the counting walk)
+    sc = _c1_with_worldpoints()
+    sc.neighbors_by_worldpoints = True
+    for v in sc.views[::3]:
+        v.worldpoints = list(v.worldpoints) + list(v.worldpoints[:40])
+    p = sc.params
+    o = oracle.OracleLine3D(sc.max_image_width, True)
+    o.load_scene(sc)
+    o.match_images(p["sigma_p"], p["sigma_a"], 6, p["epipolar_overlap"], p["knn"], p["const_reg_depth"])
+    got = api.neighbors_from_worldpoints(sc, 6)
+    for v in sc.views:
+        assert got[v.cam_id] == list(o.neighbors(v.cam_id)), ("dup", v.cam_id)
+    o.close()
     sc = _c1_with_worldpoints()
     sc.neighbors_by_worldpoints = True
     p = sc.params
