@@ -800,11 +800,8 @@ int launch_k2_exact(const PairDev* pairs, const K1Cta* ctas, uint32_t n_ctas, ui
     // test / tuning hook: 0 = row kernel always, 1 = by target-view size (default), 2 = tile kernel always
     const char* ev = getenv("L3D_K2_VARIANT");
     const int variant = ev ? atoi(ev) : 1;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k2_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K2TSmem));
-        attr_set = true;
-    }
+    // per device and cheap: set on every launch (a process may hold contexts on several GPUs)
+    cudaFuncSetAttribute(k2_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K2TSmem));
     // the tile kernel keeps a pair's whole target table in shared memory when it has <= 1024 segments
     // (C2: 0.93 vs 1.00 ms); with several chunks per pair the row kernel is the faster one (C4 shape)
     if (variant == 2 || (variant == 1 && max_tgt <= (uint32_t)K2T_TCH)) {

@@ -268,11 +268,8 @@ int launch_k4_has(const EntryDev* entries, uint32_t S, uint32_t* has, cudaStream
 int launch_k4_median(ViewDev* views, uint32_t V, const EntryDev* entries, uint32_t* overflow, cudaStream_t st)
 {
     if (!V) return 0;
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(k4_median_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MED_CAP * 4);
-        attr = true;
-    }
+    // per device and cheap: set on every launch (a process may hold contexts on several GPUs)
+    cudaFuncSetAttribute(k4_median_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MED_CAP * 4);
     k4_median_kernel<<<V, 1024, MED_CAP * 4, st>>>(views, entries, overflow);
     return 1;
 }
