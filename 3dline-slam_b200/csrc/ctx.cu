@@ -506,9 +506,19 @@ int set_params(l3d_ctx* ctx, const l3d_params* params)
     p.sigma_a = (float)std::fmin(std::fabs((double)p.sigma_a), 90.0);
     ctx->two_sigA_sqr = 2.0f * p.sigma_a * p.sigma_a;
     ctx->epi_overlap = (float)std::fmin(std::fabs((double)p.epipolar_overlap), (double)0.99f);
-    if (p.sigma_p < 0.0f)
-        return fail(L3D_ERR_ARG, "sigma_p < 0 (metric regulariser) is not supported by this build");
-    p.sigma_p = (float)std::fmax((double)0.1f, (double)p.sigma_p);
+    if (p.sigma_p < 0.0f) {
+        // fixed sigma_p in world units (src/line3D.cc:525-530): k = sigma_p / med_scene_depth for every view
+        // (View::update_k, include/view.h:138-141).  The reference takes med_scene_depth from
+        // const_regularization_depth or, if that is negative, from views_avg_depths_[size/2] -- a map
+        // indexed by POSITION as if it were a key (src/line3D.cc:557-565); only the well-defined case is built.
+        if (!(p.const_reg_depth > 0.0f))
+            return fail(L3D_ERR_ARG, "sigma_p < 0 (metric regulariser) needs const_regularization_depth > 0");
+        ctx->fixed3D = true;
+        p.sigma_p = std::fabs(p.sigma_p);
+    } else {
+        ctx->fixed3D = false;
+        p.sigma_p = (float)std::fmax((double)0.1f, (double)p.sigma_p);
+    }
     if (p.max_image_width <= 0)
         return fail(L3D_ERR_ARG, "max_image_width must be > 0 (the reference's bounds test rejects every pair otherwise)");
     ctx->have_params = true;
@@ -633,7 +643,7 @@ int l3d_match_stage12(l3d_ctx* ctx, const l3d_params* params)
         compute_translation(ctx);
         apply_translation(ctx, -1.0);
         for (auto& hv : ctx->views) {
-            hv.k = hv.cam.spatial_regularizer(ctx->prm.sigma_p);
+            hv.k = ctx->fixed3D ? ctx->prm.sigma_p / ctx->prm.const_reg_depth : hv.cam.spatial_regularizer(ctx->prm.sigma_p);
             hv.median_depth = 0.0f;
         }
     }

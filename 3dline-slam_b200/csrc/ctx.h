@@ -194,6 +194,7 @@ struct l3d_ctx {
     cudaStream_t stream = 0;
     l3d_params prm{};
     bool have_params = false;
+    bool fixed3D = false;  // sigma_p given in world units (fixed3Dregularizer_, src/line3D.cc:525-530)
 
     // host scene
     std::vector<HostView> views;  // sorted by cam id at commit

@@ -213,7 +213,9 @@ int stream_match_images(l3d_ctx* ctx, const l3d_params* params)
         l3d_ctx* c;
         ~Untranslate() { apply_translation(c, +1.0); }
     } untranslate_on_exit{ctx};
-    for (uint32_t v : cur) ctx->views[v].k = ctx->views[v].cam.spatial_regularizer(ctx->prm.sigma_p);
+    for (uint32_t v : cur)
+        ctx->views[v].k = ctx->fixed3D ? ctx->prm.sigma_p / ctx->prm.const_reg_depth
+                                       : ctx->views[v].cam.spatial_regularizer(ctx->prm.sigma_p);
 
     lap("translate+k");
     // ---- visual neighbours (src/line3D.cc:598-620) ----

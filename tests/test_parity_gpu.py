@@ -156,3 +156,19 @@ def test_sparse_matrix_layout_matches_the_oracle(api, oracle, scene_mod):
         assert ge.tobytes() == oe.tobytes() and (gs == os_).all()
         key = ge[:, 0 if by_row else 1]
         assert (np.diff(key) >= 0).all()
+
+
+def test_metric_regulariser_with_constant_depth(api, oracle, scene_mod):
+    """sigma_p < 0: the spatial regulariser is given in world units and k = |sigma_p| / const_regularization_depth
+    for every view (fixed3Dregularizer_, src/line3D.cc:525-530, 576-582); a negative depth is refused."""
+    sc = scene_mod.make_scene("tiny")
+    sc.params = dict(sc.params, sigma_p=-0.03, const_reg_depth=3.5)
+    l3 = api.run_scene(sc, keep_scored=True)
+    orc = oracle.run_scene(sc)
+    sizes = compare_full(l3, orc, sc)
+    assert sizes["entries"] > 50 and sizes["edges"] > 50
+    assert np.float32(l3.view_info(sc.views[0].cam_id)["k"]) == np.float32(0.03) / np.float32(3.5)
+    orc.close()
+    sc.params = dict(sc.params, const_reg_depth=-1.0)
+    with pytest.raises(api.L3DError, match="const_regularization_depth"):
+        api.run_scene(sc)
