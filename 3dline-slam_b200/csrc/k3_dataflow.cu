@@ -734,23 +734,24 @@ static constexpr int FIN_WARPS = 8;
 __global__ void __launch_bounds__(FIN_WARPS * 32) k3_finish_kernel(const FinishArgs a)
 {
     __shared__ uint32_t blkcnt[FIN_WARPS][DF_MAXINC];
+    // the rows of a CTA reserve their filtered entries and add their counters with ONE atomic per CTA and
+    // address (one per row serialised 50 000 same-address atomics at C2 size)
+    __shared__ uint32_t s_kept[FIN_WARPS], s_valid[FIN_WARPS], s_base;
+    __shared__ unsigned long long s_scored[FIN_WARPS], s_evals[FIN_WARPS];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t g = a.g_lo + blockIdx.x * FIN_WARPS + warp;
-    if (g >= a.g_hi) return;
+    const bool in_range = g < a.g_hi;
     const uint32_t lt_mask = (1u << lane) - 1u;
-    const size_t lbase = a.L_off[g];
-    const uint32_t m = a.L_off[g + 1] - a.L_off[g];
-    const uint32_t v = a.seg_view[g];
+    const size_t lbase = in_range ? a.L_off[g] : 0;
+    const uint32_t m = in_range ? a.L_off[g + 1] - a.L_off[g] : 0u;
+    const uint32_t v = in_range ? a.seg_view[g] : 0u;
     const ViewDev& va = a.views[v];
     const uint32_t i0 = a.inc_off[v];
-    if (m == 0) {
-        if (lane == 0) {
-            a.L_cnt[g] = 0u;
-            a.filt_off[g] = 0u;
-            a.filt_cnt[g] = 0u;
-            a.entries[g].has = 0u;
-        }
-        return;
+    if (in_range && m == 0 && lane == 0) {
+        a.L_cnt[g] = 0u;
+        a.filt_off[g] = 0u;
+        a.filt_cnt[g] = 0u;
+        a.entries[g].has = 0u;
     }
     blkcnt[warp][lane] = 0u;
     blkcnt[warp][lane + 32] = 0u;
@@ -805,9 +806,32 @@ __global__ void __launch_bounds__(FIN_WARPS * 32) k3_finish_kernel(const FinishA
     for (int d = 16; d > 0; d >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, d);
     const bool row_valid = __any_sync(0xffffffffu, any_valid);
 
-    uint32_t dst0 = 0;
-    if (lane == 0 && kept) dst0 = atomicAdd(&a.stats->filt_cursor, kept);
-    dst0 = __shfl_sync(0xffffffffu, dst0, 0);
+    if (lane == 0) {
+        s_kept[warp] = kept;
+        s_scored[warp] = n_present;
+        s_evals[warp] = (unsigned long long)n_present * n_present - sq;
+        s_valid[warp] = row_valid ? 1u : 0u;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t tk = 0, tv = 0;
+        unsigned long long ts = 0, te = 0;
+#pragma unroll
+        for (int w2 = 0; w2 < FIN_WARPS; ++w2) {
+            tk += s_kept[w2];
+            tv += s_valid[w2];
+            ts += s_scored[w2];
+            te += s_evals[w2];
+        }
+        s_base = tk ? atomicAdd(&a.stats->filt_cursor, tk) : 0u;
+        if (ts) atomicAdd(&a.stats->scored, ts);
+        if (te) atomicAdd(&a.stats->sim_evals, te);
+        if (tv) atomicAdd(&a.stats->num_valid, tv);
+    }
+    __syncthreads();
+    if (!in_range || m == 0) return;
+    uint32_t dst0 = s_base;
+    for (uint32_t w2 = 0; w2 < warp; ++w2) dst0 += s_kept[w2];
     const bool fits = (kept == 0) || ((uint64_t)dst0 + kept <= a.filt_cap);
     if (!fits && lane == 0) atomicOr(&a.stats->err, 2u);
     uint32_t w = 0;
@@ -833,9 +857,6 @@ __global__ void __launch_bounds__(FIN_WARPS * 32) k3_finish_kernel(const FinishA
         a.L_cnt[g] = n_present;
         a.filt_off[g] = dst0;
         a.filt_cnt[g] = fits ? kept : 0u;
-        atomicAdd(&a.stats->scored, (unsigned long long)n_present);
-        atomicAdd(&a.stats->sim_evals, (unsigned long long)n_present * n_present - sq);
-        if (row_valid) atomicAdd(&a.stats->num_valid, 1u);
         EntryDev& E = a.entries[g];
         if (best_idx != NOIDX && best > 0.75f) {
             const ListRec B = make_list_rec(a, i0, a.L_f[lbase + best_idx], a.L_meta[lbase + best_idx], best);
