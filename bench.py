@@ -208,10 +208,17 @@ def bench_stream(args, scene_mod):
     import stream_utils
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
-    if int(os.environ.get("RANK", "0")) != 0:
-        return
-    dev = torch.device("cuda", 0)
+    # the walk over the views is a dependency chain and a cycle brings only ~10 new pairs: the mode does not
+    # shard.  N > 1 = N independent replicas (one stream per GPU), whole-job value = N streams / slowest rank.
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    dev = torch.device("cuda", local_rank if world > 1 else 0)
     torch.cuda.set_device(dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
     fill = int(os.environ.get("L3D_C3_FILL", "24"))  # cycles until the window of 20 is full and sliding (profiling runs shorten it)
     W, K = max(args.warmup, 3), min(args.steps, 100)
     st = scene_mod.make_stream(n_keyframes=5 + fill + W + K, n_seg=1000, window=20, nbrs=10, jitter=0.3)
@@ -240,9 +247,11 @@ def bench_stream(args, scene_mod):
         calls["reconstruct"]()
         parts.append((b - a, c - b, time.perf_counter() - c))
 
-    sampler = ClockSampler(0)
+    sampler = ClockSampler(dev.index)
     if not os.environ.get("L3D_BENCH_NO_SAMPLER"):
         sampler.start()
+    if dist is not None:
+        dist.barrier()
     wall0 = wall1 = time.time()
     stage = {}
     h2d = d2h = 0
@@ -271,6 +280,14 @@ def bench_stream(args, scene_mod):
     clocks = sampler.stop(wall0, wall1) if not os.environ.get("L3D_BENCH_NO_SAMPLER") else None
     T = float(np.sum(ts))
     n = len(ts)
+    if dist is not None:  # replicas: the job is as slow as its slowest rank
+        t = torch.tensor([T], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        T = float(t.item())
+        dist.barrier()
+        dist.destroy_process_group()
+        if rank != 0:
+            return
     if os.environ.get("L3D_BENCH_TRACE"):
         for i in np.argsort(-np.asarray(ts))[:4]:
             ci = fill + W + int(i)
@@ -279,7 +296,7 @@ def bench_stream(args, scene_mod):
         pm = np.median(np.asarray(parts[fill + W:fill + W + n]), axis=0)
         print("median parts: host calls %.2f ms, match %.2f ms, reconstruct %.2f ms" % tuple(1e3 * pm), file=sys.stderr)
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
         import oracle_py
         o, oc = stream_utils.oracle_driver(oracle_py, st)
         ct, ctests = 0.0, 0
@@ -296,18 +313,20 @@ def bench_stream(args, scene_mod):
         cpu = {"value": ctests / ct, "unit": "tests/s", "cores": cores, "kind": "port",
                "sample": "the same stream, the first %d timed cycles" % min(K, 20),
                "ms_per_cycle": 1e3 * ct / min(K, 20)}
-    value = float(np.sum(tests)) / T
+    value = world * float(np.sum(tests)) / T
     line = {
-        "metric": "segment_pair_tests_per_s", "value": value, "unit": "tests/s", "n_gpus": 1, "steps": n, "warmup": W,
+        "metric": "segment_pair_tests_per_s", "value": value, "unit": "tests/s", "n_gpus": world, "steps": n, "warmup": W,
         "ms_per_step": 1e3 * T / n, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64",
         "data": "synthetic",
         "config": {"workload": "c3", "keyframes": len(st.cycles) + 4, "window": 20, "segments_per_view": 1000,
                    "neighbours": 10, "new_keyframes_per_cycle": 1, "step": "one L3DPPing cycle in steady state, wall clock",
+                   "parallelism": "1 rank" if world == 1 else "%d independent replicas (the mode does not shard)" % world,
                    "l2": "inputs larger than one kernel's footprint are not the bound here: launch-bound"},
-        "views_per_s": 20.0 * n / T,
+        "views_per_s": world * 20.0 * n / T,
         "ms_per_cycle_p50": 1e3 * float(np.median(ts)), "ms_per_cycle_max": 1e3 * float(np.max(ts)),
         "stage_ms": {k: v / n for k, v in stage.items()},
-        "e2e": {"value": value, "unit": "tests/s", "h2d_bytes_per_step": h2d // n, "d2h_bytes_per_step": d2h // n},
+        "e2e": {"value": value, "unit": "tests/s", "h2d_bytes_per_step": world * (h2d // n),
+                "d2h_bytes_per_step": world * (d2h // n)},
         "gpu_launches": int(np.sum(launches)), "clocks": clocks,
     }
     if cpu:
