@@ -170,3 +170,45 @@ def test_find_collinear_equals_findCollinCPU(api, oracle, scene_mod):
         assert (got == want).all()
         assert (ctx.find_collinear(lines, t, row_stride=224) == want).all()
     assert want.sum() > 60
+
+
+def test_cudawrapper_shim_find_collinear_runs(api, oracle, scene_mod, tmp_path):
+    """The shim's L3DPP::find_collinear_segments_GPU (include/cudawrapper.h:84-86), compiled as the
+    reference would compile it (stand-in DataArray with its 32-byte row padding) and run on the GPU:
+    the byte table it leaves in the DataArray equals View::findCollinCPU's."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "3dline-slam_b200")
+    base = scene_mod.make_scene("tiny").views[1].segs.astype(np.float32)
+    a, b = base[:30, :2], base[:30, 2:]           # 30 segments split into two collinear fragments with a gap
+    segs = np.ascontiguousarray(np.concatenate([np.concatenate([a, a + 0.4 * (b - a)], axis=1),
+                                                np.concatenate([a + 0.6 * (b - a), b], axis=1),
+                                                base[30:47]]).astype(np.float32))     # 77: rows padded to 96 bytes
+    assert segs.shape == (77, 4)
+    (tmp_path / "segs.bin").write_bytes(segs.tobytes())
+    src = tmp_path / "main.cpp"
+    src.write_text(r'''
+#include "%s/shim/cudawrapper_b200.cpp"
+#include <cstdio>
+int main(int argc, char** argv) {
+    const unsigned n = 77;
+    L3DPP::DataArray<float4> lines(n, 1);
+    FILE* f = fopen(argv[1], "rb");
+    if (!f || fread(lines.dataCPU(0, 0), sizeof(float4), n, f) != n) return 2;
+    fclose(f);
+    L3DPP::DataArray<char> C(n, n);
+    L3DPP::find_collinear_segments_GPU(&C, &lines, 2.0f);
+    FILE* o = fopen(argv[2], "wb");
+    for (unsigned r = 0; r < n; ++r) fwrite(C.dataCPU(0, r), 1, n, o);   // C(c, r): column c of row r
+    fclose(o);
+    return 0;
+}
+''' % pkg)
+    exe = tmp_path / "shim_collin"
+    subprocess.check_call(["/usr/bin/g++", "-std=c++11", "-I", os.path.join(root, "include"), str(src), "-L", pkg,
+                           "-ll3dpp_b200", "-Wl,-rpath," + pkg, "-o", str(exe)])
+    subprocess.check_call([str(exe), str(tmp_path / "segs.bin"), str(tmp_path / "out.bin")])
+    got = np.frombuffer((tmp_path / "out.bin").read_bytes(), dtype=np.int8).reshape(77, 77)
+    want = oracle.find_collinear(segs, 2.0)
+    assert (got == want).all() and want.sum() >= 60
