@@ -212,3 +212,67 @@ int main(int argc, char** argv) {
     got = np.frombuffer((tmp_path / "out.bin").read_bytes(), dtype=np.int8).reshape(77, 77)
     want = oracle.find_collinear(segs, 2.0)
     assert (got == want).all() and want.sum() >= 60
+
+
+def test_cudawrapper_shim_match_lines_runs(api, oracle, scene_mod, tmp_path):
+    """The shim's L3DPP::match_lines_GPU_f64 compiled and run: the std::vector<std::list<Match>> it fills
+    (what Line3D::matchingGPU hands to the rest of Line3D) equals Line3D::matchingCPU's lists."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "3dline-slam_b200")
+    sc, va, vb = _two_view_scene(scene_mod)
+    o = oracle.OracleLine3D(sc.max_image_width, False)
+    o.load_scene(sc)
+    F, Ms, Mt, Cs, Ct = o.match_only(va.cam_id, vb.cam_id, 0.25, 10)
+    off_o, rec_o = o.lists(va.cam_id, 1)
+    with open(tmp_path / "in.bin", "wb") as f:
+        f.write(np.array([len(va.segs), len(vb.segs)], np.uint32).tobytes())
+        f.write(np.ascontiguousarray(va.segs, np.float32).tobytes())
+        f.write(np.ascontiguousarray(vb.segs, np.float32).tobytes())
+        for a in (F, Ms, Mt, Cs, Ct):
+            f.write(np.ascontiguousarray(a, np.float64).tobytes())
+    src = tmp_path / "main.cpp"
+    src.write_text(r'''
+#include "%s/shim/cudawrapper_b200.cpp"
+#include <cstdio>
+int main(int argc, char** argv) {
+    FILE* f = fopen(argv[1], "rb");
+    unsigned n[2];
+    if (!f || fread(n, 4, 2, f) != 2) return 2;
+    L3DPP::DataArray<float4> ls(n[0], 1), lt(n[1], 1);
+    if (fread(ls.dataCPU(0, 0), 16, n[0], f) != n[0] || fread(lt.dataCPU(0, 0), 16, n[1], f) != n[1]) return 3;
+    double M[9 * 3 + 6];
+    if (fread(M, 8, 33, f) != 33) return 4;
+    fclose(f);
+    std::vector<std::list<L3DPP::Match> > matches(n[0]);
+    const unsigned got = L3DPP::match_lines_GPU_f64(&ls, &lt, M, M + 9, M + 18, M + 27, M + 30, &matches, %d, %d, 0.25f, 10, %d);
+    FILE* o = fopen(argv[2], "wb");
+    fwrite(&got, 4, 1, o);
+    for (unsigned r = 0; r < n[0]; ++r)
+        for (std::list<L3DPP::Match>::const_iterator it = matches[r].begin(); it != matches[r].end(); ++it) {
+            const unsigned ids[4] = {it->src_camID_, it->src_segID_, it->tgt_camID_, it->tgt_segID_};
+            const float v[6] = {it->overlap_score_, it->score3D_, it->depth_p1_, it->depth_p2_, it->depth_q1_, it->depth_q2_};
+            if (it->src_segID_ != r || it->match_orientation_) return 5;
+            fwrite(ids, 4, 4, o);
+            fwrite(v, 4, 6, o);
+        }
+    fclose(o);
+    return 0;
+}
+''' % (pkg, va.cam_id, vb.cam_id, sc.max_image_width))
+    exe = tmp_path / "shim_match"
+    subprocess.check_call(["/usr/bin/g++", "-std=c++11", "-I", os.path.join(root, "include"), str(src), "-L", pkg,
+                           "-ll3dpp_b200", "-Wl,-rpath," + pkg, "-o", str(exe)])
+    subprocess.check_call([str(exe), str(tmp_path / "in.bin"), str(tmp_path / "out.bin")])
+    raw = (tmp_path / "out.bin").read_bytes()
+    n = int(np.frombuffer(raw[:4], np.uint32)[0])
+    rec = np.frombuffer(raw[4:], dtype=np.dtype([("ids", "<u4", 4), ("v", "<f4", 6)]))
+    assert n == len(rec) == len(rec_o) > 0
+    assert (rec["ids"][:, 0] == va.cam_id).all() and (rec["ids"][:, 2] == vb.cam_id).all()
+    rows = np.repeat(np.arange(len(off_o) - 1), np.diff(off_o.astype(np.int64)))
+    assert (rec["ids"][:, 1] == rows).all() and (rec["ids"][:, 3] == rec_o["tgt_seg"]).all()
+    for col, name in ((0, "overlap"), (2, "d_p1"), (3, "d_p2"), (4, "d_q1"), (5, "d_q2")):
+        assert (rec["v"][:, col].view(np.uint32) == rec_o[name].view(np.uint32)).all(), name
+    assert (rec["v"][:, 1] == 0).all()
+    o.close()
