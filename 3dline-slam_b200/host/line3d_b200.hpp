@@ -20,6 +20,26 @@ struct CLEdge {  // include/clustering.h:57-61
     float w_;
 };
 
+// A_ as the reference's std::list<CLEdge> (include/clustering.h:57-61) and local2global_
+inline void read_affinity_matrix(l3d_ctx* ctx, std::list<CLEdge>& A,
+                                 std::vector<std::pair<unsigned int, unsigned int>>& local2global)
+{
+    A.clear();
+    local2global.clear();
+    l3d_counts c{};
+    if (!ctx || l3d_get_counts(ctx, &c) != L3D_OK || c.num_edges == 0) return;
+    std::vector<int32_t> ij(2 * (size_t)c.num_edges);
+    std::vector<float> w(c.num_edges);
+    std::vector<uint32_t> l2g(2 * (size_t)c.num_local_ids);
+    if (l3d_get_edges(ctx, ij.data(), w.data(), c.num_edges) != L3D_OK ||
+        l3d_get_local2global(ctx, l2g.data(), c.num_local_ids) != L3D_OK) {
+        std::cerr << "[L3D++] ERROR: " << l3d_last_error() << std::endl;
+        return;
+    }
+    for (uint32_t e = 0; e < c.num_edges; ++e) A.push_back(CLEdge{ij[2 * e], ij[2 * e + 1], w[e]});
+    for (uint32_t i = 0; i < c.num_local_ids; ++i) local2global.push_back({l2g[2 * i], l2g[2 * i + 1]});
+}
+
 class Line3D {
   public:
     // Line3D::Line3D (src/line3D.cc:6-74); load_segments / output folder are I/O options of the
@@ -118,20 +138,7 @@ class Line3D {
     // A_ as the reference's std::list<CLEdge> (include/clustering.h) and the ID maps
     void getAffinityMatrix(std::list<CLEdge>& A, std::vector<std::pair<unsigned int, unsigned int>>& local2global)
     {
-        A.clear();
-        local2global.clear();
-        l3d_counts c{};
-        if (!ctx_ || l3d_get_counts(ctx_, &c) != L3D_OK || c.num_edges == 0) return;
-        std::vector<int32_t> ij(2 * (size_t)c.num_edges);
-        std::vector<float> w(c.num_edges);
-        std::vector<uint32_t> l2g(2 * (size_t)c.num_local_ids);
-        if (l3d_get_edges(ctx_, ij.data(), w.data(), c.num_edges) != L3D_OK ||
-            l3d_get_local2global(ctx_, l2g.data(), c.num_local_ids) != L3D_OK) {
-            std::cerr << prefix_ << "ERROR: " << l3d_last_error() << std::endl;
-            return;
-        }
-        for (uint32_t e = 0; e < c.num_edges; ++e) A.push_back(CLEdge{ij[2 * e], ij[2 * e + 1], w[e]});
-        for (uint32_t i = 0; i < c.num_local_ids; ++i) local2global.push_back({l2g[2 * i], l2g[2 * i + 1]});
+        read_affinity_matrix(ctx_, A, local2global);
     }
 
     size_t numImages() const { return views_.size(); }
@@ -245,6 +252,10 @@ class Line3DStream {
         if (perform_diffusion || use_CERES || collinearity_t > 1e-12f)
             std::cout << prefix_ << "ERROR: diffusion / CERES / collinearity are not part of this path" << std::endl;
         if (report(l3d_affinity(ctx_))) report(l3d_cluster(ctx_));
+    }
+    void getAffinityMatrix(std::list<CLEdge>& A, std::vector<std::pair<unsigned int, unsigned int>>& local2global)
+    {
+        read_affinity_matrix(ctx_, A, local2global);
     }
     l3d_ctx* context() { return ctx_; }
 

@@ -276,3 +276,144 @@ int main(int argc, char** argv) {
         assert (rec["v"][:, col].view(np.uint32) == rec_o[name].view(np.uint32)).all(), name
     assert (rec["v"][:, 1] == 0).all()
     o.close()
+
+
+_MIRROR_MAIN = r'''
+#include "line3d_b200.hpp"
+#include <cstdio>
+#include <cstdlib>
+static FILE* f;
+template <typename T> static T rd() { T v; if (fread(&v, sizeof(T), 1, f) != 1) exit(9); return v; }
+template <typename T> static std::vector<T> rdv(size_t n) { std::vector<T> v(n); if (n && fread(v.data(), sizeof(T), n, f) != n) exit(9); return v; }
+static std::list<unsigned int> rdl() { unsigned n = rd<unsigned>(); std::vector<unsigned> v = rdv<unsigned>(n); return std::list<unsigned int>(v.begin(), v.end()); }
+template <class L3> static void dump(L3& l3, FILE* o) {
+    std::list<L3DPP_B200::CLEdge> A;
+    std::vector<std::pair<unsigned int, unsigned int> > l2g;
+    l3.getAffinityMatrix(A, l2g);
+    unsigned n = (unsigned)A.size(), m = (unsigned)l2g.size();
+    fwrite(&n, 4, 1, o); fwrite(&m, 4, 1, o);
+    for (std::list<L3DPP_B200::CLEdge>::const_iterator it = A.begin(); it != A.end(); ++it) { fwrite(&it->i_, 4, 1, o); fwrite(&it->j_, 4, 1, o); fwrite(&it->w_, 4, 1, o); }
+    for (size_t i = 0; i < l2g.size(); ++i) { fwrite(&l2g[i].first, 4, 1, o); fwrite(&l2g[i].second, 4, 1, o); }
+}
+int main(int argc, char** argv) {
+    f = fopen(argv[1], "rb");
+    FILE* o = fopen(argv[2], "wb");
+    if (!f || !o) return 2;
+    const unsigned stream = rd<unsigned>(), by_wps = rd<unsigned>(), width = rd<unsigned>(), n_cycles = rd<unsigned>();
+    const float sp = rd<float>(), sa = rd<float>(); const unsigned nn = rd<unsigned>(); const float eo = rd<float>(); const int knn = rd<int>();
+    L3DPP_B200::Line3D batch("", false, (int)width, 3000, by_wps != 0, true);
+    L3DPP_B200::Line3DStream st("", false, (int)width, 3000, by_wps != 0, true);
+    for (unsigned c = 0; c < n_cycles; ++c) {
+        if (stream) st.beginCycle();
+        unsigned nd = rd<unsigned>();
+        for (unsigned i = 0; i < nd; ++i) { unsigned cam = rd<unsigned>(); if (stream && !st.deleteImage(cam)) return 3; }
+        unsigned na = rd<unsigned>();
+        for (unsigned i = 0; i < na; ++i) {
+            unsigned cam = rd<unsigned>(), w = rd<unsigned>(), h = rd<unsigned>();
+            std::vector<double> K = rdv<double>(9), R = rdv<double>(9), t = rdv<double>(3);
+            float md = rd<float>();
+            std::list<unsigned int> l = rdl();
+            unsigned ns = rd<unsigned>();
+            std::vector<float> segs = rdv<float>(4 * (size_t)ns);
+            if (stream) st.addImage(cam, w, h, K.data(), R.data(), t.data(), md, l, segs);
+            else batch.addImage(cam, w, h, K.data(), R.data(), t.data(), md, l, segs);
+        }
+        unsigned nu = rd<unsigned>();
+        for (unsigned i = 0; i < nu; ++i) {
+            unsigned cam = rd<unsigned>();
+            std::vector<double> R = rdv<double>(9), t = rdv<double>(3);
+            float md = rd<float>();
+            std::list<unsigned int> l = rdl();
+            if (stream) st.UpdataImage(cam, R.data(), t.data(), md, l);
+            else batch.UpdataImage(cam, R.data(), t.data(), md, l);
+        }
+        if (stream) { st.matchImages(sp, sa, nn, eo, knn, -1.0f); st.reconstruct3Dlines(); }
+        else { batch.matchImages(sp, sa, nn, eo, knn, -1.0f); batch.reconstruct3Dlines(); }
+        if (stream) dump(st, o); else dump(batch, o);
+    }
+    fclose(o);
+    return 0;
+}
+'''
+
+
+def _write_cycles(path, stream_mode, by_wps, width, params, cycles):
+    import struct
+    with open(path, "wb") as f:
+        f.write(struct.pack("<4I", int(stream_mode), int(by_wps), width, len(cycles)))
+        f.write(struct.pack("<ffIfi", params["sigma_p"], params["sigma_a"], params["num_neighbors"],
+                            params["epipolar_overlap"], params["knn"]))
+        for dels, adds, upds in cycles:
+            f.write(struct.pack("<I", len(dels)) + np.asarray(dels, np.uint32).tobytes())
+            f.write(struct.pack("<I", len(adds)))
+            for v, lst in adds:
+                f.write(struct.pack("<3I", v.cam_id, v.width, v.height))
+                for a in (v.K, v.R, v.t):
+                    f.write(np.ascontiguousarray(a, np.float64).tobytes())
+                f.write(struct.pack("<f", v.median_depth))
+                f.write(struct.pack("<I", len(lst)) + np.asarray(lst, np.uint32).tobytes())
+                f.write(struct.pack("<I", len(v.segs)) + np.ascontiguousarray(v.segs, np.float32).tobytes())
+            f.write(struct.pack("<I", len(upds)))
+            for cam, R, t, md, lst in upds:
+                f.write(struct.pack("<I", cam) + np.ascontiguousarray(R, np.float64).tobytes() +
+                        np.ascontiguousarray(t, np.float64).tobytes() + struct.pack("<f", md))
+                f.write(struct.pack("<I", len(lst)) + np.asarray(lst, np.uint32).tobytes())
+
+
+def _read_dumps(path, n):
+    raw = open(path, "rb").read()
+    out, p = [], 0
+    for _ in range(n):
+        ne, nl = np.frombuffer(raw[p:p + 8], np.uint32)
+        p += 8
+        e = np.frombuffer(raw[p:p + 12 * ne], dtype=np.dtype([("i", "<i4"), ("j", "<i4"), ("w", "<f4")]))
+        p += 12 * int(ne)
+        l2g = np.frombuffer(raw[p:p + 8 * nl], np.uint32).reshape(-1, 2)
+        p += 8 * int(nl)
+        out.append((e, l2g))
+    return out
+
+
+def test_cpp_line3d_mirrors_run(api, oracle, scene_mod, tmp_path):
+    """The C++ host mirrors (3dline-slam_b200/host/line3d_b200.hpp) compiled and run on the GPU: the batch
+    Line3D on the tiny scene and Line3DStream on a short key-frame stream give the oracle's A_ and id maps."""
+    import os
+    import subprocess
+    import stream_utils
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "3dline-slam_b200")
+    src = tmp_path / "main.cpp"
+    src.write_text(_MIRROR_MAIN)
+    exe = tmp_path / "mirror"
+    subprocess.check_call(["/usr/bin/g++", "-std=c++11", "-I", os.path.join(root, "include"), "-I", os.path.join(pkg, "host"),
+                           str(src), "-L", pkg, "-ll3dpp_b200", "-Wl,-rpath," + pkg, "-o", str(exe)])
+    # batch
+    sc = scene_mod.make_scene("tiny")
+    _write_cycles(tmp_path / "b.bin", False, False, sc.max_image_width, sc.params,
+                  [([], [(v, v.neighbors) for v in sc.views], [])])
+    subprocess.check_call([str(exe), str(tmp_path / "b.bin"), str(tmp_path / "b.out")])
+    (e, l2g), = _read_dumps(tmp_path / "b.out", 1)
+    orc = oracle.run_scene(sc)
+    oij, ow = orc.edges()
+    assert len(e) == len(ow) > 100 and (e["i"] == oij[:, 0]).all() and (e["j"] == oij[:, 1]).all()
+    assert (e["w"].view(np.uint32) == ow.view(np.uint32)).all() and (l2g == orc.local2global()).all()
+    orc.close()
+    # key-frame stream
+    st = scene_mod.make_stream(n_keyframes=9, n_seg=250, window=6, nbrs=4, jitter=0.2, n_world=700)
+    cyc = [(c.deletes, [(v, v.worldpoints) for v in c.adds], c.updates) for c in st.cycles]
+    _write_cycles(tmp_path / "s.bin", True, True, st.max_image_width, st.params, cyc)
+    subprocess.check_call([str(exe), str(tmp_path / "s.bin"), str(tmp_path / "s.out")])
+    dumps = _read_dumps(tmp_path / "s.out", len(cyc))
+    o, calls = stream_utils.oracle_driver(oracle, st)
+    k = [0]
+
+    def on_cycle(ci, cy):
+        e, l2g = dumps[ci]
+        oij, ow = o.edges()
+        assert len(e) == len(ow), ci
+        assert (e["i"] == oij[:, 0]).all() and (e["j"] == oij[:, 1]).all() and (e["w"].view(np.uint32) == ow.view(np.uint32)).all()
+        assert (l2g == o.local2global()).all()
+        k[0] += len(ow)
+    scene_mod.drive_stream(st, on_cycle=on_cycle, **calls)
+    assert k[0] > 200
+    o.close()
