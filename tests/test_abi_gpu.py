@@ -417,3 +417,74 @@ def test_cpp_line3d_mirrors_run(api, oracle, scene_mod, tmp_path):
     scene_mod.drive_stream(st, on_cycle=on_cycle, **calls)
     assert k[0] > 200
     o.close()
+
+
+def test_cudawrapper_shim_score_matches_runs(api, oracle, scene_mod, tmp_path):
+    """The shim's L3DPP::score_matches_GPU (include/cudawrapper.h:74-81) compiled and run on buffers packed
+    the way Line3D::scoringGPU packs them; the float RtKinv / C of the reference signature are promoted to
+    double by the shim, so the oracle gets the same float-rounded camera."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "3dline-slam_b200")
+    sc = scene_mod.make_scene("tiny", seed=11)
+    orc = oracle.run_scene(sc)
+    v = sc.views[3]
+    off, rec = orc.lists(v.cam_id, 0)
+    info = orc.view_info(v.cam_id)
+    n = len(v.segs)
+    matches, ranges, regs = [], np.full((n, 2), -1, np.int32), []
+    rng = np.random.default_rng(0)
+    for i in range(n):
+        r = rec[off[i]:off[i + 1]]
+        if len(r) == 0:
+            continue
+        order = np.lexsort((r["tgt_seg"], r["tgt_cam"]))
+        ranges[i] = (len(matches), len(matches) + len(r) - 1)
+        for e in r[order]:
+            matches.append((float(i), float(e["tgt_cam"]), e["d_p1"], e["d_p2"]))
+            regs.append((abs(rng.normal(0.03, 0.01)), abs(rng.normal(0.03, 0.01))))
+    matches = np.asarray(matches, np.float32)
+    regs = np.asarray(regs, np.float32)
+    M32 = np.linalg.inv(v.K).astype(np.float32)
+    C32 = np.array([0.1, -0.2, 0.3], np.float32)
+    k = np.float32(info["k"])
+    with open(tmp_path / "in.bin", "wb") as f:
+        f.write(np.array([n, len(matches)], np.uint32).tobytes())
+        f.write(np.ascontiguousarray(v.segs, np.float32).tobytes() + matches.tobytes() + ranges.tobytes() + regs.tobytes())
+        f.write(M32.tobytes() + C32.tobytes() + np.array([200.0, k, 0.5], np.float32).tobytes())
+    src = tmp_path / "main.cpp"
+    src.write_text(r'''
+#include "%s/shim/cudawrapper_b200.cpp"
+#include <cstdio>
+int main(int argc, char** argv) {
+    FILE* f = fopen(argv[1], "rb");
+    unsigned n[2];
+    if (!f || fread(n, 4, 2, f) != 2) return 2;
+    L3DPP::DataArray<float4> lines(n[0], 1), matches(n[1], 1);
+    L3DPP::DataArray<int2> ranges(n[0], 1);
+    L3DPP::DataArray<float2> regs(n[1], 1);
+    L3DPP::DataArray<float> scores(n[1], 1), M(3, 3);
+    if (fread(lines.dataCPU(0, 0), 16, n[0], f) != n[0] || fread(matches.dataCPU(0, 0), 16, n[1], f) != n[1] ||
+        fread(ranges.dataCPU(0, 0), 8, n[0], f) != n[0] || fread(regs.dataCPU(0, 0), 8, n[1], f) != n[1]) return 3;
+    float m[9], c[3], p[3];
+    if (fread(m, 4, 9, f) != 9 || fread(c, 4, 3, f) != 3 || fread(p, 4, 3, f) != 3) return 4;
+    for (unsigned r = 0; r < 3; ++r)
+        for (unsigned col = 0; col < 3; ++col) M.dataCPU(col, r)[0] = m[3 * r + col];   // (x = col, y = row)
+    float3 C; C.x = c[0]; C.y = c[1]; C.z = c[2];
+    L3DPP::score_matches_GPU(&lines, &matches, &ranges, &scores, &regs, &M, C, p[0], p[1], p[2]);
+    FILE* o = fopen(argv[2], "wb");
+    fwrite(scores.dataCPU(0, 0), 4, n[1], o);
+    fclose(o);
+    return 0;
+}
+''' % pkg)
+    exe = tmp_path / "shim_score"
+    subprocess.check_call(["/usr/bin/g++", "-std=c++11", "-I", os.path.join(root, "include"), str(src), "-L", pkg,
+                           "-ll3dpp_b200", "-Wl,-rpath," + pkg, "-o", str(exe)])
+    subprocess.check_call([str(exe), str(tmp_path / "in.bin"), str(tmp_path / "out.bin")])
+    got = np.frombuffer((tmp_path / "out.bin").read_bytes(), np.float32)
+    exp = oracle.score_packed(v.segs, matches, ranges, regs, M32.astype(np.float64), C32.astype(np.float64), 200.0,
+                              float(k), 0.5)
+    assert len(got) == len(exp) and (got.view(np.uint32) == exp.view(np.uint32)).all() and (got > 0.75).sum() > 0
+    orc.close()
