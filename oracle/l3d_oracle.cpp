@@ -7,7 +7,9 @@
 //
 // PARITY UNPINNED: the reference ships no tests, golden vectors or runnable inputs for this path
 // and cannot be compiled in this environment (Eigen, Boost, OpenCV, PCL, tclap absent), so this
-// restatement is pinned only by hand-derived known-answer tests (tests/test_oracle_kat.py).
+// restatement is pinned only by hand-derived known-answer tests (tests/test_oracle_kat.py) -- except the
+// graph clustering, the one part that compiles from the reference's own sources (STL only): it is checked
+// against the reference itself (oracle/_ref/libref_clustering.so, tests/test_ref_clustering.py).
 //
 // Canonical arithmetic: IEEE double/float exactly where the reference
 // uses them, scalar left-to-right sums, row-major 3x3*v, true divisions, no FMA contraction

@@ -25,7 +25,33 @@ def build(force: bool = False) -> str:
     src = [os.path.join(_HERE, f) for f in ("l3d_oracle.cpp", "detmath.h", "Makefile")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in src):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
+    build_ref()
     return so
+
+
+REF_ROOT = "/root/reference"
+REF_CLUSTERING = os.path.join(_HERE, "_ref", "libref_clustering.so")
+
+
+def build_ref() -> bool:
+    """oracle/_ref: the reference's own clustering compiled from its sources (only where /root/reference
+    exists, i.e. in the authoring container; the GPU box uses the prebuilt file that travelled with the repo)."""
+    if os.path.exists(os.path.join(REF_ROOT, "src", "clustering.cc")):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "ref"])
+    return os.path.exists(REF_CLUSTERING)
+
+
+def ref_cluster(ij, w, n, c=3.0):
+    """The reference's L3DPP::performClustering itself (oracle/_ref); None if the library is not there."""
+    if not os.path.exists(REF_CLUSTERING) and not build_ref():
+        return None
+    L = C.CDLL(REF_CLUSTERING)
+    ij = np.ascontiguousarray(ij, dtype=np.int32)
+    w = np.ascontiguousarray(w, dtype=np.float32)
+    out = np.zeros(max(n, 1), dtype=np.int32)
+    L.ref_cluster.restype = C.c_int
+    L.ref_cluster(_p(ij), _p(w), len(w), int(n), C.c_float(c), _p(out))
+    return out[:n]
 
 
 def lib():
@@ -263,6 +289,15 @@ def run_scene(scene, threads=0, snapshot=True, reconstruct=True):
     if reconstruct:
         o.reconstruct()
     return o
+
+
+def kat_cluster(ij, w, n):
+    """The oracle's restatement of performClustering + the id read-out of clusterSegments (c = 3)."""
+    ij = np.ascontiguousarray(ij, dtype=np.int32)
+    w = np.ascontiguousarray(w, dtype=np.float32)
+    out = np.zeros(max(n, 1), dtype=np.int32)
+    lib().orc_kat_cluster(_p(ij), _p(w), len(w), int(n), _p(out))
+    return out[:n]
 
 
 def sparse_matrix(ij, w, n, norm=1.0, sort_by_row=False):

@@ -138,3 +138,15 @@ def test_c3_full_stream_bit_exact(api, oracle, scene_mod):
     tot = stream_utils.run_lockstep(api, oracle, st, check_scored=False)
     assert tot["cycles"] == 296 and tot["deleted"] >= 280 and tot["pairs"] > 2500
     assert tot["tests"] > 2.5e9
+
+
+def test_c2_cluster_ids_equal_the_reference_clustering(api, oracle, c2_run):
+    """The cluster IDs of config 2 against the REFERENCE's own L3DPP::performClustering (compiled from
+    /root/reference/src/clustering.cc into oracle/_ref, see tests/test_ref_clustering.py), run on the A_
+    the CUDA path produced."""
+    ij, w = c2_run.edges()
+    n = len(c2_run.local2global())
+    ref = oracle.ref_cluster(ij, w, n)
+    if ref is None:
+        pytest.skip("oracle/_ref/libref_clustering.so did not travel / is not built")
+    assert n > 5000 and (c2_run.cluster_ids() == ref).all()
