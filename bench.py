@@ -4,7 +4,10 @@ path on B200 (BASELINE.json metric), with the K1 roofline, the CPU baseline and 
 number.  One "step" = one full pass of stages 1-4 (l3d_match_images + l3d_affinity) over one
 synthetic scene.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3|c4|c4s]
+
+The default single-GPU line also carries `config3_stream`: BASELINE config[2], the key-frame stream through
+the incremental mode (what `--workload c3` measures on its own; `--no-stream` skips it).
 
 N=1: BASELINE config[1] (50 views x 1000 segments x 10 neighbours, 640x480).  N>1 (torchrun, one
 process per GPU): the scene grows with N (50*N views, weak scaling); every rank owns a contiguous
@@ -195,7 +198,7 @@ def bench_reference(args, scene_mod):
     print(json.dumps(line))
 
 
-def bench_stream(args, scene_mod):
+def bench_stream(args, scene_mod, emit=True):
     """--workload c3: BASELINE config[2], the key-frame stream through the incremental mode
     (l3d_stream_*; 640x480, 1000 segments per key frame, window of 20, 10 neighbours).  One step = one
     L3DPPing cycle in steady state: delete the culled key frames, add the new one (host buffers),
@@ -331,7 +334,9 @@ def bench_stream(args, scene_mod):
     }
     if cpu:
         line["cpu_baseline"] = cpu
-    print(json.dumps(line))
+    if emit:
+        print(json.dumps(line))
+    return line
 
 
 def main():
@@ -342,6 +347,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-stream", action="store_true", help="skip the config-3 key-frame stream measurement")
     ap.add_argument("--check", action="store_true", help="also verify the result against the CPU oracle")
     ap.add_argument("--trace-phases", action="store_true", help="N>1: wall time per phase/exchange (stderr)")
     args = ap.parse_args()
@@ -599,6 +605,22 @@ def main():
                                          "filtered_entries", "num_pairs", "num_entries", "num_edges", "num_local_ids")},
         "roofline": roofline, "stage_rooflines": stage_rooflines, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
     }
+    # BASELINE config 3 (key-frame stream, incremental mode) rides along on the default single-GPU run
+    if n_gpus == 1 and args.workload == "c2" and not args.no_stream:
+        try:
+            import copy
+            a3 = copy.copy(args)
+            a3.steps, a3.warmup = 40, 3
+            s3 = bench_stream(a3, scene_mod, emit=False)
+            line["config3_stream"] = {
+                "what": "bench.py --workload c3: one L3DPPing cycle in steady state (window 20, 1000 segments, 10 neighbours, "
+                        "one new key frame per cycle), public API with host inputs, wall clock",
+                "ms_per_cycle": s3["ms_per_step"], "ms_per_cycle_p50": s3["ms_per_cycle_p50"],
+                "tests_per_s": s3["value"], "views_per_s": s3["views_per_s"], "stage_ms": s3["stage_ms"],
+                "gpu_launches_per_cycle": s3["gpu_launches"] / max(s3["steps"], 1),
+                "cpu_baseline": s3.get("cpu_baseline")}
+        except Exception as e:  # the headline line must not depend on the extra measurement
+            line["config3_stream"] = {"error": repr(e)}
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
