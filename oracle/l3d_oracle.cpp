@@ -237,6 +237,45 @@ struct View {
         return d1 + d2;
     }
     float baseLine(const View& v) const { return (float)norm(sub(C, v.C)); }
+    // collinear segments (view.cc:180-200, 238-318)
+    std::vector<std::list<unsigned>> collin;
+    float collin_t = -1.0f;
+    static bool pointOnSegment2D(const V3& p1, const V3& p2, const V3& x)  // view.cc:321-327
+    {
+        const double v1x = p1.x - x.x, v1y = p1.y - x.y, v2x = p2.x - x.x, v2y = p2.y - x.y;
+        return (v1x * v2x + v1y * v2y) < EPS;
+    }
+    static float distPoint2Line2D(const V3& l, const V3& p)  // view.cc:296-299
+    {
+        return (float)std::fabs((l.x * p.x + l.y * p.y + l.z) / sqrtf((float)(l.x * l.x + l.y * l.y)));
+    }
+    static bool collinearPair(const Seg2f& a, const Seg2f& b, float dist_t)  // body of view.cc:256-291
+    {
+        const V3 p0 = {(double)a.x1, (double)a.y1, 1.0}, p1 = {(double)a.x2, (double)a.y2, 1.0};
+        const V3 q0 = {(double)b.x1, (double)b.y1, 1.0}, q1 = {(double)b.x2, (double)b.y2, 1.0};
+        const V3 line1 = cross(p0, p1), line2 = cross(q0, q1);
+        if (pointOnSegment2D(p0, p1, q0) || pointOnSegment2D(p0, p1, q1) || pointOnSegment2D(q0, q1, p0) ||
+            pointOnSegment2D(q0, q1, p1))
+            return false;
+        const float d1 = (float)std::fmax((double)distPoint2Line2D(line1, q0), (double)distPoint2Line2D(line1, q1));
+        const float d2 = (float)std::fmax((double)distPoint2Line2D(line2, p0), (double)distPoint2Line2D(line2, p1));
+        return (float)std::fmax((double)d1, (double)d2) < dist_t;
+    }
+    void findCollinearSegments(float dist_t)
+    {
+        if (std::fabs((double)(dist_t - collin_t)) < EPS) return;  // already computed
+        if (!(dist_t > EPS)) return;
+        collin_t = dist_t;
+        collin.assign(lines.size(), std::list<unsigned>());
+        for (size_t r = 0; r < lines.size(); ++r)
+            for (size_t c = 0; c < lines.size(); ++c)
+                if (r != c && collinearPair(lines[r], lines[c], collin_t)) collin[r].push_back((unsigned)c);
+    }
+    std::list<unsigned> collinearSegments(unsigned seg) const  // view.cc:312-318
+    {
+        if (collin.size() == lines.size() && seg < lines.size()) return collin[seg];
+        return std::list<unsigned>();
+    }
     // view.h:122-135
     void updateMedianDepth(float d, float sigmaP, float med_scene_depth)
     {
@@ -1008,7 +1047,9 @@ class Line3D {
         return id;
     }
 
-    // line3D.cc:2275-2402 (serial order; collinearity off)
+    // line3D.cc:2275-2402 (serial order), including the links to collinear segments of line3D.cc:2328-2396
+    // when collinearity_t > 0 (the product builds the collinearity-off case only)
+    float collinearity_t = -1.0f;
     void computingAffinityMatrix()
     {
         A.clear();
@@ -1016,11 +1057,13 @@ class Line3D {
         local2global.clear();
         localID = 0;
         used.clear();
+        const bool collin_on = collinearity_t > EPS;
         for (size_t i = 0; i < est3D.size(); ++i) {
             const Seg3D& s = est3D[i].seg;
             const Match m = est3D[i].m;
             const Seg2D seg(m.src_cam, m.src_seg);
             int id1 = -1;
+            bool found_aff = false;
             const std::list<Match>& ml = matches[m.src_cam][m.src_seg];
             for (const Match& m2 : ml) {
                 const Seg2D seg2(m2.tgt_cam, m2.tgt_seg);
@@ -1030,6 +1073,29 @@ class Line3D {
                     const int id2 = getLocalID(seg2);
                     A.push_back({id1, id2, sim});
                     A.push_back({id2, id1, sim});
+                    found_aff = true;
+                    if (collin_on) {  // links to the segments collinear to the target (line3D.cc:2328-2360)
+                        for (unsigned c : views[seg2.first]->collinearSegments(seg2.second)) {
+                            const Seg2D seg2c(seg2.first, c);
+                            const float simc = similarity(s, m, seg2c, false);
+                            if (simc > MIN_AFFINITY && unused(seg, seg2c)) {
+                                const int id2c = getLocalID(seg2c);
+                                A.push_back({id1, id2c, simc});
+                                A.push_back({id2c, id1, simc});
+                            }
+                        }
+                    }
+                }
+            }
+            if (found_aff && id1 >= 0 && collin_on) {  // line3D.cc:2364-2396
+                for (unsigned c : views[seg.first]->collinearSegments(seg.second)) {
+                    const Seg2D segc(seg.first, c);
+                    const float simc = similarity(s, m, segc, false);
+                    if (simc > MIN_AFFINITY && unused(seg, segc)) {
+                        const int idc = getLocalID(segc);
+                        A.push_back({id1, idc, simc});
+                        A.push_back({idc, id1, simc});
+                    }
                 }
             }
         }
@@ -1076,14 +1142,20 @@ class Line3D {
     }
 
     // line3D.cc:2018-2118 (up to and including clustering; the 3-D line tail is out of scope)
-    void reconstruct()
+    void reconstruct(float collin_t = -1.0f)
     {
         const double T0 = now();
         A_snapshot.clear();
         local2global_snapshot.clear();
         cluster_ids.clear();
         if (est3D.empty()) return;
+        const float prev_collin_t = collinearity_t;  // line3D.cc:2041-2042
+        collinearity_t = collin_t;
         translate();
+        // line3D.cc:2068-2072, 2250-2270: every view in views_ (a view added later keeps an empty table
+        // until the threshold changes, as in the reference)
+        if (collinearity_t > EPS && (prev_collin_t < EPS || std::fabs((double)(prev_collin_t - collinearity_t)) > EPS))
+            for (auto& kv : views) kv.second->findCollinearSegments(collinearity_t);
         std::vector<float> sd;
         for (auto& kv : views) {
             const bool active =
@@ -1193,6 +1265,7 @@ void orc_match_images(void* h, float sp, float sa, unsigned nn, float eo, int kn
     ((Line3D*)h)->matchImages(sp, sa, nn, eo, knn, crd);
 }
 void orc_reconstruct(void* h) { ((Line3D*)h)->reconstruct(); }
+void orc_reconstruct_collin(void* h, float collinearity_t) { ((Line3D*)h)->reconstruct(collinearity_t); }
 
 int orc_num_pairs(void* h) { return (int)((Line3D*)h)->pair_log.size(); }
 void orc_get_pairs(void* h, uint32_t* out)

@@ -198,8 +198,13 @@ class OracleLine3D:
         self.L.orc_match_images(self.h, sigma_p, sigma_a, int(num_neighbors), epipolar_overlap, int(knn),
                                 const_reg_depth)
 
-    def reconstruct(self):
-        self.L.orc_reconstruct(self.h)
+    def reconstruct(self, collinearity_t=-1.0):
+        """Line3D::reconstruct3Dlines up to the clustering; collinearity_t > 0 adds the links to collinear
+        segments (src/line3D.cc:2328-2396), which the CUDA product does not build yet."""
+        if collinearity_t > 1e-12:
+            self.L.orc_reconstruct_collin(self.h, C.c_float(collinearity_t))
+        else:
+            self.L.orc_reconstruct(self.h)
 
     # ---- results ----
     def pairs(self):
