@@ -124,3 +124,42 @@ def test_cuda_reproduces_golden_stream(api, scene_mod):
     dig, sizes = stream_utils.stream_digests(stream, l3, calls)
     assert (sizes == g["sizes"]).all()
     assert (dig == g["digests"]).all(), np.nonzero((dig != g["digests"]).any(axis=1))[0]
+
+
+def test_world_point_neighbours_randomised(api, oracle, scene_mod):
+    """The three counting paths of the host-side neighbour selection (bit rows, dense counting walk, sparse
+    key sort) against the oracle's restatement of Line3D::findVisualNeighborsFromWPs on random world-point
+    lists: few / many points, duplicates inside a list, huge ids, views without points."""
+    rng = np.random.default_rng(2026)
+    found = 0
+    for trial in range(24):
+        sc = scene_mod.make_scene("tiny", n_views=10, n_seg=40, nbrs=3, seed=100 + trial)
+        n_pts = int(rng.choice([30, 200, 3000]))
+        big = trial % 3 == 2                      # sparse ids
+        dup = trial % 4 == 1                      # a list names points twice
+        for v in sc.views:
+            k = int(rng.integers(0, min(n_pts, 150)))
+            ids = rng.choice(n_pts, size=k, replace=False)
+            if dup and k > 4:
+                ids = np.concatenate([ids, ids[:k // 3]])
+            if big:
+                ids = (ids.astype(np.uint64) * 2654435761 + 977) % (1 << 32)
+            v.worldpoints = [int(x) for x in ids]
+        if all(len(v.worldpoints) == 0 for v in sc.views):
+            continue
+        sc.neighbors_by_worldpoints = True
+        nn = int(rng.choice([2, 3, 6]))
+        o = oracle.OracleLine3D(sc.max_image_width, True)
+        for v in sc.views:                        # addImage refuses an empty list; such views simply stay out
+            if len(v.worldpoints):
+                o.add_image(v.cam_id, v.K, v.R, v.t, v.width, v.height, v.median_depth, v.worldpoints, v.segs)
+                o.update_image(v.cam_id, v.R, v.t, v.median_depth, v.worldpoints)
+        p = sc.params
+        o.match_images(p["sigma_p"], p["sigma_a"], nn, p["epipolar_overlap"], p["knn"], p["const_reg_depth"])
+        sc.views = [v for v in sc.views if len(v.worldpoints)]
+        got = api.neighbors_from_worldpoints(sc, nn)
+        for v in sc.views:
+            assert got[v.cam_id] == list(o.neighbors(v.cam_id)), (trial, v.cam_id, n_pts, big, dup)
+            found += len(got[v.cam_id])
+        o.close()
+    assert found > 150
