@@ -183,3 +183,30 @@ def test_find_collinear_known_answer(oracle):
     t1 = oracle.find_collinear(L, 1.0)              # the 1.5 px neighbours drop out
     assert t1.tolist() == [[0, 1, 0, 0, 0], [1, 0, 0, 0, 0], [0] * 5, [0] * 5, [0] * 5]
     assert (oracle.find_collinear(L, 4.0)[0] == [0, 1, 0, 1, 1]).all()   # 3.92 px < 4 px: segment 4 joins
+
+
+def test_sparse_matrix_against_an_independent_sort(oracle):
+    """The oracle's SparseMatrix restatement against numpy's lexsort on random A_-shaped edge lists
+    (every directed pair at most once, as Line3D::unused guarantees)."""
+    rng = np.random.default_rng(7)
+    for n, m in ((5, 6), (40, 300), (500, 4000)):
+        pairs = set()
+        while len(pairs) < m:
+            i, j = rng.integers(0, n, size=2)
+            if i != j:
+                pairs.add((int(i), int(j)))
+        und = sorted({tuple(sorted(p)) for p in pairs})
+        rng.shuffle(und)
+        ij = np.array([q for (a, b) in und for q in ((a, b), (b, a))], dtype=np.int32)
+        w = np.repeat(rng.uniform(0.5, 1.0, size=len(und)).astype(np.float32), 2)
+        for by_row in (False, True):
+            ent, st = oracle.sparse_matrix(ij, w, n, 1.0, by_row)
+            prim, sec = (ij[:, 0], ij[:, 1]) if by_row else (ij[:, 1], ij[:, 0])
+            order = np.lexsort((sec, prim))
+            assert (ent[:, 0] == ij[order, 0]).all() and (ent[:, 1] == ij[order, 1]).all()
+            assert (ent[:, 2].view(np.uint32) == w[order].view(np.uint32)).all()
+            want = np.full(n, -1, dtype=np.int64)
+            ps = prim[order]
+            first = np.r_[True, ps[1:] != ps[:-1]]
+            want[ps[first]] = np.nonzero(first)[0]
+            assert (st == want).all()
