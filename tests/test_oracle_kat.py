@@ -210,3 +210,33 @@ def test_sparse_matrix_against_an_independent_sort(oracle):
             first = np.r_[True, ps[1:] != ps[:-1]]
             want[ps[first]] = np.nonzero(first)[0]
             assert (st == want).all()
+
+
+def test_find_collinear_against_numpy(oracle, scene_mod):
+    """View::findCollinCPU restated a second time, vectorised in numpy with the same operation widths
+    (double cross products and dot tests, sqrtf of the float-rounded squared norm, float maxima)."""
+    base = scene_mod.make_scene("tiny").views[2].segs.astype(np.float32)
+    a, b = base[:40, :2], base[:40, 2:]
+    segs = np.ascontiguousarray(np.concatenate([np.concatenate([a, a + 0.4 * (b - a)], axis=1),
+                                                np.concatenate([a + 0.62 * (b - a), b], axis=1), base[40:]]).astype(np.float32))
+    n = len(segs)
+    P0 = np.stack([segs[:, 0], segs[:, 1], np.ones(n)], axis=1).astype(np.float64)
+    P1 = np.stack([segs[:, 2], segs[:, 3], np.ones(n)], axis=1).astype(np.float64)
+    L = np.cross(P0, P1)                                            # line of every segment
+
+    def on_seg(p1, p2, x):                                         # (n,1,3),(n,1,3),(1,n,3) -> (n,n)
+        return ((p1[..., 0] - x[..., 0]) * (p2[..., 0] - x[..., 0]) + (p1[..., 1] - x[..., 1]) * (p2[..., 1] - x[..., 1])) < 1e-12
+
+    def dist(l, p):
+        num = l[..., 0] * p[..., 0] + l[..., 1] * p[..., 1] + l[..., 2]
+        den = np.sqrt((l[..., 0] * l[..., 0] + l[..., 1] * l[..., 1]).astype(np.float32))   # sqrtf(float)
+        return np.abs(num / den.astype(np.float64)).astype(np.float32)
+    r0, r1, c0, c1 = P0[:, None, :], P1[:, None, :], P0[None, :, :], P1[None, :, :]
+    overlap = on_seg(r0, r1, c0) | on_seg(r0, r1, c1) | on_seg(c0, c1, r0) | on_seg(c0, c1, r1)
+    d1 = np.maximum(dist(L[:, None, :], c0), dist(L[:, None, :], c1))
+    d2 = np.maximum(dist(L[None, :, :], r0), dist(L[None, :, :], r1))
+    for t in (0.75, 2.0, 6.0):
+        want = (~overlap) & (np.maximum(d1, d2) < np.float32(t))
+        np.fill_diagonal(want, False)
+        got = oracle.find_collinear(segs, t)
+        assert (got.astype(bool) == want).all() and want.sum() >= 80
