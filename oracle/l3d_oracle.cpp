@@ -155,6 +155,7 @@ struct View {
     V3 t, C, pp;
     unsigned width = 0, height = 0;
     float k = 0.0f, median_depth = 0.0f, median_sigma = 0.0f, initial_median_depth = 0.0f;
+    V3 C_match{0, 0, 0};  // test hook: the (translated) centre matchImages worked with
 
     void init(uint32_t id_, const M3& K_, const M3& R_, const V3& t_, unsigned w, unsigned h,
               float med_depth)
@@ -962,6 +963,7 @@ class Line3D {
         med_scene_depth = const_reg_depth;
         // (metric-sigma median-depth quirk of line3D.cc:557-565 not restated: SURVEY.md App. B)
         translate();
+        for (uint32_t camID : view_order) views[camID]->C_match = views[camID]->C;
         for (uint32_t camID : view_order) {
             if (!fixed3Dreg)
                 views[camID]->k = views[camID]->specificSpatialReg(sigma_p);
@@ -1436,6 +1438,17 @@ int orc_get_view_info(void* h, uint32_t cam, double* C, float* kmm)
     kmm[0] = f->second->k;
     kmm[1] = f->second->median_depth;
     kmm[2] = f->second->median_sigma;
+    return 0;
+}
+// test hook: the camera exactly as the last matchImages saw it (RtKinv row-major, translated centre)
+int orc_get_match_camera(void* h, uint32_t cam, double* RtKinv9, double* C3)
+{
+    Line3D* L = (Line3D*)h;
+    auto f = L->views.find(cam);
+    if (f == L->views.end()) return -1;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) RtKinv9[3 * i + j] = f->second->RtKinv.m[i][j];
+    C3[0] = f->second->C_match.x; C3[1] = f->second->C_match.y; C3[2] = f->second->C_match.z;
     return 0;
 }
 int orc_get_neighbors(void* h, uint32_t cam, uint32_t* out, int cap)

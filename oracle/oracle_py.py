@@ -262,6 +262,14 @@ class OracleLine3D:
         assert rc == 0
         return dict(C=Cc, k=kmm[0], median_depth=kmm[1], median_sigma=kmm[2])
 
+    def match_camera(self, cam_id):
+        """(RtKinv 3x3, translated centre) exactly as the last match_images used them (test hook)."""
+        M = np.zeros(9)
+        Cc = np.zeros(3)
+        rc = self.L.orc_get_match_camera(self.h, int(cam_id), _p(M), _p(Cc))
+        assert rc == 0
+        return M.reshape(3, 3), Cc
+
     def neighbors(self, cam_id, cap=256):
         out = np.zeros(cap, dtype=np.uint32)
         n = self.L.orc_get_neighbors(self.h, int(cam_id), _p(out), cap)

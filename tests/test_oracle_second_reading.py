@@ -119,3 +119,104 @@ def test_matching_second_reading_equals_the_oracle(oracle, scene_mod):
             assert (got.view(np.uint32) == rec[name].view(np.uint32)).all(), (ia, ib, name)
         n_total += len(rec)
     assert n_total > 1000
+
+
+def _score_row_numpy(seg, entries, cam, cams, k_of, two_sigA_sqr, expf, acosf):
+    """Line3D::scoringCPU, new-match branch (src/line3D.cc:1513-1547) for ONE row, read a second time:
+    similarityForScoring (:1685-1716), angleBetweenSeg3D (:1841-1853), View::unprojectSegment
+    (src/view.cc:385-400), Segment3D ctor (include/segment3D.h:58-77), regularizerFrom3Dpoint (src/view.cc:474-477).
+    `entries` = the row's matches in list order (tgt_cam, d_p1, d_p2); returns their score3D_."""
+    M, C = cams[cam]
+    p1 = np.array([float(seg[0]), float(seg[1]), 1.0])
+    p2 = np.array([float(seg[2]), float(seg[3]), 1.0])
+    r1, r2 = _normalized(_matvec(M, p1)), _normalized(_matvec(M, p2))
+    k = np.float32(k_of[cam])
+    geo = []
+    for tgt_cam, d1, d2 in entries:
+        P1 = C + r1 * float(d1)
+        P2 = C + r2 * float(d2)
+        d = P1 - P2
+        length = np.float32(np.sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]))
+        if length > 1e-12:
+            dirv = _normalized(P2 - P1)
+        else:
+            P1 = P2 = dirv = np.zeros(3)
+            length = np.float32(0.0)
+        sig1, sig2 = np.float32(d1) * k, np.float32(d2) * k
+        reg1 = np.float32(2.0) * sig1 * sig1
+        reg2 = np.float32(2.0) * sig2 * sig2
+        Ct, kt = cams[tgt_cam][1], np.float32(k_of[tgt_cam])
+        e1, e2 = P1 - Ct, P2 - Ct
+        s1t = np.float32(np.sqrt(e1[0] * e1[0] + e1[1] * e1[1] + e1[2] * e1[2]) * float(kt))
+        s2t = np.float32(np.sqrt(e2[0] * e2[0] + e2[1] * e2[1] + e2[2] * e2[2]) * float(kt))
+        reg1 = np.float32(0.5) * (reg1 + np.float32(2.0) * s1t * s1t)
+        reg2 = np.float32(0.5) * (reg2 + np.float32(2.0) * s2t * s2t)
+        geo.append((length, dirv, reg1, reg2))
+    out = []
+    for a, (cam_a, da1, da2) in enumerate(entries):
+        la, dir_a, reg1, reg2 = geo[a]
+        score = np.float32(0.0)
+        per_cam = {}
+        for b, (cam_b, db1, db2) in enumerate(entries):
+            if cam_b == cam_a:
+                continue
+            lb, dir_b, _, _ = geo[b]
+            if la < 1e-12 or lb < 1e-12:
+                sim = np.float32(0.0)
+            else:
+                d1 = np.float32(da1) - np.float32(db1)
+                d2 = np.float32(da2) - np.float32(db2)
+                sim_p = min(expf(-d1 * d1 / reg1), expf(-d2 * d2 / reg2))
+                dot_p = np.float32(dir_a[0] * dir_b[0] + dir_a[1] * dir_b[1] + dir_a[2] * dir_b[2])
+                ang = np.float32(float(acosf(np.float32(max(min(dot_p, np.float32(1.0)), np.float32(-1.0))))) / np.pi * 180.0)
+                if ang > np.float32(90.0):
+                    ang = np.float32(180.0) - ang
+                sim_a = expf(-ang * ang / np.float32(two_sigA_sqr))
+                sim = min(sim_a, sim_p)
+                if not sim > np.float32(0.5):
+                    sim = np.float32(0.0)
+            if cam_b in per_cam:
+                if sim > per_cam[cam_b]:
+                    score = score - per_cam[cam_b]
+                    score = score + sim
+                    per_cam[cam_b] = sim
+            else:
+                score = score + sim
+                per_cam[cam_b] = sim
+        out.append(score)
+    return np.array(out, dtype=np.float32)
+
+
+def test_scoring_second_reading_equals_the_oracle(oracle, scene_mod):
+    import ctypes as C
+    L = oracle.lib()
+    L.orc_kat_expf.restype = C.c_float
+    L.orc_kat_expf.argtypes = [C.c_float]
+    L.orc_kat_acosf.restype = C.c_float
+    L.orc_kat_acosf.argtypes = [C.c_float]
+
+    def expf(x):
+        return np.float32(L.orc_kat_expf(float(np.float32(x))))
+
+    def acosf(x):
+        return np.float32(L.orc_kat_acosf(float(np.float32(x))))
+    sc = scene_mod.make_scene("tiny")
+    o = oracle.run_scene(sc)
+    cams = {v.cam_id: o.match_camera(v.cam_id) for v in sc.views}
+    k_of = {v.cam_id: o.view_info(v.cam_id)["k"] for v in sc.views}
+    checked = positive = 0
+    with np.errstate(over="ignore", under="ignore"):
+        for v in (sc.views[0], sc.views[3], sc.views[7]):      # first view: forward matches only; others: inverse too
+            off, rec = o.lists(v.cam_id, 0)                    # lists as scored (before filterMatches)
+            cand = [r for r in range(len(off) - 1) if 2 <= off[r + 1] - off[r] <= 40]
+            hot = [r for r in cand if (rec["score"][off[r]:off[r + 1]] > 0).any()]     # rows where something scores
+            rows = hot[:25] + [r for r in cand if r not in hot][:10]
+            for r in rows:
+                e = rec[off[r]:off[r + 1]]
+                got = _score_row_numpy(v.segs[r], list(zip(e["tgt_cam"].tolist(), e["d_p1"], e["d_p2"])), v.cam_id, cams,
+                                       k_of, 200.0, expf, acosf)
+                assert (got.view(np.uint32) == e["score"].view(np.uint32)).all(), (v.cam_id, r, got, e["score"])
+                checked += len(e)
+                positive += int((got > 0).sum())
+    assert checked > 1000 and positive > 100
+    o.close()
