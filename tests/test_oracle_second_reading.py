@@ -220,3 +220,63 @@ def test_scoring_second_reading_equals_the_oracle(oracle, scene_mod):
                 positive += int((got > 0).sum())
     assert checked > 1000 and positive > 100
     o.close()
+
+
+def test_affinity_similarity_second_reading_equals_the_oracle(oracle, scene_mod):
+    """Line3D::similarity(Segment3D, Match, Segment2D, false) (src/line3D.cc:1737-1823) with
+    Segment3D::distance_Point2Line (include/segment3D.h:80-84, evaluated as (dir * diff^T) * dir) read a second
+    time in numpy: every weight of A_ is reproduced from estimated_position3D_, the views' k / median depth and
+    the median scene depth of the lines."""
+    import ctypes as C
+    L = oracle.lib()
+    L.orc_kat_expf.restype = C.c_float
+    L.orc_kat_expf.argtypes = [C.c_float]
+    L.orc_kat_acosf.restype = C.c_float
+    L.orc_kat_acosf.argtypes = [C.c_float]
+    f32 = np.float32
+
+    def expf(x):
+        return f32(L.orc_kat_expf(float(f32(x))))
+
+    def acosf(x):
+        return f32(L.orc_kat_acosf(float(f32(x))))
+
+    def d_p2l(P1, dirv, P):
+        d = P - P1
+        h = np.array([(dirv[i] * d[0]) * dirv[0] + (dirv[i] * d[1]) * dirv[1] + (dirv[i] * d[2]) * dirv[2] for i in range(3)])
+        e = (P1 + h) - P
+        return f32(np.sqrt(e[0] * e[0] + e[1] * e[1] + e[2] * e[2]))
+    sc = scene_mod.make_scene("tiny")
+    o = oracle.run_scene(sc)
+    ent = {(int(e["src_cam"]), int(e["src_seg"])): e for e in o.entries()}
+    info = {v.cam_id: o.view_info(v.cam_id) for v in sc.views}
+    msdl = f32(o.med_scene_depth_lines())
+    ij, w = o.edges()
+    l2g = [tuple(x) for x in o.local2global().tolist()]
+    assert len(w) > 150
+    with np.errstate(over="ignore", under="ignore"):
+        for k in range(0, len(w), 2):
+            a, b = ent[l2g[ij[k, 0]]], ent[l2g[ij[k, 1]]]
+            va, vb = info[int(a["src_cam"])], info[int(b["src_cam"])]
+            dot_p = f32(a["dir"][0] * b["dir"][0] + a["dir"][1] * b["dir"][1] + a["dir"][2] * b["dir"][2])
+            ang = f32(float(acosf(f32(max(min(dot_p, f32(1.0)), f32(-1.0))))) / np.pi * 180.0)
+            if ang > f32(90.0):
+                ang = f32(180.0) - ang
+            sim_a = expf(-ang * ang / f32(200.0))
+            c1, c2 = f32(va["median_depth"]), f32(vb["median_depth"])
+            if msdl > 1e-12:
+                c1, c2 = min(c1, msdl), min(c2, msdl)
+            d11, d12 = d_p2l(b["P1"], b["dir"], a["P1"]), d_p2l(b["P1"], b["dir"], a["P2"])
+            d21, d22 = d_p2l(a["P1"], a["dir"], b["P1"]), d_p2l(a["P1"], a["dir"], b["P2"])
+            ka, kb = f32(va["k"]), f32(vb["k"])
+            s11 = (c1 if a["d_p1"] > c1 else f32(a["d_p1"])) * ka
+            s12 = (c1 if a["d_p2"] > c1 else f32(a["d_p2"])) * ka
+            s21 = (c2 if b["d_p1"] > c2 else f32(b["d_p1"])) * kb
+            s22 = (c2 if b["d_p2"] > c2 else f32(b["d_p2"])) * kb
+            r11, r12, r21, r22 = f32(2.0) * s11 * s11, f32(2.0) * s12 * s12, f32(2.0) * s21 * s21, f32(2.0) * s22 * s22
+            sp1 = min(expf(-d11 * d11 / r11), expf(-d12 * d12 / r12))
+            sp2 = min(expf(-d21 * d21 / r21), expf(-d22 * d22 / r22))
+            sim = min(sim_a, min(sp1, sp2))
+            assert f32(sim).tobytes() == f32(w[k]).tobytes(), (k, sim, w[k])
+            assert sim > f32(0.5)
+    o.close()
