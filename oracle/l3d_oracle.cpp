@@ -1451,6 +1451,17 @@ int orc_get_match_camera(void* h, uint32_t cam, double* RtKinv9, double* C3)
     C3[0] = f->second->C_match.x; C3[1] = f->second->C_match.y; C3[2] = f->second->C_match.z;
     return 0;
 }
+// test hook: the fundamental matrix the last matchImages cached for the ordered pair (src, tgt), row-major
+int orc_get_fundamental(void* h, uint32_t src, uint32_t tgt, double* F9)
+{
+    Line3D* L = (Line3D*)h;
+    auto fs = L->fundamentals.find(src);
+    if (fs == L->fundamentals.end() || !fs->second.count(tgt)) return -1;
+    const M3& F = fs->second[tgt];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) F9[3 * i + j] = F.m[i][j];
+    return 0;
+}
 int orc_get_neighbors(void* h, uint32_t cam, uint32_t* out, int cap)
 {
     Line3D* L = (Line3D*)h;

@@ -270,6 +270,13 @@ class OracleLine3D:
         assert rc == 0
         return M.reshape(3, 3), Cc
 
+    def fundamental(self, src, tgt):
+        """F cached by the last match_images for the ordered pair (src, tgt), or None (test hook)."""
+        F = np.zeros(9)
+        if self.L.orc_get_fundamental(self.h, int(src), int(tgt), _p(F)) != 0:
+            return None
+        return F.reshape(3, 3)
+
     def neighbors(self, cam_id, cap=256):
         out = np.zeros(cap, dtype=np.uint32)
         n = self.L.orc_get_neighbors(self.h, int(cam_id), _p(out), cap)

@@ -280,3 +280,56 @@ def test_affinity_similarity_second_reading_equals_the_oracle(oracle, scene_mod)
             assert f32(sim).tobytes() == f32(w[k]).tobytes(), (k, sim, w[k])
             assert sim > f32(0.5)
     o.close()
+
+
+def test_orientation_filter_second_reading_equals_the_oracle(oracle, scene_mod):
+    """Line3D::checkMatchOrientation (src/line3D.cc:962-1014) with View::segmentQualityAngle (src/view.cc:495-513):
+    with kNN off, the list of the FIRST view at scoring time is exactly its forward matches (targets ascending) that
+    pass the orientation test -- recomputed here from the numpy matching above plus a numpy orientation predicate,
+    with the cameras and fundamental matrices matchImages used."""
+    import ctypes as C
+    L = oracle.lib()
+    L.orc_kat_acos.restype = C.c_double
+    L.orc_kat_acos.argtypes = [C.c_double]
+    sc = scene_mod.make_scene("tiny", n_seg=120)
+    sc.params = dict(sc.params, knn=-1)
+    o = oracle.run_scene(sc)
+    v = sc.views[0]
+    off, rec = o.lists(v.cam_id, 0)
+    Ms, Cs = o.match_camera(v.cam_id)
+    per_row = [[] for _ in range(len(v.segs))]
+    rejected = []
+    for tgt in sorted(o.neighbors(v.cam_id)):
+        F = o.fundamental(v.cam_id, tgt)
+        assert F is not None                       # view 0 is the source of all its pairs
+        vt = next(x for x in sc.views if x.cam_id == tgt)
+        Mt, Ct = o.match_camera(tgt)
+        rows, cols, ov, d1, d2, d3, d4 = _match_pair_numpy(v.segs, vt.segs, F, Ms, Mt, Cs, Ct, sc.max_image_width, 0.25)
+        for r, c, a, x1, x2, x3, x4 in zip(rows, cols, ov, d1, d2, d3, d4):
+            s = v.segs[r]
+            p1 = np.array([float(s[0]), float(s[1]), 1.0])
+            p2 = np.array([float(s[2]), float(s[3]), 1.0])
+            P1 = Cs + _normalized(_matvec(Ms, p1)) * float(x1)
+            P2 = Cs + _normalized(_matvec(Ms, p2)) * float(x2)
+            d = P1 - P2
+            length = np.float32(np.sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]))
+            dirv = _normalized(P2 - P1) if length > 1e-12 else np.zeros(3)
+            mid = np.array([0.5 * (float(s[0]) + float(s[2])), 0.5 * (float(s[1]) + float(s[3])), 1.0])
+            rm = _normalized(_matvec(Ms, mid))
+            dotp = rm[0] * dirv[0] + rm[1] * dirv[1] + rm[2] * dirv[2]
+            ang = L.orc_kat_acos(min(max(float(dotp), -1.0), 1.0))
+            if ang > float(np.float32(0.098174771)) and ang < float(np.float32(3.043417886)):
+                per_row[r].append((tgt, int(c), a, x1, x2, x3, x4))
+            else:
+                rejected.append((r, tgt, int(c)))
+    n = 0
+    for r in range(len(v.segs)):
+        e = rec[off[r]:off[r + 1]]
+        assert len(e) == len(per_row[r]), r
+        for x, y in zip(e, per_row[r]):
+            assert int(x["tgt_cam"]) == y[0] and int(x["tgt_seg"]) == y[1]
+            for name, val in (("overlap", y[2]), ("d_p1", y[3]), ("d_p2", y[4]), ("d_q1", y[5]), ("d_q2", y[6])):
+                assert np.float32(x[name]).tobytes() == np.float32(val).tobytes(), (r, name)
+        n += len(e)
+    assert n > 300 and len(rejected) > 0          # the filter did reject something
+    o.close()
