@@ -333,3 +333,82 @@ def test_orientation_filter_second_reading_equals_the_oracle(oracle, scene_mod):
         n += len(e)
     assert n > 300 and len(rejected) > 0          # the filter did reject something
     o.close()
+
+
+def test_filter_matches_second_reading_equals_the_oracle(oracle, scene_mod):
+    """Line3D::filterMatches (src/line3D.cc:1911-1983) read a second time: from the lists as scored, the kept
+    entries (score > 0 and > 10 % of the view's maximum), the first strict maximum as best match, the
+    hypothesis of every row whose best match scores > 0.75 (unprojectMatch, :1826-1838) and the view's median
+    depth (View::update_median_depth, include/view.h:122-135)."""
+    sc = scene_mod.make_scene("tiny")
+    o = oracle.run_scene(sc)
+    ent = {(int(e["src_cam"]), int(e["src_seg"])): e for e in o.entries()}
+    n_ent = 0
+    for v in sc.views:
+        off0, rec0 = o.lists(v.cam_id, 0)
+        off1, rec1 = o.lists(v.cam_id, 1)
+        M, Cm = o.match_camera(v.cam_id)
+        max_score = np.float32(0.0)
+        for s in rec0["score"]:
+            max_score = max(max_score, np.float32(s))
+        lim = np.float32(0.1) * max_score
+        depths = []
+        for r in range(len(v.segs)):
+            e = rec0[off0[r]:off0[r + 1]]
+            kept = [x for x in e if x["score"] > np.float32(0.0) and x["score"] > lim]
+            got = rec1[off1[r]:off1[r + 1]]
+            assert len(kept) == len(got) and all(a.tobytes() == b.tobytes() for a, b in zip(kept, got)), (v.cam_id, r)
+            best, best_score = None, np.float32(0.0)
+            for x in kept:
+                if x["score"] > best_score:
+                    best, best_score = x, x["score"]
+            if best is not None and best_score > np.float32(0.75):
+                E = ent[(v.cam_id, r)]
+                s = v.segs[r]
+                P1 = Cm + _normalized(_matvec(M, np.array([float(s[0]), float(s[1]), 1.0]))) * float(best["d_p1"])
+                P2 = Cm + _normalized(_matvec(M, np.array([float(s[2]), float(s[3]), 1.0]))) * float(best["d_p2"])
+                assert (E["P1"] == P1).all() and (E["P2"] == P2).all() and (E["dir"] == _normalized(P2 - P1)).all()
+                assert int(E["tgt_cam"]) == int(best["tgt_cam"]) and int(E["tgt_seg"]) == int(best["tgt_seg"])
+                assert E["score"] == best["score"] and E["d_p1"] == best["d_p1"] and E["d_q2"] == best["d_q2"]
+                depths += [np.float32(best["d_p1"]), np.float32(best["d_p2"])]
+                n_ent += 1
+            else:
+                assert (v.cam_id, r) not in ent
+        med = np.float32(1e-12) if not depths else sorted(depths)[len(depths) // 2]
+        info = o.view_info(v.cam_id)
+        assert np.float32(info["median_depth"]).tobytes() == np.float32(med).tobytes()
+        assert np.float32(info["median_sigma"]).tobytes() == (np.float32(info["k"]) * np.float32(med)).tobytes()
+    assert n_ent == len(ent) > 80
+    o.close()
+
+
+def test_inverse_matches_second_reading_equals_the_oracle(oracle, scene_mod):
+    """Line3D::storeInverseMatches (src/line3D.cc:1986-2015): every match that scored > 0 in a view processed
+    earlier appears, with views and depths swapped, score 0 and the orientation flag set, in the list of its
+    target segment -- pushed in the order the sources were processed (camera id, row, list position), ahead of
+    the target view's own forward matches."""
+    sc = scene_mod.make_scene("tiny")
+    o = oracle.run_scene(sc)
+    lists = {v.cam_id: o.lists(v.cam_id, 0) for v in sc.views}       # as scored
+    expect = {v.cam_id: [[] for _ in range(len(v.segs))] for v in sc.views}
+    for v in sc.views:                                                # ascending camera id = processing order
+        off, rec = lists[v.cam_id]
+        for r in range(len(v.segs)):
+            for x in rec[off[r]:off[r + 1]]:
+                if x["score"] > np.float32(0.0) and int(x["tgt_cam"]) > v.cam_id:      # target not processed yet
+                    expect[int(x["tgt_cam"])][int(x["tgt_seg"])].append(
+                        (v.cam_id, r, x["overlap"], x["d_q1"], x["d_q2"], x["d_p1"], x["d_p2"]))
+    n_inv = 0
+    for v in sc.views:
+        off, rec = lists[v.cam_id]
+        for r in range(len(v.segs)):
+            e = rec[off[r]:off[r + 1]]
+            inv = [x for x in e if x["flags"] == 1]
+            assert len(inv) == len(expect[v.cam_id][r]), (v.cam_id, r)
+            assert list(e["flags"]) == [1] * len(inv) + [0] * (len(e) - len(inv))      # inverse first, then forward
+            for x, y in zip(inv, expect[v.cam_id][r]):
+                assert (int(x["tgt_cam"]), int(x["tgt_seg"])) == (y[0], y[1])
+                assert (x["overlap"], x["d_p1"], x["d_p2"], x["d_q1"], x["d_q2"]) == y[2:]
+            n_inv += len(inv)
+    assert n_inv > 200
+    o.close()
