@@ -222,11 +222,7 @@ def test_scoring_second_reading_equals_the_oracle(oracle, scene_mod):
     o.close()
 
 
-def test_affinity_similarity_second_reading_equals_the_oracle(oracle, scene_mod):
-    """Line3D::similarity(Segment3D, Match, Segment2D, false) (src/line3D.cc:1737-1823) with
-    Segment3D::distance_Point2Line (include/segment3D.h:80-84, evaluated as (dir * diff^T) * dir) read a second
-    time in numpy: every weight of A_ is reproduced from estimated_position3D_, the views' k / median depth and
-    the median scene depth of the lines."""
+def _det_funcs(oracle):
     import ctypes as C
     L = oracle.lib()
     L.orc_kat_expf.restype = C.c_float
@@ -234,51 +230,83 @@ def test_affinity_similarity_second_reading_equals_the_oracle(oracle, scene_mod)
     L.orc_kat_acosf.restype = C.c_float
     L.orc_kat_acosf.argtypes = [C.c_float]
     f32 = np.float32
+    return (lambda x: f32(L.orc_kat_expf(float(f32(x))))), (lambda x: f32(L.orc_kat_acosf(float(f32(x)))))
 
-    def expf(x):
-        return f32(L.orc_kat_expf(float(f32(x))))
 
-    def acosf(x):
-        return f32(L.orc_kat_acosf(float(f32(x))))
+def _affinity_sim_numpy(a, b, va, vb, msdl, expf, acosf):
+    """Line3D::similarity(Segment3D, Match, Segment2D, false) (src/line3D.cc:1737-1823) for two rows of
+    estimated_position3D_ (a, b) and their views' (k, median depth); Segment3D::distance_Point2Line
+    (include/segment3D.h:80-84) evaluated as (dir * diff^T) * dir."""
+    f32 = np.float32
 
     def d_p2l(P1, dirv, P):
         d = P - P1
         h = np.array([(dirv[i] * d[0]) * dirv[0] + (dirv[i] * d[1]) * dirv[1] + (dirv[i] * d[2]) * dirv[2] for i in range(3)])
         e = (P1 + h) - P
         return f32(np.sqrt(e[0] * e[0] + e[1] * e[1] + e[2] * e[2]))
+    if a["length"] < 1e-12 or b["length"] < 1e-12:
+        return f32(0.0)
+    dot_p = f32(a["dir"][0] * b["dir"][0] + a["dir"][1] * b["dir"][1] + a["dir"][2] * b["dir"][2])
+    ang = f32(float(acosf(f32(max(min(dot_p, f32(1.0)), f32(-1.0))))) / np.pi * 180.0)
+    if ang > f32(90.0):
+        ang = f32(180.0) - ang
+    sim_a = expf(-ang * ang / f32(200.0))
+    c1, c2 = f32(va["median_depth"]), f32(vb["median_depth"])
+    if msdl > 1e-12:
+        c1, c2 = min(c1, msdl), min(c2, msdl)
+    d11, d12 = d_p2l(b["P1"], b["dir"], a["P1"]), d_p2l(b["P1"], b["dir"], a["P2"])
+    d21, d22 = d_p2l(a["P1"], a["dir"], b["P1"]), d_p2l(a["P1"], a["dir"], b["P2"])
+    ka, kb = f32(va["k"]), f32(vb["k"])
+    s11 = (c1 if a["d_p1"] > c1 else f32(a["d_p1"])) * ka
+    s12 = (c1 if a["d_p2"] > c1 else f32(a["d_p2"])) * ka
+    s21 = (c2 if b["d_p1"] > c2 else f32(b["d_p1"])) * kb
+    s22 = (c2 if b["d_p2"] > c2 else f32(b["d_p2"])) * kb
+    r11, r12, r21, r22 = f32(2.0) * s11 * s11, f32(2.0) * s12 * s12, f32(2.0) * s21 * s21, f32(2.0) * s22 * s22
+    sp1 = min(expf(-d11 * d11 / r11), expf(-d12 * d12 / r12))
+    sp2 = min(expf(-d21 * d21 / r21), expf(-d22 * d22 / r22))
+    return f32(min(sim_a, min(sp1, sp2)))
+
+
+def test_affinity_matrix_second_reading_equals_the_oracle(oracle, scene_mod):
+    """Line3D::computingAffinityMatrix (src/line3D.cc:2275-2402, collinearity off) with Line3D::unused
+    (:2405-2425) and getLocalID (:2428-2446) read a second time: walking estimated_position3D_ and the filtered
+    lists reproduces A_ -- every (i, j, w), (j, i, w) pair in order -- and local2global_."""
+    expf, acosf = _det_funcs(oracle)
     sc = scene_mod.make_scene("tiny")
     o = oracle.run_scene(sc)
-    ent = {(int(e["src_cam"]), int(e["src_seg"])): e for e in o.entries()}
+    entries = o.entries()
+    ent = {(int(e["src_cam"]), int(e["src_seg"])): e for e in entries}
     info = {v.cam_id: o.view_info(v.cam_id) for v in sc.views}
-    msdl = f32(o.med_scene_depth_lines())
-    ij, w = o.edges()
-    l2g = [tuple(x) for x in o.local2global().tolist()]
-    assert len(w) > 150
+    lists = {v.cam_id: o.lists(v.cam_id, 1) for v in sc.views}
+    msdl = np.float32(o.med_scene_depth_lines())
+    A, ids, used = [], {}, set()
+
+    def local_id(seg):
+        if seg not in ids:
+            ids[seg] = len(ids)
+        return ids[seg]
     with np.errstate(over="ignore", under="ignore"):
-        for k in range(0, len(w), 2):
-            a, b = ent[l2g[ij[k, 0]]], ent[l2g[ij[k, 1]]]
-            va, vb = info[int(a["src_cam"])], info[int(b["src_cam"])]
-            dot_p = f32(a["dir"][0] * b["dir"][0] + a["dir"][1] * b["dir"][1] + a["dir"][2] * b["dir"][2])
-            ang = f32(float(acosf(f32(max(min(dot_p, f32(1.0)), f32(-1.0))))) / np.pi * 180.0)
-            if ang > f32(90.0):
-                ang = f32(180.0) - ang
-            sim_a = expf(-ang * ang / f32(200.0))
-            c1, c2 = f32(va["median_depth"]), f32(vb["median_depth"])
-            if msdl > 1e-12:
-                c1, c2 = min(c1, msdl), min(c2, msdl)
-            d11, d12 = d_p2l(b["P1"], b["dir"], a["P1"]), d_p2l(b["P1"], b["dir"], a["P2"])
-            d21, d22 = d_p2l(a["P1"], a["dir"], b["P1"]), d_p2l(a["P1"], a["dir"], b["P2"])
-            ka, kb = f32(va["k"]), f32(vb["k"])
-            s11 = (c1 if a["d_p1"] > c1 else f32(a["d_p1"])) * ka
-            s12 = (c1 if a["d_p2"] > c1 else f32(a["d_p2"])) * ka
-            s21 = (c2 if b["d_p1"] > c2 else f32(b["d_p1"])) * kb
-            s22 = (c2 if b["d_p2"] > c2 else f32(b["d_p2"])) * kb
-            r11, r12, r21, r22 = f32(2.0) * s11 * s11, f32(2.0) * s12 * s12, f32(2.0) * s21 * s21, f32(2.0) * s22 * s22
-            sp1 = min(expf(-d11 * d11 / r11), expf(-d12 * d12 / r12))
-            sp2 = min(expf(-d21 * d21 / r21), expf(-d22 * d22 / r22))
-            sim = min(sim_a, min(sp1, sp2))
-            assert f32(sim).tobytes() == f32(w[k]).tobytes(), (k, sim, w[k])
-            assert sim > f32(0.5)
+        for e in entries:                                              # traversal order = estimated_position3D_ order
+            seg = (int(e["src_cam"]), int(e["src_seg"]))
+            off, rec = lists[seg[0]]
+            id1 = -1
+            for m2 in rec[off[seg[1]]:off[seg[1] + 1]]:
+                seg2 = (int(m2["tgt_cam"]), int(m2["tgt_seg"]))
+                if seg2 not in ent:
+                    continue                                           # similarity() returns 0 without an entry
+                sim = _affinity_sim_numpy(e, ent[seg2], info[seg[0]], info[seg2[0]], msdl, expf, acosf)
+                if sim > np.float32(0.5) and frozenset((seg, seg2)) not in used:
+                    used.add(frozenset((seg, seg2)))
+                    if id1 < 0:
+                        id1 = local_id(seg)
+                    id2 = local_id(seg2)
+                    A += [(id1, id2, sim), (id2, id1, sim)]
+    ij, w = o.edges()
+    assert len(A) == len(w) > 150
+    assert [(a, b) for a, b, _ in A] == [tuple(x) for x in ij.tolist()]
+    assert np.array([x for _, _, x in A], np.float32).tobytes() == w.tobytes()
+    l2g = [tuple(x) for x in o.local2global().tolist()]
+    assert [s for s, _ in sorted(ids.items(), key=lambda kv: kv[1])] == l2g
     o.close()
 
 
