@@ -9,7 +9,9 @@
 // and cannot be compiled in this environment (Eigen, Boost, OpenCV, PCL, tclap absent), so this
 // restatement is pinned only by hand-derived known-answer tests (tests/test_oracle_kat.py) -- except the
 // graph clustering, the one part that compiles from the reference's own sources (STL only): it is checked
-// against the reference itself (oracle/_ref/libref_clustering.so, tests/test_ref_clustering.py).
+// against the reference itself (oracle/_ref/libref_clustering.so, tests/test_ref_clustering.py).  Stages 1-4 are
+// additionally cross-checked, bit for bit, by a second independent reading of the reference written in numpy
+// (tests/test_oracle_second_reading.py).
 //
 // Canonical arithmetic: IEEE double/float exactly where the reference
 // uses them, scalar left-to-right sums, row-major 3x3*v, true divisions, no FMA contraction
