@@ -48,3 +48,24 @@ def test_clustering_equals_the_reference_on_scene_matrices(api, oracle, scene_mo
         assert n > 50 and (o.cluster_ids() == ref).all()
         assert (api.cluster_edges(ij, w, n) == ref).all()
         o.close()
+
+
+def test_clustering_equals_the_reference_property(api, oracle):
+    """Property test (hypothesis): arbitrary small multigraphs with heavily tied weights, self-consistent
+    A_ layout or not -- the three implementations agree on every cluster id."""
+    from hypothesis import given, settings, strategies as st
+    _ref_or_skip(oracle)
+
+    @settings(max_examples=150, deadline=None)
+    @given(st.integers(2, 12).flatmap(lambda n: st.tuples(
+        st.just(n),
+        st.lists(st.tuples(st.integers(0, n - 1), st.integers(0, n - 1), st.sampled_from([0.51, 0.6, 0.6, 0.75, 0.9, 1.0])),
+                 min_size=1, max_size=40))))
+    def check(case):
+        n, edges = case
+        ij = np.array([(a, b) for a, b, _ in edges], dtype=np.int32)
+        w = np.array([x for _, _, x in edges], dtype=np.float32)
+        ref = oracle.ref_cluster(ij, w, n)
+        assert (oracle.kat_cluster(ij, w, n) == ref).all()
+        assert (api.cluster_edges(ij, w, n) == ref).all()
+    check()
