@@ -440,3 +440,136 @@ def test_inverse_matches_second_reading_equals_the_oracle(oracle, scene_mod):
             n_inv += len(inv)
     assert n_inv > 200
     o.close()
+
+
+def test_incremental_score_deltas_second_reading_equals_the_oracle(oracle, scene_mod):
+    """The incremental branch of Line3D::scoringCPU (src/line3D.cc:1439-1512) read a second time on a key-frame
+    stream with additions, deletions and pose changes: a match scored in an earlier cycle keeps its score, plus
+    the per-camera maximum similarity to every camera added this cycle, minus that to every camera deleted this
+    cycle (both summed in ascending camera id), all evaluated with the CURRENT poses; a match that is new this
+    cycle is scored from scratch against the siblings that are not being deleted.  The forward matches that fail
+    this cycle's orientation re-test (src/line3D.cc:962-1014) are gone before scoring."""
+    import ctypes as C
+    import stream_utils
+    expf, acosf = _det_funcs(oracle)
+    L = oracle.lib()
+    L.orc_kat_acos.restype = C.c_double
+    L.orc_kat_acos.argtypes = [C.c_double]
+    f32 = np.float32
+    st = scene_mod.make_stream(n_keyframes=10, n_seg=220, window=6, nbrs=4, jitter=0.25, n_world=700, cull_every=3)
+    o, calls = stream_utils.oracle_driver(oracle, st)
+    segs = {}
+    prev = {}                     # cam -> (off, rec) filtered lists after the previous cycle
+    stats = dict(delta=0, fresh=0, adds=0, dels=0, dropped=0)
+
+    def geometry(cam, seg, d1, d2, tgt_cam, cams, kk):
+        M, Cc = cams[cam]
+        s = segs[cam][seg]
+        r1 = _normalized(_matvec(M, np.array([float(s[0]), float(s[1]), 1.0])))
+        r2 = _normalized(_matvec(M, np.array([float(s[2]), float(s[3]), 1.0])))
+        P1, P2 = Cc + r1 * float(d1), Cc + r2 * float(d2)
+        d = P1 - P2
+        length = f32(np.sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]))
+        if length > 1e-12:
+            dirv = _normalized(P2 - P1)
+        else:
+            P1 = P2 = dirv = np.zeros(3)
+            length = f32(0.0)
+        k = f32(kk[cam])
+        sig1, sig2 = f32(d1) * k, f32(d2) * k
+        reg1, reg2 = f32(2.0) * sig1 * sig1, f32(2.0) * sig2 * sig2
+        Ct, kt = cams[tgt_cam][1], f32(kk[tgt_cam])
+        e1, e2 = P1 - Ct, P2 - Ct
+        s1t = f32(np.sqrt(e1[0] * e1[0] + e1[1] * e1[1] + e1[2] * e1[2]) * float(kt))
+        s2t = f32(np.sqrt(e2[0] * e2[0] + e2[1] * e2[1] + e2[2] * e2[2]) * float(kt))
+        reg1 = f32(0.5) * (reg1 + f32(2.0) * s1t * s1t)
+        reg2 = f32(0.5) * (reg2 + f32(2.0) * s2t * s2t)
+        mid = _normalized(_matvec(M, np.array([0.5 * (float(s[0]) + float(s[2])), 0.5 * (float(s[1]) + float(s[3])), 1.0])))
+        ang = L.orc_kat_acos(min(max(float(mid[0] * dirv[0] + mid[1] * dirv[1] + mid[2] * dirv[2]), -1.0), 1.0))
+        oriented = float(f32(0.098174771)) < ang < float(f32(3.043417886))
+        return length, dirv, reg1, reg2, oriented
+
+    def sim(gm, m, g2, m2):
+        if gm[0] < 1e-12 or g2[0] < 1e-12:
+            return f32(0.0)
+        d1, d2 = f32(m["d_p1"]) - f32(m2["d_p1"]), f32(m["d_p2"]) - f32(m2["d_p2"])
+        sim_p = min(expf(-d1 * d1 / gm[2]), expf(-d2 * d2 / gm[3]))
+        dot_p = f32(gm[1][0] * g2[1][0] + gm[1][1] * g2[1][1] + gm[1][2] * g2[1][2])
+        ang = f32(float(acosf(f32(max(min(dot_p, f32(1.0)), f32(-1.0))))) / np.pi * 180.0)
+        if ang > f32(90.0):
+            ang = f32(180.0) - ang
+        s = min(expf(-ang * ang / f32(200.0)), sim_p)
+        return s if s > f32(0.5) else f32(0.0)
+
+    with np.errstate(over="ignore", under="ignore"):
+        for ci, cy in enumerate(st.cycles):
+            calls["begin_cycle"]()
+            for cam in cy.deletes:
+                calls["delete"](cam)
+            for v in cy.adds:
+                calls["add"](v, v.worldpoints)
+                segs[v.cam_id] = v.segs
+            for cam, R, t, md, lst in cy.updates:
+                calls["update"](cam, R, t, md, lst)
+            calls["match"](st.params)
+            calls["reconstruct"]()
+            current = [u[0] for u in cy.updates]
+            add_cams, del_cams = {v.cam_id for v in cy.adds}, set(cy.deletes)
+            cams = {c: o.match_camera(c) for c in current}
+            for c in segs:                                     # deleted views: last pose, never translated again
+                if c not in cams:
+                    cams[c] = (o.match_camera(c)[0], o.view_info(c)["C"])
+            kk = {c: o.view_info(c)["k"] for c in segs}
+            for cam in current:
+                if cam not in prev:
+                    continue                                   # a new view: only fresh matches (checked elsewhere)
+                off, rec = o.lists(cam, 0)                     # as scored, entries to deleted cameras removed
+                poff, prec = prev[cam]
+                for r in range(len(segs[cam])):
+                    S = rec[off[r]:off[r + 1]]
+                    P = prec[poff[r]:poff[r + 1]]
+                    old = {(int(x["tgt_cam"]), int(x["tgt_seg"])): x for x in P}
+                    if len(S) == 0 and len(P) == 0:
+                        continue
+                    # the list at scoring time: the snapshot plus the persisted entries to cameras deleted now
+                    T = [(x, geometry(cam, r, x["d_p1"], x["d_p2"], int(x["tgt_cam"]), cams, kk)) for x in S]
+                    for x in P:
+                        if int(x["tgt_cam"]) in del_cams:
+                            g = geometry(cam, r, x["d_p1"], x["d_p2"], int(x["tgt_cam"]), cams, kk)
+                            if x["flags"] == 1 or g[4]:
+                                T.append((x, g))
+                            else:
+                                stats["dropped"] += 1
+                    for x, g in T[:len(S)]:
+                        key = (int(x["tgt_cam"]), int(x["tgt_seg"]))
+                        if key in old:                         # scored before: add / delete deltas
+                            score = f32(old[key]["score"])
+                            for bit, cset in (("adds", add_cams), ("dels", del_cams)):
+                                for c2 in sorted(cset):
+                                    if c2 == key[0]:
+                                        continue
+                                    sims = [sim(g, x, g2, x2) for x2, g2 in T if int(x2["tgt_cam"]) == c2]
+                                    if sims:
+                                        score = score + max(sims) if bit == "adds" else score - max(sims)
+                                        stats[bit] += 1
+                            stats["delta"] += 1
+                        else:                                  # new this cycle: from scratch, deleted siblings excluded
+                            score, per_cam = f32(0.0), {}
+                            for x2, g2 in T[:len(S)]:
+                                c2 = int(x2["tgt_cam"])
+                                if c2 == key[0]:
+                                    continue
+                                sv = sim(g, x, g2, x2)
+                                if c2 in per_cam:
+                                    if sv > per_cam[c2]:
+                                        score = score - per_cam[c2]
+                                        score = score + sv
+                                        per_cam[c2] = sv
+                                else:
+                                    score = score + sv
+                                    per_cam[c2] = sv
+                            stats["fresh"] += 1
+                        assert f32(score).tobytes() == f32(x["score"]).tobytes(), (ci, cam, r, key, score, x["score"])
+            prev = {cam: o.lists(cam, 1) for cam in current}
+    assert stats["delta"] > 500 and stats["fresh"] > 500 and stats["adds"] > 100 and stats["dels"] > 20, stats
+    o.close()
