@@ -573,3 +573,60 @@ def test_incremental_score_deltas_second_reading_equals_the_oracle(oracle, scene
             prev = {cam: o.lists(cam, 1) for cam in current}
     assert stats["delta"] > 500 and stats["fresh"] > 500 and stats["adds"] > 100 and stats["dels"] > 20, stats
     o.close()
+
+
+def test_retriangulated_hypotheses_second_reading_equals_the_oracle(oracle, scene_mod):
+    """Line3D::update_Matches_and_Estimated_position3D (src/line3D.cc:1857-1908) on a key-frame stream whose poses
+    move: every row of estimated_position3D_ carries the depths of its best match triangulated AGAIN with the
+    cycle's poses (triangulationDepths both ways), and the 3-D segment unprojected from them; rows whose new depths
+    are not all positive are gone."""
+    import stream_utils
+    st = scene_mod.make_stream(n_keyframes=9, n_seg=220, window=6, nbrs=4, jitter=0.6, n_world=700, cull_every=0)
+    o, calls = stream_utils.oracle_driver(oracle, st)
+    segs = {}
+    checked = changed = 0
+
+    def rays(cam, seg, cams):
+        M = cams[cam][0]
+        s = segs[cam][seg]
+        return (_normalized(_matvec(M, np.array([float(s[0]), float(s[1]), 1.0]))),
+                _normalized(_matvec(M, np.array([float(s[2]), float(s[3]), 1.0]))))
+
+    def tri(Ca, ra1, ra2, Cb, rb1, rb2):
+        n = _normalized(_cross(rb1, rb2))
+        a, b = _dot3(ra1, n), _dot3(ra2, n)
+        if abs(a) < EPS or abs(b) < EPS:
+            return -1.0, -1.0
+        num = _dot3(Cb, n) - _dot3(n, Ca)
+        return num / a, num / b
+    for ci, cy in enumerate(st.cycles):
+        calls["begin_cycle"]()
+        for cam in cy.deletes:
+            calls["delete"](cam)
+        for v in cy.adds:
+            calls["add"](v, v.worldpoints)
+            segs[v.cam_id] = v.segs
+        for cam, R, t, md, lst in cy.updates:
+            calls["update"](cam, R, t, md, lst)
+        calls["match"](st.params)
+        cams = {u[0]: o.match_camera(u[0]) for u in cy.updates}
+        filt = {u[0]: o.lists(u[0], 1) for u in cy.updates}
+        for E in o.entries():
+            cam, seg, tc, ts = int(E["src_cam"]), int(E["src_seg"]), int(E["tgt_cam"]), int(E["tgt_seg"])
+            rs1, rs2 = rays(cam, seg, cams)
+            rt1, rt2 = rays(tc, ts, cams)
+            ds1, ds2 = tri(cams[cam][1], rs1, rs2, cams[tc][1], rt1, rt2)
+            dt1, dt2 = tri(cams[tc][1], rt1, rt2, cams[cam][1], rs1, rs2)
+            assert ds1 > EPS and ds2 > EPS and dt1 > EPS and dt2 > EPS
+            for name, val in (("d_p1", ds1), ("d_p2", ds2), ("d_q1", dt1), ("d_q2", dt2)):
+                assert np.float32(E[name]).tobytes() == np.float32(val).tobytes(), (ci, cam, seg, name)
+            P1 = cams[cam][1] + rs1 * float(np.float32(ds1))
+            P2 = cams[cam][1] + rs2 * float(np.float32(ds2))
+            assert (E["P1"] == P1).all() and (E["P2"] == P2).all() and (E["dir"] == _normalized(P2 - P1)).all()
+            off, rec = filt[cam]                                   # the match itself keeps the depths it was made with
+            m = [x for x in rec[off[seg]:off[seg + 1]] if int(x["tgt_cam"]) == tc and int(x["tgt_seg"]) == ts]
+            assert len(m) == 1 and m[0]["score"] == E["score"]
+            changed += int(m[0]["d_p1"] != E["d_p1"])
+            checked += 1
+    assert checked > 400 and changed > 100            # later cycles: old matches, new poses -> new depths
+    o.close()
