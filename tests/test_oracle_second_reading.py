@@ -630,3 +630,27 @@ def test_retriangulated_hypotheses_second_reading_equals_the_oracle(oracle, scen
             checked += 1
     assert checked > 400 and changed > 100            # later cycles: old matches, new poses -> new depths
     o.close()
+
+
+def test_spatial_regulariser_second_reading_equals_the_oracle(oracle, scene_mod):
+    """View::computeSpatialRegularizer (src/view.cc:330-343): k = sin(angle between the rays through the principal
+    point and through the point sigma_p pixels beside it)."""
+    import ctypes as C
+    L = oracle.lib()
+    L.orc_kat_acos.restype = C.c_double
+    L.orc_kat_acos.argtypes = [C.c_double]
+    L.orc_kat_sin.restype = C.c_double
+    L.orc_kat_sin.argtypes = [C.c_double]
+    for name, sig in (("tiny", 5.0), ("tiny", 2.5)):
+        sc = scene_mod.make_scene(name)
+        sc.params = dict(sc.params, sigma_p=sig)
+        o = oracle.run_scene(sc)
+        for v in sc.views:
+            M, _ = o.match_camera(v.cam_id)
+            pp = np.array([v.K[0, 2], v.K[1, 2], 1.0])
+            pps = np.array([pp[0] + float(np.float32(sig)), pp[1] + 0.0, pp[2] + 0.0])
+            a, b = _normalized(_matvec(M, pp)), _normalized(_matvec(M, pps))
+            alpha = L.orc_kat_acos(min(max(float(_dot3(a, b)), -1.0), 1.0))
+            k = np.float32(L.orc_kat_sin(alpha))
+            assert k.tobytes() == np.float32(o.view_info(v.cam_id)["k"]).tobytes() and 0.001 < k < 0.02
+        o.close()
