@@ -46,3 +46,13 @@ def test_host_clustering_matches_oracle_kat(api, oracle):
     m = oracle.lib().orc_kat_cluster(both.ctypes.data, wb.ctypes.data, len(wb), n, exp.ctypes.data)
     assert m == n
     assert (got == exp).all()
+
+
+def test_header_is_plain_c():
+    """include/l3dpp_b200.h is a C header (the cgo / JNI / ctypes side of the boundary): it parses as C99 and as C++11."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = os.path.join(root, "include", "l3dpp_b200.h")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", hdr])
+    subprocess.check_call(["g++", "-std=c++11", "-Wall", "-Werror", "-fsyntax-only", "-x", "c++", hdr])
