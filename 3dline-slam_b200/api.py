@@ -138,6 +138,7 @@ def lib():
         L.l3d_test_expf.argtypes = [vp, vp, vp, u32]
         L.l3d_test_acos.argtypes = [vp, vp, vp, u32]
         L.l3d_bench_fp32_peak.argtypes = [vp, vp]
+        L.l3d_bench_fp64_peak.argtypes = [vp, vp]
         _LIB = L
     return _LIB
 
@@ -237,6 +238,11 @@ class Context:
     def fp32_peak_tflops(self):
         v = C.c_float(0)
         self._ck(self.L.l3d_bench_fp32_peak(self.h, C.byref(v)))
+        return float(v.value)
+
+    def fp64_peak_tflops(self):
+        v = C.c_float(0)
+        self._ck(self.L.l3d_bench_fp64_peak(self.h, C.byref(v)))
         return float(v.value)
 
 
@@ -561,6 +567,28 @@ def cluster_edges(ij, w, n):
     if rc:
         raise L3DError(L.l3d_last_error().decode())
     return out[:n]
+
+
+def result_digest(l3, cam_ids):
+    """sha256 over everything the path hands to the clustering and to the 3-D line tail: the filtered
+    match lists of every view (matches_ after filterMatches), the hypotheses (estimated_position3D_),
+    A_ (pairs and weights, reference order) and local2global_.  Equal digests on every rank of a sharded
+    run, and across different numbers of ranks, mean bit-identical results."""
+    import hashlib
+    h = hashlib.sha256()
+    for cam in cam_ids:
+        off, rec = l3.lists(cam, 1)
+        h.update(off.tobytes())
+        h.update(rec.tobytes())
+    ent = l3.entries()
+    for name in ENTRY_DTYPE.names:
+        if name != "pad":
+            h.update(np.ascontiguousarray(ent[name]).tobytes())
+    ij, w = l3.edges()
+    h.update(ij.tobytes())
+    h.update(w.tobytes())
+    h.update(l3.local2global().tobytes())
+    return h.hexdigest()
 
 
 def run_scene(scene, filter_mode=0, keep_scored=False, reconstruct=True, device=-1, stream=0):

@@ -18,11 +18,20 @@ int l3d_match_lines(l3d_ctx* ctx, const float* lines_src, uint32_t n_src, const 
             for (uint32_t i = 0; i <= n_src; ++i) out_row_off[i] = 0;
         return L3D_OK;
     }
-    // a private two-view scene in raw mode: cameras given as (RtKinv, C), F given, no translation
-    l3d_ctx t;
+    // a private two-view scene in raw mode: cameras given as (RtKinv, C), F given, no translation.  The
+    // scratch context lives inside ctx and keeps its device buffers and pinned read-back area from one
+    // call to the next: the shim calls this once per view pair.
+    if (!ctx->pair_scratch) {
+        ctx->pair_scratch = new l3d_ctx;
+        if (cudaMallocHost((void**)&ctx->pair_scratch->rb, 1u << 16) == cudaSuccess) ctx->pair_scratch->rb_cap = 1u << 16;
+        else ctx->pair_scratch->rb = nullptr;
+    }
+    l3d_ctx& t = *ctx->pair_scratch;
+    l3d_scene_begin(&t);
     t.device = ctx->device;
     t.stream = ctx->stream;
     t.raw_mode = true;
+    t.cnt = l3d_counts{};
     memcpy(t.F_override, F, sizeof(t.F_override));
     auto mk = [&](uint32_t cam, const float* segs, uint32_t n, const double* M, const double* C) {
         HostView hv;
@@ -39,10 +48,8 @@ int l3d_match_lines(l3d_ctx* ctx, const float* lines_src, uint32_t n_src, const 
     t.views.push_back(mk(src_cam, lines_src, n_src, RtKinv_src, C_src));
     t.views.push_back(mk(tgt_cam, lines_tgt, n_tgt, RtKinv_tgt, C_tgt));
     t.views[0].nbrs.push_back(tgt_cam);
-    // commit sorts by camera id; the pair list must still be (src -> tgt)
-    if (tgt_cam < src_cam) {
-        // matchingCPU is asymmetric: keep src first by giving the neighbour list to src only
-    }
+    // commit sorts by camera id; matchingCPU is asymmetric: only src carries a neighbour list, so the
+    // pair list is (src -> tgt) whichever id is smaller
     int rc = l3d_scene_commit(&t);
     if (rc) return rc;
     l3d_params prm;
@@ -571,6 +578,13 @@ int l3d_shard_import_hdr(l3d_ctx* ctx, int kind, const void* all, uint64_t strid
         sizes_out[q] = hdr[q].payload_bytes;
         if (hdr[q].payload_bytes + sizeof(ShardBlobHdr) > stride_bytes) *redo = 1;
         if (kind == L3D_X_PROGRAMS && (hdr[q].flags & 4u)) *redo = 1;
+        // a sender whose finish pass overflowed its filtered-match store (2) or timed out on a dependency (8)
+        // fails locally; every rank sees the same header, so every rank reports it instead of adopting lists
+        // that were cut short and walking into the next collective alone
+        if (kind == L3D_X_HYPOTHESES && (hdr[q].flags & 2u))
+            return fail(L3D_ERR_CAPACITY, "filtered-match store overflow on rank %d", q);
+        if (kind == L3D_X_HYPOTHESES && (hdr[q].flags & 8u))
+            return fail(L3D_ERR_STATE, "internal: scoring dependency wait timed out on rank %d", q);
     }
     if (*redo) return L3D_OK;
     return l3d_shard_import(ctx, kind, (const unsigned char*)all + sizeof(ShardBlobHdr), stride_bytes, world, sizes_out, 1);

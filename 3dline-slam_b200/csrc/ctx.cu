@@ -66,6 +66,7 @@ int l3d_ctx_set_stream(l3d_ctx* ctx, void* cuda_stream)
 int l3d_scene_begin(l3d_ctx* ctx)
 {
     if (!ctx) return fail(L3D_ERR_ARG, "ctx is NULL");
+    if (ctx) leave_translated(ctx);  // a call that failed half-way may have left the cameras shifted
     ctx->views.clear();
     ctx->cam2view.clear();
     ctx->stream_mode = false;
@@ -252,6 +253,24 @@ void apply_translation(l3d_ctx* ctx, double sign)
     const hg::V3 tv{sign * ctx->translation.x, sign * ctx->translation.y, sign * ctx->translation.z};
     for (auto& hv : ctx->views)
         if (hv.current) hv.cam.translate(tv);
+}
+// translate() / untranslate() as a guarded pair (src/line3D.cc:568,637 and :2065,2140).  The host cameras
+// are shifted in place like the reference's; `translated` remembers that a shift is pending, so a call
+// that fails half-way (capacity error, CUDA error, aborted sharded step) or a repeated stage-1/2 call
+// cannot stack a second shift on top of the first: the pending one is undone -- with the translation it
+// was made with -- before a new median is taken, and before any getter reads the cameras.
+void enter_translated(l3d_ctx* ctx)
+{
+    leave_translated(ctx);
+    compute_translation(ctx);
+    apply_translation(ctx, -1.0);
+    ctx->translated = true;
+}
+void leave_translated(l3d_ctx* ctx)
+{
+    if (!ctx->translated) return;
+    apply_translation(ctx, +1.0);
+    ctx->translated = false;
 }
 
 __global__ void pair_totals_kernel(const PairDev* __restrict__ pairs, uint32_t P, const uint32_t* __restrict__ fwd_off,
@@ -640,8 +659,7 @@ int l3d_match_stage12(l3d_ctx* ctx, const l3d_params* params)
 
     // translate(), spatial regularisers (src/line3D.cc:568-590)
     if (!ctx->raw_mode) {
-        compute_translation(ctx);
-        apply_translation(ctx, -1.0);
+        enter_translated(ctx);
         for (auto& hv : ctx->views) {
             hv.k = ctx->fixed3D ? ctx->prm.sigma_p / ctx->prm.const_reg_depth : hv.cam.spatial_regularizer(ctx->prm.sigma_p);
             hv.median_depth = 0.0f;
@@ -947,10 +965,7 @@ int score_hypotheses_ready(l3d_ctx* ctx, bool* prog_overflow, uint32_t* prog_nee
     }
     // update_Matches_and_Estimated_position3D (src/line3D.cc:1857-1908) re-triangulates the best
     // matches with unchanged poses: the identical call, hence identical depths -- nothing to do.
-    if (!ctx->raw_mode) {
-        const hg::V3 tv{ctx->translation.x, ctx->translation.y, ctx->translation.z};
-        for (auto& hv : ctx->views) hv.cam.translate(tv);  // untranslate()
-    }
+    leave_translated(ctx);  // untranslate() (src/line3D.cc:637); a no-op in raw mode
     ctx->stage = 2;
     ctx->stage3_phase = 3;
     return L3D_OK;
@@ -1007,8 +1022,7 @@ int l3d_affinity_edges(l3d_ctx* ctx)
         return L3D_OK;
     }
     // translate() again (src/line3D.cc:2065); only the camera centres move
-    compute_translation(ctx);
-    apply_translation(ctx, -1.0);
+    enter_translated(ctx);
     // median scene depth of the lines (src/line3D.cc:2074-2091)
     std::vector<float> sd;
     for (auto& hv : ctx->views)
@@ -1097,7 +1111,7 @@ int l3d_affinity_ids(l3d_ctx* ctx)
     ctx->cnt.num_edges = 2 * n_edges;  // A_ holds both directions
     if (n_edges) n_local = *ctx->rb_at<uint32_t>(l3d_ctx::RB_NLOCAL);
     ctx->cnt.num_local_ids = n_local;
-    apply_translation(ctx, +1.0);  // untranslate() (src/line3D.cc:2140)
+    leave_translated(ctx);  // untranslate() (src/line3D.cc:2140)
     ctx->stage = 3;
     ctx->stage4_phase = 2;
     return L3D_OK;
@@ -1182,6 +1196,14 @@ int l3d_neighbors_from_worldpoints(const l3d_view* views, uint32_t n_views, cons
                                    uint32_t* out_counts)
 {
     if (!views || !wps_concat || !wp_counts || !out_cam_ids || !out_counts) return fail(L3D_ERR_ARG, "NULL argument");
+    // Line3D::matchImages raises num_neighbors to 2 (src/line3D.cc:531-536); the output rows are laid out with the
+    // caller's stride, so a smaller value cannot hold what would be chosen
+    if (num_neighbors < 2) return fail(L3D_ERR_ARG, "num_neighbors must be >= 2 (got %u)", num_neighbors);
+    {
+        std::set<uint32_t> ids;
+        for (uint32_t i = 0; i < n_views; ++i)
+            if (!ids.insert(views[i].cam_id).second) return fail(L3D_ERR_ARG, "camera ID [%u] already in use!", views[i].cam_id);
+    }
     l3d_ctx t;
     size_t no = 0;
     for (uint32_t i = 0; i < n_views; ++i) {
@@ -1202,7 +1224,7 @@ int l3d_neighbors_from_worldpoints(const l3d_view* views, uint32_t n_views, cons
         cams[v] = &t.views[v].cam;
         wps[v] = t.views[v].wps;
     }
-    hg::visual_neighbors_from_worldpoints(cams, md, wps, (unsigned)std::max((int)num_neighbors, 2), nb);
+    hg::visual_neighbors_from_worldpoints(cams, md, wps, (unsigned)num_neighbors, nb);
     // output rows follow the order of `views` as given
     for (uint32_t i = 0; i < n_views; ++i) {
         uint32_t v = 0;
@@ -1535,6 +1557,9 @@ int l3d_get_view_info(l3d_ctx* ctx, uint32_t cam_id, double* C, float* kmm)
     if (f == ctx->cam2view.end()) return fail(L3D_ERR_ARG, "unknown camera %u", cam_id);
     const HostView& hv = ctx->views[f->second];
     C[0] = hv.cam.C.x; C[1] = hv.cam.C.y; C[2] = hv.cam.C.z;
+    if (ctx->translated && hv.current) {  // between two stages of a step: report what untranslate() will restore
+        C[0] += ctx->translation.x; C[1] += ctx->translation.y; C[2] += ctx->translation.z;
+    }
     kmm[0] = hv.k;
     kmm[1] = hv.median_depth;
     kmm[2] = hv.median_sigma;
@@ -1599,6 +1624,37 @@ int l3d_bench_fp32_peak(l3d_ctx* ctx, float* tflops)
         cudaEventElapsedTime(&ms, a, b);
         // 16 independent FMA chains per thread, 2 flop per FMA
         const double flop = (double)blocks * 256.0 * (double)iters * 16.0 * 2.0;
+        if (rep > 0 && ms > 0) best = std::max(best, (float)(flop / (ms * 1e-3) / 1e12));
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    *tflops = best;
+    return L3D_OK;
+}
+
+// the FP64 (DFMA) pipe peak, measured the same way: the denominator of the K2 roofline
+int l3d_bench_fp64_peak(l3d_ctx* ctx, float* tflops)
+{
+    if (!ctx || !tflops) return fail(L3D_ERR_ARG, "NULL argument");
+    CK(cudaSetDevice(ctx->device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, ctx->device));
+    DevBuf<double> sink;
+    CK(sink.ensure(1 << 19));
+    const int blocks = prop.multiProcessorCount * 8, iters = 2048;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    float best = 0.0f;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(a, ctx->stream);
+        ctx->cnt.gpu_launches += launch_fp64_peak(sink.p, blocks, iters, ctx->stream);
+        cudaEventRecord(b, ctx->stream);
+        CK(cudaStreamSynchronize(ctx->stream));
+        float ms = 0.0f;
+        cudaEventElapsedTime(&ms, a, b);
+        // 8 independent DFMA chains per thread, 2 flop per FMA
+        const double flop = (double)blocks * 256.0 * (double)iters * 8.0 * 2.0;
         if (rep > 0 && ms > 0) best = std::max(best, (float)(flop / (ms * 1e-3) / 1e12));
     }
     cudaEventDestroy(a);

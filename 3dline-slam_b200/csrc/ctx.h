@@ -59,6 +59,7 @@ int launch_k4_sparse(const int2*, const float*, uint32_t, uint32_t, int, float, 
 int launch_test_expf(const float*, float*, uint32_t, cudaStream_t);
 int launch_test_acos(const double*, double*, uint32_t, cudaStream_t);
 int launch_fp32_peak(float*, int, int, cudaStream_t);
+int launch_fp64_peak(double*, int, int, cudaStream_t);
 int launch_score_prep(const float4*, uint32_t, const float4*, const float2*, const double*, const double*, float,
                       const uint32_t*, ListRec*, ListGeo*, cudaStream_t);
 }  // namespace l3d
@@ -158,6 +159,7 @@ struct Batch {
 struct StageTimer {
     std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> ev;
     float ms[L3D_T_COUNT] = {0};
+    ~StageTimer() { reset(); }  // events of a step that returned early
     void reset()
     {
         for (auto& e : ev) {
@@ -203,6 +205,7 @@ struct l3d_ctx {
     bool by_worldpoints = false;  // neighbours are chosen from world-point lists at match time
     uint32_t S = 0;  // total segments
     hg::V3 translation{0, 0, 0};
+    bool translated = false;  // the host cameras currently carry -translation (enter_/leave_translated)
     float two_sigA_sqr = 200.0f, epi_overlap = 0.25f;
     float med_scene_depth_lines = 0.0f;
 
@@ -230,8 +233,10 @@ struct l3d_ctx {
     template <typename T>
     T* rb_at(size_t off) { return reinterpret_cast<T*>((rb ? rb : rb_fallback) + off); }
     bool rb_fits(size_t bytes) const { return rb && RB_BIG + bytes <= rb_cap; }
+    l3d_ctx* pair_scratch = nullptr;  // two-view scratch context of l3d_match_lines (owned)
     ~l3d_ctx()
     {
+        delete pair_scratch;
         if (pinned) cudaFreeHost(pinned);
         if (rb) cudaFreeHost(rb);
     }
@@ -341,6 +346,8 @@ void plan_batches(l3d_ctx* ctx);
 int run_stage12_batches(l3d_ctx* ctx);
 void compute_translation(l3d_ctx* ctx);
 void apply_translation(l3d_ctx* ctx, double sign);
+void enter_translated(l3d_ctx* ctx);
+void leave_translated(l3d_ctx* ctx);
 int stream_match_images(l3d_ctx* ctx, const l3d_params* params);
 int upload_views(l3d_ctx* ctx);
 int set_params(l3d_ctx* ctx, const l3d_params* params);

@@ -52,6 +52,28 @@ int launch_fp32_peak(float* sink, int blocks, int iters, cudaStream_t st)
     return 1;
 }
 
+// the same with DFMA: the FP64 pipe peak the K2 roofline divides by
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double* __restrict__ sink, int iters)
+{
+    double a[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = 1.0 + 1e-3 * (double)(threadIdx.x + i);
+    const double b = 0.999, c = 1e-4;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a[i] = __fma_rn(a[i], b, c);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += a[i];
+    if (s == 12345.678) sink[(blockIdx.x * blockDim.x + threadIdx.x) & ((1 << 19) - 1)] = s;
+}
+int launch_fp64_peak(double* sink, int blocks, int iters, cudaStream_t st)
+{
+    fp64_peak_kernel<<<blocks, 256, 0, st>>>(sink, iters);
+    return 1;
+}
+
 // list preparation for l3d_score_matches: one thread per source segment walks its range
 // (src/line3D.cc:1582-1623 packs the same data on the host)
 __global__ void __launch_bounds__(128) score_prep_kernel(const float4* __restrict__ lines, uint32_t n_lines,

@@ -17,6 +17,7 @@
 int l3d_stream_begin(l3d_ctx* ctx, int neighbors_by_worldpoints)
 {
     if (!ctx) return fail(L3D_ERR_ARG, "ctx is NULL");
+    if (ctx) leave_translated(ctx);  // a call that failed half-way may have left the cameras shifted
     int rc = l3d_scene_begin(ctx);
     if (rc) return rc;
     ctx->stream_mode = true;
@@ -47,6 +48,7 @@ int l3d_stream_add_image(l3d_ctx* ctx, const l3d_view* view, const float* segs, 
                          uint32_t n_list)
 {
     if (!ctx || !view) return fail(L3D_ERR_ARG, "NULL argument");
+    if (ctx) leave_translated(ctx);  // a call that failed half-way may have left the cameras shifted
     if (!ctx->stream_mode) return fail(L3D_ERR_STATE, "not in stream mode (l3d_stream_begin)");
     if (std::max(view->width, view->height) < 400)
         return fail(L3D_ERR_ARG, "image is too small for reliable results: %u px (larger side should be >= 400px)",
@@ -82,6 +84,7 @@ int l3d_stream_add_image(l3d_ctx* ctx, const l3d_view* view, const float* segs, 
 int l3d_stream_delete_image(l3d_ctx* ctx, uint32_t cam_id)
 {
     if (!ctx) return fail(L3D_ERR_ARG, "ctx is NULL");
+    if (ctx) leave_translated(ctx);  // a call that failed half-way may have left the cameras shifted
     if (!ctx->stream_mode) return fail(L3D_ERR_STATE, "not in stream mode (l3d_stream_begin)");
     auto f = ctx->cam2view.find(cam_id);
     if (f == ctx->cam2view.end() || !ctx->views[f->second].current)
@@ -102,6 +105,7 @@ int l3d_stream_update_image(l3d_ctx* ctx, uint32_t cam_id, const double* R, cons
                             const uint32_t* wps_or_nbrs, uint32_t n_list)
 {
     if (!ctx || !R || !t) return fail(L3D_ERR_ARG, "NULL argument");
+    if (ctx) leave_translated(ctx);  // a call that failed half-way may have left the cameras shifted
     if (!ctx->stream_mode) return fail(L3D_ERR_STATE, "not in stream mode (l3d_stream_begin)");
     (void)median_depth;  // only seeds View::initial_median_depth_, which the path never reads
     auto f = ctx->cam2view.find(cam_id);
@@ -205,13 +209,12 @@ int stream_match_images(l3d_ctx* ctx, const l3d_params* params)
 
     lap("upload");
     // ---- translate(), spatial regularisers of the current views (src/line3D.cc:568-590) ----
-    compute_translation(ctx);
-    apply_translation(ctx, -1.0);
+    enter_translated(ctx);
     // untranslate() (src/line3D.cc:637) on every way out; a cycle that fails half-way leaves matched_ and the
     // lists in an undefined state -- the caller starts over with l3d_stream_begin
     struct Untranslate {
         l3d_ctx* c;
-        ~Untranslate() { apply_translation(c, +1.0); }
+        ~Untranslate() { leave_translated(c); }
     } untranslate_on_exit{ctx};
     for (uint32_t v : cur)
         ctx->views[v].k = ctx->fixed3D ? ctx->prm.sigma_p / ctx->prm.const_reg_depth

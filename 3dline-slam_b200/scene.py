@@ -182,6 +182,12 @@ def _world_segments(rng, n, box_lo, box_hi, med_len):
     return c - 0.5 * ln[:, None] * d, c + 0.5 * ln[:, None] * d
 
 
+PRESET_SHAPES = {  # views, segments per view, neighbours, image -- the BASELINE.json configs
+    "tiny": (8, 160, 4, "640x480"), "c2": (50, 1000, 10, "640x480"), "c4": (500, 3000, 20, "1920x1080"),
+    "c5": (5000, 5000, 20, "1920x1080"),
+}
+
+
 def make_scene(kind: str = "c2", n_views: Optional[int] = None, n_seg: Optional[int] = None,
                nbrs: Optional[int] = None, seed: Optional[int] = None,
                n_world: Optional[int] = None) -> Scene:

@@ -13,6 +13,8 @@
 #include <cstdint>
 #include <iostream>
 #include <list>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -56,15 +58,63 @@ class SparseMatrix;
 
 namespace L3DPP {
 
+// One l3d_ctx per Line3D object (the contract of include/l3dpp_b200.h: a context is not thread-safe and
+// belongs to one Line3D).  The Line3D constructor calls l3dpp_b200_attach(this, max_image_width_) and the
+// destructor l3dpp_b200_detach(this); the entry points below act on the context of the
+// object attached last on the calling thread.  Without any attach call they fall back to one process-wide
+// context -- the behaviour of the upstream global staging buffer -- whose image width must then be given
+// with l3dpp_b200_set_max_image_width before the float-signature match_lines_GPU is used.
+struct ShimState {
+    l3d_ctx* ctx = nullptr;
+    int max_image_width = -1;  // Line3D::max_image_width_; -1 = not told yet
+};
+static std::mutex g_shim_mutex;
+static std::map<const void*, ShimState> g_shim_states;
+static thread_local const void* g_shim_current = nullptr;
+
+static ShimState* shim_state()
+{
+    std::lock_guard<std::mutex> lock(g_shim_mutex);
+    ShimState& st = g_shim_states[g_shim_current];
+    if (!st.ctx && l3d_ctx_create(&st.ctx, -1) != L3D_OK) {
+        std::cerr << "l3dpp_b200: " << l3d_last_error() << std::endl;
+        st.ctx = nullptr;
+        return nullptr;
+    }
+    return &st;
+}
 static l3d_ctx* shim_ctx()
 {
-    static l3d_ctx* ctx = nullptr;  // one context per process, like the upstream global staging buffer
-    if (!ctx && l3d_ctx_create(&ctx, -1) != L3D_OK) {
-        std::cerr << "l3dpp_b200: " << l3d_last_error() << std::endl;
-        ctx = nullptr;
-    }
-    return ctx;
+    ShimState* st = shim_state();
+    return st ? st->ctx : nullptr;
 }
+
+}  // namespace L3DPP
+extern "C" {
+void l3dpp_b200_attach(const void* line3d, int max_image_width)
+{
+    L3DPP::g_shim_current = line3d;
+    L3DPP::ShimState* st = L3DPP::shim_state();
+    if (st) st->max_image_width = max_image_width;
+}
+void l3dpp_b200_use(const void* line3d) { L3DPP::g_shim_current = line3d; }
+void l3dpp_b200_detach(const void* line3d)
+{
+    std::lock_guard<std::mutex> lock(L3DPP::g_shim_mutex);
+    auto f = L3DPP::g_shim_states.find(line3d);
+    if (f != L3DPP::g_shim_states.end()) {
+        if (f->second.ctx) l3d_ctx_destroy(f->second.ctx);
+        L3DPP::g_shim_states.erase(f);
+    }
+    if (L3DPP::g_shim_current == line3d) L3DPP::g_shim_current = nullptr;
+}
+void l3dpp_b200_set_max_image_width(int max_image_width)
+{
+    L3DPP::ShimState* st = L3DPP::shim_state();
+    if (st) st->max_image_width = max_image_width;
+}
+}
+namespace L3DPP {
 
 // 3x3 DataArray<float> is indexed (x=col, y=row): src/line3D.cc:3266-3272, src/view.cc:39-42
 static void mat_from_da(DataArray<float>* M, double out[9])
@@ -123,9 +173,17 @@ unsigned int match_lines_GPU(DataArray<float4>* lines_src, DataArray<float4>* li
     mat_from_da(RtKinv_src, Ms);
     mat_from_da(RtKinv_tgt, Mt);
     const double Cs[3] = {C_src.x, C_src.y, C_src.z}, Ct[3] = {C_tgt.x, C_tgt.y, C_tgt.z};
-    // the reference signature has no image width; L3DPPing passes 640 (include/L3DPPing.h:78)
+    // the reference signature has no image width, but Line3D::matchingCPU's bounds test needs
+    // Line3D::max_image_width_ (src/line3D.cc:1142-1148): it comes from l3dpp_b200_attach /
+    // l3dpp_b200_set_max_image_width.  Guessing it would silently drop matches, so refuse instead.
+    ShimState* st = shim_state();
+    if (!st || st->max_image_width <= 0) {
+        std::cerr << "match_lines_GPU: Line3D::max_image_width_ is unknown -- call l3dpp_b200_attach(this, max_image_width_) "
+                     "in the Line3D constructor (or l3dpp_b200_set_max_image_width), or use match_lines_GPU_f64" << std::endl;
+        return 0;
+    }
     return match_lines_GPU_f64(lines_src, lines_tgt, Fd, Ms, Mt, Cs, Ct, matches, srcCamID, tgtCamID, epi_overlap, kNN,
-                               640);
+                               st->max_image_width);
 }
 
 // include/cudawrapper.h:74-81

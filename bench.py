@@ -1,18 +1,21 @@
 #!/usr/bin/env python
 """bench.py -- segment-pair tests/s and views/s of the Line3D++ matching -> scoring -> affinity
-path on B200 (BASELINE.json metric), with the K1 roofline, the CPU baseline and the end-to-end
-number.  One "step" = one full pass of stages 1-4 (l3d_match_images + l3d_affinity) over one
-synthetic scene.
+path on B200 (BASELINE.json metric), with the rooflines of the dominant kernels, the CPU baseline,
+the end-to-end number and a parity digest.  One "step" = one full pass of stages 1-4
+(l3d_match_images + l3d_affinity) over one synthetic scene.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3|c4|c4s]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload c4|c2|c3|c4s|c5s|c5|tiny]
 
-The default single-GPU line also carries `config3_stream`: BASELINE config[2], the key-frame stream through
-the incremental mode (what `--workload c3` measures on its own; `--no-stream` skips it).
-
-N=1: BASELINE config[1] (50 views x 1000 segments x 10 neighbours, 640x480).  N>1 (torchrun, one
-process per GPU): the scene grows with N (50*N views, weak scaling); every rank owns a contiguous
-slice of reference views (matching, scoring rows, hypotheses, affinity edges), four NCCL
-all-gathers per step make the results whole on every rank.
+Default workload at every N: BASELINE config[3], the 500-view x 3000-segment x 20-neighbour scene the
+metric is quoted on "at 1/2/4/8 B200" -- the SAME scene at every N, i.e. strong scaling.  N>1
+(torchrun, one process per GPU): every rank owns a contiguous slice of reference views (matching,
+scoring rows, hypotheses, affinity edges); NCCL all-gathers make the results whole on every rank
+(DESIGN.md section 6).  After the timed region every rank hashes its results (filtered lists,
+hypotheses, A_, local2global_); the digests must agree on all ranks and the line carries
+`parity_digest`, so runs at N = 1, 2, 4, 8 can be compared.  At N = 1 the line also carries
+`config2` (BASELINE config[1], 50 x 1000 x 10, fully measured) and `config3_stream` (config[2], the
+key-frame stream through the incremental mode), and a C4-shaped cut is compared with the CPU oracle.
 """
 import argparse
 import importlib
@@ -33,9 +36,17 @@ import numpy as np
 FLOP_PER_TEST = 114.0  # algorithmic FP32 flop of one segment-pair test
 
 
-def make_workload(scene_mod, name, n_gpus):
+# the CPU arm's bounded sample of a workload: a cut of the same generator and per-view shape (the CPU
+# path's tests/s does not depend on the number of views), sized for a few seconds per pass
+CPU_SAMPLE = {"c4": ("c4", 16), "c4s": ("c4", 16), "c2": ("c2", 50), "tiny": ("tiny", 8), "c5": ("c5", 8), "c5s": ("c5", 8)}
+
+
+def make_workload(scene_mod, name, n_gpus=1):
+    """(scene, workload name).  The scene does not depend on the number of GPUs: strong scaling."""
     if name == "c2":
-        return scene_mod.make_scene("c2", n_views=50 * n_gpus), "c2" if n_gpus == 1 else "c2x%d" % n_gpus
+        return scene_mod.make_scene("c2"), "c2"
+    if name == "c2w":  # round-1 weak-scaling variant: the circle grows with N
+        return scene_mod.make_scene("c2", n_views=50 * n_gpus), "c2w"
     if name == "c4":
         return scene_mod.make_scene("c4"), "c4"
     if name == "c4s":  # BASELINE config[3] shape, 100 of the 500 views (oracle-checkable in ~1 min)
@@ -43,6 +54,17 @@ def make_workload(scene_mod, name, n_gpus):
     if name == "tiny":
         return scene_mod.make_scene("tiny"), "tiny"
     raise SystemExit("unknown workload %r" % name)
+
+
+def workload_config(scene_mod, name):
+    """The `config` object both arms print (identical dicts, so the driver can see it is the same job)."""
+    base = {"c4s": "c4", "c2w": "c2", "c5s": "c5"}.get(name, name)
+    V, N, NB, img = scene_mod.PRESET_SHAPES[base]
+    if name == "c4s":
+        V = 100
+    if name == "c5s":
+        V = 500
+    return {"workload": name, "views": V, "segments_per_view": N, "neighbours": NB, "image": img}
 
 
 class ClockSampler:
@@ -125,7 +147,8 @@ def run_cpu_oracle(scene, threads=0, snapshot=False):
 
 def bench_reference(args, scene_mod):
     """--impl reference: the reference's own CPU implementation of the path = the oracle port
-    (the reference cannot be compiled here: no Eigen/Boost/OpenCV), all host threads."""
+    (the reference cannot be compiled here: no Eigen/Boost/OpenCV), all host threads.  Each step is a
+    bounded sample of the product arm's workload: a cut of the same generator and per-view shape."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -163,18 +186,15 @@ def bench_reference(args, scene_mod):
             "impl": "reference", "metric": "segment_pair_tests_per_s", "value": value, "unit": "tests/s",
             "n_gpus": args.gpus, "steps": len(ts), "warmup": W, "ms_per_step": 1e3 * T / len(ts),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "c3", "window": 20, "segments_per_view": 1000, "neighbours": 10, "sample": sample},
+            "config": C3_CONFIG,
             "views_per_s": 20.0 * len(ts) / T,
             "cpu_baseline": {"value": value, "unit": "tests/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "tests/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}))
         return
-    # each step is a bounded sample of the arm's workload: the single-GPU scene of the same generator
-    # (at N > 1 the product's scene has N times the views; tests/s of the CPU path does not depend on it)
-    scene, sample_name = make_workload(scene_mod, args.workload, 1)
-    n = max(args.gpus, 1)
-    wname = sample_name if (n == 1 or args.workload != "c2") else "c2x%d" % n
-    full_views = scene.num_views * (n if args.workload == "c2" else 1)
+    kind, nv = CPU_SAMPLE.get(args.workload, ("c4", 16))
+    scene = scene_mod.make_scene(kind, n_views=nv)
+    cfg = workload_config(scene_mod, args.workload)
     times, tests, cores = [], 0, 1
     for i in range(args.warmup + args.steps):
         r = run_cpu_oracle(scene)
@@ -183,19 +203,24 @@ def bench_reference(args, scene_mod):
             times.append(r["timers"]["match_images"] + r["timers"]["reconstruct"])
     T = float(np.sum(times))
     value = tests * len(times) / T
-    sample = "%s scene (%d views, same generator and per-view shape), stages 1-4, %d passes" % (sample_name, scene.num_views, len(times))
+    sample = ("%d-view cut of the %s generator (same per-view shape: %d segments, %d neighbours), stages 1-4, %.2e tests per "
+              "pass, %d passes" % (scene.num_views, kind, cfg["segments_per_view"], cfg["neighbours"], tests, len(times)))
+    # views/s of the full workload at the CPU's tests/s (the cut has fewer views, the same tests per view pair)
     line = {
         "impl": "reference", "metric": "segment_pair_tests_per_s", "value": value, "unit": "tests/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * T / len(times),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wname, "views": full_views, "segments_per_view": scene.views[0].segs.shape[0],
-                   "neighbours": scene.params["num_neighbors"], "sample": sample},
-        "views_per_s": scene.num_views * len(times) / T,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": cfg,
+        "views_per_s_of_the_sample": scene.num_views * len(times) / T,
         "cpu_baseline": {"value": value, "unit": "tests/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "tests/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+C3_CONFIG = {"workload": "c3", "keyframes": 300, "window": 20, "segments_per_view": 1000, "neighbours": 10,
+             "image": "640x480", "new_keyframes_per_cycle": 1}
 
 
 def bench_stream(args, scene_mod, emit=True):
@@ -321,10 +346,10 @@ def bench_stream(args, scene_mod, emit=True):
         "metric": "segment_pair_tests_per_s", "value": value, "unit": "tests/s", "n_gpus": world, "steps": n, "warmup": W,
         "ms_per_step": 1e3 * T / n, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64",
         "data": "synthetic",
-        "config": {"workload": "c3", "keyframes": len(st.cycles) + 4, "window": 20, "segments_per_view": 1000,
-                   "neighbours": 10, "new_keyframes_per_cycle": 1, "step": "one L3DPPing cycle in steady state, wall clock",
-                   "parallelism": "1 rank" if world == 1 else "%d independent replicas (the mode does not shard)" % world,
-                   "l2": "inputs larger than one kernel's footprint are not the bound here: launch-bound"},
+        "config": C3_CONFIG,
+        "step": "one L3DPPing cycle in steady state (of a %d-key-frame prefix of the stream), wall clock" % (len(st.cycles) + 4),
+        "parallelism": "1 rank" if world == 1 else "%d independent replicas (the mode does not shard)" % world,
+        "l2_policy": "not flushed: a cycle is launch-bound, its working set is far below L2",
         "views_per_s": world * 20.0 * n / T,
         "ms_per_cycle_p50": 1e3 * float(np.median(ts)), "ms_per_cycle_max": 1e3 * float(np.max(ts)),
         "stage_ms": {k: v / n for k, v in stage.items()},
@@ -339,17 +364,304 @@ def bench_stream(args, scene_mod, emit=True):
     return line
 
 
+# SASS instruction count of K1's unrolled pair-test loop per test (profiles/r2_k1_sass.md)
+K1_ISSUED_PER_TEST = 35.5
+K2_FLOP_PER_CANDIDATE = 330.0  # SURVEY.md section 8(d) / DESIGN.md section 4.2: FP64 flop per K1 candidate
+
+
+class Env:
+    pass
+
+
+def setup_env(args):
+    import torch
+    env = Env()
+    env.torch = torch
+    env.api = importlib.import_module("3dline-slam_b200.api")
+    env.sharding = importlib.import_module("3dline-slam_b200.sharding")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+    env.world = int(os.environ.get("WORLD_SIZE", "1"))
+    env.rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    env.dist = None
+    env.dev = torch.device("cuda", local_rank if env.world > 1 else 0)
+    torch.cuda.set_device(env.dev)
+    if env.world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=env.dev)
+        env.dist = dist
+    env.n_gpus = env.world if env.world > 1 else 1
+    if args.gpus != env.n_gpus and env.rank == 0:
+        print("note: --gpus %d but WORLD_SIZE=%d; using %d" % (args.gpus, env.world, env.n_gpus), file=sys.stderr)
+    env.stream = torch.cuda.current_stream(env.dev)
+    env.flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=env.dev)  # > 126 MB L2
+    return env
+
+
+def barrier(env):
+    if env.dist is not None:
+        env.dist.barrier()
+    env.torch.cuda.synchronize(env.dev)
+
+
+def max_over_ranks(env, x):
+    if env.dist is None:
+        return float(x)
+    t = env.torch.tensor([float(x)], dtype=env.torch.float64, device=env.dev)
+    env.dist.all_reduce(t, op=env.dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sum_over_ranks(env, x):
+    if env.dist is None:
+        return float(x)
+    t = env.torch.tensor([float(x)], dtype=env.torch.float64, device=env.dev)
+    env.dist.all_reduce(t, op=env.dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+def gather_digests(env, hexdigest):
+    """Every rank's sha256 -> list of hex strings on every rank."""
+    if env.dist is None:
+        return [hexdigest]
+    torch = env.torch
+    mine = torch.tensor(list(bytes.fromhex(hexdigest)), dtype=torch.uint8, device=env.dev)
+    allb = torch.empty(32 * env.world, dtype=torch.uint8, device=env.dev)
+    env.dist.all_gather_into_tensor(allb, mine)
+    raw = bytes(allb.cpu().tolist())
+    return [raw[32 * q:32 * q + 32].hex() for q in range(env.world)]
+
+
+def bench_batch(env, args, scene, wname, steps, warmup, e2e_steps, trace_phases=False):
+    """Stages 1-4 over `scene` on env.n_gpus GPUs: device-timed steps (L2 flushed), an instrumented pass
+    for the per-stage / per-kernel numbers, the end-to-end loop with host buffers, and the result digest."""
+    torch, api, sharding, dist = env.torch, env.api, env.sharding, env.dist
+    dev, stream, n_gpus, rank = env.dev, env.stream, env.n_gpus, env.rank
+    prm = scene.params
+    l3 = api.Line3D("", False, scene.max_image_width, 3000, False, True, dev.index, stream.cuda_stream)
+    l3.shard = (rank, n_gpus)
+    l3.load_scene(scene)
+    l3.upload()  # tables resident in HBM before the timed region
+    xch = sharding.Exchanger(dist, torch, dev) if n_gpus > 1 else None
+    mp = (prm["sigma_p"], prm["sigma_a"], prm["num_neighbors"], prm["epipolar_overlap"], prm["knn"], prm["const_reg_depth"])
+
+    def step():
+        if n_gpus == 1:
+            l3.matchImages(*mp)
+            l3.affinity()
+        else:
+            sharding.run_sharded(l3, xch, prm)
+
+    sampler = ClockSampler(dev.index)
+    sampler.start()
+    for _ in range(warmup):
+        env.flush.zero_()
+        step()
+    barrier(env)
+    l3.reset_counters()
+    total_ms = 0.0
+    barrier(env)
+    wall0 = time.time()
+    for _ in range(steps):
+        env.flush.zero_()  # flush L2 between timed iterations
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier(env)
+        e0.record(stream)
+        step()
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+        total_ms += e0.elapsed_time(e1)
+    barrier(env)
+    wall1 = time.time()
+    clocks = sampler.stop(wall0, wall1)
+    cnt = l3.counts()
+    launches = cnt["gpu_launches"]
+    total_ms = max_over_ranks(env, total_ms)
+    tests_per_step = sum_over_ranks(env, cnt["pair_tests"]) / max(steps, 1)
+    free_b, total_b = torch.cuda.mem_get_info(dev)
+    hbm_used = max_over_ranks(env, total_b - free_b)
+
+    # ---- parity digest of the last timed step's results, on every rank ----
+    t0 = time.perf_counter()
+    digest = api.result_digest(l3, [v.cam_id for v in scene.views])
+    digests = gather_digests(env, digest)
+    digest_s = time.perf_counter() - t0
+
+    # ---- separate instrumented pass for the per-stage / per-kernel numbers (same workload) ----
+    if n_gpus == 1:
+        l3.match_stage12(*mp)
+        t12, c12 = l3.timings(), l3.counts()
+        l3.match_stage3()
+        t3 = l3.timings()
+        l3.affinity()
+        t4 = l3.timings()
+    else:
+        step()
+        t12 = t3 = t4 = l3.timings()   # the stage timers accumulate over the phases of one step
+        c12 = l3.counts()
+    cfin = l3.counts()
+    phases = None
+    if trace_phases and n_gpus > 1:
+        tr = {}
+        for _ in range(10):
+            barrier(env)
+            sharding.run_sharded(l3, xch, prm, trace=tr)
+        phases = {k: 1e2 * v for k, v in tr.items()}  # ms per step (10 steps)
+        allp = [None] * env.world
+        dist.all_gather_object(allp, phases)
+        phases = allp
+
+    # ---- end to end through the public API with host buffers (H2D of the scene, D2H of A_) ----
+    h2d = scene.total_segments() * 16 + scene.num_views * (8 * 21 + 20) + sum(4 * len(v.neighbors) for v in scene.views)
+    d2h = 0
+    t_e2e = 0.0
+    for i in range(2 + e2e_steps):
+        env.flush.zero_()
+        barrier(env)
+        t0 = time.perf_counter()
+        l3.upload()                      # host -> device: segments, cameras, neighbour lists
+        step()
+        ij, w = l3.edges()               # device -> host: A_ (what the CPU clustering consumes)
+        l2g = l3.local2global()
+        barrier(env)
+        dt = time.perf_counter() - t0
+        if i >= 2:
+            t_e2e += dt
+        d2h = ij.nbytes + w.nbytes + l2g.nbytes
+    t_e2e = max_over_ranks(env, t_e2e)
+    e2e = {"value": tests_per_step * e2e_steps / t_e2e, "unit": "tests/s", "h2d_bytes_per_step": int(h2d) * n_gpus,
+           "d2h_bytes_per_step": int(d2h) * n_gpus, "ms_per_step": 1e3 * t_e2e / e2e_steps, "steps": e2e_steps,
+           "views_per_s": scene.num_views * e2e_steps / t_e2e,
+           "what": "Line3D.upload (host arrays -> HBM) + matchImages + affinity + edges()/local2global() D2H, per rank"}
+    return dict(l3=l3, xch=xch, total_ms=total_ms, steps=steps, tests_per_step=tests_per_step, t12=t12, t3=t3, t4=t4,
+                c12=c12, cfin=cfin, launches=launches, clocks=clocks, e2e=e2e, digest=digest, digests=digests,
+                digest_s=digest_s, hbm_used=hbm_used, phases=phases, wname=wname)
+
+
+def load_traffic(wname):
+    """DRAM bytes per launch from the ncu --set full capture of the same workload (tools/ncu_summary.py
+    writes profiles/r2_traffic.json); None when no capture exists for this workload."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json"))).get(wname, {})
+    except Exception:
+        return {}
+
+
+def build_rooflines(env, res, scene):
+    """Roofline objects of K1 (FP32 pipe) and K2 (FP64 pipe) and the figures of K3/K4; `dominant` names
+    the kernel with the larger share of the step."""
+    torch, api = env.torch, env.api
+    t12, t3, t4, c12, cfin = res["t12"], res["t3"], res["t4"], res["c12"], res["cfin"]
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    sm_max = res["clocks"].get("sm_max_mhz") or peaks.get("sm_max_mhz") or 1965.0
+    n_sm = torch.cuda.get_device_properties(env.dev).multi_processor_count
+    pk = api.Context(env.dev.index, env.stream.cuda_stream)
+    fp32_measured, fp64_measured = pk.fp32_peak_tflops(), pk.fp64_peak_tflops()
+    pk.close()
+    fp32_nominal = n_sm * 128 * 2 * sm_max * 1e6 / 1e12
+    fp64_nominal = n_sm * 64 * 2 * sm_max * 1e6 / 1e12
+    traffic = load_traffic(res["wname"])
+    step_ms = res["total_ms"] / res["steps"]
+
+    k1_s = max(t12["k1_kernel"], 1e-9) * 1e-3
+    k1_tests = float(c12["pair_tests"])
+    k1_launches = max(t12["k1_launches"], 1)
+    a1 = FLOP_PER_TEST * k1_tests / k1_s / 1e12
+    seg_n = scene.views[0].segs.shape[0]
+    n_pairs_local = max(c12["num_pairs_local"], 1)
+    k1_bytes = n_pairs_local * (32.0 + 16.0) * seg_n + k1_tests / 8.0 + 4.0 * n_pairs_local * seg_n
+    k1 = {
+        "kernel": "k1_pairtest_kernel", "bound": "fp32", "achieved": a1, "peak": fp32_measured, "unit": "TFLOP/s",
+        "frac": a1 / fp32_measured if fp32_measured else None,
+        "frac_is": "ALGORITHMIC flop (114 per test, SURVEY 8d) / measured FFMA peak: exceeds 1 when the kernel's "
+                   "reformulation needs fewer instructions than the reference formulation; issue_slot_frac is the hardware-side figure",
+        "issue_slot_frac": K1_ISSUED_PER_TEST * k1_tests / k1_s / (n_sm * 128 * sm_max * 1e6),
+        "issued_instructions_per_test": K1_ISSUED_PER_TEST,
+        "peak_source": "measured here: dense FFMA micro-benchmark (l3d_bench_fp32_peak); MEASURED_PEAKS.json has no FP32 entry; "
+                       "nominal %d SMs x 128 x 2 x %.0f MHz = %.1f TFLOP/s" % (n_sm, sm_max, fp32_nominal),
+        "peak_nominal": fp32_nominal, "algorithmic_flop_per_test": FLOP_PER_TEST,
+        "tests_per_launch": k1_tests / k1_launches, "launches_per_step": k1_launches,
+        "launch_ms": 1e3 * k1_s / k1_launches, "k1_tests_per_s": k1_tests / k1_s,
+        "share_of_step": 1e3 * k1_s / step_ms if res["steps"] else None,
+        "traffic": traffic.get("k1_pairtest_kernel"),
+        "hbm": {"algorithmic_bytes_per_launch": k1_bytes / k1_launches, "achieved_gbs": k1_bytes / k1_s / 1e9,
+                "peak_gbs": peaks.get("hbm_gbs"),
+                "frac": (k1_bytes / k1_s / 1e9) / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None,
+                "note": "descriptors + segments + 1 bit per test + counts; the kernel is FP32-issue bound, not HBM bound"},
+    }
+    k2_s = max(t12["exact"], 1e-9) * 1e-3
+    a2 = K2_FLOP_PER_CANDIDATE * float(c12["candidates"]) / k2_s / 1e12
+    k2 = {
+        "kernel": "k2 (exact re-test + triangulation + kNN + orientation)", "bound": "fp64", "achieved": a2,
+        "peak": fp64_measured, "unit": "TFLOP/s", "frac": a2 / fp64_measured if fp64_measured else None,
+        "peak_source": "measured here: dense DFMA micro-benchmark (l3d_bench_fp64_peak); nominal %d SMs x 64 x 2 x %.0f MHz = %.1f TFLOP/s"
+                       % (n_sm, sm_max, fp64_nominal),
+        "peak_nominal": fp64_nominal, "algorithmic_flop_per_candidate": K2_FLOP_PER_CANDIDATE,
+        "candidates": c12["candidates"], "stage_ms": t12["exact"], "share_of_step": t12["exact"] / step_ms,
+        "traffic": traffic.get("k2"),
+    }
+    other = {
+        "k3_score": {"bound": "fp32+sfu, dependency chain over the views",
+                     "sim_evals_per_s": float(cfin["sim_evals"]) / max(t3["score"] * 1e-3, 1e-9),
+                     "algorithmic_flop_per_sim_eval": 40.0,
+                     "achieved_tflops": 40.0 * float(cfin["sim_evals"]) / max(t3["score"] * 1e-3, 1e-9) / 1e12,
+                     "share_of_step": t3["score"] / step_ms},
+        "k4_affinity": {"bound": "hbm gather", "algorithmic_bytes_per_edge_test": 160.0,
+                        "edge_tests": cfin["filtered_entries"],
+                        "achieved_gbs": 160.0 * float(cfin["filtered_entries"]) / max(t4["affinity"] * 1e-3, 1e-9) / 1e9,
+                        "peak_gbs": peaks.get("hbm_gbs"), "share_of_step": t4["affinity"] / step_ms},
+    }
+    dominant = k1 if (1e3 * k1_s) >= t12["exact"] else k2
+    return dominant, {"k1_pairtest": k1, "k2_exact": k2, **other}
+
+
+def cpu_baseline_and_parity(env, args, scene_mod, wname):
+    """Rank 0, N=1: the CPU oracle timed on a bounded cut of the workload, and the product compared with it
+    bit for bit on the same cut (the oracle here is the checker and the reported baseline, never the product)."""
+    import oracle_py
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from parity_utils import compare_full
+    kind, nv = CPU_SAMPLE.get(wname, ("c4", 16))
+    if wname in ("c4", "c4s"):
+        nv = 32   # ~10-30 s of CPU work on the box's cores
+    cut = scene_mod.make_scene(kind, n_views=nv)
+    t0 = time.perf_counter()
+    orc = oracle_py.run_scene(cut)
+    tests, tm = orc.pair_tests(), orc.timers()
+    tcpu = tm["match_images"] + tm["reconstruct"]
+    cores = oracle_py.lib().orc_max_threads()
+    base = {"value": tests / tcpu, "unit": "tests/s", "cores": cores, "kind": "port",
+            "sample": "%d-view cut of the %s generator (same per-view shape), stages 1-4, one pass, %.2e tests, %.1f s"
+                      % (cut.num_views, kind, tests, tcpu),
+            "views_per_s_of_the_sample": cut.num_views / tcpu, "stage1_tests_per_s": tests / max(tm["match"], 1e-9)}
+    parity = None
+    try:
+        l3 = env.api.run_scene(cut, device=env.dev.index, stream=env.stream.cuda_stream)
+        sizes = compare_full(l3, orc, cut, check_scored=False)
+        parity = {"vs": "CPU oracle, the cut above", "result": "bit-exact", "compared": sizes}
+    except AssertionError as e:
+        parity = {"vs": "CPU oracle, the cut above", "result": "MISMATCH", "detail": str(e)[:300]}
+    orc.close()
+    return base, parity
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2")
+    ap.add_argument("--workload", default="c4")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-riders", action="store_true", help="N=1: skip the config-2 and config-3 measurements")
     ap.add_argument("--no-stream", action="store_true", help="skip the config-3 key-frame stream measurement")
-    ap.add_argument("--check", action="store_true", help="also verify the result against the CPU oracle")
-    ap.add_argument("--trace-phases", action="store_true", help="N>1: wall time per phase/exchange (stderr)")
+    ap.add_argument("--check", action="store_true", help="also verify the full result against the CPU oracle (slow on c4)")
+    ap.add_argument("--trace-phases", action="store_true", help="N>1: wall time per phase/exchange on every rank")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -360,257 +672,93 @@ def main():
     if args.workload == "c3":
         bench_stream(args, scene_mod)
         return
+    if args.workload in ("c5", "c5s"):
+        c5 = importlib.import_module("3dline-slam_b200.city")
+        c5.bench_city(args, setup_env(args), sys.modules[__name__])
+        return
 
-    import torch
-    api = importlib.import_module("3dline-slam_b200.api")
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    dev = torch.device("cuda", local_rank if world > 1 else 0)
-    torch.cuda.set_device(dev)
-    n_gpus = world if world > 1 else 1
-    if args.gpus != n_gpus and rank == 0:
-        print("note: --gpus %d but WORLD_SIZE=%d; using %d" % (args.gpus, world, n_gpus), file=sys.stderr)
-
+    env = setup_env(args)
+    n_gpus, rank, dist = env.n_gpus, env.rank, env.dist
     scene, wname = make_workload(scene_mod, args.workload, n_gpus)
-    prm = scene.params
-    stream = torch.cuda.current_stream(dev)
-    l3 = api.Line3D("", False, scene.max_image_width, 3000, False, True, dev.index, stream.cuda_stream)
-    l3.shard = (rank, n_gpus)
-    l3.load_scene(scene)
-    l3.upload()  # tables resident in HBM before the timed region
+    steps = args.steps
+    res = bench_batch(env, args, scene, wname, steps, args.warmup, min(steps, 20), trace_phases=args.trace_phases)
+    if len(set(res["digests"])) != 1:
+        raise SystemExit("parity digest differs between ranks: %r" % (res["digests"],))
+    value = res["tests_per_step"] * steps / (res["total_ms"] * 1e-3)
+    views_per_s = scene.num_views * steps / (res["total_ms"] * 1e-3)
 
-    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
-
-    sharding = importlib.import_module("3dline-slam_b200.sharding")
-    xch = sharding.Exchanger(dist, torch, dev) if n_gpus > 1 else None
-
-    def step():
-        if n_gpus == 1:
-            l3.matchImages(prm["sigma_p"], prm["sigma_a"], prm["num_neighbors"], prm["epipolar_overlap"], prm["knn"],
-                           prm["const_reg_depth"])
-            l3.affinity()
-        else:
-            # view slices per rank; forward matches, fold programs, hypotheses and edges are
-            # all-gathered with NCCL (3dline-slam_b200/sharding.py)
-            sharding.run_sharded(l3, xch, prm)
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    sampler = ClockSampler(dev.index)
-    sampler.start()
-    for _ in range(args.warmup):
-        flush.zero_()
-        step()
-    barrier()
-
-    l3.reset_counters()
-    total_ms = 0.0
-    stage_ms = {}
-    k1_ms, k1_launches = 0.0, 0
-    barrier()
-    wall0 = time.time()
-    for _ in range(args.steps):
-        flush.zero_()  # flush L2 between timed iterations (inputs are smaller than L2)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        e0.record(stream)
-        step()
-        e1.record(stream)
-        torch.cuda.synchronize(dev)
-        total_ms += e0.elapsed_time(e1)
-        # stage timers of the library (CUDA events on the same stream); affinity() resets them,
-        # so read both halves
-        for k, v in l3.timings().items():
-            stage_ms[k] = stage_ms.get(k, 0.0) + v
-    barrier()
-    wall1 = time.time()
-    clocks = sampler.stop(wall0, wall1)
-    cnt = l3.counts()
-    launches = cnt["gpu_launches"]
-
-    # max over ranks
-    if dist is not None:
-        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
-        tt = torch.tensor([float(cnt["pair_tests"])], dtype=torch.float64, device=dev)
-        dist.all_reduce(tt, op=dist.ReduceOp.SUM)
-        tests_per_step = float(tt.item())
-    else:
-        tests_per_step = float(cnt["pair_tests"])
-
-    # ---- separate instrumented passes for the per-stage / K1 numbers (same workload) ----
-    if n_gpus == 1:
-        l3.match_stage12(prm["sigma_p"], prm["sigma_a"], prm["num_neighbors"], prm["epipolar_overlap"], prm["knn"],
-                         prm["const_reg_depth"])
-        t12 = l3.timings()
-        c12 = l3.counts()
-        l3.match_stage3()
-        t3 = l3.timings()
-        l3.affinity()
-        t4 = l3.timings()
-    else:
-        step()
-        t12 = t3 = t4 = l3.timings()   # the stage timers accumulate over the phases of one step
-        c12 = l3.counts()
-    cfin = l3.counts()
-    if args.trace_phases and n_gpus > 1:
-        tr = {}
-        for _ in range(10):
-            barrier()
-            sharding.run_sharded(l3, xch, prm, trace=tr)
-        if rank == 0:
-            print("phase ms (rank 0, synchronised after every phase): " +
-                  ", ".join("%s %.3f" % (k, 1e2 * v) for k, v in tr.items()), file=sys.stderr)
-    k1_s = max(t12["k1_kernel"], 1e-9) * 1e-3
-    k1_tests = float(c12["pair_tests"])
-
-    value = tests_per_step * args.steps / (total_ms * 1e-3)
-    views_per_s = scene.num_views * args.steps / (total_ms * 1e-3)
-
-    # ---- end to end through the public API with host buffers (H2D of the scene, D2H of A_) ----
-    # every rank uploads the (replicated) tables and reads back A_; wall clock, max over ranks
-    h2d = scene.total_segments() * 16 + scene.num_views * (8 * 21 + 20) + sum(4 * len(v.neighbors) for v in scene.views)
-    d2h = 0
-    t_e2e = 0.0
-    e2e_steps = min(args.steps, 20)
-    for i in range(2 + e2e_steps):
-        flush.zero_()
-        barrier()
-        t0 = time.perf_counter()
-        l3.upload()                      # host -> device: segments, cameras, neighbour lists
-        step()
-        ij, w = l3.edges()               # device -> host: A_ (what the CPU clustering consumes)
-        l2g = l3.local2global()
-        barrier()
-        dt = time.perf_counter() - t0
-        if i >= 2:
-            t_e2e += dt
-        d2h = ij.nbytes + w.nbytes + l2g.nbytes
-    if dist is not None:
-        t = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t_e2e = float(t.item())
-    e2e = {"value": tests_per_step * e2e_steps / t_e2e, "unit": "tests/s", "h2d_bytes_per_step": int(h2d) * n_gpus,
-           "d2h_bytes_per_step": int(d2h) * n_gpus, "ms_per_step": 1e3 * t_e2e / e2e_steps, "steps": e2e_steps,
-           "views_per_s": scene.num_views * e2e_steps / t_e2e,
-           "what": "Line3D.upload (pageable host arrays -> HBM) + matchImages + affinity + edges()/local2global() D2H, per rank"}
+    rider2 = None
+    if n_gpus == 1 and wname == "c4" and not args.no_riders:
+        sc2, _ = make_workload(scene_mod, "c2")
+        r2 = bench_batch(env, args, sc2, "c2", max(steps, 20), max(args.warmup, 3), 20)
+        dom2, roofs2 = build_rooflines(env, r2, sc2)
+        ms2 = r2["total_ms"] / r2["steps"]
+        rider2 = {"what": "BASELINE config[1]: 50 views x 1000 segments x 10 neighbours, 640x480, one B200, L2 flushed",
+                  "value": r2["tests_per_step"] / (ms2 * 1e-3), "unit": "tests/s", "ms_per_step": ms2,
+                  "views_per_s": sc2.num_views / (ms2 * 1e-3), "steps": r2["steps"],
+                  "stage_ms": {"prep": r2["t12"]["prep"], "k1_pairtest": r2["t12"]["pairtest"], "k2_exact": r2["t12"]["exact"],
+                               "k3_score": r2["t3"]["score"], "k4_affinity": r2["t4"]["affinity"]},
+                  "e2e": r2["e2e"], "roofline": dom2, "parity_digest": r2["digest"], "gpu_launches": r2["launches"]}
+        r2["l3"].ctx.close()
 
     if rank != 0:
         if dist is not None:
+            dist.barrier()
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (K1) ----
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    sm_max = clocks.get("sm_max_mhz") or peaks.get("sm_max_mhz") or 1965.0
-    n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
-    fp32_nominal = n_sm * 128 * 2 * sm_max * 1e6 / 1e12
-    fp32_measured = api.Context(dev.index, stream.cuda_stream).fp32_peak_tflops()
-    achieved = FLOP_PER_TEST * k1_tests / k1_s / 1e12
-    roofline = {
-        "kernel": "k1_pairtest_kernel", "bound": "fp32", "achieved": achieved, "peak": fp32_measured,
-        "unit": "TFLOP/s", "frac": achieved / fp32_measured if fp32_measured else None,
-        "peak_source": "measured here: dense FFMA micro-benchmark (l3d_bench_fp32_peak); nominal %d SMs x 128 x 2 x %.0f MHz = %.1f TFLOP/s"
-                       % (n_sm, sm_max, fp32_nominal),
-        "peak_nominal": fp32_nominal, "frac_of_nominal": achieved / fp32_nominal,
-        # the kernel's own formulation issues 35.5 SASS instructions per test (cuobjdump count over the
-        # unrolled loop): fraction of the lane-issue capacity (SMs x 4 schedulers x 32 lanes x clock)
-        "issued_instructions_per_test": 35.5,
-        "lane_issue_frac": 35.5 * k1_tests / k1_s / (n_sm * 128 * sm_max * 1e6),
-        "algorithmic_flop_per_test": FLOP_PER_TEST, "tests_per_launch": k1_tests / max(t12["k1_launches"], 1),
-        "launch_ms": 1e3 * k1_s / max(t12["k1_launches"], 1), "k1_tests_per_s": k1_tests / k1_s,
-        # dram__bytes_read.sum + dram__bytes_write.sum of one K1 launch on C2 (ncu --set full,
-        # profiles/r1f_ncu_full_c2.md); the 31 MB bit mask stays in the 126 MB L2
-        "traffic": 2435840 if wname == "c2" else None,
-    }
-    n_pairs_local = max(c12["num_pairs_local"], 1)
-    seg_n = scene.views[0].segs.shape[0]
-    k1_bytes = n_pairs_local * (32.0 + 16.0) * seg_n + k1_tests / 8.0 + 4.0 * n_pairs_local * seg_n
-    roofline["hbm"] = {"algorithmic_bytes_per_launch": k1_bytes / max(t12["k1_launches"], 1),
-                       "achieved_gbs": k1_bytes / k1_s / 1e9, "peak_gbs": peaks.get("hbm_gbs"),
-                       "frac": (k1_bytes / k1_s / 1e9) / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None,
-                       "note": "descriptors + segments + 1 bit per test + counts; the kernel is FP32-pipe bound, not HBM bound"}
-
-    # the other stages against the roofline that bounds them (SURVEY.md 8d figures); they are
-    # latency / dependency bound at this scene size, which is what the small fractions say
-    fp64_nominal = n_sm * 64 * 2 * sm_max * 1e6 / 1e12
-    k2_flop = 330.0 * float(c12["candidates"])
-    stage_rooflines = {
-        "k2_exact": {"bound": "fp64", "algorithmic_flop_per_candidate": 330.0, "candidates": c12["candidates"],
-                     "achieved_tflops": k2_flop / max(t12["exact"] * 1e-3, 1e-9) / 1e12, "peak_tflops": fp64_nominal,
-                     "frac": k2_flop / max(t12["exact"] * 1e-3, 1e-9) / 1e12 / fp64_nominal},
-        "k3_score": {"bound": "fp32+sfu, dependency chain over the views",
-                     "sim_evals_per_s": float(cfin["sim_evals"]) / max(t3["score"] * 1e-3, 1e-9),
-                     "algorithmic_flop_per_sim_eval": 40.0,
-                     "achieved_tflops": 40.0 * float(cfin["sim_evals"]) / max(t3["score"] * 1e-3, 1e-9) / 1e12},
-        "k4_affinity": {"bound": "hbm gather", "algorithmic_bytes_per_edge_test": 160.0,
-                        "edge_tests": cfin["filtered_entries"],
-                        "achieved_gbs": 160.0 * float(cfin["filtered_entries"]) / max(t4["affinity"] * 1e-3, 1e-9) / 1e9,
-                        "peak_gbs": peaks.get("hbm_gbs")},
-    }
-
-    cpu_baseline = None
+    dominant, roofs = build_rooflines(env, res, scene)
+    cpu_baseline = parity = None
     if not args.no_cpu_baseline and n_gpus == 1:   # reported on rank 0 at N=1 only
-        base_scene, bname = make_workload(scene_mod, args.workload, 1)
-        r = run_cpu_oracle(base_scene)
-        tcpu = r["timers"]["match_images"] + r["timers"]["reconstruct"]
-        cpu_baseline = {"value": r["tests"] / tcpu, "unit": "tests/s", "cores": r["cores"], "kind": "port",
-                        "sample": "full %s scene (%d views), stages 1-4, one pass, %.1f s" % (bname, base_scene.num_views, tcpu),
-                        "views_per_s": base_scene.num_views / tcpu,
-                        "stage1_tests_per_s": r["tests"] / max(r["timers"]["match"], 1e-9)}
+        cpu_baseline, parity = cpu_baseline_and_parity(env, args, scene_mod, wname)
 
     if args.check:
         import oracle_py
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         from parity_utils import compare_full
         if n_gpus == 1:
-            l3.reconstruct3Dlines()
+            res["l3"].reconstruct3Dlines()
             orc = oracle_py.run_scene(scene)
-            print("check vs oracle:", compare_full(l3, orc, scene, check_scored=False), file=sys.stderr)
-        else:  # the other ranks have left by now; sharded parity is tests/test_parity_gpu.py / test_full_size_gpu.py
-            print("--check is a single-GPU option (sharded == unsharded == oracle is covered by the GPU tests)",
-                  file=sys.stderr)
+            print("check vs oracle:", compare_full(res["l3"], orc, scene, check_scored=False), file=sys.stderr)
+        else:
+            print("--check is a single-GPU option; at N > 1 compare parity_digest with the N = 1 run", file=sys.stderr)
 
+    t12, t3, t4, cfin = res["t12"], res["t3"], res["t4"], res["cfin"]
     line = {
         "metric": "segment_pair_tests_per_s", "value": value, "unit": "tests/s", "n_gpus": n_gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32 pre-filter + f64 exact", "data": "synthetic",
-        "config": {"workload": wname, "views": scene.num_views, "segments_per_view": scene.views[0].segs.shape[0],
-                   "neighbours": prm["num_neighbors"], "image": "%dx%d" % (scene.views[0].width, scene.views[0].height),
-                   "l2": "flushed between timed iterations (256 MB write)",
-                   "parallelism": ("1 rank" if n_gpus == 1 else
-                                   "%d contiguous view slices: matching, scoring rows, hypotheses and edges per slice; "
-                                   "4 NCCL all-gathers per step; the score fold is replicated" % n_gpus)},
+        "steps": steps, "warmup": args.warmup, "ms_per_step": res["total_ms"] / steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32 pre-filter + f64 exact", "data": "synthetic",
+        "config": workload_config(scene_mod, wname),
+        "l2_policy": "flushed between timed iterations (256 MB write)",
+        "parallelism": ("1 rank" if n_gpus == 1 else
+                        "%d contiguous view slices of the same scene: matching, scoring rows, hypotheses and edges per slice; "
+                        "NCCL all-gathers make the results whole on every rank" % n_gpus),
         "views_per_s": views_per_s,
-        "stage1_tests_per_s": k1_tests / max((t12["pairtest"] + t12["exact"]) * 1e-3, 1e-9),
+        "stage1_tests_per_s": float(res["c12"]["pair_tests"]) / max((t12["pairtest"] + t12["exact"]) * 1e-3, 1e-9),
         "stage_ms": {"prep": t12["prep"], "k1_pairtest": t12["pairtest"], "k2_exact": t12["exact"],
                      "k3_score": t3["score"], "k4_affinity": t4["affinity"]},
         "counts": {k: cfin[k] for k in ("pair_tests", "candidates", "forward_matches", "scored_entries", "sim_evals",
                                          "filtered_entries", "num_pairs", "num_entries", "num_edges", "num_local_ids")},
-        "roofline": roofline, "stage_rooflines": stage_rooflines, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+        "parity_digest": res["digest"],
+        "parity_digest_what": "sha256 of filtered lists + hypotheses + A_ + local2global_ after the last timed step; equal on all %d rank(s)" % n_gpus,
+        "hbm_used_bytes_max_rank": res["hbm_used"],
+        "roofline": dominant, "rooflines": roofs, "cpu_baseline": cpu_baseline, "parity_vs_oracle": parity,
+        "e2e": res["e2e"], "gpu_launches": res["launches"], "clocks": res["clocks"],
     }
+    if res["phases"]:
+        line["phase_ms_per_rank"] = res["phases"]
+    if res["xch"] is not None:
+        line["exchange"] = {"bytes_gathered_per_step_rank0": res["xch"].bytes_gathered // max(1, steps + args.warmup + 3 + min(steps, 20)),
+                            "fallbacks": res["xch"].fallbacks}
+    if rider2 is not None:
+        line["config2"] = rider2
     # BASELINE config 3 (key-frame stream, incremental mode) rides along on the default single-GPU run
-    if n_gpus == 1 and args.workload == "c2" and not args.no_stream:
+    if n_gpus == 1 and wname == "c4" and not args.no_riders and not args.no_stream:
         try:
             import copy
             a3 = copy.copy(args)
             a3.steps, a3.warmup = 40, 3
+            a3.no_cpu_baseline = True if args.no_cpu_baseline else False
             s3 = bench_stream(a3, scene_mod, emit=False)
             line["config3_stream"] = {
                 "what": "bench.py --workload c3: one L3DPPing cycle in steady state (window 20, 1000 segments, 10 neighbours, "
@@ -623,6 +771,7 @@ def main():
             line["config3_stream"] = {"error": repr(e)}
     print(json.dumps(line))
     if dist is not None:
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -289,6 +289,8 @@ int l3d_test_expf(l3d_ctx* ctx, const float* x, float* y, uint32_t n);
 int l3d_test_acos(l3d_ctx* ctx, const double* x, double* y, uint32_t n);
 /* peak-FP32 micro-benchmark used by bench.py for the roofline denominator (TFLOP/s) */
 int l3d_bench_fp32_peak(l3d_ctx* ctx, float* tflops);
+/* the same for the FP64 pipe (DFMA chains): the denominator of the K2 roofline */
+int l3d_bench_fp64_peak(l3d_ctx* ctx, float* tflops);
 
 #ifdef __cplusplus
 }
