@@ -478,7 +478,7 @@ def bench_batch(env, args, scene, wname, steps, warmup, e2e_steps, trace_phases=
     cnt = l3.counts()
     launches = cnt["gpu_launches"]
     total_ms = max_over_ranks(env, total_ms)
-    tests_per_step = sum_over_ranks(env, cnt["pair_tests"]) / max(steps, 1)
+    tests_per_step = sum_over_ranks(env, cnt["pair_tests"])   # the counter holds the last step's tests
     free_b, total_b = torch.cuda.mem_get_info(dev)
     hbm_used = max_over_ranks(env, total_b - free_b)
 
