@@ -195,6 +195,7 @@ int l3d_scene_commit(l3d_ctx* ctx)
     CK(ctx->d_rays.ensure(S));
     CK(ctx->d_midray.ensure(3 * S));
     CK(ctx->d_planes.ensure(S));
+    CK(ctx->d_v32.ensure(S));
     CK(ctx->d_view_xb.ensure(V));
     CK(ctx->d_views.ensure(V));
     CK(cudaMemcpyAsync(ctx->d_segs.p, hseg, S * sizeof(float4), cudaMemcpyHostToDevice, st));
@@ -559,7 +560,7 @@ int run_stage12_batches(l3d_ctx* ctx)
     cudaEvent_t ev = ctx->tm.begin(L3D_T_PREP, st);
     CK(cudaMemsetAsync(ctx->d_view_xb.p, 0, V * sizeof(float), st));
     ctx->cnt.gpu_launches += launch_k0_prep(ctx->d_segs.p, ctx->d_seg_view.p, ctx->d_views.p, S,
-                                            ctx->prm.max_image_width, ctx->d_desc.p, ctx->d_rays.p, ctx->d_midray.p, ctx->d_planes.p,
+                                            ctx->prm.max_image_width, ctx->d_desc.p, ctx->d_rays.p, ctx->d_midray.p, ctx->d_planes.p, ctx->d_v32.p,
                                             ctx->d_view_xb.p, st);
     ctx->tm.end(ev, st);
 
@@ -582,6 +583,16 @@ int run_stage12_batches(l3d_ctx* ctx)
         CK(grow(ctx->d_cand_off, (size_t)max_rows + 1));
         CK(grow(ctx->d_fin_cnt, (size_t)max_rows + 1));
         CK(grow(ctx->d_fin_off, (size_t)max_rows + 1));
+        CK(grow(ctx->d_row_epi, (size_t)max_rows + 1));
+        CK(grow(ctx->d_ncont, (size_t)max_rows + 1));
+        CK(grow(ctx->d_fb_rows, (size_t)max_rows + 1));
+        CK(grow(ctx->d_row_pair, (size_t)max_rows + 1));
+        CK(ctx->d_k2ctr.ensure(8));
+        if (!ctx->n_sm) {
+            cudaDeviceProp prop;
+            CK(cudaGetDeviceProperties(&prop, ctx->device));
+            ctx->n_sm = prop.multiProcessorCount;
+        }
         CK(grow(ctx->d_scan, scan_scratch_words(std::max(max_rows, ctx->total_tgt_rows) + 1) + 64));
         CK(grow(ctx->d_ctas, ctx->ctas_h.size()));
         CK(cudaMemcpyAsync(ctx->d_ctas.p, ctx->ctas_h.data(), ctx->ctas_h.size() * sizeof(K1Cta),
@@ -597,7 +608,7 @@ int run_stage12_batches(l3d_ctx* ctx)
         cudaEvent_t ek = ctx->tm.begin(L3D_T_K1_KERNEL, st);
         ctx->cnt.gpu_launches +=
             launch_k1_pairtest(ctx->d_pairs.p, ctx->d_ctas.p + b.cta0, b.n_ctas, ctx->d_segs.p, ctx->d_desc.p,
-                               ctx->d_view_xb.p, ctx->d_mask.p, ctx->d_cand_cnt.p, ctx->epi_overlap,
+                               ctx->d_view_xb.p, ctx->d_mask.p, ctx->d_cand_cnt.p, ctx->d_row_epi.p, ctx->epi_overlap,
                                ctx->prm.filter_mode, st);
         ctx->tm.end(ek, st);
         ctx->tm.ms[L3D_T_K1_LAUNCHES] += 1.0f;
@@ -614,12 +625,21 @@ int run_stage12_batches(l3d_ctx* ctx)
         CK(grow(ctx->d_cand_rec, (size_t)n_cand + 1));
         CK(grow(ctx->d_fin_rec, (size_t)n_cand + 1));
         cudaEvent_t e2 = ctx->tm.begin(L3D_T_EXACT, st);
+        int uses_ncont = 0;
         ctx->cnt.gpu_launches +=
             launch_k2_exact(ctx->d_pairs.p, ctx->d_ctas.p + b.cta0, b.n_ctas, b.n_rows, n_cand, ctx->d_segs.p,
-                            ctx->d_rays.p, ctx->d_midray.p, ctx->d_planes.p, ctx->d_views.p, ctx->d_mask.p, ctx->d_cand_off.p,
-                            ctx->d_heap.p, ctx->d_cand_rec.p,
-                            ctx->d_fin_rec.p, ctx->d_fin_cnt.p, ctx->epi_overlap, ctx->prm.knn,
-                            ctx->prm.max_image_width, ctx->raw_mode ? 0 : 1, b.max_tgt, st);
+                            ctx->d_rays.p, ctx->d_midray.p, ctx->d_planes.p, ctx->d_v32.p, ctx->d_desc.p, ctx->d_row_epi.p,
+                            ctx->d_views.p, ctx->d_mask.p, ctx->d_cand_off.p, ctx->d_heap.p, ctx->d_cand_rec.p,
+                            ctx->d_fin_rec.p, ctx->d_fin_cnt.p, ctx->d_ncont.p, ctx->d_k2ctr.p, ctx->d_fb_rows.p, ctx->d_row_pair.p,
+                            ctx->epi_overlap, ctx->prm.knn, ctx->prm.max_image_width, ctx->raw_mode ? 0 : 1, ctx->n_sm,
+                            &uses_ncont, st);
+        if (getenv("L3D_K2_DEBUG")) {  // contenders / rows handed to the row kernel, per batch
+            uint32_t c2[4] = {0, 0, 0, 0};
+            cudaMemcpyAsync(c2, ctx->d_k2ctr.p, sizeof(c2), cudaMemcpyDeviceToHost, st);
+            cudaStreamSynchronize(st);
+            fprintf(stderr, "[k2] batch rows %u candidates %u contenders %u popped %u fallback rows %u\n", b.n_rows, n_cand, c2[0],
+                    c2[2], c2[1]);
+        }
         ctx->cnt.gpu_launches +=
             launch_scan_u32(ctx->d_fin_cnt.p, ctx->d_fin_off.p, b.n_rows, ctx->d_scan.p, ctx->d_scan.cap, st);
         CK(cudaMemcpyAsync(ctx->rb_at<uint32_t>(l3d_ctx::RB_NFIN), ctx->d_fin_off.p + b.n_rows, sizeof(uint32_t),
@@ -630,7 +650,7 @@ int run_stage12_batches(l3d_ctx* ctx)
         CK(grow(ctx->d_fwd_rec, (size_t)rec_base + n_fin, rec_base, st));
         ctx->cnt.gpu_launches +=
             launch_k2_compact(ctx->d_cand_off.p, ctx->d_fin_cnt.p, ctx->d_fin_off.p, rec_base, ctx->d_fin_rec.p,
-                              ctx->d_fwd_rec.p, ctx->d_fwd_off.p + b.row0, b.n_rows, st);
+                              ctx->d_fwd_rec.p, ctx->d_fwd_off.p + b.row0, b.n_rows, uses_ncont ? ctx->d_ncont.p : nullptr, st);
         CK(cudaMemcpyAsync(ctx->d_fwd_cnt.p + b.row0, ctx->d_fin_cnt.p, b.n_rows * sizeof(uint32_t),
                            cudaMemcpyDeviceToDevice, st));
         ctx->tm.end(e2, st);

@@ -18,13 +18,14 @@
 namespace l3d {
 // launchers defined in the other translation units
 int launch_k1_pairtest(const PairDev*, const K1Cta*, uint32_t, const float4*, const SegDesc*, const float*, uint32_t*,
-                       uint32_t*, float, int, cudaStream_t);
+                       uint32_t*, RowEpi32*, float, int, cudaStream_t);
 int k1_rows_per_cta();
 int launch_k2_exact(const PairDev*, const K1Cta*, uint32_t, uint32_t, uint32_t, const float4*, const SegRays*,
-                    const double*, const SegPlane*, const ViewDev*, const uint32_t*, const uint32_t*, unsigned long long*, FwdRec*,
-                    FwdRec*, uint32_t*, float, int, int, int, uint32_t, cudaStream_t);
+                    const double*, const SegPlane*, const SegV32*, const SegDesc*, const RowEpi32*, const ViewDev*,
+                    const uint32_t*, const uint32_t*, unsigned long long*, FwdRec*, FwdRec*, uint32_t*, uint32_t*, uint32_t*,
+                    uint2*, uint32_t*, float, int, int, int, int, int*, cudaStream_t);
 int launch_k2_compact(const uint32_t*, const uint32_t*, const uint32_t*, uint32_t, const FwdRec*, FwdRec*, uint32_t*,
-                      uint32_t, cudaStream_t);
+                      uint32_t, const uint32_t*, cudaStream_t);
 int launch_k3_score(uint32_t, const uint32_t*, ListRec*, const ListGeo*, float, float, void*, cudaStream_t);
 int launch_k3_inv_capacity(const PairDev*, uint32_t, uint32_t, const uint32_t*, const uint32_t*, const FwdRec*,
                            uint32_t*, uint32_t*, uint32_t, uint32_t, cudaStream_t);
@@ -248,6 +249,12 @@ struct l3d_ctx {
     DevBuf<SegRays> d_rays;
     DevBuf<double> d_midray;
     DevBuf<SegPlane> d_planes;
+    DevBuf<SegV32> d_v32;          // FP32 image of rays / planes (K2's certified depth-sign test)
+    DevBuf<RowEpi32> d_row_epi;    // K1's per-row epipolar lines of the current batch
+    DevBuf<uint32_t> d_ncont, d_k2ctr;  // K2: contenders per batch row; {work items, fallback rows}
+    DevBuf<uint2> d_fb_rows;       // K2: rows handed to the literal row kernel
+    DevBuf<uint32_t> d_row_pair;   // K2: pair of every batch row
+    int n_sm = 0;
     DevBuf<float> d_view_xb;
     DevBuf<ViewDev> d_views;
     DevBuf<PairDev> d_pairs;

@@ -30,6 +30,23 @@ struct __align__(16) SegPlane {
     double cn;
 };
 
+// FP32 image of the triangulation tables of one segment (K2's certified depth-sign test): plane normal and
+// n.C, endpoint rays; rounded once from the double tables of k0_prep
+struct __align__(16) SegV32 {
+    float nx, ny, nz, cn;
+    float r1x, r1y, r1z, r2x;
+    float r2y, r2z, pad0, pad1;
+};
+static_assert(sizeof(SegV32) == 48, "SegV32 must be 48 bytes");
+
+// what K1 knows about a source row and K2's FP32 ranking re-uses: the normalised epipolar lines of both
+// endpoints, the numerator error bound and the smaller of the two line norms (batch-local row index)
+struct __align__(16) RowEpi32 {
+    float A1, B1, C1, A2;
+    float B2, C2, cN, nmin;
+};
+static_assert(sizeof(RowEpi32) == 32, "RowEpi32 must be 32 bytes");
+
 struct ViewDev {
     double C[3];
     double RtKinv[9];
@@ -162,11 +179,11 @@ size_t scan_scratch_words(uint32_t n);
 
 int launch_k0_prep(const float4* segs, const uint32_t* seg_view, const ViewDev* views, uint32_t S,
                    int max_image_width, SegDesc* desc, SegRays* rays, double* midray, SegPlane* planes,
-                   float* view_xb,
+                   SegV32* v32, float* view_xb,
                    cudaStream_t st);
 
 int launch_k1_pairtest(const PairDev* pairs, const K1Cta* ctas, uint32_t n_ctas, const float4* segs,
                        const SegDesc* desc, const float* view_xb, uint32_t* mask, uint32_t* cand_cnt,
-                       float thr, int filter_mode, cudaStream_t st);
+                       RowEpi32* row_epi, float thr, int filter_mode, cudaStream_t st);
 
 }  // namespace l3d

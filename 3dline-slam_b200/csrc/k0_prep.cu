@@ -17,7 +17,7 @@ __global__ void __launch_bounds__(256) k0_prep_kernel(const float4* __restrict__
                                                       const ViewDev* __restrict__ views, uint32_t S, double W,
                                                       SegDesc* __restrict__ desc, SegRays* __restrict__ rays,
                                                       double* __restrict__ midray, SegPlane* __restrict__ planes,
-                                                      float* __restrict__ view_xb)
+                                                      SegV32* __restrict__ v32, float* __restrict__ view_xb)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= S) return;
@@ -46,6 +46,13 @@ __global__ void __launch_bounds__(256) k0_prep_kernel(const float4* __restrict__
     pl.n[0] = n.x; pl.n[1] = n.y; pl.n[2] = n.z;
     pl.cn = dot3(d3(Cv[0], Cv[1], Cv[2]), n);
     planes[i] = pl;
+    // FP32 image of the same tables for K2's certified depth-sign test (not on the decision path)
+    SegV32 f;
+    f.nx = (float)n.x; f.ny = (float)n.y; f.nz = (float)n.z; f.cn = (float)pl.cn;
+    f.r1x = (float)r1.x; f.r1y = (float)r1.y; f.r1z = (float)r1.z;
+    f.r2x = (float)r2.x; f.r2y = (float)r2.y; f.r2z = (float)r2.z;
+    f.pad0 = f.pad1 = 0.0f;
+    v32[i] = f;
 
     // ---- K1 descriptor (conservative, not on the decision path) ----
     const double dx = x2 - x1, dy = y2 - y1;
@@ -81,11 +88,11 @@ __global__ void __launch_bounds__(256) k0_prep_kernel(const float4* __restrict__
 
 int launch_k0_prep(const float4* segs, const uint32_t* seg_view, const ViewDev* views, uint32_t S,
                    int max_image_width, SegDesc* desc, SegRays* rays, double* midray, SegPlane* planes,
-                   float* view_xb, cudaStream_t st)
+                   SegV32* v32, float* view_xb, cudaStream_t st)
 {
     if (S == 0) return 0;
     k0_prep_kernel<<<(S + 255) / 256, 256, 0, st>>>(segs, seg_view, views, S, (double)max_image_width, desc,
-                                                     rays, midray, planes, view_xb);
+                                                     rays, midray, planes, v32, view_xb);
     return 1;
 }
 

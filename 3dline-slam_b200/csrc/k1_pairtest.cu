@@ -79,7 +79,8 @@ __global__ void __launch_bounds__(K1_ROWS) k1_pairtest_kernel(const PairDev* __r
                                                               const SegDesc* __restrict__ desc,
                                                               const float* __restrict__ view_xb,
                                                               uint32_t* __restrict__ mask,
-                                                              uint32_t* __restrict__ cand_cnt, float thr,
+                                                              uint32_t* __restrict__ cand_cnt,
+                                                              RowEpi32* __restrict__ row_epi, float thr,
                                                               int filter_mode)
 {
     __shared__ __align__(128) float4 tile[2][K1_TILE * 2];
@@ -111,6 +112,7 @@ __global__ void __launch_bounds__(K1_ROWS) k1_pairtest_kernel(const PairDev* __r
     e.degenerate = false;
     e.A1 = e.B1 = e.C1 = e.A2 = e.B2 = e.C2 = 0.0f;
     e.cN = 0.0f;
+    float nmin = 0.0f;
     if (row_ok) {
         const float4 sg = segs[P.src_off + r];
         const double p1x = sg.x, p1y = sg.y, p2x = sg.z, p2y = sg.w;
@@ -127,6 +129,13 @@ __global__ void __launch_bounds__(K1_ROWS) k1_pairtest_kernel(const PairDev* __r
         e.cN = u8 * (xb + fmaxf(fabsf(e.C1), fabsf(e.C2)));
         const float chk = e.A1 + e.B1 + e.C1 + e.A2 + e.B2 + e.C2;
         e.degenerate = !(fabsf(chk) < 3.0e38f);  // NaN or Inf anywhere
+        nmin = (float)fmin(n1, n2);
+        // K2's FP32 ranking re-uses the row's lines; a degenerate row carries NaN bounds (nothing is certified)
+        RowEpi32 re;
+        re.A1 = e.A1; re.B1 = e.B1; re.C1 = e.C1; re.A2 = e.A2; re.B2 = e.B2; re.C2 = e.C2;
+        re.cN = e.degenerate ? __int_as_float(0x7fc00000) : e.cN;
+        re.nmin = nmin;
+        row_epi[P.row_base - P.batch_row0 + r] = re;
     }
     const float k2thr = 2.0f * (1.0f + thr);
     const bool all_pass = (filter_mode != 0) | e.degenerate;
@@ -178,12 +187,12 @@ __global__ void __launch_bounds__(K1_ROWS) k1_pairtest_kernel(const PairDev* __r
 }
 
 int launch_k1_pairtest(const PairDev* pairs, const K1Cta* ctas, uint32_t n_ctas, const float4* segs,
-                       const SegDesc* desc, const float* view_xb, uint32_t* mask, uint32_t* cand_cnt, float thr,
-                       int filter_mode, cudaStream_t st)
+                       const SegDesc* desc, const float* view_xb, uint32_t* mask, uint32_t* cand_cnt,
+                       RowEpi32* row_epi, float thr, int filter_mode, cudaStream_t st)
 {
     if (n_ctas == 0) return 0;
-    k1_pairtest_kernel<<<n_ctas, K1_ROWS, 0, st>>>(pairs, ctas, segs, desc, view_xb, mask, cand_cnt, thr,
-                                                    filter_mode);
+    k1_pairtest_kernel<<<n_ctas, K1_ROWS, 0, st>>>(pairs, ctas, segs, desc, view_xb, mask, cand_cnt, row_epi,
+                                                    thr, filter_mode);
     return 1;
 }
 

@@ -195,6 +195,7 @@ int stream_match_images(l3d_ctx* ctx, const l3d_params* params)
     CK(ensure_roomy(ctx->d_rays, S, kSegFloor));
     CK(ensure_roomy(ctx->d_midray, 3 * (size_t)S, 3 * kSegFloor));
     CK(ensure_roomy(ctx->d_planes, S, kSegFloor));
+    CK(ensure_roomy(ctx->d_v32, S, kSegFloor));
     CK(ensure_roomy(ctx->d_view_xb, V, kViewFloor));
     CK(ensure_roomy(ctx->d_views, V, kViewFloor));
     CK(ensure_roomy(ctx->d_entries, (size_t)S + 1, kSegFloor));

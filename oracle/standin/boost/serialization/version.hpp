@@ -1,0 +1,1 @@
+#include "l3d_standin_boost.h"
