@@ -587,6 +587,7 @@ int run_stage12_batches(l3d_ctx* ctx)
         CK(grow(ctx->d_ncont, (size_t)max_rows + 1));
         CK(grow(ctx->d_fb_rows, (size_t)max_rows + 1));
         CK(grow(ctx->d_row_pair, (size_t)max_rows + 1));
+        CK(grow(ctx->d_row_T, (size_t)max_rows + 1));
         CK(ctx->d_k2ctr.ensure(8));
         if (!ctx->n_sm) {
             cudaDeviceProp prop;
@@ -630,7 +631,7 @@ int run_stage12_batches(l3d_ctx* ctx)
             launch_k2_exact(ctx->d_pairs.p, ctx->d_ctas.p + b.cta0, b.n_ctas, b.n_rows, n_cand, ctx->d_segs.p,
                             ctx->d_rays.p, ctx->d_midray.p, ctx->d_planes.p, ctx->d_v32.p, ctx->d_desc.p, ctx->d_row_epi.p,
                             ctx->d_views.p, ctx->d_mask.p, ctx->d_cand_off.p, ctx->d_heap.p, ctx->d_cand_rec.p,
-                            ctx->d_fin_rec.p, ctx->d_fin_cnt.p, ctx->d_ncont.p, ctx->d_k2ctr.p, ctx->d_fb_rows.p, ctx->d_row_pair.p,
+                            ctx->d_fin_rec.p, ctx->d_fin_cnt.p, ctx->d_ncont.p, ctx->d_k2ctr.p, ctx->d_fb_rows.p, ctx->d_row_pair.p, ctx->d_row_T.p,
                             ctx->epi_overlap, ctx->prm.knn, ctx->prm.max_image_width, ctx->raw_mode ? 0 : 1, ctx->n_sm,
                             &uses_ncont, st);
         if (getenv("L3D_K2_DEBUG")) {  // contenders / rows handed to the row kernel, per batch

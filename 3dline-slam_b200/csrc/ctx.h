@@ -23,7 +23,7 @@ int k1_rows_per_cta();
 int launch_k2_exact(const PairDev*, const K1Cta*, uint32_t, uint32_t, uint32_t, const float4*, const SegRays*,
                     const double*, const SegPlane*, const SegV32*, const SegDesc*, const RowEpi32*, const ViewDev*,
                     const uint32_t*, const uint32_t*, unsigned long long*, FwdRec*, FwdRec*, uint32_t*, uint32_t*, uint32_t*,
-                    uint2*, uint32_t*, float, int, int, int, int, int*, cudaStream_t);
+                    uint2*, uint32_t*, float*, float, int, int, int, int, int*, cudaStream_t);
 int launch_k2_compact(const uint32_t*, const uint32_t*, const uint32_t*, uint32_t, const FwdRec*, FwdRec*, uint32_t*,
                       uint32_t, const uint32_t*, cudaStream_t);
 int launch_k3_score(uint32_t, const uint32_t*, ListRec*, const ListGeo*, float, float, void*, cudaStream_t);
@@ -254,6 +254,7 @@ struct l3d_ctx {
     DevBuf<uint32_t> d_ncont, d_k2ctr;  // K2: contenders per batch row; {work items, fallback rows}
     DevBuf<uint2> d_fb_rows;       // K2: rows handed to the literal row kernel
     DevBuf<uint32_t> d_row_pair;   // K2: pair of every batch row
+    DevBuf<float> d_row_T;         // K2: kNN-th largest certain lower bound of every batch row
     int n_sm = 0;
     DevBuf<float> d_view_xb;
     DevBuf<ViewDev> d_views;

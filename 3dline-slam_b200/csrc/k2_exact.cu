@@ -507,7 +507,7 @@ __global__ void __launch_bounds__(K2_WARPS * 32) k2_row_kernel(
 // on the contenders (a pruned candidate cannot tie with a popped one) and sent to the row kernel.  Error
 // bounds are stated next to the code.
 // ------------------------------------------------------------------------------------------
-static constexpr int K2_MAXC = 48;      // contenders of one row the rank kernel holds per thread
+static constexpr int K2_MAXC = 64;      // queued survivors of one row the rank kernel holds per thread
 static constexpr int K2_TOPK = 16;      // largest kNN the select kernel prunes for (register-resident)
 #define K2_ROW_FALLBACK 0xffffffffu
 
@@ -517,9 +517,6 @@ __device__ __forceinline__ float rcp_approx_ftz(float x)
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
-
-// sign class of an FP32 value whose absolute error is below eps / 2: +1, -1 or 0 (unknown)
-__device__ __forceinline__ int sign_class(float v, float eps) { return v > eps ? 1 : (v < -eps ? -1 : 0); }
 
 // exclusive prefix of v over the warp and the warp total
 __device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, uint32_t lane, uint32_t& total)
@@ -540,7 +537,7 @@ struct RowF32 {
     float rp1x, rp1y, rp1z, rp2x, rp2y, rp2z;   // endpoint rays
     float nBx, nBy, nBz;                        // normal of the row's own plane
     float Csx, Csy, Csz, CsL1;                  // source centre
-    int clsB;                                   // exact sign of the row's plane against the target centre (0: unknown)
+    float sB;                                   // exact sign of the row's plane against the target centre: +-1, 0 = unknown
 };
 
 // One K1 candidate (row constants R, target tables T / d0 / d1) in FP32:
@@ -561,11 +558,13 @@ __device__ __forceinline__ bool certify_candidate(const RowF32& R, const SegV32&
     const float num = T.cn - fmaf(T.nx, R.Csx, fmaf(T.ny, R.Csy, T.nz * R.Csz));
     const float eps_n = fmaf(16.0f * u, fabsf(T.cn) + R.CsL1, 1e-9f);
     const float eps_a = 1e-6f;
-    const int cn_ = sign_class(num, eps_n), clsB = R.clsB;
-    const int ca1 = sign_class(a1, eps_a), ca2 = sign_class(a2, eps_a);
-    const int cb1 = sign_class(b1, eps_a), cb2 = sign_class(b2, eps_a);
-    const bool vpos = (cn_ != 0) & (ca1 == cn_) & (ca2 == cn_) & (clsB != 0) & (cb1 == clsB) & (cb2 == clsB);
-    const bool vneg = ((cn_ != 0) & ((ca1 == -cn_) | (ca2 == -cn_))) | ((clsB != 0) & ((cb1 == -clsB) | (cb2 == -clsB)));
+    // with sn = sign(num), sB = sign(numB) (0 when unknown): a quotient is certainly positive iff the signed
+    // denominator exceeds eps, certainly negative iff it is below -eps
+    const float sn = fabsf(num) > eps_n ? copysignf(1.0f, num) : 0.0f;
+    const float sB = R.sB;
+    const float q1 = a1 * sn, q2 = a2 * sn, q3 = b1 * sB, q4 = b2 * sB;
+    const bool vpos = fminf(fminf(q1, q2), fminf(q3, q4)) > eps_a;
+    const bool vneg = fminf(fminf(q1, q2), fminf(q3, q4)) < -eps_a;
     // ---- overlap bracket (k1_pairtest.cu) ----
     const RowEpi32& e = R.e;
     const float cD = 32.0f * u;
@@ -622,30 +621,36 @@ __device__ __forceinline__ bool certify_candidate(const RowF32& R, const SegV32&
 // slots (row, target | unknown-depth flag) and (U); a second pass drops the ones below the final T, packs the
 // contenders to the front of the row and queues them for the exact kernel. ----
 static constexpr int K2F_TCH = 1024;
+static constexpr int K2F_Q = 64;  // per-lane queue of chunk-local candidates (flushed when a lane passes 32)
 struct K2FSmem {
     SegV32 v32[K2F_TCH];
     SegDesc desc[K2F_TCH];
+    unsigned short q[K2F_Q][K2_ROWS];  // [slot][thread]: conflict-free for a lane walking its own queue
     uint64_t bar;
 };
 
+// KT: size of the insertion network (the smallest of 4 / 8 / 10 / 12 / 16 that holds kNN; 0 = no pruning)
+template <int KT>
 __global__ void __launch_bounds__(K2_ROWS, 2) k2_front_kernel(
     const PairDev* __restrict__ pairs, const K1Cta* __restrict__ ctas, const uint32_t* __restrict__ mask,
     const uint32_t* __restrict__ cand_off, const SegV32* __restrict__ v32, const SegDesc* __restrict__ desc,
     const SegPlane* __restrict__ planes, const ViewDev* __restrict__ views, const RowEpi32* __restrict__ row_epi,
     float thr, int knn, uint2* __restrict__ cand_rc, float* __restrict__ cand_u, uint32_t* __restrict__ ncont,
-    uint32_t* __restrict__ row_pair, uint32_t* __restrict__ work, uint32_t* __restrict__ ctr)
+    uint32_t* __restrict__ row_pair, float* __restrict__ row_T, uint32_t* __restrict__ work, uint32_t* __restrict__ ctr)
 {
     extern __shared__ __align__(128) unsigned char k2f_raw[];
     K2FSmem& S = *reinterpret_cast<K2FSmem*>(k2f_raw);
     const K1Cta cta = ctas[blockIdx.x];
     const PairDev& P = pairs[cta.pair];
     const uint32_t n_src = P.n_src, n_tgt = P.n_tgt, words = P.words;
-    const uint32_t r = cta.tile * K2_ROWS + threadIdx.x;
-    const uint32_t lane = threadIdx.x & 31;
-    const float ninf = __int_as_float(0xff800000);
-    const bool prune = knn > 0 && knn <= K2_TOPK;
+    const uint32_t tid = threadIdx.x;
+    const uint32_t r = cta.tile * K2_ROWS + tid;
+    const uint32_t lane = tid & 31;
+    const float ninf = __int_as_float(0xff800000), pinf = __int_as_float(0x7f800000);
+    constexpr bool prune = KT > 0;
+    constexpr int KN = KT > 0 ? KT : 1;
 
-    if (threadIdx.x == 0) {
+    if (tid == 0) {
         mbar_init(&S.bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -654,6 +659,7 @@ __global__ void __launch_bounds__(K2_ROWS, 2) k2_front_kernel(
     // ---- row set-up ----
     uint32_t lrow = 0, base = 0, ncand = 0;
     RowF32 R;
+    memset(&R, 0, sizeof(R));
     if (r < n_src) {
         lrow = P.row_base - P.batch_row0 + r;
         base = cand_off[lrow];
@@ -671,142 +677,192 @@ __global__ void __launch_bounds__(K2_ROWS, 2) k2_front_kernel(
         R.nBx = sv.nx; R.nBy = sv.ny; R.nBz = sv.nz;
         R.Csx = (float)vs.C[0]; R.Csy = (float)vs.C[1]; R.Csz = (float)vs.C[2];
         R.CsL1 = fabsf(R.Csx) + fabsf(R.Csy) + fabsf(R.Csz);
-        R.clsB = numB > 1e-9 ? 1 : (numB < -1e-9 ? -1 : 0);
+        R.sB = numB > 1e-9 ? 1.0f : (numB < -1e-9 ? -1.0f : 0.0f);
         row_pair[lrow] = cta.pair;
     }
-    const uint32_t* __restrict__ mrow = mask + P.mask_base + r;
+    const uint32_t* __restrict__ mrow = mask + P.mask_base + (r < n_src ? r : 0u);
 
-    float top[K2_TOPK];
+    // sorted insertion network in registers; the first KT - kNN entries are +inf, so its last entry is the
+    // kNN-th largest certain lower bound seen so far
+    float top[KN];
 #pragma unroll
-    for (int q = 0; q < K2_TOPK; ++q) top[q] = ninf;
-    float T = ninf;       // the kNN-th largest certain lower bound so far
+    for (int q = 0; q < KN; ++q) top[q] = (q < KN - knn) ? pinf : ninf;
+    float T = ninf;       // = top[KT - 1]
     uint32_t ns = 0;      // survivors written to the row's slots
+    uint32_t nq = 0;      // candidates waiting in this lane's queue
+
+    // Evaluate the queued candidates of all 32 lanes in lockstep: iteration k takes the k-th entry of every lane's
+    // queue (lanes with shorter queues idle).  No lane runs ahead, so the warp never splits into single-lane paths
+    // (the first version let every lane walk its own bits with early `continue`s: 13 active lanes per instruction).
+    auto flush = [&](uint32_t cb) {
+        uint32_t kmax = nq;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, d));
+        for (uint32_t k = 0; k < kmax; ++k) {
+            const bool act = k < nq;
+            const uint32_t cl = act ? (uint32_t)S.q[k][tid] : 0u;
+            const float4* tp = reinterpret_cast<const float4*>(&S.v32[cl]);
+            const float4 t0 = tp[0], t1 = tp[1], t2 = tp[2];
+            SegV32 Tt;
+            Tt.nx = t0.x; Tt.ny = t0.y; Tt.nz = t0.z; Tt.cn = t0.w;
+            Tt.r1x = t1.x; Tt.r1y = t1.y; Tt.r1z = t1.z; Tt.r2x = t1.w;
+            Tt.r2y = t2.x; Tt.r2z = t2.y;
+            const float4* dp = reinterpret_cast<const float4*>(&S.desc[cl]);
+            const float4 d0 = dp[0], d1 = dp[1];
+            float U, Lb;
+            bool unk;
+            bool keep = certify_candidate(R, Tt, d0, d1, thr, U, Lb, unk) & act;
+            keep &= !(U < T);  // kNN certain matches already lie strictly above it
+            if (prune && keep && Lb > T) {  // a certain match that raises T
+                float v = Lb;
+#pragma unroll
+                for (int q = 0; q < KN; ++q) {
+                    const float hi = fmaxf(top[q], v);
+                    v = fminf(top[q], v);
+                    top[q] = hi;
+                }
+                T = top[KN - 1];
+            }
+            if (keep) {
+                cand_rc[base + ns] = make_uint2(lrow, (cb + cl) | (unk ? 0x80000000u : 0u));
+                cand_u[base + ns] = U;
+                ++ns;
+            }
+        }
+        nq = 0;
+        __syncwarp();
+    };
 
     uint32_t chunk_no = 0;
     for (uint32_t cb = 0; cb < n_tgt; cb += K2F_TCH, ++chunk_no) {
         const uint32_t tcnt = min((uint32_t)K2F_TCH, n_tgt - cb);
-        if (threadIdx.x == 0) {
+        if (tid == 0) {
             mbar_expect_tx(&S.bar, tcnt * (uint32_t)(sizeof(SegV32) + sizeof(SegDesc)));
             tma_load_1d(S.v32, v32 + P.tgt_off + cb, tcnt * (uint32_t)sizeof(SegV32), &S.bar);
             tma_load_1d(S.desc, desc + P.tgt_off + cb, tcnt * (uint32_t)sizeof(SegDesc), &S.bar);
         }
         mbar_wait(&S.bar, chunk_no & 1u);
 
-        if (ncand) {
-            // per-lane iterator over the set bits of this chunk's mask words
-            const uint32_t w_end = min(words, (cb + K2F_TCH) >> 5);
-            uint32_t w = cb >> 5;
-            uint32_t bits = w < w_end ? mrow[(size_t)w * n_src] : 0u;
-            while (true) {
-                while (bits == 0u && ++w < w_end) bits = mrow[(size_t)w * n_src];
-                if (bits == 0u) break;
+        // the chunk's mask words, the same word index on every lane (coalesced loads, ascending target order)
+        const uint32_t w0 = cb >> 5, w_end = min(words, (cb + K2F_TCH) >> 5);
+        for (uint32_t w = w0; w < w_end; ++w) {
+            uint32_t bits = ncand ? mrow[(size_t)w * n_src] : 0u;
+            const uint32_t lbase = (w - w0) << 5;
+            while (bits) {
                 const uint32_t j = __ffs(bits) - 1;
                 bits &= bits - 1;
-                const uint32_t cl = (w << 5) + j - cb;  // chunk-local target
-                const float4* tp = reinterpret_cast<const float4*>(&S.v32[cl]);
-                const float4 t0 = tp[0], t1 = tp[1], t2 = tp[2];
-                SegV32 Tt;
-                Tt.nx = t0.x; Tt.ny = t0.y; Tt.nz = t0.z; Tt.cn = t0.w;
-                Tt.r1x = t1.x; Tt.r1y = t1.y; Tt.r1z = t1.z; Tt.r2x = t1.w;
-                Tt.r2y = t2.x; Tt.r2z = t2.y;
-                const float4* dp = reinterpret_cast<const float4*>(&S.desc[cl]);
-                const float4 d0 = dp[0], d1 = dp[1];
-                float U, Lb;
-                bool unk;
-                if (!certify_candidate(R, Tt, d0, d1, thr, U, Lb, unk)) continue;
-                if (U < T) continue;  // kNN certain matches already lie strictly above it
-                if (prune && Lb > T) {  // a certain match that raises T
-                    float v = Lb;
-#pragma unroll
-                    for (int q = 0; q < K2_TOPK; ++q) {
-                        const float hi = fmaxf(top[q], v);
-                        v = fminf(top[q], v);
-                        top[q] = hi;
-                    }
-#pragma unroll
-                    for (int q = 0; q < K2_TOPK; ++q)
-                        if (q == knn - 1) T = top[q];
-                }
-                cand_rc[base + ns] = make_uint2(lrow, (cb + cl) | (unk ? 0x80000000u : 0u));
-                cand_u[base + ns] = U;
-                ++ns;
+                S.q[nq++][tid] = (unsigned short)(lbase + j);
             }
+            if (__any_sync(0xffffffffu, nq > 32u)) flush(cb);
         }
+        flush(cb);
         __syncthreads();  // everyone is done with the staged tables before the next chunk overwrites them
     }
 
-    // ---- contenders: the survivors not below the final T, packed to the front in ascending target order ----
-    uint32_t nc = 0;
-    if (ncand) {
-        for (uint32_t i = 0; i < ns; ++i) {
-            if (cand_u[base + i] < T) continue;
-            if (nc != i) cand_rc[base + nc] = cand_rc[base + i];
-            ++nc;
-        }
-        ncont[lrow] = nc;
-    } else if (r < n_src) {
-        ncont[lrow] = 0u;
+    // ---- every survivor is queued; the exact kernel skips the ones below the row's FINAL T (the running T only
+    // grew), so no second pass over the row is needed here ----
+    if (r < n_src) {
+        ncont[lrow] = ns;
+        if (ncand) row_T[lrow] = T;
     }
     uint32_t total = 0;
-    const uint32_t ex = warp_excl_scan(nc, lane, total);
-    uint32_t w0 = 0;
-    if (lane == 0 && total) w0 = atomicAdd(&ctr[0], total);
-    w0 = __shfl_sync(0xffffffffu, w0, 0) + ex;
-    for (uint32_t jq = 0; jq < nc; ++jq) work[w0 + jq] = base + jq;
+    const uint32_t ex = warp_excl_scan(ns, lane, total);
+    uint32_t wq = 0;
+    if (lane == 0 && total) wq = atomicAdd(&ctr[0], total);
+    wq = __shfl_sync(0xffffffffu, wq, 0) + ex;
+    for (uint32_t jq = 0; jq < ns; ++jq) work[wq + jq] = base + jq;
 }
 
-// ---- K2b: the reference's double sequence for one contender per thread ----
+// ---- K2b: the reference's double sequence for one contender per thread.  The queue holds every survivor of the
+// front kernel; the ones below their row's FINAL T (kNN certain matches lie strictly above them) are dropped
+// here, and the rest are re-packed through a small per-warp ring so that the double-precision work runs on
+// full warps ----
+__device__ __forceinline__ unsigned long long exact_contender(
+    const PairDev* __restrict__ pairs, const float4* __restrict__ segs, const SegRays* __restrict__ rays,
+    const SegPlane* __restrict__ planes, const ViewDev* __restrict__ views, const uint32_t* __restrict__ row_pair,
+    const uint2 rc, float thr, double W)
+{
+    const PairDev& P = pairs[row_pair[rc.x]];
+    const uint32_t r = rc.x - (P.row_base - P.batch_row0), c = rc.y & 0x7fffffffu;
+    if (rc.y >> 31) {
+        // depth signs the FP32 test could not certify: the exact test of k2_row_kernel's phase V
+        const D3 Cs = ld3(views[P.src_view].C), Ct = ld3(views[P.tgt_view].C);
+        const SegRays sr = rays[P.src_off + r];
+        const SegPlane plB = planes[P.src_off + r];
+        const D3 nB = ld3(plB.n);
+        const double numB = ds(plB.cn, dot3(nB, Ct));
+        const SegRays tr = rays[P.tgt_off + c];
+        const SegPlane plA = planes[P.tgt_off + c];
+        const D3 nA = ld3(plA.n);
+        const double a1 = dot3(ld3(sr.r1), nA), a2 = dot3(ld3(sr.r2), nA);
+        const double b1 = dot3(ld3(tr.r1), nB), b2 = dot3(ld3(tr.r2), nB);
+        if (fabs(a1) < L3D_EPS || fabs(a2) < L3D_EPS || fabs(b1) < L3D_EPS || fabs(b2) < L3D_EPS) return ~0ull;
+        const double num = ds(plA.cn, dot3(nA, Cs));
+        if (!(depth_positive(num, a1) && depth_positive(num, a2) && depth_positive(numB, b1) && depth_positive(numB, b2)))
+            return ~0ull;
+    }
+    // src/line3D.cc:1113-1158
+    const float4 sg = segs[P.src_off + r];
+    const D3 p1 = d3((double)sg.x, (double)sg.y, 1.0), p2 = d3((double)sg.z, (double)sg.w, 1.0);
+    const D3 e1 = mul33(P.F, p1), e2 = mul33(P.F, p2);
+    const float4 tg = segs[P.tgt_off + c];
+    const D3 q1 = d3((double)tg.x, (double)tg.y, 1.0), q2 = d3((double)tg.z, (double)tg.w, 1.0);
+    const D3 l2 = cross3(q1, q2);
+    const D3 a = cross3(l2, e1), b = cross3(l2, e2);
+    if (fabs(a.z) > L3D_EPS && fabs(b.z) > L3D_EPS) {
+        const double ax = dd(a.x, a.z), ay = dd(a.y, a.z), bx = dd(b.x, b.z), by = dd(b.y, b.z);
+        if (!(ax < 0 || ax > W || ay < 0 || ay > W || bx < 0 || bx > W || by < 0 || by > W)) {
+            const float score = mutual_overlap_xy(ax, ay, bx, by, q1.x, q1.y, q2.x, q2.y);
+            if (score > thr) return ((unsigned long long)__float_as_uint(score) << 32) | c;
+        }
+    }
+    return ~0ull;  // not a match
+}
+
 __global__ void __launch_bounds__(256) k2b_exact_kernel(
     const PairDev* __restrict__ pairs, const float4* __restrict__ segs, const SegRays* __restrict__ rays,
     const SegPlane* __restrict__ planes, const ViewDev* __restrict__ views, const uint32_t* __restrict__ work,
-    const uint2* __restrict__ cand_rc, const uint32_t* __restrict__ row_pair, const uint32_t* __restrict__ ctr,
-    unsigned long long* __restrict__ stage, float thr, double W)
+    const uint2* __restrict__ cand_rc, const float* __restrict__ cand_u, const uint32_t* __restrict__ row_pair,
+    const float* __restrict__ row_T, const uint32_t* __restrict__ ctr, unsigned long long* __restrict__ stage, float thr,
+    double W)
 {
+    __shared__ uint32_t ring[8][64];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    uint32_t* pend = ring[warp];
+    uint32_t np = 0;  // pending slots of this warp (warp-uniform)
     const uint32_t n_work = ctr[0];
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_work; i += gridDim.x * blockDim.x) {
-        const uint32_t slot = work[i];
-        const uint2 rc = cand_rc[slot];
-        const PairDev& P = pairs[row_pair[rc.x]];
-        const uint32_t r = rc.x - (P.row_base - P.batch_row0), c = rc.y & 0x7fffffffu;
-        bool valid = true;
-        if (rc.y >> 31) {
-            // depth signs the FP32 test could not certify: the exact test of k2_row_kernel's phase V
-            const D3 Cs = ld3(views[P.src_view].C), Ct = ld3(views[P.tgt_view].C);
-            const SegRays sr = rays[P.src_off + r];
-            const SegPlane plB = planes[P.src_off + r];
-            const D3 nB = ld3(plB.n);
-            const double numB = ds(plB.cn, dot3(nB, Ct));
-            const SegRays tr = rays[P.tgt_off + c];
-            const SegPlane plA = planes[P.tgt_off + c];
-            const D3 nA = ld3(plA.n);
-            const double a1 = dot3(ld3(sr.r1), nA), a2 = dot3(ld3(sr.r2), nA);
-            const double b1 = dot3(ld3(tr.r1), nB), b2 = dot3(ld3(tr.r2), nB);
-            valid = false;
-            if (!(fabs(a1) < L3D_EPS || fabs(a2) < L3D_EPS || fabs(b1) < L3D_EPS || fabs(b2) < L3D_EPS)) {
-                const double num = ds(plA.cn, dot3(nA, Cs));
-                valid = depth_positive(num, a1) && depth_positive(num, a2) && depth_positive(numB, b1) &&
-                        depth_positive(numB, b2);
-            }
+    const uint32_t stride = gridDim.x * blockDim.x;
+    // warp-uniform trip count: every lane of a warp runs the same number of iterations
+    const uint32_t first = blockIdx.x * blockDim.x + warp * 32;
+    for (uint32_t i0 = first; i0 < n_work; i0 += stride) {
+        const uint32_t i = i0 + lane;
+        bool want = false;
+        uint32_t slot = 0;
+        if (i < n_work) {
+            slot = work[i];
+            want = !(cand_u[slot] < row_T[cand_rc[slot].x]);
+            if (!want) stage[slot] = ~0ull;  // never popped
         }
-        unsigned long long key = ~0ull;  // not a match
-        if (valid) {
-            // src/line3D.cc:1113-1158
-            const float4 sg = segs[P.src_off + r];
-            const D3 p1 = d3((double)sg.x, (double)sg.y, 1.0), p2 = d3((double)sg.z, (double)sg.w, 1.0);
-            const D3 e1 = mul33(P.F, p1), e2 = mul33(P.F, p2);
-            const float4 tg = segs[P.tgt_off + c];
-            const D3 q1 = d3((double)tg.x, (double)tg.y, 1.0), q2 = d3((double)tg.z, (double)tg.w, 1.0);
-            const D3 l2 = cross3(q1, q2);
-            const D3 a = cross3(l2, e1), b = cross3(l2, e2);
-            if (fabs(a.z) > L3D_EPS && fabs(b.z) > L3D_EPS) {
-                const double ax = dd(a.x, a.z), ay = dd(a.y, a.z), bx = dd(b.x, b.z), by = dd(b.y, b.z);
-                if (!(ax < 0 || ax > W || ay < 0 || ay > W || bx < 0 || bx > W || by < 0 || by > W)) {
-                    const float score = mutual_overlap_xy(ax, ay, bx, by, q1.x, q1.y, q2.x, q2.y);
-                    if (score > thr) key = ((unsigned long long)__float_as_uint(score) << 32) | c;
-                }
-            }
+        const uint32_t bal = __ballot_sync(0xffffffffu, want);
+        if (want) pend[np + __popc(bal & lt_mask)] = slot;
+        np += __popc(bal);
+        __syncwarp();
+        if (np >= 32u) {
+            const uint32_t s = pend[lane];
+            stage[s] = exact_contender(pairs, segs, rays, planes, views, row_pair, cand_rc[s], thr, W);
+            __syncwarp();
+            const uint32_t rest = np - 32u;
+            const uint32_t mv = lane < rest ? pend[32 + lane] : 0u;
+            __syncwarp();
+            if (lane < rest) pend[lane] = mv;
+            np = rest;
+            __syncwarp();
         }
-        stage[slot] = key;
+    }
+    if (lane < np) {
+        const uint32_t s = pend[lane];
+        stage[s] = exact_contender(pairs, segs, rays, planes, views, row_pair, cand_rc[s], thr, W);
     }
 }
 
@@ -976,7 +1032,7 @@ int launch_k2_exact(const PairDev* pairs, const K1Cta* ctas, uint32_t n_ctas, ui
                     const float4* segs, const SegRays* rays, const double* midray, const SegPlane* planes,
                     const SegV32* v32, const SegDesc* desc, const RowEpi32* row_epi,
                     const ViewDev* views, const uint32_t* mask, const uint32_t* cand_off, unsigned long long* heap, FwdRec* cand_rec,
-                    FwdRec* fin_rec, uint32_t* fin_cnt, uint32_t* ncont, uint32_t* ctr, uint2* fb_rows, uint32_t* row_pair, float thr, int knn,
+                    FwdRec* fin_rec, uint32_t* fin_cnt, uint32_t* ncont, uint32_t* ctr, uint2* fb_rows, uint32_t* row_pair, float* row_T, float thr, int knn,
                     int max_image_width, int apply_orient, int n_sm, int* uses_ncont, cudaStream_t st)
 {
     *uses_ncont = 0;
@@ -999,12 +1055,21 @@ int launch_k2_exact(const PairDev* pairs, const K1Cta* ctas, uint32_t n_ctas, ui
     unsigned long long* pop_key = reinterpret_cast<unsigned long long*>(scratch + n8);
     uint32_t* work = reinterpret_cast<uint32_t*>(scratch + 2 * n8);
     float* cand_u = reinterpret_cast<float*>(scratch + 2 * n8 + n8 / 2);
-    // per device and cheap: set on every launch (a process may hold contexts on several GPUs)
-    cudaFuncSetAttribute(k2_front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K2FSmem));
-    k2_front_kernel<<<n_ctas, K2_ROWS, sizeof(K2FSmem), st>>>(pairs, ctas, mask, cand_off, v32, desc, planes, views, row_epi, thr,
-                                                               knn, cand_rc, cand_u, ncont, row_pair, work, ctr);
+    // the front kernel with the smallest insertion network that holds kNN (0: kNN <= 0 or > 16, no pruning)
+    auto front = [&](auto kernel) {
+        // per device and cheap: set on every launch (a process may hold contexts on several GPUs)
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K2FSmem));
+        kernel<<<n_ctas, K2_ROWS, sizeof(K2FSmem), st>>>(pairs, ctas, mask, cand_off, v32, desc, planes, views, row_epi, thr, knn,
+                                                          cand_rc, cand_u, ncont, row_pair, row_T, work, ctr);
+    };
+    if (knn <= 0 || knn > K2_TOPK) front(k2_front_kernel<0>);
+    else if (knn <= 4) front(k2_front_kernel<4>);
+    else if (knn <= 8) front(k2_front_kernel<8>);
+    else if (knn <= 10) front(k2_front_kernel<10>);
+    else if (knn <= 12) front(k2_front_kernel<12>);
+    else front(k2_front_kernel<16>);
     // the number of contenders is known on the device only: a grid that fills the machine, striding over the queue
-    k2b_exact_kernel<<<n_sm * 8, 256, 0, st>>>(pairs, segs, rays, planes, views, work, cand_rc, row_pair, ctr, heap, thr,
+    k2b_exact_kernel<<<n_sm * 8, 256, 0, st>>>(pairs, segs, rays, planes, views, work, cand_rc, cand_u, row_pair, row_T, ctr, heap, thr,
                                                (double)max_image_width);
     k2_rank_kernel<<<n_ctas, K2_ROWS, 0, st>>>(pairs, ctas, cand_off, ncont, heap, pop_key, fin_cnt, knn, work, ctr, fb_rows);
     k2_finish_kernel<<<n_sm * 8, 256, 0, st>>>(pairs, rays, midray, planes, views, work, cand_rc, row_pair, pop_key, ctr,

@@ -63,7 +63,7 @@ inline double r_acos(double x) { return orc_acos(x); }
 inline double r_acos(int x) { return orc_acos((double)x); }
 inline double r_sin(double x) { return orc_sin(x); }
 }  // namespace l3d_ref
-#define expf(x) l3d_ref::r_expf(x)
-#define acos(x) l3d_ref::r_acos(x)
-#define sin(x) l3d_ref::r_sin(x)
+#define expf(x) ::l3d_ref::r_expf(x)
+#define acos(x) ::l3d_ref::r_acos(x)
+#define sin(x) ::l3d_ref::r_sin(x)
 #endif
