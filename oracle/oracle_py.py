@@ -33,9 +33,14 @@ REF_ROOT = "/root/reference"
 REF_CLUSTERING = os.path.join(_HERE, "_ref", "libref_clustering.so")
 
 
+REF_LINE3D = {"det": os.path.join(_HERE, "_ref", "libref_line3d_det.so"),
+              "libm": os.path.join(_HERE, "_ref", "libref_line3d_libm.so")}
+
+
 def build_ref() -> bool:
-    """oracle/_ref: the reference's own clustering compiled from its sources (only where /root/reference
-    exists, i.e. in the authoring container; the GPU box uses the prebuilt file that travelled with the repo)."""
+    """oracle/_ref: the reference's own sources compiled in place (only where /root/reference exists, i.e. in
+    the authoring container; the GPU box uses the prebuilt files that travelled with the repo): the graph
+    clustering, and the Line3D++ path itself (src/line3D.cc + src/view.cc against oracle/standin/)."""
     if os.path.exists(os.path.join(REF_ROOT, "src", "clustering.cc")):
         subprocess.check_call(["make", "-C", _HERE, "-s", "ref"])
     return os.path.exists(REF_CLUSTERING)
@@ -52,6 +57,74 @@ def ref_cluster(ij, w, n, c=3.0):
     L.ref_cluster.restype = C.c_int
     L.ref_cluster(_p(ij), _p(w), len(w), int(n), C.c_float(c), _p(out))
     return out[:n]
+
+
+def _bind_common(L):
+    """argtypes of the entry points the restatement and the compiled reference share."""
+    L.orc_create.restype = C.c_void_p
+    L.orc_create.argtypes = [C.c_int, C.c_int]
+    L.orc_destroy.argtypes = [C.c_void_p]
+    L.orc_set_threads.argtypes = [C.c_int]
+    L.orc_max_threads.restype = C.c_int
+    L.orc_set_snapshot.argtypes = [C.c_void_p, C.c_int]
+    L.orc_add_image.restype = C.c_int
+    L.orc_add_image.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint,
+                                C.c_uint, C.c_float, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    L.orc_update_image.restype = C.c_int
+    L.orc_update_image.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_int]
+    L.orc_delete_image.restype = C.c_int
+    L.orc_delete_image.argtypes = [C.c_void_p, C.c_uint32]
+    L.orc_begin_cycle.argtypes = [C.c_void_p]
+    L.orc_match_images.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_uint, C.c_float, C.c_int, C.c_float]
+    L.orc_reconstruct.argtypes = [C.c_void_p]
+    L.orc_reconstruct_collin.argtypes = [C.c_void_p, C.c_float]
+    L.orc_num_pairs.restype = C.c_int
+    L.orc_num_pairs.argtypes = [C.c_void_p]
+    L.orc_get_pairs.argtypes = [C.c_void_p, C.c_void_p]
+    L.orc_pair_tests.restype = C.c_uint64
+    L.orc_pair_tests.argtypes = [C.c_void_p]
+    L.orc_list_total.restype = C.c_uint64
+    L.orc_list_total.argtypes = [C.c_void_p, C.c_uint32, C.c_int]
+    L.orc_get_lists.restype = C.c_int
+    L.orc_get_lists.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p]
+    L.orc_num_entries.restype = C.c_int
+    L.orc_num_entries.argtypes = [C.c_void_p]
+    L.orc_get_entries.argtypes = [C.c_void_p, C.c_void_p]
+    L.orc_num_edges.restype = C.c_int
+    L.orc_num_edges.argtypes = [C.c_void_p]
+    L.orc_get_edges.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orc_num_local.restype = C.c_int
+    L.orc_num_local.argtypes = [C.c_void_p]
+    L.orc_get_local2global.argtypes = [C.c_void_p, C.c_void_p]
+    L.orc_get_cluster_ids.restype = C.c_int
+    L.orc_get_cluster_ids.argtypes = [C.c_void_p, C.c_void_p]
+    L.orc_get_view_info.restype = C.c_int
+    L.orc_get_view_info.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+    L.orc_get_neighbors.restype = C.c_int
+    L.orc_get_neighbors.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_int]
+    L.orc_med_scene_depth_lines.restype = C.c_float
+    L.orc_med_scene_depth_lines.argtypes = [C.c_void_p]
+    return L
+
+
+_REF_LIBS = {}
+
+
+def ref_lib(kind="det"):
+    """The reference's Line3D++ sources compiled here (oracle/_ref/libref_line3d_<kind>.so); None if absent."""
+    if kind not in _REF_LIBS:
+        path = REF_LINE3D[kind]
+        if not os.path.exists(path):
+            build_ref()
+        if not os.path.exists(path):
+            _REF_LIBS[kind] = None
+        else:
+            L = _bind_common(C.CDLL(path))
+            L.ref_lines3D_counts.argtypes = [C.c_void_p, C.c_void_p]
+            L.ref_lines3D_get.argtypes = [C.c_void_p] * 6
+            L.ref_save_txt.argtypes = [C.c_void_p, C.c_char_p]
+            _REF_LIBS[kind] = L
+    return _REF_LIBS[kind]
 
 
 def lib():
@@ -146,8 +219,8 @@ class OracleLine3D:
                    "match_images", "reconstruct")
 
     def __init__(self, max_img_width: int, neighbors_by_worldpoints: bool = False, threads: int = 0,
-                 snapshot: bool = True):
-        self.L = lib()
+                 snapshot: bool = True, library=None):
+        self.L = library if library is not None else lib()
         self.L.orc_set_threads(threads)
         self.h = self.L.orc_create(int(max_img_width), int(bool(neighbors_by_worldpoints)))
         self.L.orc_set_snapshot(self.h, int(snapshot))
@@ -298,6 +371,42 @@ class OracleLine3D:
         t = np.zeros(10)
         self.L.orc_get_timers(self.h, _p(t))
         return dict(zip(self.TIMER_NAMES, t.tolist()))
+
+
+class RefLine3D(OracleLine3D):
+    """The same driver on the REFERENCE's own Line3D class (src/line3D.cc + src/view.cc compiled into oracle/_ref,
+    see oracle/ref_line3d_wrap.cpp).  kind: "det" (deterministic libm replacements, bit-comparable with the
+    restatement) or "libm" (glibc)."""
+
+    def __init__(self, max_img_width, neighbors_by_worldpoints=False, kind="det"):
+        L = ref_lib(kind)
+        if L is None:
+            raise RuntimeError("oracle/_ref/libref_line3d_%s.so is not built" % kind)
+        super().__init__(max_img_width, neighbors_by_worldpoints, 0, True, library=L)
+
+    def lines3D(self):
+        """Final 3-D lines: list of dicts(segs (k,2,3), residuals (r,2), ref_view)."""
+        cnt = np.zeros(3, dtype=np.uint32)
+        self.L.ref_lines3D_counts(self.h, _p(cnt))
+        n, ns, nr = (int(x) for x in cnt)
+        so, ro = np.zeros(n + 1, np.uint32), np.zeros(n + 1, np.uint32)
+        segs, res, rv = np.zeros((max(ns, 1), 2, 3)), np.zeros((max(nr, 1), 2), np.uint32), np.zeros(max(n, 1), np.uint32)
+        self.L.ref_lines3D_get(self.h, _p(so), _p(segs), _p(ro), _p(res), _p(rv))
+        return [dict(segs=segs[so[i]:so[i + 1]].copy(), residuals=res[ro[i]:ro[i + 1]].copy(), ref_view=int(rv[i]))
+                for i in range(n)]
+
+    def save_txt(self, folder):
+        self.L.ref_save_txt(self.h, folder.encode())
+
+
+def run_scene_ref(scene, kind="det", reconstruct=True):
+    o = RefLine3D(scene.max_image_width, scene.neighbors_by_worldpoints, kind)
+    o.load_scene(scene)
+    p = scene.params
+    o.match_images(p["sigma_p"], p["sigma_a"], p["num_neighbors"], p["epipolar_overlap"], p["knn"], p["const_reg_depth"])
+    if reconstruct:
+        o.reconstruct()
+    return o
 
 
 def run_scene(scene, threads=0, snapshot=True, reconstruct=True):

@@ -59,6 +59,8 @@ namespace l3d_hook = L3DPP::l3d_hook;
 #include <cstdint>
 #include <cstring>
 
+#include "standin/l3d_standin_offpath.h"
+
 namespace {
 struct Ref {
     L3DPP::Line3D* L;
@@ -67,6 +69,7 @@ struct Ref {
     bool by_wps;
     uint64_t pair_tests = 0;
     std::map<unsigned, std::set<unsigned>> matched_before;
+    std::vector<std::pair<unsigned, unsigned>> pair_log;  // (src, tgt) in the order computeMatches visited them
 };
 struct OrcRec {
     uint32_t tgt_cam, tgt_seg;
@@ -161,13 +164,26 @@ void orc_match_images(void* h, float sp, float sa, unsigned nn, float eo, int kn
     Quiet q;
     Ref* r = (Ref*)h;
     r->L->matchImages(sp, sa, nn, eo, knn, crd);
-    // segment-pair tests of the pairs this call matched: matched_ grows by both directions of every new pair
-    for (auto& kv : r->L->matched_)
-        for (unsigned tgt : kv.second) {
-            if (kv.first < tgt && !r->matched_before[kv.first].count(tgt))
-                r->pair_tests += (uint64_t)r->nseg[kv.first] * r->nseg[tgt];
-            r->matched_before[kv.first].insert(tgt);
+    // The pairs this call matched, in the order Line3D::computeMatches visits them (src/line3D.cc:848-887: views
+    // ascending, their visual neighbours ascending, skipping pairs in matched_): read back from the sets the
+    // reference filled -- visual_neighbors_ (this call's neighbours) and matched_ (grown by both directions).
+    for (auto& vn : r->L->visual_neighbors_) {
+        const unsigned src = vn.first;
+        for (unsigned tgt : vn.second) {
+            if (r->matched_before[src].count(tgt)) continue;
+            if (!r->L->matched_.count(src) || !r->L->matched_[src].count(tgt)) continue;  // not matched by the reference
+            r->pair_log.push_back({src, tgt});
+            r->pair_tests += (uint64_t)r->nseg[src] * r->nseg[tgt];
+            r->matched_before[src].insert(tgt);
+            r->matched_before[tgt].insert(src);
         }
+    }
+}
+int orc_num_pairs(void* h) { return (int)((Ref*)h)->pair_log.size(); }
+void orc_get_pairs(void* h, uint32_t* out)
+{
+    auto& v = ((Ref*)h)->pair_log;
+    for (size_t i = 0; i < v.size(); ++i) { out[2 * i] = v[i].first; out[2 * i + 1] = v[i].second; }
 }
 // Line3D::reconstruct3Dlines(visibility_t = 3, diffusion off, collinearity off, CERES off): src/L3DPPing.cpp:227
 void orc_reconstruct(void* h)
