@@ -109,6 +109,10 @@ def lib():
         L.l3d_get_sparse_device.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
         L.l3d_find_collinear.argtypes = [vp, vp, u32, f32, vp, u64]
         L.l3d_cluster.argtypes = [vp]
+        L.l3d_lines3D.argtypes = [vp, u32]
+        L.l3d_get_lines3D_counts.argtypes = [vp, vp]
+        L.l3d_get_lines3D.argtypes = [vp, vp, vp, vp, vp, vp]
+        L.l3d_save_lines3D_txt.argtypes = [vp, C.c_char_p]
         L.l3d_cluster_edges.argtypes = [vp, vp, u32, u32, vp]
         L.l3d_get_counts.argtypes = [vp, C.POINTER(Counts)]
         L.l3d_reset_counters.argtypes = [vp]
@@ -370,6 +374,24 @@ class Line3D:
 
     def affinity(self):
         self._ck(self.L.l3d_affinity(self.h))
+
+    # Line3D::get3Dlines (src/line3D.cc:2924-2933) for the current reconstruction: the cluster -> 3-D line tail
+    def get3Dlines(self, visibility_t=3):
+        """list of dict(segs (k,2,3) float64, residuals (r,2) uint32 (cam, seg), ref_view)."""
+        self._ck(self.L.l3d_lines3D(self.h, int(visibility_t)))
+        cnt = np.zeros(3, dtype=np.uint32)
+        self._ck(self.L.l3d_get_lines3D_counts(self.h, _p(cnt)))
+        n, ns, nr = (int(x) for x in cnt)
+        so, ro = np.zeros(n + 1, np.uint32), np.zeros(n + 1, np.uint32)
+        segs, res = np.zeros((max(ns, 1), 2, 3)), np.zeros((max(nr, 1), 2), np.uint32)
+        rv = np.zeros(max(n, 1), np.uint32)
+        self._ck(self.L.l3d_get_lines3D(self.h, _p(so), _p(segs), _p(ro), _p(res), _p(rv)))
+        return [dict(segs=segs[so[i]:so[i + 1]].copy(), residuals=res[ro[i]:ro[i + 1]].copy(), ref_view=int(rv[i]))
+                for i in range(n)]
+
+    # Line3D::save3DLinesAsTXT (src/line3D.cc:3122-3178); needs get3Dlines() first
+    def save3DLinesAsTXT(self, path):
+        self._ck(self.L.l3d_save_lines3D_txt(self.h, str(path).encode()))
 
     def sparse_matrix(self, sort_by_row=False, normalization_factor=1.0):
         """SparseMatrix(A_, n, norm, sort_by_row) (src/sparsematrix.cc:8-61): (entries (E,4) f32, start_indices (n,) i32)."""

@@ -4,6 +4,8 @@
 // 846-930, 2018-2118): camera set-up, translation, pair list, per-batch K1/K2, the
 // scoring phases, K4, and the (unchanged) clustering on the host.  No CPU fallback: every
 // compute entry point needs a CUDA device.
+#include <fstream>
+
 #include "ctx.h"
 
 static thread_local std::string g_err;
@@ -1044,6 +1046,22 @@ int l3d_affinity_edges(l3d_ctx* ctx)
     }
     // translate() again (src/line3D.cc:2065); only the camera centres move
     enter_translated(ctx);
+    // the cluster -> 3-D line tail (l3d_lines3D) runs in this frame too (src/line3D.cc:2115-2140): keep the cameras
+    ctx->lines_ready = false;
+    ctx->tail_translation = ctx->translation;
+    ctx->tail_views.resize(ctx->views.size());
+    for (size_t v = 0; v < ctx->views.size(); ++v) {
+        const HostView& hv = ctx->views[v];
+        TailView& tv = ctx->tail_views[v];
+        memcpy(tv.K, hv.cam.K.m, sizeof(tv.K));
+        memcpy(tv.R, hv.cam.R.m, sizeof(tv.R));
+        tv.t[0] = hv.cam.t.x; tv.t[1] = hv.cam.t.y; tv.t[2] = hv.cam.t.z;
+        tv.C[0] = hv.cam.C.x; tv.C[1] = hv.cam.C.y; tv.C[2] = hv.cam.C.z;
+        // View::View (src/view.cc:28-33): diagonal_ = sqrtf(float(w*w + h*h)), min_line_length_ = diagonal_ * 0.005f
+        const float diag = sqrtf((float)(hv.v.width * hv.v.width + hv.v.height * hv.v.height));
+        tv.min_line_length = diag * 0.005f;
+        tv.cam_id = hv.v.cam_id;
+    }
     // median scene depth of the lines (src/line3D.cc:2074-2091)
     std::vector<float> sd;
     for (auto& hv : ctx->views)
@@ -1334,6 +1352,169 @@ int l3d_cluster(l3d_ctx* ctx)
     std::set<int32_t> uniq(ctx->cluster_ids.begin(), ctx->cluster_ids.end());
     ctx->cnt.num_clusters = (uint32_t)uniq.size();
     ctx->stage = 4;
+    return L3D_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// cluster -> 3-D line tail (k6_lines3d.cu)
+// ------------------------------------------------------------------------------------------
+// replaces the rest of Line3D::reconstruct3Dlines after the clustering (src/line3D.cc:2115-2141):
+// clusterSegments' bookkeeping (:2502-2575: segments per cluster root in ascending local id, clusters in order of
+// first appearance, kept if seen by >= visibility_t cameras) on the host, then get3DlineFromCluster,
+// findCollinearSegments_return, filterTinySegments and the translation back, one thread per cluster on the device
+int l3d_lines3D(l3d_ctx* ctx, uint32_t visibility_t)
+{
+    if (!ctx) return fail(L3D_ERR_ARG, "ctx is NULL");
+    if (ctx->stage < 4) return fail(L3D_ERR_STATE, "l3d_cluster has not run");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    ctx->l3_seg_off.assign(1, 0);
+    ctx->l3_res_off.assign(1, 0);
+    ctx->l3_res.clear();
+    ctx->l3_ref_cam.clear();
+    ctx->l3_segs.clear();
+    ctx->lines_ready = true;
+    const uint32_t n = ctx->cnt.num_local_ids;
+    if (n == 0 || ctx->cnt.num_edges == 0) return L3D_OK;
+    visibility_t = std::max(visibility_t, 3u);  // src/line3D.cc:2040
+    // local id -> global segment
+    std::vector<uint32_t> g(n);
+    CK(cudaMemcpyAsync(g.data(), ctx->d_l2g.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    auto view_of = [&](uint32_t gs) {
+        uint32_t lo = 0, hi = (uint32_t)ctx->views.size();
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) / 2;
+            if (ctx->views[mid].seg_off <= gs) lo = mid; else hi = mid;
+        }
+        return lo;
+    };
+    // clusters in order of first appearance, members in ascending local id
+    std::vector<int32_t> slot_of(n, -1);
+    std::vector<uint32_t> cnt;
+    std::vector<int32_t> root_of_slot;
+    for (uint32_t i = 0; i < n; ++i) {
+        const int32_t root = ctx->cluster_ids[i];
+        if (slot_of[root] < 0) {
+            slot_of[root] = (int32_t)cnt.size();
+            cnt.push_back(0);
+            root_of_slot.push_back(root);
+        }
+        ++cnt[slot_of[root]];
+    }
+    std::vector<uint32_t> off(cnt.size() + 1, 0);
+    for (size_t c = 0; c < cnt.size(); ++c) off[c + 1] = off[c] + cnt[c];
+    std::vector<uint32_t> mem(n), fill(off.begin(), off.end() - 1);
+    for (uint32_t i = 0; i < n; ++i) mem[fill[slot_of[ctx->cluster_ids[i]]]++] = g[i];
+    // clusters seen by >= visibility_t cameras
+    std::vector<uint32_t> v_off(1, 0), v_mem;
+    std::set<uint32_t> cams;
+    for (size_t c = 0; c < cnt.size(); ++c) {
+        cams.clear();
+        for (uint32_t k = off[c]; k < off[c + 1]; ++k) cams.insert(view_of(mem[k]));
+        if (cams.size() < visibility_t) continue;
+        v_mem.insert(v_mem.end(), mem.begin() + off[c], mem.begin() + off[c + 1]);
+        v_off.push_back((uint32_t)v_mem.size());
+    }
+    const uint32_t ncl = (uint32_t)v_off.size() - 1, M = (uint32_t)v_mem.size();
+    if (ncl == 0) return L3D_OK;
+    CK(ctx->d_t_cl_off.ensure((size_t)ncl + 1));
+    CK(ctx->d_t_members.ensure(M));
+    CK(ctx->d_t_views.ensure(ctx->tail_views.size()));
+    CK(ctx->d_t_L.ensure(6 * (size_t)M));
+    CK(ctx->d_t_LC.ensure(6 * (size_t)M));
+    CK(ctx->d_t_pts.ensure(6 * (size_t)M));
+    CK(ctx->d_t_dist.ensure(2 * (size_t)M));
+    CK(ctx->d_t_ord.ensure(2 * (size_t)M));
+    CK(ctx->d_t_ok.ensure(M));
+    CK(ctx->d_t_camtab.ensure(2 * (size_t)M));
+    CK(ctx->d_t_out_n.ensure(ncl));
+    CK(ctx->d_t_out_ref.ensure(ncl));
+    CK(ctx->d_t_out_seg.ensure(6 * (size_t)M));
+    CK(cudaMemcpyAsync(ctx->d_t_cl_off.p, v_off.data(), ((size_t)ncl + 1) * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_t_members.p, v_mem.data(), (size_t)M * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_t_views.p, ctx->tail_views.data(), ctx->tail_views.size() * sizeof(TailView),
+                       cudaMemcpyHostToDevice, st));
+    const double t3[3] = {ctx->tail_translation.x, ctx->tail_translation.y, ctx->tail_translation.z};
+    ctx->cnt.gpu_launches +=
+        launch_k6_lines3d(ncl, ctx->d_t_cl_off.p, ctx->d_t_members.p, ctx->d_entries.p, ctx->d_segs.p, ctx->d_rays.p,
+                          ctx->d_seg_view.p, ctx->d_t_views.p, t3, ctx->d_t_L.p, ctx->d_t_LC.p, ctx->d_t_pts.p,
+                          ctx->d_t_dist.p, ctx->d_t_ord.p, ctx->d_t_ok.p, ctx->d_t_camtab.p, ctx->d_t_out_n.p,
+                          ctx->d_t_out_ref.p, ctx->d_t_out_seg.p, st);
+    std::vector<uint32_t> out_n(ncl), out_ref(ncl);
+    std::vector<double> out_seg(6 * (size_t)M);
+    CK(cudaMemcpyAsync(out_n.data(), ctx->d_t_out_n.p, (size_t)ncl * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(out_ref.data(), ctx->d_t_out_ref.p, (size_t)ncl * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(out_seg.data(), ctx->d_t_out_seg.p, 6 * (size_t)M * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    // lines3D_: the clusters that kept at least one segment, in cluster order
+    for (uint32_t c = 0; c < ncl; ++c) {
+        if (!out_n[c]) continue;
+        const size_t base = 6 * (size_t)v_off[c];
+        ctx->l3_segs.insert(ctx->l3_segs.end(), out_seg.begin() + base, out_seg.begin() + base + 6 * (size_t)out_n[c]);
+        ctx->l3_seg_off.push_back((uint32_t)(ctx->l3_segs.size() / 6));
+        for (uint32_t k = v_off[c]; k < v_off[c + 1]; ++k) {
+            const uint32_t v = view_of(v_mem[k]);
+            ctx->l3_res.push_back(ctx->views[v].v.cam_id);
+            ctx->l3_res.push_back(v_mem[k] - ctx->views[v].seg_off);
+        }
+        ctx->l3_res_off.push_back((uint32_t)(ctx->l3_res.size() / 2));
+        ctx->l3_ref_cam.push_back(out_ref[c] == 0xffffffffu ? 0u : ctx->views[out_ref[c]].v.cam_id);
+    }
+    return L3D_OK;
+}
+
+int l3d_get_lines3D_counts(l3d_ctx* ctx, uint32_t* counts3)
+{
+    if (!ctx || !counts3) return fail(L3D_ERR_ARG, "NULL argument");
+    if (!ctx->lines_ready) return fail(L3D_ERR_STATE, "l3d_lines3D has not run");
+    counts3[0] = (uint32_t)ctx->l3_ref_cam.size();
+    counts3[1] = (uint32_t)(ctx->l3_segs.size() / 6);
+    counts3[2] = (uint32_t)(ctx->l3_res.size() / 2);
+    return L3D_OK;
+}
+
+int l3d_get_lines3D(l3d_ctx* ctx, uint32_t* seg_off, double* segs6, uint32_t* res_off, uint32_t* res2, uint32_t* ref_cam)
+{
+    if (!ctx || !seg_off || !segs6 || !res_off || !res2 || !ref_cam) return fail(L3D_ERR_ARG, "NULL argument");
+    if (!ctx->lines_ready) return fail(L3D_ERR_STATE, "l3d_lines3D has not run");
+    memcpy(seg_off, ctx->l3_seg_off.data(), ctx->l3_seg_off.size() * 4);
+    memcpy(res_off, ctx->l3_res_off.data(), ctx->l3_res_off.size() * 4);
+    if (!ctx->l3_segs.empty()) memcpy(segs6, ctx->l3_segs.data(), ctx->l3_segs.size() * 8);
+    if (!ctx->l3_res.empty()) memcpy(res2, ctx->l3_res.data(), ctx->l3_res.size() * 4);
+    if (!ctx->l3_ref_cam.empty()) memcpy(ref_cam, ctx->l3_ref_cam.data(), ctx->l3_ref_cam.size() * 4);
+    return L3D_OK;
+}
+
+// Line3D::save3DLinesAsTXT (src/line3D.cc:3122-3178): per line "k  k x (P1 P2)  r  r x (camID segID x1 y1 x2 y2)",
+// std::ofstream default formatting
+int l3d_save_lines3D_txt(l3d_ctx* ctx, const char* path)
+{
+    if (!ctx || !path) return fail(L3D_ERR_ARG, "NULL argument");
+    if (!ctx->lines_ready) return fail(L3D_ERR_STATE, "l3d_lines3D has not run");
+    if (ctx->l3_ref_cam.empty()) return fail(L3D_ERR_STATE, "no 3D lines to save!");
+    std::ofstream file(path);
+    if (!file) return fail(L3D_ERR_ARG, "cannot open %s", path);
+    for (size_t i = 0; i < ctx->l3_ref_cam.size(); ++i) {
+        const uint32_t s0 = ctx->l3_seg_off[i], s1 = ctx->l3_seg_off[i + 1];
+        file << (size_t)(s1 - s0) << " ";
+        for (uint32_t s = s0; s < s1; ++s) {
+            const double* p = &ctx->l3_segs[6 * (size_t)s];
+            file << p[0] << " " << p[1] << " " << p[2] << " ";
+            file << p[3] << " " << p[4] << " " << p[5] << " ";
+        }
+        const uint32_t r0 = ctx->l3_res_off[i], r1 = ctx->l3_res_off[i + 1];
+        file << (size_t)(r1 - r0) << " ";
+        for (uint32_t r = r0; r < r1; ++r) {
+            const uint32_t cam = ctx->l3_res[2 * (size_t)r], seg = ctx->l3_res[2 * (size_t)r + 1];
+            file << cam << " " << seg << " ";
+            const HostView& hv = ctx->views[ctx->cam2view[cam]];
+            const float* c = &hv.segs[4 * (size_t)seg];
+            file << c[0] << " " << c[1] << " ";
+            file << c[2] << " " << c[3] << " ";
+        }
+        file << std::endl;
+    }
     return L3D_OK;
 }
 

@@ -330,6 +330,18 @@ struct l3d_ctx {
     DevBuf<float4> d_collin_lines;
     // host results
     std::vector<int32_t> cluster_ids;
+    // cluster -> 3-D line tail (l3d_lines3D): the cameras as Line3D::reconstruct3Dlines sees them between translate()
+    // and untranslate(), the translation they were shifted by, and the final lines (flat, reference order)
+    std::vector<TailView> tail_views;
+    hg::V3 tail_translation{0, 0, 0};
+    std::vector<uint32_t> l3_seg_off, l3_res_off, l3_res, l3_ref_cam;
+    std::vector<double> l3_segs;
+    bool lines_ready = false;
+    DevBuf<uint32_t> d_t_cl_off, d_t_members, d_t_ord, d_t_camtab, d_t_out_n, d_t_out_ref;
+    DevBuf<double> d_t_L, d_t_LC, d_t_pts, d_t_out_seg;
+    DevBuf<float> d_t_dist;
+    DevBuf<unsigned char> d_t_ok;
+    DevBuf<TailView> d_t_views;
 
     // key-frame stream mode (stream.cu)
     bool stream_mode = false;

@@ -112,6 +112,14 @@ struct EntryDev {
     uint32_t has;  // 1 if the segment has a best match with score > 0.75
 };
 
+// a view as the cluster -> 3-D line tail needs it (k6_lines3d.cu): K, R, t and centre in the translated frame
+// of Line3D::reconstruct3Dlines, View::min_line_length_ (src/view.cc:33: diagonal * 0.005)
+struct TailView {
+    double K[9], R[9], t[3], C[3];
+    float min_line_length;
+    uint32_t cam_id;
+};
+
 struct K1Cta {
     uint32_t pair, tile;
 };
@@ -181,6 +189,12 @@ int launch_k0_prep(const float4* segs, const uint32_t* seg_view, const ViewDev* 
                    int max_image_width, SegDesc* desc, SegRays* rays, double* midray, SegPlane* planes,
                    SegV32* v32, float* view_xb,
                    cudaStream_t st);
+
+int launch_k6_lines3d(uint32_t n_clusters, const uint32_t* cl_off, const uint32_t* members, const EntryDev* entries,
+                      const float4* segs, const SegRays* rays, const uint32_t* seg_view, const TailView* views,
+                      const double* t3, double* Lbuf, double* LCbuf, double* pts, float* dist, uint32_t* ord,
+                      unsigned char* okflag, uint32_t* camtab, uint32_t* out_n, uint32_t* out_ref, double* out_seg,
+                      cudaStream_t st);
 
 int launch_k1_pairtest(const PairDev* pairs, const K1Cta* ctas, uint32_t n_ctas, const float4* segs,
                        const SegDesc* desc, const float* view_xb, uint32_t* mask, uint32_t* cand_cnt,

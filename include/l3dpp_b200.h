@@ -238,6 +238,20 @@ int l3d_cluster(l3d_ctx* ctx);
 int l3d_cluster_edges(const int32_t* edges_ij, const float* weights, uint32_t ne, uint32_t n,
                       int32_t* out_root);
 
+/* replaces the rest of Line3D::reconstruct3Dlines after the clustering (src/line3D.cc:2115-2141): for every cluster
+ * seen by >= visibility_t cameras (at least 3) Line3D::get3DlineFromCluster (src/line3D.cc:2578-2641),
+ * Line3D::findCollinearSegments_return (:2763-2870, with project2DsegmentOnto3Dline :2644-2687),
+ * Line3D::filterTinySegments (:2724-2760) and the translation back, on the device (one thread per cluster).
+ * Needs l3d_cluster.  The lines are kept in the context:
+ *   l3d_get_lines3D_counts  counts3 = {lines, 3-D segments in total, 2-D residuals in total}
+ *   l3d_get_lines3D         seg_off[lines+1], segs6[6 x segments] (P1, P2), res_off[lines+1],
+ *                           res2[2 x residuals] (camera id, segment id), ref_cam[lines] (LineCluster3D::reference_view)
+ *   l3d_save_lines3D_txt    Line3D::save3DLinesAsTXT (src/line3D.cc:3122-3178) into the file `path` */
+int l3d_lines3D(l3d_ctx* ctx, uint32_t visibility_t);
+int l3d_get_lines3D_counts(l3d_ctx* ctx, uint32_t* counts3);
+int l3d_get_lines3D(l3d_ctx* ctx, uint32_t* seg_off, double* segs6, uint32_t* res_off, uint32_t* res2, uint32_t* ref_cam);
+int l3d_save_lines3D_txt(l3d_ctx* ctx, const char* path);
+
 /* results (host pointers) */
 int l3d_get_counts(l3d_ctx* ctx, l3d_counts* out);
 int l3d_reset_counters(l3d_ctx* ctx);

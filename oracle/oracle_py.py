@@ -34,7 +34,8 @@ REF_CLUSTERING = os.path.join(_HERE, "_ref", "libref_clustering.so")
 
 
 REF_LINE3D = {"det": os.path.join(_HERE, "_ref", "libref_line3d_det.so"),
-              "libm": os.path.join(_HERE, "_ref", "libref_line3d_libm.so")}
+              "libm": os.path.join(_HERE, "_ref", "libref_line3d_libm.so"),
+              "omp": os.path.join(_HERE, "_ref", "libref_line3d_omp.so")}   # timing only: order depends on the schedule
 
 
 def build_ref() -> bool:

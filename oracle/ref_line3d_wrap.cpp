@@ -58,6 +58,9 @@ namespace l3d_hook = L3DPP::l3d_hook;
 
 #include <cstdint>
 #include <cstring>
+#ifdef L3D_REF_OPENMP
+#include <omp.h>
+#endif
 
 #include "standin/l3d_standin_offpath.h"
 
@@ -118,8 +121,13 @@ void orc_destroy(void* h)
     delete r->L;
     delete r;
 }
+#ifdef L3D_REF_OPENMP
+void orc_set_threads(int n) { omp_set_num_threads(n > 0 ? n : omp_get_num_procs()); }
+int orc_max_threads() { return omp_get_max_threads(); }
+#else
 void orc_set_threads(int) {}
 int orc_max_threads() { return 1; }
+#endif
 void orc_set_snapshot(void*, int) {}
 
 int orc_add_image(void* h, uint32_t camID, const double* K, const double* R, const double* t, unsigned w, unsigned hh,

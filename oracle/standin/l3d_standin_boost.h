@@ -1,17 +1,21 @@
 // oracle/standin/l3d_standin_boost.h -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
 // Stand-ins for the Boost names the reference's Line3D++ headers mention (mutexes around its OpenMP loops,
 // the serialization hooks of its result types, filesystem calls of the segment cache), so that the sources
-// compile unmodified into oracle/_ref.  The build is single-threaded, the cache and the archives are unused.
+// compile unmodified into oracle/_ref.  The cache and the archives are unused.
 #pragma once
 #include <fstream>
+#include <mutex>
 #include <string>
 #include <sys/stat.h>
 
 namespace boost {
+// a real lock: the _omp build (timing only) runs the reference's OpenMP loops, which rely on these mutexes
 class mutex {
   public:
-    void lock() {}
-    void unlock() {}
+    void lock() { m_.lock(); }
+    void unlock() { m_.unlock(); }
+  private:
+    std::mutex m_;
 };
 namespace filesystem {
 class path {
