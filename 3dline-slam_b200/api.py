@@ -133,6 +133,9 @@ def lib():
         L.l3d_shard_export.argtypes = [vp, C.c_int, vp, u64, C.c_int]
         L.l3d_shard_import.argtypes = [vp, C.c_int, vp, u64, C.c_int, vp, C.c_int]
         L.l3d_shard_export_hdr.argtypes = [vp, C.c_int, vp, u64]
+        L.l3d_shard_forward_plan.argtypes = [vp, vp, vp]
+        L.l3d_shard_forward_pack.argtypes = [vp, vp, u64, C.c_int]
+        L.l3d_shard_forward_unpack.argtypes = [vp, vp, u64, C.c_int]
         L.l3d_shard_import_hdr.argtypes = [vp, C.c_int, vp, u64, C.c_int, vp, C.POINTER(C.c_int)]
         L.l3d_stream_begin.argtypes = [vp, C.c_int]
         L.l3d_stream_begin_cycle.argtypes = [vp]
@@ -495,6 +498,19 @@ class Line3D:
         self._ck(self.L.l3d_shard_import(self.h, int(kind), C.c_void_p(ptr), stride_bytes, int(world), _p(sz),
                                          int(device_ptr)))
 
+
+    def shard_forward_plan(self):
+        """(send, recv): records this rank sends to / receives from every peer (uint64 arrays of world entries)."""
+        world = max(self.shard[1], 1)
+        send, recv = np.zeros(world, dtype=np.uint64), np.zeros(world, dtype=np.uint64)
+        self._ck(self.L.l3d_shard_forward_plan(self.h, _p(send), _p(recv)))
+        return send, recv
+
+    def shard_forward_pack(self, ptr, cap_bytes, device_ptr):
+        self._ck(self.L.l3d_shard_forward_pack(self.h, C.c_void_p(ptr), int(cap_bytes), int(device_ptr)))
+
+    def shard_forward_unpack(self, ptr, nbytes, device_ptr):
+        self._ck(self.L.l3d_shard_forward_unpack(self.h, C.c_void_p(ptr), int(nbytes), int(device_ptr)))
 
     def shard_export_hdr(self, kind, ptr, stride_bytes):
         self._ck(self.L.l3d_shard_export_hdr(self.h, int(kind), C.c_void_p(ptr), stride_bytes))

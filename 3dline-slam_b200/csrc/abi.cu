@@ -175,9 +175,10 @@ int l3d_score_matches(l3d_ctx* ctx, const float* lines, uint32_t n_lines, const 
 // multi-GPU: the four exchange points of a sharded run (one process per GPU; the collective itself
 // is torch.distributed / NCCL, see 3dline-slam_b200/sharding.py).  Every rank exports one blob,
 // the blobs are all-gathered `stride` bytes apart, every rank imports all of them.
-//   FORWARD     u32 cnt[rows_pad8] | FwdRec recs[] of the boundary pairs  rows = pair rows of the slice
-//               (only the matches whose target view belongs to another slice travel: nobody else reads
-//               the rest; every rank still learns all per-row counts, i.e. the global record numbering)
+//   FORWARD     u32 cnt[rows_pad8]                                        rows = pair rows of the slice
+//               (every rank learns all per-row counts, i.e. the global record numbering).  The RECORDS of a
+//               boundary pair -- target view in another slice -- are needed by one rank only, the owner of the
+//               target view, so they travel all-to-all right after: l3d_shard_forward_plan / _pack / _unpack.
 //   PROGRAMS    u32 nh[rows_pad4] | u32 off[rows_pad4] | uint4 rec[]     rows = segments of the slice
 //   HYPOTHESES  ShardHypHdr | u32 filt_cnt[rows_pad4] | u32 filt_off[rows_pad4] | EntryDev e[rows] | ListRec filt[]
 //   EDGES       {u32 src, u32 tgt, float w}[]
@@ -233,43 +234,12 @@ static int check_phase(l3d_ctx* ctx, int kind)
     return L3D_OK;
 }
 
-// FORWARD: the records of this rank's boundary pairs, gathered into d_bx_rec; count at d_bx_off[rows]
-static int prepare_forward_export(l3d_ctx* ctx)
-{
-    cudaStream_t st = ctx->stream;
-    const uint32_t r0 = ctx->slice_row[ctx->rank], r1 = ctx->slice_row[ctx->rank + 1], rows = r1 - r0;
-    CK(ctx->d_bx_cnt.ensure((size_t)rows + 1));
-    CK(ctx->d_bx_off.ensure((size_t)rows + 2));
-    CK(ctx->d_bx_rec.ensure((size_t)ctx->local_fwd + 1));
-    CK(ctx->d_scan.ensure(scan_scratch_words(rows + 1) + 64));
-    if (!rows) {
-        CK(cudaMemsetAsync(ctx->d_bx_off.p, 0, 8, st));
-        return L3D_OK;
-    }
-    ctx->cnt.gpu_launches += launch_fwd_bmask(ctx->d_pairs.p, (uint32_t)ctx->pairs.size(), ctx->d_fwd_cnt.p, r0, r1,
-                                              ctx->d_bx_cnt.p, st);
-    ctx->cnt.gpu_launches += launch_scan_u32(ctx->d_bx_cnt.p, ctx->d_bx_off.p, rows, ctx->d_scan.p, ctx->d_scan.cap, st);
-    // d_fwd_off still holds the local offsets of this rank's rows
-    ctx->cnt.gpu_launches += launch_fwd_bgather(ctx->d_bx_cnt.p, ctx->d_bx_off.p, ctx->d_fwd_off.p, r0, r1,
-                                                ctx->d_fwd_rec.p, ctx->d_bx_rec.p, st);
-    return L3D_OK;
-}
-
 // variable part of this rank's blob (elements); reads the device cursors, so it synchronises
 static int blob_var_count(l3d_ctx* ctx, int kind, uint64_t* n)
 {
     cudaStream_t st = ctx->stream;
     switch (kind) {
-    case L3D_X_FORWARD: {
-        int rc = prepare_forward_export(ctx);
-        if (rc) return rc;
-        uint32_t nb = 0;
-        const uint32_t rows = ctx->slice_row[ctx->rank + 1] - ctx->slice_row[ctx->rank];
-        CK(cudaMemcpyAsync(&nb, ctx->d_bx_off.p + rows, 4, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        *n = nb;
-        return L3D_OK;
-    }
+    case L3D_X_FORWARD: *n = 0; return L3D_OK;  // counts only; the records travel all-to-all
     case L3D_X_EDGES: *n = ctx->n_edges_local; return L3D_OK;
     case L3D_X_PROGRAMS:
         for (int attempt = 0;; ++attempt) {
@@ -330,7 +300,6 @@ static int export_payload(l3d_ctx* ctx, int kind, unsigned char* d, uint64_t n, 
     case L3D_X_FORWARD: {
         const uint32_t r0 = ctx->slice_row[ctx->rank];
         if (rows) CK(cudaMemcpyAsync(d, ctx->d_fwd_cnt.p + r0, (size_t)rows * 4, ck, st));
-        if (n) CK(cudaMemcpyAsync(d + pad_to(rows, 8) * 4, ctx->d_bx_rec.p, n * sizeof(FwdRec), ck, st));
         break;
     }
     case L3D_X_PROGRAMS: {
@@ -415,13 +384,7 @@ int l3d_shard_export_hdr(l3d_ctx* ctx, int kind, void* dst, uint64_t stride_byte
     const uint32_t* n_dev = nullptr;
     const uint32_t* f_dev = nullptr;
     switch (kind) {
-    case L3D_X_FORWARD: {
-        rc = prepare_forward_export(ctx);
-        if (rc) return rc;
-        have = ctx->local_fwd;  // upper bound of the boundary records; the exact count is on the device
-        n_dev = ctx->d_bx_off.p + (ctx->slice_row[ctx->rank + 1] - ctx->slice_row[ctx->rank]);
-        break;
-    }
+    case L3D_X_FORWARD: have = 0; break;  // counts only
     case L3D_X_EDGES: have = ctx->n_edges_local; break;
     case L3D_X_PROGRAMS:
         have = ctx->prog_cap;
@@ -485,24 +448,21 @@ int l3d_shard_import(l3d_ctx* ctx, int kind, const void* all, uint64_t stride_by
         }
         CK(ctx->d_scan.ensure(scan_scratch_words(R + 1) + 64));
         ctx->cnt.gpu_launches += launch_scan_u32(ctx->d_fwd_cnt.p, ctx->d_fwd_off.p, R, ctx->d_scan.p, ctx->d_scan.cap, st);
-        // where the boundary records of every rank sit inside its blob
-        CK(ctx->d_bx_cnt_all.ensure((size_t)R + 1));
-        CK(ctx->d_bx_off_all.ensure((size_t)R + 2));
-        ctx->cnt.gpu_launches += launch_fwd_bmask(ctx->d_pairs.p, P, ctx->d_fwd_cnt.p, 0, R, ctx->d_bx_cnt_all.p, st);
-        ctx->cnt.gpu_launches += launch_scan_u32(ctx->d_bx_cnt_all.p, ctx->d_bx_off_all.p, R, ctx->d_scan.p, ctx->d_scan.cap, st);
         rc = refresh_pair_totals(ctx);  // synchronises: record totals per pair and overall
         if (rc) return rc;
         const uint64_t total = ctx->pair_total_sum;
         if (total > 0xfffffff0ull) return fail(L3D_ERR_CAPACITY, "too many forward matches");
         CK(ctx->d_fwd_alt.ensure((size_t)total + 1));
-        ctx->cnt.gpu_launches += launch_fwd_place(src, stride_bytes, world, ctx->slice_row.data(), ctx->rank, R,
-                                                  ctx->d_fwd_cnt.p, ctx->d_fwd_off.p, ctx->d_bx_cnt_all.p,
-                                                  ctx->d_bx_off_all.p, ctx->d_fwd_rec.p, ctx->d_fwd_off_local.p,
-                                                  ctx->d_fwd_alt.p, st);
+        // this rank's own records: local layout -> canonical layout (the boundary records of the other ranks
+        // arrive through l3d_shard_forward_unpack)
+        (void)P;
+        ctx->cnt.gpu_launches += launch_fwd_move(ctx->d_fwd_cnt.p + r0, r0, r1, ctx->d_fwd_off_local.p, ctx->d_fwd_rec.p,
+                                                 ctx->d_fwd_off.p, ctx->d_fwd_alt.p, st);
         std::swap(ctx->d_fwd_rec.p, ctx->d_fwd_alt.p);
         std::swap(ctx->d_fwd_rec.cap, ctx->d_fwd_alt.cap);
         ctx->total_fwd = total;
         ctx->cnt.forward_matches = total;
+        ctx->fwd_planned = false;
         return L3D_OK;
     }
     case L3D_X_PROGRAMS: {
@@ -556,6 +516,111 @@ int l3d_shard_import(l3d_ctx* ctx, int kind, const void* all, uint64_t stride_by
     }
     }
     return fail(L3D_ERR_ARG, "unknown exchange kind %d", kind);
+}
+
+// ---- FORWARD records, all-to-all.  After the FORWARD exchange (every rank holds all per-row counts):
+//   plan    send_records[d] / recv_records[q]: records this rank sends to rank d / receives from rank q
+//           (0 for itself); reads a world x world matrix back, so it synchronises
+//   pack    this rank's boundary records grouped by destination rank (ascending), rows ascending inside a group
+//   unpack  the received records, grouped by source rank (ascending) = ascending global row, into the canonical store
+int l3d_shard_forward_plan(l3d_ctx* ctx, uint64_t* send_records, uint64_t* recv_records)
+{
+    int rc = check_phase(ctx, L3D_X_FORWARD);
+    if (rc) return rc;
+    if (!send_records || !recv_records) return fail(L3D_ERR_ARG, "NULL argument");
+    const int world = ctx->world;
+    if (world > L3D_MAX_WORLD_C) return fail(L3D_ERR_ARG, "world %d too large", world);
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    CK(ctx->d_fwd_plan.ensure((size_t)world * world));
+    CK(cudaMemsetAsync(ctx->d_fwd_plan.p, 0, (size_t)world * world * 8, st));
+    ctx->cnt.gpu_launches += launch_fwd_plan(ctx->d_pairs.p, (uint32_t)ctx->pairs.size(), ctx->d_fwd_cnt.p, ctx->total_rows,
+                                             ctx->slice_row.data(), world, ctx->d_fwd_plan.p, st);
+    std::vector<unsigned long long> M((size_t)world * world);
+    CK(cudaMemcpyAsync(M.data(), ctx->d_fwd_plan.p, M.size() * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    for (int q = 0; q < world; ++q) {
+        ctx->fwd_send[q] = send_records[q] = q == ctx->rank ? 0 : M[(size_t)ctx->rank * world + q];
+        ctx->fwd_recv[q] = recv_records[q] = q == ctx->rank ? 0 : M[(size_t)q * world + ctx->rank];
+    }
+    ctx->fwd_planned = true;
+    return L3D_OK;
+}
+
+int l3d_shard_forward_pack(l3d_ctx* ctx, void* dst, uint64_t cap_bytes, int device_ptr)
+{
+    int rc = check_phase(ctx, L3D_X_FORWARD);
+    if (rc) return rc;
+    if (!ctx->fwd_planned) return fail(L3D_ERR_STATE, "l3d_shard_forward_plan has not run");
+    const int world = ctx->world;
+    uint64_t total = 0;
+    for (int d = 0; d < world; ++d) total += ctx->fwd_send[d];
+    if (total * sizeof(FwdRec) > cap_bytes) return fail(L3D_ERR_CAPACITY, "need %llu bytes", (unsigned long long)(total * sizeof(FwdRec)));
+    if (!total) return L3D_OK;
+    if (!dst) return fail(L3D_ERR_ARG, "NULL argument");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const uint32_t r0 = ctx->slice_row[ctx->rank], r1 = ctx->slice_row[ctx->rank + 1], rows = r1 - r0;
+    CK(ctx->d_fx_cnt.ensure((size_t)rows + 1));
+    CK(ctx->d_fx_off.ensure((size_t)rows + 2));
+    CK(ctx->d_scan.ensure(scan_scratch_words(rows + 1) + 64));
+    FwdRec* out = (FwdRec*)dst;
+    DevBuf<FwdRec>& stg = ctx->d_bx_rec;
+    if (!device_ptr) {
+        CK(stg.ensure((size_t)total + 1));
+        out = stg.p;
+    }
+    uint64_t at = 0;
+    for (int d = 0; d < world; ++d) {
+        if (!ctx->fwd_send[d]) continue;
+        // d_fwd_rec / d_fwd_off hold the canonical layout since the FORWARD import: own rows are in place there
+        ctx->cnt.gpu_launches += launch_fwd_dmask(ctx->d_pairs.p, (uint32_t)ctx->pairs.size(), ctx->d_fwd_cnt.p, r0, r1,
+                                                  (uint32_t)d, ctx->slice_row.data(), world, -1, ctx->d_fx_cnt.p, st);
+        ctx->cnt.gpu_launches += launch_scan_u32(ctx->d_fx_cnt.p, ctx->d_fx_off.p, rows, ctx->d_scan.p, ctx->d_scan.cap, st);
+        // row-relative views of the offset arrays: the move kernel indexes src_off / dst_off by absolute row
+        ctx->cnt.gpu_launches += launch_fwd_move(ctx->d_fx_cnt.p, r0, r1, ctx->d_fwd_off.p, ctx->d_fwd_rec.p,
+                                                 ctx->d_fx_off.p - r0, out + at, st);
+        at += ctx->fwd_send[d];
+    }
+    if (!device_ptr) {
+        CK(cudaMemcpyAsync(dst, stg.p, total * sizeof(FwdRec), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    return L3D_OK;
+}
+
+int l3d_shard_forward_unpack(l3d_ctx* ctx, const void* src, uint64_t bytes, int device_ptr)
+{
+    int rc = check_phase(ctx, L3D_X_FORWARD);
+    if (rc) return rc;
+    if (!ctx->fwd_planned) return fail(L3D_ERR_STATE, "l3d_shard_forward_plan has not run");
+    const int world = ctx->world;
+    uint64_t total = 0;
+    for (int q = 0; q < world; ++q) total += ctx->fwd_recv[q];
+    if (bytes != total * sizeof(FwdRec)) return fail(L3D_ERR_ARG, "expected %llu bytes, got %llu", (unsigned long long)(total * sizeof(FwdRec)), (unsigned long long)bytes);
+    if (!total) return L3D_OK;
+    if (!src) return fail(L3D_ERR_ARG, "NULL argument");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const uint32_t R = ctx->total_rows;
+    const FwdRec* in = (const FwdRec*)src;
+    if (!device_ptr) {
+        DevBuf<unsigned char>& stg = ctx->d_xchg_stage[L3D_X_FORWARD];
+        CK(stg.ensure(bytes));
+        CK(cudaMemcpyAsync(stg.p, src, bytes, cudaMemcpyHostToDevice, st));
+        in = (const FwdRec*)stg.p;
+    }
+    // received records = the rows of the other ranks whose pair targets a view of this rank, in ascending row
+    CK(ctx->d_bx_cnt_all.ensure((size_t)R + 1));
+    CK(ctx->d_bx_off_all.ensure((size_t)R + 2));
+    CK(ctx->d_scan.ensure(scan_scratch_words(R + 1) + 64));
+    ctx->cnt.gpu_launches += launch_fwd_dmask(ctx->d_pairs.p, (uint32_t)ctx->pairs.size(), ctx->d_fwd_cnt.p, 0, R,
+                                              (uint32_t)ctx->rank, ctx->slice_row.data(), world, ctx->rank,
+                                              ctx->d_bx_cnt_all.p, st);
+    ctx->cnt.gpu_launches += launch_scan_u32(ctx->d_bx_cnt_all.p, ctx->d_bx_off_all.p, R, ctx->d_scan.p, ctx->d_scan.cap, st);
+    ctx->cnt.gpu_launches += launch_fwd_move(ctx->d_bx_cnt_all.p, 0, R, ctx->d_bx_off_all.p, in, ctx->d_fwd_off.p,
+                                             ctx->d_fwd_rec.p, st);
+    return L3D_OK;
 }
 
 // sizes_out[q] = payload bytes of rank q; *redo != 0: some blob did not fit / some program store

@@ -456,7 +456,8 @@ int plan_pairs(l3d_ctx* ctx)
         d.tgt_base = (uint32_t)trow;
         d.words = (d.n_tgt + 31) / 32;
         d.emit_inverse = hp.tgt > hp.src ? 1u : 0u;  // !processed_[tgt] (src/line3D.cc:1994)
-        d.xflag = (owner_of(hp.tgt) != owner_of(hp.src)) ? 1u : 0u;
+        // boundary pair: 1 + the rank that owns the target view (it receives the pair's records as inverse candidates)
+        d.xflag = (owner_of(hp.tgt) != owner_of(hp.src)) ? (uint32_t)owner_of(hp.tgt) + 1u : 0u;
         row += d.n_src;
         trow += d.n_tgt;
         if (hp.local) {

@@ -35,6 +35,12 @@ int launch_fwd_bgather(const uint32_t*, const uint32_t*, const uint32_t*, uint32
 int launch_fwd_place(const unsigned char*, uint64_t, int, const uint32_t*, int, uint32_t, const uint32_t*,
                      const uint32_t*, const uint32_t*, const uint32_t*, const FwdRec*, const uint32_t*, FwdRec*,
                      cudaStream_t);
+int launch_fwd_plan(const PairDev*, uint32_t, const uint32_t*, uint32_t, const uint32_t*, int, unsigned long long*,
+                    cudaStream_t);
+int launch_fwd_dmask(const PairDev*, uint32_t, const uint32_t*, uint32_t, uint32_t, uint32_t, const uint32_t*, int, int,
+                     uint32_t*, cudaStream_t);
+int launch_fwd_move(const uint32_t*, uint32_t, uint32_t, const uint32_t*, const FwdRec*, const uint32_t*, FwdRec*,
+                    cudaStream_t);
 int launch_k3_list_capacity(const ViewDev*, const uint32_t*, uint32_t, const IncDev*, const uint32_t*, const PairDev*,
                             const uint32_t*, const uint32_t*, uint32_t*, void*, cudaStream_t);
 int launch_k3_records(const PairDev*, uint32_t, uint32_t, const uint32_t*, const FwdRec*, float*, const uint32_t*,
@@ -192,6 +198,7 @@ struct StageTimer {
     }
 };
 
+#define L3D_MAX_WORLD_C 16
 struct l3d_ctx {
     int device = 0;
     cudaStream_t stream = 0;
@@ -303,6 +310,10 @@ struct l3d_ctx {
     uint32_t n_edges_local = 0, n_edges_all = 0;
     uint64_t local_fwd = 0;      // forward records produced by this rank's pairs
     uint64_t xchg_var[4] = {0, 0, 0, 0};
+    uint64_t fwd_send[L3D_MAX_WORLD_C] = {0}, fwd_recv[L3D_MAX_WORLD_C] = {0};  // FORWARD records per peer (forward_plan)
+    bool fwd_planned = false;
+    DevBuf<unsigned long long> d_fwd_plan;
+    DevBuf<uint32_t> d_fx_cnt, d_fx_off;
     DevBuf<unsigned char> d_xchg_stage[4];
     DevBuf<uint32_t> d_slice_g;
     uint64_t shard_sim_evals = 0, shard_scored = 0, shard_filtered = 0;

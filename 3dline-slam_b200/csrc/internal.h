@@ -70,7 +70,7 @@ struct PairDev {
     uint32_t emit_inverse;  // tgt view is processed after src view (line3D.cc:1994)
     uint64_t mask_base;  // word offset of this pair's bit mask inside the batch buffer
     uint32_t batch_row0; // first row of the batch this pair belongs to
-    uint32_t xflag;      // multi-GPU: the target view belongs to another rank's slice (boundary pair)
+    uint32_t xflag;      // multi-GPU: 0, or 1 + the rank owning the target view when it is in another rank's slice
 };
 
 // forward match record, 32 B (matches_ entries produced by matching, line3D.cc:1169-1181)

@@ -4,8 +4,13 @@ A rank matches the pairs whose source view it owns (stages 1-2), builds and fini
 rows of its views and computes their affinity edges; four exchanges (all-gather over NCCL / NVLink
 on the GPU box, gloo in the CPU tests) make every result whole on every rank:
 
-    match_stage12 -> FORWARD -> score_build -> PROGRAMS -> score_fold -> HYPOTHESES
-                  -> affinity_edges -> EDGES -> affinity_ids
+    match_stage12 -> FORWARD (+ forward records, all-to-all) -> score_build -> PROGRAMS -> score_fold
+                  -> HYPOTHESES -> affinity_edges -> EDGES -> affinity_ids
+
+FORWARD carries the per-row match counts only (every rank needs the global record numbering).  The match
+records of a boundary pair are needed by ONE other rank, the owner of the pair's target view, so they travel
+all-to-all (`Exchanger.forward_records`): all-gathering them sent every record to every rank and was the
+largest exchange of a step (C4 on 8 GPUs: 3.9 of 26 ms).
 
 Each exchange is an all-gather-v by padding into a buffer that persists between steps (the fold
 programs are read in place by the next phase).  The first time, the blob sizes are gathered first
@@ -85,6 +90,37 @@ class Exchanger:
         self.stride[kind] = self._stride_for(int(sizes.max()))
         return sizes
 
+    REC = 32   # bytes per forward-match record on the wire (FwdRec)
+
+    def forward_records(self, shard):
+        """All-to-all-v of the boundary pairs' match records, after the FORWARD exchange."""
+        torch, dist, world = self.torch, self.dist, self.world
+        send, recv = shard.shard_forward_plan()
+        ns, nr = int(send.sum()) * self.REC, int(recv.sum()) * self.REC
+        inp = self._buf(self.mine, "fwd_send", max(ns, 32))
+        out = self._buf(self.all, "fwd_recv", max(nr, 32))
+        shard.shard_forward_pack(inp.data_ptr(), ns, self.on_gpu)
+        in_split = [int(x) * self.REC for x in send]
+        out_split = [int(x) * self.REC for x in recv]
+        if self.on_gpu:
+            dist.all_to_all_single(out[:nr], inp[:ns], output_split_sizes=out_split, input_split_sizes=in_split)
+        else:   # gloo has no all-to-all: point-to-point per peer
+            ops, io, oo = [], 0, 0
+            me = dist.get_rank()
+            for q in range(world):
+                if in_split[q]:
+                    ops.append(dist.P2POp(dist.isend, inp[io:io + in_split[q]], q))
+                if out_split[q]:
+                    ops.append(dist.P2POp(dist.irecv, out[oo:oo + out_split[q]], q))
+                io += in_split[q]
+                oo += out_split[q]
+            assert in_split[me] == 0 and out_split[me] == 0
+            for w in (dist.batch_isend_irecv(ops) if ops else []):
+                w.wait()
+        shard.shard_forward_unpack(out.data_ptr(), nr, self.on_gpu)
+        self.bytes_gathered += nr
+        return ns, nr
+
     @staticmethod
     def _stride_for(max_payload):
         """Stride of the self-describing exchange: 25 % head room over the largest blob seen."""
@@ -98,6 +134,7 @@ def run_sharded(l3, xch, params, trace=None):
     steps = [("match_stage12", lambda: l3.match_stage12(p["sigma_p"], p["sigma_a"], p["num_neighbors"],
                                                         p["epipolar_overlap"], p["knn"], p["const_reg_depth"])),
              ("x_forward", lambda: xch.exchange(l3, X_FORWARD)),
+             ("x_forward_records", lambda: xch.forward_records(l3)),
              ("score_build", l3.score_build),
              ("x_programs", lambda: xch.exchange(l3, X_PROGRAMS)),
              ("score_fold", l3.score_fold),
@@ -153,12 +190,32 @@ class LocalGroup:
         self.stride[kind] = Exchanger._stride_for(int(sizes.max()))
         return sizes
 
+    def forward_records(self):
+        """The all-to-all of the forward-match records between the shards of this process (host buffers)."""
+        world = len(self.shards)
+        plans = [s.shard_forward_plan() for s in self.shards]
+        packed = []
+        for s, (send, _) in zip(self.shards, plans):
+            buf = np.zeros(max(int(send.sum()) * Exchanger.REC, 1), dtype=np.uint8)
+            s.shard_forward_pack(buf.ctypes.data, int(send.sum()) * Exchanger.REC, False)
+            packed.append(buf)
+        for d, s in enumerate(self.shards):
+            parts = []
+            for q in range(world):
+                send = plans[q][0]
+                assert int(send[d]) == int(plans[d][1][q]), "send / receive plans disagree"
+                o = int(send[:d].sum()) * Exchanger.REC
+                parts.append(packed[q][o:o + int(send[d]) * Exchanger.REC])
+            got = np.ascontiguousarray(np.concatenate(parts)) if parts else np.zeros(0, np.uint8)
+            s.shard_forward_unpack(got.ctypes.data if got.size else 0, int(got.size), False)
+
     def run(self, params):
         p = params
         for s in self.shards:
             s.match_stage12(p["sigma_p"], p["sigma_a"], p["num_neighbors"], p["epipolar_overlap"], p["knn"],
                             p["const_reg_depth"])
         self.exchange(X_FORWARD)
+        self.forward_records()
         for s in self.shards:
             s.score_build()
         self.exchange(X_PROGRAMS)

@@ -274,7 +274,7 @@ int l3d_get_med_scene_depth_lines(l3d_ctx* ctx, float* out);
  * views are split into `shard_world` contiguous slices (l3d_params); a rank matches the pairs whose
  * source view it owns, builds / finishes the scoring rows and the affinity edges of its views, and
  * four exchanges make the results whole again on every rank:
- *   l3d_match_stage12 -> FORWARD -> l3d_score_build -> PROGRAMS -> l3d_score_fold -> HYPOTHESES
+ *   l3d_match_stage12 -> FORWARD (+ forward records all-to-all) -> l3d_score_build -> PROGRAMS -> l3d_score_fold -> HYPOTHESES
  *   -> l3d_affinity_edges -> EDGES -> l3d_affinity_ids (-> l3d_cluster).
  * Per exchange: every rank calls l3d_shard_blob_size + l3d_shard_export, the blobs are all-gathered
  * `stride` bytes apart (stride >= the largest size, multiple of 32), every rank calls
@@ -290,6 +290,14 @@ int l3d_shard_blob_size(l3d_ctx* ctx, int kind, uint64_t* bytes);
 int l3d_shard_export(l3d_ctx* ctx, int kind, void* dst, uint64_t cap_bytes, int device_ptr);
 int l3d_shard_import(l3d_ctx* ctx, int kind, const void* all_blobs, uint64_t stride_bytes, int world,
                      const uint64_t* sizes, int device_ptr);
+/* FORWARD carries the per-row match counts only.  The match RECORDS of a boundary pair (target view in another
+ * slice) are needed by one rank, the owner of the target view, so they travel all-to-all right after the FORWARD
+ * exchange: every rank calls l3d_shard_forward_plan (records it sends to / receives from every peer), packs its
+ * records grouped by destination rank, the groups are exchanged (all-to-all-v, 32 bytes per record), and every rank
+ * unpacks what it received (grouped by source rank, ascending). */
+int l3d_shard_forward_plan(l3d_ctx* ctx, uint64_t* send_records, uint64_t* recv_records);
+int l3d_shard_forward_pack(l3d_ctx* ctx, void* dst, uint64_t cap_bytes, int device_ptr);
+int l3d_shard_forward_unpack(l3d_ctx* ctx, const void* src, uint64_t bytes, int device_ptr);
 /* Steady-state variant without the size exchange (device pointers only): the blob carries a 32-byte
  * header with its own size, written by the device, so the sender never waits for its cursors; the
  * stride comes from the previous step.  *redo != 0 after the import: a blob did not fit -- nothing
