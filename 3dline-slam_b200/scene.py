@@ -99,13 +99,39 @@ def _clip_segment_to_image(p, q, w, h):
     return p + t0 * d, p + t1 * d
 
 
-def _project_world_segments(P1, P2, K, R, t, w, h, near=0.2):
-    """Project world segments, clip against the near plane and the image rectangle."""
+def _project_world_segments(P1, P2, K, R, t, w, h, near=0.2, max_depth=None):
+    """Project world segments, clip against the near plane and the image rectangle.  A vectorised, conservative
+    pre-cull (both end points behind the near plane, or the bounding box of the projected end points outside the
+    image) removes what the per-segment loop below would drop anyway, so the result is unchanged; max_depth
+    (city-scale scenes only) additionally ignores segments farther away than that."""
     X1 = P1 @ R.T + t
     X2 = P2 @ R.T + t
+    z1, z2 = X1[:, 2], X2[:, 2]
+    cand = ~((z1 < near) & (z2 < near))
+    both = (z1 >= near) & (z2 >= near)
+    if both.any():
+        fx, fy, cx, cy = K[0, 0], K[1, 1], K[0, 2], K[1, 2]
+        skew = K[0, 1]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            u1 = (fx * X1[:, 0] + skew * X1[:, 1]) / z1 + cx
+            v1 = fy * X1[:, 1] / z1 + cy
+            u2 = (fx * X2[:, 0] + skew * X2[:, 1]) / z2 + cx
+            v2 = fy * X2[:, 1] / z2 + cy
+        m = 1.0  # one pixel of slack: the loop below decides exactly
+        outside = (np.maximum(u1, u2) < -m) | (np.minimum(u1, u2) > w + m) | (np.maximum(v1, v2) < -m) | \
+                  (np.minimum(v1, v2) > h + m)
+        cand &= ~(both & outside)
+        if max_depth is not None:
+            # city scale: a segment that projects shorter than 8 px cannot reach the 15 px minimum with 0.5 px noise
+            cand &= ~(both & (np.hypot(u1 - u2, v1 - v2) < 8.0))
+    if max_depth is not None:
+        cand &= np.minimum(np.linalg.norm(X1, axis=1), np.linalg.norm(X2, axis=1)) < max_depth
+    idx = np.nonzero(cand)[0]
+    if max_depth is not None:
+        return _project_clip_vectorised(X1[idx], X2[idx], K, w, h, near)
     out = []
     depths = []
-    for a, b in zip(X1, X2):
+    for a, b in zip(X1[idx], X2[idx]):
         if a[2] < near and b[2] < near:
             continue
         if a[2] < near:
@@ -126,8 +152,50 @@ def _project_world_segments(P1, P2, K, R, t, w, h, near=0.2):
     return np.asarray(out, dtype=np.float64).reshape(-1, 4), np.asarray(depths)
 
 
-def _make_view_segments(rng, P1, P2, K, R, t, w, h, n_seg, noise_px, min_len, clutter_med):
-    real, depths = _project_world_segments(P1, P2, K, R, t, w, h)
+def _project_clip_vectorised(A, B, K, w, h, near):
+    """The loop of _project_world_segments in array form (city-scale scenes: thousands of visible segments per view):
+    near-plane clip, pinhole projection, Liang-Barsky clip against the image rectangle."""
+    A, B = A.copy(), B.copy()
+    za, zb = A[:, 2], B[:, 2]
+    keep = ~((za < near) & (zb < near))
+    A, B, za, zb = A[keep], B[keep], za[keep], zb[keep]
+    ca = za < near
+    if ca.any():
+        sa = ((near - za[ca]) / (zb[ca] - za[ca]))[:, None]
+        A[ca] = A[ca] + sa * (B[ca] - A[ca])
+    cb = B[:, 2] < near
+    if cb.any():
+        sb = ((near - B[cb, 2]) / (A[cb, 2] - B[cb, 2]))[:, None]
+        B[cb] = B[cb] + sb * (A[cb] - B[cb])
+    pa = A @ K.T
+    pb = B @ K.T
+    p = pa[:, :2] / pa[:, 2:3]
+    q = pb[:, :2] / pb[:, 2:3]
+    d = q - p
+    t0 = np.zeros(len(p))
+    t1 = np.ones(len(p))
+    ok = np.ones(len(p), dtype=bool)
+    for pk, qk in ((-d[:, 0], p[:, 0]), (d[:, 0], w - p[:, 0]), (-d[:, 1], p[:, 1]), (d[:, 1], h - p[:, 1])):
+        par = np.abs(pk) < 1e-12
+        ok &= ~(par & (qk < 0))
+        with np.errstate(divide="ignore", invalid="ignore"):
+            r = np.where(par, 0.0, qk / np.where(par, 1.0, pk))
+        neg = (~par) & (pk < 0)
+        pos = (~par) & (pk > 0)
+        ok &= ~(neg & (r > t1))
+        t0 = np.where(neg, np.maximum(t0, r), t0)
+        ok &= ~(pos & (r < t0))
+        t1 = np.where(pos, np.minimum(t1, r), t1)
+    ok &= (t1 - t0) > 0
+    c0 = p + t0[:, None] * d
+    c1 = p + t1[:, None] * d
+    out = np.concatenate([c0, c1], axis=1)[ok]
+    depths = 0.5 * (np.linalg.norm(A, axis=1) + np.linalg.norm(B, axis=1))[ok]
+    return out.reshape(-1, 4), depths
+
+
+def _make_view_segments(rng, P1, P2, K, R, t, w, h, n_seg, noise_px, min_len, clutter_med, max_depth=None):
+    real, depths = _project_world_segments(P1, P2, K, R, t, w, h, max_depth=max_depth)
     if real.shape[0]:
         real = real + rng.normal(0.0, noise_px, size=real.shape)
         real[:, 0::2] = np.clip(real[:, 0::2], 0.0, float(w))
@@ -165,6 +233,16 @@ def _nearest_neighbors(centers: np.ndarray, axes: np.ndarray, nbrs: int) -> List
     for i in range(n):
         d = np.linalg.norm(centers - centers[i], axis=1)
         ang_ok = (axes @ axes[i]) > 0.0  # optical-axis angle < pi/2
+        if n > 2000:
+            # large scenes: the nbrs nearest admissible cameras are among the 4*nbrs+8 nearest ones unless many are
+            # inadmissible; fall back to the full sort then (same result, stable order by distance then index)
+            k = min(n - 1, 4 * nbrs + 8)
+            part = np.argpartition(d, k)[:k + 1]
+            part = part[np.lexsort((part, d[part]))]
+            cand = [int(j) for j in part if j != i and ang_ok[j]]
+            if len(cand) >= nbrs and (k + 1 >= n or d[part[-1]] > d[cand[nbrs - 1]]):
+                out.append(sorted(cand[:nbrs]))
+                continue
         cand = [j for j in np.argsort(d, kind="stable") if j != i and ang_ok[j]]
         out.append(sorted(int(j) for j in cand[:nbrs]))
     return out
@@ -255,6 +333,55 @@ def make_scene(kind: str = "c2", n_views: Optional[int] = None, n_seg: Optional[
     params = dict(DEFAULT_PARAMS)
     params["num_neighbors"] = NB
     return Scene(kind, views, max(w, h), params, False)
+
+
+def make_city(n_views: int = 5000, n_seg: int = 5000, nbrs: int = 20, n_world: int = 200000, seed: Optional[int] = None,
+              view_range=None, max_depth: float = 300.0):
+    """BASELINE config 5 (city scale): the "c5" preset's street-grid cameras (2 m spacing) and world segments, with
+    ONE random stream per view so that the views can be generated independently -- every rank of a sharded run
+    generates a slice and the segment tables are all-gathered (the scene tables are replicated).
+    Returns (Scene with empty segment arrays outside view_range, segs (hi-lo, n_seg, 4) float32, median depths).
+    World segments farther than max_depth from the camera are ignored (they would project below the 15 px
+    minimum length anyway: 3 m at 300 m and f = 1500 is 15 px)."""
+    V, N, NB, L = n_views, n_seg, nbrs, n_world
+    w, h, f = 1920, 1080, 1500.0
+    lo_b, hi_b = np.array([-500.0, -500.0, 0.0]), np.array([500.0, 500.0, 30.0])
+    base = (seed if seed is not None else BASE_SEED + 4)
+    rng = np.random.Generator(np.random.PCG64(base))
+    P1, P2 = _world_segments(rng, L, lo_b, hi_b, 3.0)
+    K = np.array([[f, 0, w / 2.0], [0, f, h / 2.0], [0, 0, 1.0]], dtype=np.float64)
+    per_row = max(2, int(round(math.sqrt(V))))
+    centers, Rs = [], []
+    for i in range(V):
+        row, col = divmod(i, per_row)
+        c = np.array([lo_b[0] + 20 + 2.0 * col, lo_b[1] + 20 + 14.0 * row, 1.7])
+        yaw = 0.5 * math.sin(0.11 * i)
+        tgt = c + np.array([math.cos(yaw), math.sin(yaw), 0.1])
+        centers.append(c)
+        Rs.append(look_at(c, tgt))
+    centers = np.asarray(centers)
+    axes = np.asarray([R[2] for R in Rs])
+    nbr_lists = _nearest_neighbors(centers, axes, NB)
+    lo, hi = (0, V) if view_range is None else view_range
+    segs = np.zeros((hi - lo, N, 4), dtype=np.float32)
+    meds = np.zeros(hi - lo, dtype=np.float32)
+    for i in range(lo, hi):
+        vr = np.random.Generator(np.random.PCG64([base, 1000003 + i]))
+        R = Rs[i]
+        t = -R @ centers[i]
+        sg, med = _make_view_segments(vr, P1, P2, K, R, t, w, h, N, 0.5, 15.0, 40.0, max_depth=max_depth)
+        segs[i - lo] = sg
+        meds[i - lo] = med
+    views = []
+    empty = np.zeros((0, 4), dtype=np.float32)
+    for i in range(V):
+        R = Rs[i]
+        own = lo <= i < hi
+        views.append(SceneView(i, K.copy(), R, -R @ centers[i], w, h, float(meds[i - lo]) if own else 1.0,
+                               segs[i - lo] if own else empty, nbr_lists[i]))
+    params = dict(DEFAULT_PARAMS)
+    params["num_neighbors"] = NB
+    return Scene("c5", views, max(w, h), params, False), segs, meds
 
 
 # ----------------------------------------------------------------------------------------------
