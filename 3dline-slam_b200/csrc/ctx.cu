@@ -522,6 +522,12 @@ int plan_pairs(l3d_ctx* ctx)
 int set_params(l3d_ctx* ctx, const l3d_params* params)
 {
     if (!params) return fail(L3D_ERR_ARG, "params is NULL");
+    // the longest match list of the committed scene is cached between runs (score build); it depends on the
+    // matching parameters, so a change invalidates it (a stale, too small value sized the row staging wrongly)
+    if (ctx->have_params && (ctx->prm.knn != params->knn || ctx->prm.epipolar_overlap != params->epipolar_overlap ||
+                             ctx->prm.num_neighbors != params->num_neighbors || ctx->prm.filter_mode != params->filter_mode ||
+                             ctx->prm.max_image_width != params->max_image_width))
+        ctx->k3_list_max = 0;
     ctx->prm = *params;
     l3d_params& p = ctx->prm;
     // parameter clamps of Line3D::matchImages (src/line3D.cc:517-536)

@@ -49,6 +49,22 @@ def test_knn_variants(api, oracle, scene_mod):
         compare_full(l3, orc, sc)
 
 
+def test_rematch_with_other_parameters_on_the_same_context(api, oracle, scene_mod):
+    """A context that is matched again with parameters that make the lists much longer (kNN 10 -> all matches):
+    the cached longest-list size of the first run must not size the second one (it did: illegal memory access,
+    found by tools/sanitize_run.py)."""
+    sc = scene_mod.make_scene("tiny")
+    l3 = api.run_scene(sc, keep_scored=True)
+    for knn in (0, 3):
+        sc.params["knn"] = knn
+        p = sc.params
+        l3.matchImages(p["sigma_p"], p["sigma_a"], p["num_neighbors"], p["epipolar_overlap"], p["knn"], p["const_reg_depth"])
+        l3.reconstruct3Dlines()
+        orc = oracle.run_scene(sc)
+        compare_full(l3, orc, sc)
+        orc.close()
+
+
 @pytest.mark.parametrize("knn", [-1, 40, 10])
 def test_dense_rows_take_the_rare_kernel_paths(api, oracle, scene_mod, knn):
     """Without the pre-filter every target is a candidate: more than 256 candidates per mask chunk
