@@ -518,11 +518,41 @@ int l3d_shard_import(l3d_ctx* ctx, int kind, const void* all, uint64_t stride_by
     return fail(L3D_ERR_ARG, "unknown exchange kind %d", kind);
 }
 
-// ---- FORWARD records, all-to-all.  After the FORWARD exchange (every rank holds all per-row counts):
+// ---- FORWARD records, all-to-all.  After the FORWARD exchange every rank holds all per-row counts, hence the
+// canonical record range of every pair (refresh_pair_totals); the records of a pair are contiguous there.
 //   plan    send_records[d] / recv_records[q]: records this rank sends to rank d / receives from rank q
-//           (0 for itself); reads a world x world matrix back, so it synchronises
-//   pack    this rank's boundary records grouped by destination rank (ascending), rows ascending inside a group
-//   unpack  the received records, grouped by source rank (ascending) = ascending global row, into the canonical store
+//           (0 for itself), summed over the boundary pairs on the host -- no device work
+//   pack    this rank's boundary pairs grouped by destination rank (ascending), pairs ascending inside a group
+//   unpack  the received pairs, grouped by source rank (ascending) = ascending pair index, into the canonical store
+static int owner_of_view(const l3d_ctx* ctx, uint32_t v)
+{
+    int q = 0;
+    while (q + 1 < ctx->world && ctx->slice_view[q + 1] <= v) ++q;
+    return q;
+}
+// copy the record blocks `items` ({src, dst, n}) with one kernel
+static int copy_record_blocks(l3d_ctx* ctx, const std::vector<uint4>& items, const FwdRec* src, FwdRec* dst)
+{
+    if (items.empty()) return L3D_OK;
+    cudaStream_t st = ctx->stream;
+    std::vector<uint32_t> chunk_item, chunk_first(items.size());
+    for (size_t i = 0; i < items.size(); ++i) {
+        chunk_first[i] = (uint32_t)chunk_item.size();
+        for (uint32_t c = 0; c < (items[i].z + 127u) / 128u; ++c) chunk_item.push_back((uint32_t)i);
+    }
+    if (chunk_item.empty()) return L3D_OK;
+    CK(ctx->d_blk_items.ensure(items.size()));
+    CK(ctx->d_blk_chunks.ensure(chunk_item.size() + chunk_first.size()));
+    CK(cudaMemcpyAsync(ctx->d_blk_items.p, items.data(), items.size() * sizeof(uint4), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_blk_chunks.p, chunk_item.data(), chunk_item.size() * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_blk_chunks.p + chunk_item.size(), chunk_first.data(), chunk_first.size() * 4,
+                       cudaMemcpyHostToDevice, st));
+    ctx->cnt.gpu_launches += launch_rec_blocks(ctx->d_blk_items.p, ctx->d_blk_chunks.p, ctx->d_blk_chunks.p + chunk_item.size(),
+                                               (uint32_t)chunk_item.size(), src, dst, st);
+    // the pageable host vectors are staged by the runtime before cudaMemcpyAsync returns
+    return L3D_OK;
+}
+
 int l3d_shard_forward_plan(l3d_ctx* ctx, uint64_t* send_records, uint64_t* recv_records)
 {
     int rc = check_phase(ctx, L3D_X_FORWARD);
@@ -530,18 +560,16 @@ int l3d_shard_forward_plan(l3d_ctx* ctx, uint64_t* send_records, uint64_t* recv_
     if (!send_records || !recv_records) return fail(L3D_ERR_ARG, "NULL argument");
     const int world = ctx->world;
     if (world > L3D_MAX_WORLD_C) return fail(L3D_ERR_ARG, "world %d too large", world);
-    CK(cudaSetDevice(ctx->device));
-    cudaStream_t st = ctx->stream;
-    CK(ctx->d_fwd_plan.ensure((size_t)world * world));
-    CK(cudaMemsetAsync(ctx->d_fwd_plan.p, 0, (size_t)world * world * 8, st));
-    ctx->cnt.gpu_launches += launch_fwd_plan(ctx->d_pairs.p, (uint32_t)ctx->pairs.size(), ctx->d_fwd_cnt.p, ctx->total_rows,
-                                             ctx->slice_row.data(), world, ctx->d_fwd_plan.p, st);
-    std::vector<unsigned long long> M((size_t)world * world);
-    CK(cudaMemcpyAsync(M.data(), ctx->d_fwd_plan.p, M.size() * 8, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    for (int q = 0; q < world; ++q) ctx->fwd_send[q] = ctx->fwd_recv[q] = 0;
+    for (const HostPair& hp : ctx->pairs) {
+        const int so = owner_of_view(ctx, hp.src), to = owner_of_view(ctx, hp.tgt);
+        if (so == to) continue;
+        if (so == ctx->rank) ctx->fwd_send[to] += hp.fwd_total;
+        if (to == ctx->rank) ctx->fwd_recv[so] += hp.fwd_total;
+    }
     for (int q = 0; q < world; ++q) {
-        ctx->fwd_send[q] = send_records[q] = q == ctx->rank ? 0 : M[(size_t)ctx->rank * world + q];
-        ctx->fwd_recv[q] = recv_records[q] = q == ctx->rank ? 0 : M[(size_t)q * world + ctx->rank];
+        send_records[q] = ctx->fwd_send[q];
+        recv_records[q] = ctx->fwd_recv[q];
     }
     ctx->fwd_planned = true;
     return L3D_OK;
@@ -555,33 +583,31 @@ int l3d_shard_forward_pack(l3d_ctx* ctx, void* dst, uint64_t cap_bytes, int devi
     const int world = ctx->world;
     uint64_t total = 0;
     for (int d = 0; d < world; ++d) total += ctx->fwd_send[d];
-    if (total * sizeof(FwdRec) > cap_bytes) return fail(L3D_ERR_CAPACITY, "need %llu bytes", (unsigned long long)(total * sizeof(FwdRec)));
+    if (total * sizeof(FwdRec) > cap_bytes)
+        return fail(L3D_ERR_CAPACITY, "need %llu bytes", (unsigned long long)(total * sizeof(FwdRec)));
     if (!total) return L3D_OK;
     if (!dst) return fail(L3D_ERR_ARG, "NULL argument");
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
-    const uint32_t r0 = ctx->slice_row[ctx->rank], r1 = ctx->slice_row[ctx->rank + 1], rows = r1 - r0;
-    CK(ctx->d_fx_cnt.ensure((size_t)rows + 1));
-    CK(ctx->d_fx_off.ensure((size_t)rows + 2));
-    CK(ctx->d_scan.ensure(scan_scratch_words(rows + 1) + 64));
     FwdRec* out = (FwdRec*)dst;
     DevBuf<FwdRec>& stg = ctx->d_bx_rec;
     if (!device_ptr) {
         CK(stg.ensure((size_t)total + 1));
         out = stg.p;
     }
+    // d_fwd_rec holds the canonical layout since the FORWARD import: this rank's pairs are in place there
+    std::vector<uint4> items;
     uint64_t at = 0;
     for (int d = 0; d < world; ++d) {
         if (!ctx->fwd_send[d]) continue;
-        // d_fwd_rec / d_fwd_off hold the canonical layout since the FORWARD import: own rows are in place there
-        ctx->cnt.gpu_launches += launch_fwd_dmask(ctx->d_pairs.p, (uint32_t)ctx->pairs.size(), ctx->d_fwd_cnt.p, r0, r1,
-                                                  (uint32_t)d, ctx->slice_row.data(), world, -1, ctx->d_fx_cnt.p, st);
-        ctx->cnt.gpu_launches += launch_scan_u32(ctx->d_fx_cnt.p, ctx->d_fx_off.p, rows, ctx->d_scan.p, ctx->d_scan.cap, st);
-        // row-relative views of the offset arrays: the move kernel indexes src_off / dst_off by absolute row
-        ctx->cnt.gpu_launches += launch_fwd_move(ctx->d_fx_cnt.p, r0, r1, ctx->d_fwd_off.p, ctx->d_fwd_rec.p,
-                                                 ctx->d_fx_off.p - r0, out + at, st);
-        at += ctx->fwd_send[d];
+        for (const HostPair& hp : ctx->pairs) {
+            if (!hp.fwd_total || owner_of_view(ctx, hp.src) != ctx->rank || owner_of_view(ctx, hp.tgt) != d) continue;
+            items.push_back(make_uint4(hp.rec_start, (uint32_t)at, (uint32_t)hp.fwd_total, 0u));
+            at += hp.fwd_total;
+        }
     }
+    rc = copy_record_blocks(ctx, items, ctx->d_fwd_rec.p, out);
+    if (rc) return rc;
     if (!device_ptr) {
         CK(cudaMemcpyAsync(dst, stg.p, total * sizeof(FwdRec), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
@@ -597,12 +623,13 @@ int l3d_shard_forward_unpack(l3d_ctx* ctx, const void* src, uint64_t bytes, int 
     const int world = ctx->world;
     uint64_t total = 0;
     for (int q = 0; q < world; ++q) total += ctx->fwd_recv[q];
-    if (bytes != total * sizeof(FwdRec)) return fail(L3D_ERR_ARG, "expected %llu bytes, got %llu", (unsigned long long)(total * sizeof(FwdRec)), (unsigned long long)bytes);
+    if (bytes != total * sizeof(FwdRec))
+        return fail(L3D_ERR_ARG, "expected %llu bytes, got %llu", (unsigned long long)(total * sizeof(FwdRec)),
+                    (unsigned long long)bytes);
     if (!total) return L3D_OK;
     if (!src) return fail(L3D_ERR_ARG, "NULL argument");
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
-    const uint32_t R = ctx->total_rows;
     const FwdRec* in = (const FwdRec*)src;
     if (!device_ptr) {
         DevBuf<unsigned char>& stg = ctx->d_xchg_stage[L3D_X_FORWARD];
@@ -610,17 +637,15 @@ int l3d_shard_forward_unpack(l3d_ctx* ctx, const void* src, uint64_t bytes, int 
         CK(cudaMemcpyAsync(stg.p, src, bytes, cudaMemcpyHostToDevice, st));
         in = (const FwdRec*)stg.p;
     }
-    // received records = the rows of the other ranks whose pair targets a view of this rank, in ascending row
-    CK(ctx->d_bx_cnt_all.ensure((size_t)R + 1));
-    CK(ctx->d_bx_off_all.ensure((size_t)R + 2));
-    CK(ctx->d_scan.ensure(scan_scratch_words(R + 1) + 64));
-    ctx->cnt.gpu_launches += launch_fwd_dmask(ctx->d_pairs.p, (uint32_t)ctx->pairs.size(), ctx->d_fwd_cnt.p, 0, R,
-                                              (uint32_t)ctx->rank, ctx->slice_row.data(), world, ctx->rank,
-                                              ctx->d_bx_cnt_all.p, st);
-    ctx->cnt.gpu_launches += launch_scan_u32(ctx->d_bx_cnt_all.p, ctx->d_bx_off_all.p, R, ctx->d_scan.p, ctx->d_scan.cap, st);
-    ctx->cnt.gpu_launches += launch_fwd_move(ctx->d_bx_cnt_all.p, 0, R, ctx->d_bx_off_all.p, in, ctx->d_fwd_off.p,
-                                             ctx->d_fwd_rec.p, st);
-    return L3D_OK;
+    // pairs are sorted by source view, so "source rank ascending, pairs ascending" is plain pair order
+    std::vector<uint4> items;
+    uint64_t at = 0;
+    for (const HostPair& hp : ctx->pairs) {
+        if (!hp.fwd_total || owner_of_view(ctx, hp.tgt) != ctx->rank || owner_of_view(ctx, hp.src) == ctx->rank) continue;
+        items.push_back(make_uint4((uint32_t)at, hp.rec_start, (uint32_t)hp.fwd_total, 0u));
+        at += hp.fwd_total;
+    }
+    return copy_record_blocks(ctx, items, in, ctx->d_fwd_rec.p);
 }
 
 // sizes_out[q] = payload bytes of rank q; *redo != 0: some blob did not fit / some program store

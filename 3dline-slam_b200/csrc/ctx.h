@@ -35,10 +35,7 @@ int launch_fwd_bgather(const uint32_t*, const uint32_t*, const uint32_t*, uint32
 int launch_fwd_place(const unsigned char*, uint64_t, int, const uint32_t*, int, uint32_t, const uint32_t*,
                      const uint32_t*, const uint32_t*, const uint32_t*, const FwdRec*, const uint32_t*, FwdRec*,
                      cudaStream_t);
-int launch_fwd_plan(const PairDev*, uint32_t, const uint32_t*, uint32_t, const uint32_t*, int, unsigned long long*,
-                    cudaStream_t);
-int launch_fwd_dmask(const PairDev*, uint32_t, const uint32_t*, uint32_t, uint32_t, uint32_t, const uint32_t*, int, int,
-                     uint32_t*, cudaStream_t);
+int launch_rec_blocks(const uint4*, const uint32_t*, const uint32_t*, uint32_t, const FwdRec*, FwdRec*, cudaStream_t);
 int launch_fwd_move(const uint32_t*, uint32_t, uint32_t, const uint32_t*, const FwdRec*, const uint32_t*, FwdRec*,
                     cudaStream_t);
 int launch_k3_list_capacity(const ViewDev*, const uint32_t*, uint32_t, const IncDev*, const uint32_t*, const PairDev*,
@@ -312,8 +309,8 @@ struct l3d_ctx {
     uint64_t xchg_var[4] = {0, 0, 0, 0};
     uint64_t fwd_send[L3D_MAX_WORLD_C] = {0}, fwd_recv[L3D_MAX_WORLD_C] = {0};  // FORWARD records per peer (forward_plan)
     bool fwd_planned = false;
-    DevBuf<unsigned long long> d_fwd_plan;
-    DevBuf<uint32_t> d_fx_cnt, d_fx_off;
+    DevBuf<uint4> d_blk_items;
+    DevBuf<uint32_t> d_blk_chunks;
     DevBuf<unsigned char> d_xchg_stage[4];
     DevBuf<uint32_t> d_slice_g;
     uint64_t shard_sim_evals = 0, shard_scored = 0, shard_filtered = 0;

@@ -177,46 +177,7 @@ __global__ void __launch_bounds__(256) fwd_bgather_kernel(const uint32_t* __rest
     FwdRec* dst = out + boff[row - row_lo];
     for (uint32_t e = 0; e < n; ++e) dst[e] = src[e];
 }
-// ---- FORWARD records by destination (abi.cu: l3d_shard_forward_plan / pack / unpack): a boundary pair's records
-// are needed by ONE other rank, the owner of its target view (PairDev::xflag - 1), so they travel all-to-all ----
-struct SliceRows17 {
-    uint32_t row[17];
-};
-__device__ __forceinline__ int owner_of_row(const SliceRows17& sl, int world, uint32_t row)
-{
-    int q = 0;
-    while (q + 1 < world && sl.row[q + 1] <= row) ++q;
-    return q;
-}
-// M[owner * world + dest] += records of the row (boundary rows only)
-__global__ void __launch_bounds__(256) fwd_plan_kernel(const PairDev* __restrict__ pairs, uint32_t P,
-                                                       const uint32_t* __restrict__ fwd_cnt, uint32_t n_rows,
-                                                       SliceRows17 sl, int world, unsigned long long* __restrict__ M)
-{
-    const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
-    if (row >= n_rows) return;
-    const uint32_t n = fwd_cnt[row];
-    if (!n) return;
-    const uint32_t xf = pairs[pair_of_row_m(pairs, P, row)].xflag;
-    if (!xf) return;
-    atomicAdd(&M[owner_of_row(sl, world, row) * world + (int)(xf - 1u)], (unsigned long long)n);
-}
-// cnt[row - row_lo] = records of the row that go to rank `dest` (rows of one owner) / that rank `me` receives
-// (all rows: owner != me, dest == me)
-__global__ void __launch_bounds__(256) fwd_dmask_kernel(const PairDev* __restrict__ pairs, uint32_t P,
-                                                        const uint32_t* __restrict__ fwd_cnt, uint32_t row_lo,
-                                                        uint32_t row_hi, uint32_t dest, SliceRows17 sl, int world,
-                                                        int skip_owner, uint32_t* __restrict__ out)
-{
-    const uint32_t row = row_lo + blockIdx.x * blockDim.x + threadIdx.x;
-    if (row >= row_hi) return;
-    const uint32_t n = fwd_cnt[row];
-    uint32_t v = 0;
-    if (n && pairs[pair_of_row_m(pairs, P, row)].xflag == dest + 1u &&
-        (skip_owner < 0 || owner_of_row(sl, world, row) != skip_owner))
-        v = n;
-    out[row - row_lo] = v;
-}
+// ---- FORWARD records (abi.cu): own rows into the canonical layout; pair blocks for the all-to-all ----
 // copies the rows' records: src_off / dst_off index the two stores, n from cnt (0 = skip)
 __global__ void __launch_bounds__(256) fwd_move_kernel(const uint32_t* __restrict__ cnt, uint32_t row_lo, uint32_t row_hi,
                                                        const uint32_t* __restrict__ src_off, const FwdRec* __restrict__ src,
@@ -230,23 +191,25 @@ __global__ void __launch_bounds__(256) fwd_move_kernel(const uint32_t* __restric
     FwdRec* b = dst + dst_off[row];
     for (uint32_t e = 0; e < n; ++e) b[e] = a[e];
 }
-int launch_fwd_plan(const PairDev* pairs, uint32_t P, const uint32_t* fwd_cnt, uint32_t n_rows, const uint32_t* slice_row,
-                    int world, unsigned long long* M, cudaStream_t st)
+// copies record blocks: item i = {src record, dst record, count}; one CTA per (item, 128-record chunk), two threads per 32-byte record
+__global__ void __launch_bounds__(256) rec_blocks_kernel(const uint4* __restrict__ items, const uint32_t* __restrict__ chunk_item,
+                                                         const uint32_t* __restrict__ chunk_first,
+                                                         const FwdRec* __restrict__ src, FwdRec* __restrict__ dst)
 {
-    if (!n_rows) return 0;
-    SliceRows17 sl;
-    for (int q = 0; q < 17; ++q) sl.row[q] = q <= world ? slice_row[q] : 0xffffffffu;
-    fwd_plan_kernel<<<(n_rows + 255) / 256, 256, 0, st>>>(pairs, P, fwd_cnt, n_rows, sl, world, M);
-    return 1;
+    const uint32_t it = chunk_item[blockIdx.x];
+    const uint4 b = items[it];
+    const uint32_t k = (blockIdx.x - chunk_first[it]) * 128u + (threadIdx.x >> 1);
+    if (k >= b.z) return;
+    // 32-byte records as two 16-byte halves per thread pair
+    const uint4* s4 = reinterpret_cast<const uint4*>(src + b.x + k) + (threadIdx.x & 1);
+    uint4* d4 = reinterpret_cast<uint4*>(dst + b.y + k) + (threadIdx.x & 1);
+    *d4 = *s4;
 }
-int launch_fwd_dmask(const PairDev* pairs, uint32_t P, const uint32_t* fwd_cnt, uint32_t row_lo, uint32_t row_hi,
-                     uint32_t dest, const uint32_t* slice_row, int world, int skip_owner, uint32_t* out, cudaStream_t st)
+int launch_rec_blocks(const uint4* items, const uint32_t* chunk_item, const uint32_t* chunk_first, uint32_t n_chunks,
+                      const FwdRec* src, FwdRec* dst, cudaStream_t st)
 {
-    if (row_hi <= row_lo) return 0;
-    SliceRows17 sl;
-    for (int q = 0; q < 17; ++q) sl.row[q] = q <= world ? slice_row[q] : 0xffffffffu;
-    fwd_dmask_kernel<<<(row_hi - row_lo + 255) / 256, 256, 0, st>>>(pairs, P, fwd_cnt, row_lo, row_hi, dest, sl, world,
-                                                                     skip_owner, out);
+    if (!n_chunks) return 0;
+    rec_blocks_kernel<<<n_chunks, 256, 0, st>>>(items, chunk_item, chunk_first, src, dst);
     return 1;
 }
 int launch_fwd_move(const uint32_t* cnt, uint32_t row_lo, uint32_t row_hi, const uint32_t* src_off, const FwdRec* src,
