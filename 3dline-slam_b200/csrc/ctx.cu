@@ -79,7 +79,8 @@ int l3d_scene_begin(l3d_ctx* ctx)
     return L3D_OK;
 }
 
-static int add_view(l3d_ctx* ctx, const l3d_view* view, const float* segs, const uint32_t* nbrs, uint32_t nn, bool wps);
+static int add_view(l3d_ctx* ctx, const l3d_view* view, const float* segs, const uint32_t* nbrs, uint32_t nn, bool wps,
+                    bool copy_segs = true);
 
 int l3d_scene_add_view(l3d_ctx* ctx, const l3d_view* view, const float* segs, const uint32_t* nbrs, uint32_t nn)
 {
@@ -93,7 +94,8 @@ int l3d_scene_add_view_wps(l3d_ctx* ctx, const l3d_view* view, const float* segs
     return add_view(ctx, view, segs, wps, nw, true);
 }
 
-static int add_view(l3d_ctx* ctx, const l3d_view* view, const float* segs, const uint32_t* nbrs, uint32_t nn, bool wps)
+static int add_view(l3d_ctx* ctx, const l3d_view* view, const float* segs, const uint32_t* nbrs, uint32_t nn, bool wps,
+                    bool copy_segs)
 {
     if (!ctx || !view) return fail(L3D_ERR_ARG, "NULL argument");
     if (ctx->committed) return fail(L3D_ERR_STATE, "scene already committed; call l3d_scene_begin");
@@ -111,7 +113,10 @@ static int add_view(l3d_ctx* ctx, const l3d_view* view, const float* segs, const
     if (view->num_segs == 0 || !segs) return fail(L3D_ERR_ARG, "no line segments found in image [%u]!", view->cam_id);
     HostView hv;
     hv.v = *view;
-    hv.segs.assign(segs, segs + 4 * (size_t)view->num_segs);
+    // l3d_scene_set commits inside the same call: the segments go from the caller's buffer straight into the pinned
+    // staging (one host copy instead of two); the staging keeps them readable for the TXT writer
+    if (copy_segs) hv.segs.assign(segs, segs + 4 * (size_t)view->num_segs);
+    else hv.ext_segs = segs;
     if (wps) hv.wps.assign(nbrs, nbrs + nn);
     else hv.nbrs.assign(nbrs, nbrs + nn);
     hv.cam.init(view->K, view->R, view->t);
@@ -140,7 +145,7 @@ static int scene_set(l3d_ctx* ctx, const l3d_view* views, uint32_t n_views, cons
     if (rc) return rc;
     size_t so = 0, no = 0;
     for (uint32_t i = 0; i < n_views; ++i) {
-        rc = add_view(ctx, &views[i], segs_concat + 4 * so, nbrs_concat + no, nbr_counts[i], wps);
+        rc = add_view(ctx, &views[i], segs_concat + 4 * so, nbrs_concat + no, nbr_counts[i], wps, false);
         if (rc) return rc;
         so += views[i].num_segs;
         no += nbr_counts[i];
@@ -187,8 +192,9 @@ int l3d_scene_commit(l3d_ctx* ctx)
     float4* hseg = (float4*)ctx->pinned;
     uint32_t* seg_view = (uint32_t*)(hseg + std::max<size_t>(S, 1));
     for (uint32_t v = 0; v < V; ++v) {
-        const HostView& hv = ctx->views[v];
-        memcpy(hseg + hv.seg_off, hv.segs.data(), hv.segs.size() * sizeof(float));
+        HostView& hv = ctx->views[v];
+        memcpy(hseg + hv.seg_off, hv.ext_segs ? hv.ext_segs : hv.segs.data(), (size_t)hv.v.num_segs * sizeof(float4));
+        hv.ext_segs = nullptr;
         std::fill(seg_view + hv.seg_off, seg_view + hv.seg_off + hv.v.num_segs, v);
     }
     CK(ctx->d_segs.ensure(S));
@@ -1516,7 +1522,8 @@ int l3d_save_lines3D_txt(l3d_ctx* ctx, const char* path)
             const uint32_t cam = ctx->l3_res[2 * (size_t)r], seg = ctx->l3_res[2 * (size_t)r + 1];
             file << cam << " " << seg << " ";
             const HostView& hv = ctx->views[ctx->cam2view[cam]];
-            const float* c = &hv.segs[4 * (size_t)seg];
+            // batch scenes keep their segments in the pinned staging of the commit, stream scenes per view
+            const float* c = hv.segs.empty() ? (const float*)ctx->pinned + 4 * ((size_t)hv.seg_off + seg) : &hv.segs[4 * (size_t)seg];
             file << c[0] << " " << c[1] << " ";
             file << c[2] << " " << c[3] << " ";
         }

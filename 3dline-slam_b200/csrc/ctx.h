@@ -127,6 +127,7 @@ static inline cudaError_t ensure_roomy(DevBuf<T>& b, size_t n, size_t floor, siz
 struct HostView {
     l3d_view v;
     std::vector<float> segs;
+    const float* ext_segs = nullptr;  // l3d_scene_set: the caller's buffer, valid until the commit inside the same call
     std::vector<uint32_t> nbrs;
     std::vector<uint32_t> nb_views;  // neighbours as ascending view indices (l3d_scene_commit / plan_pairs)
     std::vector<uint32_t> wps;       // observed world points (neighbors_by_worldpoints mode)

@@ -365,7 +365,7 @@ def bench_stream(args, scene_mod, emit=True):
 
 
 # SASS instruction count of K1's unrolled pair-test loop per test (profiles/r2_k1_sass.md)
-K1_ISSUED_PER_TEST = 35.5
+K1_ISSUED_PER_TEST = 38.0
 K2_FLOP_PER_CANDIDATE = 330.0  # SURVEY.md section 8(d) / DESIGN.md section 4.2: FP64 flop per K1 candidate
 
 
