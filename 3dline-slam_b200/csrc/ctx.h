@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <list>
 #include <map>
@@ -101,6 +102,9 @@ struct DevBuf {
         size_t ncap = std::max(n, cap + cap / 2);
         T* np = nullptr;
         cudaError_t e = cudaMalloc((void**)&np, std::max<size_t>(ncap, 1) * sizeof(T));
+        if (getenv("L3D_MEM_DEBUG") && ncap * sizeof(T) >= ((size_t)256 << 20))   // where the HBM goes (capacity planning)
+            fprintf(stderr, "[mem] %.2f GB = %zu x %zu B (%s)\n", ncap * sizeof(T) / 1073741824.0, ncap, sizeof(T),
+                    __PRETTY_FUNCTION__);
         if (e != cudaSuccess) return e;
         if (keep && p) {
             e = cudaMemcpyAsync(np, p, keep * sizeof(T), cudaMemcpyDeviceToDevice, st);

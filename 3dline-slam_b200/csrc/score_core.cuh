@@ -33,11 +33,13 @@ __device__ __forceinline__ float sim_for_scoring(float Md1, float Md2, float reg
     const float x1 = fd(n1, reg1);
     const float x2 = fd(n2, reg2);
     if (x1 < xcut || x2 < xcut) return 0.0f;
-    const float sim_p = fminf(det_expf(x1), det_expf(x2));
-    if (sim_p <= pcut) return 0.0f;
+    // the direction test before the two exponentials of the position term: both orders return 0 for the same
+    // pairs (each early exit is certain on its own), and the dot product is the cheaper one
     const float dot_p = (float)dot3(dirM, d3(dir2[0], dir2[1], dir2[2]));
     // |dot| < cos(angle_cut + 0.01 deg) => angle > angle_cut => -angle^2/two_sigA_sqr < -0.70 => sim_a < 0.4966
     if (fabsf(dot_p) < dotcut) return 0.0f;
+    const float sim_p = fminf(det_expf(x1), det_expf(x2));
+    if (sim_p <= pcut) return 0.0f;
     float angle = (float)dm(dd((double)det_acosf(fmaxf(fminf(dot_p, 1.0f), -1.0f)), L3D_PI), (double)180.0f);
     if (angle > 90.0f) angle = fs(180.0f, angle);
     const float sim_a = det_expf(fd(fm(-angle, angle), two_sigA_sqr));
