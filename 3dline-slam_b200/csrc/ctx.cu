@@ -599,6 +599,10 @@ int run_stage12_batches(l3d_ctx* ctx)
         CK(grow(ctx->d_fin_cnt, (size_t)max_rows + 1));
         CK(grow(ctx->d_fin_off, (size_t)max_rows + 1));
         CK(grow(ctx->d_row_epi, (size_t)max_rows + 1));
+        CK(grow(ctx->d_row_epi_nat, (size_t)max_rows + 1));
+        CK(grow(ctx->d_row_key, (size_t)max_rows + 1));
+        CK(grow(ctx->d_perm, (size_t)max_rows + 1));
+        CK(grow(ctx->d_iperm, (size_t)max_rows + 1));
         CK(grow(ctx->d_ncont, (size_t)max_rows + 1));
         CK(grow(ctx->d_fb_rows, (size_t)max_rows + 1));
         CK(grow(ctx->d_row_pair, (size_t)max_rows + 1));
@@ -623,8 +627,11 @@ int run_stage12_batches(l3d_ctx* ctx)
         cudaEvent_t e1 = ctx->tm.begin(L3D_T_PAIRTEST, st);
         cudaEvent_t ek = ctx->tm.begin(L3D_T_K1_KERNEL, st);
         ctx->cnt.gpu_launches +=
-            launch_k1_pairtest(ctx->d_pairs.p, ctx->d_ctas.p + b.cta0, b.n_ctas, ctx->d_segs.p, ctx->d_desc.p,
-                               ctx->d_view_xb.p, ctx->d_mask.p, ctx->d_cand_cnt.p, ctx->d_row_epi.p, ctx->epi_overlap,
+            launch_k1_rowsort(ctx->d_pairs.p, ctx->d_ctas.p + b.cta0, b.n_ctas, ctx->d_segs.p, ctx->d_view_xb.p,
+                              ctx->d_row_epi_nat.p, ctx->d_row_epi.p, ctx->d_row_key.p, ctx->d_perm.p, ctx->d_iperm.p, st);
+        ctx->cnt.gpu_launches +=
+            launch_k1_pairtest(ctx->d_pairs.p, ctx->d_ctas.p + b.cta0, b.n_ctas, ctx->d_desc.p, ctx->d_row_epi.p,
+                               ctx->d_row_key.p, ctx->d_perm.p, ctx->d_mask.p, ctx->d_cand_cnt.p, ctx->epi_overlap,
                                ctx->prm.filter_mode, st);
         ctx->tm.end(ek, st);
         ctx->tm.ms[L3D_T_K1_LAUNCHES] += 1.0f;
@@ -644,7 +651,7 @@ int run_stage12_batches(l3d_ctx* ctx)
         int uses_ncont = 0;
         ctx->cnt.gpu_launches +=
             launch_k2_exact(ctx->d_pairs.p, ctx->d_ctas.p + b.cta0, b.n_ctas, b.n_rows, n_cand, ctx->d_segs.p,
-                            ctx->d_rays.p, ctx->d_midray.p, ctx->d_planes.p, ctx->d_v32.p, ctx->d_desc.p, ctx->d_row_epi.p,
+                            ctx->d_rays.p, ctx->d_midray.p, ctx->d_planes.p, ctx->d_v32.p, ctx->d_desc.p, ctx->d_row_epi.p, ctx->d_perm.p, ctx->d_iperm.p,
                             ctx->d_views.p, ctx->d_mask.p, ctx->d_cand_off.p, ctx->d_heap.p, ctx->d_cand_rec.p,
                             ctx->d_fin_rec.p, ctx->d_fin_cnt.p, ctx->d_ncont.p, ctx->d_k2ctr.p, ctx->d_fb_rows.p, ctx->d_row_pair.p, ctx->d_row_T.p,
                             ctx->epi_overlap, ctx->prm.knn, ctx->prm.max_image_width, ctx->raw_mode ? 0 : 1, ctx->n_sm,
@@ -744,6 +751,7 @@ static K3Tables k3_tables(l3d_ctx* ctx)
     t.filt_off = ctx->d_filt_off.p; t.filt_cnt = ctx->d_filt_cnt.p; t.entries = ctx->d_entries.p;
     t.stats = ctx->d_stats.p; t.S = ctx->S; t.maxm = ctx->k3_maxm; t.two_sigA_sqr = ctx->two_sigA_sqr;
     t.g_lo = ctx->slice_g[ctx->rank]; t.g_hi = ctx->slice_g[ctx->rank + 1];
+    t.cls = ctx->d_k3_cls.p;
     return t;
 }
 
@@ -852,6 +860,21 @@ int l3d_score_build(l3d_ctx* ctx)
         CK(ctx->d_L_c.ensure(Lcap + S + 2));
         CK(ctx->d_L_h.ensure(Lcap + S + 2));
     }
+    if (getenv("L3D_K3_DEBUG")) {  // histogram of the potential-list lengths (debugging aid)
+        std::vector<uint32_t> ub(S);
+        CK(cudaMemcpyAsync(ub.data(), ctx->d_L_ub.p, (size_t)S * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        const uint32_t edges[] = {0, 16, 32, 64, 128, 256, 512, 1024, 2048, 0xffffffffu};
+        uint64_t n[10] = {0}, sm[10] = {0}, sq[10] = {0};
+        for (uint32_t g = 0; g < S; ++g) {
+            int b = 0;
+            while (ub[g] > edges[b]) ++b;
+            n[b]++; sm[b] += ub[g]; sq[b] += (uint64_t)ub[g] * ub[g];
+        }
+        for (int b = 0; b < 10; ++b)
+            if (n[b]) fprintf(stderr, "[k3] len<=%u rows %llu sum %llu sumsq %llu\n", edges[b], (unsigned long long)n[b],
+                              (unsigned long long)sm[b], (unsigned long long)sq[b]);
+    }
     ctx->k3_maxm = maxm;
     ctx->k3_big_rows = big_rows;
     ctx->filt_cap = 2 * F + 1;
@@ -866,6 +889,7 @@ int l3d_score_build(l3d_ctx* ctx)
     CK(ctx->d_prog_off.ensure((size_t)S + 1));
     CK(ctx->d_prog_nh.ensure((size_t)S + 1));
     const uint32_t my_rows = ctx->slice_g[ctx->rank + 1] - ctx->slice_g[ctx->rank];
+    CK(ctx->d_k3_cls.ensure(k3_class_words(my_rows)));
     if (ctx->prog_cap == 0) ctx->prog_cap = std::max<uint64_t>(24ull * my_rows + 1024, 4096);
     if (ctx->prog_cap > 0xfffffff0ull) return fail(L3D_ERR_CAPACITY, "fold programs too large");
     CK(ctx->d_prog.ensure(ctx->prog_cap * 16));

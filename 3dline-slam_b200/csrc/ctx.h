@@ -18,12 +18,10 @@
 
 namespace l3d {
 // launchers defined in the other translation units
-int launch_k1_pairtest(const PairDev*, const K1Cta*, uint32_t, const float4*, const SegDesc*, const float*, uint32_t*,
-                       uint32_t*, RowEpi32*, float, int, cudaStream_t);
 int k1_rows_per_cta();
 int launch_k2_exact(const PairDev*, const K1Cta*, uint32_t, uint32_t, uint32_t, const float4*, const SegRays*,
-                    const double*, const SegPlane*, const SegV32*, const SegDesc*, const RowEpi32*, const ViewDev*,
-                    const uint32_t*, const uint32_t*, unsigned long long*, FwdRec*, FwdRec*, uint32_t*, uint32_t*, uint32_t*,
+                    const double*, const SegPlane*, const SegV32*, const SegDesc*, const RowEpi32*, const uint32_t*, const uint32_t*,
+                    const ViewDev*, const uint32_t*, const uint32_t*, unsigned long long*, FwdRec*, FwdRec*, uint32_t*, uint32_t*, uint32_t*,
                     uint2*, uint32_t*, float*, float, int, int, int, int, int*, cudaStream_t);
 int launch_k2_compact(const uint32_t*, const uint32_t*, const uint32_t*, uint32_t, const FwdRec*, FwdRec*, uint32_t*,
                       uint32_t, const uint32_t*, cudaStream_t);
@@ -259,7 +257,10 @@ struct l3d_ctx {
     DevBuf<double> d_midray;
     DevBuf<SegPlane> d_planes;
     DevBuf<SegV32> d_v32;          // FP32 image of rays / planes (K2's certified depth-sign test)
-    DevBuf<RowEpi32> d_row_epi;    // K1's per-row epipolar lines of the current batch
+    DevBuf<RowEpi32> d_row_epi;    // K1's per-row epipolar lines of the current batch, in K1's sorted row order
+    DevBuf<RowEpi32> d_row_epi_nat;  // the same in natural row order (staging of the row sort)
+    DevBuf<float2> d_row_key;      // direction keys of the row's two lines (sorted row order)
+    DevBuf<uint32_t> d_perm, d_iperm;  // sorted position -> natural row and back (batch-local)
     DevBuf<uint32_t> d_ncont, d_k2ctr;  // K2: contenders per batch row; {work items, fallback rows}
     DevBuf<uint2> d_fb_rows;       // K2: rows handed to the literal row kernel
     DevBuf<uint32_t> d_row_pair;   // K2: pair of every batch row
@@ -271,7 +272,7 @@ struct l3d_ctx {
     DevBuf<K1Cta> d_ctas;
     DevBuf<IncDev> d_inc;
     // stage 1/2 scratch
-    DevBuf<uint32_t> d_mask, d_cand_cnt, d_cand_off, d_fin_cnt, d_fin_off, d_scan;
+    DevBuf<uint32_t> d_mask, d_cand_cnt, d_cand_off, d_fin_cnt, d_fin_off, d_scan, d_k3_cls;
     DevBuf<unsigned long long> d_heap;
     DevBuf<FwdRec> d_cand_rec, d_fin_rec;
     // forward store

@@ -141,7 +141,9 @@ struct K3Tables {
     uint32_t* filt_off; uint32_t* filt_cnt; EntryDev* entries; void* stats;
     uint32_t S, maxm; float two_sigA_sqr;
     uint32_t g_lo, g_hi;  // rows (global segment indices) this rank builds and finishes
+    uint32_t* cls;        // build: 16 counters + 3 row lists (k3_class_words(g_hi - g_lo) words)
 };
+size_t k3_class_words(uint32_t rows);
 int launch_k3_build(const K3Tables& t, cudaStream_t st, int* err);
 int launch_k3_fold(const K3Tables& t, cudaStream_t st, int* err);
 int launch_k3_finish(const K3Tables& t, cudaStream_t st);
@@ -196,8 +198,13 @@ int launch_k6_lines3d(uint32_t n_clusters, const uint32_t* cl_off, const uint32_
                       unsigned char* okflag, uint32_t* camtab, uint32_t* out_n, uint32_t* out_ref, double* out_seg,
                       cudaStream_t st);
 
-int launch_k1_pairtest(const PairDev* pairs, const K1Cta* ctas, uint32_t n_ctas, const float4* segs,
-                       const SegDesc* desc, const float* view_xb, uint32_t* mask, uint32_t* cand_cnt,
-                       RowEpi32* row_epi, float thr, int filter_mode, cudaStream_t st);
+// K1: rows of every pair sorted by the direction of their epipolar lines (k1_pairtest.cu); epi_rho / key_rho /
+// the mask are in sorted ("rho") order, perm[rho] = natural row, iperm[natural row] = rho (batch-local indices)
+int launch_k1_rowsort(const PairDev* pairs, const K1Cta* ctas, uint32_t n_ctas, const float4* segs,
+                      const float* view_xb, RowEpi32* epi_nat, RowEpi32* epi_rho, float2* key_rho, uint32_t* perm,
+                      uint32_t* iperm, cudaStream_t st);
+int launch_k1_pairtest(const PairDev* pairs, const K1Cta* ctas, uint32_t n_ctas, const SegDesc* desc,
+                       const RowEpi32* epi_rho, const float2* key_rho, const uint32_t* perm, uint32_t* mask,
+                       uint32_t* cand_cnt, float thr, int filter_mode, cudaStream_t st);
 
 }  // namespace l3d

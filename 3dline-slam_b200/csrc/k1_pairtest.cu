@@ -16,6 +16,8 @@
 // One CTA = 256 source rows of one pair; target descriptors (32 B each) are streamed through
 // shared memory in 512-entry tiles with TMA bulk copies (cp.async.bulk) on a two-stage
 // mbarrier pipeline; every lane reads the same descriptor (shared-memory broadcast).
+#include <cstdlib>
+
 #include "internal.h"
 #include "tma.cuh"
 
@@ -73,15 +75,209 @@ __device__ __forceinline__ bool pair_candidate(const RowEpi& e, const float4 d0,
     return !rej;
 }
 
+// ------------------------------------------------------------------------------------------
+// row order.  All epipolar lines of a pair pass through one point (the epipole), and a target segment can only
+// overlap a source row if it reaches into the wedge between the row's two lines.  The rows of a pair are
+// therefore SORTED by the direction of their lines before the test kernel runs: the 32 rows of a warp then span a
+// narrow wedge (their "hull"), and a target segment that lies outside that wedge by more than half a pixel is
+// skipped for the whole warp (k1_pairtest_kernel below).  The order only decides which tests are skipped -- any
+// permutation gives the same mask -- so the sort keys may be as coarse as they like; what the skip test needs
+// to be sound is stated next to it.
+//
+// One CTA sorts one chunk of up to KS_N rows of one pair:
+//   * per row, in double: the two normalised epipolar lines (src/line3D.cc:1113-1121), with their signs chosen
+//     so that the normals of all lines of the pair lie in one half plane (n.g >= 0, g = the direction at right
+//     angles to the one from the epipole towards the image: no line that crosses the image comes near n.g = 0
+//     unless the epipole is inside the image); the direction key t = n.g' (the sine of the angle to g), which
+//     is monotone in the direction over that half plane and, for a distant epipole, a small number whose float
+//     image keeps its relative precision;
+//   * sort key: width class (log2 of the row's wedge against the mean, 8 classes) above the quantised wedge
+//     centre -- wide rows would otherwise widen the hull of every warp they land in;
+//   * bitonic sort in shared memory; the rows' line records, keys and the permutation (both ways) are written
+//     in sorted ("rho") order.  K1's mask and K2's front kernel work in rho order; everything else keeps the
+//     natural row order through perm / iperm.
+// ------------------------------------------------------------------------------------------
+static constexpr int KS_N = 4096;  // rows per sort chunk = 16 K1 tiles
+static constexpr int KS_THREADS = 512;
+
+__global__ void __launch_bounds__(KS_THREADS) k1_rowsort_kernel(const PairDev* __restrict__ pairs,
+                                                                 const K1Cta* __restrict__ ctas,
+                                                                 const float4* __restrict__ segs,
+                                                                 const float* __restrict__ view_xb,
+                                                                 RowEpi32* __restrict__ epi_nat,
+                                                                 RowEpi32* __restrict__ epi_rho,
+                                                                 float2* __restrict__ key_rho,
+                                                                 uint32_t* __restrict__ perm,
+                                                                 uint32_t* __restrict__ iperm, int sort_on)
+{
+    extern __shared__ __align__(16) unsigned char ks_raw[];  // 64 KB: above the static limit
+    unsigned long long* sk = reinterpret_cast<unsigned long long*>(ks_raw);
+    float2* skey = reinterpret_cast<float2*>(ks_raw + sizeof(unsigned long long) * KS_N);
+    __shared__ float red_lo[KS_THREADS / 32], red_hi[KS_THREADS / 32], red_w[KS_THREADS / 32];
+    __shared__ uint32_t red_n[KS_THREADS / 32];
+    __shared__ double s_g[2];
+    const K1Cta cta = ctas[blockIdx.x];
+    if (cta.tile % (KS_N / K1_ROWS)) return;  // one sort CTA per chunk: the K1 CTA list is reused as its grid
+    const PairDev& P = pairs[cta.pair];
+    const uint32_t r0 = (cta.tile / (KS_N / K1_ROWS)) * KS_N;
+    const uint32_t n = min((uint32_t)KS_N, P.n_src - r0);
+    const uint32_t lbase = P.row_base - P.batch_row0 + r0;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double* F = P.F;
+    if (tid == 0) {
+        // the epipole e (e^T F = 0) is at right angles to every column of F: the cross product of the two columns
+        // that give the longest one
+        const double c0[3] = {F[0], F[3], F[6]}, c1[3] = {F[1], F[4], F[7]}, c2[3] = {F[2], F[5], F[8]};
+        const double* cols[3] = {c0, c1, c2};
+        double best[3] = {0, 0, 0}, bn = -1.0;
+        for (int a = 0; a < 3; ++a) {
+            const double* u = cols[a];
+            const double* v = cols[(a + 1) % 3];
+            const double x = u[1] * v[2] - u[2] * v[1], y = u[2] * v[0] - u[0] * v[2], z = u[0] * v[1] - u[1] * v[0];
+            const double nn = x * x + y * y + z * z;
+            if (nn > bn) { bn = nn; best[0] = x; best[1] = y; best[2] = z; }
+        }
+        // direction from the epipole towards the middle of the image, d = c e_w - e_xy (sign-free), g at right angles
+        const double cx = 0.25 * (double)view_xb[P.tgt_view], cy = cx;  // xb bounds |x| + |y|
+        double dx = cx * best[2] - best[0], dy = cy * best[2] - best[1];
+        const double dn = sqrt(dx * dx + dy * dy);
+        if (dn > 0.0 && dn < 1e300) { dx /= dn; dy /= dn; } else { dx = 1.0; dy = 0.0; }
+        s_g[0] = -dy;
+        s_g[1] = dx;
+    }
+    __syncthreads();
+    const double gx = s_g[0], gy = s_g[1];
+    const float xb = view_xb[P.tgt_view];
+    const float pinf = __int_as_float(0x7f800000);
+    float clo = pinf, chi = -pinf, wsum = 0.0f;
+    uint32_t nval = 0;
+    for (uint32_t i = tid; i < n; i += KS_THREADS) {
+        const float4 sg = segs[P.src_off + r0 + i];
+        const double p1x = sg.x, p1y = sg.y, p2x = sg.z, p2y = sg.w;
+        double a1 = F[0] * p1x + F[1] * p1y + F[2], b1 = F[3] * p1x + F[4] * p1y + F[5], c1 = F[6] * p1x + F[7] * p1y + F[8];
+        double a2 = F[0] * p2x + F[1] * p2y + F[2], b2 = F[3] * p2x + F[4] * p2y + F[5], c2 = F[6] * p2x + F[7] * p2y + F[8];
+        const double n1 = sqrt(a1 * a1 + b1 * b1), n2 = sqrt(a2 * a2 + b2 * b2);
+        a1 /= n1; b1 /= n1; c1 /= n1;
+        a2 /= n2; b2 /= n2; c2 /= n2;
+        // s = -N / D is unchanged by the sign of a line: choose it so that n.g >= 0
+        if (a1 * gx + b1 * gy < 0.0) { a1 = -a1; b1 = -b1; c1 = -c1; }
+        if (a2 * gx + b2 * gy < 0.0) { a2 = -a2; b2 = -b2; c2 = -c2; }
+        const double t1 = b1 * gx - a1 * gy, t2 = b2 * gx - a2 * gy;  // n.g', g' = (-gy, gx)
+        RowEpi32 re;
+        re.A1 = (float)a1; re.B1 = (float)b1; re.C1 = (float)c1;
+        re.A2 = (float)a2; re.B2 = (float)b2; re.C2 = (float)c2;
+        const float u8 = 8.0f * 5.9604645e-08f;
+        const float cN = u8 * (xb + fmaxf(fabsf(re.C1), fabsf(re.C2)));
+        const float chk = re.A1 + re.B1 + re.C1 + re.A2 + re.B2 + re.C2;
+        const bool degenerate = !(fabsf(chk) < 3.0e38f);  // NaN or Inf anywhere
+        // K2's FP32 ranking re-uses the row's lines; a degenerate row carries NaN bounds (nothing is certified)
+        re.cN = degenerate ? __int_as_float(0x7fc00000) : cN;
+        re.nmin = (float)fmin(n1, n2);
+        epi_nat[lbase + i] = re;
+        float2 k = make_float2((float)t1, (float)t2);
+        if (degenerate) k = make_float2(__int_as_float(0x7fc00000), __int_as_float(0x7fc00000));
+        skey[i] = k;
+        if (!degenerate) {
+            const float c = 0.5f * (k.x + k.y);
+            clo = fminf(clo, c);
+            chi = fmaxf(chi, c);
+            wsum += fabsf(k.x - k.y);
+            ++nval;
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        clo = fminf(clo, __shfl_xor_sync(0xffffffffu, clo, d));
+        chi = fmaxf(chi, __shfl_xor_sync(0xffffffffu, chi, d));
+        wsum += __shfl_xor_sync(0xffffffffu, wsum, d);
+        nval += __shfl_xor_sync(0xffffffffu, nval, d);
+    }
+    if (lane == 0) { red_lo[warp] = clo; red_hi[warp] = chi; red_w[warp] = wsum; red_n[warp] = nval; }
+    __syncthreads();
+    clo = red_lo[0]; chi = red_hi[0]; wsum = red_w[0]; nval = red_n[0];
+    for (int w = 1; w < KS_THREADS / 32; ++w) {
+        clo = fminf(clo, red_lo[w]);
+        chi = fmaxf(chi, red_hi[w]);
+        wsum += red_w[w];
+        nval += red_n[w];
+    }
+    const float wmean = nval ? wsum / (float)nval : 0.0f;
+    const float cscale = (chi > clo) ? (float)((1u << 29) - 1u) / (chi - clo) : 0.0f;
+    uint32_t np2 = 32;
+    while (np2 < n) np2 <<= 1;
+    for (uint32_t i = tid; i < np2; i += KS_THREADS) {
+        unsigned long long v = ~0ull;
+        if (i < n) {
+            const float2 k = skey[i];
+            uint32_t key = 0xffffffffu;  // degenerate rows last
+            if (k.x == k.x && sort_on) {
+                const float w = fabsf(k.x - k.y), c = 0.5f * (k.x + k.y);
+                int cls = 0;
+                if (wmean > 0.0f && w > 0.0f) cls = min(7, max(0, (int)floorf(__log2f(w / wmean)) + 3));
+                const uint32_t q = (uint32_t)fminf(fmaxf((c - clo) * cscale, 0.0f), (float)((1u << 29) - 1u));
+                key = ((uint32_t)cls << 29) | q;
+            } else if (!sort_on) {
+                key = 0u;  // ties keep the row index order (the index is the low word)
+            }
+            v = ((unsigned long long)key << 32) | i;
+        }
+        sk[i] = v;
+    }
+    __syncthreads();
+    if (sort_on)
+        for (uint32_t k = 2; k <= np2; k <<= 1)
+            for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+                for (uint32_t t = tid; t < (np2 >> 1); t += KS_THREADS) {
+                    const uint32_t i = 2 * t - (t & (j - 1));
+                    const unsigned long long a = sk[i], b = sk[i + j];
+                    const bool asc = (i & k) == 0;
+                    if ((a > b) == asc) {
+                        sk[i] = b;
+                        sk[i + j] = a;
+                    }
+                }
+                __syncthreads();
+            }
+    for (uint32_t i = tid; i < n; i += KS_THREADS) {
+        const uint32_t idx = (uint32_t)(sk[i] & 0xffffffffull);
+        perm[lbase + i] = r0 + idx;
+        iperm[lbase + idx] = r0 + i;
+        epi_rho[lbase + i] = epi_nat[lbase + idx];  // written by this CTA before the barriers above
+        key_rho[lbase + i] = skey[idx];
+    }
+}
+
+// Hull test of one target segment against the wedge of a warp's rows, hull lines (Al, Bl, Cl) and (Ah, Bh, Ch)
+// (the rows' lines with the smallest / largest direction key; every other line of the warp is a combination
+// a Hl + b Hh with a, b >= 0, a + b >= 1, because all lines pass through the epipole and their normals lie in one
+// half plane).  With f(x) the signed distance of x to a line: if f_l and f_h are both > m (or both < -m) at both
+// end points of the target segment, every line e of the warp has |f_e| >= m on the whole segment, so neither
+// of a row's two intersection parameters lies in [-m, L + m]; if in addition the slopes D_l and D_h (and with
+// them D_e, which lies between them) have one sign, both parameters lie on the SAME side: inner = min(hi, L) -
+// max(lo, 0) <= -m, the reference's overlap is 0 and the pair is no match.  m = 0.5 px: the float roundings of
+// the lines, of N, D and L D (each below 1e-2 px on image coordinates, see pair_candidate) and the lines not
+// being exactly concurrent after rounding are far below it.  Every comparison is false for NaN: NaN never skips.
+__device__ __forceinline__ bool hull_skips(float Al, float Bl, float Cl, float Ah, float Bh, float Ch, const float4 d0,
+                                           float L)
+{
+    const float Nl = fmaf(Al, d0.x, fmaf(Bl, d0.y, Cl)), Dl = fmaf(Al, d0.z, Bl * d0.w);
+    const float Nh = fmaf(Ah, d0.x, fmaf(Bh, d0.y, Ch)), Dh = fmaf(Ah, d0.z, Bh * d0.w);
+    const float Nl2 = fmaf(L, Dl, Nl), Nh2 = fmaf(L, Dh, Nh);
+    const float mn = fminf(fminf(Nl, Nl2), fminf(Nh, Nh2)), mx = fmaxf(fmaxf(Nl, Nl2), fmaxf(Nh, Nh2));
+    const bool outside = (mn > 0.5f) | (mx < -0.5f);
+    const bool slopes = (Dl * Dh > 0.0f) & (fminf(fabsf(Dl), fabsf(Dh)) > 1.0e-5f);
+    return outside & slopes;
+}
+
 __global__ void __launch_bounds__(K1_ROWS) k1_pairtest_kernel(const PairDev* __restrict__ pairs,
                                                               const K1Cta* __restrict__ ctas,
-                                                              const float4* __restrict__ segs,
                                                               const SegDesc* __restrict__ desc,
-                                                              const float* __restrict__ view_xb,
+                                                              const RowEpi32* __restrict__ epi_rho,
+                                                              const float2* __restrict__ key_rho,
+                                                              const uint32_t* __restrict__ perm,
                                                               uint32_t* __restrict__ mask,
-                                                              uint32_t* __restrict__ cand_cnt,
-                                                              RowEpi32* __restrict__ row_epi, float thr,
-                                                              int filter_mode)
+                                                              uint32_t* __restrict__ cand_cnt, float thr,
+                                                              int filter_mode, int hull_on)
 {
     __shared__ __align__(128) float4 tile[2][K1_TILE * 2];
     __shared__ __align__(8) uint64_t bars[2];
@@ -89,8 +285,9 @@ __global__ void __launch_bounds__(K1_ROWS) k1_pairtest_kernel(const PairDev* __r
     const K1Cta cta = ctas[blockIdx.x];
     const PairDev& P = pairs[cta.pair];
     const uint32_t n_src = P.n_src, n_tgt = P.n_tgt;
-    const uint32_t r = cta.tile * K1_ROWS + threadIdx.x;
-    const bool row_ok = r < n_src;
+    const uint32_t rho = cta.tile * K1_ROWS + threadIdx.x;  // position in the sorted row order
+    const bool row_ok = rho < n_src;
+    const uint32_t lane = threadIdx.x & 31;
     const SegDesc* __restrict__ tdesc = desc + P.tgt_off;
 
     if (threadIdx.x == 0) {
@@ -107,41 +304,51 @@ __global__ void __launch_bounds__(K1_ROWS) k1_pairtest_kernel(const PairDev* __r
         tma_load_1d(&tile[0][0], tdesc, cnt * 32u, &bars[0]);
     }
 
-    // ---- per-row set-up: epipolar lines in double, normalised, rounded to float ----
+    // ---- the row's lines (k1_rowsort_kernel) and the hull of the warp ----
     RowEpi e;
     e.degenerate = false;
     e.A1 = e.B1 = e.C1 = e.A2 = e.B2 = e.C2 = 0.0f;
     e.cN = 0.0f;
-    float nmin = 0.0f;
+    uint32_t lrow = 0;
+    const float pinf = __int_as_float(0x7f800000);
+    float klo = pinf, khi = -pinf;
+    bool first_lo = true;
     if (row_ok) {
-        const float4 sg = segs[P.src_off + r];
-        const double p1x = sg.x, p1y = sg.y, p2x = sg.z, p2y = sg.w;
-        const double* F = P.F;
-        const double a1 = F[0] * p1x + F[1] * p1y + F[2], b1 = F[3] * p1x + F[4] * p1y + F[5],
-                     c1 = F[6] * p1x + F[7] * p1y + F[8];
-        const double a2 = F[0] * p2x + F[1] * p2y + F[2], b2 = F[3] * p2x + F[4] * p2y + F[5],
-                     c2 = F[6] * p2x + F[7] * p2y + F[8];
-        const double n1 = sqrt(a1 * a1 + b1 * b1), n2 = sqrt(a2 * a2 + b2 * b2);
-        e.A1 = (float)(a1 / n1); e.B1 = (float)(b1 / n1); e.C1 = (float)(c1 / n1);
-        e.A2 = (float)(a2 / n2); e.B2 = (float)(b2 / n2); e.C2 = (float)(c2 / n2);
-        const float xb = view_xb[P.tgt_view];
-        const float u8 = 8.0f * 5.9604645e-08f;
-        e.cN = u8 * (xb + fmaxf(fabsf(e.C1), fabsf(e.C2)));
-        const float chk = e.A1 + e.B1 + e.C1 + e.A2 + e.B2 + e.C2;
-        e.degenerate = !(fabsf(chk) < 3.0e38f);  // NaN or Inf anywhere
-        nmin = (float)fmin(n1, n2);
-        // K2's FP32 ranking re-uses the row's lines; a degenerate row carries NaN bounds (nothing is certified)
-        RowEpi32 re;
-        re.A1 = e.A1; re.B1 = e.B1; re.C1 = e.C1; re.A2 = e.A2; re.B2 = e.B2; re.C2 = e.C2;
-        re.cN = e.degenerate ? __int_as_float(0x7fc00000) : e.cN;
-        re.nmin = nmin;
-        row_epi[P.row_base - P.batch_row0 + r] = re;
+        const uint32_t lrho = P.row_base - P.batch_row0 + rho;
+        const RowEpi32 re = epi_rho[lrho];
+        e.A1 = re.A1; e.B1 = re.B1; e.C1 = re.C1; e.A2 = re.A2; e.B2 = re.B2; e.C2 = re.C2;
+        e.degenerate = !(re.cN == re.cN);
+        e.cN = e.degenerate ? 0.0f : re.cN;
+        lrow = P.row_base - P.batch_row0 + perm[lrho];
+        const float2 k = key_rho[lrho];
+        first_lo = k.x <= k.y;
+        klo = fminf(k.x, k.y);
+        khi = fmaxf(k.x, k.y);
     }
     const float k2thr = 2.0f * (1.0f + thr);
     const bool all_pass = (filter_mode != 0) | e.degenerate;
+    // hull lines: the line with the smallest key and the one with the largest key among the warp's rows
+    float wlo = klo, whi = khi;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        wlo = fminf(wlo, __shfl_xor_sync(0xffffffffu, wlo, d));
+        whi = fmaxf(whi, __shfl_xor_sync(0xffffffffu, whi, d));
+    }
+    const uint32_t own_lo = __ffs(__ballot_sync(0xffffffffu, row_ok && klo == wlo)) - 1;
+    const uint32_t own_hi = __ffs(__ballot_sync(0xffffffffu, row_ok && khi == whi)) - 1;
+    // no skipping unless every row of the warp has finite keys and the wedge is well below a half turn (keys are
+    // sines of the angle to g: a span of 1 is at most 90 degrees)
+    const bool hull_ok = hull_on && !__any_sync(0xffffffffu, row_ok && (all_pass || !(khi - klo >= 0.0f))) &&
+                         (whi - wlo < 1.0f) && own_lo < 32u && own_hi < 32u;
+    const float lA = first_lo ? e.A1 : e.A2, lB = first_lo ? e.B1 : e.B2, lC = first_lo ? e.C1 : e.C2;
+    const float hA = first_lo ? e.A2 : e.A1, hB = first_lo ? e.B2 : e.B1, hC = first_lo ? e.C2 : e.C1;
+    const float Al = __shfl_sync(0xffffffffu, lA, own_lo & 31u), Bl = __shfl_sync(0xffffffffu, lB, own_lo & 31u),
+                Cl = __shfl_sync(0xffffffffu, lC, own_lo & 31u);
+    const float Ah = __shfl_sync(0xffffffffu, hA, own_hi & 31u), Bh = __shfl_sync(0xffffffffu, hB, own_hi & 31u),
+                Ch = __shfl_sync(0xffffffffu, hC, own_hi & 31u);
 
     uint32_t total = 0;
-    uint32_t* __restrict__ mrow = mask + P.mask_base + r;
+    uint32_t* __restrict__ mrow = mask + P.mask_base + rho;
 
     for (uint32_t t = 0; t < ntiles; ++t) {
         const uint32_t buf = t & 1;
@@ -157,42 +364,65 @@ __global__ void __launch_bounds__(K1_ROWS) k1_pairtest_kernel(const PairDev* __r
         const uint32_t base = t * K1_TILE;
         const uint32_t cnt = min((uint32_t)K1_TILE, n_tgt - base);
         const float4* __restrict__ tl = tile[buf];
-        if (row_ok) {
-            const uint32_t nwords = (cnt + 31) / 32;
-            for (uint32_t w = 0; w < nwords; ++w) {
-                const uint32_t j0 = w * 32;
-                const uint32_t nj = min(32u, cnt - j0);
-                uint32_t bits = 0;
-                if (all_pass) {
-                    bits = (nj == 32) ? 0xffffffffu : ((1u << nj) - 1u);
-                } else if (nj == 32) {
-#pragma unroll 8
-                    for (uint32_t j = 0; j < 32; ++j) {
-                        const float4 d0 = tl[2 * (j0 + j)], d1 = tl[2 * (j0 + j) + 1];
-                        bits |= (pair_candidate(e, d0, d1, thr, k2thr) ? 1u : 0u) << j;
-                    }
-                } else {
-                    for (uint32_t j = 0; j < nj; ++j) {
-                        const float4 d0 = tl[2 * (j0 + j)], d1 = tl[2 * (j0 + j) + 1];
-                        bits |= (pair_candidate(e, d0, d1, thr, k2thr) ? 1u : 0u) << j;
-                    }
-                }
+        const uint32_t nwords = (cnt + 31) / 32;
+        for (uint32_t w = 0; w < nwords; ++w) {  // warp-uniform
+            const uint32_t j0 = w * 32;
+            const uint32_t nj = min(32u, cnt - j0);
+            const uint32_t full = (nj == 32) ? 0xffffffffu : ((1u << nj) - 1u);
+            // which of the 32 targets the warp has to test: lane j looks at target j0 + j
+            uint32_t need = full;
+            if (hull_ok) {
+                bool skip = true;
+                if (lane < nj) skip = hull_skips(Al, Bl, Cl, Ah, Bh, Ch, tl[2 * (j0 + lane)], tl[2 * (j0 + lane) + 1].x);
+                need = __ballot_sync(0xffffffffu, !skip) & full;
+            }
+            uint32_t bits = 0;
+            while (need) {
+                const uint32_t j = __ffs(need) - 1;
+                need &= need - 1;
+                const float4 d0 = tl[2 * (j0 + j)], d1 = tl[2 * (j0 + j) + 1];
+                bits |= (pair_candidate(e, d0, d1, thr, k2thr) ? 1u : 0u) << j;
+            }
+            if (all_pass) bits = full;
+            if (row_ok) {
                 mrow[(size_t)((base >> 5) + w) * n_src] = bits;
                 total += __popc(bits);
             }
         }
         __syncthreads();  // everyone is done with tile[buf] before it is refilled
     }
-    if (row_ok) cand_cnt[P.row_base - P.batch_row0 + r] = total;
+    if (row_ok) cand_cnt[lrow] = total;
 }
 
-int launch_k1_pairtest(const PairDev* pairs, const K1Cta* ctas, uint32_t n_ctas, const float4* segs,
-                       const SegDesc* desc, const float* view_xb, uint32_t* mask, uint32_t* cand_cnt,
-                       RowEpi32* row_epi, float thr, int filter_mode, cudaStream_t st)
+int launch_k1_rowsort(const PairDev* pairs, const K1Cta* ctas, uint32_t n_ctas, const float4* segs,
+                      const float* view_xb, RowEpi32* epi_nat, RowEpi32* epi_rho, float2* key_rho, uint32_t* perm,
+                      uint32_t* iperm, cudaStream_t st)
 {
     if (n_ctas == 0) return 0;
-    k1_pairtest_kernel<<<n_ctas, K1_ROWS, 0, st>>>(pairs, ctas, segs, desc, view_xb, mask, cand_cnt, row_epi,
-                                                    thr, filter_mode);
+    static int sort_on = -1;
+    if (sort_on < 0) {
+        const char* ev = getenv("L3D_K1_SORT");  // 0: keep the natural row order (A/B runs)
+        sort_on = ev ? atoi(ev) : 1;
+    }
+    const size_t smem = (sizeof(unsigned long long) + sizeof(float2)) * KS_N;
+    cudaFuncSetAttribute(k1_rowsort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k1_rowsort_kernel<<<n_ctas, KS_THREADS, smem, st>>>(pairs, ctas, segs, view_xb, epi_nat, epi_rho, key_rho, perm, iperm,
+                                                      sort_on);
+    return 1;
+}
+
+int launch_k1_pairtest(const PairDev* pairs, const K1Cta* ctas, uint32_t n_ctas, const SegDesc* desc,
+                       const RowEpi32* epi_rho, const float2* key_rho, const uint32_t* perm, uint32_t* mask,
+                       uint32_t* cand_cnt, float thr, int filter_mode, cudaStream_t st)
+{
+    if (n_ctas == 0) return 0;
+    static int hull_on = -1;
+    if (hull_on < 0) {
+        const char* ev = getenv("L3D_K1_HULL");  // 0: test every pair (A/B runs)
+        hull_on = ev ? atoi(ev) : 1;
+    }
+    k1_pairtest_kernel<<<n_ctas, K1_ROWS, 0, st>>>(pairs, ctas, desc, epi_rho, key_rho, perm, mask, cand_cnt, thr,
+                                                    filter_mode, hull_on);
     return 1;
 }
 

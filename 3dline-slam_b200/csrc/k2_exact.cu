@@ -208,7 +208,8 @@ __global__ void __launch_bounds__(K2_WARPS * 32) k2_row_kernel(
     const uint32_t* __restrict__ cand_off, const float4* __restrict__ segs, const SegRays* __restrict__ rays,
     const double* __restrict__ midray, const SegPlane* __restrict__ planes, const ViewDev* __restrict__ views,
     unsigned long long* __restrict__ heap, FwdRec* __restrict__ cand_rec, FwdRec* __restrict__ fin_rec, uint32_t* __restrict__ fin_cnt, float thr, double W,
-    int knn, int apply_orient, const uint2* __restrict__ fb_rows, const uint32_t* __restrict__ ctr)
+    int knn, int apply_orient, const uint2* __restrict__ fb_rows, const uint32_t* __restrict__ ctr,
+    const uint32_t* __restrict__ iperm)
 {
     __shared__ K2WarpSmem wsm[K2_WARPS];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -246,7 +247,7 @@ __global__ void __launch_bounds__(K2_WARPS * 32) k2_row_kernel(
         unsigned long long* __restrict__ hscr = reinterpret_cast<unsigned long long*>(cand_rec + base);
         uint32_t* __restrict__ gsel = reinterpret_cast<uint32_t*>(hscr + (cand_off[lrow + 1] - base));
         FwdRec* __restrict__ frec = fin_rec + base;
-        const uint32_t* __restrict__ mrow = mask + P.mask_base + r;
+        const uint32_t* __restrict__ mrow = mask + P.mask_base + iperm[lrow];  // the mask is in K1's sorted row order
 
         // row constants (src/line3D.cc:1113-1121)
         const float4 sg = segs[P.src_off + r];
@@ -635,8 +636,9 @@ __global__ void __launch_bounds__(K2_ROWS, 2) k2_front_kernel(
     const PairDev* __restrict__ pairs, const K1Cta* __restrict__ ctas, const uint32_t* __restrict__ mask,
     const uint32_t* __restrict__ cand_off, const SegV32* __restrict__ v32, const SegDesc* __restrict__ desc,
     const SegPlane* __restrict__ planes, const ViewDev* __restrict__ views, const RowEpi32* __restrict__ row_epi,
-    float thr, int knn, uint2* __restrict__ cand_rc, float* __restrict__ cand_u, uint32_t* __restrict__ ncont,
-    uint32_t* __restrict__ row_pair, float* __restrict__ row_T, uint32_t* __restrict__ work, uint32_t* __restrict__ ctr)
+    const uint32_t* __restrict__ perm, float thr, int knn, uint2* __restrict__ cand_rc, float* __restrict__ cand_u,
+    uint32_t* __restrict__ ncont, uint32_t* __restrict__ row_pair, float* __restrict__ row_T, uint32_t* __restrict__ work,
+    uint32_t* __restrict__ ctr)
 {
     extern __shared__ __align__(128) unsigned char k2f_raw[];
     K2FSmem& S = *reinterpret_cast<K2FSmem*>(k2f_raw);
@@ -644,7 +646,11 @@ __global__ void __launch_bounds__(K2_ROWS, 2) k2_front_kernel(
     const PairDev& P = pairs[cta.pair];
     const uint32_t n_src = P.n_src, n_tgt = P.n_tgt, words = P.words;
     const uint32_t tid = threadIdx.x;
-    const uint32_t r = cta.tile * K2_ROWS + tid;
+    // thread = position rho in K1's sorted row order (the mask and the line records are in that order: coalesced,
+    // and neighbouring lanes see similar candidate sets); r = the natural row everything else is indexed by
+    const uint32_t rho = cta.tile * K2_ROWS + tid;
+    const uint32_t lrho = P.row_base - P.batch_row0 + (rho < n_src ? rho : 0u);
+    const uint32_t r = rho < n_src ? perm[lrho] : n_src;
     const uint32_t lane = tid & 31;
     const float ninf = __int_as_float(0xff800000), pinf = __int_as_float(0x7f800000);
     constexpr bool prune = KT > 0;
@@ -672,7 +678,7 @@ __global__ void __launch_bounds__(K2_ROWS, 2) k2_front_kernel(
         // the row's own plane against the target centre, in the exact sequence: its sign is known exactly
         const SegPlane plB = planes[P.src_off + r];
         const double numB = ds(plB.cn, dot3(ld3(plB.n), Ct));
-        R.e = row_epi[lrow];
+        R.e = row_epi[lrho];
         R.rp1x = sv.r1x; R.rp1y = sv.r1y; R.rp1z = sv.r1z; R.rp2x = sv.r2x; R.rp2y = sv.r2y; R.rp2z = sv.r2z;
         R.nBx = sv.nx; R.nBy = sv.ny; R.nBz = sv.nz;
         R.Csx = (float)vs.C[0]; R.Csy = (float)vs.C[1]; R.Csz = (float)vs.C[2];
@@ -680,7 +686,7 @@ __global__ void __launch_bounds__(K2_ROWS, 2) k2_front_kernel(
         R.sB = numB > 1e-9 ? 1.0f : (numB < -1e-9 ? -1.0f : 0.0f);
         row_pair[lrow] = cta.pair;
     }
-    const uint32_t* __restrict__ mrow = mask + P.mask_base + (r < n_src ? r : 0u);
+    const uint32_t* __restrict__ mrow = mask + P.mask_base + (rho < n_src ? rho : 0u);
 
     // sorted insertion network in registers; the first KT - kNN entries are +inf, so its last entry is the
     // kNN-th largest certain lower bound seen so far
@@ -1030,7 +1036,7 @@ __global__ void __launch_bounds__(256) k2_compact_kernel(const uint32_t* __restr
 // *uses_ncont tells the compaction whether ncont is meaningful.
 int launch_k2_exact(const PairDev* pairs, const K1Cta* ctas, uint32_t n_ctas, uint32_t n_rows, uint32_t n_cand,
                     const float4* segs, const SegRays* rays, const double* midray, const SegPlane* planes,
-                    const SegV32* v32, const SegDesc* desc, const RowEpi32* row_epi,
+                    const SegV32* v32, const SegDesc* desc, const RowEpi32* row_epi, const uint32_t* perm, const uint32_t* iperm,
                     const ViewDev* views, const uint32_t* mask, const uint32_t* cand_off, unsigned long long* heap, FwdRec* cand_rec,
                     FwdRec* fin_rec, uint32_t* fin_cnt, uint32_t* ncont, uint32_t* ctr, uint2* fb_rows, uint32_t* row_pair, float* row_T, float thr, int knn,
                     int max_image_width, int apply_orient, int n_sm, int* uses_ncont, cudaStream_t st)
@@ -1043,7 +1049,7 @@ int launch_k2_exact(const PairDev* pairs, const K1Cta* ctas, uint32_t n_ctas, ui
     if (variant == 0) {
         k2_row_kernel<false><<<n_ctas * (K2_ROWS / K2_SUB), K2_WARPS * 32, 0, st>>>(
             pairs, ctas, mask, cand_off, segs, rays, midray, planes, views, heap, cand_rec, fin_rec, fin_cnt, thr,
-            (double)max_image_width, knn, apply_orient, nullptr, nullptr);
+            (double)max_image_width, knn, apply_orient, nullptr, nullptr, iperm);
         return 1;
     }
     *uses_ncont = 1;
@@ -1059,7 +1065,7 @@ int launch_k2_exact(const PairDev* pairs, const K1Cta* ctas, uint32_t n_ctas, ui
     auto front = [&](auto kernel) {
         // per device and cheap: set on every launch (a process may hold contexts on several GPUs)
         cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K2FSmem));
-        kernel<<<n_ctas, K2_ROWS, sizeof(K2FSmem), st>>>(pairs, ctas, mask, cand_off, v32, desc, planes, views, row_epi, thr, knn,
+        kernel<<<n_ctas, K2_ROWS, sizeof(K2FSmem), st>>>(pairs, ctas, mask, cand_off, v32, desc, planes, views, row_epi, perm, thr, knn,
                                                           cand_rc, cand_u, ncont, row_pair, row_T, work, ctr);
     };
     if (knn <= 0 || knn > K2_TOPK) front(k2_front_kernel<0>);
@@ -1077,7 +1083,7 @@ int launch_k2_exact(const PairDev* pairs, const K1Cta* ctas, uint32_t n_ctas, ui
     // rows the fast path could not decide (ties among the popped matches, very long rows): usually none
     k2_row_kernel<true><<<n_sm, K2_WARPS * 32, 0, st>>>(pairs, ctas, mask, cand_off, segs, rays, midray, planes, views, heap,
                                                        cand_rec, fin_rec, fin_cnt, thr, (double)max_image_width, knn,
-                                                       apply_orient, fb_rows, ctr);
+                                                       apply_orient, fb_rows, ctr, iperm);
     return 5;
 }
 

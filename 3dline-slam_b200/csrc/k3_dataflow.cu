@@ -28,6 +28,7 @@
 // A sibling with similarity 0 never changes score3D_ (x + 0 = x; 0 > stored is false; a later
 // s > 0 of the same camera gives (score - 0) + s, the same value as a first add), so only pairs
 // that pass the cheap certain-reject test are evaluated and folded.
+#include <algorithm>
 #include <cstdlib>
 
 #include "internal.h"
@@ -37,7 +38,6 @@ namespace l3d {
 
 #define L3D_EPS 1e-12
 static constexpr uint32_t NOIDX = 0xffffffffu;
-static constexpr int DF_THREADS = 64;
 static constexpr int DF_MAXINC = 64;      // incident pairs of one view
 static constexpr int DF_MAXM_CAP = 2048;  // potential entries staged in shared memory at most
 static constexpr uint32_t DF_SPIN_LIMIT = 1u << 22;
@@ -213,7 +213,6 @@ struct BuildArgs {
     WfStats* stats;
     uint32_t S;
     uint32_t g_lo, g_hi;  // rows built by this rank (global segment indices)
-    uint32_t m_lo, m_hi;  // this launch builds the rows with m_lo < length <= m_hi
     uint32_t maxm;
     float two_sigA_sqr;
     float dotcut;  // see score_core.cuh
@@ -243,20 +242,12 @@ static constexpr int DF_MASKM = 256;  // rows up to this length keep their flag 
                                       // between the count and emit passes (maskw words per entry)
 static constexpr int DF_SMALL = 128;  // rows up to this length are built by a launch with small staging
 
-__global__ void __launch_bounds__(DF_THREADS, 16) k3_build_kernel(const BuildArgs a)
+// one row (global segment g) by one CTA of NT threads; every early return is CTA-uniform
+template <int NT>
+__device__ __forceinline__ void build_row(const BuildArgs& a, const uint32_t g, unsigned char* df_smem, BlockTab& bt,
+                                          uint32_t* s_tot, uint32_t& s_base)
 {
-    extern __shared__ __align__(16) unsigned char df_smem[];
-    __shared__ BlockTab bt;
-    __shared__ uint32_t s_tot[2], s_base;
-    const uint32_t g = a.g_lo + blockIdx.x;
-    if (g >= a.g_hi) return;
-    {
-        const uint32_t len = a.L_off[g + 1] - a.L_off[g];
-        if (len <= a.m_lo || len > a.m_hi) {
-            if (len == 0 && a.m_lo == 0 && threadIdx.x == 0) a.prog_nh[g] = 0u;
-            return;  // another launch (or nothing) handles this row
-        }
-    }
+    constexpr int DF_THREADS = NT;
     const uint32_t v = a.seg_view[g];
     const ViewDev& va = a.views[v];
     const uint32_t i = g - va.seg_off;
@@ -528,6 +519,47 @@ __global__ void __launch_bounds__(DF_THREADS, 16) k3_build_kernel(const BuildArg
         const float sim = sim_for_scoring(M.d_p1, M.d_p2, rg.x, rg.y, true, dirM, sib[j], dirs + 3 * j, a.two_sigA_sqr,
                                           0.5f, -0.70f, 0.5f, a.dotcut);
         prs[t].y = __float_as_uint(sim);
+    }
+}
+
+// rows by length class (the launcher gives every class its own staging size and CTA width); empty rows
+// are closed here
+__global__ void __launch_bounds__(256) k3_classify_kernel(const uint32_t* __restrict__ L_off, uint32_t g_lo,
+                                                          uint32_t g_hi, uint32_t b0, uint32_t b1,
+                                                          uint32_t* __restrict__ cls_cnt, uint32_t* __restrict__ cls_rows,
+                                                          uint32_t* __restrict__ prog_nh)
+{
+    const uint32_t g = g_lo + blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31, rows = g_hi - g_lo;
+    int cls = -1;
+    if (g < g_hi) {
+        const uint32_t len = L_off[g + 1] - L_off[g];
+        if (len == 0) prog_nh[g] = 0u;
+        else cls = len <= b0 ? 0 : (len <= b1 ? 1 : 2);
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const uint32_t bal = __ballot_sync(0xffffffffu, cls == c);
+        if (!bal) continue;
+        uint32_t base = 0;
+        if (lane == (uint32_t)(__ffs(bal) - 1)) base = atomicAdd(&cls_cnt[c], (uint32_t)__popc(bal));
+        base = __shfl_sync(0xffffffffu, base, __ffs(bal) - 1);
+        if (cls == c) cls_rows[(size_t)c * rows + base + __popc(bal & ((1u << lane) - 1u))] = g;
+    }
+}
+
+// persistent CTAs: CTA b takes the rows b, b + gridDim.x, ... of its class
+template <int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) k3_build_kernel(const BuildArgs a, const uint32_t* __restrict__ cls_cnt,
+                                                            const uint32_t* __restrict__ cls_rows)
+{
+    extern __shared__ __align__(16) unsigned char df_smem[];
+    __shared__ BlockTab bt;
+    __shared__ uint32_t s_tot[2], s_base;
+    const uint32_t n = *cls_cnt;
+    for (uint32_t x = blockIdx.x; x < n; x += gridDim.x) {
+        build_row<NT>(a, cls_rows[x], df_smem, bt, s_tot, s_base);
+        __syncthreads();  // the shared tables are reused by the next row
     }
 }
 
@@ -944,9 +976,32 @@ static BuildArgs build_args(const K3Tables& t, uint32_t maxm)
     return b;
 }
 
-// build: potential lists and fold programs of the rows [g_lo, g_hi).  Two launches by row length:
-// the many short rows get a small shared-memory staging (more rows in flight per SM: the kernel is
-// bound by the latency of its dependent gathers), the few long ones the full-size staging.
+// build: potential lists and fold programs of the rows [g_lo, g_hi).  The rows are sorted into three length
+// classes; every class is built by persistent CTAs with its own staging size and width: the many short
+// rows get a small shared-memory staging and 64 threads (more rows in flight per SM: a row is a chain of
+// dependent gathers), the long ones more threads per row (their per-entry loops are the critical path).
+template <int NT, int MINB>
+static int launch_build_class(const K3Tables& t, uint32_t mm, uint32_t max_smem_m, int cls, uint32_t rows, int n_sm,
+                              cudaStream_t st, int* err)
+{
+    const BuildArgs b = build_args(t, mm);
+    const size_t smem = build_smem_bytes(mm);
+    cudaError_t e = cudaFuncSetAttribute(k3_build_kernel<NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)build_smem_bytes(max_smem_m));
+    int per_sm = 0;
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k3_build_kernel<NT, MINB>, NT, smem);
+    if (e != cudaSuccess || per_sm < 1) {
+        *err = (int)(e != cudaSuccess ? e : cudaErrorLaunchOutOfResources);
+        return -1;
+    }
+    uint32_t grid = (uint32_t)(n_sm * per_sm);
+    if (grid > rows) grid = rows;
+    k3_build_kernel<NT, MINB><<<grid, NT, smem, st>>>(b, t.cls + cls, t.cls + 16 + (size_t)cls * rows);
+    return 1;
+}
+
+size_t k3_class_words(uint32_t rows) { return 16 + 3 * (size_t)rows; }
+
 int launch_k3_build(const K3Tables& t, cudaStream_t st, int* err)
 {
     if (t.g_hi <= t.g_lo) return 0;
@@ -954,23 +1009,35 @@ int launch_k3_build(const K3Tables& t, cudaStream_t st, int* err)
     if (maxm > (uint32_t)DF_MAXM_CAP) maxm = DF_MAXM_CAP;
     maxm = (maxm + 3u) & ~3u;  // keeps the shared-memory arrays 16-byte aligned
     if (maxm < 4) maxm = 4;
-    int launches = 0;
-    const uint32_t small = maxm < (uint32_t)DF_SMALL ? maxm : (uint32_t)DF_SMALL;
-    for (int cls = 0; cls < 2; ++cls) {
-        if (cls == 1 && t.maxm <= small && t.L_sib == nullptr) break;  // no row is longer than the small staging
-        const uint32_t mm = cls == 0 ? small : maxm;
-        BuildArgs b = build_args(t, mm);
-        b.m_lo = cls == 0 ? 0u : small;
-        b.m_hi = cls == 0 ? small : 0xffffffffu;
-        const size_t smem = build_smem_bytes(mm);
-        cudaError_t e = cudaFuncSetAttribute(k3_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)build_smem_bytes(maxm));
-        if (e != cudaSuccess) {
-            *err = (int)e;
-            return -1;
-        }
-        k3_build_kernel<<<t.g_hi - t.g_lo, DF_THREADS, smem, st>>>(b);
-        ++launches;
+    static int b0 = -1, b1 = -1, n_sm = 0;
+    if (b0 < 0) {
+        const char* e0 = getenv("L3D_K3_B0");  // tuning hooks: the class bounds
+        const char* e1 = getenv("L3D_K3_B1");
+        b0 = e0 ? atoi(e0) : DF_SMALL;
+        b1 = e1 ? atoi(e1) : DF_MASKM;
+        b0 = (std::max(b0, 4) + 3) & ~3;
+        b1 = (std::max(b1, b0) + 3) & ~3;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const uint32_t rows = t.g_hi - t.g_lo;
+    const uint32_t m0 = std::min<uint32_t>(maxm, (uint32_t)b0), m1 = std::min<uint32_t>(maxm, (uint32_t)b1);
+    // a row longer than the staging of the last class is built in the global staging (t.L_sib)
+    const bool only0 = t.maxm <= m0 && t.L_sib == nullptr, only01 = t.maxm <= m1 && t.L_sib == nullptr;
+    cudaMemsetAsync(t.cls, 0, 16 * sizeof(uint32_t), st);
+    k3_classify_kernel<<<(rows + 255) / 256, 256, 0, st>>>(t.L_off, t.g_lo, t.g_hi, only0 ? 0xffffffffu : m0,
+                                                           only01 ? 0xffffffffu : m1, t.cls, t.cls + 16, t.prog_nh);
+    int launches = 1, r;
+    if ((r = launch_build_class<64, 16>(t, m0, maxm, 0, rows, n_sm, st, err)) < 0) return -1;
+    launches += r;
+    if (!only0) {
+        if ((r = launch_build_class<128, 8>(t, m1, maxm, 1, rows, n_sm, st, err)) < 0) return -1;
+        launches += r;
+    }
+    if (!only01) {
+        if ((r = launch_build_class<256, 4>(t, maxm, maxm, 2, rows, n_sm, st, err)) < 0) return -1;
+        launches += r;
     }
     return launches;
 }
