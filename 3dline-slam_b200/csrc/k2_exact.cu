@@ -751,15 +751,24 @@ __global__ void __launch_bounds__(K2_ROWS, 2) k2_front_kernel(
 
         // the chunk's mask words, the same word index on every lane (coalesced loads, ascending target order)
         const uint32_t w0 = cb >> 5, w_end = min(words, (cb + K2F_TCH) >> 5);
-        for (uint32_t w = w0; w < w_end; ++w) {
-            uint32_t bits = ncand ? mrow[(size_t)w * n_src] : 0u;
-            const uint32_t lbase = (w - w0) << 5;
-            while (bits) {
-                const uint32_t j = __ffs(bits) - 1;
-                bits &= bits - 1;
-                S.q[nq++][tid] = (unsigned short)(lbase + j);
+        // eight words are fetched at a time: one load per word with the walk of its bits hanging on it was a chain of
+        // exposed global-memory latencies (ncu: 4.6 warps per issue waiting on the long scoreboard)
+        for (uint32_t wg = w0; wg < w_end; wg += 8) {
+            uint32_t wb[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) wb[i] = (ncand && wg + i < w_end) ? mrow[(size_t)(wg + i) * n_src] : 0u;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if (wg + i >= w_end) break;  // warp-uniform
+                uint32_t bits = wb[i];
+                const uint32_t lbase = (wg + i - w0) << 5;
+                while (bits) {
+                    const uint32_t j = __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    S.q[nq++][tid] = (unsigned short)(lbase + j);
+                }
+                if (__any_sync(0xffffffffu, nq > 32u)) flush(cb);
             }
-            if (__any_sync(0xffffffffu, nq > 32u)) flush(cb);
         }
         flush(cb);
         __syncthreads();  // everyone is done with the staged tables before the next chunk overwrites them
