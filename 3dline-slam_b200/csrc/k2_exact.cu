@@ -621,7 +621,7 @@ __device__ __forceinline__ bool certify_candidate(const RowF32& R, const SegV32&
 // candidate whose upper bound is below T can be dropped at once (T only grows).  Survivors go to the row's
 // slots (row, target | unknown-depth flag) and (U); a second pass drops the ones below the final T, packs the
 // contenders to the front of the row and queues them for the exact kernel. ----
-static constexpr int K2F_TCH = 1024;
+static constexpr int K2F_TCH = 512;
 static constexpr int K2F_Q = 64;  // per-lane queue of chunk-local candidates (flushed when a lane passes 32)
 struct K2FSmem {
     SegV32 v32[K2F_TCH];
@@ -632,7 +632,7 @@ struct K2FSmem {
 
 // KT: size of the insertion network (the smallest of 4 / 8 / 10 / 12 / 16 that holds kNN; 0 = no pruning)
 template <int KT>
-__global__ void __launch_bounds__(K2_ROWS, 2) k2_front_kernel(
+__global__ void __launch_bounds__(K2_ROWS, 3) k2_front_kernel(
     const PairDev* __restrict__ pairs, const K1Cta* __restrict__ ctas, const uint32_t* __restrict__ mask,
     const uint32_t* __restrict__ cand_off, const SegV32* __restrict__ v32, const SegDesc* __restrict__ desc,
     const SegPlane* __restrict__ planes, const ViewDev* __restrict__ views, const RowEpi32* __restrict__ row_epi,

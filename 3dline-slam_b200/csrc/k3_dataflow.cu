@@ -78,7 +78,19 @@ __device__ __forceinline__ uint32_t pair_of_row(const PairDev* __restrict__ pair
     return lo;
 }
 
-// per (pair, source row): the row of every forward record, and how many records point at each
+// the pair of each of 32 ascending consecutive rows: lane 0 searches, the others walk on from its answer (a search
+// per thread was fourteen dependent loads, the whole cost of the two kernels below)
+__device__ __forceinline__ uint32_t pair_of_row_warp(const PairDev* __restrict__ pairs, uint32_t P, uint32_t row,
+                                                     uint32_t first_row)
+{
+    uint32_t p = 0;
+    if ((threadIdx.x & 31) == 0) p = pair_of_row(pairs, P, first_row);
+    p = __shfl_sync(0xffffffffu, p, 0);
+    while (p + 1 < P && pairs[p + 1].row_base <= row) ++p;
+    return p;
+}
+
+// per (pair, source row): the row and the pair of every forward record, and how many records point at each
 // (pair, target segment) = the capacity of its inverse-match slot
 __global__ void __launch_bounds__(256) k3_inv_capacity_kernel(const PairDev* __restrict__ pairs, uint32_t P,
                                                               uint32_t n_rows, const uint32_t* __restrict__ fwd_off,
@@ -89,10 +101,12 @@ __global__ void __launch_bounds__(256) k3_inv_capacity_kernel(const PairDev* __r
                                                               uint32_t v_hi)
 {
     const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t rc = min(row, n_rows - 1);
+    const uint32_t pidx = pair_of_row_warp(pairs, P, rc, min(row - (threadIdx.x & 31), n_rows - 1));
     if (row >= n_rows) return;
     const uint32_t n = fwd_cnt[row];
     if (!n) return;
-    const PairDev& D = pairs[pair_of_row(pairs, P, row)];
+    const PairDev& D = pairs[pidx];
     const uint32_t b = fwd_off[row];
     // inverse slots are only needed (and, in a sharded run, the records only present) for the
     // target views [v_lo, v_hi) this rank builds
@@ -170,10 +184,12 @@ __global__ void __launch_bounds__(256) k3_record_kernel(const PairDev* __restric
                                                         uint32_t v_lo, uint32_t v_hi)
 {
     const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+    // records are in row order: the rows of a warp's 32 records ascend
+    const uint32_t row = fwd_row[min(f, F - 1)];
+    const uint32_t pidx = pair_of_row_warp(pairs, P, row, __shfl_sync(0xffffffffu, row, 0));
     if (f >= F) return;
     fwd_score[f] = 0.0f;
-    const uint32_t row = fwd_row[f];
-    const PairDev& D = pairs[pair_of_row(pairs, P, row)];
+    const PairDev& D = pairs[pidx];
     if (!(D.emit_inverse && D.tgt_view >= v_lo && D.tgt_view < v_hi)) return;
     const uint32_t tr_row = D.tgt_base + fwd_rec[f].c;
     const uint32_t slot = atomicAdd(&inv_fill[tr_row], 1u);
@@ -327,8 +343,11 @@ __device__ __forceinline__ void build_row(const BuildArgs& a, const uint32_t g, 
     const SegRays sra = a.rays[g];
     const D3 Ca = ld3w(va.C), ra1 = ld3w(sra.r1), ra2 = ld3w(sra.r2);
     for (uint32_t e = tid; e < m; e += DF_THREADS) {
-        uint32_t q = 0;
-        while (bt.pos[q + 1] <= e) ++q;  // n_inc is small
+        uint32_t q = 0, qh = n_inc;  // the block of entry e: the last one that starts at or before it
+        while (qh - q > 1) {
+            const uint32_t mid = (q + qh) >> 1;
+            if (bt.pos[mid] <= e) q = mid; else qh = mid;
+        }
         const uint32_t j = e - bt.pos[q];
         const uint32_t b = bt.b[q], n = bt.n[q];
         uint32_t dst = e, f;
