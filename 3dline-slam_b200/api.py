@@ -49,6 +49,7 @@ class Params(C.Structure):
 class Counts(C.Structure):
     _fields_ = [("pair_tests", C.c_uint64), ("candidates", C.c_uint64), ("forward_matches", C.c_uint64),
                 ("scored_entries", C.c_uint64), ("sim_evals", C.c_uint64), ("filtered_entries", C.c_uint64),
+                ("pair_tests_run", C.c_uint64),
                 ("num_views", C.c_uint32), ("num_pairs", C.c_uint32), ("num_pairs_local", C.c_uint32),
                 ("num_entries", C.c_uint32), ("num_edges", C.c_uint32), ("num_local_ids", C.c_uint32),
                 ("num_clusters", C.c_uint32), ("gpu_launches", C.c_uint32)]

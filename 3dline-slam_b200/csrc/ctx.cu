@@ -608,6 +608,8 @@ int run_stage12_batches(l3d_ctx* ctx)
         CK(grow(ctx->d_row_pair, (size_t)max_rows + 1));
         CK(grow(ctx->d_row_T, (size_t)max_rows + 1));
         CK(ctx->d_k2ctr.ensure(8));
+        CK(ctx->d_k1_run.ensure(2));
+        CK(cudaMemsetAsync(ctx->d_k1_run.p, 0, 2 * sizeof(unsigned long long), st));
         if (!ctx->n_sm) {
             cudaDeviceProp prop;
             CK(cudaGetDeviceProperties(&prop, ctx->device));
@@ -632,7 +634,7 @@ int run_stage12_batches(l3d_ctx* ctx)
         ctx->cnt.gpu_launches +=
             launch_k1_pairtest(ctx->d_pairs.p, ctx->d_ctas.p + b.cta0, b.n_ctas, ctx->d_desc.p, ctx->d_row_epi.p,
                                ctx->d_row_key.p, ctx->d_perm.p, ctx->d_mask.p, ctx->d_cand_cnt.p, ctx->epi_overlap,
-                               ctx->prm.filter_mode, st);
+                               ctx->prm.filter_mode, ctx->d_k1_run.p, st);
         ctx->tm.end(ek, st);
         ctx->tm.ms[L3D_T_K1_LAUNCHES] += 1.0f;
         ctx->cnt.gpu_launches += launch_scan_u32(ctx->d_cand_cnt.p, ctx->d_cand_off.p, b.n_rows, ctx->d_scan.p,
@@ -679,6 +681,12 @@ int run_stage12_batches(l3d_ctx* ctx)
         ctx->tm.end(e2, st);
         rec_base += n_fin;
     }
+    ctx->cnt.pair_tests_run = 0;
+    if (P) {  // read with the per-pair totals' synchronisation (refresh_pair_totals)
+        CK(cudaMemcpyAsync(ctx->rb_at<unsigned long long>(l3d_ctx::RB_K1RUN), ctx->d_k1_run.p, sizeof(unsigned long long),
+                           cudaMemcpyDeviceToHost, st));
+        ctx->k1_run_pending = true;
+    }
     ctx->total_fwd = rec_base;
     ctx->local_fwd = rec_base;
     ctx->prog_all = nullptr;
@@ -720,6 +728,8 @@ int l3d_match_stage12(l3d_ctx* ctx, const l3d_params* params)
     CK(cudaStreamSynchronize(st));
     ctx->tm.collect();
     ctx->cnt.forward_matches = ctx->total_fwd;
+    if (ctx->k1_run_pending) ctx->cnt.pair_tests_run = *ctx->rb_at<unsigned long long>(l3d_ctx::RB_K1RUN);
+    ctx->k1_run_pending = false;
     ctx->stage = 1;
     return L3D_OK;
 }

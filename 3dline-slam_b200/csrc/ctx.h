@@ -237,7 +237,8 @@ struct l3d_ctx {
     size_t rb_cap = 0;            // reads back into the pageable fallback below
     unsigned char rb_fallback[4096] = {0};
     enum { RB_NCAND = 0, RB_NFIN = 8, RB_DEVMAX = 16, RB_SMALL = 32, RB_NENT = 64, RB_STATS = 128, RB_NEDGES = 512,
-           RB_NLOCAL = 520, RB_BIG = 4096 };
+           RB_NLOCAL = 520, RB_K1RUN = 528, RB_BIG = 4096 };
+    bool k1_run_pending = false;
     template <typename T>
     T* rb_at(size_t off) { return reinterpret_cast<T*>((rb ? rb : rb_fallback) + off); }
     bool rb_fits(size_t bytes) const { return rb && RB_BIG + bytes <= rb_cap; }
@@ -261,6 +262,7 @@ struct l3d_ctx {
     DevBuf<RowEpi32> d_row_epi_nat;  // the same in natural row order (staging of the row sort)
     DevBuf<float2> d_row_key;      // direction keys of the row's two lines (sorted row order)
     DevBuf<uint32_t> d_perm, d_iperm;  // sorted position -> natural row and back (batch-local)
+    DevBuf<unsigned long long> d_k1_run;  // pair tests K1 evaluated (l3d_counts::pair_tests_run)
     DevBuf<uint32_t> d_ncont, d_k2ctr;  // K2: contenders per batch row; {work items, fallback rows}
     DevBuf<uint2> d_fb_rows;       // K2: rows handed to the literal row kernel
     DevBuf<uint32_t> d_row_pair;   // K2: pair of every batch row

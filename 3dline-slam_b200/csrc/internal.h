@@ -205,6 +205,7 @@ int launch_k1_rowsort(const PairDev* pairs, const K1Cta* ctas, uint32_t n_ctas, 
                       uint32_t* iperm, cudaStream_t st);
 int launch_k1_pairtest(const PairDev* pairs, const K1Cta* ctas, uint32_t n_ctas, const SegDesc* desc,
                        const RowEpi32* epi_rho, const float2* key_rho, const uint32_t* perm, uint32_t* mask,
-                       uint32_t* cand_cnt, float thr, int filter_mode, cudaStream_t st);
+                       uint32_t* cand_cnt, float thr, int filter_mode, unsigned long long* tests_run,
+                       cudaStream_t st);
 
 }  // namespace l3d

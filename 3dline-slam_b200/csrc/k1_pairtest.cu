@@ -25,7 +25,6 @@ namespace l3d {
 
 static constexpr int K1_ROWS = 256;
 static constexpr int K1_TILE = 512;  // descriptors per stage (16 KB)
-static constexpr int K1_MAXUNROLL = 8;
 
 // one MUFU.RCP, <= 1 ulp (covered by the guard band).  The .ftz form skips the range fix-up code of
 // rcp.approx.f32 (six more instructions per reciprocal): a denormal denominator gives +-inf here,
@@ -102,7 +101,7 @@ __device__ __forceinline__ bool pair_candidate(const RowEpi& e, const float4 d0,
 static constexpr int KS_N = 4096;  // rows per sort chunk = 16 K1 tiles
 static constexpr int KS_THREADS = 512;
 
-__global__ void __launch_bounds__(KS_THREADS) k1_rowsort_kernel(const PairDev* __restrict__ pairs,
+__global__ void __launch_bounds__(KS_THREADS, 2) k1_rowsort_kernel(const PairDev* __restrict__ pairs,
                                                                  const K1Cta* __restrict__ ctas,
                                                                  const float4* __restrict__ segs,
                                                                  const float* __restrict__ view_xb,
@@ -276,7 +275,7 @@ __device__ __forceinline__ bool hull_skips(float Al, float Bl, float Cl, float A
 }
 
 // K1_UNROLL: independent tests in flight per lane
-template <int K1_UNROLL, bool STAGED>
+template <int K1_UNROLL>
 __global__ void __launch_bounds__(K1_ROWS) k1_pairtest_kernel(const PairDev* __restrict__ pairs,
                                                               const K1Cta* __restrict__ ctas,
                                                               const SegDesc* __restrict__ desc,
@@ -285,11 +284,11 @@ __global__ void __launch_bounds__(K1_ROWS) k1_pairtest_kernel(const PairDev* __r
                                                               const uint32_t* __restrict__ perm,
                                                               uint32_t* __restrict__ mask,
                                                               uint32_t* __restrict__ cand_cnt, float thr,
-                                                              int filter_mode, int hull_on)
+                                                              int filter_mode, int hull_on,
+                                                              unsigned long long* __restrict__ tests_run)
 {
-    __shared__ __align__(128) float4 tile[STAGED ? 2 : 1][STAGED ? K1_TILE * 2 : 1];
+    __shared__ __align__(128) float4 tile[2][K1_TILE * 2];
     __shared__ __align__(8) uint64_t bars[2];
-    __shared__ unsigned short wq[K1_ROWS / 32][K1_TILE + K1_MAXUNROLL];  // per warp: the targets of the tile it tests
 
     const K1Cta cta = ctas[blockIdx.x];
     const PairDev& P = pairs[cta.pair];
@@ -299,17 +298,15 @@ __global__ void __launch_bounds__(K1_ROWS) k1_pairtest_kernel(const PairDev* __r
     const uint32_t lane = threadIdx.x & 31;
     const SegDesc* __restrict__ tdesc = desc + P.tgt_off;
 
-    if (STAGED) {
-        if (threadIdx.x == 0) {
-            mbar_init(&bars[0], 1);
-            mbar_init(&bars[1], 1);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
-        __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    __syncthreads();
 
     const uint32_t ntiles = (n_tgt + K1_TILE - 1) / K1_TILE;
-    if (STAGED && threadIdx.x == 0 && ntiles > 0) {
+    if (threadIdx.x == 0 && ntiles > 0) {
         const uint32_t cnt = min((uint32_t)K1_TILE, n_tgt);
         mbar_expect_tx(&bars[0], cnt * 32u);
         tma_load_1d(&tile[0][0], tdesc, cnt * 32u, &bars[0]);
@@ -359,73 +356,66 @@ __global__ void __launch_bounds__(K1_ROWS) k1_pairtest_kernel(const PairDev* __r
                 Ch = __shfl_sync(0xffffffffu, hC, own_hi & 31u);
 
     uint32_t total = 0;
+    unsigned long long n_run = 0;  // targets this warp tested
     uint32_t* __restrict__ mrow = mask + P.mask_base + rho;
 
     for (uint32_t t = 0; t < ntiles; ++t) {
         const uint32_t buf = t & 1;
-        if (STAGED) {
-            if (threadIdx.x == 0 && t + 1 < ntiles) {
-                const uint32_t nb = buf ^ 1;
-                const uint32_t base = (t + 1) * K1_TILE;
-                const uint32_t cnt = min((uint32_t)K1_TILE, n_tgt - base);
-                mbar_expect_tx(&bars[nb], cnt * 32u);
-                tma_load_1d(&tile[nb][0], tdesc + base, cnt * 32u, &bars[nb]);
-            }
-            mbar_wait(&bars[buf], (t >> 1) & 1);
+        if (threadIdx.x == 0 && t + 1 < ntiles) {
+            const uint32_t nb = buf ^ 1;
+            const uint32_t base = (t + 1) * K1_TILE;
+            const uint32_t cnt = min((uint32_t)K1_TILE, n_tgt - base);
+            mbar_expect_tx(&bars[nb], cnt * 32u);
+            tma_load_1d(&tile[nb][0], tdesc + base, cnt * 32u, &bars[nb]);
         }
+        mbar_wait(&bars[buf], (t >> 1) & 1);
 
         const uint32_t base = t * K1_TILE;
         const uint32_t cnt = min((uint32_t)K1_TILE, n_tgt - base);
-        // not STAGED: the descriptors are read through L1 (every lane the same address in the tests); the warps of
-        // a CTA then never wait for each other
-        const float4* __restrict__ tl = STAGED ? tile[buf] : reinterpret_cast<const float4*>(tdesc + base);
+        const float4* __restrict__ tl = tile[buf];
         const uint32_t nwords = (cnt + 31) / 32;
-        // (1) which targets of the tile the warp has to test: lane j looks at target 32 w + j; the survivors go to
-        // the warp's queue in ascending order
-        unsigned short* __restrict__ q = wq[threadIdx.x >> 5];
-        uint32_t nq = 0;
         for (uint32_t w = 0; w < nwords; ++w) {  // warp-uniform
-            const uint32_t j = w * 32 + lane;
-            bool keep = j < cnt;
-            if (hull_ok && keep) keep = !hull_skips(Al, Bl, Cl, Ah, Bh, Ch, tl[2 * j], tl[2 * j + 1].x);
-            const uint32_t bal = __ballot_sync(0xffffffffu, keep);
-            if (keep) q[nq + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)j;
-            nq += __popc(bal);
-        }
-        // pad to a multiple of the unroll factor with copies of the last entry (a repeated test sets the same bit)
-        if (nq && lane < K1_UNROLL) q[nq + lane] = q[nq - 1];
-        __syncwarp();
-        // (2) the queued tests, K1_UNROLL independent ones per iteration; the words of the tile are written in
-        // order, all-zero words of skipped targets included
-        uint32_t cur = 0, bits = 0;
-        auto put = [&]() {
-            if (all_pass) bits = (cur * 32 + 32 <= cnt) ? 0xffffffffu : ((1u << (cnt - cur * 32)) - 1u);
+            const uint32_t j0 = w * 32;
+            const uint32_t nj = min(32u, cnt - j0);
+            const uint32_t full = (nj == 32) ? 0xffffffffu : ((1u << nj) - 1u);
+            const float4* __restrict__ tw = tl + 2 * j0;
+            // which of the word's 32 targets the warp has to test: lane j looks at target j0 + j.  The ballot is a
+            // warp-uniform value: the loop below, its bit positions and its shared-memory addresses run on the
+            // uniform datapath.  (A queue of survivors across the words of a tile, read back per test, cost 34
+            // instructions per test to put each result bit into its word -- the compiler could not know that the
+            // queued indices were uniform.)
+            uint32_t need = full;
+            if (hull_ok) {
+                bool skip = true;
+                if (lane < nj) skip = hull_skips(Al, Bl, Cl, Ah, Bh, Ch, tw[2 * lane], tw[2 * lane + 1].x);
+                need = __ballot_sync(0xffffffffu, !skip);
+            }
+            n_run += __popc(need);
+            uint32_t bits = 0;
+            while (need) {  // K1_UNROLL independent tests per iteration; a short tail repeats the last target
+                uint32_t jj[K1_UNROLL];
+                bool c[K1_UNROLL];
+#pragma unroll
+                for (int u = 0; u < K1_UNROLL; ++u) {
+                    jj[u] = (u == 0 || need) ? (uint32_t)__ffs(need) - 1u : jj[u > 0 ? u - 1 : 0];
+                    need &= need - 1u;
+                }
+#pragma unroll
+                for (int u = 0; u < K1_UNROLL; ++u) c[u] = pair_candidate(e, tw[2 * jj[u]], tw[2 * jj[u] + 1], thr, k2thr);
+#pragma unroll
+                for (int u = 0; u < K1_UNROLL; ++u) bits |= (c[u] ? 1u : 0u) << jj[u];
+            }
+            if (all_pass) bits = full;
             if (row_ok) {
-                mrow[(size_t)((base >> 5) + cur) * n_src] = bits;
+                mrow[(size_t)((base >> 5) + w) * n_src] = bits;
                 total += __popc(bits);
             }
-            bits = 0;
-            ++cur;
-        };
-        for (uint32_t k = 0; k < nq; k += K1_UNROLL) {
-            uint32_t jj[K1_UNROLL];
-            bool c[K1_UNROLL];
-#pragma unroll
-            for (int u = 0; u < K1_UNROLL; ++u) {
-                jj[u] = q[k + u];
-                c[u] = pair_candidate(e, tl[2 * jj[u]], tl[2 * jj[u] + 1], thr, k2thr);
-            }
-#pragma unroll
-            for (int u = 0; u < K1_UNROLL; ++u) {
-                while (cur < (jj[u] >> 5)) put();  // warp-uniform
-                bits |= (c[u] ? 1u : 0u) << (jj[u] & 31u);
-            }
         }
-        while (cur < nwords) put();
-        if (STAGED) __syncthreads();  // everyone is done with tile[buf] before it is refilled
-        else __syncwarp();            // ... with the warp's queue before it is refilled
+        __syncthreads();  // everyone is done with tile[buf] before it is refilled
     }
     if (row_ok) cand_cnt[lrow] = total;
+    const uint32_t live = __popc(__ballot_sync(0xffffffffu, row_ok));
+    if (lane == 0 && live) atomicAdd(tests_run, n_run * live);
 }
 
 int launch_k1_rowsort(const PairDev* pairs, const K1Cta* ctas, uint32_t n_ctas, const float4* segs,
@@ -447,7 +437,8 @@ int launch_k1_rowsort(const PairDev* pairs, const K1Cta* ctas, uint32_t n_ctas, 
 
 int launch_k1_pairtest(const PairDev* pairs, const K1Cta* ctas, uint32_t n_ctas, const SegDesc* desc,
                        const RowEpi32* epi_rho, const float2* key_rho, const uint32_t* perm, uint32_t* mask,
-                       uint32_t* cand_cnt, float thr, int filter_mode, cudaStream_t st)
+                       uint32_t* cand_cnt, float thr, int filter_mode, unsigned long long* tests_run,
+                       cudaStream_t st)
 {
     if (n_ctas == 0) return 0;
     static int hull_on = -1;
@@ -458,25 +449,14 @@ int launch_k1_pairtest(const PairDev* pairs, const K1Cta* ctas, uint32_t n_ctas,
     static int unroll = -1;
     if (unroll < 0) {
         const char* ev = getenv("L3D_K1_UNROLL");  // tuning hook
-        unroll = ev ? atoi(ev) : 8;
+        unroll = ev ? atoi(ev) : 2;
     }
-    static int staged = -1;
-    if (staged < 0) {
-        const char* ev = getenv("L3D_K1_STAGED");  // tuning hook: 1 = descriptors through shared memory (TMA tiles)
-        staged = ev ? atoi(ev) : 1;
-    }
-#define K1_LAUNCH(U, S) \
-    k1_pairtest_kernel<U, S><<<n_ctas, K1_ROWS, 0, st>>>(pairs, ctas, desc, epi_rho, key_rho, perm, mask, cand_cnt, thr, \
-                                                         filter_mode, hull_on)
-    if (staged) {
-        if (unroll >= 8) K1_LAUNCH(8, true);
-        else if (unroll >= 4) K1_LAUNCH(4, true);
-        else K1_LAUNCH(2, true);
-    } else {
-        if (unroll >= 8) K1_LAUNCH(8, false);
-        else if (unroll >= 4) K1_LAUNCH(4, false);
-        else K1_LAUNCH(2, false);
-    }
+#define K1_LAUNCH(U) \
+    k1_pairtest_kernel<U><<<n_ctas, K1_ROWS, 0, st>>>(pairs, ctas, desc, epi_rho, key_rho, perm, mask, cand_cnt, thr, \
+                                                      filter_mode, hull_on, tests_run)
+    if (unroll >= 4) K1_LAUNCH(4);
+    else if (unroll >= 2) K1_LAUNCH(2);
+    else K1_LAUNCH(1);
 #undef K1_LAUNCH
     return 1;
 }

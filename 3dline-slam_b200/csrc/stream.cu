@@ -328,6 +328,8 @@ int stream_match_images(l3d_ctx* ctx, const l3d_params* params)
     rc = refresh_pair_totals(ctx);
     if (rc) return rc;
     ctx->cnt.forward_matches = ctx->total_fwd;
+    if (ctx->k1_run_pending) ctx->cnt.pair_tests_run = *ctx->rb_at<unsigned long long>(l3d_ctx::RB_K1RUN);
+    ctx->k1_run_pending = false;
     const size_t F = (size_t)ctx->total_fwd;
     CK(ensure_roomy(ctx->d_fwd_score, F + 1, kListFloor));
     CK(cudaMemsetAsync(ctx->d_fwd_score.p, 0, (F + 1) * sizeof(float), st));

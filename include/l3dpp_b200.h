@@ -93,6 +93,8 @@ typedef struct {
     uint64_t scored_entries;  /* sum of list lengths at scoring time */
     uint64_t sim_evals;       /* sibling pairs visited by the scoring kernel */
     uint64_t filtered_entries;
+    uint64_t pair_tests_run;  /* of pair_tests, the ones the FP32 kernel evaluated; the others were skipped with their
+                                 whole warp of source rows because the target lay outside the warp's epipolar wedge */
     uint32_t num_views, num_pairs, num_pairs_local;
     uint32_t num_entries, num_edges, num_local_ids, num_clusters;
     uint32_t gpu_launches;    /* kernels launched since the last l3d_reset_counters */
