@@ -834,7 +834,7 @@ __device__ __forceinline__ unsigned long long exact_contender(
     return ~0ull;  // not a match
 }
 
-__global__ void __launch_bounds__(256) k2b_exact_kernel(
+__global__ void __launch_bounds__(256, 4) k2b_exact_kernel(
     const PairDev* __restrict__ pairs, const float4* __restrict__ segs, const SegRays* __restrict__ rays,
     const SegPlane* __restrict__ planes, const ViewDev* __restrict__ views, const uint32_t* __restrict__ work,
     const uint2* __restrict__ cand_rc, const float* __restrict__ cand_u, const uint32_t* __restrict__ row_pair,
@@ -948,7 +948,7 @@ __global__ void __launch_bounds__(K2_ROWS) k2_rank_kernel(
 // ---- depths (src/line3D.cc:1365-1390) and orientation test (checkMatchOrientation, src/line3D.cc:962-1014)
 // of one popped match per thread; a match that fails the test keeps its slot, flagged, and is skipped by the
 // compaction ----
-__global__ void __launch_bounds__(256) k2_finish_kernel(
+__global__ void __launch_bounds__(256, 4) k2_finish_kernel(
     const PairDev* __restrict__ pairs, const SegRays* __restrict__ rays, const double* __restrict__ midray,
     const SegPlane* __restrict__ planes, const ViewDev* __restrict__ views, const uint32_t* __restrict__ fwork,
     const uint2* __restrict__ cand_rc, const uint32_t* __restrict__ row_pair, const unsigned long long* __restrict__ pop_key,
