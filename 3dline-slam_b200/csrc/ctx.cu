@@ -5,6 +5,7 @@
 // scoring phases, K4, and the (unchanged) clustering on the host.  No CPU fallback: every
 // compute entry point needs a CUDA device.
 #include <fstream>
+#include <thread>
 
 #include "ctx.h"
 
@@ -191,11 +192,22 @@ int l3d_scene_commit(l3d_ctx* ctx)
     }
     float4* hseg = (float4*)ctx->pinned;
     uint32_t* seg_view = (uint32_t*)(hseg + std::max<size_t>(S, 1));
-    for (uint32_t v = 0; v < V; ++v) {
-        HostView& hv = ctx->views[v];
-        memcpy(hseg + hv.seg_off, hv.ext_segs ? hv.ext_segs : hv.segs.data(), (size_t)hv.v.num_segs * sizeof(float4));
-        hv.ext_segs = nullptr;
-        std::fill(seg_view + hv.seg_off, seg_view + hv.seg_off + hv.v.num_segs, v);
+    auto stage_views = [&](uint32_t v0, uint32_t v1) {
+        for (uint32_t v = v0; v < v1; ++v) {
+            HostView& hv = ctx->views[v];
+            memcpy(hseg + hv.seg_off, hv.ext_segs ? hv.ext_segs : hv.segs.data(), (size_t)hv.v.num_segs * sizeof(float4));
+            hv.ext_segs = nullptr;
+            std::fill(seg_view + hv.seg_off, seg_view + hv.seg_off + hv.v.num_segs, v);
+        }
+    };
+    if (S >= (1u << 19) && V >= 8) {  // tens of MB: one core copies at ~10 GB/s, the H2D link takes five times that
+        const uint32_t T = 4;
+        std::vector<std::thread> th;
+        for (uint32_t t = 1; t < T; ++t) th.emplace_back(stage_views, V * t / T, V * (t + 1) / T);
+        stage_views(0, V / T);
+        for (auto& x : th) x.join();
+    } else {
+        stage_views(0, V);
     }
     CK(ctx->d_segs.ensure(S));
     CK(ctx->d_seg_view.ensure(S));
@@ -1775,19 +1787,11 @@ int l3d_get_local2global(l3d_ctx* ctx, uint32_t* cam_seg, uint32_t cap)
     if (cap < n) return fail(L3D_ERR_CAPACITY, "need %u ids", n);
     if (!n) return L3D_OK;
     CK(cudaSetDevice(ctx->device));
-    std::vector<uint32_t> g(n);
-    CK(cudaMemcpyAsync(g.data(), ctx->d_l2g.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    // (camera id, segment) of every id on the device, one copy into the caller's buffer
+    CK(ctx->d_l2g_cs.ensure(n));
+    ctx->cnt.gpu_launches += launch_l2g_camseg(ctx->d_l2g.p, n, ctx->d_seg_view.p, ctx->d_views.p, ctx->d_l2g_cs.p, ctx->stream);
+    CK(cudaMemcpyAsync(cam_seg, ctx->d_l2g_cs.p, (size_t)n * sizeof(uint2), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    for (uint32_t i = 0; i < n; ++i) {
-        // global segment -> (cam, seg): views are sorted by seg_off
-        uint32_t lo = 0, hi = (uint32_t)ctx->views.size();
-        while (hi - lo > 1) {
-            const uint32_t mid = (lo + hi) / 2;
-            if (ctx->views[mid].seg_off <= g[i]) lo = mid; else hi = mid;
-        }
-        cam_seg[2 * i] = ctx->views[lo].v.cam_id;
-        cam_seg[2 * i + 1] = g[i] - ctx->views[lo].seg_off;
-    }
     return L3D_OK;
 }
 

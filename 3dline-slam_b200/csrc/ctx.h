@@ -262,6 +262,7 @@ struct l3d_ctx {
     DevBuf<RowEpi32> d_row_epi_nat;  // the same in natural row order (staging of the row sort)
     DevBuf<float2> d_row_key;      // direction keys of the row's two lines (sorted row order)
     DevBuf<uint32_t> d_perm, d_iperm;  // sorted position -> natural row and back (batch-local)
+    DevBuf<uint2> d_l2g_cs;  // local2global_ as (camera id, segment) pairs (l3d_get_local2global)
     DevBuf<unsigned long long> d_k1_run;  // pair tests K1 evaluated (l3d_counts::pair_tests_run)
     DevBuf<uint32_t> d_ncont, d_k2ctr;  // K2: contenders per batch row; {work items, fallback rows}
     DevBuf<uint2> d_fb_rows;       // K2: rows handed to the literal row kernel

@@ -198,6 +198,9 @@ int launch_k6_lines3d(uint32_t n_clusters, const uint32_t* cl_off, const uint32_
                       unsigned char* okflag, uint32_t* camtab, uint32_t* out_n, uint32_t* out_ref, double* out_seg,
                       cudaStream_t st);
 
+int launch_l2g_camseg(const uint32_t* l2g, uint32_t n, const uint32_t* seg_view, const ViewDev* views, uint2* out,
+                      cudaStream_t st);
+
 // K1: rows of every pair sorted by the direction of their epipolar lines (k1_pairtest.cu); epi_rho / key_rho /
 // the mask are in sorted ("rho") order, perm[rho] = natural row, iperm[natural row] = rho (batch-local indices)
 int launch_k1_rowsort(const PairDev* pairs, const K1Cta* ctas, uint32_t n_ctas, const float4* segs,

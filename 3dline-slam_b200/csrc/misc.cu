@@ -177,6 +177,26 @@ __global__ void __launch_bounds__(256) fwd_bgather_kernel(const uint32_t* __rest
     FwdRec* dst = out + boff[row - row_lo];
     for (uint32_t e = 0; e < n; ++e) dst[e] = src[e];
 }
+// ---- local2global_ as (camera id, segment) pairs (l3d_get_local2global): the host used to do a binary search
+// over the views per id after the copy ----
+__global__ void __launch_bounds__(256) l2g_camseg_kernel(const uint32_t* __restrict__ l2g, uint32_t n,
+                                                         const uint32_t* __restrict__ seg_view,
+                                                         const ViewDev* __restrict__ views, uint2* __restrict__ out)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t g = l2g[i];
+    const ViewDev& v = views[seg_view[g]];
+    out[i] = make_uint2(v.cam_id, g - v.seg_off);
+}
+int launch_l2g_camseg(const uint32_t* l2g, uint32_t n, const uint32_t* seg_view, const ViewDev* views, uint2* out,
+                      cudaStream_t st)
+{
+    if (!n) return 0;
+    l2g_camseg_kernel<<<(n + 255) / 256, 256, 0, st>>>(l2g, n, seg_view, views, out);
+    return 1;
+}
+
 // ---- FORWARD records (abi.cu): own rows into the canonical layout; pair blocks for the all-to-all ----
 // copies the rows' records: src_off / dst_off index the two stores, n from cnt (0 = skip)
 __global__ void __launch_bounds__(256) fwd_move_kernel(const uint32_t* __restrict__ cnt, uint32_t row_lo, uint32_t row_hi,
