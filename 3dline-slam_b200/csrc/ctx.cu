@@ -581,6 +581,16 @@ int set_params(l3d_ctx* ctx, const l3d_params* params)
     return L3D_OK;
 }
 
+// Wait for the stream by polling: the step reads a count back after K1 and after K2 of every batch, and a blocking
+// cudaStreamSynchronize puts the thread to sleep -- the wake-up (tens of microseconds) is GPU idle time each time
+static cudaError_t spin_sync(cudaStream_t st)
+{
+    cudaError_t e;
+    while ((e = cudaStreamQuery(st)) == cudaErrorNotReady) {
+    }
+    return e;
+}
+
 // per-segment tables (K0), then K1 + K2 over the planned batches -> forward store
 int run_stage12_batches(l3d_ctx* ctx)
 {
@@ -663,7 +673,7 @@ int run_stage12_batches(l3d_ctx* ctx)
         ctx->tm.end(e1, st);
         CK(cudaMemcpyAsync(ctx->rb_at<uint32_t>(l3d_ctx::RB_NCAND), ctx->d_cand_off.p + b.n_rows, sizeof(uint32_t),
                            cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
+        CK(spin_sync(st));
         const uint32_t n_cand = *ctx->rb_at<uint32_t>(l3d_ctx::RB_NCAND);
         ctx->cnt.candidates += n_cand;
         // K2
@@ -690,7 +700,7 @@ int run_stage12_batches(l3d_ctx* ctx)
             launch_scan_u32(ctx->d_fin_cnt.p, ctx->d_fin_off.p, b.n_rows, ctx->d_scan.p, ctx->d_scan.cap, st);
         CK(cudaMemcpyAsync(ctx->rb_at<uint32_t>(l3d_ctx::RB_NFIN), ctx->d_fin_off.p + b.n_rows, sizeof(uint32_t),
                            cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
+        CK(spin_sync(st));
         const uint32_t n_fin = *ctx->rb_at<uint32_t>(l3d_ctx::RB_NFIN);
         if ((uint64_t)rec_base + n_fin > 0xfffffff0ull) return fail(L3D_ERR_CAPACITY, "too many forward matches");
         CK(grow(ctx->d_fwd_rec, (size_t)rec_base + n_fin, rec_base, st));
