@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(KS_THREADS, 2) k1_rowsort_kernel(const PairDev
     float2* skey = reinterpret_cast<float2*>(ks_raw + sizeof(unsigned long long) * KS_N);
     __shared__ float red_lo[KS_THREADS / 32], red_hi[KS_THREADS / 32], red_w[KS_THREADS / 32];
     __shared__ uint32_t red_n[KS_THREADS / 32];
-    __shared__ double s_g[2];
+    __shared__ double s_g[3];
     const K1Cta cta = ctas[blockIdx.x];
     if (cta.tile % (KS_N / K1_ROWS)) return;  // one sort CTA per chunk: the K1 CTA list is reused as its grid
     const PairDev& P = pairs[cta.pair];
@@ -145,9 +145,23 @@ __global__ void __launch_bounds__(KS_THREADS, 2) k1_rowsort_kernel(const PairDev
         if (dn > 0.0 && dn < 1e300) { dx /= dn; dy /= dn; } else { dx = 1.0; dy = 0.0; }
         s_g[0] = -dy;
         s_g[1] = dx;
+        // The wedge test needs the epipolar lines of the pair to pass through ONE point, i.e. a rank-2 F: true to
+        // 1e-16 for a matrix made from two cameras in double, not guaranteed for a matrix handed in through
+        // match_lines_GPU.  If the third column is not at right angles to the epipole to 1e-9, the rows keep their
+        // order and get NaN keys: no warp of this pair skips anything.
+        double worst = 0.0;
+        const double nb = sqrt(bn);
+        for (int a = 0; a < 3; ++a) {
+            const double* u = cols[a];
+            const double nu = sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
+            const double r = fabs(u[0] * best[0] + u[1] * best[1] + u[2] * best[2]);
+            if (nu > 0.0 && nb > 0.0) worst = fmax(worst, r / (nu * nb));
+        }
+        s_g[2] = (bn > 0.0 && worst <= 1e-9) ? 1.0 : 0.0;
     }
     __syncthreads();
     const double gx = s_g[0], gy = s_g[1];
+    const bool concurrent = s_g[2] != 0.0;
     const float xb = view_xb[P.tgt_view];
     const float pinf = __int_as_float(0x7f800000);
     float clo = pinf, chi = -pinf, wsum = 0.0f;
@@ -176,7 +190,7 @@ __global__ void __launch_bounds__(KS_THREADS, 2) k1_rowsort_kernel(const PairDev
         re.nmin = (float)fmin(n1, n2);
         epi_nat[lbase + i] = re;
         float2 k = make_float2((float)t1, (float)t2);
-        if (degenerate) k = make_float2(__int_as_float(0x7fc00000), __int_as_float(0x7fc00000));
+        if (degenerate || !concurrent) k = make_float2(__int_as_float(0x7fc00000), __int_as_float(0x7fc00000));
         skey[i] = k;
         if (!degenerate) {
             const float c = 0.5f * (k.x + k.y);

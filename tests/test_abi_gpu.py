@@ -37,6 +37,25 @@ def test_match_lines_equals_matchingCPU(api, oracle, scene_mod, knn):
     assert got2.tobytes() == got.tobytes()
 
 
+@pytest.mark.parametrize("eps", [1e-3, 0.05])
+def test_match_lines_with_a_full_rank_F(api, oracle, scene_mod, eps):
+    """A matrix that is NOT a fundamental matrix (rank 3: its "epipolar lines" do not meet in one point) is legal
+    input to match_lines_GPU.  K1's wedge test assumes concurrent lines, so it must switch itself off for such a
+    pair: the pre-filtered run and the all-pairs-exact run agree."""
+    sc, va, vb = _two_view_scene(scene_mod, n_seg=400)
+    o = oracle.OracleLine3D(sc.max_image_width, False)
+    o.load_scene(sc)
+    F, Ms, Mt, Cs, Ct = o.match_only(va.cam_id, vb.cam_id, 0.25, 10)
+    rng = np.random.default_rng(5)
+    F3 = np.asarray(F, dtype=np.float64).reshape(3, 3) + eps * np.abs(F).max() * rng.standard_normal((3, 3))
+    assert abs(np.linalg.det(F3)) > 1e-9 * np.abs(F3).max() ** 3
+    ctx = api.Context()
+    a, off_a = ctx.match_lines(va.segs, vb.segs, F3, Ms, Mt, Cs, Ct, va.cam_id, vb.cam_id, 0.25, 10, sc.max_image_width)
+    b, off_b = ctx.match_lines(va.segs, vb.segs, F3, Ms, Mt, Cs, Ct, va.cam_id, vb.cam_id, 0.25, 10, sc.max_image_width,
+                               filter_mode=1)
+    assert (off_a == off_b).all() and a.tobytes() == b.tobytes()
+
+
 def test_match_lines_empty_and_capacity(api, scene_mod):
     sc, va, vb = _two_view_scene(scene_mod)
     ctx = api.Context()
