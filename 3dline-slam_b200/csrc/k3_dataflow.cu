@@ -838,7 +838,7 @@ __device__ __forceinline__ ListRec make_list_rec(const FinishArgs& a, uint32_t i
 
 static constexpr int FIN_WARPS = 8;
 
-__global__ void __launch_bounds__(FIN_WARPS * 32) k3_finish_kernel(const FinishArgs a)
+__global__ void __launch_bounds__(FIN_WARPS * 32, 6) k3_finish_kernel(const FinishArgs a)
 {
     __shared__ uint32_t blkcnt[FIN_WARPS][DF_MAXINC];
     // the rows of a CTA reserve their filtered entries and add their counters with ONE atomic per CTA and
