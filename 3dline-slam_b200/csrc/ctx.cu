@@ -467,12 +467,7 @@ int plan_pairs(l3d_ctx* ctx)
         const HostView& vs = ctx->views[hp.src];
         const HostView& vt = ctx->views[hp.tgt];
         PairDev& d = ctx->pairs_h[p];
-        if (ctx->raw_mode) {
-            memcpy(d.F, ctx->F_override, sizeof(d.F));
-        } else {
-            const hg::M3 F = hg::fundamental(vs.cam, vt.cam);
-            memcpy(d.F, F.m, sizeof(d.F));
-        }
+        if (ctx->raw_mode) memcpy(d.F, ctx->F_override, sizeof(d.F));  // else: below, on several threads
         d.src_view = hp.src;
         d.tgt_view = hp.tgt;
         d.src_off = vs.seg_off;
@@ -490,6 +485,25 @@ int plan_pairs(l3d_ctx* ctx)
         if (hp.local) {
             ctx->cnt.pair_tests += (uint64_t)d.n_src * d.n_tgt;
             ctx->cnt.num_pairs_local++;
+        }
+    }
+    if (!ctx->raw_mode) {
+        // fundamental matrices (src/line3D.cc:1082-1104): five 3x3 products and two inverses per pair; 10^4 pairs
+        // of config 4 are a millisecond and more of a step on one core, with the GPU waiting
+        auto fill_F = [&](uint32_t p0, uint32_t p1) {
+            for (uint32_t p = p0; p < p1; ++p) {
+                const hg::M3 F = hg::fundamental(ctx->views[ctx->pairs[p].src].cam, ctx->views[ctx->pairs[p].tgt].cam);
+                memcpy(ctx->pairs_h[p].F, F.m, sizeof(ctx->pairs_h[p].F));
+            }
+        };
+        if (P >= 2048) {
+            const uint32_t T = 4;
+            std::vector<std::thread> th;
+            for (uint32_t t = 1; t < T; ++t) th.emplace_back(fill_F, (uint32_t)((uint64_t)P * t / T), (uint32_t)((uint64_t)P * (t + 1) / T));
+            fill_F(0, (uint32_t)((uint64_t)P / T));
+            for (auto& x : th) x.join();
+        } else {
+            fill_F(0, P);
         }
     }
     if (row > 0xfffffff0ull || trow > 0xfffffff0ull)
