@@ -365,9 +365,9 @@ def bench_stream(args, scene_mod, emit=True):
 
 
 # SASS instruction counts of K1 (profiles/r2_k1_sass.md): per test the kernel RUNS (two tests per loop iteration,
-# 89 instructions), and per 32-target word of every source row (the wedge test of the warp, ballot, mask store)
-K1_ISSUED_PER_RUN_TEST = 44.5
-K1_ISSUED_PER_WORD = 67.0
+# 90 instructions), and per 32-target word of every source row (the wedge test of the warp, ballot, mask store)
+K1_ISSUED_PER_RUN_TEST = 45.0
+K1_ISSUED_PER_WORD = 74.0
 K2_FLOP_PER_CANDIDATE = 330.0  # SURVEY.md section 8(d) / DESIGN.md section 4.2: FP64 flop per K1 candidate
 
 
@@ -585,7 +585,7 @@ def build_rooflines(env, res, scene):
         "frac_is": "ALGORITHMIC flop (114 per segment-pair test, SURVEY 8d, over ALL tests of the launch) / measured FFMA peak.  "
                    "It exceeds 1 because most tests are decided without being evaluated: the rows of a pair are sorted by "
                    "epipolar direction and a target outside the wedge of a warp's 32 rows is skipped for the warp "
-                   "(tests_run_frac of the tests are evaluated), and an evaluated test needs 44.5 instructions, not 114 flop.  "
+                   "(tests_run_frac of the tests are evaluated), and an evaluated test needs 45 instructions, not 114 flop.  "
                    "issue_slot_frac is the hardware-side figure: instructions the kernel issues / lane-issue capacity",
         "tests_run_frac": k1_run / k1_tests if k1_tests else None,
         "issue_slot_frac": k1_issued / k1_s / (n_sm * 128 * sm_max * 1e6),
