@@ -50,6 +50,10 @@ def _gather_segments(env, scene_mod, V, N, nbrs, n_world):
 
 def bench_city(args, env, bench_mod):
     torch, api, sharding, dist = env.torch, env.api, env.sharding, env.dist
+    # memory, not time, is the limit at this scale: the 512 MB mask batches the published run used
+    # (the library default of 2 GB would put four times the K2 scratch, ~ 48 GB, on every rank); read by the
+    # library when it plans its first batch
+    os.environ.setdefault("L3D_MASK_WORDS_LOG2", "27")
     scene_mod = importlib.import_module("3dline-slam_b200.scene")
     full = args.workload == "c5"
     V = 5000 if full else int(os.environ.get("L3D_C5_VIEWS", "1000"))
