@@ -56,3 +56,29 @@ def test_header_is_plain_c():
     hdr = os.path.join(root, "include", "l3dpp_b200.h")
     subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", hdr])
     subprocess.check_call(["g++", "-std=c++11", "-Wall", "-Werror", "-fsyntax-only", "-x", "c++", hdr])
+
+
+def test_ctypes_mirrors_have_the_c_layout(api, tmp_path):
+    """The ctypes structures of api.py against sizeof / offsetof of the C header, compiled with gcc: a field added on
+    one side only (l3d_counts.pair_tests_run was the last one) shifts everything behind it."""
+    import ctypes
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "layout.c"
+    src.write_text('''#include <stdio.h>
+#include <stddef.h>
+#include "l3dpp_b200.h"
+int main(void) {
+    printf("%zu %zu %zu\\n", sizeof(l3d_view), sizeof(l3d_params), sizeof(l3d_counts));
+    printf("%zu %zu %zu %zu\\n", offsetof(l3d_counts, pair_tests_run), offsetof(l3d_counts, num_views),
+           offsetof(l3d_counts, gpu_launches), offsetof(l3d_params, shard_world));
+    return 0;
+}
+''')
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)])
+    out = subprocess.check_output([str(exe)], text=True).split()
+    sizes, offs = [int(x) for x in out[:3]], [int(x) for x in out[3:]]
+    assert sizes == [ctypes.sizeof(api.View), ctypes.sizeof(api.Params), ctypes.sizeof(api.Counts)]
+    assert offs == [api.Counts.pair_tests_run.offset, api.Counts.num_views.offset, api.Counts.gpu_launches.offset,
+                    api.Params.shard_world.offset]
