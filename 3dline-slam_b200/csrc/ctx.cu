@@ -492,6 +492,7 @@ int plan_pairs(l3d_ctx* ctx)
         // of config 4 are a millisecond and more of a step on one core, with the GPU waiting
         auto fill_F = [&](uint32_t p0, uint32_t p1) {
             for (uint32_t p = p0; p < p1; ++p) {
+                if (!ctx->pairs[p].local) continue;  // only K1 / K2 read F, and only for this rank's pairs
                 const hg::M3 F = hg::fundamental(ctx->views[ctx->pairs[p].src].cam, ctx->views[ctx->pairs[p].tgt].cam);
                 memcpy(ctx->pairs_h[p].F, F.m, sizeof(ctx->pairs_h[p].F));
             }
