@@ -10,12 +10,18 @@
 // A pair is REJECTED only if it fails by more than the rounding-error bound D of the FP32
 // evaluation (derivation in DESIGN.md section 4.1); everything else is a candidate and is
 // re-evaluated in the reference's double sequence.  Surviving pairs are written as one bit per
-// test, layout [pair][word = c/32][row r] so that both this kernel's stores and K2's loads are
-// coalesced; per-row candidate counts come out of the same pass (popc).
+// test, layout [pair][word = c/32][rho] (rho = position of the source row in the sorted order below) so that both
+// this kernel's stores and K2's loads are coalesced; per-row candidate counts come out of the same pass (popc).
 //
-// One CTA = 256 source rows of one pair; target descriptors (32 B each) are streamed through
-// shared memory in 512-entry tiles with TMA bulk copies (cp.async.bulk) on a two-stage
-// mbarrier pipeline; every lane reads the same descriptor (shared-memory broadcast).
+// Two kernels per batch:
+//   k1_rowsort_kernel   sorts the rows of every pair by the direction of their epipolar lines, so that the 32 rows
+//                       of a warp span a narrow wedge through the epipole;
+//   k1_pairtest_kernel  one CTA = 256 consecutive rows of the sorted order of one pair; target descriptors (32 B
+//                       each) are streamed through shared memory in 512-entry tiles with TMA bulk copies
+//                       (cp.async.bulk) on a two-stage mbarrier pipeline; per 32 targets the warp first tests the
+//                       targets against its wedge (one target per lane) and then evaluates only the ones that reach
+//                       into it (every lane the same descriptor: shared-memory broadcast).  On BASELINE config 4 one
+//                       test in six is evaluated.
 #include <cstdlib>
 
 #include "internal.h"
