@@ -12,7 +12,7 @@
 
 namespace l3d {
 
-__global__ void __launch_bounds__(256) k0_prep_kernel(const float4* __restrict__ segs,
+__global__ void __launch_bounds__(256, 5) k0_prep_kernel(const float4* __restrict__ segs,
                                                       const uint32_t* __restrict__ seg_view,
                                                       const ViewDev* __restrict__ views, uint32_t S, double W,
                                                       SegDesc* __restrict__ desc, SegRays* __restrict__ rays,
