@@ -94,9 +94,10 @@ __device__ __forceinline__ bool pair_candidate(const RowEpi& e, const float4 d0,
 //   * per row, in double: the two normalised epipolar lines (src/line3D.cc:1113-1121), with their signs chosen
 //     so that the normals of all lines of the pair lie in one half plane (n.g >= 0, g = the direction at right
 //     angles to the one from the epipole towards the image: no line that crosses the image comes near n.g = 0
-//     unless the epipole is inside the image); the direction key t = n.g' (the sine of the angle to g), which
-//     is monotone in the direction over that half plane and, for a distant epipole, a small number whose float
-//     image keeps its relative precision;
+//     unless the epipole is inside the image); the direction key: t = n.g' (the sine of the angle to g), monotone
+//     in the direction over that half plane, for an epipole near the image; the signed distance of the middle of
+//     the image to the line (= R t, R the distance of the epipole) for a far one, which also orders the
+//     PARALLEL epipolar lines of a rectified stereo pair, where every angle is the same;
 //   * sort key: width class (log2 of the row's wedge against the mean, 8 classes) above the quantised wedge
 //     centre -- wide rows would otherwise widen the hull of every warp they land in; the centres run forwards in
 //     even classes and backwards in odd ones;
@@ -122,7 +123,7 @@ __global__ void __launch_bounds__(KS_THREADS, 2) k1_rowsort_kernel(const PairDev
     float2* skey = reinterpret_cast<float2*>(ks_raw + sizeof(unsigned long long) * KS_N);
     __shared__ float red_lo[KS_THREADS / 32], red_hi[KS_THREADS / 32], red_w[KS_THREADS / 32];
     __shared__ uint32_t red_n[KS_THREADS / 32];
-    __shared__ double s_g[3];
+    __shared__ double s_g[6];
     const K1Cta cta = ctas[blockIdx.x];
     if (cta.tile % (KS_N / K1_ROWS)) return;  // one sort CTA per chunk: the K1 CTA list is reused as its grid
     const PairDev& P = pairs[cta.pair];
@@ -148,9 +149,18 @@ __global__ void __launch_bounds__(KS_THREADS, 2) k1_rowsort_kernel(const PairDev
         const double cx = 0.25 * (double)view_xb[P.tgt_view], cy = cx;  // xb bounds |x| + |y|
         double dx = cx * best[2] - best[0], dy = cy * best[2] - best[1];
         const double dn = sqrt(dx * dx + dy * dy);
+        // distance of the epipole from the middle of the image, in pixels: |c e_w - e_xy| / |e_w|
+        const double R = dn / fabs(best[2]);
         if (dn > 0.0 && dn < 1e300) { dx /= dn; dy /= dn; } else { dx = 1.0; dy = 0.0; }
         s_g[0] = -dy;
         s_g[1] = dx;
+        // which key orders the lines of the pencil: near epipole -- the sine of the angle to g; far epipole (also at
+        // infinity: parallel epipolar lines, a rectified stereo pair) -- the signed distance of the middle of the
+        // image to the line, which is R times that sine and stays exact when the angles no longer tell the lines
+        // apart.  (The distance alone would fail the other way round: an epipole at the middle of the image.)
+        s_g[3] = (R <= 4.0 * (double)view_xb[P.tgt_view]) ? 0.0 : 1.0;  // NaN / inf: far
+        s_g[4] = cx;
+        s_g[5] = cy;
         // The wedge test needs the epipolar lines of the pair to pass through ONE point, i.e. a rank-2 F: true to
         // 1e-16 for a matrix made from two cameras in double, not guaranteed for a matrix handed in through
         // match_lines_GPU.  If the third column is not at right angles to the epipole to 1e-9, the rows keep their
@@ -167,7 +177,8 @@ __global__ void __launch_bounds__(KS_THREADS, 2) k1_rowsort_kernel(const PairDev
     }
     __syncthreads();
     const double gx = s_g[0], gy = s_g[1];
-    const bool concurrent = s_g[2] != 0.0;
+    const bool concurrent = s_g[2] != 0.0, far = s_g[3] != 0.0;
+    const double kcx = s_g[4], kcy = s_g[5];
     const float xb = view_xb[P.tgt_view];
     const float pinf = __int_as_float(0x7f800000);
     float clo = pinf, chi = -pinf, wsum = 0.0f;
@@ -183,7 +194,9 @@ __global__ void __launch_bounds__(KS_THREADS, 2) k1_rowsort_kernel(const PairDev
         // s = -N / D is unchanged by the sign of a line: choose it so that n.g >= 0
         if (a1 * gx + b1 * gy < 0.0) { a1 = -a1; b1 = -b1; c1 = -c1; }
         if (a2 * gx + b2 * gy < 0.0) { a2 = -a2; b2 = -b2; c2 = -c2; }
-        const double t1 = b1 * gx - a1 * gy, t2 = b2 * gx - a2 * gy;  // n.g', g' = (-gy, gx)
+        // direction keys: n.g' with g' = (-gy, gx), or the distance of the image centre (see above)
+        const double t1 = far ? a1 * kcx + b1 * kcy + c1 : b1 * gx - a1 * gy;
+        const double t2 = far ? a2 * kcx + b2 * kcy + c2 : b2 * gx - a2 * gy;
         RowEpi32 re;
         re.A1 = (float)a1; re.B1 = (float)b1; re.C1 = (float)c1;
         re.A2 = (float)a2; re.B2 = (float)b2; re.C2 = (float)c2;
@@ -364,10 +377,10 @@ __global__ void __launch_bounds__(K1_ROWS) k1_pairtest_kernel(const PairDev* __r
     }
     const uint32_t own_lo = __ffs(__ballot_sync(0xffffffffu, row_ok && klo == wlo)) - 1;
     const uint32_t own_hi = __ffs(__ballot_sync(0xffffffffu, row_ok && khi == whi)) - 1;
-    // no skipping unless every row of the warp has finite keys and the wedge is well below a half turn (keys are
-    // sines of the angle to g: a span of 1 is at most 90 degrees)
+    // no skipping unless every row of the warp has finite keys.  (All normals of a pair lie in one half plane, so
+    // the lines between the two hull lines are non-negative combinations of them whatever the width of the wedge.)
     const bool hull_ok = hull_on && !__any_sync(0xffffffffu, row_ok && (all_pass || !(khi - klo >= 0.0f))) &&
-                         (whi - wlo < 1.0f) && own_lo < 32u && own_hi < 32u;
+                         own_lo < 32u && own_hi < 32u;
     const float lA = first_lo ? e.A1 : e.A2, lB = first_lo ? e.B1 : e.B2, lC = first_lo ? e.C1 : e.C2;
     const float hA = first_lo ? e.A2 : e.A1, hB = first_lo ? e.B2 : e.B1, hC = first_lo ? e.C2 : e.C1;
     const float Al = __shfl_sync(0xffffffffu, lA, own_lo & 31u), Bl = __shfl_sync(0xffffffffu, lB, own_lo & 31u),

@@ -62,6 +62,22 @@ def test_forward_motion_epipole_inside_the_image(api, oracle, scene_mod):
     orc.close()
 
 
+def test_rectified_stereo_parallel_epipolar_lines(api, oracle, scene_mod):
+    """Cameras side by side with one common rotation: the epipole of every pair is a point at infinity and all its
+    epipolar lines are parallel -- the angle of a line no longer orders the rows, the sort key has to be the
+    distance of the line from the middle of the image (an angle-only key made every warp take the wedge of its
+    first row for its hull and skip the matches of the others)."""
+    from test_wedge_rule import rectified_scene
+    sc = rectified_scene(scene_mod, n_views=5, n_seg=700)
+    l3 = api.run_scene(sc)
+    orc = oracle.run_scene(sc)
+    sizes = compare_full(l3, orc, sc, check_scored=False)
+    c = l3.counts()
+    assert c["forward_matches"] > 1000 and c["pair_tests_run"] < c["pair_tests"]
+    assert sizes["pairs"] >= 5
+    orc.close()
+
+
 _HOOK_SCRIPT = r"""
 import importlib, sys
 sys.path.insert(0, %r)

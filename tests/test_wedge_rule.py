@@ -27,11 +27,18 @@ def _rule(F, S, T, xb, order, dtype):
     d = np.array([cx * e[2] - e[0], cx * e[2] - e[1]])
     d = d / np.linalg.norm(d)
     g = np.array([-d[1], d[0]])
+    with np.errstate(divide="ignore"):
+        R = np.linalg.norm([cx * e[2] - e[0], cx * e[2] - e[1]]) / abs(e[2])
+    far = not (R <= 4.0 * xb)
     l1, l2 = _lines(F, S[:, 0:2]), _lines(F, S[:, 2:4])
     l1 = l1 * np.where(l1[:, :2] @ g < 0, -1.0, 1.0)[:, None]
     l2 = l2 * np.where(l2[:, :2] @ g < 0, -1.0, 1.0)[:, None]
-    k1 = (l1[:, 1] * g[0] - l1[:, 0] * g[1]).astype(np.float32)
-    k2 = (l2[:, 1] * g[0] - l2[:, 0] * g[1]).astype(np.float32)
+    if far:    # distance of the middle of the image to the line: orders parallel lines too
+        k1 = (l1[:, 0] * cx + l1[:, 1] * cx + l1[:, 2]).astype(np.float32)
+        k2 = (l2[:, 0] * cx + l2[:, 1] * cx + l2[:, 2]).astype(np.float32)
+    else:      # sine of the angle to g
+        k1 = (l1[:, 1] * g[0] - l1[:, 0] * g[1]).astype(np.float32)
+        k2 = (l2[:, 1] * g[0] - l2[:, 0] * g[1]).astype(np.float32)
     lo_line = np.where((k1 <= k2)[:, None], l1, l2).astype(dtype)
     hi_line = np.where((k1 <= k2)[:, None], l2, l1).astype(dtype)
     klo, khi = np.minimum(k1, k2), np.maximum(k1, k2)
@@ -44,8 +51,6 @@ def _rule(F, S, T, xb, order, dtype):
     for w in range(0, N, 32):
         idx = order[w:w + 32]
         a, b = idx[np.argmin(klo[idx])], idx[np.argmax(khi[idx])]
-        if not (khi[b] - klo[a] < 1.0):
-            continue
         Hl, Hh = lo_line[a], hi_line[b]
         Nl = Hl[0] * q1[:, 0] + Hl[1] * q1[:, 1] + Hl[2]
         Dl = Hl[0] * u_[:, 0] + Hl[1] * u_[:, 1]
@@ -115,6 +120,32 @@ def test_wedge_rule_never_skips_a_match_c4_shape(oracle, scene_mod):
     sc = scene_mod.make_scene("c4", n_views=4, n_seg=640, nbrs=3)
     n, m = _check_pair(oracle, sc, sc.views[0], sc.views[1])
     assert n > 0.5 * 4 * 640 * 640 * 0.5 and m > 0
+
+
+def rectified_scene(scene_mod, n_views=4, n_seg=400):
+    """cameras side by side with one common rotation: every pair is a rectified stereo pair, its epipole a point
+    at infinity, its epipolar lines parallel"""
+    sc = scene_mod.make_scene("c2", n_views=n_views, n_seg=n_seg, nbrs=2)
+    rng = np.random.Generator(np.random.PCG64(77))
+    P1, P2 = scene_mod._world_segments(rng, 600, np.array([-5.0, -5.0, 0.0]), np.array([5.0, 5.0, 4.0]), 1.0)
+    for i, v in enumerate(sc.views):
+        c = np.array([-1.0 + 0.25 * i, -6.0, 1.6])
+        R = scene_mod.look_at(c, c + np.array([0.0, 1.0, 0.0]))
+        t = -R @ c
+        segs, med = scene_mod._make_view_segments(rng, P1, P2, v.K, R, t, v.width, v.height, n_seg, 0.5, 15.0, 40.0)
+        v.R, v.t, v.segs, v.median_depth = R, t, segs, med
+    return sc
+
+
+def test_wedge_rule_rectified_stereo(oracle, scene_mod):
+    """parallel epipolar lines: the angle key cannot tell them apart, the distance key must"""
+    sc = rectified_scene(scene_mod)
+    tot = matches = 0
+    for a, b in ((0, 1), (2, 1), (0, 3)):
+        n, m = _check_pair(oracle, sc, sc.views[a], sc.views[b])
+        tot += n
+        matches += m
+    assert tot > 0 and matches > 100
 
 
 def test_wedge_rule_forward_motion(oracle, scene_mod):
