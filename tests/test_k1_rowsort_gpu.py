@@ -78,6 +78,19 @@ def test_rectified_stereo_parallel_epipolar_lines(api, oracle, scene_mod):
     orc.close()
 
 
+@pytest.mark.parametrize("seed", [0, 1, 2, 3, 6, 7])
+def test_random_two_view_geometries(api, oracle, scene_mod, seed):
+    """epipole at the image centre / far away / at infinity / oblique, small and large rotations (the scenes of
+    tests/test_wedge_rule.py, 900 segments per view so that several warps per class exist)"""
+    from test_wedge_rule import random_two_view_scene
+    sc = random_two_view_scene(scene_mod, seed, n_seg=900)
+    l3 = api.run_scene(sc)
+    orc = oracle.run_scene(sc)
+    compare_full(l3, orc, sc, check_scored=False)
+    assert l3.counts()["forward_matches"] > 0
+    orc.close()
+
+
 _HOOK_SCRIPT = r"""
 import importlib, sys
 sys.path.insert(0, %r)

@@ -159,13 +159,12 @@ def test_wedge_rule_forward_motion(oracle, scene_mod):
         _check_pair(oracle, sc, sc.views[a], sc.views[b])
 
 
-@pytest.mark.parametrize("seed", range(8))
-def test_wedge_rule_random_two_view_geometries(oracle, scene_mod, seed):
-    """Random relative poses around the cases that stress the sort key: translation along the optical axis (epipole
-    at the image centre), sideways (epipole far away or at infinity), oblique, with small and large rotations.  The
-    segments of both views come from one random 3-D scene, so real matches exist."""
+def random_two_view_scene(scene_mod, seed, n_seg=300):
+    """Two views of one random 3-D scene; the relative pose cycles through the cases that stress the sort key:
+    translation along the optical axis (epipole at the image centre), sideways (far away or at infinity), vertical,
+    oblique, with small and large rotations."""
     rng = np.random.Generator(np.random.PCG64(1000 + seed))
-    sc = scene_mod.make_scene("c2", n_views=2, n_seg=300, nbrs=1)
+    sc = scene_mod.make_scene("c2", n_views=2, n_seg=n_seg, nbrs=1)
     P1, P2 = scene_mod._world_segments(rng, 500, np.array([-4.0, -2.0, 0.0]), np.array([4.0, 6.0, 3.5]), 1.0)
     direction = [np.array([0.0, 1.0, 0.0]), np.array([1.0, 0.0, 0.0]), np.array([0.0, 0.0, 1.0]),
                  rng.standard_normal(3)][seed % 4]
@@ -177,9 +176,15 @@ def test_wedge_rule_random_two_view_geometries(oracle, scene_mod, seed):
         tgt = c + np.array([math.sin(i * yaw), math.cos(i * yaw), 0.03 * i * (seed % 3)])
         R = scene_mod.look_at(c, tgt)
         t = -R @ c
-        segs, med = scene_mod._make_view_segments(rng, P1, P2, v.K, R, t, v.width, v.height, 300, 0.5, 15.0, 40.0)
+        segs, med = scene_mod._make_view_segments(rng, P1, P2, v.K, R, t, v.width, v.height, n_seg, 0.5, 15.0, 40.0)
         v.R, v.t, v.segs, v.median_depth = R, t, segs, med
         v.neighbors = [sc.views[1 - i].cam_id]
+    return sc
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_wedge_rule_random_two_view_geometries(oracle, scene_mod, seed):
+    sc = random_two_view_scene(scene_mod, seed)
     n, m = _check_pair(oracle, sc, sc.views[0], sc.views[1])
     n2, m2 = _check_pair(oracle, sc, sc.views[1], sc.views[0])
     assert m + m2 > 0
